@@ -1,0 +1,194 @@
+// Host-side SoA packer; see packer.h.
+#include "packer.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+struct side
+{
+	// bundle_base fields the record loop needs (rnacore/bundle_base.h:31-36)
+	int32_t tid = -1;
+	int32_t rpos = 0;
+	bool spliced = false;
+	int32_t last_pos = 0, last_rpos = 0;
+	std::vector<int64_t> recs;          // record indices admitted so far
+	std::vector<uint8_t> strand;
+	void clear() { tid = -1; rpos = 0; spliced = false; recs.clear(); strand.clear(); }
+};
+
+struct packer
+{
+	std::vector<int64_t> hit_off{0};
+	std::vector<int32_t> b_tid, b_sample;
+	std::vector<uint8_t> b_side;
+	std::vector<int32_t> pos, rpos, mpos, isize;
+	std::vector<uint16_t> flag;
+	std::vector<uint8_t> strand, xs;
+	std::vector<uint64_t> qid;
+	std::vector<uint32_t> cigar_off{0};
+	std::vector<uint32_t> cigar;
+	int64_t seen = 0;
+};
+
+// hit::set_strand (rnacore/hit.cc:152-185)
+inline char strand_of(uint16_t flag, int libtype)
+{
+	char s = '.';
+	bool paired = (flag & 0x1) != 0, rev = (flag & 0x10) != 0, r1 = (flag & 0x40) != 0, r2 = (flag & 0x80) != 0;
+	if(libtype == AGPU_FR_FIRST && paired)
+	{
+		if(!rev && r1 && !r2) s = '-';
+		if(rev && r1 && !r2) s = '+';
+		if(!rev && !r1 && r2) s = '+';
+		if(rev && !r1 && r2) s = '-';
+	}
+	if(libtype == AGPU_FR_SECOND && paired)
+	{
+		if(!rev && r1 && !r2) s = '+';
+		if(rev && r1 && !r2) s = '-';
+		if(!rev && !r1 && r2) s = '-';
+		if(rev && !r1 && r2) s = '+';
+	}
+	if(libtype == AGPU_FR_FIRST && !paired) s = rev ? '+' : '-';
+	if(libtype == AGPU_FR_SECOND && !paired) s = rev ? '-' : '+';
+	return s;
+}
+
+inline bool has_splice(const uint32_t *c, uint32_t n)
+{
+	for(uint32_t k = 0; k < n; k++) if((c[k] & 0xf) == 3) return true;      // hit::contain_splices, rnacore/hit.cc:67-75
+	return false;
+}
+
+inline bool has_inner_splice(const uint32_t *c, uint32_t n)
+{
+	for(uint32_t k = 1; k + 1 < n; k++) if((c[k] & 0xf) == 3) return true;  // hit::extract_splices, rnacore/hit.cc:91-92
+	return false;
+}
+
+// bundle_base::add_hit (rnacore/bundle_base.cc:73-104)
+void admit(side &s, const packer_records &r, int64_t i, char strand)
+{
+	if(!s.recs.empty() && s.last_pos == r.pos[i] && s.last_rpos == r.rpos[i]) return;
+	s.recs.push_back(i);
+	s.strand.push_back((uint8_t)strand);
+	s.last_pos = r.pos[i];
+	s.last_rpos = r.rpos[i];
+	int32_t p = r.rpos[i];
+	if(r.mpos[i] > r.rpos[i] && r.mpos[i] <= r.rpos[i] + 500000) p = r.mpos[i];
+	if(p > s.rpos) s.rpos = p;
+	if(s.tid == -1) s.tid = r.tid[i];
+	if(has_inner_splice(r.cigar + r.cigar_off[i], r.cigar_off[i + 1] - r.cigar_off[i])) s.spliced = true;
+}
+
+// generator::generate (meta/generator.cc:203-227)
+void flush(packer &pk, side &s, const packer_records &r, const packer_params &p, int32_t sample, int which)
+{
+	if(s.tid < 0) return;
+	if(p.skip_single_exon_transcripts && !s.spliced) return;
+	for(size_t k = 0; k < s.recs.size(); k++)
+	{
+		int64_t i = s.recs[k];
+		pk.pos.push_back(r.pos[i]); pk.rpos.push_back(r.rpos[i]); pk.mpos.push_back(r.mpos[i]); pk.isize.push_back(r.isize[i]);
+		pk.flag.push_back(r.flag[i]); pk.strand.push_back(s.strand[k]); pk.xs.push_back(r.xs[i]); pk.qid.push_back(r.qid[i]);
+		pk.cigar.insert(pk.cigar.end(), r.cigar + r.cigar_off[i], r.cigar + r.cigar_off[i + 1]);
+		pk.cigar_off.push_back((uint32_t)pk.cigar.size());
+	}
+	pk.hit_off.push_back((int64_t)pk.pos.size());
+	pk.b_tid.push_back(s.tid);
+	pk.b_sample.push_back(sample);
+	pk.b_side.push_back((uint8_t)which);
+}
+
+} // namespace
+
+extern "C" {
+
+void packer_default_params(packer_params *p)
+{
+	p->library_type = AGPU_FR_FIRST;
+	p->min_mapping_quality = 1;
+	p->max_num_cigar = 10000;
+	p->max_read_span = 500000;
+	p->min_bundle_gap = 200;
+	p->use_second_alignment = 1;
+	p->skip_single_exon_transcripts = 1;
+}
+
+void *packer_create(void) { return new packer; }
+void packer_destroy(void *pk) { delete (packer*)pk; }
+int64_t packer_records_seen(void *pk) { return ((packer*)pk)->seen; }
+const uint8_t *packer_bundle_side(void *pk) { return ((packer*)pk)->b_side.data(); }
+
+int packer_add_sample(void *pkp, const packer_records *rp, const packer_params *pp, int32_t sample)
+{
+	packer &pk = *(packer*)pkp;
+	const packer_records &r = *rp;
+	const packer_params &p = *pp;
+	side bb1, bb2;
+	int32_t pre_lpos = -1, pre_rpos = -1;
+	for(int64_t i = 0; i < r.n; i++)
+	{
+		pk.seen++;
+		uint16_t fl = r.flag[i];
+		uint32_t nc = r.cigar_off[i + 1] - r.cigar_off[i];
+		// meta/generator.cc:87-97
+		if((fl & 0x4) >= 1) continue;
+		if((fl & 0x100) >= 1 && !p.use_second_alignment) continue;
+		if((int64_t)nc > (int64_t)p.max_num_cigar) continue;
+		if((int32_t)r.mapq[i] < p.min_mapping_quality) continue;
+		if(nc < 1) continue;
+		if(std::fabs((double)r.pos[i] - (double)r.rpos[i]) >= p.max_read_span) continue;
+		if(((fl & 0x8) <= 0) && std::fabs((double)r.pos[i] - (double)r.mpos[i]) >= p.max_read_span) continue;
+		if(r.pos[i] == pre_lpos && r.rpos[i] == pre_rpos) continue;
+		pre_lpos = r.pos[i];
+		pre_rpos = r.rpos[i];
+
+		char xs = (char)r.xs[i];
+		char st = strand_of(fl, p.library_type);
+
+		// meta/generator.cc:107-135: close bundles left behind by more than min_bundle_gap
+		if(!bb1.recs.empty() && (r.tid[i] != bb1.tid || r.pos[i] > bb1.rpos + p.min_bundle_gap)) { flush(pk, bb1, r, p, sample, 0); bb1.clear(); }
+		if(!bb2.recs.empty() && (r.tid[i] != bb2.tid || r.pos[i] > bb2.rpos + p.min_bundle_gap)) { flush(pk, bb2, r, p, sample, 1); bb2.clear(); }
+
+		// meta/generator.cc:155-179: strand routing
+		if(p.library_type != AGPU_UNSTRANDED)
+		{
+			if(st == '+' && xs == '-') continue;
+			if(st == '-' && xs == '+') continue;
+			if(st == '.' && xs != '.') st = xs;
+			if(st == '+') admit(bb1, r, i, st);
+			if(st == '-') admit(bb2, r, i, st);
+		}
+		else
+		{
+			if(xs == '+') admit(bb1, r, i, st);
+			if(xs == '-') admit(bb2, r, i, st);
+			if(xs == '.' && !has_splice(r.cigar + r.cigar_off[i], nc)) { admit(bb1, r, i, st); admit(bb2, r, i, st); }
+		}
+	}
+	flush(pk, bb1, r, p, sample, 0);
+	flush(pk, bb2, r, p, sample, 1);
+	return 0;
+}
+
+int packer_view(void *pkp, agpu_batch_in *out)
+{
+	packer &pk = *(packer*)pkp;
+	out->n_bundles = (int32_t)pk.b_tid.size();
+	out->n_hits = (int64_t)pk.pos.size();
+	out->n_cigar = (int64_t)pk.cigar.size();
+	out->bundle_hit_off = pk.hit_off.data();
+	out->bundle_tid = pk.b_tid.data();
+	out->bundle_sample = pk.b_sample.data();
+	out->pos = pk.pos.data(); out->rpos = pk.rpos.data(); out->mpos = pk.mpos.data(); out->isize = pk.isize.data();
+	out->flag = pk.flag.data(); out->strand = pk.strand.data(); out->xs = pk.xs.data(); out->qid = pk.qid.data();
+	out->cigar_off = pk.cigar_off.data(); out->cigar = pk.cigar.data();
+	return 0;
+}
+
+}

@@ -1,0 +1,53 @@
+// Host-side SoA packer: the record loop of generator::resolve (meta/generator.cc:77-201) with
+// bundle_base::add_hit's admission rules (rnacore/bundle_base.cc:73-104), emitting packed
+// bundles in the layout of agpu_batch_in (include/aletsch_gpu.h) instead of bundle_base objects.
+#ifndef ALETSCH_B200_HOST_PACKER_H
+#define ALETSCH_B200_HOST_PACKER_H
+
+#include <stdint.h>
+#include "../../include/aletsch_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// what the record loop reads from `parameters` (util/parameters.cc:53-62) and sample_profile
+typedef struct packer_params
+{
+	int32_t library_type;
+	int32_t min_mapping_quality;         // 1
+	int32_t max_num_cigar;               // 10000
+	int32_t max_read_span;               // 500000
+	int32_t min_bundle_gap;              // 200
+	int32_t use_second_alignment;        // 1
+	int32_t skip_single_exon_transcripts;// 1
+} packer_params;
+
+// coordinate-sorted decoded records of one sample (what htslib hands the reference per record)
+typedef struct packer_records
+{
+	int64_t n;
+	const int32_t *tid, *pos, *rpos, *mpos, *isize;
+	const uint16_t *flag;
+	const uint8_t *mapq;
+	const uint8_t *xs;
+	const uint64_t *qid;
+	const uint32_t *cigar_off;
+	const uint32_t *cigar;
+} packer_records;
+
+void packer_default_params(packer_params *p);
+void *packer_create(void);
+void packer_destroy(void *pk);
+// run the record loop over one sample and append its bundles to the batch under construction
+int packer_add_sample(void *pk, const packer_records *r, const packer_params *p, int32_t sample);
+// view of everything appended so far (pointers stay valid until the next add / destroy)
+int packer_view(void *pk, agpu_batch_in *out);
+int64_t packer_records_seen(void *pk);
+// extra per-bundle info for tests: 0 = bb1 ('+' side), 1 = bb2 ('-' side)
+const uint8_t *packer_bundle_side(void *pk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,225 @@
+"""ctypes bindings of libaletsch_host.so: synthetic record generator (host/synth.h) and the
+SoA packer (host/packer.h, the record loop of meta/generator.cc:77-201)."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SYNTH_PAIRED, SYNTH_SINGLE, SYNTH_LONG = 0, 1, 2
+UNSTRANDED, FR_FIRST, FR_SECOND = 0, 1, 2
+
+
+class SynthConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("mode", C.c_int32), ("n_chrom", C.c_int32), ("chrom_len", C.c_int32),
+                ("gene_spacing", C.c_int32), ("read_len", C.c_int32), ("min_exons", C.c_int32), ("max_exons", C.c_int32),
+                ("expressed_fraction", C.c_double), ("secondary_rate", C.c_double), ("indel_rate", C.c_double),
+                ("clip_rate", C.c_double), ("odd_rate", C.c_double)]
+
+
+class SynthRecords(C.Structure):
+    _fields_ = [("n", C.c_int64), ("tid", C.POINTER(C.c_int32)), ("pos", C.POINTER(C.c_int32)), ("rpos", C.POINTER(C.c_int32)),
+                ("mpos", C.POINTER(C.c_int32)), ("isize", C.POINTER(C.c_int32)), ("flag", C.POINTER(C.c_uint16)),
+                ("mapq", C.POINTER(C.c_uint8)), ("xs", C.POINTER(C.c_uint8)), ("qid", C.POINTER(C.c_uint64)),
+                ("cigar_off", C.POINTER(C.c_uint32)), ("cigar", C.POINTER(C.c_uint32)), ("n_cigar", C.c_int64)]
+
+
+class PackerParams(C.Structure):
+    _fields_ = [("library_type", C.c_int32), ("min_mapping_quality", C.c_int32), ("max_num_cigar", C.c_int32),
+                ("max_read_span", C.c_int32), ("min_bundle_gap", C.c_int32), ("use_second_alignment", C.c_int32),
+                ("skip_single_exon_transcripts", C.c_int32)]
+
+
+class PackerRecords(C.Structure):
+    _fields_ = [("n", C.c_int64), ("tid", C.c_void_p), ("pos", C.c_void_p), ("rpos", C.c_void_p), ("mpos", C.c_void_p),
+                ("isize", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p), ("xs", C.c_void_p), ("qid", C.c_void_p),
+                ("cigar_off", C.c_void_p), ("cigar", C.c_void_p)]
+
+
+class BatchIn(C.Structure):
+    """agpu_batch_in (include/aletsch_gpu.h)."""
+    _fields_ = [("n_bundles", C.c_int32), ("n_hits", C.c_int64), ("n_cigar", C.c_int64),
+                ("bundle_hit_off", C.c_void_p), ("bundle_tid", C.c_void_p), ("bundle_sample", C.c_void_p),
+                ("pos", C.c_void_p), ("rpos", C.c_void_p), ("mpos", C.c_void_p), ("isize", C.c_void_p),
+                ("flag", C.c_void_p), ("strand", C.c_void_p), ("xs", C.c_void_p), ("qid", C.c_void_p),
+                ("cigar_off", C.c_void_p), ("cigar", C.c_void_p)]
+
+
+HIT_FIELDS = [("pos", np.int32), ("rpos", np.int32), ("mpos", np.int32), ("isize", np.int32), ("flag", np.uint16),
+              ("strand", np.uint8), ("xs", np.uint8), ("qid", np.uint64)]
+
+
+def build():
+    """compile libaletsch_host.so in-tree (g++)."""
+    import subprocess
+    src = [os.path.join(_HERE, "host", f) for f in ("synth.cc", "packer.cc")]
+    out = os.path.join(_HERE, "libaletsch_host.so")
+    deps = src + [os.path.join(_HERE, "host", f) for f in ("synth.h", "packer.h")] + \
+        [os.path.join(_HERE, "..", "include", "aletsch_gpu.h")]
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", out] + src + ["-lpthread"])
+    return out
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libaletsch_host.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.synth_create.restype = C.c_void_p
+        L.synth_create.argtypes = [C.POINTER(SynthConfig)]
+        L.synth_destroy.argtypes = [C.c_void_p]
+        L.synth_num_genes.argtypes = [C.c_void_p]
+        L.synth_generate.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.POINTER(SynthRecords)]
+        L.synth_default_config.argtypes = [C.POINTER(SynthConfig), C.c_int]
+        L.synth_records_free.argtypes = [C.POINTER(SynthRecords)]
+        L.packer_create.restype = C.c_void_p
+        L.packer_destroy.argtypes = [C.c_void_p]
+        L.packer_add_sample.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
+        L.packer_view.argtypes = [C.c_void_p, C.POINTER(BatchIn)]
+        L.packer_default_params.argtypes = [C.POINTER(PackerParams)]
+        L.packer_records_seen.restype = C.c_int64
+        L.packer_records_seen.argtypes = [C.c_void_p]
+        L.packer_bundle_side.restype = C.POINTER(C.c_uint8)
+        L.packer_bundle_side.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,)).copy()
+
+
+def default_config(mode=SYNTH_PAIRED, **kw):
+    c = SynthConfig()
+    lib().synth_default_config(C.byref(c), mode)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+class Synth:
+    """synthetic transcriptome + read simulator "synth-v1"."""
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self._h = lib().synth_create(C.byref(cfg))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().synth_destroy(self._h)
+            self._h = None
+
+    @property
+    def num_genes(self):
+        return lib().synth_num_genes(self._h)
+
+    def sample(self, sample, templates, threads=8):
+        """coordinate-sorted records of one sample as a dict of numpy arrays."""
+        r = SynthRecords()
+        rc = lib().synth_generate(self._h, sample, templates, threads, C.byref(r))
+        if rc != 0:
+            raise RuntimeError("synth_generate failed")
+        n, nc = r.n, r.n_cigar
+        out = {"n": n,
+               "tid": _np(r.tid, n, np.int32), "pos": _np(r.pos, n, np.int32), "rpos": _np(r.rpos, n, np.int32),
+               "mpos": _np(r.mpos, n, np.int32), "isize": _np(r.isize, n, np.int32), "flag": _np(r.flag, n, np.uint16),
+               "mapq": _np(r.mapq, n, np.uint8), "xs": _np(r.xs, n, np.uint8), "qid": _np(r.qid, n, np.uint64),
+               "cigar_off": _np(r.cigar_off, n + 1, np.uint32), "cigar": _np(r.cigar, nc, np.uint32)}
+        lib().synth_records_free(C.byref(r))
+        return out
+
+
+def default_packer_params(library_type=FR_FIRST, **kw):
+    p = PackerParams()
+    lib().packer_default_params(C.byref(p))
+    p.library_type = library_type
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class PackedBatch:
+    """host copy of an agpu_batch_in: NB packed bundles (numpy arrays) + ctypes view."""
+
+    def __init__(self, arrays):
+        self.a = arrays
+        self.n_bundles = len(arrays["bundle_tid"])
+        self.n_hits = len(arrays["pos"])
+        self.n_cigar = len(arrays["cigar"])
+
+    def view(self):
+        b = BatchIn()
+        b.n_bundles, b.n_hits, b.n_cigar = self.n_bundles, self.n_hits, self.n_cigar
+        for k in ("bundle_hit_off", "bundle_tid", "bundle_sample", "pos", "rpos", "mpos", "isize", "flag", "strand", "xs",
+                  "qid", "cigar_off", "cigar"):
+            setattr(b, k, self.a[k].ctypes.data)
+        return b
+
+    def bundle(self, k):
+        """arrays of bundle k alone (cigar offsets rebased)."""
+        a = self.a
+        h0, h1 = int(a["bundle_hit_off"][k]), int(a["bundle_hit_off"][k + 1])
+        c0, c1 = int(a["cigar_off"][h0]), int(a["cigar_off"][h1])
+        out = {f: np.ascontiguousarray(a[f][h0:h1]) for f, _ in HIT_FIELDS}
+        out["cigar_off"] = np.ascontiguousarray(a["cigar_off"][h0:h1 + 1] - np.uint32(c0))
+        out["cigar"] = np.ascontiguousarray(a["cigar"][c0:c1])
+        out["tid"] = int(a["bundle_tid"][k])
+        out["sample"] = int(a["bundle_sample"][k])
+        return out
+
+    def select(self, ks):
+        """new PackedBatch holding bundles ks in that order."""
+        a = self.a
+        parts = [self.bundle(k) for k in ks]
+        arr = {f: (np.concatenate([p[f] for p in parts]) if parts else np.zeros(0, dt)) for f, dt in HIT_FIELDS}
+        hit_off = np.zeros(len(parts) + 1, np.int64)
+        cig_off = [np.zeros(1, np.uint32)]
+        cbase = 0
+        for i, p in enumerate(parts):
+            hit_off[i + 1] = hit_off[i] + len(p["pos"])
+            cig_off.append(p["cigar_off"][1:] + np.uint32(cbase))
+            cbase += len(p["cigar"])
+        arr["bundle_hit_off"] = hit_off
+        arr["cigar_off"] = np.concatenate(cig_off).astype(np.uint32)
+        arr["cigar"] = np.concatenate([p["cigar"] for p in parts]).astype(np.uint32) if parts else np.zeros(0, np.uint32)
+        arr["bundle_tid"] = np.array([p["tid"] for p in parts], np.int32)
+        arr["bundle_sample"] = np.array([p["sample"] for p in parts], np.int32)
+        arr["bundle_side"] = np.array([a["bundle_side"][k] for k in ks], np.uint8) if "bundle_side" in a else np.zeros(len(parts), np.uint8)
+        return PackedBatch(arr)
+
+
+def pack(samples, params, sample_ids=None):
+    """run the record loop (meta/generator.cc:77-201) over each sample's records and pack all bundles."""
+    L = lib()
+    pk = L.packer_create()
+    try:
+        for si, s in enumerate(samples):
+            r = PackerRecords()
+            r.n = s["n"]
+            keep = []
+            for k in ("tid", "pos", "rpos", "mpos", "isize", "flag", "mapq", "xs", "qid", "cigar_off", "cigar"):
+                arr = np.ascontiguousarray(s[k])
+                keep.append(arr)
+                setattr(r, k, arr.ctypes.data)
+            sid = si if sample_ids is None else sample_ids[si]
+            if L.packer_add_sample(pk, C.byref(r), C.byref(params), sid) != 0:
+                raise RuntimeError("packer_add_sample failed")
+        v = BatchIn()
+        L.packer_view(pk, C.byref(v))
+        nb, nh, nc = v.n_bundles, v.n_hits, v.n_cigar
+        arr = {"bundle_hit_off": _np(v.bundle_hit_off, nb + 1, np.int64), "bundle_tid": _np(v.bundle_tid, nb, np.int32),
+               "bundle_sample": _np(v.bundle_sample, nb, np.int32),
+               "cigar_off": _np(v.cigar_off, nh + 1, np.uint32), "cigar": _np(v.cigar, nc, np.uint32)}
+        for f, dt in HIT_FIELDS:
+            arr[f] = _np(getattr(v, f), nh, dt)
+        arr["bundle_side"] = _np(L.packer_bundle_side(pk), nb, np.uint8)
+        return PackedBatch(arr)
+    finally:
+        L.packer_destroy(pk)

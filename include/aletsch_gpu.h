@@ -1,0 +1,242 @@
+/* aletsch_gpu.h -- C ABI of the B200-native per-bundle read-evidence path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry
+ * point names the reference seam it replaces (file:line under the reference tree).  The
+ * library is libaletsch_gpu.so (aletsch_b200/csrc, hand-written sm_100a CUDA); there is no
+ * CPU fallback: every compute entry point returns AGPU_ERR_CUDA when no device is usable.
+ *
+ * Unit of work: a BATCH of bundles.  The reference enters its seams once per bundle from a
+ * thread pool (meta/incubator.cc:615-635); here the host packs many bundles into one
+ * structure-of-arrays batch and each call processes all of them.  Device state of a batch
+ * (hits, chain sets hcst/fcst, coverage map mmap, fragments, graph, clusters, bridge
+ * choices) lives in HBM between calls, exactly like a `bundle` object lives between the
+ * reference's calls; `agpu_*_fetch` copies a stage's results into pinned host memory and
+ * hands out flat views.
+ *
+ * Stage map:
+ *   agpu_batch_evidence   bundle_base::add_hit_intervals  rnacore/bundle_base.cc:33-47,73-173
+ *                         + generator::generate           meta/generator.cc:203-227
+ *   agpu_batch_fragments  bundle_base::build_fragments    rnacore/bundle_base.cc:267-323
+ *   agpu_batch_graph      graph_builder::build            rnacore/graph_builder.cc:24-35
+ *                         + splice_graph::build_vertex_index  rnacore/splice_graph.cc:1087-1099
+ *   agpu_batch_cluster    graph_cluster ctor + build_pereads_clusters  rnacore/graph_cluster.cc:13-26
+ *   agpu_batch_bridge     bridge_solver ctor              bridge/bridge_solver.cc:32-46
+ *   agpu_batch_update     bundle_base::update_bridges     rnacore/bundle_base.cc:420-507
+ *                         as looped in bundle::bridge     meta/bundle.cc:73-79
+ *   agpu_batch_bridge_all bundle::bridge                  meta/bundle.cc:55-88
+ *   agpu_similarity       bundle_group::build_splice_similarity  meta/bundle_group.cc:190-231
+ */
+#ifndef ALETSCH_GPU_H
+#define ALETSCH_GPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGPU_OK                 0
+#define AGPU_ERR_ARG           -1   /* bad argument / call order */
+#define AGPU_ERR_CUDA          -2   /* CUDA error (no device, launch failure); see agpu_last_error */
+#define AGPU_ERR_OOM           -3   /* device or pinned allocation failed */
+#define AGPU_ERR_INPUT         -4   /* input violates the packing contract (see agpu_batch_in) */
+#define AGPU_ERR_CAPACITY      -5   /* an internal scratch bound was exceeded; nothing partial is returned */
+
+/* library types (util/constants.h:59-62) */
+#define AGPU_UNSTRANDED 0
+#define AGPU_FR_FIRST   1
+#define AGPU_FR_SECOND  2
+
+typedef struct agpu_ctx agpu_ctx;       /* one per host thread / stream */
+typedef struct agpu_batch agpu_batch;   /* device-resident state of one batch of bundles */
+
+/* The values of `parameters` (util/parameters.h:19-118, defaults util/parameters.cc:19-113)
+ * and `sample_profile` (rnacore/sample_profile.cc:17-33) that the path reads. */
+typedef struct agpu_params
+{
+	int32_t library_type;                  /* sample_profile::library_type */
+	int32_t min_junction_support;          /* 1 (ONT / PacBio-sub: 2) */
+	int32_t normal_junction_threshold;     /* 10 */
+	int32_t extend_junction_threshold;     /* 20 */
+	int32_t min_subregion_gap;             /* 15 */
+	int32_t min_subregion_length;          /* 15 */
+	int32_t max_reads_partition_gap;       /* 10 */
+	int32_t bridge_end_relaxing;           /* 10 */
+	int32_t bridge_dp_solution_size;       /* 10, at most AGPU_MAX_DP_SOLUTIONS */
+	int32_t bridge_dp_stack_size;          /* 5, at most AGPU_MAX_DP_STACK */
+	int32_t insertsize_low;                /* sample_profile::insertsize_low, 80 until profiled */
+	int32_t insertsize_high;               /* sample_profile::insertsize_high, 500 until profiled */
+	int32_t max_group_size;                /* -c, 200 */
+	int32_t max_num_junctions_to_combine;  /* 500 */
+	double min_subregion_overlap;          /* 1.5 */
+	double min_guaranteed_edge_weight;     /* 0.01 */
+	double min_grouping_similarity;        /* -s, 0.10 */
+	double max_grouping_similarity;        /* 0.80 */
+} agpu_params;
+
+#define AGPU_MAX_DP_SOLUTIONS 16
+#define AGPU_MAX_DP_STACK      8
+
+void agpu_default_params(agpu_params *p);
+
+/* Packed input: NB bundles, hits concatenated bundle by bundle in BAM order.
+ * Packing contract (what meta/generator.cc:77-179 + bundle_base::add_hit guarantee):
+ *   - within a bundle pos[] is non-decreasing;
+ *   - no hit equals its predecessor in (pos, rpos)        (rnacore/bundle_base.cc:75-82);
+ *   - rpos[i] == pos[i] + bam_cigar2rlen(cigar of i)      (rnacore/hit.cc:64);
+ *   - strand[] / xs[] hold '+', '-' or '.'; all hits of a bundle share strand[]
+ *     (rnacore/bundle_base.cc:100-101).
+ * agpu_batch_evidence verifies these on the device and returns AGPU_ERR_INPUT if violated.
+ * All arrays are caller-owned host memory (pinned memory makes the upload asynchronous). */
+typedef struct agpu_batch_in
+{
+	int32_t n_bundles;
+	int64_t n_hits;
+	int64_t n_cigar;
+	const int64_t *bundle_hit_off;   /* [NB+1] */
+	const int32_t *bundle_tid;       /* [NB] chromosome id */
+	const int32_t *bundle_sample;    /* [NB] sample id (informational; carried through) */
+	const int32_t *pos;              /* [H] hit.pos */
+	const int32_t *rpos;             /* [H] hit.rpos */
+	const int32_t *mpos;             /* [H] hit.mpos */
+	const int32_t *isize;            /* [H] hit.isize */
+	const uint16_t *flag;            /* [H] hit.flag */
+	const uint8_t *strand;           /* [H] hit.strand */
+	const uint8_t *xs;               /* [H] hit.xs */
+	const uint64_t *qid;             /* [H] query-name key: equal <=> same qname (rnacore/bundle_base.cc:308) */
+	const uint32_t *cigar_off;       /* [H+1] into cigar[] */
+	const uint32_t *cigar;           /* [n_cigar] raw BAM CIGAR ops (len<<4 | op) */
+} agpu_batch_in;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to create one. */
+int agpu_create(int device, void *stream, agpu_ctx **out);
+void agpu_destroy(agpu_ctx *ctx);
+const char *agpu_last_error(agpu_ctx *ctx);
+int agpu_sync(agpu_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t agpu_launch_count(agpu_ctx *ctx);
+
+/* ---- batch life cycle ---------------------------------------------------------------- */
+/* host -> device copy of the packed batch (cudaMemcpyAsync per array on the ctx stream) */
+int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out);
+/* same, but the arrays of `in` are DEVICE pointers already resident in HBM (no copy) */
+int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in_device, agpu_batch **out);
+void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b);
+/* forget all derived state (chains, coverage, fragments, graph ...) but keep the uploaded hits */
+int agpu_batch_reset(agpu_ctx *ctx, agpu_batch *b);
+
+/* ---- stages (asynchronous on the ctx stream unless noted) ----------------------------- */
+int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p);
+int agpu_batch_fragments(agpu_ctx *ctx, agpu_batch *b);
+int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p);
+int agpu_batch_cluster(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p);
+int agpu_batch_bridge(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p);
+int agpu_batch_update(agpu_ctx *ctx, agpu_batch *b);
+/* evidence (if not done) + fragments (if not done) + graph + cluster + bridge + update */
+int agpu_batch_bridge_all(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p);
+
+/* ---- results: flat views into ctx-owned pinned host memory, valid until the next fetch
+ *      of the same kind on this batch or agpu_batch_free.  Each fetch synchronises. ------ */
+
+typedef struct agpu_chainset_view       /* chain_set (rnacore/chain_set.h:18-35), insertion-ordered */
+{
+	const int32_t *bundle_chain_off;    /* [NB+1] chains of bundle b: [off[b], off[b+1]) */
+	const int32_t *chain_off;           /* [C+1] into chain_val */
+	const int32_t *chain_val;           /* splice coordinates l0 r0 l1 r1 ... */
+	const int32_t *chain_cnt;           /* [3C] n. n+ n-  (AI3) */
+	const int32_t *chain_grp;           /* [C] index i of chains[i][j] inside its bundle */
+	const int32_t *handle_chain;        /* [H or F] bundle-local chain index of hit / fragment, -1 if none (hmap) */
+	int64_t n_chains;
+	int64_t n_handles;
+} agpu_chainset_view;
+
+typedef struct agpu_evidence_view
+{
+	int32_t n_bundles;
+	const int32_t *lpos;                /* [NB] bundle_base::lpos */
+	const int32_t *rpos;                /* [NB] bundle_base::rpos */
+	const uint8_t *strand;              /* [NB] bundle_base::strand after compute_strand */
+	const int64_t *seg_off;             /* [NB+1] */
+	const int32_t *seg;                 /* [3S] l r cov: split_interval_map mmap in order */
+	const int64_t *splice_off;          /* [NB+1] */
+	const int32_t *splices;             /* bundle_base::splices (sorted unique) */
+	agpu_chainset_view hcst;
+} agpu_evidence_view;
+
+typedef struct agpu_fragments_view
+{
+	const int64_t *frg_off;             /* [NB+1] */
+	const int32_t *frgs;                /* [3F] h1 h2 type, h bundle-local; bundle_base::frgs in order */
+	agpu_chainset_view fcst;            /* handles are bundle-local fragment indices */
+	const int32_t *bridged;             /* [NB] sum of update_bridges return values so far */
+} agpu_fragments_view;
+
+typedef struct agpu_graph_view
+{
+	const int32_t *junc_off;            /* [NB+1] */
+	const int32_t *junc;                /* [9J] lpos rpos count xs0 xs1 xs2 strand lexon rexon (graph_builder::junctions order) */
+	const int32_t *pexon_off;           /* [NB+1] */
+	const int32_t *pexon;               /* [5P] lpos rpos ltype rtype regional */
+	const double *pexon_d;              /* [4P] ave dev max pvalue (max = -1 for the 1-bp stubs, which the reference leaves unset) */
+	const int32_t *vert_off;            /* [NB+1]; V = P + 2 per bundle */
+	const int32_t *vert;                /* [5V] lpos rpos length type regional */
+	const double *vert_d;               /* [3V] weight stddev maxcov */
+	const int32_t *edge_off;            /* [NB+1] */
+	const int32_t *edge;                /* [3E] src dst strand, in the reference's insertion order; removed edges have src = -1 */
+	const double *edge_d;               /* [E] weight */
+	const uint8_t *strand;              /* [NB] splice_graph::strand */
+} agpu_graph_view;
+
+typedef struct agpu_cluster_view        /* vector<pereads_cluster> per bundle, in order */
+{
+	const int64_t *clu_off;             /* [NB+1] */
+	const int32_t *bounds;              /* [4C] */
+	const int32_t *extend;              /* [4C] */
+	const int32_t *count;               /* [C] */
+	const int32_t *chain1;              /* [C] bundle-local hcst chain index of chain1, -1 if empty */
+	const int32_t *chain2;              /* [C] */
+	const int64_t *frlist_off;          /* [C+1] */
+	const int32_t *frlist;              /* bundle-local fragment indices */
+	int64_t n_clusters;
+} agpu_cluster_view;
+
+typedef struct agpu_bridge_view         /* bridge_solver::opt per cluster */
+{
+	const int32_t *type;                /* [C] -1 / 1 / 2 */
+	const int32_t *strand;              /* [C] */
+	const int32_t *choices;             /* [C] */
+	const double *score;                /* [C] */
+	const int64_t *chain_off;           /* [C+1] */
+	const int32_t *chain;
+	const int64_t *whole_off;           /* [C+1] */
+	const int32_t *whole;
+} agpu_bridge_view;
+
+int agpu_evidence_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_evidence_view *v);
+int agpu_fragments_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_fragments_view *v);
+int agpu_graph_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_graph_view *v);
+int agpu_cluster_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_cluster_view *v);
+int agpu_bridge_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_bridge_view *v);
+
+/* counters of the batch (host copies, synchronises): hits, cigar ops, coverage span L,
+ * segments S, chains, junctions J, vertices V, edges E, fragments F, clusters C, bridged pairs */
+typedef struct agpu_counts
+{
+	int64_t hits, cigar_ops, span, segments, chains, splice_ints, junctions, vertices, edges;
+	int64_t fragments, clusters, bridged, piers;
+} agpu_counts;
+int agpu_batch_counts(agpu_ctx *ctx, agpu_batch *b, agpu_counts *c);
+
+/* ---- stage 5: junction-set similarity ------------------------------------------------ */
+/* G sorted splice lists (bundle::splices); for every pair i<j: c = |splices_i ∩ splices_j| and
+ * r = c / min(|splices_i|, |splices_j|).  out_c / out_r are dense G x G (row-major, upper
+ * triangle filled, diagonal and lower triangle 0), caller-owned host memory. */
+int agpu_similarity(agpu_ctx *ctx, int32_t n_lists, const int64_t *list_off, const int32_t *list_val,
+		int32_t *out_c, double *out_r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,85 @@
+/* TEST INFRASTRUCTURE ONLY (oracle/).  Shared flat C interface of the two CPU checkers:
+ *   - oracle/_ref/libaletsch_ref.so   the reference's own translation units, compiled
+ *                                     unchanged from /root/reference (prefix "ref_")
+ *   - oracle/liboracle.so             our CPU restatement of the same algorithms (prefix "orc_")
+ * Both take the same packed bundle input and write results into a "bag" of named flat
+ * arrays so that tests compare them array by array.  Nothing under aletsch_b200/ may
+ * include, link or call this.
+ */
+#ifndef ALETSCH_B200_ORACLE_ORC_API_H
+#define ALETSCH_B200_ORACLE_ORC_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* one bundle's hits, already routed to this strand bundle by the packer
+ * (meta/generator.cc:87-179), in BAM order */
+typedef struct orc_bundle_in
+{
+	int32_t n_hits;
+	int32_t tid;
+	const int32_t *pos;          /* [H] 0-based leftmost coordinate */
+	const int32_t *mpos;         /* [H] mate position */
+	const int32_t *isize;        /* [H] template length */
+	const uint16_t *flag;        /* [H] BAM flag */
+	const uint8_t *strand;       /* [H] hit.strand after set_strand + generator fix-up: '+','-','.' */
+	const uint8_t *xs;           /* [H] hit.xs after set_tags: '+','-','.' */
+	const uint64_t *qid;         /* [H] query-name key: equal keys <=> equal qnames */
+	const uint32_t *cigar_off;   /* [H+1] offsets into cigar[] */
+	const uint32_t *cigar;       /* raw BAM CIGAR ops, len<<4|op */
+} orc_bundle_in;
+
+/* the values of util/parameters.h + rnacore/sample_profile.h that the path reads */
+typedef struct orc_params
+{
+	int32_t library_type;                 /* UNSTRANDED 0, FR_FIRST 1, FR_SECOND 2 */
+	int32_t min_junction_support;
+	int32_t normal_junction_threshold;
+	int32_t extend_junction_threshold;
+	int32_t min_subregion_gap;
+	int32_t min_subregion_length;
+	int32_t max_reads_partition_gap;
+	int32_t bridge_end_relaxing;
+	int32_t bridge_dp_solution_size;
+	int32_t bridge_dp_stack_size;
+	int32_t insertsize_low;
+	int32_t insertsize_high;
+	int32_t max_group_size;
+	int32_t max_num_junctions_to_combine;
+	double min_subregion_overlap;
+	double min_guaranteed_edge_weight;
+	double min_grouping_similarity;
+	double max_grouping_similarity;
+} orc_params;
+
+/* result bag: named flat arrays, kind 0 = int32, 1 = float64 */
+void *orc_bag_new(void);
+void orc_bag_free(void *bag);
+void orc_bag_clear(void *bag);
+int orc_bag_count(void *bag);
+const char *orc_bag_name(void *bag, int i);
+int orc_bag_kind(void *bag, int i);
+int64_t orc_bag_len(void *bag, int i);
+const void *orc_bag_data(void *bag, int i);
+
+#define ORC_DECLARE(P) \
+	void *P##_bundle_new(const orc_bundle_in *in, const orc_params *prm); \
+	void P##_bundle_free(void *b); \
+	int P##_bundle_evidence(void *b, void *bag); \
+	int P##_bundle_fragments(void *b, void *bag); \
+	int P##_bundle_graph(void *b, void *bag); \
+	int P##_bundle_bridge(void *b, void *bag); \
+	int P##_group_bridge(void **bs, int n, void *bag); \
+	int P##_group_resolve(void **bs, int n, const orc_params *prm, void *bag);
+
+ORC_DECLARE(ref)
+ORC_DECLARE(orc)
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

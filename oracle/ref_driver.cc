@@ -1,0 +1,440 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): drives the reference's OWN classes (compiled unchanged
+// from /root/reference, see oracle/Makefile) through the hot path and dumps what they computed
+// as flat named arrays (orc_api.h).  This file contains no algorithm of its own: it only calls
+// the reference in the order the reference's callers do and copies fields out.
+//
+// Call orders mirrored:
+//   ref_bundle_new       meta/generator.cc:155-179 (add_hit_intervals per hit) + :203-227 (generate)
+//   ref_bundle_fragments meta/assembler.cc:39       (build_fragments)
+//   ref_bundle_graph     meta/assembler.cc:930-934  (graph_builder::build + build_vertex_index)
+//   ref_bundle_bridge    meta/bundle.cc:55-88       (bundle::bridge)
+//   ref_group_bridge     meta/assembler.cc:977-1018 (assembler::bridge)
+//   ref_group_resolve    meta/bundle_group.cc:26-56 (bundle_group::resolve)
+#include "orc_api.h"
+#include "orc_bag.h"
+#include "compat/hts_shim.h"
+
+#include "bundle.h"
+#include "bundle_group.h"
+#include "graph_builder.h"
+#include "graph_cluster.h"
+#include "bridge_solver.h"
+#include "essential.h"
+#include "parameters.h"
+#include "sample_profile.h"
+
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct ref_handle
+{
+	parameters cfg;
+	sample_profile sp;
+	bundle bd;
+	std::vector<int> keep;        // input index of every stored hit
+	ref_handle() : sp(0, 1000000), bd(cfg, sp) {}
+};
+
+void apply_params(const orc_params *p, parameters &cfg, sample_profile &sp)
+{
+	cfg.verbose = 0;
+	cfg.min_junction_support = p->min_junction_support;
+	cfg.normal_junction_threshold = p->normal_junction_threshold;
+	cfg.extend_junction_threshold = p->extend_junction_threshold;
+	cfg.min_subregion_gap = p->min_subregion_gap;
+	cfg.min_subregion_length = p->min_subregion_length;
+	cfg.min_subregion_overlap = p->min_subregion_overlap;
+	cfg.min_guaranteed_edge_weight = p->min_guaranteed_edge_weight;
+	cfg.max_reads_partition_gap = p->max_reads_partition_gap;
+	cfg.bridge_end_relaxing = p->bridge_end_relaxing;
+	cfg.bridge_dp_solution_size = p->bridge_dp_solution_size;
+	cfg.bridge_dp_stack_size = p->bridge_dp_stack_size;
+	cfg.max_group_size = p->max_group_size;
+	cfg.max_num_junctions_to_combine = p->max_num_junctions_to_combine;
+	cfg.min_grouping_similarity = p->min_grouping_similarity;
+	cfg.max_grouping_similarity = p->max_grouping_similarity;
+	sp.library_type = p->library_type;
+	sp.insertsize_low = p->insertsize_low;
+	sp.insertsize_high = p->insertsize_high;
+}
+
+std::string qname_of(uint64_t q)
+{
+	char buf[32];
+	snprintf(buf, sizeof(buf), "q%016llx", (unsigned long long)q);
+	return std::string(buf);
+}
+
+void dump_chain_set(const chain_set &cs, orc_bag &bag, const std::string &pre, int nh, const std::string &hname)
+{
+	std::vector<int32_t> &off = bag.ints(pre + "_off");
+	std::vector<int32_t> &val = bag.ints(pre + "_val");
+	std::vector<int32_t> &cnt = bag.ints(pre + "_cnt");
+	std::vector<int32_t> &grp = bag.ints(pre + "_grp");
+	off.clear(); val.clear(); cnt.clear(); grp.clear();
+	std::vector< std::vector<int> > flat(cs.chains.size());
+	off.push_back(0);
+	int c = 0;
+	for(size_t i = 0; i < cs.chains.size(); i++)
+	{
+		for(size_t j = 0; j < cs.chains[i].size(); j++)
+		{
+			const PVI3 &p = cs.chains[i][j];
+			val.insert(val.end(), p.first.begin(), p.first.end());
+			off.push_back((int32_t)val.size());
+			cnt.push_back(p.second[0]);
+			cnt.push_back(p.second[1]);
+			cnt.push_back(p.second[2]);
+			grp.push_back((int32_t)i);
+			flat[i].push_back(c++);
+		}
+	}
+	std::vector<int32_t> &hc = bag.ints(hname);
+	std::vector<int32_t> &hx = bag.ints(hname + "_xs");
+	hc.assign(nh, -1);
+	hx.assign(nh, -1);
+	for(std::map<int, AI3>::const_iterator it = cs.hmap.begin(); it != cs.hmap.end(); ++it)
+	{
+		if(it->first < 0 || it->first >= nh) continue;
+		hc[it->first] = flat[it->second[0]][it->second[1]];
+		hx[it->first] = it->second[2];
+	}
+}
+
+void dump_segments(const split_interval_map &m, orc_bag &bag, const std::string &name)
+{
+	std::vector<int32_t> &seg = bag.ints(name);
+	seg.clear();
+	for(SIMI it = m.begin(); it != m.end(); ++it)
+	{
+		seg.push_back(lower(it->first));
+		seg.push_back(upper(it->first));
+		seg.push_back(it->second);
+	}
+}
+
+void dump_evidence(ref_handle &h, orc_bag &bag)
+{
+	bundle &bd = h.bd;
+	std::vector<int32_t> &b = bag.ints("bundle");
+	b.clear();
+	b.push_back(bd.lpos);
+	b.push_back(bd.rpos);
+	b.push_back((int32_t)bd.strand);
+	b.push_back((int32_t)bd.hits.size());
+	std::vector<int32_t> &kp = bag.ints("hits");
+	kp.assign(h.keep.begin(), h.keep.end());
+	dump_segments(bd.mmap, bag, "seg");
+	bag.ints("splices") = bd.splices;
+	dump_chain_set(bd.hcst, bag, "hcst", (int)bd.hits.size(), "hit_chain");
+}
+
+void dump_frgs(bundle_base &bd, orc_bag &bag, const std::string &name)
+{
+	std::vector<int32_t> &f = bag.ints(name);
+	f.clear();
+	for(size_t i = 0; i < bd.frgs.size(); i++)
+	{
+		f.push_back(bd.frgs[i][0]);
+		f.push_back(bd.frgs[i][1]);
+		f.push_back(bd.frgs[i][2]);
+	}
+}
+
+void dump_builder(graph_builder &gb, parameters &cfg, orc_bag &bag, const std::string &pre)
+{
+	std::vector<int32_t> &jc = bag.ints(pre + "junc");
+	jc.clear();
+	for(size_t i = 0; i < gb.junctions.size(); i++)
+	{
+		const junction &j = gb.junctions[i];
+		jc.push_back(j.lpos); jc.push_back(j.rpos); jc.push_back(j.count);
+		jc.push_back(j.xs0); jc.push_back(j.xs1); jc.push_back(j.xs2);
+		jc.push_back((int32_t)j.strand); jc.push_back(j.lexon); jc.push_back(j.rexon);
+	}
+	std::vector<int32_t> &pe = bag.ints(pre + "pexon");
+	std::vector<double> &pd = bag.reals(pre + "pexon_d");
+	pe.clear(); pd.clear();
+	for(size_t i = 0; i < gb.pexons.size(); i++)
+	{
+		const partial_exon &p = gb.pexons[i];
+		pe.push_back(p.lpos); pe.push_back(p.rpos); pe.push_back(p.ltype); pe.push_back(p.rtype);
+		pe.push_back(gb.regional[i] ? 1 : 0);
+		// partial_exon::max is left uninitialised for the 1-bp stub pexons
+		// (rnacore/region.cc:118-121, :135-138, :162-165): report -1 there
+		bool stub = (p.rpos - p.lpos == 1 && p.ave == cfg.min_guaranteed_edge_weight && p.dev == 1.0);
+		pd.push_back(p.ave); pd.push_back(p.dev); pd.push_back(stub ? -1.0 : p.max); pd.push_back(p.pvalue);
+	}
+}
+
+void dump_graph(splice_graph &gr, parameters &cfg, orc_bag &bag, const std::string &pre)
+{
+	std::vector<int32_t> &vi = bag.ints(pre + "vert");
+	std::vector<double> &vd = bag.reals(pre + "vert_d");
+	std::vector<int32_t> &ei = bag.ints(pre + "edge");
+	std::vector<double> &ed = bag.reals(pre + "edge_d");
+	vi.clear(); vd.clear(); ei.clear(); ed.clear();
+	int n = (int)gr.num_vertices();
+	for(int i = 0; i < n; i++)
+	{
+		const vertex_info &v = gr.get_vertex_info(i);
+		double w = gr.get_vertex_weight(i);
+		vi.push_back(v.lpos); vi.push_back(v.rpos); vi.push_back(v.length); vi.push_back(v.type);
+		vi.push_back(v.regional ? 1 : 0);
+		bool stub = (i != 0 && i != n - 1 && v.rpos - v.lpos == 1 && w == cfg.min_guaranteed_edge_weight && v.stddev == 1.0);
+		vd.push_back(w); vd.push_back(v.stddev); vd.push_back(stub ? -1.0 : v.maxcov);
+	}
+	for(int i = 0; i < n; i++)
+	{
+		PEEI pe = gr.out_edges(i);
+		for(edge_iterator it = pe.first; it != pe.second; ++it)
+		{
+			edge_descriptor e = *it;
+			ei.push_back(e->source()); ei.push_back(e->target()); ei.push_back(gr.get_edge_info(e).strand);
+			ed.push_back(gr.get_edge_weight(e));
+		}
+	}
+	std::vector<int32_t> &gs = bag.ints(pre + "graph");
+	gs.clear();
+	gs.push_back((int32_t)gr.strand);
+}
+
+void dump_clusters(const std::vector<pereads_cluster> &vc, orc_bag &bag, const std::string &pre)
+{
+	std::vector<int32_t> &bo = bag.ints(pre + "clu_bounds");
+	std::vector<int32_t> &ex = bag.ints(pre + "clu_extend");
+	std::vector<int32_t> &ct = bag.ints(pre + "clu_count");
+	std::vector<int32_t> &o1 = bag.ints(pre + "clu_c1_off");
+	std::vector<int32_t> &v1 = bag.ints(pre + "clu_c1_val");
+	std::vector<int32_t> &o2 = bag.ints(pre + "clu_c2_off");
+	std::vector<int32_t> &v2 = bag.ints(pre + "clu_c2_val");
+	std::vector<int32_t> &of = bag.ints(pre + "clu_fr_off");
+	std::vector<int32_t> &vf = bag.ints(pre + "clu_fr_val");
+	bo.clear(); ex.clear(); ct.clear(); o1.clear(); v1.clear(); o2.clear(); v2.clear(); of.clear(); vf.clear();
+	o1.push_back(0); o2.push_back(0); of.push_back(0);
+	for(size_t i = 0; i < vc.size(); i++)
+	{
+		const pereads_cluster &pc = vc[i];
+		bo.insert(bo.end(), pc.bounds.begin(), pc.bounds.end());
+		ex.insert(ex.end(), pc.extend.begin(), pc.extend.end());
+		ct.push_back(pc.count);
+		v1.insert(v1.end(), pc.chain1.begin(), pc.chain1.end());
+		o1.push_back((int32_t)v1.size());
+		v2.insert(v2.end(), pc.chain2.begin(), pc.chain2.end());
+		o2.push_back((int32_t)v2.size());
+		vf.insert(vf.end(), pc.frlist.begin(), pc.frlist.end());
+		of.push_back((int32_t)vf.size());
+	}
+}
+
+void dump_opt(const std::vector<bridge_path> &opt, orc_bag &bag, const std::string &pre)
+{
+	std::vector<int32_t> &o = bag.ints(pre + "opt");
+	std::vector<double> &os = bag.reals(pre + "opt_score");
+	std::vector<int32_t> &co = bag.ints(pre + "opt_chain_off");
+	std::vector<int32_t> &cv = bag.ints(pre + "opt_chain_val");
+	std::vector<int32_t> &wo = bag.ints(pre + "opt_whole_off");
+	std::vector<int32_t> &wv = bag.ints(pre + "opt_whole_val");
+	o.clear(); os.clear(); co.clear(); cv.clear(); wo.clear(); wv.clear();
+	co.push_back(0); wo.push_back(0);
+	for(size_t i = 0; i < opt.size(); i++)
+	{
+		const bridge_path &p = opt[i];
+		o.push_back(p.type); o.push_back(p.strand); o.push_back(p.choices);
+		os.push_back(p.score);
+		cv.insert(cv.end(), p.chain.begin(), p.chain.end());
+		co.push_back((int32_t)cv.size());
+		wv.insert(wv.end(), p.whole.begin(), p.whole.end());
+		wo.push_back((int32_t)wv.size());
+	}
+}
+
+// meta/bundle.cc:66-79 / meta/assembler.cc:989-1012: cluster, solve, update one bundle against gr
+int cluster_solve_update(splice_graph &gr, bundle &bd, const parameters &cfg, orc_bag &bag, const std::string &pre, bool skip_if_empty)
+{
+	std::vector<pereads_cluster> vc;
+	graph_cluster gc(gr, bd, cfg.max_reads_partition_gap, false);
+	gc.build_pereads_clusters(vc);
+	dump_frgs(bd, bag, pre + "frgs_clustered");
+	dump_clusters(vc, bag, pre);
+	int cnt = 0;
+	if(skip_if_empty && vc.size() <= 0)
+	{
+		dump_opt(std::vector<bridge_path>(), bag, pre);
+	}
+	else
+	{
+		bridge_solver bs(gr, vc, cfg, bd.sp.insertsize_low, bd.sp.insertsize_high);
+		dump_opt(bs.opt, bag, pre);
+		for(size_t k = 0; k < vc.size(); k++)
+		{
+			if(bs.opt[k].type <= 0) continue;
+			cnt += bd.update_bridges(vc[k].frlist, bs.opt[k].chain, bs.opt[k].strand);
+		}
+	}
+	dump_frgs(bd, bag, pre + "frgs");
+	dump_chain_set(bd.fcst, bag, pre + "fcst", (int)bd.frgs.size(), pre + "frg_chain");
+	dump_segments(bd.mmap, bag, pre + "seg");
+	std::vector<int32_t> &bc = bag.ints(pre + "bridged");
+	bc.clear();
+	bc.push_back(cnt);
+	return cnt;
+}
+
+} // namespace
+
+extern "C" {
+
+void *ref_bundle_new(const orc_bundle_in *in, const orc_params *prm)
+{
+	ref_handle *h = new ref_handle;
+	apply_params(prm, h->cfg, h->sp);
+	bundle_base &bb = h->bd;
+	bam1_t b1t;
+	for(int i = 0; i < in->n_hits; i++)
+	{
+		uint32_t c0 = in->cigar_off[i];
+		uint32_t c1 = in->cigar_off[i + 1];
+		hts_shim_record rec = hts_shim_make_record(in->tid, in->pos[i], 60, in->flag[i], in->tid, in->mpos[i], in->isize[i],
+				qname_of(in->qid[i]), in->cigar + c0, c1 - c0, (char)in->xs[i], '.', 1, 1, -1);
+		hts_shim_view(rec, &b1t);
+		hit ht(&b1t, i);
+		ht.set_tags(&b1t);
+		ht.strand = (char)in->strand[i];
+		size_t before = bb.hits.size();
+		bb.add_hit_intervals(ht, &b1t);
+		if(bb.hits.size() > before) h->keep.push_back(i);
+	}
+	// meta/generator.cc:203-227
+	bb.add_buf_intervals();
+	bb.splices = bb.hcst.get_splices();
+	h->bd.chrm = "chr";
+	h->bd.compute_strand(h->sp.library_type);
+	return h;
+}
+
+void ref_bundle_free(void *b) { delete (ref_handle*)b; }
+
+int ref_bundle_evidence(void *b, void *bag)
+{
+	dump_evidence(*(ref_handle*)b, *(orc_bag*)bag);
+	return 0;
+}
+
+int ref_bundle_fragments(void *b, void *bag)
+{
+	ref_handle *h = (ref_handle*)b;
+	h->bd.build_fragments();
+	dump_frgs(h->bd, *(orc_bag*)bag, "frgs");
+	return 0;
+}
+
+int ref_bundle_graph(void *b, void *bagp)
+{
+	ref_handle *h = (ref_handle*)b;
+	orc_bag &bag = *(orc_bag*)bagp;
+	splice_graph gr;
+	graph_builder gb(h->bd, h->cfg, h->sp);
+	gb.build(gr);
+	gr.build_vertex_index();
+	dump_builder(gb, h->cfg, bag, "");
+	dump_graph(gr, h->cfg, bag, "");
+	return 0;
+}
+
+int ref_bundle_bridge(void *b, void *bagp)
+{
+	ref_handle *h = (ref_handle*)b;
+	orc_bag &bag = *(orc_bag*)bagp;
+	splice_graph gr;
+	graph_builder gb(h->bd, h->cfg, h->sp);
+	gb.build(gr);
+	gr.build_vertex_index();
+	dump_builder(gb, h->cfg, bag, "");
+	dump_graph(gr, h->cfg, bag, "");
+	return cluster_solve_update(gr, h->bd, h->cfg, bag, "", false);
+}
+
+int ref_group_bridge(void **bs, int n, void *bagp)
+{
+	orc_bag &bag = *(orc_bag*)bagp;
+	if(n < 2) return -1;
+	ref_handle *h0 = (ref_handle*)bs[0];
+	// meta/assembler.cc:977-987
+	bundle cb(h0->cfg, h0->sp);
+	cb.copy_meta_information(h0->bd);
+	// meta/assembler.cc:152-175 (combine_bundles)
+	std::vector<PI> v;
+	for(int k = 0; k < n; k++)
+	{
+		bundle &g = ((ref_handle*)bs[k])->bd;
+		v.push_back(PI(k, std::distance(g.mmap.begin(), g.mmap.end())));
+	}
+	sort(v.begin(), v.end(), [](const PI &x, const PI &y){ return x.second > y.second; });
+	std::vector<int32_t> &ord = bag.ints("combine_order");
+	ord.clear();
+	for(size_t i = 0; i < v.size(); i++)
+	{
+		cb.combine(((ref_handle*)bs[v[i].first])->bd, true);
+		ord.push_back(v[i].first);
+	}
+	dump_chain_set(cb.hcst, bag, "cb_hcst", 0, "cb_hit_chain");
+	dump_chain_set(cb.fcst, bag, "cb_fcst", 0, "cb_frg_chain");
+	dump_segments(cb.mmap, bag, "cb_seg");
+	std::vector<int32_t> &cbb = bag.ints("cb_bundle");
+	cbb.clear();
+	cbb.push_back(cb.lpos); cbb.push_back(cb.rpos); cbb.push_back((int32_t)cb.strand);
+
+	splice_graph gr;
+	graph_builder gb(cb, h0->cfg, cb.sp);
+	gb.build(gr);
+	gr.build_vertex_index();
+	dump_builder(gb, h0->cfg, bag, "cb_");
+	dump_graph(gr, h0->cfg, bag, "cb_");
+
+	int total = 0;
+	for(int k = 0; k < n; k++)
+	{
+		ref_handle *h = (ref_handle*)bs[k];
+		char pre[32];
+		snprintf(pre, sizeof(pre), "b%d_", k);
+		total += cluster_solve_update(gr, h->bd, h0->cfg, bag, pre, true);
+	}
+	return total;
+}
+
+int ref_group_resolve(void **bs, int n, const orc_params *prm, void *bagp)
+{
+	orc_bag &bag = *(orc_bag*)bagp;
+	parameters cfg;
+	sample_profile sp(0, 1000000);
+	apply_params(prm, cfg, sp);
+	std::map<std::string, std::vector<PI> > sidx;
+	bundle_group grp("chr", '.', 0, cfg, sidx);
+	for(int k = 0; k < n; k++)
+	{
+		ref_handle *h = (ref_handle*)bs[k];
+		bundle b(cfg, sp);
+		b.chrm = "chr";
+		b.strand = '.';
+		b.tid = h->bd.tid;
+		b.splices = h->bd.splices;
+		grp.gset.push_back(b);
+	}
+	grp.resolve();
+	std::vector<int32_t> &off = bag.ints("gvv_off");
+	std::vector<int32_t> &val = bag.ints("gvv_val");
+	off.clear(); val.clear();
+	off.push_back(0);
+	for(size_t i = 0; i < grp.gvv.size(); i++)
+	{
+		val.insert(val.end(), grp.gvv[i].begin(), grp.gvv[i].end());
+		off.push_back((int32_t)val.size());
+	}
+	return 0;
+}
+
+}
