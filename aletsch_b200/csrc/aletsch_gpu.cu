@@ -1,0 +1,492 @@
+// libaletsch_gpu.so: implementation of include/aletsch_gpu.h.
+// Compiled by nvcc for sm_100a (product) or, for the CPU-only kernel-logic tests, by g++ with
+// -DAGPU_EMU (tests/emu; never shipped, see dev.h).
+#include "runtime.h"
+#include "k_evidence.h"
+#include "k_graph.h"
+#include "k_fragments.h"
+#include "k_cluster.h"
+#include "k_bridge.h"
+#include "k_similarity.h"
+
+#include <algorithm>
+#include <map>
+#include <new>
+
+#ifdef AGPU_EMU
+thread_local agpu_emu_dim threadIdx, blockIdx, blockDim, gridDim;
+#endif
+
+using namespace agpu;
+
+// ------------------------------------------------------------------------------------------
+// device chain_set (hcst / fcst)
+struct chainset_state
+{
+	bool built = false;
+	int64_t n_elem = 0;
+	const int64_t *d_elem_off = NULL;     // [NB+1]
+	const int32_t *val = NULL;
+	const u32 *voff32 = NULL;
+	const int64_t *voff64 = NULL;
+	const int32_t *elem_len = NULL;
+	dbuf<int64_t> reg_off, elem_slot, c_slot, val_base;
+	dbuf<u64> slot_word, key_scratch, key_scratch2;
+	dbuf<int32_t> slot_first, slot_cnt, slot_chain, n_chains, n_splices, c_rep, c_cnt, c_grp, handle_chain, splices_scratch;
+	int64_t n_slots = 0;
+
+	void release(agpu_ctx *ctx)
+	{
+		reg_off.release(ctx); elem_slot.release(ctx); c_slot.release(ctx); val_base.release(ctx);
+		slot_word.release(ctx); key_scratch.release(ctx); key_scratch2.release(ctx);
+		slot_first.release(ctx); slot_cnt.release(ctx); slot_chain.release(ctx); n_chains.release(ctx); n_splices.release(ctx);
+		c_rep.release(ctx); c_cnt.release(ctx); c_grp.release(ctx); handle_chain.release(ctx); splices_scratch.release(ctx);
+		built = false;
+	}
+
+	chains_view view() const
+	{
+		chains_view v;
+		v.present = built ? 1 : 0;
+		v.elem_off = d_elem_off; v.n_chains = n_chains.p; v.c_rep = c_rep.p; v.c_cnt = c_cnt.p;
+		v.elem_len = elem_len; v.voff32 = voff32; v.voff64 = voff64; v.val = val;
+		return v;
+	}
+};
+
+struct graph_state
+{
+	bool built = false;
+	dbuf<int64_t> ub[5], off[5];
+	int64_t tot[5] = {0, 0, 0, 0, 0};
+	dbuf<int32_t> iarena;
+	dbuf<u64> karena;
+	dbuf<int32_t> n_junc, n_pex, n_edge;
+	dbuf<int32_t> j[9];
+	dbuf<int32_t> p_i[6];
+	dbuf<double> p_d[3];
+	dbuf<int32_t> v_i[6];
+	dbuf<double> v_d[3];
+	dbuf<int32_t> e_i[3];
+	dbuf<double> e_w;
+	dbuf<int32_t> in_off, in_src, in_eid, out_off, out_dst, out_eid;
+
+	void release(agpu_ctx *ctx)
+	{
+		for(int k = 0; k < 5; k++) { ub[k].release(ctx); off[k].release(ctx); }
+		iarena.release(ctx); karena.release(ctx); n_junc.release(ctx); n_pex.release(ctx); n_edge.release(ctx);
+		for(int k = 0; k < 9; k++) j[k].release(ctx);
+		for(int k = 0; k < 6; k++) { p_i[k].release(ctx); v_i[k].release(ctx); }
+		for(int k = 0; k < 3; k++) { p_d[k].release(ctx); v_d[k].release(ctx); e_i[k].release(ctx); }
+		e_w.release(ctx);
+		in_off.release(ctx); in_src.release(ctx); in_eid.release(ctx); out_off.release(ctx); out_dst.release(ctx); out_eid.release(ctx);
+		built = false;
+	}
+
+	graph_dev dev(int *err) const
+	{
+		graph_dev g;
+		g.junc_off = off[0].p; g.pex_off = off[1].p; g.edge_off = off[2].p; g.iarena_off = off[3].p; g.karena_off = off[4].p;
+		g.iarena = iarena.p; g.karena = karena.p;
+		g.n_junc = n_junc.p; g.n_pex = n_pex.p; g.n_edge = n_edge.p;
+		g.j_l = j[0].p; g.j_r = j[1].p; g.j_cnt = j[2].p; g.j_xs0 = j[3].p; g.j_xs1 = j[4].p; g.j_xs2 = j[5].p;
+		g.j_strand = j[6].p; g.j_lexon = j[7].p; g.j_rexon = j[8].p;
+		g.p_l = p_i[0].p; g.p_r = p_i[1].p; g.p_lt = p_i[2].p; g.p_rt = p_i[3].p; g.p_regional = p_i[4].p; g.p_type = p_i[5].p;
+		g.p_ave = p_d[0].p; g.p_dev = p_d[1].p; g.p_max = p_d[2].p;
+		g.v_l = v_i[0].p; g.v_r = v_i[1].p; g.v_len = v_i[2].p; g.v_type = v_i[3].p; g.v_regional = v_i[4].p; g.v_brk = v_i[5].p;
+		g.v_w = v_d[0].p; g.v_dev = v_d[1].p; g.v_max = v_d[2].p;
+		g.e_s = e_i[0].p; g.e_t = e_i[1].p; g.e_strand = e_i[2].p; g.e_w = e_w.p;
+		g.in_off = in_off.p; g.in_src = in_src.p; g.in_eid = in_eid.p;
+		g.out_off = out_off.p; g.out_dst = out_dst.p; g.out_eid = out_eid.p;
+		g.err = err;
+		return g;
+	}
+};
+
+struct agpu_batch
+{
+	int32_t nb = 0;
+	int64_t nh = 0, nc = 0;
+	bool owns_input = false;
+	hits_dev h;
+	// owned copies of the input (upload path)
+	dbuf<int64_t> in_hit_off;
+	dbuf<int32_t> in_pos, in_rpos, in_mpos, in_isize;
+	dbuf<uint16_t> in_flag;
+	dbuf<uint8_t> in_strand, in_xs;
+	dbuf<u64> in_qid;
+	dbuf<u32> in_cigar_off, in_cigar;
+	std::vector<int64_t> hit_off_host;
+	std::vector<int32_t> tid_host, sample_host;
+
+	dbuf<int> err;
+
+	// evidence
+	bool evidence = false;
+	dbuf<int32_t> b_lpos, b_rpos, b_covhi;
+	dbuf<uint8_t> b_strand;
+	dbuf<int64_t> b_span, cov_base;
+	int64_t ltot = 0;
+	dbuf<int32_t> diff;
+	dbuf<u32> border;
+	dbuf<int32_t> spl, hit_nspl, hit_bundle;
+	dbuf<u64> hit_hash;
+	chainset_state hcst, fcst;
+	// segments
+	bool cov_dirty = true;
+	dbuf<int32_t> tile_sum, tile_cnt;
+	dbuf<int64_t> tile_pre, tile_seg_off, seg_off;
+	dbuf<int32_t> seg_l, seg_r, seg_c;
+	int64_t n_seg = 0;
+
+	// fragments / clusters / bridges live in their own headers' state structs
+	fragments_state frg;
+	graph_state gr;
+	cluster_state clu;
+	bridge_state brg;
+
+	// pinned result mirrors, by name
+	std::map<std::string, hbuf<char> > pinned;
+	template<typename T> T *host(const std::string &name, size_t count) { return (T*)pinned[name].ensure((count + 2) * sizeof(T)); }
+};
+
+static int check_err(agpu_ctx *ctx, agpu_batch *b, const char *stage)
+{
+	int e[ERR_WORDS];
+	TRY(d2h(ctx, e, b->err.p, sizeof(e)));
+	TRY(stream_sync(ctx));
+	const char *names[] = {"hit order", "duplicate (pos,rpos)", "mixed strand", "rpos != pos + cigar2rlen", "junction without partial exon",
+		"reserved qid", "scratch capacity"};
+	for(int k = 0; k < 7; k++)
+	{
+		if(e[k] == 0) continue;
+		char buf[256];
+		snprintf(buf, sizeof(buf), "%s: %d violation(s) of: %s", stage, e[k], names[k]);
+		ctx->last_error = buf;
+		return (k == ERR_CAP) ? AGPU_ERR_CAPACITY : AGPU_ERR_INPUT;
+	}
+	return AGPU_OK;
+}
+
+template<typename T> static int pull(agpu_ctx *ctx, agpu_batch *b, const std::string &name, const T *dev, size_t n, T **out)
+{
+	T *h = b->host<T>(name, n);
+	if(!h) return AGPU_ERR_OOM;
+	*out = h;
+	if(n == 0 || dev == NULL) return AGPU_OK;
+	return d2h(ctx, h, dev, n * sizeof(T));
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+void agpu_default_params(agpu_params *p)
+{
+	p->library_type = AGPU_FR_FIRST;
+	p->min_junction_support = 1;
+	p->normal_junction_threshold = 10;
+	p->extend_junction_threshold = 20;
+	p->min_subregion_gap = 15;
+	p->min_subregion_length = 15;
+	p->max_reads_partition_gap = 10;
+	p->bridge_end_relaxing = 10;
+	p->bridge_dp_solution_size = 10;
+	p->bridge_dp_stack_size = 5;
+	p->insertsize_low = 80;
+	p->insertsize_high = 500;
+	p->max_group_size = 200;
+	p->max_num_junctions_to_combine = 500;
+	p->min_subregion_overlap = 1.5;
+	p->min_guaranteed_edge_weight = 0.01;
+	p->min_grouping_similarity = 0.10;
+	p->max_grouping_similarity = 0.80;
+}
+
+int agpu_create(int device, void *stream, agpu_ctx **out)
+{
+	if(!out) return AGPU_ERR_ARG;
+	*out = NULL;
+	agpu_ctx *ctx = new (std::nothrow) agpu_ctx;
+	if(!ctx) return AGPU_ERR_OOM;
+	ctx->device = device;
+	ctx->launches = 0;
+	ctx->own_stream = false;
+	ctx->stream = (cudaStream_t)stream;
+	ctx->sm_count = 148;
+#ifndef AGPU_EMU
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { delete ctx; cudaGetLastError(); return AGPU_ERR_CUDA; }
+	if(cudaSetDevice(device) != cudaSuccess) { delete ctx; return AGPU_ERR_CUDA; }
+	cudaDeviceProp prop;
+	if(cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+	if(stream == NULL)
+	{
+		if(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGPU_ERR_CUDA; }
+		ctx->own_stream = true;
+	}
+	// keep freed blocks in the pool: the stages allocate and free stream-ordered scratch all the time
+	cudaMemPool_t pool;
+	if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+	{
+		uint64_t thr = ~0ULL;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+	}
+#endif
+	*out = ctx;
+	return AGPU_OK;
+}
+
+void agpu_destroy(agpu_ctx *ctx)
+{
+	if(!ctx) return;
+#ifndef AGPU_EMU
+	cudaStreamSynchronize(ctx->stream);
+	if(ctx->own_stream) cudaStreamDestroy(ctx->stream);
+#endif
+	delete ctx;
+}
+
+const char *agpu_last_error(agpu_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+int agpu_sync(agpu_ctx *ctx) { return ctx ? stream_sync(ctx) : AGPU_ERR_ARG; }
+int64_t agpu_launch_count(agpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int batch_common(agpu_ctx *ctx, agpu_batch *b)
+{
+	TRY(b->err.alloc(ctx, ERR_WORDS, true));
+	return AGPU_OK;
+}
+
+int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
+{
+	if(!ctx || !in || !out || in->n_bundles < 0 || in->n_hits < 0) return AGPU_ERR_ARG;
+	*out = NULL;
+	agpu_batch *b = new (std::nothrow) agpu_batch;
+	if(!b) return AGPU_ERR_OOM;
+	b->nb = in->n_bundles; b->nh = in->n_hits; b->nc = in->n_cigar;
+	b->owns_input = true;
+	b->hit_off_host.assign(in->bundle_hit_off, in->bundle_hit_off + b->nb + 1);
+	b->tid_host.assign(in->bundle_tid, in->bundle_tid + b->nb);
+	if(in->bundle_sample) b->sample_host.assign(in->bundle_sample, in->bundle_sample + b->nb);
+	int rc = AGPU_OK;
+#define UP(buf, src, count) do { if(rc == AGPU_OK) rc = b->buf.alloc(ctx, (size_t)(count) + 1); if(rc == AGPU_OK) rc = h2d(ctx, b->buf.p, src, sizeof(*(src)) * (size_t)(count)); } while(0)
+	UP(in_hit_off, in->bundle_hit_off, b->nb + 1);
+	UP(in_pos, in->pos, b->nh); UP(in_rpos, in->rpos, b->nh); UP(in_mpos, in->mpos, b->nh); UP(in_isize, in->isize, b->nh);
+	UP(in_flag, in->flag, b->nh); UP(in_strand, in->strand, b->nh); UP(in_xs, in->xs, b->nh); UP(in_qid, in->qid, b->nh);
+	UP(in_cigar_off, in->cigar_off, b->nh + 1); UP(in_cigar, in->cigar, b->nc);
+#undef UP
+	if(rc == AGPU_OK) rc = batch_common(ctx, b);
+	if(rc != AGPU_OK) { agpu_batch_free(ctx, b); return rc; }
+	b->h.n_hits = b->nh; b->h.n_bundles = b->nb;
+	b->h.bundle_hit_off = b->in_hit_off.p;
+	b->h.pos = b->in_pos.p; b->h.rpos = b->in_rpos.p; b->h.mpos = b->in_mpos.p; b->h.isize = b->in_isize.p;
+	b->h.flag = b->in_flag.p; b->h.strand = b->in_strand.p; b->h.xs = b->in_xs.p; b->h.qid = (const u64*)b->in_qid.p;
+	b->h.cigar_off = b->in_cigar_off.p; b->h.cigar = b->in_cigar.p;
+	*out = b;
+	return AGPU_OK;
+}
+
+int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
+{
+	if(!ctx || !in || !out || in->n_bundles < 0 || in->n_hits < 0) return AGPU_ERR_ARG;
+	*out = NULL;
+	agpu_batch *b = new (std::nothrow) agpu_batch;
+	if(!b) return AGPU_ERR_OOM;
+	b->nb = in->n_bundles; b->nh = in->n_hits; b->nc = in->n_cigar;
+	b->owns_input = false;
+	b->hit_off_host.resize(b->nb + 1);
+	b->tid_host.resize(b->nb);
+	int rc = d2h(ctx, b->hit_off_host.data(), in->bundle_hit_off, sizeof(int64_t) * (b->nb + 1));
+	if(rc == AGPU_OK) rc = d2h(ctx, b->tid_host.data(), in->bundle_tid, sizeof(int32_t) * b->nb);
+	if(rc == AGPU_OK) rc = stream_sync(ctx);
+	if(rc == AGPU_OK) rc = batch_common(ctx, b);
+	if(rc != AGPU_OK) { agpu_batch_free(ctx, b); return rc; }
+	b->h.n_hits = b->nh; b->h.n_bundles = b->nb;
+	b->h.bundle_hit_off = in->bundle_hit_off;
+	b->h.pos = in->pos; b->h.rpos = in->rpos; b->h.mpos = in->mpos; b->h.isize = in->isize;
+	b->h.flag = in->flag; b->h.strand = in->strand; b->h.xs = in->xs; b->h.qid = (const u64*)in->qid;
+	b->h.cigar_off = in->cigar_off; b->h.cigar = in->cigar;
+	*out = b;
+	return AGPU_OK;
+}
+
+static void release_derived(agpu_ctx *ctx, agpu_batch *b)
+{
+	b->b_lpos.release(ctx); b->b_rpos.release(ctx); b->b_covhi.release(ctx); b->b_strand.release(ctx);
+	b->b_span.release(ctx); b->cov_base.release(ctx); b->diff.release(ctx); b->border.release(ctx);
+	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx); b->hit_hash.release(ctx);
+	b->hcst.release(ctx); b->fcst.release(ctx);
+	b->tile_sum.release(ctx); b->tile_cnt.release(ctx); b->tile_pre.release(ctx); b->tile_seg_off.release(ctx); b->seg_off.release(ctx);
+	b->seg_l.release(ctx); b->seg_r.release(ctx); b->seg_c.release(ctx);
+	b->frg.release(ctx); b->gr.release(ctx); b->clu.release(ctx); b->brg.release(ctx);
+	b->evidence = false; b->cov_dirty = true; b->n_seg = 0; b->ltot = 0;
+}
+
+void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
+{
+	if(!ctx || !b) return;
+	release_derived(ctx, b);
+	b->in_hit_off.release(ctx); b->in_pos.release(ctx); b->in_rpos.release(ctx); b->in_mpos.release(ctx); b->in_isize.release(ctx);
+	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
+	b->in_cigar_off.release(ctx); b->in_cigar.release(ctx);
+	b->err.release(ctx);
+	stream_sync(ctx);
+	for(auto &r : b->pinned) r.second.release();
+	delete b;
+}
+
+int agpu_batch_reset(agpu_ctx *ctx, agpu_batch *b)
+{
+	if(!ctx || !b) return AGPU_ERR_ARG;
+	release_derived(ctx, b);
+	TRY(b->err.fill(ctx, 0));
+	return AGPU_OK;
+}
+
+// ---- chain set construction shared by hcst (elements = hits) and fcst (elements = fragments)
+static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int64_t n_elem, const int64_t *d_elem_off,
+		const std::vector<int64_t> &elem_off_host)
+{
+	int nb = b->nb;
+	cs.n_elem = n_elem;
+	cs.d_elem_off = d_elem_off;
+	std::vector<int64_t> reg(nb + 1);
+	reg[0] = 0;
+	for(int k = 0; k < nb; k++)
+	{
+		int64_t ne = elem_off_host[k + 1] - elem_off_host[k];
+		reg[k + 1] = reg[k] + (int64_t)pow2_ceil((u32)std::max<int64_t>(2 * ne, 2));
+	}
+	cs.n_slots = reg[nb];
+	TRY(cs.reg_off.alloc(ctx, nb + 1));
+	TRY(h2d(ctx, cs.reg_off.p, reg.data(), sizeof(int64_t) * (nb + 1)));
+	TRY(stream_sync(ctx));                 // `reg` is pageable stack-owned memory
+	TRY(cs.slot_word.alloc(ctx, cs.n_slots, true));
+	TRY(cs.slot_first.alloc(ctx, cs.n_slots)); TRY(cs.slot_first.fill(ctx, 0x7f));
+	TRY(cs.slot_cnt.alloc(ctx, cs.n_slots * 3, true));
+	TRY(cs.slot_chain.alloc(ctx, cs.n_slots));
+	TRY(cs.elem_slot.alloc(ctx, n_elem));
+	TRY(cs.n_chains.alloc(ctx, nb, true)); TRY(cs.n_splices.alloc(ctx, nb, true));
+	TRY(cs.c_rep.alloc(ctx, n_elem)); TRY(cs.c_cnt.alloc(ctx, n_elem * 3)); TRY(cs.c_grp.alloc(ctx, n_elem)); TRY(cs.c_slot.alloc(ctx, n_elem));
+	TRY(cs.handle_chain.alloc(ctx, n_elem));
+	TRY(cs.key_scratch.alloc(ctx, n_elem));
+	return AGPU_OK;
+}
+
+static int chainset_finish(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int64_t n_val)
+{
+	int nb = b->nb;
+	LAUNCH_B(ctx, k_chain_order, nb, 128, nb, cs.d_elem_off, cs.elem_slot.p, cs.slot_first.p, cs.slot_cnt.p, cs.voff32, cs.voff64, cs.val,
+			cs.key_scratch.p, cs.slot_chain.p, cs.n_chains.p, cs.c_rep.p, cs.c_cnt.p, cs.c_grp.p, cs.c_slot.p);
+	TRY(cs.key_scratch2.alloc(ctx, 2 * n_val + 2));
+	TRY(cs.splices_scratch.alloc(ctx, n_val + 1));
+	LAUNCH_B(ctx, k_chain_splices, nb, 128, nb, cs.d_elem_off, cs.val_base.p, cs.n_chains.p, cs.c_rep.p, cs.c_cnt.p,
+			cs.elem_len, cs.voff32, cs.voff64, cs.val, cs.key_scratch2.p, cs.n_splices.p, cs.splices_scratch.p);
+	LAUNCH_T(ctx, k_handle_chain, cs.n_elem, cs.n_elem, cs.elem_slot.p, cs.slot_chain.p, cs.handle_chain.p);
+	cs.built = true;
+	return AGPU_OK;
+}
+
+// coverage difference array -> segments
+static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
+{
+	int64_t nt = b->ltot / COV_TILE;
+	TRY(b->tile_sum.alloc(ctx, nt + 1)); TRY(b->tile_cnt.alloc(ctx, nt + 1));
+	TRY(b->tile_pre.alloc(ctx, nt + 2)); TRY(b->tile_seg_off.alloc(ctx, nt + 2));
+	TRY(b->seg_off.alloc(ctx, b->nb + 1, true));
+	b->n_seg = 0;
+	if(nt > 0)
+	{
+		LAUNCH_B(ctx, k_cov_tile_sum, nt, 256, b->diff.p, nt, b->tile_sum.p);
+		LAUNCH_B(ctx, k_scan_i32_to_i64, 1, 1024, b->tile_sum.p, b->tile_pre.p, nt);
+		LAUNCH_B(ctx, k_cov_segments, nt, 256, b->diff.p, b->border.p, nt, b->tile_pre.p, 0, b->tile_cnt.p, b->tile_seg_off.p,
+				b->nb, b->cov_base.p, b->b_lpos.p, (int32_t*)NULL, (int32_t*)NULL, (int32_t*)NULL);
+		LAUNCH_B(ctx, k_scan_i32_to_i64, 1, 1024, b->tile_cnt.p, b->tile_seg_off.p, nt);
+		TRY(d2h(ctx, &b->n_seg, b->tile_seg_off.p + nt, sizeof(int64_t)));
+		TRY(stream_sync(ctx));
+	}
+	TRY(b->seg_l.alloc(ctx, b->n_seg + 1)); TRY(b->seg_r.alloc(ctx, b->n_seg + 1)); TRY(b->seg_c.alloc(ctx, b->n_seg + 1));
+	if(nt > 0)
+	{
+		LAUNCH_B(ctx, k_cov_segments, nt, 256, b->diff.p, b->border.p, nt, b->tile_pre.p, 1, b->tile_cnt.p, b->tile_seg_off.p,
+				b->nb, b->cov_base.p, b->b_lpos.p, b->seg_l.p, b->seg_r.p, b->seg_c.p);
+		LAUNCH_T(ctx, k_seg_off, b->nb + 1, b->nb, b->cov_base.p, b->tile_seg_off.p, b->seg_off.p);
+	}
+	b->cov_dirty = false;
+	return AGPU_OK;
+}
+
+int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
+{
+	if(!ctx || !b || !p) return AGPU_ERR_ARG;
+	if(b->evidence) return AGPU_OK;
+	int nb = b->nb;
+	int64_t nh = b->nh, nc = b->nc;
+	TRY(b->b_lpos.alloc(ctx, nb + 1)); TRY(b->b_rpos.alloc(ctx, nb + 1)); TRY(b->b_covhi.alloc(ctx, nb + 1));
+	TRY(b->b_strand.alloc(ctx, nb + 1)); TRY(b->b_span.alloc(ctx, nb + 1)); TRY(b->cov_base.alloc(ctx, nb + 2));
+	LAUNCH_B(ctx, k_bundle_bounds, nb, 128, b->h, p->library_type, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, b->b_strand.p, b->b_span.p, b->err.p);
+	LAUNCH_B(ctx, k_scan_i64, 1, 1024, b->b_span.p, b->cov_base.p, nb);
+	b->ltot = 0;
+	TRY(d2h(ctx, &b->ltot, b->cov_base.p + nb, sizeof(int64_t)));
+	TRY(stream_sync(ctx));
+	TRY(b->diff.alloc(ctx, b->ltot + COV_TILE, true));
+	TRY(b->border.alloc(ctx, b->ltot / 32 + COV_TILE, true));
+	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1)); TRY(b->hit_bundle.alloc(ctx, nh + 1)); TRY(b->hit_hash.alloc(ctx, nh + 1));
+	LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->diff.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_hash.p,
+			b->hit_bundle.p, b->err.p);
+	// hcst
+	chainset_state &cs = b->hcst;
+	cs.val = b->spl.p; cs.voff32 = b->h.cigar_off; cs.voff64 = NULL; cs.elem_len = b->hit_nspl.p;
+	TRY(chainset_build(ctx, b, cs, nh, b->h.bundle_hit_off, b->hit_off_host));
+	LAUNCH_T(ctx, k_hcst_insert, nh, b->h, b->hit_nspl.p, b->hit_hash.p, b->hit_bundle.p, b->spl.p, cs.reg_off.p, cs.slot_word.p,
+			cs.slot_first.p, cs.slot_cnt.p, cs.elem_slot.p, b->err.p);
+	TRY(cs.val_base.alloc(ctx, nb + 1));
+	LAUNCH_T(ctx, k_gather_off, nb + 1, nb + 1, b->h.bundle_hit_off, b->h.cigar_off, cs.val_base.p);
+	TRY(chainset_finish(ctx, b, cs, nc));
+	TRY(coverage_scan(ctx, b));
+	b->evidence = true;
+	return check_err(ctx, b, "agpu_batch_evidence");
+}
+
+int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
+{
+	if(!ctx || !b || !p) return AGPU_ERR_ARG;
+	if(!b->evidence) return AGPU_ERR_ARG;
+	if(b->cov_dirty) TRY(coverage_scan(ctx, b));
+	graph_state &gs = b->gr;
+	gs.release(ctx);
+	int nb = b->nb;
+	graph_in in;
+	in.n = nb; in.lpos = b->b_lpos.p; in.rpos = b->b_rpos.p; in.strand = b->b_strand.p;
+	in.hc = b->hcst.view(); in.fc = b->fcst.view();
+	in.seg_off = b->seg_off.p; in.seg_l = b->seg_l.p; in.seg_r = b->seg_r.p; in.seg_c = b->seg_c.p;
+	for(int k = 0; k < 5; k++) { TRY(gs.ub[k].alloc(ctx, nb + 1)); TRY(gs.off[k].alloc(ctx, nb + 2)); }
+	LAUNCH_B(ctx, k_graph_bounds, nb, 128, in, gs.ub[0].p, gs.ub[1].p, gs.ub[2].p, gs.ub[3].p, gs.ub[4].p);
+	for(int k = 0; k < 5; k++)
+	{
+		LAUNCH_B(ctx, k_scan_i64, 1, 1024, gs.ub[k].p, gs.off[k].p, nb);
+		TRY(d2h(ctx, &gs.tot[k], gs.off[k].p + nb, sizeof(int64_t)));
+	}
+	TRY(stream_sync(ctx));
+	int64_t J = gs.tot[0], P = gs.tot[1], E = gs.tot[2];
+	int64_t V = P + 2 * (int64_t)nb, VO = P + 3 * (int64_t)nb;
+	TRY(gs.iarena.alloc(ctx, gs.tot[3] + 16)); TRY(gs.karena.alloc(ctx, gs.tot[4] + 16));
+	TRY(gs.n_junc.alloc(ctx, nb + 1, true)); TRY(gs.n_pex.alloc(ctx, nb + 1, true)); TRY(gs.n_edge.alloc(ctx, nb + 1, true));
+	for(int k = 0; k < 9; k++) TRY(gs.j[k].alloc(ctx, J + 1));
+	for(int k = 0; k < 6; k++) { TRY(gs.p_i[k].alloc(ctx, P + 1)); TRY(gs.v_i[k].alloc(ctx, V + 1)); }
+	for(int k = 0; k < 3; k++) { TRY(gs.p_d[k].alloc(ctx, P + 1)); TRY(gs.v_d[k].alloc(ctx, V + 1)); TRY(gs.e_i[k].alloc(ctx, E + 1)); }
+	TRY(gs.e_w.alloc(ctx, E + 1));
+	TRY(gs.in_off.alloc(ctx, VO + 1)); TRY(gs.in_src.alloc(ctx, E + 1)); TRY(gs.in_eid.alloc(ctx, E + 1));
+	TRY(gs.out_off.alloc(ctx, VO + 1)); TRY(gs.out_dst.alloc(ctx, E + 1)); TRY(gs.out_eid.alloc(ctx, E + 1));
+	graph_params gp;
+	gp.min_junction_support = p->min_junction_support;
+	gp.min_subregion_gap = p->min_subregion_gap; gp.min_subregion_length = p->min_subregion_length;
+	gp.min_subregion_overlap = p->min_subregion_overlap; gp.min_guaranteed_edge_weight = p->min_guaranteed_edge_weight;
+	LAUNCH_B(ctx, k_graph_build, nb, 128, in, gs.dev(b->err.p), gp);
+	gs.built = true;
+	return check_err(ctx, b, "agpu_batch_graph");
+}
+
+#include "abi_stages.inc"
+#include "abi_fetch.inc"
+
+}

@@ -1,0 +1,501 @@
+// Stage 1-2a kernels: per-hit CIGAR walk (coverage difference array + border bitmap, splice
+// extraction, chain hashing), chain-set construction, coverage scan -> segments.
+//
+// Reference semantics reproduced:
+//   bundle_base::add_hit            rnacore/bundle_base.cc:73-104   (bundle bounds, dedupe contract)
+//   bundle_base::add_intervals      rnacore/bundle_base.cc:106-158  (only BAM_CMATCH adds coverage)
+//   hit::extract_splices            rnacore/hit.cc:77-104
+//   chain_set::add(v, h, xs)        rnacore/chain_set.cc:64-123     (insertion order, AI3 counts)
+//   chain_set::get_splices          rnacore/chain_set.cc:187-210
+//   split_interval_map semantics    rnacore/interval_map.h:31       (every inserted border is kept;
+//                                                                    zero-valued stretches are absent)
+#ifndef ALETSCH_B200_CSRC_K_EVIDENCE_H
+#define ALETSCH_B200_CSRC_K_EVIDENCE_H
+
+#include "dev.h"
+#include "blockops.h"
+
+namespace agpu {
+
+#define COV_TILE 2048            // coverage positions per scan tile; bundle bases are tile-aligned
+#define EMPTY_SLOT 0ULL
+#define INT_BIG 0x7fffffff
+
+struct hits_dev
+{
+	int64_t n_hits;
+	int32_t n_bundles;
+	const int64_t *bundle_hit_off;
+	const int32_t *pos, *rpos, *mpos, *isize;
+	const uint16_t *flag;
+	const uint8_t *strand, *xs;
+	const u64 *qid;
+	const u32 *cigar_off;
+	const u32 *cigar;
+};
+
+// error / statistics words shared by all kernels of a batch
+enum { ERR_ORDER = 0, ERR_DUP, ERR_STRAND, ERR_RPOS, ERR_LINK, ERR_QID, ERR_CAP, ERR_WORDS = 16 };
+
+// ---- E0: bundle bounds (bundle_base::add_hit) + packing-contract check; one CTA per bundle
+KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b_rpos, int32_t *b_covhi,
+		uint8_t *b_strand, int64_t *b_span, int *err)
+{
+	SHARED int s_min, s_max, s_cov, s_np, s_nq;
+	for(int b = blockIdx.x; b < h.n_bundles; b += gridDim.x)
+	{
+		int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
+		if(threadIdx.x == 0) { s_min = 1 << 30; s_max = 0; s_cov = 0; s_np = 0; s_nq = 0; }   // rnacore/bundle_base.cc:21-22
+		BLOCK_SYNC();
+		int lmin = 1 << 30, lmax = 0, lcov = 0, np = 0, nq = 0;
+		for(int64_t i = h0 + threadIdx.x; i < h1; i += blockDim.x)
+		{
+			int p = h.pos[i], r = h.rpos[i], m = h.mpos[i];
+			if(p < lmin) lmin = p;
+			int q = r;
+			if(m > r && m <= r + 500000) q = m;            // rnacore/bundle_base.cc:92
+			if(q > lmax) lmax = q;
+			if(r > lcov) lcov = r;
+			if(h.xs[i] == '+') np++;
+			if(h.xs[i] == '-') nq++;
+			if(i > h0)
+			{
+				if(h.pos[i - 1] > p) atomicAdd(&err[ERR_ORDER], 1);
+				if(h.pos[i - 1] == p && h.rpos[i - 1] == r) atomicAdd(&err[ERR_DUP], 1);
+				if(h.strand[i] != h.strand[h0]) atomicAdd(&err[ERR_STRAND], 1);
+			}
+		}
+		atomicMin(&s_min, lmin); atomicMax(&s_max, lmax); atomicMax(&s_cov, lcov);
+		atomicAdd(&s_np, np); atomicAdd(&s_nq, nq);
+		BLOCK_SYNC();
+		if(threadIdx.x == 0)
+		{
+			b_lpos[b] = s_min;
+			b_rpos[b] = s_max;
+			b_covhi[b] = s_cov;
+			uint8_t st = '.';
+			if(h1 > h0) st = h.strand[h0];                 // rnacore/bundle_base.cc:100
+			if(library_type == 0)                          // bundle_base::compute_strand, rnacore/bundle_base.cc:205-225
+			{
+				if(s_np > s_nq) st = '+';
+				else if(s_np < s_nq) st = '-';
+				else st = '.';
+			}
+			b_strand[b] = st;
+			// positions [lpos, covhi] inclusive (the -1 of a block ending at covhi lands there), tile-aligned
+			int64_t span = (h1 > h0) ? ((int64_t)s_cov - (int64_t)s_min + 1) : 0;
+			b_span[b] = (span + COV_TILE - 1) / COV_TILE * COV_TILE;
+		}
+		BLOCK_SYNC();
+	}
+}
+
+// ---- generic single-CTA exclusive scan of int64 (NB-sized arrays); out[n] = total
+KERNEL k_scan_i64(const int64_t *in, int64_t *out, int n)
+{
+	SHARED int64_t part[AGPU_MAX_BLOCK];
+	int nt = blockDim.x, t = threadIdx.x;
+	int chunk = (n + nt - 1) / nt;
+	int lo = t * chunk, hi = lo + chunk;
+	if(lo > n) lo = n;
+	if(hi > n) hi = n;
+	int64_t s = 0;
+	for(int i = lo; i < hi; i++) s += in[i];
+	part[t] = s;
+	BLOCK_SYNC();
+	if(t == 0)
+	{
+		int64_t run = 0;
+		for(int k = 0; k < nt; k++) { int64_t v = part[k]; part[k] = run; run += v; }
+		out[n] = run;
+	}
+	BLOCK_SYNC();
+	int64_t run = part[t];
+	for(int i = lo; i < hi; i++) { int64_t v = in[i]; out[i] = run; run += v; }
+}
+
+// hash of one intron chain (length + coordinates)
+HD u64 chain_hash(const int32_t *v, int n)
+{
+	u64 hsh = mix64((u64)n);
+	for(int k = 0; k < n; k++) hsh = mix64(hsh ^ (u64)(u32)v[k]);
+	return hsh;
+}
+
+// ---- E2: one thread per hit: CIGAR walk
+//   coverage: +1 at the start and -1 at the end of every BAM_CMATCH block, border bits at both
+//   splices : (p - len, p) for every inner BAM_CREF_SKIP, written at spl[cigar_off[i] ...]
+KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, int32_t *diff, u32 *border,
+		int32_t *spl, int32_t *hit_nspl, u64 *hit_hash, int32_t *hit_bundle, int *err)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	int b = find_segment(h.bundle_hit_off, h.n_bundles, i);
+	hit_bundle[i] = b;
+	int64_t base = cov_base[b] - (int64_t)b_lpos[b];
+	u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
+	int32_t p = h.pos[i];
+	int ns = 0;
+	int32_t *out = spl + c0;
+	for(u32 k = c0; k < c1; k++)
+	{
+		u32 c = h.cigar[k];
+		u32 op = c & 0xf, len = c >> 4;
+		if((0x3C1A7 >> (op << 1)) & 2) p += (int32_t)len;      // bam_cigar_type: consumes reference
+		if(op == 0)                                            // BAM_CMATCH
+		{
+			int64_t s = base + p - (int32_t)len, e = base + p;
+			if(len > 0)
+			{
+				atomicAdd(&diff[s], 1);
+				atomicAdd(&diff[e], -1);
+				atomicOr(&border[s >> 5], 1u << (s & 31));
+				atomicOr(&border[e >> 5], 1u << (e & 31));
+			}
+		}
+		if(op == 3 && k != c0 && k != c1 - 1)                  // BAM_CREF_SKIP, not first / last op
+		{
+			out[ns++] = p - (int32_t)len;
+			out[ns++] = p;
+		}
+	}
+	if(p != h.rpos[i]) atomicAdd(&err[ERR_RPOS], 1);
+	hit_nspl[i] = ns;
+	hit_hash[i] = ns > 0 ? chain_hash(out, ns) : 0;
+}
+
+// ---- chain table: one open-addressing region per bundle; slot word = hash32 << 32 | (rep + 1)
+// `rep` is the global index of the element that claimed the slot; equality is verified on the
+// actual coordinates, so hash collisions only cost a probe.
+struct chain_src
+{
+	const int32_t *val;        // coordinates
+	const int64_t *off;        // element e owns val[off[e] .. off[e] + len[e])   (NULL: use off32)
+	const u32 *off32;
+	const int32_t *len;
+	HD const int32_t *ptr(int64_t e) const { return val + (off ? off[e] : (int64_t)off32[e]); }
+};
+
+HD bool same_chain(const chain_src &s, int64_t a, int64_t b)
+{
+	int n = s.len[a];
+	if(n != s.len[b]) return false;
+	const int32_t *x = s.ptr(a), *y = s.ptr(b);
+	for(int k = 0; k < n; k++) if(x[k] != y[k]) return false;
+	return true;
+}
+
+// returns the slot (global index) holding the chain of element e, inserting it if new
+DEV int64_t chain_table_insert(u64 *slot_word, int64_t reg0, u32 reg_size, const chain_src &s, int64_t e, u64 hsh)
+{
+	u32 mask = reg_size - 1;
+	u32 pos = (u32)(hsh >> 7) & mask;
+	u64 mine = ((hsh >> 32) << 32) | (u64)(u32)(e + 1);
+	for(u32 probe = 0; probe <= mask; probe++)
+	{
+		u64 cur = atomicCAS(&slot_word[reg0 + pos], (u64)EMPTY_SLOT, mine);
+		if(cur == EMPTY_SLOT) return reg0 + pos;
+		if((cur >> 32) == (mine >> 32))
+		{
+			int64_t rep = (int64_t)(u32)(cur & 0xffffffffULL) - 1;
+			if(same_chain(s, rep, e)) return reg0 + pos;
+		}
+		pos = (pos + 1) & mask;
+	}
+	return -1;
+}
+
+// ---- E3: one thread per hit with splices: insert into hcst table, count xs class, track first hit
+KERNEL k_hcst_insert(hits_dev h, const int32_t *hit_nspl, const u64 *hit_hash, const int32_t *hit_bundle, const int32_t *spl,
+		const int64_t *reg_off, u64 *slot_word, int32_t *slot_first, int32_t *slot_cnt, int64_t *hit_slot, int *err)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	hit_slot[i] = -1;
+	if(hit_nspl[i] <= 0) return;
+	int b = hit_bundle[i];
+	chain_src s;
+	s.val = spl; s.off = NULL; s.off32 = h.cigar_off; s.len = hit_nspl;
+	int64_t r0 = reg_off[b];
+	u32 rs = (u32)(reg_off[b + 1] - r0);
+	int64_t sl = chain_table_insert(slot_word, r0, rs, s, i, hit_hash[i]);
+	if(sl < 0) { atomicAdd(&err[ERR_CAP], 1); return; }
+	hit_slot[i] = sl;
+	int x = 0;
+	if(h.xs[i] == '+') x = 1;
+	if(h.xs[i] == '-') x = 2;
+	atomicAdd(&slot_cnt[sl * 3 + x], 1);
+	atomicMin(&slot_first[sl], (int32_t)(i - h.bundle_hit_off[b]));
+}
+
+// ---- E4: per bundle: order the chains the way chain_set::add leaves them
+// (groups by first appearance of the first coordinate, chains by first appearance), number
+// them, and build the sorted unique splice list.
+KERNEL k_chain_order(int32_t n_bundles, const int64_t *elem_off, const int64_t *hit_slot, const int32_t *slot_first,
+		const int32_t *slot_cnt, const u32 *elem_voff32, const int64_t *elem_voff64, const int32_t *val,
+		u64 *key_scratch, int32_t *slot_chain,
+		int32_t *n_chains, int32_t *c_rep, int32_t *c_cnt, int32_t *c_grp, int64_t *c_slot)
+{
+	SHARED int s_n;
+	for(int b = blockIdx.x; b < n_bundles; b += gridDim.x)
+	{
+		int64_t e0 = elem_off[b], e1 = elem_off[b + 1];
+		int ne = (int)(e1 - e0);
+		u64 *key = key_scratch + e0;
+		int32_t *tmp = c_grp + e0;
+		if(threadIdx.x == 0) s_n = 0;
+		BLOCK_SYNC();
+		// chain heads: elements that are the first appearance of their chain
+		for(int i = threadIdx.x; i < ne; i += blockDim.x)
+		{
+			int64_t sl = hit_slot[e0 + i];
+			if(sl >= 0 && slot_first[sl] == i)
+			{
+				int k = atomicAdd(&s_n, 1);
+				const int32_t *v = val + (elem_voff64 ? elem_voff64[e0 + i] : (int64_t)elem_voff32[e0 + i]);
+				key[k] = ((u64)(u32)v[0] << 32) | (u64)(u32)i;        // (first coordinate, first element)
+			}
+		}
+		BLOCK_SYNC();
+		int nc = s_n;
+		block_sort_u64(key, nc);
+		// a group's rank is the first element that opened it = low word of the group's first key
+		for(int k = threadIdx.x; k < nc; k += blockDim.x)
+			tmp[k] = (k == 0 || (key[k - 1] >> 32) != (key[k] >> 32)) ? k : 0;
+		BLOCK_SYNC();
+		block_incl_maxscan(tmp, nc);
+		for(int k = threadIdx.x; k < nc; k += blockDim.x)
+			c_rep[e0 + k] = (int32_t)(u32)(key[tmp[k]] & 0xffffffffULL);
+		BLOCK_SYNC();
+		for(int k = threadIdx.x; k < nc; k += blockDim.x)
+			key[k] = ((u64)(u32)c_rep[e0 + k] << 32) | (key[k] & 0xffffffffULL);   // (group first element, chain first element)
+		BLOCK_SYNC();
+		block_sort_u64(key, nc);
+		// dense group index = number of group changes up to and including k
+		for(int k = threadIdx.x; k < nc; k += blockDim.x)
+			tmp[k] = (k > 0 && (key[k - 1] >> 32) != (key[k] >> 32)) ? 1 : 0;
+		BLOCK_SYNC();
+		block_excl_scan(tmp, nc);
+		for(int k = threadIdx.x; k < nc; k += blockDim.x)
+		{
+			int rep = (int)(u32)(key[k] & 0xffffffffULL);
+			int64_t sl = hit_slot[e0 + rep];
+			int chg = (k > 0 && (key[k - 1] >> 32) != (key[k] >> 32)) ? 1 : 0;
+			c_rep[e0 + k] = rep;
+			c_slot[e0 + k] = sl;
+			c_cnt[(e0 + k) * 3 + 0] = slot_cnt[sl * 3 + 0];
+			c_cnt[(e0 + k) * 3 + 1] = slot_cnt[sl * 3 + 1];
+			c_cnt[(e0 + k) * 3 + 2] = slot_cnt[sl * 3 + 2];
+			slot_chain[sl] = k;
+			tmp[k] = tmp[k] + chg;
+		}
+		if(threadIdx.x == 0) n_chains[b] = nc;
+		BLOCK_SYNC();
+	}
+}
+
+// per bundle: sorted unique coordinates over all chains with a positive count (chain_set::get_splices)
+// scratch regions start at 2 * val_base[b]: n keys followed by n flags
+KERNEL k_chain_splices(int32_t n_bundles, const int64_t *elem_off, const int64_t *val_base,
+		const int32_t *n_chains, const int32_t *c_rep, const int32_t *c_cnt,
+		const int32_t *elem_len, const u32 *elem_voff32, const int64_t *elem_voff64, const int32_t *val,
+		u64 *key_scratch, int32_t *n_splices, int32_t *splices_scratch)
+{
+	SHARED int s_n;
+	for(int b = blockIdx.x; b < n_bundles; b += gridDim.x)
+	{
+		int64_t e0 = elem_off[b];
+		int nc = n_chains[b];
+		u64 *key = key_scratch + 2 * val_base[b];
+		if(threadIdx.x == 0) s_n = 0;
+		BLOCK_SYNC();
+		for(int k = threadIdx.x; k < nc; k += blockDim.x)
+		{
+			int64_t e = e0 + c_rep[e0 + k];
+			if(c_cnt[(e0 + k) * 3] + c_cnt[(e0 + k) * 3 + 1] + c_cnt[(e0 + k) * 3 + 2] <= 0) continue;
+			const int32_t *v = val + (elem_voff64 ? elem_voff64[e] : (int64_t)elem_voff32[e]);
+			int n = elem_len[e];
+			int at = atomicAdd(&s_n, n);
+			for(int j = 0; j < n; j++) key[at + j] = (u64)(u32)v[j];
+		}
+		BLOCK_SYNC();
+		int n = s_n;
+		block_sort_u64(key, n);
+		int *flag = (int*)(key + n);
+		for(int i = threadIdx.x; i < n; i += blockDim.x) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+		BLOCK_SYNC();
+		int tot = block_excl_scan(flag, n);
+		int32_t *out = splices_scratch + val_base[b];
+		for(int i = threadIdx.x; i < n; i += blockDim.x)
+			if(i == 0 || key[i] != key[i - 1]) out[flag[i]] = (int32_t)(u32)key[i];
+		if(threadIdx.x == 0) n_splices[b] = tot;
+		BLOCK_SYNC();
+	}
+}
+
+// per element: handle -> bundle-local chain index
+KERNEL k_handle_chain(int64_t n, const int64_t *hit_slot, const int32_t *slot_chain, int32_t *handle_chain)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	int64_t sl = hit_slot[i];
+	handle_chain[i] = sl >= 0 ? slot_chain[sl] : -1;
+}
+
+KERNEL k_gather_off(int64_t n, const int64_t *idx, const u32 *src, int64_t *out)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	out[i] = (int64_t)src[idx[i]];
+}
+
+KERNEL k_seg_off(int32_t nb, const int64_t *cov_base, const int64_t *tile_seg_off, int64_t *seg_off)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i > nb) return;
+	seg_off[i] = tile_seg_off[cov_base[i] / COV_TILE];
+}
+
+// ---- coverage scan: diff -> coverage, segments = [border_k, border_k+1) with coverage > 0
+KERNEL k_cov_tile_sum(const int32_t *diff, int64_t n_tiles, int32_t *tile_sum)
+{
+	SHARED int s;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		if(threadIdx.x == 0) s = 0;
+		BLOCK_SYNC();
+		int acc = 0;
+		const int32_t *d = diff + t * COV_TILE;
+		for(int i = threadIdx.x; i < COV_TILE; i += blockDim.x) acc += d[i];
+		atomicAdd(&s, acc);
+		BLOCK_SYNC();
+		if(threadIdx.x == 0) tile_sum[t] = s;
+		BLOCK_SYNC();
+	}
+}
+
+// single CTA: exclusive scan of int32 array of length n into int64 out (out[n] = total)
+KERNEL k_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n)
+{
+	SHARED int64_t part[AGPU_MAX_BLOCK];
+	int nt = blockDim.x, t = threadIdx.x;
+	int64_t chunk = (n + nt - 1) / nt;
+	int64_t lo = t * chunk, hi = lo + chunk;
+	if(lo > n) lo = n;
+	if(hi > n) hi = n;
+	int64_t s = 0;
+	for(int64_t i = lo; i < hi; i++) s += in[i];
+	part[t] = s;
+	BLOCK_SYNC();
+	if(t == 0)
+	{
+		int64_t run = 0;
+		for(int k = 0; k < nt; k++) { int64_t v = part[k]; part[k] = run; run += v; }
+		out[n] = run;
+	}
+	BLOCK_SYNC();
+	int64_t run = part[t];
+	for(int64_t i = lo; i < hi; i++) { int64_t v = in[i]; out[i] = run; run += v; }
+}
+
+// per tile: coverage at every position (tile prefix + local scan), count / emit segment starts.
+// mode 0: count segment starts into tile_cnt; mode 1: emit segments at tile_seg_off.
+KERNEL k_cov_segments(const int32_t *diff, const u32 *border, int64_t n_tiles, const int64_t *tile_pre /* coverage before tile */,
+		int mode, int32_t *tile_cnt, const int64_t *tile_seg_off,
+		int32_t n_bundles, const int64_t *cov_base, const int32_t *b_lpos, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c)
+{
+	SHARED int cov[COV_TILE];
+	SHARED int flg[COV_TILE];
+	SHARED int s_cnt;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		const int32_t *d = diff + t * COV_TILE;
+		for(int i = threadIdx.x; i < COV_TILE; i += blockDim.x) cov[i] = d[i];
+		BLOCK_SYNC();
+		// inclusive scan of the tile: chunk per thread
+		{
+			int nt = blockDim.x, th = threadIdx.x;
+			int chunk = (COV_TILE + nt - 1) / nt;
+			int lo = th * chunk, hi = lo + chunk;
+			if(lo > COV_TILE) lo = COV_TILE;
+			if(hi > COV_TILE) hi = COV_TILE;
+			int s = 0;
+			for(int i = lo; i < hi; i++) s += cov[i];
+			flg[th] = s;
+			BLOCK_SYNC();
+			if(th == 0)
+			{
+				int run = (int)tile_pre[t];
+				for(int k = 0; k < nt; k++) { int v = flg[k]; flg[k] = run; run += v; }
+			}
+			BLOCK_SYNC();
+			int run = flg[th];
+			BLOCK_SYNC();
+			for(int i = lo; i < hi; i++) { run += cov[i]; cov[i] = run; }
+			BLOCK_SYNC();
+		}
+		const u32 *bw = border + t * (COV_TILE / 32);
+		for(int i = threadIdx.x; i < COV_TILE; i += blockDim.x)
+			flg[i] = (((bw[i >> 5] >> (i & 31)) & 1) && cov[i] > 0) ? 1 : 0;
+		BLOCK_SYNC();
+		if(mode == 0)
+		{
+			if(threadIdx.x == 0) s_cnt = 0;
+			BLOCK_SYNC();
+			int acc = 0;
+			for(int i = threadIdx.x; i < COV_TILE; i += blockDim.x) acc += flg[i];
+			atomicAdd(&s_cnt, acc);
+			BLOCK_SYNC();
+			if(threadIdx.x == 0) tile_cnt[t] = s_cnt;
+			BLOCK_SYNC();
+		}
+		else
+		{
+			// local ranks
+			int nt = blockDim.x, th = threadIdx.x;
+			int chunk = (COV_TILE + nt - 1) / nt;
+			int lo = th * chunk, hi = lo + chunk;
+			if(lo > COV_TILE) lo = COV_TILE;
+			if(hi > COV_TILE) hi = COV_TILE;
+			SHARED int part[AGPU_MAX_BLOCK];
+			int s = 0;
+			for(int i = lo; i < hi; i++) s += flg[i];
+			part[th] = s;
+			BLOCK_SYNC();
+			if(th == 0)
+			{
+				int run = 0;
+				for(int k = 0; k < nt; k++) { int v = part[k]; part[k] = run; run += v; }
+			}
+			BLOCK_SYNC();
+			int64_t gpos0 = t * COV_TILE;
+			int b = find_segment(cov_base, n_bundles, gpos0);
+			int64_t org = cov_base[b] - (int64_t)b_lpos[b];
+			int64_t end = cov_base[b + 1];
+			int rank = part[th];
+			for(int i = lo; i < hi; i++)
+			{
+				if(!flg[i]) continue;
+				int64_t o = tile_seg_off[t] + rank++;
+				int64_t g = gpos0 + i;
+				// next border after g (exists: coverage returns to 0 at a border inside the bundle)
+				int64_t q = g + 1;
+				int64_t r = -1;
+				while(q < end)
+				{
+					u32 w = border[q >> 5] >> (q & 31);
+					if(w) { r = q + (__ffs((int)w) - 1); break; }
+					q = ((q >> 5) + 1) << 5;
+				}
+				seg_l[o] = (int32_t)(g - org);
+				seg_r[o] = (int32_t)((r < 0 ? end : r) - org);
+				seg_c[o] = cov[i];
+			}
+			BLOCK_SYNC();
+		}
+	}
+}
+
+} // namespace agpu
+
+#endif

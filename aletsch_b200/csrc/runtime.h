@@ -1,0 +1,119 @@
+// Host-side runtime of libaletsch_gpu.so: context, stream-ordered device buffers, launch macros.
+#ifndef ALETSCH_B200_CSRC_RUNTIME_H
+#define ALETSCH_B200_CSRC_RUNTIME_H
+
+#include "dev.h"
+#include "../../include/aletsch_gpu.h"
+
+#include <string>
+#include <vector>
+
+struct agpu_ctx
+{
+	int device;
+	cudaStream_t stream;
+	bool own_stream;
+	int64_t launches;
+	std::string last_error;
+	int sm_count;
+};
+
+namespace agpu {
+
+#ifndef AGPU_EMU
+#define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_); return AGPU_ERR_CUDA; } } while(0)
+
+// per-thread kernel: grid covers n items
+#define LAUNCH_T(ctx, kern, n, ...) do { int64_t n_ = (int64_t)(n); if(n_ > 0) { unsigned g_ = (unsigned)((n_ + 255) / 256); \
+	kern<<<g_, 256, 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } } while(0)
+// block-cooperative kernel: one CTA per work item (the kernel loops if the grid is smaller)
+#define LAUNCH_B(ctx, kern, nblocks, nthreads, ...) do { int64_t n_ = (int64_t)(nblocks); if(n_ > 0) { unsigned g_ = (unsigned)(n_ > 1048576 ? 1048576 : n_); \
+	kern<<<g_, (nthreads), 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } } while(0)
+
+inline int dev_alloc_bytes(agpu_ctx *ctx, void **p, size_t bytes, bool zero)
+{
+	*p = NULL;
+	if(bytes == 0) bytes = 16;
+	cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+	if(e != cudaSuccess) { ctx->last_error = std::string("cudaMallocAsync: ") + cudaGetErrorString(e); cudaGetLastError(); return AGPU_ERR_OOM; }
+	if(zero) { e = cudaMemsetAsync(*p, 0, bytes, ctx->stream); if(e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); return AGPU_ERR_CUDA; } }
+	return AGPU_OK;
+}
+inline void dev_free_bytes(agpu_ctx *ctx, void *p) { if(p) cudaFreeAsync(p, ctx->stream); }
+inline int dev_fill(agpu_ctx *ctx, void *p, int byte, size_t bytes) { if(bytes == 0) return AGPU_OK; return cudaMemsetAsync(p, byte, bytes, ctx->stream) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA; }
+inline int h2d(agpu_ctx *ctx, void *d, const void *h, size_t bytes) { if(bytes == 0) return AGPU_OK; return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA; }
+inline int d2h(agpu_ctx *ctx, void *h, const void *d, size_t bytes) { if(bytes == 0) return AGPU_OK; return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA; }
+inline int d2d(agpu_ctx *ctx, void *d, const void *s, size_t bytes) { if(bytes == 0) return AGPU_OK; return cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA; }
+inline int stream_sync(agpu_ctx *ctx)
+{
+	cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	if(e != cudaSuccess) { ctx->last_error = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e); return AGPU_ERR_CUDA; }
+	e = cudaGetLastError();
+	if(e != cudaSuccess) { ctx->last_error = std::string("kernel launch: ") + cudaGetErrorString(e); return AGPU_ERR_CUDA; }
+	return AGPU_OK;
+}
+inline void *pinned_alloc(size_t bytes) { void *p = NULL; if(bytes == 0) bytes = 16; if(cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return NULL; } return p; }
+inline void pinned_free(void *p) { if(p) cudaFreeHost(p); }
+#else
+// ------------------------------------------------------------- kernel-logic test build (host)
+#define CUDA_TRY(ctx, call) do { (void)(call); } while(0)
+template<typename F, typename... A> inline void emu_launch(bool coop, F f, int64_t grid, unsigned block, A... a)
+{
+	gridDim.x = (unsigned)grid; gridDim.y = gridDim.z = 1;
+	blockDim.x = coop ? 1 : block; blockDim.y = blockDim.z = 1;
+	for(int64_t b = 0; b < grid; b++)
+	{
+		blockIdx.x = (unsigned)b; blockIdx.y = blockIdx.z = 0;
+		for(unsigned t = 0; t < blockDim.x; t++)
+		{
+			threadIdx.x = t; threadIdx.y = threadIdx.z = 0;
+			f(a...);
+		}
+	}
+}
+#define LAUNCH_T(ctx, kern, n, ...) do { int64_t n_ = (int64_t)(n); if(n_ > 0) { emu_launch(false, kern, (n_ + 255) / 256, 256, __VA_ARGS__); (ctx)->launches++; } } while(0)
+#define LAUNCH_B(ctx, kern, nblocks, nthreads, ...) do { int64_t n_ = (int64_t)(nblocks); if(n_ > 0) { emu_launch(true, kern, n_, (nthreads), __VA_ARGS__); (ctx)->launches++; } } while(0)
+inline int dev_alloc_bytes(agpu_ctx *, void **p, size_t bytes, bool zero) { if(bytes == 0) bytes = 16; *p = zero ? calloc(1, bytes) : malloc(bytes); return *p ? AGPU_OK : AGPU_ERR_OOM; }
+inline void dev_free_bytes(agpu_ctx *, void *p) { free(p); }
+inline int dev_fill(agpu_ctx *, void *p, int byte, size_t bytes) { memset(p, byte, bytes); return AGPU_OK; }
+inline int h2d(agpu_ctx *, void *d, const void *h, size_t bytes) { memcpy(d, h, bytes); return AGPU_OK; }
+inline int d2h(agpu_ctx *, void *h, const void *d, size_t bytes) { memcpy(h, d, bytes); return AGPU_OK; }
+inline int d2d(agpu_ctx *, void *d, const void *s, size_t bytes) { memcpy(d, s, bytes); return AGPU_OK; }
+inline int stream_sync(agpu_ctx *) { return AGPU_OK; }
+inline void *pinned_alloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
+inline void pinned_free(void *p) { free(p); }
+#endif
+
+// stream-ordered device array
+template<typename T> struct dbuf
+{
+	T *p = NULL;
+	size_t n = 0;
+	int alloc(agpu_ctx *ctx, size_t count, bool zero = false)
+	{
+		release(ctx);
+		n = count;
+		return dev_alloc_bytes(ctx, (void**)&p, count * sizeof(T), zero);
+	}
+	void release(agpu_ctx *ctx) { if(p) dev_free_bytes(ctx, p); p = NULL; n = 0; }
+	int fill(agpu_ctx *ctx, int byte) { return dev_fill(ctx, p, byte, n * sizeof(T)); }
+};
+
+// pinned host array (results)
+template<typename T> struct hbuf
+{
+	T *p = NULL;
+	size_t cap = 0;
+	T *ensure(size_t count)
+	{
+		if(count + 1 > cap) { pinned_free(p); cap = (count + 1) * 5 / 4 + 16; p = (T*)pinned_alloc(cap * sizeof(T)); }
+		return p;
+	}
+	void release() { pinned_free(p); p = NULL; cap = 0; }
+};
+
+#define TRY(x) do { int rc_ = (x); if(rc_ != AGPU_OK) return rc_; } while(0)
+
+} // namespace agpu
+
+#endif

@@ -1,0 +1,198 @@
+// Device-callable re-implementation of the PERMUTATION produced by libstdc++'s std::sort
+// (g++ 13, bits/stl_algo.h: __sort / __introsort_loop / __unguarded_partition_pivot /
+// __move_median_to_first / __final_insertion_sort; bits/stl_heap.h for the depth-limit
+// fallback).  The reference sorts with comparators that are only partial orders
+// (rnacore/graph_cluster.cc:183-186, bridge/bridge_solver.cc:525, :262, :272), and std::sort
+// is unstable above 16 elements, so the order of tied elements -- which leaks into
+// pereads_cluster::bounds, the K-cut of the bridging DP and the bridge chosen by vote -- is
+// whatever this exact algorithm leaves.  The permutation depends only on the input order and
+// on comparator outcomes, so running the same algorithm over an array of handles with the
+// same comparator reproduces it.
+#ifndef ALETSCH_B200_CSRC_STDSORT_H
+#define ALETSCH_B200_CSRC_STDSORT_H
+
+#include "dev.h"
+
+namespace agpu {
+
+// a[] holds handles; less(x, y) compares the elements the handles stand for
+template<typename Less>
+struct std_sort_emul
+{
+	int *a;
+	Less less;
+
+	HD std_sort_emul(int *arr, Less l) : a(arr), less(l) {}
+
+	HD void swap_at(int i, int j) { int t = a[i]; a[i] = a[j]; a[j] = t; }
+
+	HD void unguarded_linear_insert(int last)
+	{
+		int val = a[last];
+		int next = last - 1;
+		while(less(val, a[next]))
+		{
+			a[last] = a[next];
+			last = next;
+			--next;
+		}
+		a[last] = val;
+	}
+
+	HD void insertion_sort(int first, int last)
+	{
+		if(first == last) return;
+		for(int i = first + 1; i != last; ++i)
+		{
+			if(less(a[i], a[first]))
+			{
+				int val = a[i];
+				for(int k = i; k > first; --k) a[k] = a[k - 1];
+				a[first] = val;
+			}
+			else unguarded_linear_insert(i);
+		}
+	}
+
+	HD void final_insertion_sort(int first, int last)
+	{
+		if(last - first > 16)
+		{
+			insertion_sort(first, first + 16);
+			for(int i = first + 16; i != last; ++i) unguarded_linear_insert(i);
+		}
+		else insertion_sort(first, last);
+	}
+
+	HD void move_median_to_first(int result, int x, int y, int z)
+	{
+		if(less(a[x], a[y]))
+		{
+			if(less(a[y], a[z])) swap_at(result, y);
+			else if(less(a[x], a[z])) swap_at(result, z);
+			else swap_at(result, x);
+		}
+		else if(less(a[x], a[z])) swap_at(result, x);
+		else if(less(a[y], a[z])) swap_at(result, z);
+		else swap_at(result, y);
+	}
+
+	HD int unguarded_partition(int first, int last, int pivot)
+	{
+		while(true)
+		{
+			while(less(a[first], a[pivot])) ++first;
+			--last;
+			while(less(a[pivot], a[last])) --last;
+			if(!(first < last)) return first;
+			swap_at(first, last);
+			++first;
+		}
+	}
+
+	// ---- heap fallback (depth limit reached) ----
+	HD void push_heap(int first, int hole, int top, int value)
+	{
+		int parent = (hole - 1) / 2;
+		while(hole > top && less(a[first + parent], value))
+		{
+			a[first + hole] = a[first + parent];
+			hole = parent;
+			parent = (hole - 1) / 2;
+		}
+		a[first + hole] = value;
+	}
+
+	HD void adjust_heap(int first, int hole, int len, int value)
+	{
+		const int top = hole;
+		int second = hole;
+		while(second < (len - 1) / 2)
+		{
+			second = 2 * (second + 1);
+			if(less(a[first + second], a[first + (second - 1)])) second--;
+			a[first + hole] = a[first + second];
+			hole = second;
+		}
+		if((len & 1) == 0 && second == (len - 2) / 2)
+		{
+			second = 2 * (second + 1);
+			a[first + hole] = a[first + (second - 1)];
+			hole = second - 1;
+		}
+		push_heap(first, hole, top, value);
+	}
+
+	HD void pop_heap(int first, int last, int result)
+	{
+		int value = a[result];
+		a[result] = a[first];
+		adjust_heap(first, 0, last - first, value);
+	}
+
+	HD void make_heap(int first, int last)
+	{
+		if(last - first < 2) return;
+		const int len = last - first;
+		int parent = (len - 2) / 2;
+		while(true)
+		{
+			int value = a[first + parent];
+			adjust_heap(first, parent, len, value);
+			if(parent == 0) return;
+			parent--;
+		}
+	}
+
+	HD void partial_sort_all(int first, int last)
+	{
+		// __partial_sort(first, last, last): heap_select over an empty tail, then sort_heap
+		make_heap(first, last);
+		int l = last;
+		while(l - first > 1)
+		{
+			--l;
+			pop_heap(first, l, l);
+		}
+	}
+
+	HD void sort(int first, int last)
+	{
+		if(first == last) return;
+		int n = last - first;
+		int lg = 0;
+		while((n >> (lg + 1)) != 0) lg++;          // std::__lg
+		// __introsort_loop with an explicit stack: the recursive call handles [cut, last) and the
+		// loop continues on [first, cut); the two ranges are disjoint, so the order is immaterial
+		int st_first[64], st_last[64], st_depth[64];
+		int sp = 0;
+		st_first[0] = first; st_last[0] = last; st_depth[0] = lg * 2; sp = 1;
+		while(sp > 0)
+		{
+			--sp;
+			int f = st_first[sp], l = st_last[sp], d = st_depth[sp];
+			while(l - f > 16)
+			{
+				if(d == 0) { partial_sort_all(f, l); break; }
+				--d;
+				int mid = f + (l - f) / 2;
+				move_median_to_first(f, f + 1, mid, l - 1);
+				int cut = unguarded_partition(f + 1, l, f);
+				st_first[sp] = cut; st_last[sp] = l; st_depth[sp] = d; sp++;
+				l = cut;
+			}
+		}
+		final_insertion_sort(first, last);
+	}
+};
+
+template<typename Less>
+HD inline void std_sort_handles(int *a, int n, Less less)
+{
+	std_sort_emul<Less> s(a, less);
+	s.sort(0, n);
+}
+
+} // namespace agpu
+
+#endif

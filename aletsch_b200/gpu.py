@@ -1,0 +1,297 @@
+"""ctypes binding of the C ABI in include/aletsch_gpu.h (libaletsch_gpu.so, hand-written sm_100a CUDA).
+
+No fallback: importing is cheap, but ``Context()`` raises if the CUDA library is missing or no
+device is usable.  The kernel-logic test tier may pass ``lib_path`` of the host emulation build
+(tests/emu) explicitly; nothing in the product selects it.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from .hostlib import BatchIn
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+GPU_SO = os.path.join(_HERE, "libaletsch_gpu.so")
+
+
+class Params(C.Structure):
+    """agpu_params"""
+    _fields_ = [("library_type", C.c_int32), ("min_junction_support", C.c_int32), ("normal_junction_threshold", C.c_int32),
+                ("extend_junction_threshold", C.c_int32), ("min_subregion_gap", C.c_int32), ("min_subregion_length", C.c_int32),
+                ("max_reads_partition_gap", C.c_int32), ("bridge_end_relaxing", C.c_int32),
+                ("bridge_dp_solution_size", C.c_int32), ("bridge_dp_stack_size", C.c_int32), ("insertsize_low", C.c_int32),
+                ("insertsize_high", C.c_int32), ("max_group_size", C.c_int32), ("max_num_junctions_to_combine", C.c_int32),
+                ("min_subregion_overlap", C.c_double), ("min_guaranteed_edge_weight", C.c_double),
+                ("min_grouping_similarity", C.c_double), ("max_grouping_similarity", C.c_double)]
+
+
+P32 = C.POINTER(C.c_int32)
+P64 = C.POINTER(C.c_int64)
+PF = C.POINTER(C.c_double)
+PU8 = C.POINTER(C.c_uint8)
+
+
+class ChainsetView(C.Structure):
+    _fields_ = [("bundle_chain_off", P32), ("chain_off", P32), ("chain_val", P32), ("chain_cnt", P32), ("chain_grp", P32),
+                ("handle_chain", P32), ("n_chains", C.c_int64), ("n_handles", C.c_int64)]
+
+
+class EvidenceView(C.Structure):
+    _fields_ = [("n_bundles", C.c_int32), ("lpos", P32), ("rpos", P32), ("strand", PU8), ("seg_off", P64), ("seg", P32),
+                ("splice_off", P64), ("splices", P32), ("hcst", ChainsetView)]
+
+
+class FragmentsView(C.Structure):
+    _fields_ = [("frg_off", P64), ("frgs", P32), ("fcst", ChainsetView), ("bridged", P32)]
+
+
+class GraphView(C.Structure):
+    _fields_ = [("junc_off", P32), ("junc", P32), ("pexon_off", P32), ("pexon", P32), ("pexon_d", PF), ("vert_off", P32),
+                ("vert", P32), ("vert_d", PF), ("edge_off", P32), ("edge", P32), ("edge_d", PF), ("strand", PU8)]
+
+
+class ClusterView(C.Structure):
+    _fields_ = [("clu_off", P64), ("bounds", P32), ("extend", P32), ("count", P32), ("chain1", P32), ("chain2", P32),
+                ("frlist_off", P64), ("frlist", P32), ("n_clusters", C.c_int64)]
+
+
+class BridgeView(C.Structure):
+    _fields_ = [("type", P32), ("strand", P32), ("choices", P32), ("score", PF), ("chain_off", P64), ("chain", P32),
+                ("whole_off", P64), ("whole", P32)]
+
+
+class Counts(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("hits", "cigar_ops", "span", "segments", "chains", "splice_ints", "junctions", "vertices",
+                                         "edges", "fragments", "clusters", "bridged", "piers")]
+
+
+ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_sync", "agpu_launch_count",
+               "agpu_batch_upload", "agpu_batch_adopt", "agpu_batch_free", "agpu_batch_reset", "agpu_batch_evidence",
+               "agpu_batch_fragments", "agpu_batch_graph", "agpu_batch_cluster", "agpu_batch_bridge", "agpu_batch_update",
+               "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
+               "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity"]
+
+
+def load(lib_path=None):
+    path = lib_path or GPU_SO
+    if not os.path.exists(path):
+        raise RuntimeError("CUDA library %s is missing: run __graft_entry__.build() (there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    L.agpu_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.agpu_destroy.argtypes = [C.c_void_p]
+    L.agpu_last_error.restype = C.c_char_p
+    L.agpu_last_error.argtypes = [C.c_void_p]
+    L.agpu_sync.argtypes = [C.c_void_p]
+    L.agpu_launch_count.restype = C.c_int64
+    L.agpu_launch_count.argtypes = [C.c_void_p]
+    L.agpu_default_params.argtypes = [C.POINTER(Params)]
+    L.agpu_batch_upload.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
+    L.agpu_batch_adopt.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
+    L.agpu_batch_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.agpu_batch_reset.argtypes = [C.c_void_p, C.c_void_p]
+    for n in ("evidence", "graph", "cluster", "bridge", "bridge_all"):
+        getattr(L, "agpu_batch_" + n).argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params)]
+    for n in ("fragments", "update"):
+        getattr(L, "agpu_batch_" + n).argtypes = [C.c_void_p, C.c_void_p]
+    L.agpu_evidence_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EvidenceView)]
+    L.agpu_fragments_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(FragmentsView)]
+    L.agpu_graph_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(GraphView)]
+    L.agpu_cluster_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ClusterView)]
+    L.agpu_bridge_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BridgeView)]
+    L.agpu_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Counts)]
+    L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def default_params(**kw):
+    p = Params()
+    # defaults of util/parameters.cc:19-113; filled by the library itself when loadable, else statically
+    p.library_type, p.min_junction_support, p.normal_junction_threshold, p.extend_junction_threshold = 1, 1, 10, 20
+    p.min_subregion_gap, p.min_subregion_length, p.max_reads_partition_gap, p.bridge_end_relaxing = 15, 15, 10, 10
+    p.bridge_dp_solution_size, p.bridge_dp_stack_size, p.insertsize_low, p.insertsize_high = 10, 5, 80, 500
+    p.max_group_size, p.max_num_junctions_to_combine = 200, 500
+    p.min_subregion_overlap, p.min_guaranteed_edge_weight = 1.5, 0.01
+    p.min_grouping_similarity, p.max_grouping_similarity = 0.10, 0.80
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _arr(ptr, n, dtype=None):
+    if n <= 0:
+        return np.zeros(0, dtype or np.int32)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).copy()
+
+
+class AgpuError(RuntimeError):
+    pass
+
+
+class Context:
+    """agpu_ctx: one CUDA stream.  `stream` may be a raw cudaStream_t (int), e.g. torch's current stream."""
+
+    def __init__(self, device=0, stream=None, lib_path=None):
+        self.L = load(lib_path)
+        h = C.c_void_p()
+        rc = self.L.agpu_create(device, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise AgpuError("agpu_create(device=%d) failed with %d: no usable CUDA device (no CPU fallback)" % (device, rc))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.agpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise AgpuError("%s failed with %d: %s" % (what, rc, self.L.agpu_last_error(self.h).decode()))
+
+    def sync(self):
+        self.check(self.L.agpu_sync(self.h), "agpu_sync")
+
+    @property
+    def launches(self):
+        return self.L.agpu_launch_count(self.h)
+
+    def upload(self, batch_in, keepalive=None):
+        return Batch(self, batch_in, False, keepalive)
+
+    def adopt(self, batch_in_device, keepalive=None):
+        return Batch(self, batch_in_device, True, keepalive)
+
+    def similarity(self, lists):
+        """dense c (int32) and r (float64) of |A∩B| and c / min(|A|,|B|) over sorted splice lists."""
+        g = len(lists)
+        off = np.zeros(g + 1, np.int64)
+        for i, l in enumerate(lists):
+            off[i + 1] = off[i] + len(l)
+        val = np.concatenate([np.asarray(l, np.int32) for l in lists]) if g and off[g] else np.zeros(0, np.int32)
+        val = np.ascontiguousarray(val, np.int32)
+        c = np.zeros((g, g), np.int32)
+        r = np.zeros((g, g), np.float64)
+        self.check(self.L.agpu_similarity(self.h, g, off.ctypes.data, val.ctypes.data, c.ctypes.data, r.ctypes.data), "agpu_similarity")
+        return c, r
+
+
+class Batch:
+    """agpu_batch: device-resident state of a batch of bundles."""
+
+    def __init__(self, ctx, bin_struct, adopt, keepalive):
+        self.ctx = ctx
+        self.keep = keepalive
+        self.nb = bin_struct.n_bundles
+        self.hit_off = None
+        h = C.c_void_p()
+        fn = ctx.L.agpu_batch_adopt if adopt else ctx.L.agpu_batch_upload
+        ctx.check(fn(ctx.h, C.byref(bin_struct), C.byref(h)), "agpu_batch_adopt" if adopt else "agpu_batch_upload")
+        self.h = h
+
+    def free(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.L.agpu_batch_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        self.free()
+
+    def _run(self, name, params=None):
+        fn = getattr(self.ctx.L, "agpu_batch_" + name)
+        rc = fn(self.ctx.h, self.h, C.byref(params)) if params is not None else fn(self.ctx.h, self.h)
+        self.ctx.check(rc, "agpu_batch_" + name)
+
+    def reset(self):
+        self._run("reset")
+
+    def evidence(self, p):
+        self._run("evidence", p)
+
+    def fragments(self):
+        self._run("fragments")
+
+    def graph(self, p):
+        self._run("graph", p)
+
+    def cluster(self, p):
+        self._run("cluster", p)
+
+    def bridge(self, p):
+        self._run("bridge", p)
+
+    def update(self):
+        self._run("update")
+
+    def bridge_all(self, p):
+        self._run("bridge_all", p)
+
+    def counts(self):
+        c = Counts()
+        self.ctx.check(self.ctx.L.agpu_batch_counts(self.ctx.h, self.h, C.byref(c)), "agpu_batch_counts")
+        return {n: getattr(c, n) for n, _ in Counts._fields_}
+
+    # ---- fetches: per-bundle dicts in the oracle's array naming (tests/orclib.py) ----------
+    @staticmethod
+    def _chainset(v, nb, handle_off, pre, hname):
+        out = []
+        bco = _arr(v.bundle_chain_off, nb + 1)
+        nc = int(bco[nb]) if nb else 0
+        co = _arr(v.chain_off, nc + 1)
+        cv = _arr(v.chain_val, int(co[nc]) if nc else 0)
+        cc = _arr(v.chain_cnt, 3 * nc)
+        cg = _arr(v.chain_grp, nc)
+        hc = _arr(v.handle_chain, v.n_handles)
+        for k in range(nb):
+            a, b = int(bco[k]), int(bco[k + 1])
+            o = co[a:b + 1] - (co[a] if b >= a and len(co) else 0)
+            d = {pre + "_off": o.astype(np.int32), pre + "_val": cv[int(co[a]):int(co[b])], pre + "_cnt": cc[3 * a:3 * b],
+                 pre + "_grp": cg[a:b]}
+            if handle_off is not None:
+                d[hname] = hc[int(handle_off[k]):int(handle_off[k + 1])]
+            out.append(d)
+        return out
+
+    def fetch_evidence(self, hit_off):
+        v = EvidenceView()
+        self.ctx.check(self.ctx.L.agpu_evidence_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_evidence_fetch")
+        nb = self.nb
+        lpos, rpos, strand = _arr(v.lpos, nb), _arr(v.rpos, nb), _arr(v.strand, nb, np.uint8)
+        so = _arr(v.seg_off, nb + 1, np.int64)
+        seg = _arr(v.seg, 3 * int(so[nb]) if nb else 0)
+        spo = _arr(v.splice_off, nb + 1, np.int64)
+        spv = _arr(v.splices, int(spo[nb]) if nb else 0)
+        cs = self._chainset(v.hcst, nb, hit_off, "hcst", "hit_chain")
+        out = []
+        for k in range(nb):
+            d = {"bundle": np.array([lpos[k], rpos[k], strand[k], hit_off[k + 1] - hit_off[k]], np.int32),
+                 "seg": seg[3 * int(so[k]):3 * int(so[k + 1])], "splices": spv[int(spo[k]):int(spo[k + 1])]}
+            d.update(cs[k])
+            out.append(d)
+        return out
+
+    def fetch_graph(self):
+        v = GraphView()
+        self.ctx.check(self.ctx.L.agpu_graph_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_graph_fetch")
+        nb = self.nb
+        jo, po, vo, eo = (_arr(x, nb + 1) for x in (v.junc_off, v.pexon_off, v.vert_off, v.edge_off))
+        junc, pex, vert, edge = _arr(v.junc, 9 * int(jo[nb])), _arr(v.pexon, 5 * int(po[nb])), _arr(v.vert, 5 * int(vo[nb])), _arr(v.edge, 3 * int(eo[nb]))
+        pexd, vertd, edged = _arr(v.pexon_d, 4 * int(po[nb]), np.float64), _arr(v.vert_d, 3 * int(vo[nb]), np.float64), _arr(v.edge_d, int(eo[nb]), np.float64)
+        strand = _arr(v.strand, nb, np.uint8)
+        out = []
+        for k in range(nb):
+            e = edge[3 * int(eo[k]):3 * int(eo[k + 1])].reshape(-1, 3)
+            ew = edged[int(eo[k]):int(eo[k + 1])]
+            alive = e[:, 0] >= 0
+            out.append({"junc": junc[9 * int(jo[k]):9 * int(jo[k + 1])], "pexon": pex[5 * int(po[k]):5 * int(po[k + 1])],
+                        "pexon_d": pexd[4 * int(po[k]):4 * int(po[k + 1])], "vert": vert[5 * int(vo[k]):5 * int(vo[k + 1])],
+                        "vert_d": vertd[3 * int(vo[k]):3 * int(vo[k + 1])],
+                        "edge_ins": e[alive].reshape(-1), "edge_ins_d": ew[alive],     # insertion order, alive only
+                        "graph": np.array([strand[k]], np.int32)})
+            # oracle convention: edges sorted by (s, t)
+            ea, wa = e[alive], ew[alive]
+            order = np.lexsort((ea[:, 1], ea[:, 0])) if len(ea) else np.zeros(0, np.int64)
+            out[-1]["edge"] = ea[order].reshape(-1).astype(np.int32)
+            out[-1]["edge_d"] = wa[order]
+        return out

@@ -250,8 +250,10 @@ void make_template(const model &m, int32_t iso_flat, rng &r, uint64_t qid, uint1
 			else c1.push_back(op(len, 0));
 		}
 		sp = bl.size() >= 2;
-		uint16_t flag = (uint16_t)(((r.next() & 1) ? 0x10 : 0) | extra_flag);
-		push_hit(ob, ge.tid, pos, rpos, 0, 0, flag, sp ? (uint8_t)ge.strand : (uint8_t)'.', qid, c1);
+		// unpaired records carry flag 0x8 and mpos -1: without 0x8 the reference's span filter
+		// (meta/generator.cc:95) drops every unpaired hit beyond max_read_span
+		uint16_t flag = (uint16_t)(((r.next() & 1) ? 0x10 : 0) | 0x8 | extra_flag);
+		push_hit(ob, ge.tid, pos, rpos, -1, 0, flag, sp ? (uint8_t)ge.strand : (uint8_t)'.', qid, c1);
 		return;
 	}
 
@@ -262,8 +264,8 @@ void make_template(const model &m, int32_t iso_flat, rng &r, uint64_t qid, uint1
 		project(ge, is, s, s + rl, bl, br);
 		int32_t pos, rpos; bool sp;
 		emit_cigar(c, r, bl, br, true, c1, pos, rpos, sp);
-		uint16_t flag = (uint16_t)(((r.next() & 1) ? 0x10 : 0) | extra_flag);
-		push_hit(ob, ge.tid, pos, rpos, 0, 0, flag, sp ? (uint8_t)ge.strand : (uint8_t)'.', qid, c1);
+		uint16_t flag = (uint16_t)(((r.next() & 1) ? 0x10 : 0) | 0x8 | extra_flag);
+		push_hit(ob, ge.tid, pos, rpos, -1, 0, flag, sp ? (uint8_t)ge.strand : (uint8_t)'.', qid, c1);
 		return;
 	}
 

@@ -1,0 +1,26 @@
+"""CPU tier: the kernel bodies, compiled for the host with a serial thread model (test-only build,
+see aletsch_b200/csrc/dev.h), against the CPU checkers.  This checks orderings, tie-breaks and index
+arithmetic of the kernels without a GPU; the -m gpu tier repeats it on the real CUDA path."""
+import pytest
+
+import parity
+from aletsch_b200 import gpu as G
+from aletsch_b200 import hostlib as H
+
+
+@pytest.fixture(scope="module")
+def ctx(emu_lib):
+    c = G.Context(0, lib_path=emu_lib)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("mode,templates", [(H.SYNTH_PAIRED, 30000), (H.SYNTH_SINGLE, 20000), (H.SYNTH_LONG, 3000)])
+def test_evidence_graph_parity(ctx, checkers, mode, templates):
+    assert checkers
+    batch, lt = parity.make_batch(mode, templates)
+    assert batch.n_bundles > 0
+    gp, op = parity.params_pair(lt)
+    for name, chk in checkers.items():
+        bad = parity.compare_evidence_graph(ctx, batch, chk, gp, op)
+        assert not bad, "%s: %d mismatches, first: %s" % (name, len(bad), bad[:3])
