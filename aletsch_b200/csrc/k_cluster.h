@@ -1,5 +1,514 @@
+// Stage 3b kernels: paired-read clustering (rnacore/graph_cluster.cc).
+//
+//   group_pereads            :28-91    align both mates of every to-be-bridged fragment to vertex paths and
+//                                      group fragments by the pair of paths, groups in first-seen order
+//   align_hit_to_splice_graph rnacore/essential.cc:461-472 -> build_path_from_mixed_coordinates :405-434
+//                             -> build_path_from_intron_coordinates :368-403, check_continuous_vertices :436-446
+//   build_pereads_clusters   :93-168   per group 4-level gap partition, bounds = first + sum(x - first) / count
+//   partition                :170-203  std::sort per level (unstable: the libstdc++ permutation is reproduced)
+//
+// A vertex path is compared in run-length form (maximal runs of consecutive vertex numbers): the runs
+// of a spliced mate are the runs of its intron chain's path (computed once per chain) with the first run
+// stretched down to the vertex holding pos and the last run stretched up to the vertex holding rpos - 1.
 #ifndef ALETSCH_B200_CSRC_K_CLUSTER_H
 #define ALETSCH_B200_CSRC_K_CLUSTER_H
+
 #include "runtime.h"
-struct cluster_state { bool built = false; void release(agpu_ctx *) { built = false; } };
+#include "k_graph.h"
+#include "stdsort.h"
+
+namespace agpu {
+
+struct gview                     // read-only view of the graph of one bundle
+{
+	int nv;
+	const int32_t *v_l, *v_r, *v_brk;
+};
+
+DEV gview graph_of(const graph_dev &g, int b)
+{
+	gview v;
+	int64_t v0 = vert_base(g, b);
+	v.nv = g.n_pex[b] + 2;
+	v.v_l = g.v_l + v0; v.v_r = g.v_r + v0; v.v_brk = g.v_brk + v0;
+	return v;
+}
+
+// splice_graph::locate_vertex(p) (rnacore/splice_graph.cc:1166-1215)
+DEV int locate_vertex(const gview &g, int32_t p)
+{
+	int a = 1, b = g.nv - 1;
+	int m = -1;
+	while(a < b)
+	{
+		int mid = (a + b) / 2;
+		if(p >= g.v_l[mid] && p < g.v_r[mid]) { m = mid; break; }
+		if(p < g.v_l[mid]) b = mid;
+		else a = mid + 1;
+	}
+	if(m < 0) m = b;
+	if(p >= g.v_l[m] && p < g.v_r[m]) return m;
+	return -1;
+}
+
+// rindex[p] (vertices 0 .. n-1 keyed by rpos) and lindex[q] (vertices 1 .. n keyed by lpos); -1 if absent
+DEV int rindex_find(const gview &g, int32_t p)
+{
+	int k = lower_bound_idx(g.v_r, g.nv - 1, p);
+	return (k < g.nv - 1 && g.v_r[k] == p) ? k : -1;
+}
+DEV int lindex_find(const gview &g, int32_t q)
+{
+	int k = lower_bound_idx(g.v_l + 1, g.nv - 1, q) + 1;
+	return (k < g.nv && g.v_l[k] == q) ? k : -1;
+}
+// check_continuous_vertices(x, y)
+DEV bool continuous(const gview &g, int x, int y) { return x >= y || (g.v_brk[y] - g.v_brk[x]) == 0; }
+
+// per chain record: path of the intron chain in the bundle's graph, in run-length form
+struct chain_paths
+{
+	int32_t *valid;          // build_path_from_intron_coordinates succeeded
+	int32_t *mono;           // chain coordinates non-decreasing
+	int32_t *first, *last;   // chain.front(), chain.back()
+	int32_t *nruns;
+	int32_t *runs;           // pairs (start, end) at run_base(record)
+};
+
+// run storage of the chain record at scratch slot e (its representative element's coordinates start at voff):
+// records own disjoint windows of len + 2 ints
+HD int64_t run_base(int64_t rep_elem, int64_t voff) { return voff + 2 * rep_elem; }
+
+KERNEL k_chain_paths(int64_t n_elem, int32_t n_bundles, chains_view cv, graph_dev g, chain_paths cp)
+{
+	int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(e >= n_elem) return;
+	int b = find_segment(cv.elem_off, n_bundles, e);
+	int k = (int)(e - cv.elem_off[b]);
+	if(k >= cv.n_chains[b]) return;
+	gview gv = graph_of(g, b);
+	int len = cv.len(b, k);
+	const int32_t *v = cv.ptr(b, k);
+	int64_t rep = cv.elem_off[b] + cv.c_rep[cv.elem_off[b] + k];
+	int64_t voff = cv.voff64 ? cv.voff64[rep] : (int64_t)cv.voff32[rep];
+	int32_t *runs = cp.runs + run_base(rep, voff);
+	bool mono = true;
+	for(int i = 0; i + 1 < len; i++) if(v[i] > v[i + 1]) mono = false;
+	cp.mono[e] = mono ? 1 : 0;
+	cp.first[e] = len > 0 ? v[0] : 0;
+	cp.last[e] = len > 0 ? v[len - 1] : 0;
+	int n = len / 2;
+	bool ok = (len > 0 && (len & 1) == 0);
+	int nr = 0;
+	int prev_kq = -1;
+	for(int i = 0; ok && i < n; i++)
+	{
+		int32_t p = v[2 * i], q = v[2 * i + 1];
+		if(p >= q) { ok = false; break; }
+		int kp = rindex_find(gv, p), kq = lindex_find(gv, q);
+		if(kp < 0 || kq < 0) { ok = false; break; }
+		if(i == 0) { runs[0] = kp; runs[1] = kp; nr = 1; }
+		else
+		{
+			// vertices prev_kq .. kp must be continuous
+			if(prev_kq > kp || !continuous(gv, prev_kq, kp)) { ok = false; break; }
+			// append range prev_kq .. kp to the run list
+			if(runs[2 * nr - 1] + 1 == prev_kq) runs[2 * nr - 1] = kp;
+			else { runs[2 * nr] = prev_kq; runs[2 * nr + 1] = kp; nr++; }
+		}
+		prev_kq = kq;
+	}
+	if(ok)
+	{
+		// the path ends with pp.back().second
+		if(runs[2 * nr - 1] + 1 == prev_kq) runs[2 * nr - 1] = prev_kq;
+		else { runs[2 * nr] = prev_kq; runs[2 * nr + 1] = prev_kq; nr++; }
+	}
+	cp.valid[e] = ok ? 1 : 0;
+	cp.nruns[e] = ok ? nr : 0;
+}
+
+// aligned mate: runs of its vertex path are (a1 .. runs[0].end), runs[1..nr-2], (runs[nr-1].start .. a2)
+struct mate_path
+{
+	int32_t a1, a2;          // first / last vertex of the path
+	int32_t nr;              // number of runs (1 if the mate has no chain)
+	const int32_t *runs;     // chain runs (NULL without chain)
+	DEV int32_t rs(int i) const { int32_t s = runs ? runs[2 * i] : a1; return i == 0 ? a1 : s; }
+	DEV int32_t re(int i) const { int32_t e = runs ? runs[2 * i + 1] : a2; return i == nr - 1 ? a2 : e; }
+};
+
+struct cluster_dev
+{
+	// per fragment (global index)
+	int32_t *f_ok;                       // both mates aligned
+	int32_t *m_a1, *m_a2;                // [2F] per mate
+	u64 *f_hash;
+	int64_t *f_slot;
+	int32_t *f_next;
+	// group table
+	const int64_t *reg_off;
+	u64 *slot_word;
+	int32_t *slot_min, *slot_n, *slot_head;
+};
+
+DEV mate_path mate_of(const chains_view &cv, const chain_paths &cp, const cluster_dev &c, const int32_t *handle_chain,
+		int b, int64_t hit, int64_t f, int which)
+{
+	mate_path m;
+	m.a1 = c.m_a1[2 * f + which]; m.a2 = c.m_a2[2 * f + which];
+	int ch = handle_chain[hit];
+	if(ch < 0) { m.nr = 1; m.runs = NULL; return m; }
+	int64_t e = cv.elem_off[b] + ch;
+	int64_t rep = cv.elem_off[b] + cv.c_rep[e];
+	int64_t voff = cv.voff64 ? cv.voff64[rep] : (int64_t)cv.voff32[rep];
+	m.nr = cp.nruns[e];
+	m.runs = cp.runs + run_base(rep, voff);
+	return m;
+}
+
+DEV bool same_path(const mate_path &x, const mate_path &y)
+{
+	if(x.nr != y.nr) return false;
+	for(int i = 0; i < x.nr; i++) if(x.rs(i) != y.rs(i) || x.re(i) != y.re(i)) return false;
+	return true;
+}
+
+DEV u64 path_hash(const mate_path &x, u64 h)
+{
+	h = mix64(h ^ (u64)x.nr);
+	for(int i = 0; i < x.nr; i++) h = mix64(h ^ (((u64)(u32)x.rs(i) << 32) | (u64)(u32)x.re(i)));
+	return h;
+}
+
+// ---- C1: align both mates of every to-be-bridged fragment; frgs[i][2] := -1, then 0 if both align
+KERNEL k_frag_align(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+		int32_t *f_type, chains_view cv, chain_paths cp, const int32_t *handle_chain, graph_dev g, cluster_dev c)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(f >= n_frg) return;
+	c.f_ok[f] = 0;
+	c.f_slot[f] = -1;
+	if(f_type[f] != 0) return;                    // only unbridged fragments are grouped (:37-38)
+	f_type[f] = -1;
+	int b = find_segment(frg_off, n_bundles, f);
+	int64_t h0 = h.bundle_hit_off[b];
+	int64_t i1 = h0 + f_h1[f], i2 = h0 + f_h2[f];
+	if(h.pos[i1] > h.pos[i2]) return;
+	if(h.rpos[i1] > h.rpos[i2]) return;
+	gview gv = graph_of(g, b);
+	u64 hsh = 0x1234567ULL;
+	for(int w = 0; w < 2; w++)
+	{
+		int64_t hi = w == 0 ? i1 : i2;
+		int32_t pos = h.pos[hi], rpos = h.rpos[hi];
+		int ch = handle_chain[hi];
+		int64_t e = ch >= 0 ? cv.elem_off[b] + ch : -1;
+		// check_increasing_sequence(pos, chain..., rpos)
+		if(ch >= 0) { if(!cp.mono[e] || pos > cp.first[e] || cp.last[e] > rpos) return; }
+		else if(pos > rpos) return;
+		int u1 = locate_vertex(gv, pos), u2 = locate_vertex(gv, rpos - 1);
+		if(u1 < 0 || u2 < 0) return;
+		if(u1 > u2) return;
+		int32_t a1 = u1, a2 = u2;
+		if(ch >= 0)
+		{
+			if(!cp.valid[e]) return;
+			int64_t rep = cv.elem_off[b] + cv.c_rep[e];
+			int64_t voff = cv.voff64 ? cv.voff64[rep] : (int64_t)cv.voff32[rep];
+			const int32_t *runs = cp.runs + run_base(rep, voff);
+			int nr = cp.nruns[e];
+			int32_t front = runs[0], back = runs[2 * nr - 1];
+			if(front < a1) a1 = front;             // for(i = u1; i < uu.front(); i++) adds nothing when u1 >= uu.front()
+			if(back > a2) a2 = back;
+		}
+		c.m_a1[2 * f + w] = a1; c.m_a2[2 * f + w] = a2;
+	}
+	f_type[f] = 0;
+	c.f_ok[f] = 1;
+	mate_path p1 = mate_of(cv, cp, c, handle_chain, b, i1, f, 0), p2 = mate_of(cv, cp, c, handle_chain, b, i2, f, 1);
+	hsh = path_hash(p2, path_hash(p1, hsh));
+	c.f_hash[f] = hsh;
+}
+
+// ---- C2: group by (path1, path2): per-bundle table, exact comparison against the slot's first claimer
+KERNEL k_frag_group(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+		chains_view cv, chain_paths cp, const int32_t *handle_chain, cluster_dev c, int *err)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(f >= n_frg) return;
+	if(!c.f_ok[f]) return;
+	int b = find_segment(frg_off, n_bundles, f);
+	int64_t h0 = h.bundle_hit_off[b];
+	int64_t r0 = c.reg_off[b];
+	u32 mask = (u32)(c.reg_off[b + 1] - r0) - 1;
+	u64 hsh = c.f_hash[f];
+	u32 pos = (u32)(hsh >> 7) & mask;
+	u64 mine = ((hsh >> 32) << 32) | (u64)(u32)(f + 1);
+	mate_path p1 = mate_of(cv, cp, c, handle_chain, b, h0 + f_h1[f], f, 0), p2 = mate_of(cv, cp, c, handle_chain, b, h0 + f_h2[f], f, 1);
+	int64_t sl = -1;
+	for(u32 probe = 0; probe <= mask; probe++)
+	{
+		u64 cur = atomicCAS(&c.slot_word[r0 + pos], (u64)0, mine);
+		if(cur == 0) { sl = r0 + pos; break; }
+		if((cur >> 32) == (mine >> 32))
+		{
+			int64_t rf = (int64_t)(u32)(cur & 0xffffffffULL) - 1;
+			mate_path q1 = mate_of(cv, cp, c, handle_chain, b, h0 + f_h1[rf], rf, 0), q2 = mate_of(cv, cp, c, handle_chain, b, h0 + f_h2[rf], rf, 1);
+			if(same_path(p1, q1) && same_path(p2, q2)) { sl = r0 + pos; break; }
+		}
+		pos = (pos + 1) & mask;
+	}
+	if(sl < 0) { atomicAdd(&err[ERR_CAP], 1); c.f_ok[f] = 0; return; }
+	c.f_slot[f] = sl;
+	int32_t lf = (int32_t)(f - frg_off[b]);
+	c.f_next[f] = atomicExch(&c.slot_head[sl], lf);
+	atomicMin(&c.slot_min[sl], lf);
+	atomicAdd(&c.slot_n[sl], 1);
+}
+
+// leader[f] = group size if f is the first fragment of its group, else -1 (input of the flag scans)
+KERNEL k_group_leaders(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, cluster_dev c, int32_t *leader, int32_t *leader_size)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(f >= n_frg) return;
+	leader[f] = -1;
+	leader_size[f] = 0;
+	int64_t sl = c.f_slot[f];
+	if(sl < 0) return;
+	int b = find_segment(frg_off, n_bundles, f);
+	if(c.slot_min[sl] != (int32_t)(f - frg_off[b])) return;
+	leader[f] = 1;
+	leader_size[f] = c.slot_n[sl];
+}
+
+// generic device-wide exclusive scan of int32 values into int64 (tile sums + single-CTA scan + apply)
+KERNEL k_val_tile_sum(const int32_t *v, int64_t n, int64_t n_tiles, int32_t *tile_sum)
+{
+	SHARED int s;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		if(threadIdx.x == 0) s = 0;
+		BLOCK_SYNC();
+		int acc = 0;
+		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
+		{
+			int64_t gi = t * SCAN_TILE + i;
+			if(gi < n) acc += v[gi];
+		}
+		atomicAdd(&s, acc);
+		BLOCK_SYNC();
+		if(threadIdx.x == 0) tile_sum[t] = s;
+		BLOCK_SYNC();
+	}
+}
+
+KERNEL k_val_tile_scan(const int32_t *v, int64_t n, int64_t n_tiles, const int64_t *tile_off, int64_t *out)
+{
+	SHARED int f[SCAN_TILE];
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
+		{
+			int64_t gi = t * SCAN_TILE + i;
+			f[i] = gi < n ? v[gi] : 0;
+		}
+		BLOCK_SYNC();
+		block_excl_scan(f, SCAN_TILE);
+		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
+		{
+			int64_t gi = t * SCAN_TILE + i;
+			if(gi <= n) out[gi] = tile_off[t] + f[i];
+		}
+		BLOCK_SYNC();
+	}
+}
+
+struct part_ctx
+{
+	int32_t *m;                  // members (bundle-local fragment indices) of the group, in place
+	int32_t *cflag;              // cluster-start flags parallel to m
+	const int32_t *f_h1, *f_h2;  // bundle's fragments
+	const int32_t *pos, *rpos;   // bundle's hits
+	int gap;
+	DEV int32_t key(int r, int32_t fr) const
+	{
+		int32_t hh = (r < 2) ? f_h1[fr] : f_h2[fr];
+		return (r & 1) ? rpos[hh] : pos[hh];
+	}
+};
+
+struct key_less
+{
+	const part_ctx *c;
+	int r;
+	HD bool operator()(int x, int y) const { return c->key(r, x) < c->key(r, y); }
+};
+
+// graph_cluster::partition (rnacore/graph_cluster.cc:170-203), in place on the member array
+template<int R> DEV void partition_rec(const part_ctx &c, int lo, int hi)
+{
+	key_less less;
+	less.c = &c; less.r = R;
+	std_sort_handles(c.m + lo, hi - lo, less);
+	int pre = lo;
+	for(int k = lo + 1; k <= hi; k++)
+	{
+		if(k < hi && c.key(R, c.m[k]) - c.key(R, c.m[k - 1]) <= c.gap) continue;
+		partition_rec<R + 1>(c, pre, k);
+		pre = k;
+	}
+}
+template<> DEV void partition_rec<4>(const part_ctx &c, int lo, int hi) { (void)hi; c.cflag[lo] = 1; }
+
+// ---- C3: the first fragment of every group gathers the members (ascending fragment index) and partitions them
+KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+		cluster_dev c, const int32_t *leader, const int64_t *member_off, int32_t *members, int32_t *cflag, int gap)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(f >= n_frg) return;
+	if(leader[f] < 0) return;
+	int b = find_segment(frg_off, n_bundles, f);
+	int64_t f0 = frg_off[b];
+	int64_t sl = c.f_slot[f];
+	int n = c.slot_n[sl];
+	int32_t *m = members + member_off[f];
+	int k = 0;
+	for(int32_t x = c.slot_head[sl]; x >= 0 && k < n; x = c.f_next[f0 + x]) m[k++] = x;
+	// ascending fragment index = the order group_pereads appended them (heap sort, keys are distinct)
+	for(int i = n / 2 - 1; i >= 0; i--)
+	{
+		int root = i;
+		while(true)
+		{
+			int ch = 2 * root + 1;
+			if(ch >= n) break;
+			if(ch + 1 < n && m[ch + 1] > m[ch]) ch++;
+			if(m[root] >= m[ch]) break;
+			int32_t t = m[root]; m[root] = m[ch]; m[ch] = t;
+			root = ch;
+		}
+	}
+	for(int end = n - 1; end > 0; end--)
+	{
+		int32_t t = m[0]; m[0] = m[end]; m[end] = t;
+		int root = 0;
+		while(true)
+		{
+			int ch = 2 * root + 1;
+			if(ch >= end) break;
+			if(ch + 1 < end && m[ch + 1] > m[ch]) ch++;
+			if(m[root] >= m[ch]) break;
+			int32_t t2 = m[root]; m[root] = m[ch]; m[ch] = t2;
+			root = ch;
+		}
+	}
+	part_ctx pc;
+	pc.m = m; pc.cflag = cflag + member_off[f];
+	pc.f_h1 = f_h1 + f0; pc.f_h2 = f_h2 + f0;
+	pc.pos = h.pos + h.bundle_hit_off[b]; pc.rpos = h.rpos + h.bundle_hit_off[b];
+	pc.gap = gap;
+	partition_rec<0>(pc, 0, n);
+}
+
+struct clusters_out
+{
+	int32_t *bounds, *extend, *count, *chain1, *chain2, *bundle;
+	int64_t *fr_begin;           // [C+1] member range of the cluster
+};
+
+// ---- C4: one thread per member position that starts a cluster (rnacore/graph_cluster.cc:106-165)
+KERNEL k_cluster_emit(int64_t n_mem, const int32_t *cflag_i /* >= 0 at cluster starts, -1 elsewhere */, const int64_t *crank,
+		const int32_t *members, const int32_t *mem_bundle_hint, int32_t n_bundles, const int64_t *frg_off, const int64_t *member_boff,
+		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, const int32_t *handle_chain, graph_dev g, cluster_dev c, clusters_out o)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_mem) return;
+	if(cflag_i[i] < 0) return;
+	int64_t cid = crank[i];
+	o.fr_begin[cid] = i;
+	int b = find_segment(member_boff, n_bundles, i);
+	int64_t f0 = frg_off[b], h0 = h.bundle_hit_off[b];
+	// extent: up to the next cluster start (every group start is one) or the end of the members
+	int64_t j = i + 1;
+	while(j < n_mem && cflag_i[j] < 0) j++;
+	int cnt = (int)(j - i);
+	int32_t fr0 = members[i];
+	int64_t a1 = h0 + f_h1[f0 + fr0], a2 = h0 + f_h2[f0 + fr0];
+	int32_t b0 = h.pos[a1], b1 = h.rpos[a1], b2 = h.pos[a2], b3 = h.rpos[a2];
+	int32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+	for(int64_t x = i; x < j; x++)
+	{
+		int32_t fr = members[x];
+		int64_t x1 = h0 + f_h1[f0 + fr], x2 = h0 + f_h2[f0 + fr];
+		s0 += h.pos[x1] - b0; s1 += h.rpos[x1] - b1; s2 += h.pos[x2] - b2; s3 += h.rpos[x2] - b3;
+	}
+	o.bounds[4 * cid] = s0 / cnt + b0; o.bounds[4 * cid + 1] = s1 / cnt + b1;
+	o.bounds[4 * cid + 2] = s2 / cnt + b2; o.bounds[4 * cid + 3] = s3 / cnt + b3;
+	o.count[cid] = cnt;
+	o.chain1[cid] = handle_chain[a1];
+	o.chain2[cid] = handle_chain[a2];
+	o.bundle[cid] = b;
+	gview gv = graph_of(g, b);
+	int64_t gf = f0 + fr0;
+	o.extend[4 * cid] = gv.v_l[c.m_a1[2 * gf]]; o.extend[4 * cid + 1] = gv.v_r[c.m_a2[2 * gf]];
+	o.extend[4 * cid + 2] = gv.v_l[c.m_a1[2 * gf + 1]]; o.extend[4 * cid + 3] = gv.v_r[c.m_a2[2 * gf + 1]];
+}
+
+// cflag (0/1) -> -1 / 1 so that the flag-rank scan can be reused
+KERNEL k_flag_to_sign(int64_t n, int32_t *v)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	v[i] = v[i] > 0 ? 1 : -1;
+}
+
+} // namespace agpu
+
+struct cluster_state
+{
+	bool built = false;
+	// chain paths
+	agpu::dbuf<int32_t> cp_valid, cp_mono, cp_first, cp_last, cp_nruns, cp_runs;
+	// per fragment
+	agpu::dbuf<int32_t> f_ok, m_a1, m_a2, f_next, leader, leader_size;
+	agpu::dbuf<agpu::u64> f_hash, slot_word;
+	agpu::dbuf<int64_t> f_slot, reg_off, member_off, member_boff, crank, clu_off;
+	agpu::dbuf<int32_t> slot_min, slot_n, slot_head, members, cflag, tile_cnt;
+	agpu::dbuf<int64_t> tile_off, grank;
+	// clusters
+	int64_t n_mem = 0, n_clu = 0;
+	agpu::dbuf<int32_t> c_bounds, c_extend, c_count, c_chain1, c_chain2, c_bundle;
+	agpu::dbuf<int64_t> c_fr_begin;
+	std::vector<int64_t> clu_off_host;
+
+	void release(agpu_ctx *ctx)
+	{
+		cp_valid.release(ctx); cp_mono.release(ctx); cp_first.release(ctx); cp_last.release(ctx); cp_nruns.release(ctx); cp_runs.release(ctx);
+		f_ok.release(ctx); m_a1.release(ctx); m_a2.release(ctx); f_next.release(ctx); leader.release(ctx); leader_size.release(ctx);
+		f_hash.release(ctx); slot_word.release(ctx); f_slot.release(ctx); reg_off.release(ctx); member_off.release(ctx);
+		member_boff.release(ctx); crank.release(ctx); clu_off.release(ctx);
+		slot_min.release(ctx); slot_n.release(ctx); slot_head.release(ctx); members.release(ctx); cflag.release(ctx); tile_cnt.release(ctx);
+		tile_off.release(ctx); grank.release(ctx);
+		c_bounds.release(ctx); c_extend.release(ctx); c_count.release(ctx); c_chain1.release(ctx); c_chain2.release(ctx); c_bundle.release(ctx);
+		c_fr_begin.release(ctx);
+		built = false; n_mem = 0; n_clu = 0;
+	}
+
+	agpu::chain_paths paths()
+	{
+		agpu::chain_paths cp;
+		cp.valid = cp_valid.p; cp.mono = cp_mono.p; cp.first = cp_first.p; cp.last = cp_last.p; cp.nruns = cp_nruns.p; cp.runs = cp_runs.p;
+		return cp;
+	}
+
+	agpu::cluster_dev dev()
+	{
+		agpu::cluster_dev c;
+		c.f_ok = f_ok.p; c.m_a1 = m_a1.p; c.m_a2 = m_a2.p; c.f_hash = f_hash.p; c.f_slot = f_slot.p; c.f_next = f_next.p;
+		c.reg_off = reg_off.p; c.slot_word = slot_word.p; c.slot_min = slot_min.p; c.slot_n = slot_n.p; c.slot_head = slot_head.p;
+		return c;
+	}
+};
+
 #endif

@@ -1,6 +1,171 @@
-// placeholder, filled below
+// Stage 3a kernels: mate pairing (bundle_base::build_fragments, rnacore/bundle_base.cc:267-323).
+//
+// Reference semantics: for i ascending, an unpaired hit i takes the first unpaired u != i (in index
+// order) with hits[u].pos == hits[i].mpos, isize sum 0 and the same qname; frgs is ordered by i.
+// The bucket hash of the reference only accelerates the search, so the result is a function of
+// the groups of equal qname alone: the greedy is run independently inside every qname group.
+// Groups are found with a per-bundle open-addressing table keyed by the 64-bit qname key; members
+// are chained through an atomicExch linked list and sorted by index by the group's first hit.
 #ifndef ALETSCH_B200_CSRC_K_FRAGMENTS_H
 #define ALETSCH_B200_CSRC_K_FRAGMENTS_H
+
 #include "runtime.h"
-struct fragments_state { bool built = false; void release(agpu_ctx *) { built = false; } };
+#include "k_evidence.h"
+
+namespace agpu {
+
+#define QID_EMPTY 0xffffffffffffffffULL
+#define SCAN_TILE 2048
+
+KERNEL k_qid_insert(hits_dev h, const int32_t *hit_bundle, const int64_t *reg_off, u64 *slot_key, int32_t *slot_head, int32_t *slot_min,
+		int32_t *slot_n, int64_t *hit_qslot, int32_t *next, int *err)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	int b = hit_bundle[i];
+	int64_t r0 = reg_off[b];
+	u32 mask = (u32)(reg_off[b + 1] - r0) - 1;
+	u64 key = h.qid[i];
+	if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); hit_qslot[i] = -1; return; }
+	u32 pos = (u32)(mix64(key) >> 11) & mask;
+	int64_t sl = -1;
+	for(u32 probe = 0; probe <= mask; probe++)
+	{
+		u64 cur = atomicCAS(&slot_key[r0 + pos], (u64)QID_EMPTY, key);
+		if(cur == QID_EMPTY || cur == key) { sl = r0 + pos; break; }
+		pos = (pos + 1) & mask;
+	}
+	hit_qslot[i] = sl;
+	if(sl < 0) { atomicAdd(&err[ERR_CAP], 1); return; }
+	int32_t li = (int32_t)(i - h.bundle_hit_off[b]);
+	next[i] = atomicExch(&slot_head[sl], li);
+	atomicMin(&slot_min[sl], li);
+	atomicAdd(&slot_n[sl], 1);
+}
+
+// the first hit of every qname group runs the reference's greedy over the group
+KERNEL k_pair(hits_dev h, const int32_t *hit_bundle, const int64_t *hit_qslot, const int32_t *slot_head, const int32_t *slot_min,
+		const int32_t *slot_n, const int32_t *next, int32_t *cursor, int32_t *members, int32_t *mate)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	int64_t sl = hit_qslot[i];
+	if(sl < 0) return;
+	int b = hit_bundle[i];
+	int64_t h0 = h.bundle_hit_off[b];
+	if(slot_min[sl] != (int32_t)(i - h0)) return;
+	int n = slot_n[sl];
+	if(n < 2) return;
+	int32_t *m = members + h0 + atomicAdd(&cursor[b], n);
+	int k = 0;
+	for(int32_t x = slot_head[sl]; x >= 0 && k < n; x = next[h0 + x]) m[k++] = x;
+	// ascending hit index (insertion sort; groups are tiny)
+	for(int a = 1; a < n; a++)
+	{
+		int32_t v = m[a];
+		int c = a - 1;
+		while(c >= 0 && m[c] > v) { m[c + 1] = m[c]; c--; }
+		m[c + 1] = v;
+	}
+	for(int a = 0; a < n; a++)
+	{
+		int64_t ia = h0 + m[a];
+		if(mate[ia] != -1) continue;
+		for(int c = 0; c < n; c++)
+		{
+			if(c == a) continue;
+			int64_t ic = h0 + m[c];
+			if(mate[ic] != -1) continue;
+			if(h.pos[ic] != h.mpos[ia]) continue;
+			if(h.isize[ic] + h.isize[ia] != 0) continue;
+			mate[ia] = m[c];                 // i discovered the pair
+			mate[ic] = -2 - m[a];            // partner
+			break;
+		}
+	}
+}
+
+// ---- generic device-wide exclusive scan of 0/1 flags derived from an int array (flag = v[i] >= 0)
+KERNEL k_flag_tile_count(const int32_t *v, int64_t n, int64_t n_tiles, int32_t *tile_cnt)
+{
+	SHARED int s;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		if(threadIdx.x == 0) s = 0;
+		BLOCK_SYNC();
+		int acc = 0;
+		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
+		{
+			int64_t g = t * SCAN_TILE + i;
+			if(g < n && v[g] >= 0) acc++;
+		}
+		atomicAdd(&s, acc);
+		BLOCK_SYNC();
+		if(threadIdx.x == 0) tile_cnt[t] = s;
+		BLOCK_SYNC();
+	}
+}
+
+// rank[i] = number of flagged elements before i (written for every i, plus rank[n] = total)
+KERNEL k_flag_tile_rank(const int32_t *v, int64_t n, int64_t n_tiles, const int64_t *tile_off, int64_t *rank)
+{
+	SHARED int f[SCAN_TILE];
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
+		{
+			int64_t g = t * SCAN_TILE + i;
+			f[i] = (g < n && v[g] >= 0) ? 1 : 0;
+		}
+		BLOCK_SYNC();
+		block_excl_scan(f, SCAN_TILE);
+		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
+		{
+			int64_t g = t * SCAN_TILE + i;
+			if(g <= n) rank[g] = tile_off[t] + f[i];
+		}
+		BLOCK_SYNC();
+	}
+}
+
+KERNEL k_frag_emit(hits_dev h, const int32_t *hit_bundle, const int32_t *mate, const int64_t *rank, int32_t *f_h1, int32_t *f_h2, int32_t *f_type)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	if(mate[i] < 0) return;
+	int64_t f = rank[i];
+	f_h1[f] = (int32_t)(i - h.bundle_hit_off[hit_bundle[i]]);
+	f_h2[f] = mate[i];
+	f_type[f] = 0;
+}
+
+KERNEL k_gather_i64(int64_t n, const int64_t *idx, const int64_t *src, int64_t *out)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	out[i] = src[idx[i]];
+}
+
+} // namespace agpu
+
+struct fragments_state
+{
+	bool built = false;
+	agpu::dbuf<agpu::u64> slot_key;
+	agpu::dbuf<int32_t> slot_head, slot_min, slot_n, next, cursor, members, mate, tile_cnt;
+	agpu::dbuf<int64_t> hit_qslot, tile_off, rank, frg_off;
+	agpu::dbuf<int32_t> f_h1, f_h2, f_type, bridged;
+	int64_t n_frg = 0;
+	std::vector<int64_t> frg_off_host;
+
+	void release(agpu_ctx *ctx)
+	{
+		slot_key.release(ctx); slot_head.release(ctx); slot_min.release(ctx); slot_n.release(ctx); next.release(ctx);
+		cursor.release(ctx); members.release(ctx); mate.release(ctx); tile_cnt.release(ctx);
+		hit_qslot.release(ctx); tile_off.release(ctx); rank.release(ctx); frg_off.release(ctx);
+		f_h1.release(ctx); f_h2.release(ctx); f_type.release(ctx); bridged.release(ctx);
+		built = false; n_frg = 0;
+	}
+};
+
 #endif

@@ -187,7 +187,7 @@ struct std_sort_emul
 };
 
 template<typename Less>
-HD inline void std_sort_handles(int *a, int n, Less less)
+HD void std_sort_handles(int *a, int n, Less less)
 {
 	std_sort_emul<Less> s(a, less);
 	s.sort(0, n);

@@ -295,3 +295,48 @@ class Batch:
             out[-1]["edge"] = ea[order].reshape(-1).astype(np.int32)
             out[-1]["edge_d"] = wa[order]
         return out
+
+    def fetch_fragments(self):
+        v = FragmentsView()
+        self.ctx.check(self.ctx.L.agpu_fragments_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_fragments_fetch")
+        nb = self.nb
+        fo = _arr(v.frg_off, nb + 1, np.int64)
+        fr = _arr(v.frgs, 3 * int(fo[nb]) if nb else 0)
+        br = _arr(v.bridged, nb)
+        cs = self._chainset(v.fcst, nb, fo, "fcst", "frg_chain")
+        out = []
+        for k in range(nb):
+            d = {"frgs": fr[3 * int(fo[k]):3 * int(fo[k + 1])], "bridged": br[k:k + 1]}
+            d.update(cs[k])
+            out.append(d)
+        return out
+
+    def fetch_clusters(self, evidence):
+        """`evidence`: result of fetch_evidence (chain indices are expanded to coordinates)."""
+        v = ClusterView()
+        self.ctx.check(self.ctx.L.agpu_cluster_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_cluster_fetch")
+        nb = self.nb
+        co = _arr(v.clu_off, nb + 1, np.int64)
+        nc = int(v.n_clusters)
+        bo, ex, ct = _arr(v.bounds, 4 * nc), _arr(v.extend, 4 * nc), _arr(v.count, nc)
+        c1, c2 = _arr(v.chain1, nc), _arr(v.chain2, nc)
+        fo = _arr(v.frlist_off, nc + 1, np.int64)
+        fl = _arr(v.frlist, int(fo[nc]) if nc else 0)
+        out = []
+        for k in range(nb):
+            a, b = int(co[k]), int(co[k + 1])
+            ev = evidence[k]
+
+            def chains(idx):
+                off, val = [0], []
+                for c in idx:
+                    if c >= 0:
+                        val.extend(ev["hcst_val"][ev["hcst_off"][c]:ev["hcst_off"][c + 1]].tolist())
+                    off.append(len(val))
+                return np.array(off, np.int32), np.array(val, np.int32)
+            o1, v1 = chains(c1[a:b])
+            o2, v2 = chains(c2[a:b])
+            out.append({"clu_bounds": bo[4 * a:4 * b], "clu_extend": ex[4 * a:4 * b], "clu_count": ct[a:b],
+                        "clu_c1_off": o1, "clu_c1_val": v1, "clu_c2_off": o2, "clu_c2_val": v2,
+                        "clu_fr_off": (fo[a:b + 1] - fo[a]).astype(np.int32), "clu_fr_val": fl[int(fo[a]):int(fo[b])]})
+        return out
