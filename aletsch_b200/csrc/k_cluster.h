@@ -331,7 +331,7 @@ struct part_ctx
 	const int32_t *f_h1, *f_h2;  // bundle's fragments
 	const int32_t *pos, *rpos;   // bundle's hits
 	int gap;
-	DEV int32_t key(int r, int32_t fr) const
+	HD int32_t key(int r, int32_t fr) const
 	{
 		int32_t hh = (r < 2) ? f_h1[fr] : f_h2[fr];
 		return (r & 1) ? rpos[hh] : pos[hh];

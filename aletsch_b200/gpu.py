@@ -340,3 +340,26 @@ class Batch:
                         "clu_c1_off": o1, "clu_c1_val": v1, "clu_c2_off": o2, "clu_c2_val": v2,
                         "clu_fr_off": (fo[a:b + 1] - fo[a]).astype(np.int32), "clu_fr_val": fl[int(fo[a]):int(fo[b])]})
         return out
+
+    def fetch_bridge(self, clu_off):
+        v = BridgeView()
+        self.ctx.check(self.ctx.L.agpu_bridge_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_bridge_fetch")
+        nb = self.nb
+        nc = int(clu_off[nb]) if nb else 0
+        ty, st, ch = _arr(v.type, nc), _arr(v.strand, nc), _arr(v.choices, nc)
+        sc = _arr(v.score, nc, np.float64)
+        co, wo = _arr(v.chain_off, nc + 1, np.int64), _arr(v.whole_off, nc + 1, np.int64)
+        cv, wv = _arr(v.chain, int(co[nc]) if nc else 0), _arr(v.whole, int(wo[nc]) if nc else 0)
+        out = []
+        for k in range(nb):
+            a, b = int(clu_off[k]), int(clu_off[k + 1])
+            opt = np.stack([ty[a:b], st[a:b], ch[a:b]], axis=1).reshape(-1).astype(np.int32) if b > a else np.zeros(0, np.int32)
+            out.append({"opt": opt, "opt_score": sc[a:b],
+                        "opt_chain_off": (co[a:b + 1] - co[a]).astype(np.int32), "opt_chain_val": cv[int(co[a]):int(co[b])],
+                        "opt_whole_off": (wo[a:b + 1] - wo[a]).astype(np.int32), "opt_whole_val": wv[int(wo[a]):int(wo[b])]})
+        return out
+
+    def cluster_offsets(self):
+        v = ClusterView()
+        self.ctx.check(self.ctx.L.agpu_cluster_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_cluster_fetch")
+        return _arr(v.clu_off, self.nb + 1, np.int64)

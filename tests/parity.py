@@ -64,3 +64,59 @@ def compare_evidence_graph(ctx, batch, checker, gp, op):
             cmp_f64(n, rgr[n], gr[k][n], w, bad)
     bt.free()
     return bad
+
+
+INT_BRIDGE = ("opt", "opt_chain_off", "opt_chain_val", "opt_whole_off", "opt_whole_val")
+INT_CLUSTER = ("clu_bounds", "clu_extend", "clu_count", "clu_c1_off", "clu_c1_val", "clu_c2_off", "clu_c2_val", "clu_fr_off", "clu_fr_val")
+INT_FCST = ("fcst_off", "fcst_val", "fcst_cnt", "fcst_grp", "frg_chain")
+
+
+def compare_full(ctx, batch, checker, gp, op, stats=None):
+    """bundle::bridge (meta/bundle.cc:55-88) on the whole batch, every intermediate compared with the checker:
+    evidence, fragments, graph, clusters, bridge choices, updated fragments / fcst / coverage, bridged count."""
+    bad = []
+    hit_off = batch.a["bundle_hit_off"]
+    bt = ctx.upload(batch.view(), keepalive=batch)
+    bt.evidence(gp)
+    ev = bt.fetch_evidence(hit_off)
+    bt.fragments()
+    fr0 = bt.fetch_fragments()
+    bt.graph(gp)
+    gr = bt.fetch_graph()
+    bt.cluster(gp)
+    fr1 = bt.fetch_fragments()
+    cl = bt.fetch_clusters(ev)
+    bt.bridge(gp)
+    br = bt.fetch_bridge(bt.cluster_offsets())
+    bt.update()
+    fr2 = bt.fetch_fragments()
+    ev2 = bt.fetch_evidence(hit_off)
+    if stats is not None:
+        stats.update(bt.counts())
+    for k in range(batch.n_bundles):
+        h = checker.new_bundle(batch.bundle(k), op)
+        _, rev = checker.run(h, "evidence")
+        _, rfr = checker.run(h, "fragments")
+        _, rbr = checker.run(h, "bridge")
+        checker.free_bundle(h)
+        w = "bundle %d" % k
+        for n in INT_EVIDENCE:
+            cmp_int(n, rev[n], ev[k][n], w, bad)
+        cmp_int("frgs", rfr["frgs"], fr0[k]["frgs"], w + " build_fragments", bad)
+        for n in INT_GRAPH:
+            cmp_int(n, rbr[n], gr[k][n], w, bad)
+        for n in F64_GRAPH:
+            cmp_f64(n, rbr[n], gr[k][n], w, bad)
+        cmp_int("frgs", rbr["frgs_clustered"], fr1[k]["frgs"], w + " group_pereads", bad)
+        for n in INT_CLUSTER:
+            cmp_int(n, rbr[n], cl[k][n], w, bad)
+        for n in INT_BRIDGE:
+            cmp_int(n, rbr[n], br[k][n], w, bad)
+        cmp_f64("opt_score", rbr["opt_score"], br[k]["opt_score"], w, bad)
+        cmp_int("frgs", rbr["frgs"], fr2[k]["frgs"], w + " update_bridges", bad)
+        cmp_int("bridged", rbr["bridged"], fr2[k]["bridged"], w, bad)
+        for n in INT_FCST:
+            cmp_int(n, rbr[n], fr2[k][n], w, bad)
+        cmp_int("seg", rbr["seg"], ev2[k]["seg"], w + " update_bridges", bad)
+    bt.free()
+    return bad

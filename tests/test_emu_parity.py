@@ -24,3 +24,18 @@ def test_evidence_graph_parity(ctx, checkers, mode, templates):
     for name, chk in checkers.items():
         bad = parity.compare_evidence_graph(ctx, batch, chk, gp, op)
         assert not bad, "%s: %d mismatches, first: %s" % (name, len(bad), bad[:3])
+
+
+@pytest.mark.parametrize("mode,templates,seed", [(H.SYNTH_PAIRED, 60000, 20260101), (H.SYNTH_PAIRED, 150000, 20260102),
+                                                 (H.SYNTH_SINGLE, 20000, 20260104), (H.SYNTH_LONG, 3000, 20260105)])
+def test_bundle_bridge_parity(ctx, checkers, mode, templates, seed):
+    """the whole per-bundle path (bundle::bridge) with every intermediate compared"""
+    assert checkers
+    batch, lt = parity.make_batch(mode, templates, seed=seed)
+    gp, op = parity.params_pair(lt)
+    for name, chk in checkers.items():
+        stats = {}
+        bad = parity.compare_full(ctx, batch, chk, gp, op, stats)
+        assert not bad, "%s: %d mismatches, first: %s" % (name, len(bad), bad[:3])
+        if mode == H.SYNTH_PAIRED:
+            assert stats["bridged"] > 0 and stats["clusters"] > 0
