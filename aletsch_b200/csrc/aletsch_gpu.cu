@@ -250,6 +250,32 @@ const char *agpu_last_error(agpu_ctx *ctx) { return ctx ? ctx->last_error.c_str(
 int agpu_sync(agpu_ctx *ctx) { return ctx ? stream_sync(ctx) : AGPU_ERR_ARG; }
 int64_t agpu_launch_count(agpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int agpu_profile_enable(agpu_ctx *ctx, int on) { if(!ctx) return AGPU_ERR_ARG; ctx->profiling = on != 0; return AGPU_OK; }
+int agpu_profile_reset(agpu_ctx *ctx)
+{
+	if(!ctx) return AGPU_ERR_ARG;
+	TRY(stream_sync(ctx));
+	prof_collect(ctx);
+	ctx->prof_acc.clear();
+	return AGPU_OK;
+}
+int agpu_profile_read(agpu_ctx *ctx, char *buf, size_t cap)
+{
+	if(!ctx || !buf || cap == 0) return AGPU_ERR_ARG;
+	TRY(stream_sync(ctx));
+	prof_collect(ctx);
+	std::string out;
+	for(auto &kv : ctx->prof_acc)
+	{
+		char line[256];
+		snprintf(line, sizeof(line), "%s\t%.6f\t%lld\n", kv.first.c_str(), kv.second.first, (long long)kv.second.second);
+		out += line;
+	}
+	if(out.size() + 1 > cap) return AGPU_ERR_CAPACITY;
+	memcpy(buf, out.c_str(), out.size() + 1);
+	return AGPU_OK;
+}
+
 static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 {
 	TRY(b->err.alloc(ctx, ERR_WORDS, true));
@@ -317,7 +343,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	b->hcst.release(ctx); b->fcst.release(ctx);
 	b->tile_sum.release(ctx); b->tile_cnt.release(ctx); b->tile_pre.release(ctx); b->tile_seg_off.release(ctx); b->seg_off.release(ctx);
 	b->seg_l.release(ctx); b->seg_r.release(ctx); b->seg_c.release(ctx);
-	b->frg.release(ctx); b->gr.release(ctx); b->clu.release(ctx); b->brg.release(ctx);
+	b->frg.release(ctx); b->gr.release(ctx); b->clu.release(ctx); b->brg.release(ctx); b->brg.release_entries(ctx);
 	b->evidence = false; b->cov_dirty = true; b->n_seg = 0; b->ltot = 0;
 }
 

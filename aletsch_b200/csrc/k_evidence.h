@@ -114,6 +114,68 @@ KERNEL k_scan_i64(const int64_t *in, int64_t *out, int n)
 	for(int i = lo; i < hi; i++) { int64_t v = in[i]; out[i] = run; run += v; }
 }
 
+// ---- device-wide exclusive scan of int64: tile sums, single-CTA scan of the sums, per-tile apply
+#define SCAN64_TILE 2048
+KERNEL k_i64_tile_sum(const int64_t *in, int64_t n, int64_t n_tiles, int64_t *tile_sum)
+{
+	SHARED unsigned long long s;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		if(threadIdx.x == 0) s = 0;
+		BLOCK_SYNC();
+		unsigned long long acc = 0;
+		for(int i = threadIdx.x; i < SCAN64_TILE; i += blockDim.x)
+		{
+			int64_t g = t * SCAN64_TILE + i;
+			if(g < n) acc += (unsigned long long)in[g];
+		}
+		atomicAdd(&s, acc);
+		BLOCK_SYNC();
+		if(threadIdx.x == 0) tile_sum[t] = (int64_t)s;
+		BLOCK_SYNC();
+	}
+}
+
+KERNEL k_i64_tile_apply(const int64_t *in, int64_t n, int64_t n_tiles, const int64_t *tile_off, int64_t *out)
+{
+	SHARED int64_t f[SCAN64_TILE];
+	SHARED int64_t part[AGPU_MAX_BLOCK];
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		for(int i = threadIdx.x; i < SCAN64_TILE; i += blockDim.x)
+		{
+			int64_t g = t * SCAN64_TILE + i;
+			f[i] = g < n ? in[g] : 0;
+		}
+		BLOCK_SYNC();
+		int nt = blockDim.x, th = threadIdx.x;
+		int chunk = (SCAN64_TILE + nt - 1) / nt;
+		int lo = th * chunk, hi = lo + chunk;
+		if(lo > SCAN64_TILE) lo = SCAN64_TILE;
+		if(hi > SCAN64_TILE) hi = SCAN64_TILE;
+		int64_t sm = 0;
+		for(int i = lo; i < hi; i++) sm += f[i];
+		part[th] = sm;
+		BLOCK_SYNC();
+		if(th == 0)
+		{
+			int64_t run = tile_off[t];
+			for(int k = 0; k < nt; k++) { int64_t v = part[k]; part[k] = run; run += v; }
+		}
+		BLOCK_SYNC();
+		int64_t run = part[th];
+		for(int i = lo; i < hi; i++) { int64_t v = f[i]; f[i] = run; run += v; }
+		BLOCK_SYNC();
+		for(int i = threadIdx.x; i < SCAN64_TILE; i += blockDim.x)
+		{
+			int64_t g = t * SCAN64_TILE + i;
+			if(g < n) out[g] = f[i];
+		}
+		if(t == n_tiles - 1 && threadIdx.x == 0) out[n] = tile_off[n_tiles];
+		BLOCK_SYNC();
+	}
+}
+
 // hash of one intron chain (length + coordinates)
 HD u64 chain_hash(const int32_t *v, int n)
 {

@@ -5,8 +5,11 @@
 #include "dev.h"
 #include "../../include/aletsch_gpu.h"
 
+#include <map>
 #include <string>
 #include <vector>
+
+struct agpu_prof_rec { const char *name; void *e0, *e1; };
 
 struct agpu_ctx
 {
@@ -16,6 +19,11 @@ struct agpu_ctx
 	int64_t launches;
 	std::string last_error;
 	int sm_count;
+	// optional per-kernel timing (CUDA events around every launch on the ctx stream)
+	bool profiling = false;
+	std::vector<agpu_prof_rec> prof;
+	std::vector<void*> free_events;
+	std::map<std::string, std::pair<double, int64_t> > prof_acc;    // name -> (ms, launches)
 };
 
 namespace agpu {
@@ -23,12 +31,50 @@ namespace agpu {
 #ifndef AGPU_EMU
 #define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_); return AGPU_ERR_CUDA; } } while(0)
 
+inline void prof_begin(agpu_ctx *ctx, const char *name)
+{
+	if(!ctx->profiling) return;
+	agpu_prof_rec r;
+	r.name = name;
+	cudaEvent_t e[2];
+	for(int k = 0; k < 2; k++)
+	{
+		if(!ctx->free_events.empty()) { e[k] = (cudaEvent_t)ctx->free_events.back(); ctx->free_events.pop_back(); }
+		else cudaEventCreate(&e[k]);
+	}
+	r.e0 = e[0]; r.e1 = e[1];
+	cudaEventRecord(e[0], ctx->stream);
+	ctx->prof.push_back(r);
+}
+inline void prof_end(agpu_ctx *ctx)
+{
+	if(!ctx->profiling) return;
+	cudaEventRecord((cudaEvent_t)ctx->prof.back().e1, ctx->stream);
+}
+// fold finished records into the per-kernel accumulators (call after a stream synchronisation)
+inline void prof_collect(agpu_ctx *ctx)
+{
+	for(size_t k = 0; k < ctx->prof.size(); k++)
+	{
+		float ms = 0;
+		agpu_prof_rec &r = ctx->prof[k];
+		if(cudaEventElapsedTime(&ms, (cudaEvent_t)r.e0, (cudaEvent_t)r.e1) == cudaSuccess)
+		{
+			std::pair<double, int64_t> &a = ctx->prof_acc[r.name];
+			a.first += ms; a.second += 1;
+		}
+		else cudaGetLastError();
+		ctx->free_events.push_back(r.e0); ctx->free_events.push_back(r.e1);
+	}
+	ctx->prof.clear();
+}
+
 // per-thread kernel: grid covers n items
 #define LAUNCH_T(ctx, kern, n, ...) do { int64_t n_ = (int64_t)(n); if(n_ > 0) { unsigned g_ = (unsigned)((n_ + 255) / 256); \
-	kern<<<g_, 256, 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } } while(0)
+	prof_begin(ctx, #kern); kern<<<g_, 256, 0, (ctx)->stream>>>(__VA_ARGS__); prof_end(ctx); (ctx)->launches++; } } while(0)
 // block-cooperative kernel: one CTA per work item (the kernel loops if the grid is smaller)
 #define LAUNCH_B(ctx, kern, nblocks, nthreads, ...) do { int64_t n_ = (int64_t)(nblocks); if(n_ > 0) { unsigned g_ = (unsigned)(n_ > 1048576 ? 1048576 : n_); \
-	kern<<<g_, (nthreads), 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } } while(0)
+	prof_begin(ctx, #kern); kern<<<g_, (nthreads), 0, (ctx)->stream>>>(__VA_ARGS__); prof_end(ctx); (ctx)->launches++; } } while(0)
 
 inline int dev_alloc_bytes(agpu_ctx *ctx, void **p, size_t bytes, bool zero)
 {
@@ -80,6 +126,7 @@ inline int h2d(agpu_ctx *, void *d, const void *h, size_t bytes) { memcpy(d, h, 
 inline int d2h(agpu_ctx *, void *h, const void *d, size_t bytes) { memcpy(h, d, bytes); return AGPU_OK; }
 inline int d2d(agpu_ctx *, void *d, const void *s, size_t bytes) { memcpy(d, s, bytes); return AGPU_OK; }
 inline int stream_sync(agpu_ctx *) { return AGPU_OK; }
+inline void prof_collect(agpu_ctx *) {}
 inline void *pinned_alloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
 inline void pinned_free(void *p) { free(p); }
 #endif

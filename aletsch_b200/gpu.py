@@ -69,7 +69,8 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_upload", "agpu_batch_adopt", "agpu_batch_free", "agpu_batch_reset", "agpu_batch_evidence",
                "agpu_batch_fragments", "agpu_batch_graph", "agpu_batch_cluster", "agpu_batch_bridge", "agpu_batch_update",
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
-               "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity"]
+               "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
+               "agpu_profile_read"]
 
 
 def load(lib_path=None):
@@ -100,6 +101,9 @@ def load(lib_path=None):
     L.agpu_bridge_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BridgeView)]
     L.agpu_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Counts)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.agpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.agpu_profile_reset.argtypes = [C.c_void_p]
+    L.agpu_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     return L
 
 
@@ -156,6 +160,22 @@ class Context:
     @property
     def launches(self):
         return self.L.agpu_launch_count(self.h)
+
+    def profile(self, on=True):
+        self.check(self.L.agpu_profile_enable(self.h, 1 if on else 0), "agpu_profile_enable")
+
+    def profile_reset(self):
+        self.check(self.L.agpu_profile_reset(self.h), "agpu_profile_reset")
+
+    def profile_read(self):
+        """{kernel: (ms, launches)} accumulated since the last reset (synchronises)"""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.L.agpu_profile_read(self.h, buf, len(buf)), "agpu_profile_read")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            n, ms, cnt = line.split("\t")
+            out[n] = (float(ms), int(cnt))
+        return out
 
     def upload(self, batch_in, keepalive=None):
         return Batch(self, batch_in, False, keepalive)

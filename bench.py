@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the per-bundle read-evidence hot path (bundle::bridge, meta/bundle.cc:55-88)
+on synthetic sorted-BAM records of BASELINE.json's shape.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                     the reference's own C++ (oracle/_ref) on the host cores
+
+Workload at N = 1: configs[1] of BASELINE.json -- 10 synthetic paired_end samples x 5M pairs on one 100 Mb
+chromosome, bridging on.  For N > 1 every rank gets its own chromosome of that shape (weak scaling; bundles
+are independent, there is no data-path collective).  A step = one pass of the hot path over the batch:
+evidence (CIGAR -> coverage / chains) -> mate pairing -> splice graphs -> paired-read clusters -> bridging DP +
+vote -> update_bridges.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from aletsch_b200 import hostlib as H   # noqa: E402
+
+SAMPLES = 10
+PAIRS = 5_000_000
+CHROM_LEN = 100_000_000
+SEED = 20260101 + 1          # synth-v1, config index 1
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def build_workload(rank, scale, threads):
+    """records of SAMPLES samples on this rank's chromosome, packed into one batch of bundles"""
+    t0 = time.time()
+    cfg = H.default_config(H.SYNTH_PAIRED, chrom_len=CHROM_LEN, seed=SEED + 1000 * rank)
+    syn = H.Synth(cfg)
+    pairs = max(1000, int(PAIRS * scale))
+    recs = [None] * SAMPLES
+    n_records = [0] * SAMPLES
+
+    def work(k):
+        recs[k] = syn.sample(k, pairs, threads=2)
+        n_records[k] = recs[k]["n"]
+
+    sem = threading.Semaphore(max(1, threads // 2))
+
+    def guarded(k):
+        with sem:
+            work(k)
+
+    ths = [threading.Thread(target=guarded, args=(k,)) for k in range(SAMPLES)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    t1 = time.time()
+    batch = H.pack(recs, H.default_packer_params(H.FR_FIRST))
+    t2 = time.time()
+    log("[bench] rank %d: %d records generated in %.1fs, packed %d bundles / %d admitted hits in %.1fs" %
+        (rank, sum(n_records), t1 - t0, batch.n_bundles, batch.n_hits, t2 - t1))
+    return batch, sum(n_records), pairs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = "/tmp/agpu_clocks_%d_%d.csv" % (os.getpid(), index)
+
+    def start(self):
+        q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
+    """bytes a kernel has to read + write once per launch (DESIGN.md, section 'kernels'), from the real counts"""
+    Hh, S, L, F = cnt["hits"], cnt["segments"], cnt["span"], cnt["fragments"]
+    if kernel == "k_hit_cigar":
+        # in: pos, rpos, cigar_off (12 B/hit) + CIGAR ops; out: nspl, hash, bundle id (16 B/hit) + splice coordinates
+        # + one 4-byte difference word and one 4-byte bitmap word per block end
+        return Hh * (12 + 16) + 4 * n_cigar + 8 * n_splice_pairs + 16 * n_mblocks
+    if kernel == "k_cov_segments":
+        # difference array + border bitmap read once per pass, segments written once (12 B each)
+        return 2 * (4 * L + L // 8) + 12 * S
+    if kernel == "k_cov_tile_sum":
+        return 4 * L
+    if kernel == "k_qid_insert":
+        return Hh * (8 + 4 + 8 + 4) + Hh * 16       # qid, bundle id in; slot index, next out; one 16-byte slot touch
+    if kernel == "k_pair":
+        return Hh * (8 + 4 + 4 + 4 + 4 + 4)         # slot, next, pos, mpos, isize in; mate out
+    if kernel == "k_hcst_insert":
+        return Hh * (4 + 8 + 4 + 1 + 8) + 8 * n_splice_pairs
+    if kernel == "k_frag_align":
+        return F * (12 + 2 * (4 + 4 + 4) + 16 + 8 + 4)
+    return None
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from aletsch_b200 import gpu as G
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ncpu = os.cpu_count() or 8
+    batch, n_records, pairs = build_workload(rank, args.scale, max(2, ncpu // max(1, world)))
+    gp = G.default_params(library_type=H.FR_FIRST)
+
+    stream = torch.cuda.current_stream()
+    ctx = G.Context(local, stream=stream.cuda_stream)
+
+    # pinned host copies (e2e path) and device-resident copies (kernel path)
+    fields = ["bundle_hit_off", "bundle_tid", "bundle_sample", "pos", "rpos", "mpos", "isize", "flag", "strand", "xs", "qid", "cigar_off", "cigar"]
+    pinned, dev = {}, {}
+    h2d_bytes = 0
+    for f in fields:
+        a = batch.a[f]
+        v = a.view(np.int64) if a.dtype == np.uint64 else (a.view(np.int32) if a.dtype == np.uint32 else (a.view(np.int16) if a.dtype == np.uint16 else a))
+        t = torch.from_numpy(v).pin_memory()
+        pinned[f] = t
+        dev[f] = t.to("cuda", non_blocking=True)
+        h2d_bytes += t.numel() * t.element_size()
+    torch.cuda.synchronize()
+
+    def view_of(tensors):
+        b = H.BatchIn()
+        b.n_bundles, b.n_hits, b.n_cigar = batch.n_bundles, batch.n_hits, batch.n_cigar
+        for f in fields:
+            setattr(b, f, tensors[f].data_ptr())
+        return b
+
+    n_hits = batch.n_hits
+    cig = batch.a["cigar"]
+    ops = cig & 0xF
+    n_mblocks = int(np.count_nonzero(ops == 0))
+    n_cigar = int(batch.n_cigar)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: inputs already in HBM, a step = reset + bridge_all -------------------
+    bt = ctx.adopt(view_of(dev), keepalive=dev)
+    counts = None
+    for _ in range(args.warmup):
+        bt.reset()
+        bt.bridge_all(gp)
+    ctx.sync()
+    counts = bt.counts()
+    ctx.profile(True)
+    ctx.profile_reset()
+    launches0 = ctx.launches
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        bt.reset()
+        bt.bridge_all(gp)
+    e1.record(stream)
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    counts = bt.counts()
+    bt.free()
+
+    # ---- end to end: pinned host buffers -> upload -> bridge_all -> counters back to the host ----------
+    for _ in range(min(args.warmup, 1)):
+        b2 = ctx.upload(view_of(pinned), keepalive=pinned)
+        b2.bridge_all(gp)
+        b2.counts()
+        b2.free()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    d2h_bytes = 0
+    for _ in range(args.steps):
+        b2 = ctx.upload(view_of(pinned), keepalive=pinned)
+        b2.bridge_all(gp)
+        c2 = b2.counts()
+        d2h_bytes = 6 * 4 * batch.n_bundles
+        b2.free()
+    e3.record(stream)
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+
+    # max over ranks, totals over ranks
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_hits), float(counts["bridged"]), float(h2d_bytes), float(d2h_bytes)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    hits_all, bridged_all = float(tot[0]), float(tot[1])
+
+    if rank == 0:
+        steps = args.steps
+        value = hits_all * steps / (ms_dev / 1e3)
+        e2e_value = hits_all * steps / (ms_e2e / 1e3)
+        # dominant kernel by accumulated device time
+        total_k = sum(v[0] for v in prof.values())
+        top = sorted(prof.items(), key=lambda kv: -kv[1][0])
+        for name, (ms, cnt) in top[:14]:
+            log("[bench] kernel %-22s %9.3f ms/step  (%d launches/step, %.1f%% of kernel time)" %
+                (name, ms / steps, cnt // steps, 100 * ms / max(total_k, 1e-9)))
+        dom = None
+        n_pairs_spl = counts["splice_ints"]   # placeholder, replaced below
+        # splice pairs over hits: inner N ops
+        n_splice_pairs = int(np.count_nonzero(ops == 3))
+        for name, (ms, cnt) in top:
+            ab = algorithmic_bytes(name, counts, n_cigar, n_mblocks, n_splice_pairs)
+            if ab is not None:
+                dom = (name, ms, cnt, ab)
+                break
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        roof = None
+        if dom:
+            name, ms, cnt, ab = dom
+            per_launch_ms = ms / cnt
+            launches_per_step = cnt / steps
+            achieved = ab / launches_per_step / (per_launch_ms / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    "algorithmic_bytes_per_launch": ab / launches_per_step, "ms_per_launch": per_launch_ms,
+                    "share_of_kernel_time": ms / max(total_k, 1e-9), "traffic": None}
+        out = {"metric": "hits_per_sec", "value": value, "unit": "hits/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+               "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+               "data": "synthetic", "impl": "ours",
+               "config": {"workload": "configs[1]: %d synthetic paired_end samples x %d pairs, 1 chromosome of %d bp per GPU, bridging on"
+                          % (SAMPLES, pairs, CHROM_LEN), "generator": "synth-v1 seed %d" % SEED,
+                          "records_per_gpu": n_records, "admitted_hits_per_gpu": n_hits, "bundles_per_gpu": batch.n_bundles,
+                          "l2": "inputs (%.1f GB) and scratch far larger than the 126 MB L2" % (h2d_bytes / 1e9), "scale": args.scale},
+               "bridged_pairs_per_sec": bridged_all * steps / (ms_dev / 1e3), "bridged_pairs_per_step": bridged_all,
+               "counts": counts, "gpu_launches": int(launches),
+               "e2e": {"value": e2e_value, "unit": "hits/s", "h2d_bytes_per_step": float(tot[2]), "d2h_bytes_per_step": float(tot[3]),
+                       "ms_per_step": ms_e2e / steps},
+               "roofline": roof, "clocks": clk}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(batch, min(10, ncpu), args.cpu_seconds)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(batch, threads, budget_s, all_cores=False):
+    """the reference's own C++ (oracle/_ref) over a bounded sample of the same bundles, one bundle per task
+    on a pool of `threads` workers (the granularity of aletsch -t N, meta/incubator.cc:615-635)"""
+    import orclib
+    kind = "reference"
+    try:
+        chk0 = orclib.Checker("ref")
+    except (OSError, FileNotFoundError):
+        chk0 = orclib.Checker("orc")
+        kind = "port"
+    del chk0
+    op = orclib.default_params(library_type=H.FR_FIRST)
+    sizes = np.diff(batch.a["bundle_hit_off"])
+    # bounded sample: every k-th bundle until the estimated work fits the budget (~60k hits/s per core)
+    target_hits = int(60_000 * threads * budget_s)
+    step = max(1, int(np.ceil(sizes.sum() / max(target_hits, 1))))
+    sample = list(range(0, batch.n_bundles, step))
+    bundles = [batch.bundle(k) for k in sample]
+    hits = int(sum(len(b["pos"]) for b in bundles))
+    lock = threading.Lock()
+    nxt = [0]
+    bridged = [0]
+
+    def worker():
+        chk = orclib.Checker("ref" if kind == "reference" else "orc")
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= len(bundles):
+                return
+            h = chk.new_bundle(bundles[i], op)
+            chk.run_quiet(h, "fragments")
+            c = chk.run_quiet(h, "bridge")
+            chk.free_bundle(h)
+            with lock:
+                bridged[0] += max(c, 0)
+
+    t0 = time.time()
+    ths = [threading.Thread(target=worker) for _ in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.time() - t0
+    return {"value": hits / dt, "unit": "hits/s", "cores": threads, "kind": kind,
+            "sample": "every %d-th bundle of the same batch: %d bundles, %d hits, %.1f s wall" % (step, len(bundles), hits, dt),
+            "bridged_pairs_per_sec": bridged[0] / dt}
+
+
+def run_reference(args):
+    """reference arm: the reference's own CPU implementation of the path on all host cores"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncpu = os.cpu_count() or 8
+    batch, n_records, pairs = build_workload(0, args.scale, ncpu)
+    per_step = max(2.0, args.cpu_seconds / max(1, args.steps + args.warmup))
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(batch, ncpu, per_step)
+        if i >= args.warmup:
+            vals.append(r)
+        last = r
+    value = float(np.mean([v["value"] for v in vals]))
+    bps = float(np.mean([v["bridged_pairs_per_sec"] for v in vals]))
+    hits_sample = float(last["sample"].split("bundles, ")[1].split(" hits")[0])
+    out = {"metric": "hits_per_sec", "value": value, "unit": "hits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * hits_sample / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": "configs[1]: %d synthetic paired_end samples x %d pairs, 1 chromosome of %d bp per GPU, bridging on"
+                      % (SAMPLES, pairs, CHROM_LEN), "generator": "synth-v1 seed %d" % SEED, "scale": args.scale},
+           "bridged_pairs_per_sec": bps,
+           "cpu_baseline": {"value": value, "unit": "hits/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+           "e2e": {"value": value, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 5M pairs per sample (development only; 1.0 = the named config)")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

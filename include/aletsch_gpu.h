@@ -118,6 +118,12 @@ int agpu_sync(agpu_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t agpu_launch_count(agpu_ctx *ctx);
 
+/* optional per-kernel timing: CUDA events around every launch of this context.  agpu_profile_read
+ * synchronises and writes "kernel_name\tms\tlaunches\n" lines (cumulative since the last reset). */
+int agpu_profile_enable(agpu_ctx *ctx, int on);
+int agpu_profile_reset(agpu_ctx *ctx);
+int agpu_profile_read(agpu_ctx *ctx, char *buf, size_t cap);
+
 /* ---- batch life cycle ---------------------------------------------------------------- */
 /* host -> device copy of the packed batch (cudaMemcpyAsync per array on the ctx stream) */
 int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out);
