@@ -437,4 +437,61 @@ int ref_group_resolve(void **bs, int n, const orc_params *prm, void *bagp)
 	return 0;
 }
 
+
+// known-answer and randomised checks of the Boost.ICL stand-in (oracle/compat/boost/icl/interval_map.hpp), through the
+// reference's own helpers (create_split, locate_boundary_iterators, compute_coverage, get_overlapped_length)
+int ref_icl_kat(int32_t *out, int cap)
+{
+	int n = 0;
+	// rnacore/interval_map.cc:320-331 (test_split_interval_map)
+	split_interval_map imap;
+	imap += make_pair(ROI(6, 7), 3);
+	imap += make_pair(ROI(1, 3), 3);
+	imap += make_pair(ROI(1, 2), 1);
+	imap += make_pair(ROI(2, 5), 2);
+	create_split(imap, 4);
+	for(SIMI it = imap.begin(); it != imap.end() && n + 3 <= cap; it++) { out[n++] = lower(it->first); out[n++] = upper(it->first); out[n++] = it->second; }
+	if(n < cap) out[n++] = -1;
+	// coverage [i, j) for 0 <= i <= j <= 8 (:372-380)
+	for(int i = 0; i <= 8; i++)
+		for(int j = i; j <= 8; j++)
+		{
+			pair<SIMI, SIMI> p = locate_boundary_iterators(imap, i, j);
+			if(n < cap) out[n++] = compute_coverage(imap, p.first, p.second);
+		}
+	if(n < cap) out[n++] = -1;
+	// rnacore/interval_map.cc:435-451 (test_join_interval_map)
+	join_interval_map m1, m2;
+	m1 += make_pair(ROI(6, 7), 3);
+	m1 += make_pair(ROI(1, 2), 1);
+	m1 += make_pair(ROI(2, 5), 1);
+	m2 += make_pair(ROI(1, 3), 3);
+	m2 += make_pair(ROI(3, 4), 3);
+	m2 += make_pair(ROI(5, 7), 1);
+	if(n < cap) out[n++] = get_overlapped_length(m1, m2);
+	if(n < cap) out[n++] = (int32_t)std::distance(m1.begin(), m1.end());
+	if(n < cap) out[n++] = (int32_t)std::distance(m2.begin(), m2.end());
+	if(n < cap) out[n++] = (int32_t)m1.size();          // ICL size() is the cardinality: 4 + 1
+	return n;
+}
+
+// apply additions (l, r, v) to a split (join = 0) or joining (join = 1) map and dump its segments
+int ref_icl_apply(int n, const int32_t *l, const int32_t *r, const int32_t *v, int join, int32_t *out, int cap)
+{
+	int k = 0;
+	if(join)
+	{
+		join_interval_map m;
+		for(int i = 0; i < n; i++) m += make_pair(ROI(l[i], r[i]), v[i]);
+		for(JIMI it = m.begin(); it != m.end() && k + 3 <= cap; it++) { out[k++] = lower(it->first); out[k++] = upper(it->first); out[k++] = it->second; }
+	}
+	else
+	{
+		split_interval_map m;
+		for(int i = 0; i < n; i++) m += make_pair(ROI(l[i], r[i]), v[i]);
+		for(SIMI it = m.begin(); it != m.end() && k + 3 <= cap; it++) { out[k++] = lower(it->first); out[k++] = upper(it->first); out[k++] = it->second; }
+	}
+	return k;
+}
+
 }
