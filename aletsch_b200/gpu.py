@@ -70,7 +70,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_fragments", "agpu_batch_graph", "agpu_batch_cluster", "agpu_batch_bridge", "agpu_batch_update",
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
-               "agpu_profile_read"]
+               "agpu_profile_read", "agpu_group_resolve"]
 
 
 def load(lib_path=None):
@@ -101,6 +101,7 @@ def load(lib_path=None):
     L.agpu_bridge_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BridgeView)]
     L.agpu_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Counts)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.agpu_group_resolve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
     L.agpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.agpu_profile_reset.argtypes = [C.c_void_p]
     L.agpu_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
@@ -195,6 +196,29 @@ class Context:
         r = np.zeros((g, g), np.float64)
         self.check(self.L.agpu_similarity(self.h, g, off.ctypes.data, val.ctypes.data, c.ctypes.data, r.ctypes.data), "agpu_similarity")
         return c, r
+
+
+def _pack_lists(lists):
+    g = len(lists)
+    off = np.zeros(g + 1, np.int64)
+    for i, l in enumerate(lists):
+        off[i + 1] = off[i] + len(l)
+    val = np.concatenate([np.asarray(l, np.int32) for l in lists]) if g and off[g] else np.zeros(1, np.int32)
+    return off, np.ascontiguousarray(val, np.int32)
+
+
+def group_resolve(ctx, lists, params):
+    """bundle_group::resolve over sorted splice lists; returns the groups (lists of bundle indices) in gvv order"""
+    off, val = _pack_lists(lists)
+    g = len(lists)
+    grp = np.zeros(max(g, 1), np.int32)
+    ng = C.c_int32(0)
+    ctx.check(ctx.L.agpu_group_resolve(ctx.h, g, off.ctypes.data, val.ctypes.data, C.byref(params), grp.ctypes.data, C.byref(ng)),
+              "agpu_group_resolve")
+    out = [[] for _ in range(ng.value)]
+    for i in range(g):
+        out[grp[i]].append(i)
+    return out
 
 
 class Batch:

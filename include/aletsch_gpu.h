@@ -242,6 +242,14 @@ int agpu_batch_counts(agpu_ctx *ctx, agpu_batch *b, agpu_counts *c);
 int agpu_similarity(agpu_ctx *ctx, int32_t n_lists, const int64_t *list_off, const int32_t *list_val,
 		int32_t *out_c, double *out_r);
 
+/* bundle_group::resolve (meta/bundle_group.cc:26-56) over G bundles given by their sorted splice lists: splice-position
+ * inverted index, two rounds (max_grouping_similarity, then min_grouping_similarity) of size-capped single-linkage with the
+ * pairwise similarities taken from the device (agpu_similarity).  out_group_of[i] = group of bundle i, groups numbered in
+ * first-member order like bundle_group::gvv (build_groups, :320-342).  The unions follow the reference's order: pairs of one
+ * splice position sorted by r descending with std::sort (ties as libstdc++ leaves them). */
+int agpu_group_resolve(agpu_ctx *ctx, int32_t n_lists, const int64_t *list_off, const int32_t *list_val, const agpu_params *p,
+		int32_t *out_group_of, int32_t *out_n_groups);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,3 +39,29 @@ def test_bundle_bridge_parity(ctx, checkers, mode, templates, seed):
         assert not bad, "%s: %d mismatches, first: %s" % (name, len(bad), bad[:3])
         if mode == H.SYNTH_PAIRED:
             assert stats["bridged"] > 0 and stats["clusters"] > 0
+
+
+def test_group_resolve_parity(ctx, checkers):
+    """bundle_group::resolve: device similarity + host control flow against the checker, with the size cap binding"""
+    import numpy as np
+    from aletsch_b200 import gpu as G
+    batch, lt = parity.make_batch(H.SYNTH_PAIRED, 30000, samples=6)
+    gp, op = parity.params_pair(lt, max_group_size=4)
+    n = min(batch.n_bundles, 200)
+    for name, chk in checkers.items():
+        hs = [chk.new_bundle(batch.bundle(k), op) for k in range(n)]
+        lists = [chk.run(h, "evidence")[1]["splices"] for h in hs]
+        _, gr = chk.group_resolve(hs, op)
+        for h in hs:
+            chk.free_bundle(h)
+        want = [gr["gvv_val"][gr["gvv_off"][i]:gr["gvv_off"][i + 1]].tolist() for i in range(len(gr["gvv_off"]) - 1)]
+        got = G.group_resolve(ctx, lists, gp)
+        assert got == want, name
+        assert max(len(g) for g in want) == 4
+    c, r = ctx.similarity(lists)
+    for i in range(0, n, 7):
+        for j in range(i + 1, n, 3):
+            cc = len(np.intersect1d(lists[i], lists[j]))
+            assert cc == c[i, j]
+            if cc:
+                assert abs(r[i, j] - cc / min(len(lists[i]), len(lists[j]))) <= 1e-9 * r[i, j]       # BASELINE.json tolerance
