@@ -412,31 +412,41 @@ static int chainset_finish(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int
 	return AGPU_OK;
 }
 
-// coverage difference array -> segments
+// coverage difference array -> segments (single pass with decoupled look-back)
 static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 {
 	int64_t nt = b->ltot / COV_TILE;
-	TRY(b->tile_sum.alloc(ctx, nt + 1)); TRY(b->tile_cnt.alloc(ctx, nt + 1));
-	TRY(b->tile_pre.alloc(ctx, nt + 2)); TRY(b->tile_seg_off.alloc(ctx, nt + 2));
+	TRY(b->tile_seg_off.alloc(ctx, nt + 2, true));
 	TRY(b->seg_off.alloc(ctx, b->nb + 1, true));
 	b->n_seg = 0;
 	if(nt > 0)
 	{
-		LAUNCH_B(ctx, k_cov_tile_sum, nt, 256, b->diff.p, nt, b->tile_sum.p);
-		LAUNCH_B(ctx, k_scan_i32_to_i64, 1, 1024, b->tile_sum.p, b->tile_pre.p, nt);
-		LAUNCH_B(ctx, k_cov_segments, nt, 256, b->diff.p, b->border.p, nt, b->tile_pre.p, 0, b->tile_cnt.p, b->tile_seg_off.p,
-				b->nb, b->cov_base.p, b->b_lpos.p, (int32_t*)NULL, (int32_t*)NULL, (int32_t*)NULL);
-		LAUNCH_B(ctx, k_scan_i32_to_i64, 1, 1024, b->tile_cnt.p, b->tile_seg_off.p, nt);
-		TRY(d2h(ctx, &b->n_seg, b->tile_seg_off.p + nt, sizeof(int64_t)));
+		dbuf<u64> cov_state, seg_state;
+		dbuf<int> ticket;
+		dbuf<unsigned long long> nbord;
+		TRY(cov_state.alloc(ctx, nt + 1, true)); TRY(seg_state.alloc(ctx, nt + 1, true)); TRY(ticket.alloc(ctx, 1, true)); TRY(nbord.alloc(ctx, 1, true));
+		int64_t nwords = b->ltot / 32;
+		LAUNCH_T(ctx, k_border_count, nwords, b->border.p, nwords, nbord.p);
+		unsigned long long cap = 0;
+		TRY(d2h(ctx, &cap, nbord.p, sizeof(cap)));
 		TRY(stream_sync(ctx));
-	}
-	TRY(b->seg_l.alloc(ctx, b->n_seg + 1)); TRY(b->seg_r.alloc(ctx, b->n_seg + 1)); TRY(b->seg_c.alloc(ctx, b->n_seg + 1));
-	if(nt > 0)
-	{
-		LAUNCH_B(ctx, k_cov_segments, nt, 256, b->diff.p, b->border.p, nt, b->tile_pre.p, 1, b->tile_cnt.p, b->tile_seg_off.p,
-				b->nb, b->cov_base.p, b->b_lpos.p, b->seg_l.p, b->seg_r.p, b->seg_c.p);
+		TRY(b->seg_l.alloc(ctx, cap + 1)); TRY(b->seg_r.alloc(ctx, cap + 1)); TRY(b->seg_c.alloc(ctx, cap + 1));
+		cov_scan_args a;
+		a.diff = b->diff.p; a.border = b->border.p; a.n_tiles = nt; a.cov_state = cov_state.p; a.seg_state = seg_state.p; a.ticket = ticket.p;
+		a.tile_seg_off = b->tile_seg_off.p; a.n_bundles = b->nb; a.cov_base = b->cov_base.p; a.b_lpos = b->b_lpos.p;
+		a.seg_l = b->seg_l.p; a.seg_r = b->seg_r.p; a.seg_c = b->seg_c.p; a.seg_cap = (int64_t)cap; a.err = b->err.p;
+		int64_t grid = (int64_t)ctx->sm_count * 8;
+		if(grid > nt) grid = nt;
+#ifdef AGPU_EMU
+		grid = 1;
+#endif
+		LAUNCH_B(ctx, k_cov_scan, grid, CS_THREADS, a);
+		TRY(d2h(ctx, &b->n_seg, b->tile_seg_off.p + nt, sizeof(int64_t)));
 		LAUNCH_T(ctx, k_seg_off, b->nb + 1, b->nb, b->cov_base.p, b->tile_seg_off.p, b->seg_off.p);
+		TRY(stream_sync(ctx));
+		cov_state.release(ctx); seg_state.release(ctx); ticket.release(ctx); nbord.release(ctx);
 	}
+	else { TRY(b->seg_l.alloc(ctx, 1)); TRY(b->seg_r.alloc(ctx, 1)); TRY(b->seg_c.alloc(ctx, 1)); }
 	b->cov_dirty = false;
 	return AGPU_OK;
 }

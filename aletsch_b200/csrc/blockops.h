@@ -9,29 +9,21 @@ namespace agpu {
 
 #define AGPU_MAX_BLOCK 1024
 
+#define SORT_SMEM_CAP 2048
+
 // Normalised bitonic network (all compare-exchanges ascending; the first step of every merge
 // pairs i with i ^ (k - 1)).  With this form, virtual +inf padding beyond n never moves, so
 // any n works in place.  Keys must be distinct for a deterministic result (callers pack a
-// unique rank into the low bits).
-DEV void block_sort_u64(u64 *key, int n)
+// unique rank into the low bits).  Up to SORT_SMEM_CAP keys are sorted in shared memory.
+DEV void bitonic_u64(u64 *key, int n)
 {
 	for(int k = 2; (k >> 1) < n; k <<= 1)
 	{
-		for(int i = threadIdx.x; i < n; i += blockDim.x)
-		{
-			int p = i ^ (k - 1);
-			if(p > i && p < n)
-			{
-				u64 a = key[i], b = key[p];
-				if(b < a) { key[i] = b; key[p] = a; }
-			}
-		}
-		BLOCK_SYNC();
-		for(int j = k >> 2; j > 0; j >>= 1)
+		for(int j = k >> 1, first = 1; j > 0; j >>= 1, first = 0)
 		{
 			for(int i = threadIdx.x; i < n; i += blockDim.x)
 			{
-				int p = i ^ j;
+				int p = first ? (i ^ (k - 1)) : (i ^ j);
 				if(p > i && p < n)
 				{
 					u64 a = key[i], b = key[p];
@@ -43,8 +35,29 @@ DEV void block_sort_u64(u64 *key, int n)
 	}
 }
 
-// same network over (key, val) pairs ordered by key then val
-DEV void block_sort_pairs(u64 *key, u32 *val, int n)
+// one shared staging pool for both sorts: SORT_SMEM_CAP keys followed by SORT_SMEM_CAP 32-bit payloads
+DEV u64 *sort_pool()
+{
+	SHARED u64 pool[SORT_SMEM_CAP + SORT_SMEM_CAP / 2];
+	return pool;
+}
+
+DEV void block_sort_u64(u64 *key, int n)
+{
+	u64 *sk = sort_pool();
+	if(n <= 1) return;
+	if(n <= SORT_SMEM_CAP)
+	{
+		for(int i = threadIdx.x; i < n; i += blockDim.x) sk[i] = key[i];
+		BLOCK_SYNC();
+		bitonic_u64(sk, n);
+		for(int i = threadIdx.x; i < n; i += blockDim.x) key[i] = sk[i];
+		BLOCK_SYNC();
+	}
+	else bitonic_u64(key, n);
+}
+
+DEV void bitonic_pairs(u64 *key, u32 *val, int n)
 {
 	for(int k = 2; (k >> 1) < n; k <<= 1)
 	{
@@ -63,6 +76,23 @@ DEV void block_sort_pairs(u64 *key, u32 *val, int n)
 			BLOCK_SYNC();
 		}
 	}
+}
+
+// same network over (key, val) pairs ordered by key then val
+DEV void block_sort_pairs(u64 *key, u32 *val, int n)
+{
+	u64 *sk = sort_pool();
+	u32 *sv = (u32*)(sk + SORT_SMEM_CAP);
+	if(n <= 1) return;
+	if(n <= SORT_SMEM_CAP)
+	{
+		for(int i = threadIdx.x; i < n; i += blockDim.x) { sk[i] = key[i]; sv[i] = val[i]; }
+		BLOCK_SYNC();
+		bitonic_pairs(sk, sv, n);
+		for(int i = threadIdx.x; i < n; i += blockDim.x) { key[i] = sk[i]; val[i] = sv[i]; }
+		BLOCK_SYNC();
+	}
+	else bitonic_pairs(key, val, n);
 }
 
 // exclusive prefix sum of a[0..n) in place; returns the total to every thread

@@ -326,8 +326,8 @@ KERNEL k_val_tile_scan(const int32_t *v, int64_t n, int64_t n_tiles, const int64
 
 struct part_ctx
 {
-	int32_t *m;                  // members (bundle-local fragment indices) of the group, in place
-	int32_t *cflag;              // cluster-start flags parallel to m
+	u64 *el;                     // elements of the group: key of the current level in the high word, fragment in the low word
+	int32_t *cflag;              // cluster-start flags parallel to el
 	const int32_t *f_h1, *f_h2;  // bundle's fragments
 	const int32_t *pos, *rpos;   // bundle's hits
 	int gap;
@@ -338,23 +338,25 @@ struct part_ctx
 	}
 };
 
+// compare_rank0..3 (rnacore/graph_cluster.cc:205-208) on elements that carry their key in the high word
+// (biased so that the unsigned order of the word is the signed order of the key)
 struct key_less
 {
-	const part_ctx *c;
-	int r;
-	HD bool operator()(int x, int y) const { return c->key(r, x) < c->key(r, y); }
+	HD bool operator()(u64 x, u64 y) const { return (x >> 32) < (y >> 32); }
 };
+HD u64 pack_key(int32_t key, int32_t fr) { return ((u64)((u32)key ^ 0x80000000u) << 32) | (u64)(u32)fr; }
+HD int32_t unpack_key(u64 e) { return (int32_t)((u32)(e >> 32) ^ 0x80000000u); }
 
 // graph_cluster::partition (rnacore/graph_cluster.cc:170-203), in place on the member array
 template<int R> DEV void partition_rec(const part_ctx &c, int lo, int hi)
 {
+	for(int k = lo; k < hi; k++) { int32_t fr = (int32_t)(u32)(c.el[k] & 0xffffffffULL); c.el[k] = pack_key(c.key(R, fr), fr); }
 	key_less less;
-	less.c = &c; less.r = R;
-	std_sort_handles(c.m + lo, hi - lo, less);
+	std_sort_handles(c.el + lo, hi - lo, less);
 	int pre = lo;
 	for(int k = lo + 1; k <= hi; k++)
 	{
-		if(k < hi && c.key(R, c.m[k]) - c.key(R, c.m[k - 1]) <= c.gap) continue;
+		if(k < hi && unpack_key(c.el[k]) - unpack_key(c.el[k - 1]) <= c.gap) continue;
 		partition_rec<R + 1>(c, pre, k);
 		pre = k;
 	}
@@ -363,7 +365,7 @@ template<> DEV void partition_rec<4>(const part_ctx &c, int lo, int hi) { (void)
 
 // ---- C3: the first fragment of every group gathers the members (ascending fragment index) and partitions them
 KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
-		cluster_dev c, const int32_t *leader, const int64_t *member_off, int32_t *members, int32_t *cflag, int gap)
+		cluster_dev c, const int32_t *leader, const int64_t *member_off, int32_t *members, u64 *elems, int32_t *cflag, int gap)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(f >= n_frg) return;
@@ -404,11 +406,13 @@ KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_of
 		}
 	}
 	part_ctx pc;
-	pc.m = m; pc.cflag = cflag + member_off[f];
+	pc.el = elems + member_off[f]; pc.cflag = cflag + member_off[f];
+	for(int i = 0; i < n; i++) pc.el[i] = (u64)(u32)m[i];
 	pc.f_h1 = f_h1 + f0; pc.f_h2 = f_h2 + f0;
 	pc.pos = h.pos + h.bundle_hit_off[b]; pc.rpos = h.rpos + h.bundle_hit_off[b];
 	pc.gap = gap;
 	partition_rec<0>(pc, 0, n);
+	for(int i = 0; i < n; i++) m[i] = (int32_t)(u32)(pc.el[i] & 0xffffffffULL);
 }
 
 struct clusters_out
@@ -472,7 +476,7 @@ struct cluster_state
 	agpu::dbuf<int32_t> cp_valid, cp_mono, cp_first, cp_last, cp_nruns, cp_runs;
 	// per fragment
 	agpu::dbuf<int32_t> f_ok, m_a1, m_a2, f_next, leader, leader_size;
-	agpu::dbuf<agpu::u64> f_hash, slot_word;
+	agpu::dbuf<agpu::u64> f_hash, slot_word, elems;
 	agpu::dbuf<int64_t> f_slot, reg_off, member_off, member_boff, crank, clu_off;
 	agpu::dbuf<int32_t> slot_min, slot_n, slot_head, members, cflag, tile_cnt;
 	agpu::dbuf<int64_t> tile_off, grank;
@@ -486,7 +490,7 @@ struct cluster_state
 	{
 		cp_valid.release(ctx); cp_mono.release(ctx); cp_first.release(ctx); cp_last.release(ctx); cp_nruns.release(ctx); cp_runs.release(ctx);
 		f_ok.release(ctx); m_a1.release(ctx); m_a2.release(ctx); f_next.release(ctx); leader.release(ctx); leader_size.release(ctx);
-		f_hash.release(ctx); slot_word.release(ctx); f_slot.release(ctx); reg_off.release(ctx); member_off.release(ctx);
+		f_hash.release(ctx); slot_word.release(ctx); elems.release(ctx); f_slot.release(ctx); reg_off.release(ctx); member_off.release(ctx);
 		member_boff.release(ctx); crank.release(ctx); clu_off.release(ctx);
 		slot_min.release(ctx); slot_n.release(ctx); slot_head.release(ctx); members.release(ctx); cflag.release(ctx); tile_cnt.release(ctx);
 		tile_off.release(ctx); grank.release(ctx);

@@ -558,6 +558,242 @@ KERNEL k_cov_segments(const int32_t *diff, const u32 *border, int64_t n_tiles, c
 	}
 }
 
+// ---- single-pass coverage scan (decoupled look-back): one read of the difference array and the border bitmap,
+// segments written once.  Two chained look-backs per tile: the coverage prefix (needed to know which borders open a
+// segment) and then the segment-count prefix (the output offset).
+#define CS_THREADS 256
+#define CS_ITEMS 8                 // CS_THREADS * CS_ITEMS == COV_TILE
+#define ST_AGG 1ULL
+#define ST_INCL 2ULL
+
+HD u64 st_pack(u64 status, long long v) { return (status << 62) | ((u64)v & 0x3fffffffffffffffULL); }
+HD u64 st_status(u64 x) { return x >> 62; }
+HD long long st_value(u64 x) { return ((long long)(x << 2)) >> 2; }
+
+KERNEL k_border_count(const u32 *border, int64_t n_words, unsigned long long *total)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int c = (i < n_words) ? __popc(border[i]) : 0;
+#ifndef AGPU_EMU
+	for(int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+	if((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
+#else
+	if(c) *total += (unsigned long long)c;
+#endif
+}
+
+struct cov_scan_args
+{
+	const int32_t *diff;
+	const u32 *border;
+	int64_t n_tiles;
+	u64 *cov_state, *seg_state;
+	int *ticket;
+	int64_t *tile_seg_off;         // [n_tiles + 1]
+	int32_t n_bundles;
+	const int64_t *cov_base;
+	const int32_t *b_lpos;
+	int32_t *seg_l, *seg_r, *seg_c;
+	int64_t seg_cap;
+	int *err;
+};
+
+// next set border bit strictly after global position g, searching up to `end`; -1 if none
+DEV int64_t next_border(const u32 *border, int64_t g, int64_t end)
+{
+	int64_t q = g + 1;
+	while(q < end)
+	{
+		u32 w = border[q >> 5] >> (q & 31);
+		if(w) return q + (__ffs((int)w) - 1);
+		q = ((q >> 5) + 1) << 5;
+	}
+	return -1;
+}
+
+#ifndef AGPU_EMU
+// warp 0: exclusive prefix of tile t from the states of its predecessors
+DEV long long lookback(volatile u64 *state, int64_t t)
+{
+	const int lane = threadIdx.x & 31;
+	long long prefix = 0;
+	int64_t look = t - 1;
+	while(look >= 0)
+	{
+		int64_t idx = look - lane;
+		u64 st = (idx >= 0) ? state[idx] : st_pack(ST_INCL, 0);
+		while(__any_sync(0xffffffffu, st_status(st) == 0)) { if(st_status(st) == 0) st = state[idx]; }
+		unsigned incl = __ballot_sync(0xffffffffu, st_status(st) == ST_INCL);
+		long long v = st_value(st);
+		if(incl)
+		{
+			int first = __ffs((int)incl) - 1;
+			if(lane > first) v = 0;
+			for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+			prefix += v;
+			break;
+		}
+		for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		prefix += v;
+		look -= 32;
+	}
+	return prefix;
+}
+
+// block-wide exclusive scan of one int per thread (CS_THREADS threads); returns the exclusive prefix, total in *tot
+DEV int block_scan_1(int x, int *tot, int *wsum)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int inc = x;
+	for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+	if(lane == 31) wsum[warp] = inc;
+	__syncthreads();
+	if(warp == 0)
+	{
+		int w = lane < CS_THREADS / 32 ? wsum[lane] : 0;
+		int wi = w;
+		for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, wi, o); if(lane >= o) wi += y; }
+		if(lane < CS_THREADS / 32) wsum[lane] = wi - w;
+		if(lane == 31) wsum[CS_THREADS / 32] = wi;
+	}
+	__syncthreads();
+	int r = wsum[warp] + inc - x;
+	*tot = wsum[CS_THREADS / 32];
+	__syncthreads();
+	return r;
+}
+
+__global__ void __launch_bounds__(CS_THREADS) k_cov_scan(cov_scan_args a)
+{
+	__shared__ int s_tile_lo, s_tile_hi, s_bundle;
+	__shared__ int wsum[CS_THREADS / 32 + 1];
+	__shared__ long long s_pre;
+	const int tid = threadIdx.x;
+	while(true)
+	{
+		if(tid == 0)
+		{
+			int64_t t0 = (int64_t)atomicAdd(a.ticket, 1);
+			s_tile_lo = (int)(t0 & 0x7fffffff); s_tile_hi = (int)(t0 >> 31);
+		}
+		__syncthreads();
+		const int64_t t = (int64_t)s_tile_lo | ((int64_t)s_tile_hi << 31);
+		if(t >= a.n_tiles) break;
+		const int64_t g0 = t * COV_TILE;
+		// 8 consecutive difference words per thread: two coalesced 128-bit loads
+		const int4 *d4 = reinterpret_cast<const int4*>(a.diff + g0) + tid * 2;
+		int4 x = d4[0], y = d4[1];
+		int v[CS_ITEMS] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+		for(int i = 1; i < CS_ITEMS; i++) v[i] += v[i - 1];
+		int tile_sum;
+		int texcl = block_scan_1(v[CS_ITEMS - 1], &tile_sum, wsum);
+		if(tid == 0)
+		{
+			((volatile u64*)a.cov_state)[t] = st_pack(t == 0 ? ST_INCL : ST_AGG, tile_sum);
+			if(a.n_bundles > 0) s_bundle = find_segment(a.cov_base, a.n_bundles, g0);
+		}
+		if(tid < 32)
+		{
+			long long p = lookback((volatile u64*)a.cov_state, t);
+			if(tid == 0)
+			{
+				if(t > 0) ((volatile u64*)a.cov_state)[t] = st_pack(ST_INCL, p + tile_sum);
+				s_pre = p;
+			}
+		}
+		__syncthreads();
+		const int base = (int)s_pre + texcl;
+		const int b = s_bundle;
+		// this thread's byte of the border bitmap
+		u32 w = a.border[(g0 >> 5) + (tid >> 2)];
+		u32 byte = (w >> (8 * (tid & 3))) & 0xffu;
+		u32 fm = 0;
+		for(int i = 0; i < CS_ITEMS; i++) if(((byte >> i) & 1u) && (base + v[i]) > 0) fm |= 1u << i;
+		int cnt = __popc(fm);
+		int tile_cnt;
+		int cexcl = block_scan_1(cnt, &tile_cnt, wsum);
+		if(tid == 0) ((volatile u64*)a.seg_state)[t] = st_pack(t == 0 ? ST_INCL : ST_AGG, tile_cnt);
+		if(tid < 32)
+		{
+			long long q = lookback((volatile u64*)a.seg_state, t);
+			if(tid == 0)
+			{
+				if(t > 0) ((volatile u64*)a.seg_state)[t] = st_pack(ST_INCL, q + tile_cnt);
+				s_pre = q;
+				a.tile_seg_off[t] = q;
+				if(t == a.n_tiles - 1) a.tile_seg_off[a.n_tiles] = q + tile_cnt;
+			}
+		}
+		__syncthreads();
+		if(fm)
+		{
+			int64_t o = s_pre + cexcl;
+			const int64_t org = a.cov_base[b] - (int64_t)a.b_lpos[b];
+			const int64_t end = a.cov_base[b + 1];
+			for(int i = 0; i < CS_ITEMS; i++)
+			{
+				if(!((fm >> i) & 1u)) continue;
+				int64_t g = g0 + tid * CS_ITEMS + i;
+				int64_t r;
+				u32 above = byte >> (i + 1);
+				if(above) r = g + __ffs((int)above);
+				else
+				{
+					u32 rest = (tid & 3) == 3 ? 0u : (w >> (8 * ((tid & 3) + 1)));
+					if(rest) r = g0 + (int64_t)(tid + 1) * CS_ITEMS + (__ffs((int)rest) - 1);
+					else r = next_border(a.border, ((g >> 5) << 5) + 31, end);
+				}
+				if(o < a.seg_cap)
+				{
+					a.seg_l[o] = (int32_t)(g - org);
+					a.seg_r[o] = (int32_t)((r < 0 ? end : r) - org);
+					a.seg_c[o] = base + v[i];
+				}
+				else atomicAdd(&a.err[ERR_CAP], 1);
+				o++;
+			}
+		}
+		__syncthreads();
+	}
+}
+#else
+// kernel-logic test build: the same tile protocol executed by one thread per tile, tiles in ticket order
+KERNEL k_cov_scan(cov_scan_args a)
+{
+	while(true)
+	{
+		int64_t t = (int64_t)atomicAdd(a.ticket, 1);
+		if(t >= a.n_tiles) break;
+		const int64_t g0 = t * COV_TILE;
+		long long pre = t > 0 ? st_value(a.cov_state[t - 1]) : 0;
+		long long q = t > 0 ? st_value(a.seg_state[t - 1]) : 0;
+		a.tile_seg_off[t] = q;
+		int b = a.n_bundles > 0 ? find_segment(a.cov_base, a.n_bundles, g0) : 0;
+		const int64_t org = a.cov_base[b] - (int64_t)a.b_lpos[b];
+		const int64_t end = a.cov_base[b + 1];
+		long long cov = pre;
+		for(int i = 0; i < COV_TILE; i++)
+		{
+			int64_t g = g0 + i;
+			cov += a.diff[g];
+			if(!((a.border[g >> 5] >> (g & 31)) & 1u) || cov <= 0) continue;
+			int64_t r = next_border(a.border, g, end);
+			if(q < a.seg_cap)
+			{
+				a.seg_l[q] = (int32_t)(g - org);
+				a.seg_r[q] = (int32_t)((r < 0 ? end : r) - org);
+				a.seg_c[q] = (int32_t)cov;
+			}
+			else atomicAdd(&a.err[ERR_CAP], 1);
+			q++;
+		}
+		a.cov_state[t] = st_pack(ST_INCL, cov);
+		a.seg_state[t] = st_pack(ST_INCL, q);
+		if(t == a.n_tiles - 1) a.tile_seg_off[a.n_tiles] = q;
+	}
+}
+#endif
+
 } // namespace agpu
 
 #endif

@@ -15,20 +15,20 @@
 
 namespace agpu {
 
-// a[] holds handles; less(x, y) compares the elements the handles stand for
-template<typename Less>
+// a[] holds handles (or small self-contained elements); less(x, y) compares the elements they stand for
+template<typename T, typename Less>
 struct std_sort_emul
 {
-	int *a;
+	T *a;
 	Less less;
 
-	HD std_sort_emul(int *arr, Less l) : a(arr), less(l) {}
+	HD std_sort_emul(T *arr, Less l) : a(arr), less(l) {}
 
-	HD void swap_at(int i, int j) { int t = a[i]; a[i] = a[j]; a[j] = t; }
+	HD void swap_at(int i, int j) { T t = a[i]; a[i] = a[j]; a[j] = t; }
 
 	HD void unguarded_linear_insert(int last)
 	{
-		int val = a[last];
+		T val = a[last];
 		int next = last - 1;
 		while(less(val, a[next]))
 		{
@@ -46,7 +46,7 @@ struct std_sort_emul
 		{
 			if(less(a[i], a[first]))
 			{
-				int val = a[i];
+				T val = a[i];
 				for(int k = i; k > first; --k) a[k] = a[k - 1];
 				a[first] = val;
 			}
@@ -91,7 +91,7 @@ struct std_sort_emul
 	}
 
 	// ---- heap fallback (depth limit reached) ----
-	HD void push_heap(int first, int hole, int top, int value)
+	HD void push_heap(int first, int hole, int top, T value)
 	{
 		int parent = (hole - 1) / 2;
 		while(hole > top && less(a[first + parent], value))
@@ -103,7 +103,7 @@ struct std_sort_emul
 		a[first + hole] = value;
 	}
 
-	HD void adjust_heap(int first, int hole, int len, int value)
+	HD void adjust_heap(int first, int hole, int len, T value)
 	{
 		const int top = hole;
 		int second = hole;
@@ -125,7 +125,7 @@ struct std_sort_emul
 
 	HD void pop_heap(int first, int last, int result)
 	{
-		int value = a[result];
+		T value = a[result];
 		a[result] = a[first];
 		adjust_heap(first, 0, last - first, value);
 	}
@@ -137,7 +137,7 @@ struct std_sort_emul
 		int parent = (len - 2) / 2;
 		while(true)
 		{
-			int value = a[first + parent];
+			T value = a[first + parent];
 			adjust_heap(first, parent, len, value);
 			if(parent == 0) return;
 			parent--;
@@ -186,10 +186,10 @@ struct std_sort_emul
 	}
 };
 
-template<typename Less>
-HD void std_sort_handles(int *a, int n, Less less)
+template<typename T, typename Less>
+HD void std_sort_handles(T *a, int n, Less less)
 {
-	std_sort_emul<Less> s(a, less);
+	std_sort_emul<T, Less> s(a, less);
 	s.sort(0, n);
 }
 
