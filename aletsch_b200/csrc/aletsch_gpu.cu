@@ -118,6 +118,9 @@ struct agpu_batch
 	dbuf<u32> in_cigar_off, in_cigar;
 	std::vector<int64_t> hit_off_host;
 	std::vector<int32_t> tid_host, sample_host;
+	// bundles by descending hit count: [0, n_large) get wide CTAs, the rest one warp each
+	dbuf<int32_t> order;
+	int32_t n_large = 0;
 
 	dbuf<int> err;
 
@@ -276,11 +279,28 @@ int agpu_profile_read(agpu_ctx *ctx, char *buf, size_t cap)
 	return AGPU_OK;
 }
 
+#define LARGE_BUNDLE_HITS 4096
+
 static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 {
 	TRY(b->err.alloc(ctx, ERR_WORDS, true));
+	std::vector<int32_t> ord(b->nb);
+	for(int k = 0; k < b->nb; k++) ord[k] = k;
+	const std::vector<int64_t> &ho = b->hit_off_host;
+	std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ho[x + 1] - ho[x] > ho[y + 1] - ho[y]; });
+	b->n_large = 0;
+	while(b->n_large < b->nb && ho[ord[b->n_large] + 1] - ho[ord[b->n_large]] >= LARGE_BUNDLE_HITS) b->n_large++;
+	TRY(b->order.alloc(ctx, b->nb + 1));
+	TRY(h2d(ctx, b->order.p, ord.data(), sizeof(int32_t) * b->nb));
+	TRY(stream_sync(ctx));
 	return AGPU_OK;
 }
+
+// per-bundle block-cooperative kernel over the size-binned bundle order: wide CTAs for the large bundles, one warp for the rest
+#define LAUNCH_BINNED(ctx, b, kern, ...) do { \
+	if((b)->n_large > 0) LAUNCH_B(ctx, kern, (b)->n_large, 256, (b)->order.p, (b)->n_large, __VA_ARGS__); \
+	if((b)->nb > (b)->n_large) LAUNCH_B(ctx, kern, (b)->nb - (b)->n_large, 32, (b)->order.p + (b)->n_large, (b)->nb - (b)->n_large, __VA_ARGS__); } while(0)
+
 
 int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 {
@@ -354,7 +374,7 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 	b->in_hit_off.release(ctx); b->in_pos.release(ctx); b->in_rpos.release(ctx); b->in_mpos.release(ctx); b->in_isize.release(ctx);
 	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
 	b->in_cigar_off.release(ctx); b->in_cigar.release(ctx);
-	b->err.release(ctx);
+	b->err.release(ctx); b->order.release(ctx);
 	stream_sync(ctx);
 	for(auto &r : b->pinned) r.second.release();
 	delete b;
@@ -401,11 +421,11 @@ static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int6
 static int chainset_finish(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int64_t n_val)
 {
 	int nb = b->nb;
-	LAUNCH_B(ctx, k_chain_order, nb, 128, nb, cs.d_elem_off, cs.elem_slot.p, cs.slot_first.p, cs.slot_cnt.p, cs.voff32, cs.voff64, cs.val,
+	LAUNCH_BINNED(ctx, b, k_chain_order, cs.d_elem_off, cs.elem_slot.p, cs.slot_first.p, cs.slot_cnt.p, cs.voff32, cs.voff64, cs.val,
 			cs.key_scratch.p, cs.slot_chain.p, cs.n_chains.p, cs.c_rep.p, cs.c_cnt.p, cs.c_grp.p, cs.c_slot.p);
 	TRY(cs.key_scratch2.alloc(ctx, 2 * n_val + 2));
 	TRY(cs.splices_scratch.alloc(ctx, n_val + 1));
-	LAUNCH_B(ctx, k_chain_splices, nb, 128, nb, cs.d_elem_off, cs.val_base.p, cs.n_chains.p, cs.c_rep.p, cs.c_cnt.p,
+	LAUNCH_BINNED(ctx, b, k_chain_splices, cs.d_elem_off, cs.val_base.p, cs.n_chains.p, cs.c_rep.p, cs.c_cnt.p,
 			cs.elem_len, cs.voff32, cs.voff64, cs.val, cs.key_scratch2.p, cs.n_splices.p, cs.splices_scratch.p);
 	LAUNCH_T(ctx, k_handle_chain, cs.n_elem, cs.n_elem, cs.elem_slot.p, cs.slot_chain.p, cs.handle_chain.p);
 	cs.built = true;
@@ -517,7 +537,7 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	gp.min_junction_support = p->min_junction_support;
 	gp.min_subregion_gap = p->min_subregion_gap; gp.min_subregion_length = p->min_subregion_length;
 	gp.min_subregion_overlap = p->min_subregion_overlap; gp.min_guaranteed_edge_weight = p->min_guaranteed_edge_weight;
-	LAUNCH_B(ctx, k_graph_build, nb, 128, in, gs.dev(b->err.p), gp);
+	LAUNCH_BINNED(ctx, b, k_graph_build, in, gs.dev(b->err.p), gp);
 	gs.built = true;
 	return check_err(ctx, b, "agpu_batch_graph");
 }

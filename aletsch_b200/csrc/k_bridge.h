@@ -277,11 +277,12 @@ KERNEL k_bridge_vertices(int64_t n_clu, const int32_t *c_bundle, const int32_t *
 }
 
 // ---- B2: piers and pier groups of every bundle (build_piers, build_bounds); one CTA per bundle
-KERNEL k_piers(int32_t n_bundles, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand, bridge_dev br, u64 *key_scratch)
+KERNEL k_piers(const int32_t *order, int32_t n_bundles, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand, bridge_dev br, u64 *key_scratch)
 {
 	SHARED int s_n, s_max;
-	for(int b = blockIdx.x; b < n_bundles; b += gridDim.x)
+	for(int bi = blockIdx.x; bi < n_bundles; bi += gridDim.x)
 	{
+		const int b = order ? order[bi] : bi;
 		int64_t c0 = clu_off[b];
 		int nc = (int)(clu_off[b + 1] - c0);
 		u64 *key = key_scratch + c0;

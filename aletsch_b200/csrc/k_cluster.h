@@ -268,7 +268,10 @@ KERNEL k_frag_group(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hi
 }
 
 // leader[f] = group size if f is the first fragment of its group, else -1 (input of the flag scans)
-KERNEL k_group_leaders(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, cluster_dev c, int32_t *leader, int32_t *leader_size)
+#define BIG_GROUP 48            // groups above this size are partitioned by a whole warp (CUDA build)
+
+KERNEL k_group_leaders(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, cluster_dev c, int32_t *leader, int32_t *leader_size,
+		int32_t *n_big, int32_t *big_list, int32_t big_cap)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(f >= n_frg) return;
@@ -280,6 +283,13 @@ KERNEL k_group_leaders(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off,
 	if(c.slot_min[sl] != (int32_t)(f - frg_off[b])) return;
 	leader[f] = 1;
 	leader_size[f] = c.slot_n[sl];
+#ifndef AGPU_EMU
+	if(c.slot_n[sl] > BIG_GROUP)
+	{
+		int k = atomicAdd(n_big, 1);
+		if(k < big_cap) big_list[k] = (int32_t)f;
+	}
+#endif
 }
 
 // generic device-wide exclusive scan of int32 values into int64 (tile sums + single-CTA scan + apply)
@@ -374,6 +384,9 @@ KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_of
 	int64_t f0 = frg_off[b];
 	int64_t sl = c.f_slot[f];
 	int n = c.slot_n[sl];
+#ifndef AGPU_EMU
+	if(n > BIG_GROUP) return;                      // handled by k_group_partition_warp
+#endif
 	int32_t *m = members + member_off[f];
 	int k = 0;
 	for(int32_t x = c.slot_head[sl]; x >= 0 && k < n; x = c.f_next[f0 + x]) m[k++] = x;
@@ -413,6 +426,105 @@ KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_of
 	pc.gap = gap;
 	partition_rec<0>(pc, 0, n);
 	for(int i = 0; i < n; i++) m[i] = (int32_t)(u32)(pc.el[i] & 0xffffffffULL);
+}
+
+#ifndef AGPU_EMU
+// One warp per big group: members gathered in fragment order by scanning the bundle's fragments, then the four
+// partition levels breadth first.  A level = (re)key every element, sort every current range with the std::sort
+// permutation (big ranges by the whole warp, small ones one lane each), then open a new range wherever the gap
+// between neighbours exceeds max_reads_partition_gap.  Range starts are flags by position, so the clusters come
+// out in the same left-to-right order as the reference's recursion.
+__global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_list, int32_t big_cap, int32_t n_bundles, const int64_t *frg_off,
+		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, cluster_dev c, const int64_t *member_off, int32_t *members, u64 *elems,
+		int32_t *cflag, int32_t *scratch, int gap)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	int nb_ = *n_big;
+	if(nb_ > big_cap) nb_ = big_cap;
+	if(w >= nb_) return;
+	const int64_t f = big_list[w];
+	const int b = find_segment(frg_off, n_bundles, f);
+	const int64_t f0 = frg_off[b];
+	const int nfb = (int)(frg_off[b + 1] - f0);
+	const int64_t sl = c.f_slot[f];
+	const int n = c.slot_n[sl];
+	const int64_t mo = member_off[f];
+	u64 *el = elems + mo;
+	int32_t *flag = cflag + mo;
+	int32_t *rl = scratch + 4 * mo;              // range list (n ints), then 3n ints of sort scratch
+	int32_t *ss = rl + n;
+	part_ctx pc;
+	pc.el = el; pc.cflag = flag;
+	pc.f_h1 = f_h1 + f0; pc.f_h2 = f_h2 + f0;
+	pc.pos = h.pos + h.bundle_hit_off[b]; pc.rpos = h.rpos + h.bundle_hit_off[b];
+	pc.gap = gap;
+	// members in ascending fragment index
+	int cnt = 0;
+	for(int base = 0; base < nfb; base += 32)
+	{
+		int i = base + lane;
+		bool in = i < nfb && c.f_slot[f0 + i] == sl;
+		unsigned m = __ballot_sync(FULL, in);
+		if(in) el[cnt + __popc(m & ((1u << lane) - 1u))] = (u64)(u32)i;
+		cnt += __popc(m);
+	}
+	for(int i = lane; i < n; i += 32) flag[i] = (i == 0) ? 1 : 0;
+	__syncwarp();
+	key_less less;
+	for(int r = 0; r < 4; r++)
+	{
+		for(int i = lane; i < n; i += 32) { int32_t fr = (int32_t)(u32)(el[i] & 0xffffffffULL); el[i] = pack_key(pc.key(r, fr), fr); }
+		// current ranges
+		int nr = 0;
+		for(int base = 0; base < n; base += 32)
+		{
+			int i = base + lane;
+			bool st = i < n && flag[i];
+			unsigned m = __ballot_sync(FULL, st);
+			if(st) rl[nr + __popc(m & ((1u << lane) - 1u))] = i;
+			nr += __popc(m);
+		}
+		__syncwarp();
+		// big ranges: the whole warp, one after the other
+		for(int k = 0; k < nr; k++)
+		{
+			int lo = rl[k], hi = (k + 1 < nr) ? rl[k + 1] : n;
+			if(hi - lo > BIG_GROUP) warp_std_sort(el + lo, hi - lo, less, ss + 3 * lo);
+		}
+		// small ranges: one lane each
+		for(int k = lane; k < nr; k += 32)
+		{
+			int lo = rl[k], hi = (k + 1 < nr) ? rl[k + 1] : n;
+			if(hi - lo <= BIG_GROUP) std_sort_handles(el + lo, hi - lo, less);
+		}
+		__syncwarp();
+		for(int i = lane; i < n; i += 32)
+			if(i > 0 && !flag[i] && unpack_key(el[i]) - unpack_key(el[i - 1]) > gap) flag[i] = 1;
+		__syncwarp();
+	}
+	for(int i = lane; i < n; i += 32) members[mo + i] = (int32_t)(u32)(el[i] & 0xffffffffULL);
+}
+#endif
+
+// diagnostic kernel behind agpu_debug_sort_perm: elements carry (key, original index)
+KERNEL k_debug_sort(const int32_t *keys, int n, u64 *el, int32_t *scratch, int32_t *perm)
+{
+	key_less less;
+#ifndef AGPU_EMU
+	const int lane = threadIdx.x & 31;
+	for(int i = lane; i < n; i += 32) el[i] = pack_key(keys[i], i);
+	__syncwarp();
+	if(n > BIG_GROUP) warp_std_sort(el, n, less, scratch);
+	else { if(lane == 0) std_sort_handles(el, n, less); __syncwarp(); }
+	for(int i = lane; i < n; i += 32) perm[i] = (int32_t)(u32)(el[i] & 0xffffffffULL);
+#else
+	for(int i = 0; i < n; i++) el[i] = pack_key(keys[i], i);
+	std_sort_handles(el, n, less);
+	for(int i = 0; i < n; i++) perm[i] = (int32_t)(u32)(el[i] & 0xffffffffULL);
+	(void)scratch;
+#endif
 }
 
 struct clusters_out
@@ -478,7 +590,7 @@ struct cluster_state
 	agpu::dbuf<int32_t> f_ok, m_a1, m_a2, f_next, leader, leader_size;
 	agpu::dbuf<agpu::u64> f_hash, slot_word, elems;
 	agpu::dbuf<int64_t> f_slot, reg_off, member_off, member_boff, crank, clu_off;
-	agpu::dbuf<int32_t> slot_min, slot_n, slot_head, members, cflag, tile_cnt;
+	agpu::dbuf<int32_t> slot_min, slot_n, slot_head, members, cflag, tile_cnt, n_big, big_list, part_scratch;
 	agpu::dbuf<int64_t> tile_off, grank;
 	// clusters
 	int64_t n_mem = 0, n_clu = 0;
@@ -493,6 +605,7 @@ struct cluster_state
 		f_hash.release(ctx); slot_word.release(ctx); elems.release(ctx); f_slot.release(ctx); reg_off.release(ctx); member_off.release(ctx);
 		member_boff.release(ctx); crank.release(ctx); clu_off.release(ctx);
 		slot_min.release(ctx); slot_n.release(ctx); slot_head.release(ctx); members.release(ctx); cflag.release(ctx); tile_cnt.release(ctx);
+		n_big.release(ctx); big_list.release(ctx); part_scratch.release(ctx);
 		tile_off.release(ctx); grank.release(ctx);
 		c_bounds.release(ctx); c_extend.release(ctx); c_count.release(ctx); c_chain1.release(ctx); c_chain2.release(ctx); c_bundle.release(ctx);
 		c_fr_begin.release(ctx);

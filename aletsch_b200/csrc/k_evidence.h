@@ -17,6 +17,7 @@
 
 namespace agpu {
 
+#define SCAN1_MAX 1024           // threads of the single-CTA scans
 #define COV_TILE 2048            // coverage positions per scan tile; bundle bases are tile-aligned
 #define EMPTY_SLOT 0ULL
 #define INT_BIG 0x7fffffff
@@ -93,7 +94,7 @@ KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b
 // ---- generic single-CTA exclusive scan of int64 (NB-sized arrays); out[n] = total
 KERNEL k_scan_i64(const int64_t *in, int64_t *out, int n)
 {
-	SHARED int64_t part[AGPU_MAX_BLOCK];
+	SHARED int64_t part[SCAN1_MAX];
 	int nt = blockDim.x, t = threadIdx.x;
 	int chunk = (n + nt - 1) / nt;
 	int lo = t * chunk, hi = lo + chunk;
@@ -139,7 +140,7 @@ KERNEL k_i64_tile_sum(const int64_t *in, int64_t n, int64_t n_tiles, int64_t *ti
 KERNEL k_i64_tile_apply(const int64_t *in, int64_t n, int64_t n_tiles, const int64_t *tile_off, int64_t *out)
 {
 	SHARED int64_t f[SCAN64_TILE];
-	SHARED int64_t part[AGPU_MAX_BLOCK];
+	SHARED int64_t part[SCAN1_MAX];
 	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
 	{
 		for(int i = threadIdx.x; i < SCAN64_TILE; i += blockDim.x)
@@ -293,14 +294,15 @@ KERNEL k_hcst_insert(hits_dev h, const int32_t *hit_nspl, const u64 *hit_hash, c
 // ---- E4: per bundle: order the chains the way chain_set::add leaves them
 // (groups by first appearance of the first coordinate, chains by first appearance), number
 // them, and build the sorted unique splice list.
-KERNEL k_chain_order(int32_t n_bundles, const int64_t *elem_off, const int64_t *hit_slot, const int32_t *slot_first,
+KERNEL k_chain_order(const int32_t *order, int32_t n_bundles, const int64_t *elem_off, const int64_t *hit_slot, const int32_t *slot_first,
 		const int32_t *slot_cnt, const u32 *elem_voff32, const int64_t *elem_voff64, const int32_t *val,
 		u64 *key_scratch, int32_t *slot_chain,
 		int32_t *n_chains, int32_t *c_rep, int32_t *c_cnt, int32_t *c_grp, int64_t *c_slot)
 {
 	SHARED int s_n;
-	for(int b = blockIdx.x; b < n_bundles; b += gridDim.x)
+	for(int bi = blockIdx.x; bi < n_bundles; bi += gridDim.x)
 	{
+		const int b = order ? order[bi] : bi;
 		int64_t e0 = elem_off[b], e1 = elem_off[b + 1];
 		int ne = (int)(e1 - e0);
 		u64 *key = key_scratch + e0;
@@ -358,14 +360,15 @@ KERNEL k_chain_order(int32_t n_bundles, const int64_t *elem_off, const int64_t *
 
 // per bundle: sorted unique coordinates over all chains with a positive count (chain_set::get_splices)
 // scratch regions start at 2 * val_base[b]: n keys followed by n flags
-KERNEL k_chain_splices(int32_t n_bundles, const int64_t *elem_off, const int64_t *val_base,
+KERNEL k_chain_splices(const int32_t *order, int32_t n_bundles, const int64_t *elem_off, const int64_t *val_base,
 		const int32_t *n_chains, const int32_t *c_rep, const int32_t *c_cnt,
 		const int32_t *elem_len, const u32 *elem_voff32, const int64_t *elem_voff64, const int32_t *val,
 		u64 *key_scratch, int32_t *n_splices, int32_t *splices_scratch)
 {
 	SHARED int s_n;
-	for(int b = blockIdx.x; b < n_bundles; b += gridDim.x)
+	for(int bi = blockIdx.x; bi < n_bundles; bi += gridDim.x)
 	{
+		const int b = order ? order[bi] : bi;
 		int64_t e0 = elem_off[b];
 		int nc = n_chains[b];
 		u64 *key = key_scratch + 2 * val_base[b];
@@ -418,28 +421,10 @@ KERNEL k_seg_off(int32_t nb, const int64_t *cov_base, const int64_t *tile_seg_of
 	seg_off[i] = tile_seg_off[cov_base[i] / COV_TILE];
 }
 
-// ---- coverage scan: diff -> coverage, segments = [border_k, border_k+1) with coverage > 0
-KERNEL k_cov_tile_sum(const int32_t *diff, int64_t n_tiles, int32_t *tile_sum)
-{
-	SHARED int s;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		if(threadIdx.x == 0) s = 0;
-		BLOCK_SYNC();
-		int acc = 0;
-		const int32_t *d = diff + t * COV_TILE;
-		for(int i = threadIdx.x; i < COV_TILE; i += blockDim.x) acc += d[i];
-		atomicAdd(&s, acc);
-		BLOCK_SYNC();
-		if(threadIdx.x == 0) tile_sum[t] = s;
-		BLOCK_SYNC();
-	}
-}
-
 // single CTA: exclusive scan of int32 array of length n into int64 out (out[n] = total)
 KERNEL k_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n)
 {
-	SHARED int64_t part[AGPU_MAX_BLOCK];
+	SHARED int64_t part[SCAN1_MAX];
 	int nt = blockDim.x, t = threadIdx.x;
 	int64_t chunk = (n + nt - 1) / nt;
 	int64_t lo = t * chunk, hi = lo + chunk;
@@ -458,104 +443,6 @@ KERNEL k_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n)
 	BLOCK_SYNC();
 	int64_t run = part[t];
 	for(int64_t i = lo; i < hi; i++) { int64_t v = in[i]; out[i] = run; run += v; }
-}
-
-// per tile: coverage at every position (tile prefix + local scan), count / emit segment starts.
-// mode 0: count segment starts into tile_cnt; mode 1: emit segments at tile_seg_off.
-KERNEL k_cov_segments(const int32_t *diff, const u32 *border, int64_t n_tiles, const int64_t *tile_pre /* coverage before tile */,
-		int mode, int32_t *tile_cnt, const int64_t *tile_seg_off,
-		int32_t n_bundles, const int64_t *cov_base, const int32_t *b_lpos, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c)
-{
-	SHARED int cov[COV_TILE];
-	SHARED int flg[COV_TILE];
-	SHARED int s_cnt;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		const int32_t *d = diff + t * COV_TILE;
-		for(int i = threadIdx.x; i < COV_TILE; i += blockDim.x) cov[i] = d[i];
-		BLOCK_SYNC();
-		// inclusive scan of the tile: chunk per thread
-		{
-			int nt = blockDim.x, th = threadIdx.x;
-			int chunk = (COV_TILE + nt - 1) / nt;
-			int lo = th * chunk, hi = lo + chunk;
-			if(lo > COV_TILE) lo = COV_TILE;
-			if(hi > COV_TILE) hi = COV_TILE;
-			int s = 0;
-			for(int i = lo; i < hi; i++) s += cov[i];
-			flg[th] = s;
-			BLOCK_SYNC();
-			if(th == 0)
-			{
-				int run = (int)tile_pre[t];
-				for(int k = 0; k < nt; k++) { int v = flg[k]; flg[k] = run; run += v; }
-			}
-			BLOCK_SYNC();
-			int run = flg[th];
-			BLOCK_SYNC();
-			for(int i = lo; i < hi; i++) { run += cov[i]; cov[i] = run; }
-			BLOCK_SYNC();
-		}
-		const u32 *bw = border + t * (COV_TILE / 32);
-		for(int i = threadIdx.x; i < COV_TILE; i += blockDim.x)
-			flg[i] = (((bw[i >> 5] >> (i & 31)) & 1) && cov[i] > 0) ? 1 : 0;
-		BLOCK_SYNC();
-		if(mode == 0)
-		{
-			if(threadIdx.x == 0) s_cnt = 0;
-			BLOCK_SYNC();
-			int acc = 0;
-			for(int i = threadIdx.x; i < COV_TILE; i += blockDim.x) acc += flg[i];
-			atomicAdd(&s_cnt, acc);
-			BLOCK_SYNC();
-			if(threadIdx.x == 0) tile_cnt[t] = s_cnt;
-			BLOCK_SYNC();
-		}
-		else
-		{
-			// local ranks
-			int nt = blockDim.x, th = threadIdx.x;
-			int chunk = (COV_TILE + nt - 1) / nt;
-			int lo = th * chunk, hi = lo + chunk;
-			if(lo > COV_TILE) lo = COV_TILE;
-			if(hi > COV_TILE) hi = COV_TILE;
-			SHARED int part[AGPU_MAX_BLOCK];
-			int s = 0;
-			for(int i = lo; i < hi; i++) s += flg[i];
-			part[th] = s;
-			BLOCK_SYNC();
-			if(th == 0)
-			{
-				int run = 0;
-				for(int k = 0; k < nt; k++) { int v = part[k]; part[k] = run; run += v; }
-			}
-			BLOCK_SYNC();
-			int64_t gpos0 = t * COV_TILE;
-			int b = find_segment(cov_base, n_bundles, gpos0);
-			int64_t org = cov_base[b] - (int64_t)b_lpos[b];
-			int64_t end = cov_base[b + 1];
-			int rank = part[th];
-			for(int i = lo; i < hi; i++)
-			{
-				if(!flg[i]) continue;
-				int64_t o = tile_seg_off[t] + rank++;
-				int64_t g = gpos0 + i;
-				// next border after g (exists: coverage returns to 0 at a border inside the bundle)
-				int64_t q = g + 1;
-				int64_t r = -1;
-				while(q < end)
-				{
-					u32 w = border[q >> 5] >> (q & 31);
-					if(w) { r = q + (__ffs((int)w) - 1); break; }
-					q = ((q >> 5) + 1) << 5;
-				}
-				seg_l[o] = (int32_t)(g - org);
-				seg_r[o] = (int32_t)((r < 0 ? end : r) - org);
-				seg_c[o] = cov[i];
-			}
-			BLOCK_SYNC();
-		}
-	}
 }
 
 // ---- single-pass coverage scan (decoupled look-back): one read of the difference array and the border bitmap,

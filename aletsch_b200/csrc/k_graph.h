@@ -305,11 +305,12 @@ struct graph_params
 	double min_subregion_overlap, min_guaranteed_edge_weight;
 };
 
-KERNEL k_graph_build(graph_in in, graph_dev g, graph_params prm)
+KERNEL k_graph_build(const int32_t *order, int n_order, graph_in in, graph_dev g, graph_params prm)
 {
 	SHARED int s_a, s_b, s_c;
-	for(int b = blockIdx.x; b < in.n; b += gridDim.x)
+	for(int bi = blockIdx.x; bi < n_order; bi += gridDim.x)
 	{
+		const int b = order ? order[bi] : bi;
 		const int nt = blockDim.x, t = threadIdx.x;
 		int32_t *ia = g.iarena + g.iarena_off[b];
 		u64 *ka = g.karena + g.karena_off[b];

@@ -193,6 +193,103 @@ HD void std_sort_handles(T *a, int n, Less less)
 	s.sort(0, n);
 }
 
+#ifndef AGPU_EMU
+// Warp-cooperative version producing the SAME permutation as std_sort_emul::sort (hence as std::sort).
+// All 32 lanes call it with identical arguments.  scratch holds 3 * n ints.
+//
+// Why the parallel steps are exact:
+//  * __unguarded_partition swaps, for k = 1, 2, ..., the k-th element from the left that is not less than the
+//    pivot with the k-th element from the right that the pivot is not less than, as long as the former lies left
+//    of the latter.  Both position lists depend only on the array as it was when the partition started, so they
+//    can be produced by two compactions and the swaps applied in parallel; the returned cut is
+//    min(next left candidate, last right position swapped).
+//  * After __introsort_loop every range of at most 16 elements is ordered relative to its neighbours, and
+//    __final_insertion_sort never moves an element across such a boundary (it stops at the first element that is
+//    not greater), so it equals an independent stable insertion sort of every such range.
+template<typename T, typename Less>
+__device__ void warp_std_sort(T *a, int n, Less less, int *scratch)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	if(n <= 1) return;
+	std_sort_emul<T, Less> seq(a, less);
+	if(n <= 16) { if(lane == 0) seq.insertion_sort(0, n); __syncwarp(); return; }
+	int *Lp = scratch, *Rp = scratch + n, *leaf = scratch + 2 * n;
+	int nleaf = 0;
+	int lg = 0;
+	while((n >> (lg + 1)) != 0) lg++;
+	int st_first[64], st_last[64], st_depth[64];
+	int sp = 1;
+	st_first[0] = 0; st_last[0] = n; st_depth[0] = lg * 2;
+	while(sp > 0)
+	{
+		--sp;
+		int f = st_first[sp], l = st_last[sp], d = st_depth[sp];
+		while(l - f > 16)
+		{
+			if(d == 0)
+			{
+				if(lane == 0) seq.partial_sort_all(f, l);
+				__syncwarp();
+				f = l;                      // sorted: nothing left for the insertion pass
+				break;
+			}
+			--d;
+			if(lane == 0) seq.move_median_to_first(f, f + 1, f + (l - f) / 2, l - 1);
+			__syncwarp();
+			const T pv = a[f];
+			int nL = 0, nR = 0;
+			for(int base = f + 1; base < l; base += 32)
+			{
+				int i = base + lane;
+				bool valid = i < l;
+				T x = valid ? a[i] : pv;
+				bool ge = valid && !less(x, pv);
+				bool le = valid && !less(pv, x);
+				unsigned mg = __ballot_sync(FULL, ge), ml = __ballot_sync(FULL, le);
+				unsigned below = (1u << lane) - 1u;
+				if(ge) Lp[nL + __popc(mg & below)] = i;
+				if(le) Rp[nR + __popc(ml & below)] = i;
+				nL += __popc(mg); nR += __popc(ml);
+			}
+			__syncwarp();
+			// K = number of swaps: pairs (Lp[k], Rp[nR - 1 - k]) with the left one strictly left of the right one
+			int m = nL < nR ? nL : nR;
+			int cnt = 0;
+			for(int k = lane; k < m; k += 32) if(Lp[k] < Rp[nR - 1 - k]) cnt++;
+			for(int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+			const int K = cnt;
+			for(int k = lane; k < K; k += 32)
+			{
+				int x = Lp[k], y = Rp[nR - 1 - k];
+				T t = a[x]; a[x] = a[y]; a[y] = t;
+			}
+			int cut = l;
+			if(K > 0) cut = Rp[nR - K];
+			if(K < nL && Lp[K] < cut) cut = Lp[K];
+			__syncwarp();
+			st_first[sp] = cut; st_last[sp] = l; st_depth[sp] = d; sp++;
+			l = cut;
+		}
+		if(l - f > 0) { if(lane == 0) leaf[nleaf] = (f << 5) | (l - f); nleaf++; }
+	}
+	__syncwarp();
+	for(int k = lane; k < nleaf; k += 32)
+	{
+		int f = leaf[k] >> 5, len = leaf[k] & 31;
+		// stable insertion sort of a[f .. f + len)
+		for(int i = f + 1; i < f + len; i++)
+		{
+			T val = a[i];
+			int j = i - 1;
+			while(j >= f && less(val, a[j])) { a[j + 1] = a[j]; j--; }
+			a[j + 1] = val;
+		}
+	}
+	__syncwarp();
+}
+#endif
+
 } // namespace agpu
 
 #endif

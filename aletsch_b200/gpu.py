@@ -70,7 +70,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_fragments", "agpu_batch_graph", "agpu_batch_cluster", "agpu_batch_bridge", "agpu_batch_update",
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
-               "agpu_profile_read", "agpu_group_resolve"]
+               "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm"]
 
 
 def load(lib_path=None):
@@ -102,6 +102,7 @@ def load(lib_path=None):
     L.agpu_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Counts)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.agpu_group_resolve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
+    L.agpu_debug_sort_perm.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     L.agpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.agpu_profile_reset.argtypes = [C.c_void_p]
     L.agpu_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
@@ -183,6 +184,12 @@ class Context:
 
     def adopt(self, batch_in_device, keepalive=None):
         return Batch(self, batch_in_device, True, keepalive)
+
+    def sort_perm(self, keys):
+        keys = np.ascontiguousarray(keys, np.int32)
+        perm = np.zeros(len(keys), np.int32)
+        self.check(self.L.agpu_debug_sort_perm(self.h, keys.ctypes.data, len(keys), perm.ctypes.data), "agpu_debug_sort_perm")
+        return perm
 
     def similarity(self, lists):
         """dense c (int32) and r (float64) of |A∩B| and c / min(|A|,|B|) over sorted splice lists."""

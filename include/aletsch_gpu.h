@@ -242,6 +242,11 @@ int agpu_batch_counts(agpu_ctx *ctx, agpu_batch *b, agpu_counts *c);
 int agpu_similarity(agpu_ctx *ctx, int32_t n_lists, const int64_t *list_off, const int32_t *list_val,
 		int32_t *out_c, double *out_r);
 
+/* diagnostic: the permutation std::sort(v.begin(), v.end(), [](a, b){ return key[a] < key[b]; }) leaves on v = 0..n-1, as
+ * computed by the device's re-implementation of libstdc++'s introsort (one thread for n <= 48, a whole warp above).  Used by
+ * the tests to pin the tie order that leaks into pereads_cluster::bounds (rnacore/graph_cluster.cc:183-186). */
+int agpu_debug_sort_perm(agpu_ctx *ctx, const int32_t *keys, int32_t n, int32_t *perm_out);
+
 /* bundle_group::resolve (meta/bundle_group.cc:26-56) over G bundles given by their sorted splice lists: splice-position
  * inverted index, two rounds (max_grouping_similarity, then min_grouping_similarity) of size-capped single-linkage with the
  * pairwise similarities taken from the device (agpu_similarity).  out_group_of[i] = group of bundle i, groups numbered in

@@ -385,4 +385,15 @@ int orc_group_resolve(void **bs, int n, const orc_params *prm, void *bagp)
 	return 0;
 }
 
+
+// the permutation libstdc++'s std::sort leaves for the comparator key[a] < key[b] (a partial order when keys tie)
+int orc_std_sort_perm(const int32_t *keys, int32_t n, int32_t *perm)
+{
+	std::vector<int32_t> v(n);
+	for(int i = 0; i < n; i++) v[i] = i;
+	std::sort(v.begin(), v.end(), [keys](int32_t a, int32_t b) { return keys[a] < keys[b]; });
+	for(int i = 0; i < n; i++) perm[i] = v[i];
+	return 0;
+}
+
 }

@@ -65,3 +65,33 @@ def test_group_resolve_parity(ctx, checkers):
             assert cc == c[i, j]
             if cc:
                 assert abs(r[i, j] - cc / min(len(lists[i]), len(lists[j]))) <= 1e-9 * r[i, j]       # BASELINE.json tolerance
+
+
+def test_std_sort_permutation(ctx):
+    """the device re-implementation of libstdc++'s introsort against the real std::sort on heavily tied keys"""
+    import ctypes as C
+    import numpy as np
+    import orclib
+    L = C.CDLL(orclib.ORC_SO)
+    L.orc_std_sort_perm.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    rng = np.random.default_rng(5)
+    sizes = [1, 2, 15, 16, 17, 31, 33, 48, 49, 64, 100, 257, 1000, 4096, 20000]
+    for n in sizes:
+        for kind in range(6):
+            if kind == 0:
+                keys = rng.integers(0, 4, n)
+            elif kind == 1:
+                keys = rng.integers(0, max(2, n // 3), n)
+            elif kind == 2:
+                keys = np.arange(n) // 5
+            elif kind == 3:
+                keys = (np.arange(n)[::-1]) // 3
+            elif kind == 4:
+                keys = np.minimum(np.arange(n), np.arange(n)[::-1])          # organ pipe
+            else:
+                keys = np.zeros(n)
+            keys = np.ascontiguousarray(keys, np.int32)
+            want = np.zeros(n, np.int32)
+            L.orc_std_sort_perm(keys.ctypes.data, n, want.ctypes.data)
+            got = ctx.sort_perm(keys)
+            assert np.array_equal(got, want), (n, kind)
