@@ -268,7 +268,8 @@ KERNEL k_frag_group(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hi
 }
 
 // leader[f] = group size if f is the first fragment of its group, else -1 (input of the flag scans)
-#define BIG_GROUP 48            // groups above this size are partitioned by a whole warp (CUDA build)
+#define BIG_GROUP 16            // groups above this size are partitioned by a whole warp (CUDA build)
+#define LANE_RANGE 48           // inside the warp kernel, ranges up to this size are sorted by a single lane
 
 KERNEL k_group_leaders(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, cluster_dev c, int32_t *leader, int32_t *leader_size,
 		int32_t *n_big, int32_t *big_list, int32_t big_cap)
@@ -388,6 +389,47 @@ KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_of
 	if(n > BIG_GROUP) return;                      // handled by k_group_partition_warp
 #endif
 	int32_t *m = members + member_off[f];
+#ifndef AGPU_EMU
+	{
+		// at most 16 members: everything stays in thread-local memory, and std::sort on <= 16 elements is a stable
+		// insertion sort (__final_insertion_sort -> __insertion_sort)
+		const int32_t *fh1 = f_h1 + f0, *fh2 = f_h2 + f0;
+		const int32_t *hp = h.pos + h.bundle_hit_off[b], *hr = h.rpos + h.bundle_hit_off[b];
+		u64 e[BIG_GROUP];
+		int k = 0;
+		for(int32_t x = c.slot_head[sl]; x >= 0 && k < n; x = c.f_next[f0 + x]) e[k++] = (u64)(u32)x;
+		for(int a = 1; a < n; a++)              // ascending fragment index
+		{
+			u64 v = e[a];
+			int q = a - 1;
+			while(q >= 0 && e[q] > v) { e[q + 1] = e[q]; q--; }
+			e[q + 1] = v;
+		}
+		unsigned starts = 1u;
+		for(int r = 0; r < 4; r++)
+		{
+			for(int i = 0; i < n; i++)
+			{
+				int32_t fr = (int32_t)(u32)(e[i] & 0xffffffffULL);
+				int32_t hh = (r < 2) ? fh1[fr] : fh2[fr];
+				e[i] = pack_key((r & 1) ? hr[hh] : hp[hh], fr);
+			}
+			for(int i = 1; i < n; i++)
+			{
+				if((starts >> i) & 1u) continue;          // first element of a range
+				u64 v = e[i];
+				int q = i - 1;
+				while((v >> 32) < (e[q] >> 32)) { e[q + 1] = e[q]; q--; if((starts >> (q + 1)) & 1u) break; }
+				e[q + 1] = v;
+			}
+			for(int i = 1; i < n; i++)
+				if(!((starts >> i) & 1u) && unpack_key(e[i]) - unpack_key(e[i - 1]) > gap) starts |= 1u << i;
+		}
+		int32_t *cf = cflag + member_off[f];
+		for(int i = 0; i < n; i++) { m[i] = (int32_t)(u32)(e[i] & 0xffffffffULL); cf[i] = (starts >> i) & 1u; }
+		return;
+	}
+#else
 	int k = 0;
 	for(int32_t x = c.slot_head[sl]; x >= 0 && k < n; x = c.f_next[f0 + x]) m[k++] = x;
 	// ascending fragment index = the order group_pereads appended them (heap sort, keys are distinct)
@@ -426,6 +468,7 @@ KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_of
 	pc.gap = gap;
 	partition_rec<0>(pc, 0, n);
 	for(int i = 0; i < n; i++) m[i] = (int32_t)(u32)(pc.el[i] & 0xffffffffULL);
+#endif
 }
 
 #ifndef AGPU_EMU
@@ -461,15 +504,33 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 	pc.pos = h.pos + h.bundle_hit_off[b]; pc.rpos = h.rpos + h.bundle_hit_off[b];
 	pc.gap = gap;
 	// members in ascending fragment index
-	int cnt = 0;
-	for(int base = 0; base < nfb; base += 32)
+	if(n <= 1024 && n * 8 < nfb)
 	{
-		int i = base + lane;
-		bool in = i < nfb && c.f_slot[f0 + i] == sl;
-		unsigned m = __ballot_sync(FULL, in);
-		if(in) el[cnt + __popc(m & ((1u << lane) - 1u))] = (u64)(u32)i;
-		cnt += __popc(m);
+		// moderate group inside a big bundle: walk the group's list, then order by counting smaller members
+		u64 *tmp = (u64*)rl;                 // 4n ints of scratch are free at this point (8-byte aligned: 4 * mo ints)
+		if(lane == 0) { int k = 0; for(int32_t x = c.slot_head[sl]; x >= 0 && k < n; x = c.f_next[f0 + x]) tmp[k++] = (u64)(u32)x; }
+		__syncwarp();
+		for(int i = lane; i < n; i += 32)
+		{
+			u64 v = tmp[i];
+			int rk = 0;
+			for(int j = 0; j < n; j++) rk += tmp[j] < v;
+			el[rk] = v;
+		}
 	}
+	else
+	{
+		int cnt = 0;
+		for(int base = 0; base < nfb; base += 32)
+		{
+			int i = base + lane;
+			bool in = i < nfb && c.f_slot[f0 + i] == sl;
+			unsigned m = __ballot_sync(FULL, in);
+			if(in) el[cnt + __popc(m & ((1u << lane) - 1u))] = (u64)(u32)i;
+			cnt += __popc(m);
+		}
+	}
+	__syncwarp();
 	for(int i = lane; i < n; i += 32) flag[i] = (i == 0) ? 1 : 0;
 	__syncwarp();
 	key_less less;
@@ -491,13 +552,13 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 		for(int k = 0; k < nr; k++)
 		{
 			int lo = rl[k], hi = (k + 1 < nr) ? rl[k + 1] : n;
-			if(hi - lo > BIG_GROUP) warp_std_sort(el + lo, hi - lo, less, ss + 3 * lo);
+			if(hi - lo > LANE_RANGE) warp_std_sort(el + lo, hi - lo, less, ss + 3 * lo);
 		}
 		// small ranges: one lane each
 		for(int k = lane; k < nr; k += 32)
 		{
 			int lo = rl[k], hi = (k + 1 < nr) ? rl[k + 1] : n;
-			if(hi - lo <= BIG_GROUP) std_sort_handles(el + lo, hi - lo, less);
+			if(hi - lo <= LANE_RANGE) std_sort_handles(el + lo, hi - lo, less);
 		}
 		__syncwarp();
 		for(int i = lane; i < n; i += 32)
@@ -516,7 +577,7 @@ KERNEL k_debug_sort(const int32_t *keys, int n, u64 *el, int32_t *scratch, int32
 	const int lane = threadIdx.x & 31;
 	for(int i = lane; i < n; i += 32) el[i] = pack_key(keys[i], i);
 	__syncwarp();
-	if(n > BIG_GROUP) warp_std_sort(el, n, less, scratch);
+	if(n > LANE_RANGE) warp_std_sort(el, n, less, scratch);
 	else { if(lane == 0) std_sort_handles(el, n, less); __syncwarp(); }
 	for(int i = lane; i < n; i += 32) perm[i] = (int32_t)(u32)(el[i] & 0xffffffffULL);
 #else
