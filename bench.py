@@ -128,9 +128,9 @@ def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
         # in: pos, rpos, cigar_off (12 B/hit) + CIGAR ops; out: nspl, hash, bundle id (16 B/hit) + splice coordinates
         # + one 4-byte difference word and one 4-byte bitmap word per block end
         return Hh * (12 + 16) + 4 * n_cigar + 8 * n_splice_pairs + 16 * n_mblocks
-    if kernel == "k_cov_segments":
-        # difference array + border bitmap read once per pass, segments written once (12 B each)
-        return 2 * (4 * L + L // 8) + 12 * S
+    if kernel == "k_cov_scan":
+        # single pass: difference array + border bitmap read once, segments written once (12 B each)
+        return 4 * L + L // 8 + 12 * S
     if kernel == "k_cov_tile_sum":
         return 4 * L
     if kernel == "k_qid_insert":
