@@ -130,15 +130,17 @@ struct agpu_batch
 	dbuf<uint8_t> b_strand;
 	dbuf<int64_t> b_span, cov_base;
 	int64_t ltot = 0;
-	dbuf<int32_t> diff;
-	dbuf<u32> border;
+	// coverage map on border-compacted coordinates (k_evidence.h, coverage section)
+	dbuf<u32> border, wrank;
+	dbuf<int32_t> diffc, posc, covc;
+	dbuf<int64_t> bord_off, ex_s, ex_e;
+	int64_t n_bord = 0, n_extra = 0;
 	dbuf<int32_t> spl, hit_nspl, hit_bundle;
 	dbuf<u64> hit_hash;
 	chainset_state hcst, fcst;
 	// segments
 	bool cov_dirty = true;
-	dbuf<int32_t> tile_sum, tile_cnt;
-	dbuf<int64_t> tile_pre, tile_seg_off, seg_off;
+	dbuf<int64_t> seg_off;
 	dbuf<int32_t> seg_l, seg_r, seg_c;
 	int64_t n_seg = 0;
 
@@ -358,10 +360,12 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 {
 	b->b_lpos.release(ctx); b->b_rpos.release(ctx); b->b_covhi.release(ctx); b->b_strand.release(ctx);
-	b->b_span.release(ctx); b->cov_base.release(ctx); b->diff.release(ctx); b->border.release(ctx);
+	b->b_span.release(ctx); b->cov_base.release(ctx); b->border.release(ctx); b->wrank.release(ctx);
+	b->diffc.release(ctx); b->posc.release(ctx); b->covc.release(ctx); b->bord_off.release(ctx); b->ex_s.release(ctx); b->ex_e.release(ctx);
+	b->n_bord = 0; b->n_extra = 0;
 	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx); b->hit_hash.release(ctx);
 	b->hcst.release(ctx); b->fcst.release(ctx);
-	b->tile_sum.release(ctx); b->tile_cnt.release(ctx); b->tile_pre.release(ctx); b->tile_seg_off.release(ctx); b->seg_off.release(ctx);
+	b->seg_off.release(ctx);
 	b->seg_l.release(ctx); b->seg_r.release(ctx); b->seg_c.release(ctx);
 	b->frg.release(ctx); b->gr.release(ctx); b->clu.release(ctx); b->brg.release(ctx); b->brg.release_entries(ctx);
 	b->evidence = false; b->cov_dirty = true; b->n_seg = 0; b->ltot = 0;
@@ -432,41 +436,60 @@ static int chainset_finish(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int
 	return AGPU_OK;
 }
 
-// coverage difference array -> segments (single pass with decoupled look-back)
+// device-wide exclusive scan of per-tile int32 sums (at most a few 10^4 tiles): one CTA
+static int tile_scan(agpu_ctx *ctx, dbuf<int32_t> &tile_sum, dbuf<int64_t> &tile_off, int64_t nt)
+{
+	TRY(tile_off.alloc(ctx, nt + 2));
+	LAUNCH_B(ctx, k_scan_i32_to_i64, 1, 1024, tile_sum.p, tile_off.p, nt);
+	return AGPU_OK;
+}
+
+// border bitmap + hits (+ the stretches of update_bridges) -> ranked borders, differences, coverage, segments
 static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 {
-	int64_t nt = b->ltot / COV_TILE;
-	TRY(b->tile_seg_off.alloc(ctx, nt + 2, true));
-	TRY(b->seg_off.alloc(ctx, b->nb + 1, true));
-	b->n_seg = 0;
-	if(nt > 0)
+	const int nb = b->nb;
+	TRY(b->seg_off.alloc(ctx, nb + 2, true));
+	b->n_seg = 0; b->n_bord = 0;
+	const int64_t nw = b->ltot / 32;
+	dbuf<int32_t> ts;
+	dbuf<int64_t> to;
+	if(nw > 0)
 	{
-		dbuf<u64> cov_state, seg_state;
-		dbuf<int> ticket;
-		dbuf<unsigned long long> nbord;
-		TRY(cov_state.alloc(ctx, nt + 1, true)); TRY(seg_state.alloc(ctx, nt + 1, true)); TRY(ticket.alloc(ctx, 1, true)); TRY(nbord.alloc(ctx, 1, true));
-		int64_t nwords = b->ltot / 32;
-		LAUNCH_T(ctx, k_border_count, nwords, b->border.p, nwords, nbord.p);
-		unsigned long long cap = 0;
-		TRY(d2h(ctx, &cap, nbord.p, sizeof(cap)));
+		// rank the borders
+		int64_t nt = (nw + 1 + CTILE - 1) / CTILE;
+		TRY(ts.alloc(ctx, nt + 1));
+		TRY(b->wrank.alloc(ctx, nw + 2));
+		LAUNCH_B(ctx, k_bord_tile_sum, nt, 256, b->border.p, nw, nt, ts.p);
+		TRY(tile_scan(ctx, ts, to, nt));
+		LAUNCH_B(ctx, k_bord_tile_rank, nt, 256, b->border.p, nw, nt, to.p, b->wrank.p);
+		TRY(d2h(ctx, &b->n_bord, to.p + nt, sizeof(int64_t)));
 		TRY(stream_sync(ctx));
-		TRY(b->seg_l.alloc(ctx, cap + 1)); TRY(b->seg_r.alloc(ctx, cap + 1)); TRY(b->seg_c.alloc(ctx, cap + 1));
-		cov_scan_args a;
-		a.diff = b->diff.p; a.border = b->border.p; a.n_tiles = nt; a.cov_state = cov_state.p; a.seg_state = seg_state.p; a.ticket = ticket.p;
-		a.tile_seg_off = b->tile_seg_off.p; a.n_bundles = b->nb; a.cov_base = b->cov_base.p; a.b_lpos = b->b_lpos.p;
-		a.seg_l = b->seg_l.p; a.seg_r = b->seg_r.p; a.seg_c = b->seg_c.p; a.seg_cap = (int64_t)cap; a.err = b->err.p;
-		int64_t grid = (int64_t)ctx->sm_count * 8;
-		if(grid > nt) grid = nt;
-#ifdef AGPU_EMU
-		grid = 1;
-#endif
-		LAUNCH_B(ctx, k_cov_scan, grid, CS_THREADS, a);
-		TRY(d2h(ctx, &b->n_seg, b->tile_seg_off.p + nt, sizeof(int64_t)));
-		LAUNCH_T(ctx, k_seg_off, b->nb + 1, b->nb, b->cov_base.p, b->tile_seg_off.p, b->seg_off.p);
-		TRY(stream_sync(ctx));
-		cov_state.release(ctx); seg_state.release(ctx); ticket.release(ctx); nbord.release(ctx);
 	}
-	else { TRY(b->seg_l.alloc(ctx, 1)); TRY(b->seg_r.alloc(ctx, 1)); TRY(b->seg_c.alloc(ctx, 1)); }
+	const int64_t n = b->n_bord;
+	TRY(b->seg_l.alloc(ctx, n + 1)); TRY(b->seg_r.alloc(ctx, n + 1)); TRY(b->seg_c.alloc(ctx, n + 1));
+	if(n > 0)
+	{
+		TRY(b->diffc.alloc(ctx, n + 1, true)); TRY(b->posc.alloc(ctx, n + 1)); TRY(b->covc.alloc(ctx, n + 1));
+		TRY(b->bord_off.alloc(ctx, nb + 2));
+		LAUNCH_T(ctx, k_bord_off, nb + 1, nb, b->cov_base.p, b->wrank.p, b->bord_off.p);
+		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
+		LAUNCH_T(ctx, k_cov_add, b->nh, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p);
+		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
+		// coverage = prefix sum of the differences; segments = borders with positive coverage
+		int64_t nt = (n + CTILE - 1) / CTILE;
+		dbuf<int32_t> tc;
+		dbuf<int64_t> tco;
+		TRY(ts.alloc(ctx, nt + 1)); TRY(tc.alloc(ctx, nt + 1));
+		LAUNCH_B(ctx, k_covc_tile_sum, nt, 256, b->diffc.p, n, nt, ts.p);
+		TRY(tile_scan(ctx, ts, to, nt));
+		LAUNCH_B(ctx, k_covc_tile_cover, nt, 256, b->diffc.p, n, nt, to.p, b->covc.p, tc.p);
+		TRY(tile_scan(ctx, tc, tco, nt));
+		LAUNCH_B(ctx, k_covc_emit, nt, 256, b->covc.p, b->posc.p, n, nt, tco.p, nb, b->bord_off.p, b->seg_l.p, b->seg_r.p, b->seg_c.p, b->seg_off.p);
+		TRY(d2h(ctx, &b->n_seg, tco.p + nt, sizeof(int64_t)));
+		TRY(stream_sync(ctx));
+		tc.release(ctx); tco.release(ctx);
+	}
+	ts.release(ctx); to.release(ctx);
 	b->cov_dirty = false;
 	return AGPU_OK;
 }
@@ -484,10 +507,10 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	b->ltot = 0;
 	TRY(d2h(ctx, &b->ltot, b->cov_base.p + nb, sizeof(int64_t)));
 	TRY(stream_sync(ctx));
-	TRY(b->diff.alloc(ctx, b->ltot + COV_TILE, true));
-	TRY(b->border.alloc(ctx, b->ltot / 32 + COV_TILE, true));
+	if(b->ltot >= ((int64_t)1 << 32) - 64) { ctx->last_error = "batch spans 2^32 or more window positions: split it"; return AGPU_ERR_CAPACITY; }
+	TRY(b->border.alloc(ctx, b->ltot / 32 + 8, true));
 	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1)); TRY(b->hit_bundle.alloc(ctx, nh + 1)); TRY(b->hit_hash.alloc(ctx, nh + 1));
-	LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->diff.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_hash.p,
+	LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_hash.p,
 			b->hit_bundle.p, b->err.p);
 	// hcst
 	chainset_state &cs = b->hcst;

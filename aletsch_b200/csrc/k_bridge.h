@@ -692,23 +692,27 @@ struct update_dev
 	int32_t *ent_frag, *ent_xs, *ent_len;
 	int64_t *ent_voff;
 	int32_t *bridged;            // [NB]
+	int32_t *gap_cnt;            // coverage stretches (mmap += 1) per cluster
+	const int64_t *gap_off;      // scanned
+	int64_t *ex_s, *ex_e;        // the stretches as global window positions, appended after the earlier rounds' at ex_base
+	int64_t ex_base;
 };
 
 KERNEL k_update(int64_t n_clu, int apply, const int32_t *c_bundle, const int64_t *frg_off, const int64_t *fr_begin, const int32_t *members,
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, int32_t *f_type, const int32_t *o_type, const int32_t *o_strand,
 		const int64_t *o_coff, const int32_t *o_chain, const int32_t *b_lpos, const int32_t *b_covhi, const int64_t *cov_base,
-		int32_t *diff, u32 *border, update_dev u, int *err)
+		u32 *border, update_dev u, int *err)
 {
 	int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(c >= n_clu) return;
-	if(!apply) { u.acc_cnt[c] = 0; u.ent_cnt[c] = 0; }
+	if(!apply) { u.acc_cnt[c] = 0; u.ent_cnt[c] = 0; u.gap_cnt[c] = 0; }
 	if(o_type[c] <= 0) return;
 	int b = c_bundle[c];
 	int64_t f0 = frg_off[b], h0 = h.bundle_hit_off[b];
 	const int32_t *chain = o_chain + o_coff[c];
 	int cl = (int)(o_coff[c + 1] - o_coff[c]);
 	int strand = o_strand[c];
-	int acc = 0, ent = 0;
+	int acc = 0, ent = 0, gaps = 0;
 	int64_t cbase = cov_base[b] - (int64_t)b_lpos[b];
 	for(int64_t x = fr_begin[c]; x < fr_begin[c + 1]; x++)
 	{
@@ -750,26 +754,27 @@ KERNEL k_update(int64_t n_clu, int apply, const int32_t *c_bundle, const int64_t
 			}
 			ent++;
 		}
-		if(apply)
+		if(apply) f_type[f0 + fr] = cl > 0 ? 2 : 1;
+		// mmap += 1 over every stretch (v1[2k], v1[2k+1]) with v1[2k] < v1[2k+1]: new borders + a list entry
+		int nv = cl + 2;
+		for(int k = 0; k < nv / 2; k++)
 		{
-			f_type[f0 + fr] = cl > 0 ? 2 : 1;
-			// mmap += 1 over every stretch (v1[2k], v1[2k+1]) with v1[2k] < v1[2k+1]
-			int nv = cl + 2;
-			for(int k = 0; k < nv / 2; k++)
+			int32_t a = (2 * k == 0) ? r1 : chain[2 * k - 1];
+			int32_t e = (2 * k + 1 == nv - 1) ? p2 : chain[2 * k];
+			if(a >= e) continue;
+			if(a < b_lpos[b] || e > b_covhi[b]) { if(apply) atomicAdd(&err[ERR_CAP], 1); continue; }
+			if(apply)
 			{
-				int32_t a = (2 * k == 0) ? r1 : chain[2 * k - 1];
-				int32_t e = (2 * k + 1 == nv - 1) ? p2 : chain[2 * k];
-				if(a >= e) continue;
-				if(a < b_lpos[b] || e > b_covhi[b]) { atomicAdd(&err[ERR_CAP], 1); continue; }
 				int64_t s0 = cbase + a, e0 = cbase + e;
-				atomicAdd(&diff[s0], 1);
-				atomicAdd(&diff[e0], -1);
+				int64_t at = u.ex_base + u.gap_off[c] + gaps;
+				u.ex_s[at] = s0; u.ex_e[at] = e0;
 				atomicOr(&border[s0 >> 5], 1u << (s0 & 31));
 				atomicOr(&border[e0 >> 5], 1u << (e0 & 31));
 			}
+			gaps++;
 		}
 	}
-	if(!apply) { u.acc_cnt[c] = acc; u.ent_cnt[c] = ent; }
+	if(!apply) { u.acc_cnt[c] = acc; u.ent_cnt[c] = ent; u.gap_cnt[c] = gaps; }
 	else if(acc > 0) atomicAdd(&u.bridged[b], acc);
 }
 

@@ -18,7 +18,8 @@
 namespace agpu {
 
 #define SCAN1_MAX 1024           // threads of the single-CTA scans
-#define COV_TILE 2048            // coverage positions per scan tile; bundle bases are tile-aligned
+#define COV_ALIGN 128            // bundle windows of the border bitmap start at multiples of 128 positions (4 words)
+#define CTILE 2048               // elements per tile of the device-wide scans over border words / borders
 #define EMPTY_SLOT 0ULL
 #define INT_BIG 0x7fffffff
 
@@ -85,7 +86,7 @@ KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b
 			b_strand[b] = st;
 			// positions [lpos, covhi] inclusive (the -1 of a block ending at covhi lands there), tile-aligned
 			int64_t span = (h1 > h0) ? ((int64_t)s_cov - (int64_t)s_min + 1) : 0;
-			b_span[b] = (span + COV_TILE - 1) / COV_TILE * COV_TILE;
+			b_span[b] = (span + COV_ALIGN - 1) / COV_ALIGN * COV_ALIGN;
 		}
 		BLOCK_SYNC();
 	}
@@ -186,9 +187,10 @@ HD u64 chain_hash(const int32_t *v, int n)
 }
 
 // ---- E2: one thread per hit: CIGAR walk
-//   coverage: +1 at the start and -1 at the end of every BAM_CMATCH block, border bits at both
+//   coverage: a border bit at the start and at the end of every BAM_CMATCH block (the +1 / -1 are added by
+//             k_cov_add once the borders have been ranked, see the coverage section below)
 //   splices : (p - len, p) for every inner BAM_CREF_SKIP, written at spl[cigar_off[i] ...]
-KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, int32_t *diff, u32 *border,
+KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
 		int32_t *spl, int32_t *hit_nspl, u64 *hit_hash, int32_t *hit_bundle, int *err)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,8 +212,6 @@ KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, i
 			int64_t s = base + p - (int32_t)len, e = base + p;
 			if(len > 0)
 			{
-				atomicAdd(&diff[s], 1);
-				atomicAdd(&diff[e], -1);
 				atomicOr(&border[s >> 5], 1u << (s & 31));
 				atomicOr(&border[e >> 5], 1u << (e & 31));
 			}
@@ -414,13 +414,6 @@ KERNEL k_gather_off(int64_t n, const int64_t *idx, const u32 *src, int64_t *out)
 	out[i] = (int64_t)src[idx[i]];
 }
 
-KERNEL k_seg_off(int32_t nb, const int64_t *cov_base, const int64_t *tile_seg_off, int64_t *seg_off)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i > nb) return;
-	seg_off[i] = tile_seg_off[cov_base[i] / COV_TILE];
-}
-
 // single CTA: exclusive scan of int32 array of length n into int64 out (out[n] = total)
 KERNEL k_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n)
 {
@@ -445,241 +438,218 @@ KERNEL k_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n)
 	for(int64_t i = lo; i < hi; i++) { int64_t v = in[i]; out[i] = run; run += v; }
 }
 
-// ---- single-pass coverage scan (decoupled look-back): one read of the difference array and the border bitmap,
-// segments written once.  Two chained look-backs per tile: the coverage prefix (needed to know which borders open a
-// segment) and then the segment-count prefix (the output offset).
-#define CS_THREADS 256
-#define CS_ITEMS 8                 // CS_THREADS * CS_ITEMS == COV_TILE
-#define ST_AGG 1ULL
-#define ST_INCL 2ULL
+// ---- coverage map (bundle_base::mmap, a Boost.ICL split_interval_map) on BORDER-COMPACTED coordinates
+//
+// split_interval_map semantics (rnacore/interval_map.h:31): every inserted interval end stays a segment border for
+// ever, and stretches whose summed value is 0 are absent.  So the map is fully described by (1) the set of borders and
+// (2) a +1/-1 difference per border.  Exonic coverage touches only a few percent of a bundle's genomic window, hence:
+//   border[L/32]   per-base bitmap of the borders of all bundles' windows (the only per-base structure)
+//   wrank[L/32+1]  exclusive prefix popcount of the bitmap words: rank of a position among the borders
+//   diffc[NB]      difference array indexed by border rank;   posc[NB] genomic coordinate of every border
+// A bundle's differences sum to 0, so ONE device-wide prefix sum over diffc yields every bundle's coverage, and one
+// device-wide rank of (coverage > 0) compacts the segments: seg i = (posc[i], posc[i + 1], cov[i]).
 
-HD u64 st_pack(u64 status, long long v) { return (status << 62) | ((u64)v & 0x3fffffffffffffffULL); }
-HD u64 st_status(u64 x) { return x >> 62; }
-HD long long st_value(u64 x) { return ((long long)(x << 2)) >> 2; }
+// tile sums of the border popcounts
+KERNEL k_bord_tile_sum(const u32 *border, int64_t n_words, int64_t n_tiles, int32_t *tile_sum)
+{
+	SHARED int s;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		if(threadIdx.x == 0) s = 0;
+		BLOCK_SYNC();
+		int acc = 0;
+		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
+		{
+			int64_t w = t * CTILE + i;
+			if(w < n_words) acc += __popc(border[w]);
+		}
+		if(acc) atomicAdd(&s, acc);
+		BLOCK_SYNC();
+		if(threadIdx.x == 0) tile_sum[t] = s;
+		BLOCK_SYNC();
+	}
+}
 
-KERNEL k_border_count(const u32 *border, int64_t n_words, unsigned long long *total)
+// wrank[w] = number of borders before word w (wrank[n_words] = total)
+KERNEL k_bord_tile_rank(const u32 *border, int64_t n_words, int64_t n_tiles, const int64_t *tile_off, u32 *wrank)
+{
+	SHARED int f[CTILE];
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
+		{
+			int64_t w = t * CTILE + i;
+			f[i] = w < n_words ? __popc(border[w]) : 0;
+		}
+		BLOCK_SYNC();
+		block_excl_scan(f, CTILE);
+		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
+		{
+			int64_t w = t * CTILE + i;
+			if(w <= n_words) wrank[w] = (u32)(tile_off[t] + f[i]);
+		}
+		BLOCK_SYNC();
+	}
+}
+
+// rank of global window position g among the borders (g itself must be a border)
+DEV int64_t border_rank(const u32 *border, const u32 *wrank, int64_t g)
+{
+	u32 w = border[g >> 5];
+	return (int64_t)wrank[g >> 5] + __popc(w & ((1u << (g & 31)) - 1u));
+}
+
+// genomic coordinate of every border; one thread per bitmap word
+KERNEL k_bord_positions(int64_t n_words, const u32 *border, const u32 *wrank, int32_t n_bundles, const int64_t *cov_base,
+		const int32_t *b_lpos, int32_t *posc)
+{
+	int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(w >= n_words) return;
+	u32 bits = border[w];
+	if(!bits) return;
+	int64_t g0 = w << 5;
+	int b = find_segment(cov_base, n_bundles, g0);
+	int32_t p0 = (int32_t)(g0 - cov_base[b]) + b_lpos[b];
+	int64_t o = wrank[w];
+	while(bits)
+	{
+		int k = __ffs((int)bits) - 1;
+		bits &= bits - 1;
+		posc[o++] = p0 + k;
+	}
+}
+
+// bord_off[b] = rank of the first border of bundle b's window (bord_off[NB] = total)
+KERNEL k_bord_off(int32_t nb, const int64_t *cov_base, const u32 *wrank, int64_t *bord_off)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	int c = (i < n_words) ? __popc(border[i]) : 0;
-#ifndef AGPU_EMU
-	for(int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
-	if((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
-#else
-	if(c) *total += (unsigned long long)c;
-#endif
+	if(i > nb) return;
+	bord_off[i] = (int64_t)wrank[cov_base[i] >> 5];
 }
 
-struct cov_scan_args
+// one thread per hit: +1 at the start and -1 at the end of every BAM_CMATCH block (bundle_base::add_intervals,
+// rnacore/bundle_base.cc:106-158: only op M adds coverage)
+KERNEL k_cov_add(hits_dev h, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, const u32 *border,
+		const u32 *wrank, int32_t *diffc)
 {
-	const int32_t *diff;
-	const u32 *border;
-	int64_t n_tiles;
-	u64 *cov_state, *seg_state;
-	int *ticket;
-	int64_t *tile_seg_off;         // [n_tiles + 1]
-	int32_t n_bundles;
-	const int64_t *cov_base;
-	const int32_t *b_lpos;
-	int32_t *seg_l, *seg_r, *seg_c;
-	int64_t seg_cap;
-	int *err;
-};
-
-// next set border bit strictly after global position g, searching up to `end`; -1 if none
-DEV int64_t next_border(const u32 *border, int64_t g, int64_t end)
-{
-	int64_t q = g + 1;
-	while(q < end)
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	int b = hit_bundle[i];
+	int64_t base = cov_base[b] - (int64_t)b_lpos[b];
+	u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
+	int32_t p = h.pos[i];
+	for(u32 k = c0; k < c1; k++)
 	{
-		u32 w = border[q >> 5] >> (q & 31);
-		if(w) return q + (__ffs((int)w) - 1);
-		q = ((q >> 5) + 1) << 5;
-	}
-	return -1;
-}
-
-#ifndef AGPU_EMU
-// warp 0: exclusive prefix of tile t from the states of its predecessors
-DEV long long lookback(volatile u64 *state, int64_t t)
-{
-	const int lane = threadIdx.x & 31;
-	long long prefix = 0;
-	int64_t look = t - 1;
-	while(look >= 0)
-	{
-		int64_t idx = look - lane;
-		u64 st = (idx >= 0) ? state[idx] : st_pack(ST_INCL, 0);
-		while(__any_sync(0xffffffffu, st_status(st) == 0)) { if(st_status(st) == 0) st = state[idx]; }
-		unsigned incl = __ballot_sync(0xffffffffu, st_status(st) == ST_INCL);
-		long long v = st_value(st);
-		if(incl)
+		u32 c = h.cigar[k];
+		u32 op = c & 0xf, len = c >> 4;
+		if((0x3C1A7 >> (op << 1)) & 2) p += (int32_t)len;
+		if(op == 0 && len > 0)
 		{
-			int first = __ffs((int)incl) - 1;
-			if(lane > first) v = 0;
-			for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-			prefix += v;
-			break;
+			atomicAdd(&diffc[border_rank(border, wrank, base + p - (int32_t)len)], 1);
+			atomicAdd(&diffc[border_rank(border, wrank, base + p)], -1);
 		}
-		for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-		prefix += v;
-		look -= 32;
-	}
-	return prefix;
-}
-
-// block-wide exclusive scan of one int per thread (CS_THREADS threads); returns the exclusive prefix, total in *tot
-DEV int block_scan_1(int x, int *tot, int *wsum)
-{
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	int inc = x;
-	for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
-	if(lane == 31) wsum[warp] = inc;
-	__syncthreads();
-	if(warp == 0)
-	{
-		int w = lane < CS_THREADS / 32 ? wsum[lane] : 0;
-		int wi = w;
-		for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, wi, o); if(lane >= o) wi += y; }
-		if(lane < CS_THREADS / 32) wsum[lane] = wi - w;
-		if(lane == 31) wsum[CS_THREADS / 32] = wi;
-	}
-	__syncthreads();
-	int r = wsum[warp] + inc - x;
-	*tot = wsum[CS_THREADS / 32];
-	__syncthreads();
-	return r;
-}
-
-__global__ void __launch_bounds__(CS_THREADS) k_cov_scan(cov_scan_args a)
-{
-	__shared__ int s_tile_lo, s_tile_hi, s_bundle;
-	__shared__ int wsum[CS_THREADS / 32 + 1];
-	__shared__ long long s_pre;
-	const int tid = threadIdx.x;
-	while(true)
-	{
-		if(tid == 0)
-		{
-			int64_t t0 = (int64_t)atomicAdd(a.ticket, 1);
-			s_tile_lo = (int)(t0 & 0x7fffffff); s_tile_hi = (int)(t0 >> 31);
-		}
-		__syncthreads();
-		const int64_t t = (int64_t)s_tile_lo | ((int64_t)s_tile_hi << 31);
-		if(t >= a.n_tiles) break;
-		const int64_t g0 = t * COV_TILE;
-		// 8 consecutive difference words per thread: two coalesced 128-bit loads
-		const int4 *d4 = reinterpret_cast<const int4*>(a.diff + g0) + tid * 2;
-		int4 x = d4[0], y = d4[1];
-		int v[CS_ITEMS] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
-		for(int i = 1; i < CS_ITEMS; i++) v[i] += v[i - 1];
-		int tile_sum;
-		int texcl = block_scan_1(v[CS_ITEMS - 1], &tile_sum, wsum);
-		if(tid == 0)
-		{
-			((volatile u64*)a.cov_state)[t] = st_pack(t == 0 ? ST_INCL : ST_AGG, tile_sum);
-			if(a.n_bundles > 0) s_bundle = find_segment(a.cov_base, a.n_bundles, g0);
-		}
-		if(tid < 32)
-		{
-			long long p = lookback((volatile u64*)a.cov_state, t);
-			if(tid == 0)
-			{
-				if(t > 0) ((volatile u64*)a.cov_state)[t] = st_pack(ST_INCL, p + tile_sum);
-				s_pre = p;
-			}
-		}
-		__syncthreads();
-		const int base = (int)s_pre + texcl;
-		const int b = s_bundle;
-		// this thread's byte of the border bitmap
-		u32 w = a.border[(g0 >> 5) + (tid >> 2)];
-		u32 byte = (w >> (8 * (tid & 3))) & 0xffu;
-		u32 fm = 0;
-		for(int i = 0; i < CS_ITEMS; i++) if(((byte >> i) & 1u) && (base + v[i]) > 0) fm |= 1u << i;
-		int cnt = __popc(fm);
-		int tile_cnt;
-		int cexcl = block_scan_1(cnt, &tile_cnt, wsum);
-		if(tid == 0) ((volatile u64*)a.seg_state)[t] = st_pack(t == 0 ? ST_INCL : ST_AGG, tile_cnt);
-		if(tid < 32)
-		{
-			long long q = lookback((volatile u64*)a.seg_state, t);
-			if(tid == 0)
-			{
-				if(t > 0) ((volatile u64*)a.seg_state)[t] = st_pack(ST_INCL, q + tile_cnt);
-				s_pre = q;
-				a.tile_seg_off[t] = q;
-				if(t == a.n_tiles - 1) a.tile_seg_off[a.n_tiles] = q + tile_cnt;
-			}
-		}
-		__syncthreads();
-		if(fm)
-		{
-			int64_t o = s_pre + cexcl;
-			const int64_t org = a.cov_base[b] - (int64_t)a.b_lpos[b];
-			const int64_t end = a.cov_base[b + 1];
-			for(int i = 0; i < CS_ITEMS; i++)
-			{
-				if(!((fm >> i) & 1u)) continue;
-				int64_t g = g0 + tid * CS_ITEMS + i;
-				int64_t r;
-				u32 above = byte >> (i + 1);
-				if(above) r = g + __ffs((int)above);
-				else
-				{
-					u32 rest = (tid & 3) == 3 ? 0u : (w >> (8 * ((tid & 3) + 1)));
-					if(rest) r = g0 + (int64_t)(tid + 1) * CS_ITEMS + (__ffs((int)rest) - 1);
-					else r = next_border(a.border, ((g >> 5) << 5) + 31, end);
-				}
-				if(o < a.seg_cap)
-				{
-					a.seg_l[o] = (int32_t)(g - org);
-					a.seg_r[o] = (int32_t)((r < 0 ? end : r) - org);
-					a.seg_c[o] = base + v[i];
-				}
-				else atomicAdd(&a.err[ERR_CAP], 1);
-				o++;
-			}
-		}
-		__syncthreads();
 	}
 }
-#else
-// kernel-logic test build: the same tile protocol executed by one thread per tile, tiles in ticket order
-KERNEL k_cov_scan(cov_scan_args a)
+
+// the stretches added by update_bridges (rnacore/bundle_base.cc:498-504), kept as a list of global window positions
+KERNEL k_cov_add_extra(int64_t n, const int64_t *ex_s, const int64_t *ex_e, const u32 *border, const u32 *wrank, int32_t *diffc)
 {
-	while(true)
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	atomicAdd(&diffc[border_rank(border, wrank, ex_s[i])], 1);
+	atomicAdd(&diffc[border_rank(border, wrank, ex_e[i])], -1);
+}
+
+// tile sums of the differences
+KERNEL k_covc_tile_sum(const int32_t *diffc, int64_t n, int64_t n_tiles, int32_t *tile_sum)
+{
+	SHARED int s;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
 	{
-		int64_t t = (int64_t)atomicAdd(a.ticket, 1);
-		if(t >= a.n_tiles) break;
-		const int64_t g0 = t * COV_TILE;
-		long long pre = t > 0 ? st_value(a.cov_state[t - 1]) : 0;
-		long long q = t > 0 ? st_value(a.seg_state[t - 1]) : 0;
-		a.tile_seg_off[t] = q;
-		int b = a.n_bundles > 0 ? find_segment(a.cov_base, a.n_bundles, g0) : 0;
-		const int64_t org = a.cov_base[b] - (int64_t)a.b_lpos[b];
-		const int64_t end = a.cov_base[b + 1];
-		long long cov = pre;
-		for(int i = 0; i < COV_TILE; i++)
+		if(threadIdx.x == 0) s = 0;
+		BLOCK_SYNC();
+		int acc = 0;
+		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
+		{
+			int64_t g = t * CTILE + i;
+			if(g < n) acc += diffc[g];
+		}
+		if(acc) atomicAdd(&s, acc);
+		BLOCK_SYNC();
+		if(threadIdx.x == 0) tile_sum[t] = s;
+		BLOCK_SYNC();
+	}
+}
+
+// cov[i] = coverage right of border i (inclusive prefix sum, written in place of the differences is NOT done: the
+// differences stay, update_bridges adds to them); tile_cnt[t] = borders of the tile that open a segment (cov > 0)
+KERNEL k_covc_tile_cover(const int32_t *diffc, int64_t n, int64_t n_tiles, const int64_t *tile_pre, int32_t *cov, int32_t *tile_cnt)
+{
+	SHARED int f[CTILE];
+	SHARED int s;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		if(threadIdx.x == 0) s = 0;
+		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
+		{
+			int64_t g = t * CTILE + i;
+			f[i] = g < n ? diffc[g] : 0;
+		}
+		BLOCK_SYNC();
+		block_excl_scan(f, CTILE);
+		int acc = 0;
+		int pre = (int)tile_pre[t];
+		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
+		{
+			int64_t g = t * CTILE + i;
+			if(g >= n) continue;
+			int c = pre + f[i] + diffc[g];
+			cov[g] = c;
+			if(c > 0) acc++;
+		}
+		if(acc) atomicAdd(&s, acc);
+		BLOCK_SYNC();
+		if(threadIdx.x == 0) tile_cnt[t] = s;
+		BLOCK_SYNC();
+	}
+}
+
+// segments in order: border i with cov[i] > 0 opens [posc[i], posc[i + 1]) with value cov[i]; also seg_off[b] = number of
+// segments before the first border of bundle b
+KERNEL k_covc_emit(const int32_t *cov, const int32_t *posc, int64_t n, int64_t n_tiles, const int64_t *tile_off, int32_t n_bundles,
+		const int64_t *bord_off, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c, int64_t *seg_off)
+{
+	SHARED int f[CTILE + 1];
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		const int64_t g0 = t * CTILE;
+		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
 		{
 			int64_t g = g0 + i;
-			cov += a.diff[g];
-			if(!((a.border[g >> 5] >> (g & 31)) & 1u) || cov <= 0) continue;
-			int64_t r = next_border(a.border, g, end);
-			if(q < a.seg_cap)
-			{
-				a.seg_l[q] = (int32_t)(g - org);
-				a.seg_r[q] = (int32_t)((r < 0 ? end : r) - org);
-				a.seg_c[q] = (int32_t)cov;
-			}
-			else atomicAdd(&a.err[ERR_CAP], 1);
-			q++;
+			f[i] = (g < n && cov[g] > 0) ? 1 : 0;
 		}
-		a.cov_state[t] = st_pack(ST_INCL, cov);
-		a.seg_state[t] = st_pack(ST_INCL, q);
-		if(t == a.n_tiles - 1) a.tile_seg_off[a.n_tiles] = q;
+		BLOCK_SYNC();
+		int tot = block_excl_scan(f, CTILE);
+		if(threadIdx.x == 0) f[CTILE] = tot;
+		BLOCK_SYNC();
+		const int64_t o0 = tile_off[t];
+		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
+		{
+			int64_t g = g0 + i;
+			if(g >= n || cov[g] <= 0) continue;
+			int64_t o = o0 + f[i];
+			seg_l[o] = posc[g];
+			seg_r[o] = g + 1 < n ? posc[g + 1] : posc[g];
+			seg_c[o] = cov[g];
+		}
+		// bundles whose first border falls into this tile (the last tile also owns rank n)
+		int64_t hi = (t == n_tiles - 1) ? n + 1 : g0 + CTILE;
+		int b0 = lower_bound_idx(bord_off, n_bundles + 1, g0);
+		for(int b = b0 + (int)threadIdx.x; b <= n_bundles && bord_off[b] < hi; b += blockDim.x)
+			seg_off[b] = o0 + f[bord_off[b] - g0];
+		BLOCK_SYNC();
 	}
 }
-#endif
 
 } // namespace agpu
 

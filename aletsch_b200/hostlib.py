@@ -174,6 +174,29 @@ class PackedBatch:
         out["sample"] = int(a["bundle_sample"][k])
         return out
 
+    def slice(self, b0, b1):
+        """new PackedBatch holding the contiguous bundle range [b0, b1) (array slices, cigar offsets rebased)."""
+        a = self.a
+        h0, h1 = int(a["bundle_hit_off"][b0]), int(a["bundle_hit_off"][b1])
+        c0, c1 = int(a["cigar_off"][h0]), int(a["cigar_off"][h1])
+        arr = {f: np.ascontiguousarray(a[f][h0:h1]) for f, _ in HIT_FIELDS}
+        arr["bundle_hit_off"] = np.ascontiguousarray(a["bundle_hit_off"][b0:b1 + 1] - h0)
+        arr["cigar_off"] = np.ascontiguousarray(a["cigar_off"][h0:h1 + 1] - np.uint32(c0))
+        arr["cigar"] = np.ascontiguousarray(a["cigar"][c0:c1])
+        for f in ("bundle_tid", "bundle_sample", "bundle_side"):
+            if f in a:
+                arr[f] = np.ascontiguousarray(a[f][b0:b1])
+        return PackedBatch(arr)
+
+    def split(self, parts):
+        """`parts` contiguous sub-batches of roughly equal hit counts (bundles stay whole)."""
+        off = self.a["bundle_hit_off"]
+        cuts = [0]
+        for k in range(1, parts):
+            cuts.append(max(cuts[-1], int(np.searchsorted(off, self.n_hits * k // parts))))
+        cuts.append(self.n_bundles)
+        return [self.slice(cuts[k], cuts[k + 1]) for k in range(parts) if cuts[k + 1] > cuts[k]]
+
     def select(self, ks):
         """new PackedBatch holding bundles ks in that order."""
         a = self.a

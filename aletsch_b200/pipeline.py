@@ -1,0 +1,63 @@
+"""Host-side pipelining of batches through the C ABI: the call a user of the path makes for a region's worth of
+samples.  The reference enters bundle::bridge once per bundle from `-t N` pool threads (meta/incubator.cc:615-635);
+here a few host threads each own an agpu_ctx (= one CUDA stream) and take whole batches (e.g. one sample's bundles
+of a region) from a queue: upload from pinned host memory -> agpu_batch_bridge_all -> results back.  While one
+stream computes, another stream's host->device copy is in flight on the copy engine, so the PCIe transfer of
+batch i+1 hides behind the kernels of batch i.  The ABI is re-entrant across contexts."""
+import threading
+
+from . import gpu as G
+
+
+class Pipeline:
+    def __init__(self, device=0, n_streams=3, lib_path=None):
+        self.ctxs = [G.Context(device, lib_path=lib_path) for _ in range(max(1, n_streams))]
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+        self.ctxs = []
+
+    @property
+    def launches(self):
+        return sum(c.launches for c in self.ctxs)
+
+    def sync(self):
+        for c in self.ctxs:
+            c.sync()
+
+    def run(self, views, params, consume=None):
+        """views: list of (agpu_batch_in with HOST pointers, keepalive).  Each batch goes through upload + bridge_all;
+        consume(i, batch) may fetch results while the batch is still resident (default: the counters).  Returns the list of
+        per-batch results in input order."""
+        out = [None] * len(views)
+        nxt = [0]
+        lock = threading.Lock()
+        errs = []
+
+        def work(ctx):
+            try:
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= len(views) or errs:
+                        return
+                    v, keep = views[i]
+                    bt = ctx.upload(v, keepalive=keep)
+                    try:
+                        bt.bridge_all(params)
+                        out[i] = consume(i, bt) if consume else bt.counts()
+                    finally:
+                        bt.free()
+            except Exception as e:      # noqa: BLE001 -- re-raised on the caller's thread
+                errs.append(e)
+
+        ths = [threading.Thread(target=work, args=(c,)) for c in self.ctxs[:max(1, min(len(self.ctxs), len(views)))]]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
