@@ -95,6 +95,77 @@ DEV void block_sort_pairs(u64 *key, u32 *val, int n)
 	else bitonic_pairs(key, val, n);
 }
 
+#ifndef AGPU_EMU
+// exclusive prefix sum of a[0..n) in place; returns the total to every thread.  Coalesced sweeps of blockDim elements:
+// warp-shuffle scan, warp totals through shared memory, running carry in a register.
+DEV int block_excl_scan(int *a, int n)
+{
+	__shared__ int wsum[AGPU_MAX_BLOCK / 32];
+	const int nt = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = (nt + 31) >> 5;
+	int carry = 0;
+	for(int base = 0; base < n; base += nt)
+	{
+		const int i = base + t;
+		const int x = i < n ? a[i] : 0;
+		int inc = x;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+		if(nw > 1)
+		{
+			if(lane == 31) wsum[w] = inc;
+			__syncthreads();
+			int pre = 0, tot = 0;
+			for(int k = 0; k < nw; k++) { int v = wsum[k]; if(k < w) pre += v; tot += v; }
+			if(i < n) a[i] = carry + pre + inc - x;
+			carry += tot;
+			__syncthreads();
+		}
+		else
+		{
+			if(i < n) a[i] = carry + inc - x;
+			carry += __shfl_sync(0xffffffffu, inc, 31);
+		}
+	}
+	__syncthreads();
+	return carry;
+}
+
+// inclusive running maximum of a[0..n) in place
+DEV void block_incl_maxscan(int *a, int n)
+{
+	__shared__ int wmax[AGPU_MAX_BLOCK / 32];
+	const int nt = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = (nt + 31) >> 5;
+	const int NEG = -0x7fffffff;
+	int carry = NEG;
+	for(int base = 0; base < n; base += nt)
+	{
+		const int i = base + t;
+		int inc = i < n ? a[i] : NEG;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o && y > inc) inc = y; }
+		if(nw > 1)
+		{
+			if(lane == 31) wmax[w] = inc;
+			__syncthreads();
+			int pre = NEG, tot = NEG;
+			for(int k = 0; k < nw; k++) { int v = wmax[k]; if(k < w && v > pre) pre = v; if(v > tot) tot = v; }
+			int r = inc > pre ? inc : pre;
+			if(carry > r) r = carry;
+			if(i < n) a[i] = r;
+			if(tot > carry) carry = tot;
+			__syncthreads();
+		}
+		else
+		{
+			int r = inc > carry ? inc : carry;
+			if(i < n) a[i] = r;
+			int tot = __shfl_sync(0xffffffffu, inc, 31);
+			if(tot > carry) carry = tot;
+		}
+	}
+	__syncthreads();
+}
+#else
 // exclusive prefix sum of a[0..n) in place; returns the total to every thread
 DEV int block_excl_scan(int *a, int n)
 {
@@ -147,6 +218,8 @@ DEV void block_incl_maxscan(int *a, int n)
 	for(int i = lo; i < hi; i++) { if(a[i] > run) run = a[i]; a[i] = run; }
 	BLOCK_SYNC();
 }
+
+#endif
 
 } // namespace agpu
 

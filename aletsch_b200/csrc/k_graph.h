@@ -108,7 +108,7 @@ KERNEL k_graph_bounds(graph_in in, int64_t *ub_junc, int64_t *ub_pex, int64_t *u
 			ub_junc[b] = J;
 			ub_pex[b] = P;
 			ub_edge[b] = J + 3 * P + 2;
-			ub_iarena[b] = (nh + nf) + 20 * ninst + 10 * P + 128;
+			ub_iarena[b] = (nh + nf) + 20 * ninst + 10 * P + 2 * S + 136;
 			ub_karena[b] = 6 * ninst + (J + 3 * P + 2) + 64;
 		}
 		BLOCK_SYNC();
@@ -119,6 +119,8 @@ struct seg_view
 {
 	const int32_t *l, *r, *c;
 	int n;
+	const int32_t *nhead;      // nhead[i] = first index > i whose segment does not touch its predecessor (n if none)
+	const u32 *psum;           // psum[i] = sum over segments < i of (r - l) * c in 32-bit wrap arithmetic (n + 1 entries)
 };
 
 // locate_boundary_iterators (rnacore/interval_map.cc:70-87): index range of the segments lying fully inside [x, y)
@@ -131,37 +133,35 @@ DEV bool segs_inside(const seg_view &s, int32_t x, int32_t y, int &i0, int &i1)
 	return i0 <= i1;
 }
 
-// evaluate_rectangle (rnacore/interval_map.cc:166-195)
-DEV void evaluate_rectangle(const seg_view &s, int32_t ll, int32_t rr, double &ave, double &dev, double &mx)
+// compute_sum_overlap (rnacore/interval_map.cc:128-149) over the segments a..e: int32 arithmetic
+DEV int32_t seg_sum(const seg_view &s, int a, int e) { return (int32_t)(s.psum[e + 1] - s.psum[a]); }
+
+// evaluate_rectangle (rnacore/interval_map.cc:166-195) over [ll, rr) whose inside segments are a..e (none if e < a)
+DEV void evaluate_rectangle(const seg_view &s, int32_t ll, int32_t rr, int a, int e, double &ave, double &dev, double &mx)
 {
 	ave = 0; dev = 1; mx = 0;
-	int i0, i1;
-	if(!segs_inside(s, ll, rr, i0, i1)) return;
-	int32_t sum = 0, m = 0;
-	for(int i = i0; i <= i1; i++)
-	{
-		sum = (int32_t)((u32)sum + (u32)((s.r[i] - s.l[i]) * s.c[i]));     // int32 arithmetic, as in compute_sum_overlap
-		if(s.c[i] > m) m = s.c[i];
-	}
-	mx = 1.0 * m;
+	if(e < a) return;
+	int32_t sum = seg_sum(s, a, e);
 	ave = 1.0 * sum / (rr - ll);
+	int32_t m = 0;
 	double var = 0;
-	for(int i = i0; i <= i1; i++)
+	for(int i = a; i <= e; i++)                        // the reference's accumulation order
 	{
-		double d = s.c[i] - ave;
+		int32_t c = s.c[i];
+		if(c > m) m = c;
+		double d = c - ave;
 		var += d * d * (s.r[i] - s.l[i]);
 	}
+	mx = 1.0 * m;
 	dev = sqrt(var / (rr - ll));
 }
 
-// region::empty_subregion (rnacore/region.cc:88-107)
-DEV bool empty_subregion(const seg_view &s, int32_t p1, int32_t p2, int min_len, double min_overlap)
+// region::empty_subregion (rnacore/region.cc:88-107) for the run [p1, p2) made of the segments a..e
+DEV bool empty_subregion(const seg_view &s, int32_t p1, int32_t p2, int a, int e, int min_len, double min_overlap)
 {
 	if(p2 - p1 < min_len) return true;
-	int i0, i1;
-	if(!segs_inside(s, p1, p2, i0, i1)) return true;
-	int32_t sum = 0;
-	for(int i = i0; i <= i1; i++) sum = (int32_t)((u32)sum + (u32)((s.r[i] - s.l[i]) * s.c[i]));
+	if(e < a) return true;
+	int32_t sum = seg_sum(s, a, e);
 	double ratio = sum * 1.0 / (p2 - p1);
 	if(ratio < min_overlap) return true;
 	return false;
@@ -180,7 +180,8 @@ struct pexon_sink
 	}
 };
 
-// iterates the runs of region::jmap after build_join_interval_map (+ smooth_join_interval_map)
+// iterates the runs of region::jmap after build_join_interval_map (+ smooth_join_interval_map); every run comes with the
+// index range a..e of the segments inside it
 struct run_iter
 {
 	const seg_view &s;
@@ -190,6 +191,7 @@ struct run_iter
 	// pending raw run
 	bool have_raw;
 	int32_t raw_l, raw_r;
+	int raw_a, raw_e;
 	bool tail_done;
 	int32_t prev_end;          // `p` of smooth_join_interval_map
 
@@ -203,29 +205,32 @@ struct run_iter
 		prev_end = lp;
 	}
 
-	DEV bool next_raw(int32_t &l, int32_t &r)
+	DEV bool next_raw(int32_t &l, int32_t &r, int &a, int &e)
 	{
 		if(!any || i > i1) return false;
-		l = s.l[i]; r = s.r[i]; i++;
-		while(i <= i1 && s.l[i] == r) { r = s.r[i]; i++; }     // touching segments join (all values are 1)
+		a = i;
+		e = s.nhead[i] - 1;                                // touching segments join (all values are 1)
+		if(e > i1) e = i1;
+		l = s.l[a]; r = s.r[e];
+		i = e + 1;
 		return true;
 	}
 
 	// next run of the (smoothed) join map
-	DEV bool next(int32_t &l, int32_t &r)
+	DEV bool next(int32_t &l, int32_t &r, int &a, int &e)
 	{
-		if(!smooth) return next_raw(l, r);
+		if(!smooth) return next_raw(l, r, a, e);
 		// smoothing (rnacore/region.cc:60-86): the stretch between the previous run (or lpos) and a run is filled
 		// when it is at most min_subregion_gap long; likewise the stretch between the last run and rpos
 		int32_t cl, cr;
-		if(have_raw) { cl = raw_l; cr = raw_r; have_raw = false; }
-		else if(!next_raw(cl, cr))
+		if(have_raw) { cl = raw_l; cr = raw_r; a = raw_a; e = raw_e; have_raw = false; }
+		else if(!next_raw(cl, cr, a, e))
 		{
 			if(tail_done) return false;
 			tail_done = true;
 			// no run is pending: the tail stretch [prev_end, rpos) becomes a run of its own only if nothing precedes it
 			// (otherwise it was merged below); this happens when the region holds no run at all
-			if(prev_end == lpos && prev_end < rpos && rpos - prev_end <= gap) { l = prev_end; r = rpos; prev_end = rpos; return true; }
+			if(prev_end == lpos && prev_end < rpos && rpos - prev_end <= gap) { l = prev_end; r = rpos; a = 0; e = -1; prev_end = rpos; return true; }
 			return false;
 		}
 		if(cl - prev_end <= gap) cl = prev_end;              // fill [p, p1); at the region start this extends to lpos
@@ -233,14 +238,15 @@ struct run_iter
 		while(true)
 		{
 			int32_t nl, nr;
-			if(!next_raw(nl, nr))
+			int na, ne;
+			if(!next_raw(nl, nr, na, ne))
 			{
 				tail_done = true;
 				if(cr < rpos && rpos - cr <= gap) cr = rpos;
 				break;
 			}
-			if(nl - cr <= gap) { cr = nr; continue; }
-			raw_l = nl; raw_r = nr; have_raw = true;
+			if(nl - cr <= gap) { cr = nr; e = ne; continue; }
+			raw_l = nl; raw_r = nr; raw_a = na; raw_e = ne; have_raw = true;
 			break;
 		}
 		prev_end = cr;
@@ -254,45 +260,39 @@ DEV void region_pexons(const seg_view &s, int32_t lpos, int32_t rpos, int ltype,
 		int min_gap, int min_len, double min_overlap, double min_weight, pexon_sink &out)
 {
 	bool smooth = (ltype == RIGHT_SPLICE && rtype == LEFT_SPLICE);
-	// peek: is the join map empty / does its first run span the whole region?
-	int32_t f_l = 0, f_r = 0;
-	bool nonempty;
-	{
-		run_iter it(s, lpos, rpos, smooth, min_gap);
-		nonempty = it.next(f_l, f_r);
-	}
+	run_iter it(s, lpos, rpos, smooth, min_gap);
+	// the first run: is the join map empty / does the run span the whole region?
+	int32_t p1 = 0, p2 = 0;
+	int a = 0, e = -1;
+	bool nonempty = it.next(p1, p2, a, e);
 	if(!nonempty && rpos == lpos + 1 && (ltype == END_BOUNDARY || rtype == START_BOUNDARY))
 	{
 		out.push(lpos, rpos, ltype, rtype, min_weight, 1.0, -1.0);
 		return;
 	}
-	if(nonempty && f_l == lpos && f_r == rpos)
+	if(nonempty && p1 == lpos && p2 == rpos)
 	{
-		double a, d, m;
-		evaluate_rectangle(s, lpos, rpos, a, d, m);
-		out.push(lpos, rpos, ltype, rtype, a, d, m);
+		double av = 0, d = 1, m = 0;
+		if(out.emit) evaluate_rectangle(s, lpos, rpos, a, e, av, d, m);
+		out.push(lpos, rpos, ltype, rtype, av, d, m);
 		return;
 	}
 	// jmap.find(ROI(lpos, lpos + 1)) == end  <=>  no run starts at lpos (runs lie inside [lpos, rpos))
-	if(ltype == RIGHT_SPLICE && !(nonempty && f_l == lpos))
+	if(ltype == RIGHT_SPLICE && !(nonempty && p1 == lpos))
 		out.push(lpos, lpos + 1, ltype, END_BOUNDARY, min_weight, 1.0, -1.0);
 	bool covers_end = false;
+	for(bool have = nonempty; have; have = it.next(p1, p2, a, e))
 	{
-		run_iter it(s, lpos, rpos, smooth, min_gap);
-		int32_t p1, p2;
-		while(it.next(p1, p2))
-		{
-			if(p2 == rpos) covers_end = true;
-			bool b = empty_subregion(s, p1, p2, min_len, min_overlap);
-			if(p1 == lpos && ltype == RIGHT_SPLICE) b = false;
-			if(p2 == rpos && rtype == LEFT_SPLICE) b = false;
-			if(b) continue;
-			int lt = (p1 == lpos) ? ltype : START_BOUNDARY;
-			int rt = (p2 == rpos) ? rtype : END_BOUNDARY;
-			double a, d, m;
-			evaluate_rectangle(s, p1, p2, a, d, m);
-			out.push(p1, p2, lt, rt, a, d, m);
-		}
+		if(p2 == rpos) covers_end = true;
+		bool b = empty_subregion(s, p1, p2, a, e, min_len, min_overlap);
+		if(p1 == lpos && ltype == RIGHT_SPLICE) b = false;
+		if(p2 == rpos && rtype == LEFT_SPLICE) b = false;
+		if(b) continue;
+		int lt = (p1 == lpos) ? ltype : START_BOUNDARY;
+		int rt = (p2 == rpos) ? rtype : END_BOUNDARY;
+		double av = 0, d = 1, m = 0;
+		if(out.emit) evaluate_rectangle(s, p1, p2, a, e, av, d, m);
+		out.push(p1, p2, lt, rt, av, d, m);
 	}
 	if(rtype == LEFT_SPLICE && !covers_end)
 		out.push(rpos - 1, rpos, START_BOUNDARY, rtype, min_weight, 1.0, -1.0);
@@ -319,6 +319,33 @@ KERNEL k_graph_build(const int32_t *order, int n_order, graph_in in, graph_dev g
 		sv.l = in.seg_l + in.seg_off[b]; sv.r = in.seg_r + in.seg_off[b]; sv.c = in.seg_c + in.seg_off[b];
 		sv.n = (int)(in.seg_off[b + 1] - in.seg_off[b]);
 		const int nh = in.hc.count(b), nf = in.fc.count(b), nch = nh + nf;
+
+		// ---- segment side tables: run structure (touching segments) and prefix sums of len * cov
+		{
+			const int S = sv.n;
+			int32_t *nhead = ia; ia += S + 1;
+			u32 *psum = (u32*)ia; ia += S + 2;
+			// reverse running minimum of "next index that starts a run", as an inclusive max-scan of the negated candidates
+			for(int k = t; k < S; k += nt)
+			{
+				int i = S - 1 - k;
+				nhead[k] = (i + 1 < S && sv.l[i + 1] != sv.r[i]) ? -(i + 1) : -S;
+				psum[i] = (u32)(sv.r[i] - sv.l[i]) * (u32)sv.c[i];
+			}
+			BLOCK_SYNC();
+			block_incl_maxscan(nhead, S);
+			// un-reverse in place (pairwise swap) and negate
+			for(int k = t; k < (S + 1) / 2; k += nt)
+			{
+				int x = nhead[k], y = nhead[S - 1 - k];
+				nhead[k] = -y; nhead[S - 1 - k] = -x;
+			}
+			BLOCK_SYNC();
+			int tot = block_excl_scan((int*)psum, S);
+			if(t == 0) psum[S] = (u32)tot;
+			BLOCK_SYNC();
+			sv.nhead = nhead; sv.psum = psum;
+		}
 
 		// ---- junction instances in the order build_junctions feeds jcst: hcst chains, then fcst chains
 		int32_t *ci = ia; ia += nch + 1;
