@@ -599,6 +599,7 @@ struct vote_out
 {
 	int32_t *type, *strand, *choices;
 	double *score;
+	int32_t *pick;               // index of the chosen candidate (pass 0), -1 if none
 	int32_t *clen, *wlen;        // lengths (pass 0), then
 	const int64_t *coff, *woff;  // offsets (pass 1)
 	int32_t *chain, *whole;
@@ -610,31 +611,62 @@ KERNEL k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *c
 {
 	int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(c >= n_clu) return;
-	if(!emit) { o.type[c] = -1; o.strand[c] = 0; o.choices[c] = 0; o.score[c] = 0; o.clen[c] = 0; o.wlen[c] = 0; }
-	int ss = br.vp1[c], tt = br.vp2[c];
-	if(ss < 0 || tt < 0) return;
-	int b = c_bundle[c];
-	sgraph sg = sgraph_of(g, b_strand, b);
+	const int ss = br.vp1[c], tt = br.vp2[c];
+	if(!emit)
+	{
+		o.type[c] = -1; o.strand[c] = 0; o.choices[c] = 0; o.score[c] = 0; o.clen[c] = 0; o.wlen[c] = 0; o.pick[c] = -1;
+		if(ss < 0 || tt < 0) return;
+	}
+	else if(o.pick[c] < 0) return;
+	const int b = c_bundle[c];
 	const int K = br.K;
 	const int32_t *ch1 = NULL, *ch2 = NULL;
 	int n1 = 0, n2 = 0;
 	if(c_chain1[c] >= 0) { ch1 = cv.ptr(b, c_chain1[c]); n1 = cv.len(b, c_chain1[c]); }
 	if(c_chain2[c] >= 0) { ch2 = cv.ptr(b, c_chain2[c]); n2 = cv.len(b, c_chain2[c]); }
-	int32_t bd0 = c_bounds[4 * c], bd3 = c_bounds[4 * c + 3];
-	int type = 0, be = -1, choices = 0, best_strand = 0;
-	double best_score = 0;
-	seq3 best_w, best_c;
-	best_w.n[0] = best_w.n[1] = best_w.n[2] = 0; best_c = best_w;
-	best_w.p[0] = best_w.p[1] = best_w.p[2] = ch1; best_c.p[0] = best_c.p[1] = best_c.p[2] = ch1;
-	int ncand = 0;
+	int type = 0;
 	int64_t slot = -1;
-	if(ss >= tt) { type = 1; ncand = 1; }
-	else if(br.pier_of[c] >= 0) { type = 2; slot = clu_off[b] + br.pier_of[c]; ncand = br.p_nbr[slot]; }
-	for(int e = 0; e < ncand; e++)
+	if(ss >= tt) type = 1;
+	else if(br.pier_of[c] >= 0) { type = 2; slot = clu_off[b] + br.pier_of[c]; }
+	if(emit)
 	{
+		// the choice is known: rebuild its coordinates only
 		seq3 w, cc;
 		cc.n[0] = cc.n[1] = cc.n[2] = 0; cc.p[0] = cc.p[1] = cc.p[2] = ch1;
-		int s;
+		if(type == 1) merge_intron_chains(ch1, n1, ch2, n2, w);
+		else
+		{
+			int bi = br.br_order[slot * 2 * K + o.pick[c]];
+			int stride = br.p_bt[slot] - br.p_bs[slot] + 1;
+			const int32_t *bc = br.chains + 2 * br.p_path_off[slot] + (int64_t)bi * 2 * stride;
+			int bl = br.br_clen[slot * 2 * K + bi];
+			w.p[0] = ch1; w.n[0] = n1; w.p[1] = bc; w.n[1] = bl; w.p[2] = ch2; w.n[2] = n2;
+			cc.p[0] = bc; cc.n[0] = bl;
+		}
+		int nc = cc.size(), nw = w.size();
+		for(int k = 0; k < nc; k++) o.chain[o.coff[c] + k] = cc.at(k);
+		for(int k = 0; k < nw; k++) o.whole[o.woff[c] + k] = w.at(k);
+		return;
+	}
+	const int32_t bd0 = c_bounds[4 * c], bd3 = c_bounds[4 * c + 3];
+	if(type == 1 && n1 == 0 && n2 == 0)
+	{
+		// both mates unspliced inside overlapping vertices: `whole` is empty, only the fragment length decides
+		int32_t length = bd3 - bd0;
+		if(length < br.low || length > br.high) return;
+		o.type[c] = 1; o.strand[c] = 0; o.choices[c] = 1; o.score[c] = 10; o.pick[c] = 0;
+		return;
+	}
+	sgraph sg = sgraph_of(g, b_strand, b);
+	int be = -1, choices = 0, best_strand = 0, best_cn = 0, best_wn = 0;
+	double best_score = 0;
+	int ncand = 0;
+	if(type == 1) ncand = 1;
+	else if(type == 2) ncand = br.p_nbr[slot];
+	for(int e = 0; e < ncand; e++)
+	{
+		seq3 w;
+		int s, cn = 0;
 		double score;
 		if(type == 1)
 		{
@@ -654,7 +686,7 @@ KERNEL k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *c
 			if(!seq_increasing(w)) continue;
 			s = check_strand(sg, w);
 			if(s < 0) continue;
-			cc.p[0] = bc; cc.n[0] = bl;
+			cn = bl;
 			score = br.br_stack[(slot * 2 * K + bi) * br.D];
 		}
 		int wn = w.size();
@@ -665,21 +697,12 @@ KERNEL k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *c
 		int32_t length = bd3 - bd0 - intron;
 		if(length < br.low) continue;
 		if(length > br.high) continue;
-		if(be < 0) { be = e; best_w = w; best_c = cc; best_strand = s; best_score = score; }
+		if(be < 0) { be = e; best_cn = cn; best_wn = wn; best_strand = s; best_score = score; }
 		choices++;
 	}
 	if(be < 0) return;
-	if(!emit)
-	{
-		o.type[c] = type; o.strand[c] = best_strand; o.choices[c] = choices; o.score[c] = best_score;
-		o.clen[c] = best_c.size(); o.wlen[c] = best_w.size();
-	}
-	else
-	{
-		int nc = best_c.size(), nw = best_w.size();
-		for(int k = 0; k < nc; k++) o.chain[o.coff[c] + k] = best_c.at(k);
-		for(int k = 0; k < nw; k++) o.whole[o.woff[c] + k] = best_w.at(k);
-	}
+	o.type[c] = type; o.strand[c] = best_strand; o.choices[c] = choices; o.score[c] = best_score;
+	o.clen[c] = best_cn; o.wlen[c] = best_wn; o.pick[c] = be;
 }
 
 // ---- update_bridges (rnacore/bundle_base.cc:420-507) for every bridged cluster, as looped in meta/bundle.cc:73-79

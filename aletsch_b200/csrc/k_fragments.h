@@ -17,8 +17,9 @@ namespace agpu {
 #define QID_EMPTY 0xffffffffffffffffULL
 #define SCAN_TILE 2048
 
-KERNEL k_qid_insert(hits_dev h, const int32_t *hit_bundle, const int64_t *reg_off, u64 *slot_key, int32_t *slot_head, int32_t *slot_min,
-		int32_t *slot_n, int64_t *hit_qslot, int32_t *next, int *err)
+// qname table slot: two 64-bit words, [0] = qname key (QID_EMPTY when free), [1] low half = head of the member list
+// (bundle-local hit index, -1 when empty).  A memset with 0xff initialises both.
+KERNEL k_qid_insert(hits_dev h, const int32_t *hit_bundle, const int64_t *reg_off, u64 *slots, int64_t *hit_qslot, int32_t *next, int *err)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
@@ -31,42 +32,19 @@ KERNEL k_qid_insert(hits_dev h, const int32_t *hit_bundle, const int64_t *reg_of
 	int64_t sl = -1;
 	for(u32 probe = 0; probe <= mask; probe++)
 	{
-		u64 cur = atomicCAS(&slot_key[r0 + pos], (u64)QID_EMPTY, key);
+		u64 cur = atomicCAS(&slots[2 * (r0 + pos)], (u64)QID_EMPTY, key);
 		if(cur == QID_EMPTY || cur == key) { sl = r0 + pos; break; }
 		pos = (pos + 1) & mask;
 	}
 	hit_qslot[i] = sl;
 	if(sl < 0) { atomicAdd(&err[ERR_CAP], 1); return; }
 	int32_t li = (int32_t)(i - h.bundle_hit_off[b]);
-	next[i] = atomicExch(&slot_head[sl], li);
-	atomicMin(&slot_min[sl], li);
-	atomicAdd(&slot_n[sl], 1);
+	next[i] = atomicExch((int32_t*)&slots[2 * sl + 1], li);
 }
 
-// the first hit of every qname group runs the reference's greedy over the group
-KERNEL k_pair(hits_dev h, const int32_t *hit_bundle, const int64_t *hit_qslot, const int32_t *slot_head, const int32_t *slot_min,
-		const int32_t *slot_n, const int32_t *next, int32_t *cursor, int32_t *members, int32_t *mate)
+// the reference's greedy over one qname group whose members m[0..n) are in ascending hit index
+DEV void pair_group(const hits_dev &h, int64_t h0, const int32_t *m, int n, int32_t *mate)
 {
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= h.n_hits) return;
-	int64_t sl = hit_qslot[i];
-	if(sl < 0) return;
-	int b = hit_bundle[i];
-	int64_t h0 = h.bundle_hit_off[b];
-	if(slot_min[sl] != (int32_t)(i - h0)) return;
-	int n = slot_n[sl];
-	if(n < 2) return;
-	int32_t *m = members + h0 + atomicAdd(&cursor[b], n);
-	int k = 0;
-	for(int32_t x = slot_head[sl]; x >= 0 && k < n; x = next[h0 + x]) m[k++] = x;
-	// ascending hit index (insertion sort; groups are tiny)
-	for(int a = 1; a < n; a++)
-	{
-		int32_t v = m[a];
-		int c = a - 1;
-		while(c >= 0 && m[c] > v) { m[c + 1] = m[c]; c--; }
-		m[c + 1] = v;
-	}
 	for(int a = 0; a < n; a++)
 	{
 		int64_t ia = h0 + m[a];
@@ -83,6 +61,55 @@ KERNEL k_pair(hits_dev h, const int32_t *hit_bundle, const int64_t *hit_qslot, c
 			break;
 		}
 	}
+}
+
+// one thread per qname group (the hit at the head of the group's member list) runs the greedy; frgs order is by
+// discoverer index, so which member runs it does not matter
+#define PAIR_LOCAL 8
+KERNEL k_pair(hits_dev h, const int32_t *hit_bundle, const int64_t *hit_qslot, const u64 *slots, const int32_t *next,
+		int32_t *cursor, int32_t *members, int32_t *mate)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	int64_t sl = hit_qslot[i];
+	if(sl < 0) return;
+	int b = hit_bundle[i];
+	int64_t h0 = h.bundle_hit_off[b];
+	const int32_t li = (int32_t)(i - h0);
+	if((int32_t)(u32)(slots[2 * sl + 1] & 0xffffffffULL) != li) return;
+	int32_t x1 = next[i];
+	if(x1 < 0) return;                       // group of one
+	int32_t x2 = next[h0 + x1];
+	if(x2 < 0)
+	{
+		// the common case, a group of two: members (lo, hi) in index order
+		int32_t lo = li < x1 ? li : x1, hi = li < x1 ? x1 : li;
+		int64_t ia = h0 + lo, ic = h0 + hi;
+		int32_t sum = h.isize[ia] + h.isize[ic];
+		if(sum != 0) return;
+		if(h.pos[ic] == h.mpos[ia]) { mate[ia] = hi; mate[ic] = -2 - lo; }
+		else if(h.pos[ia] == h.mpos[ic]) { mate[ic] = lo; mate[ia] = -2 - hi; }
+		return;
+	}
+	int32_t loc[PAIR_LOCAL];
+	int n = 0;
+	for(int32_t x = li; x >= 0; x = next[h0 + x]) { if(n < PAIR_LOCAL) loc[n] = x; n++; }
+	int32_t *m = loc;
+	if(n > PAIR_LOCAL)
+	{
+		m = members + h0 + atomicAdd(&cursor[b], n);
+		int k = 0;
+		for(int32_t x = li; x >= 0 && k < n; x = next[h0 + x]) m[k++] = x;
+	}
+	// ascending hit index (insertion sort; groups are tiny)
+	for(int a = 1; a < n; a++)
+	{
+		int32_t v = m[a];
+		int c = a - 1;
+		while(c >= 0 && m[c] > v) { m[c + 1] = m[c]; c--; }
+		m[c + 1] = v;
+	}
+	pair_group(h, h0, m, n, mate);
 }
 
 // ---- generic device-wide exclusive scan of 0/1 flags derived from an int array (flag = v[i] >= 0)
@@ -151,8 +178,8 @@ KERNEL k_gather_i64(int64_t n, const int64_t *idx, const int64_t *src, int64_t *
 struct fragments_state
 {
 	bool built = false;
-	agpu::dbuf<agpu::u64> slot_key;
-	agpu::dbuf<int32_t> slot_head, slot_min, slot_n, next, cursor, members, mate, tile_cnt;
+	agpu::dbuf<agpu::u64> slots;
+	agpu::dbuf<int32_t> next, cursor, members, mate, tile_cnt;
 	agpu::dbuf<int64_t> hit_qslot, tile_off, rank, frg_off;
 	agpu::dbuf<int32_t> f_h1, f_h2, f_type, bridged;
 	int64_t n_frg = 0;
@@ -160,7 +187,7 @@ struct fragments_state
 
 	void release(agpu_ctx *ctx)
 	{
-		slot_key.release(ctx); slot_head.release(ctx); slot_min.release(ctx); slot_n.release(ctx); next.release(ctx);
+		slots.release(ctx); next.release(ctx);
 		cursor.release(ctx); members.release(ctx); mate.release(ctx); tile_cnt.release(ctx);
 		hit_qslot.release(ctx); tile_off.release(ctx); rank.release(ctx); frg_off.release(ctx);
 		f_h1.release(ctx); f_h2.release(ctx); f_type.release(ctx); bridged.release(ctx);
