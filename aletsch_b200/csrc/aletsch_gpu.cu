@@ -113,7 +113,7 @@ struct agpu_batch
 	dbuf<int64_t> in_hit_off;
 	dbuf<int32_t> in_pos, in_rpos, in_mpos, in_isize;
 	dbuf<uint16_t> in_flag;
-	dbuf<uint8_t> in_strand, in_xs;
+	dbuf<uint8_t> in_strand, in_xs, in_bstrand;
 	dbuf<u64> in_qid;
 	dbuf<u32> in_cigar_off, in_cigar;
 	std::vector<int64_t> hit_off_host;
@@ -121,6 +121,9 @@ struct agpu_batch
 	// bundles by descending hit count: [0, n_large) get wide CTAs, the rest one warp each
 	dbuf<int32_t> order;
 	int32_t n_large = 0;
+	// regions of the per-bundle qname tables (mate pairing): a power of two >= 1.5 x the bundle's hits
+	dbuf<int64_t> qreg_off;
+	int64_t q_slots = 0;
 
 	dbuf<int> err;
 
@@ -229,6 +232,13 @@ int agpu_create(int device, void *stream, agpu_ctx **out)
 		if(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return AGPU_ERR_CUDA; }
 		ctx->own_stream = true;
 	}
+	{
+		cudaEvent_t e1, e2;
+		if(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess ||
+				cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess)
+		{ delete ctx; return AGPU_ERR_CUDA; }
+		ctx->ev_fork = e1; ctx->ev_join = e2;
+	}
 	// keep freed blocks in the pool: the stages allocate and free stream-ordered scratch all the time
 	cudaMemPool_t pool;
 	if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
@@ -246,6 +256,9 @@ void agpu_destroy(agpu_ctx *ctx)
 	if(!ctx) return;
 #ifndef AGPU_EMU
 	cudaStreamSynchronize(ctx->stream);
+	if(ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+	if(ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
+	if(ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
 	if(ctx->own_stream) cudaStreamDestroy(ctx->stream);
 #endif
 	delete ctx;
@@ -294,14 +307,28 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	while(b->n_large < b->nb && ho[ord[b->n_large] + 1] - ho[ord[b->n_large]] >= LARGE_BUNDLE_HITS) b->n_large++;
 	TRY(b->order.alloc(ctx, b->nb + 1));
 	TRY(h2d(ctx, b->order.p, ord.data(), sizeof(int32_t) * b->nb));
+	std::vector<int64_t> qreg(b->nb + 1);
+	qreg[0] = 0;
+	for(int k = 0; k < b->nb; k++)
+	{
+		int64_t ne = ho[k + 1] - ho[k];
+		qreg[k + 1] = qreg[k] + (int64_t)pow2_ceil((u32)std::max<int64_t>(ne + ne / 2, 2));
+	}
+	b->q_slots = qreg[b->nb];
+	TRY(b->qreg_off.alloc(ctx, b->nb + 2));
+	TRY(h2d(ctx, b->qreg_off.p, qreg.data(), sizeof(int64_t) * (b->nb + 1)));
 	TRY(stream_sync(ctx));
 	return AGPU_OK;
 }
 
-// per-bundle block-cooperative kernel over the size-binned bundle order: wide CTAs for the large bundles, one warp for the rest
+// per-bundle block-cooperative kernel over the size-binned bundle order: wide CTAs for the large bundles (few, long: on the
+// side stream, next to the bulk launch), one warp for the rest
 #define LAUNCH_BINNED(ctx, b, kern, ...) do { \
-	if((b)->n_large > 0) LAUNCH_B(ctx, kern, (b)->n_large, 256, (b)->order.p, (b)->n_large, __VA_ARGS__); \
-	if((b)->nb > (b)->n_large) LAUNCH_B(ctx, kern, (b)->nb - (b)->n_large, 32, (b)->order.p + (b)->n_large, (b)->nb - (b)->n_large, __VA_ARGS__); } while(0)
+	bool both_ = (b)->n_large > 0 && (b)->nb > (b)->n_large; \
+	if(both_) { side_fork(ctx); LAUNCH_B_SIDE(ctx, kern, (b)->n_large, 256, (b)->order.p, (b)->n_large, __VA_ARGS__); } \
+	else if((b)->n_large > 0) LAUNCH_B(ctx, kern, (b)->n_large, 256, (b)->order.p, (b)->n_large, __VA_ARGS__); \
+	if((b)->nb > (b)->n_large) LAUNCH_B(ctx, kern, (b)->nb - (b)->n_large, 32, (b)->order.p + (b)->n_large, (b)->nb - (b)->n_large, __VA_ARGS__); \
+	if(both_) side_join(ctx); } while(0)
 
 
 int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
@@ -318,8 +345,13 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	int rc = AGPU_OK;
 #define UP(buf, src, count) do { if(rc == AGPU_OK) rc = b->buf.alloc(ctx, (size_t)(count) + 1); if(rc == AGPU_OK) rc = h2d(ctx, b->buf.p, src, sizeof(*(src)) * (size_t)(count)); } while(0)
 	UP(in_hit_off, in->bundle_hit_off, b->nb + 1);
-	UP(in_pos, in->pos, b->nh); UP(in_rpos, in->rpos, b->nh); UP(in_mpos, in->mpos, b->nh); UP(in_isize, in->isize, b->nh);
-	UP(in_flag, in->flag, b->nh); UP(in_strand, in->strand, b->nh); UP(in_xs, in->xs, b->nh); UP(in_qid, in->qid, b->nh);
+	UP(in_pos, in->pos, b->nh); UP(in_mpos, in->mpos, b->nh); UP(in_isize, in->isize, b->nh);
+	UP(in_xs, in->xs, b->nh); UP(in_qid, in->qid, b->nh);
+	// flag[] is not read by any kernel and stays on the host; rpos[] and strand[] are optional (see agpu_batch_in)
+	if(in->rpos) UP(in_rpos, in->rpos, b->nh);
+	if(in->strand) UP(in_strand, in->strand, b->nh);
+	else if(in->bundle_strand) UP(in_bstrand, in->bundle_strand, b->nb);
+	else rc = rc == AGPU_OK ? AGPU_ERR_ARG : rc;
 	UP(in_cigar_off, in->cigar_off, b->nh + 1); UP(in_cigar, in->cigar, b->nc);
 #undef UP
 	if(rc == AGPU_OK) rc = batch_common(ctx, b);
@@ -327,8 +359,15 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.n_hits = b->nh; b->h.n_bundles = b->nb;
 	b->h.bundle_hit_off = b->in_hit_off.p;
 	b->h.pos = b->in_pos.p; b->h.rpos = b->in_rpos.p; b->h.mpos = b->in_mpos.p; b->h.isize = b->in_isize.p;
-	b->h.flag = b->in_flag.p; b->h.strand = b->in_strand.p; b->h.xs = b->in_xs.p; b->h.qid = (const u64*)b->in_qid.p;
+	b->h.flag = NULL; b->h.strand = b->in_strand.p; b->h.bundle_strand = b->in_bstrand.p; b->h.xs = b->in_xs.p; b->h.qid = (const u64*)b->in_qid.p;
 	b->h.cigar_off = b->in_cigar_off.p; b->h.cigar = b->in_cigar.p;
+	if(!in->rpos)
+	{
+		// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), derived on the device
+		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
+		b->h.rpos = b->in_rpos.p;
+		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
+	}
 	*out = b;
 	return AGPU_OK;
 }
@@ -351,8 +390,15 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.n_hits = b->nh; b->h.n_bundles = b->nb;
 	b->h.bundle_hit_off = in->bundle_hit_off;
 	b->h.pos = in->pos; b->h.rpos = in->rpos; b->h.mpos = in->mpos; b->h.isize = in->isize;
-	b->h.flag = in->flag; b->h.strand = in->strand; b->h.xs = in->xs; b->h.qid = (const u64*)in->qid;
+	b->h.flag = in->flag; b->h.strand = in->strand; b->h.bundle_strand = in->bundle_strand; b->h.xs = in->xs; b->h.qid = (const u64*)in->qid;
 	b->h.cigar_off = in->cigar_off; b->h.cigar = in->cigar;
+	if(!in->strand && !in->bundle_strand) { agpu_batch_free(ctx, b); return AGPU_ERR_ARG; }
+	if(!in->rpos)
+	{
+		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
+		b->h.rpos = b->in_rpos.p;
+		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
+	}
 	*out = b;
 	return AGPU_OK;
 }
@@ -376,9 +422,9 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 	if(!ctx || !b) return;
 	release_derived(ctx, b);
 	b->in_hit_off.release(ctx); b->in_pos.release(ctx); b->in_rpos.release(ctx); b->in_mpos.release(ctx); b->in_isize.release(ctx);
-	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
+	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_bstrand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
 	b->in_cigar_off.release(ctx); b->in_cigar.release(ctx);
-	b->err.release(ctx); b->order.release(ctx);
+	b->err.release(ctx); b->order.release(ctx); b->qreg_off.release(ctx);
 	stream_sync(ctx);
 	for(auto &r : b->pinned) r.second.release();
 	delete b;
@@ -393,23 +439,38 @@ int agpu_batch_reset(agpu_ctx *ctx, agpu_batch *b)
 }
 
 // ---- chain set construction shared by hcst (elements = hits) and fcst (elements = fragments)
+// Table regions: a power of two >= 2 x the elements that will be inserted.  `d_count` (device, per bundle) gives that number
+// when only some elements carry a chain (hcst: the spliced hits); otherwise every element of the bundle counts.
 static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int64_t n_elem, const int64_t *d_elem_off,
-		const std::vector<int64_t> &elem_off_host)
+		const std::vector<int64_t> &elem_off_host, const int32_t *d_count = NULL)
 {
 	int nb = b->nb;
 	cs.n_elem = n_elem;
 	cs.d_elem_off = d_elem_off;
-	std::vector<int64_t> reg(nb + 1);
-	reg[0] = 0;
-	for(int k = 0; k < nb; k++)
+	TRY(cs.reg_off.alloc(ctx, nb + 2));
+	if(d_count)
 	{
-		int64_t ne = elem_off_host[k + 1] - elem_off_host[k];
-		reg[k + 1] = reg[k] + (int64_t)pow2_ceil((u32)std::max<int64_t>(2 * ne, 2));
+		dbuf<int64_t> sz;
+		TRY(sz.alloc(ctx, nb + 1));
+		LAUNCH_T(ctx, k_table_sizes, nb, nb, d_count, sz.p);
+		LAUNCH_B(ctx, k_scan_i64, 1, 1024, sz.p, cs.reg_off.p, nb);
+		TRY(d2h(ctx, &cs.n_slots, cs.reg_off.p + nb, sizeof(int64_t)));
+		TRY(stream_sync(ctx));
+		sz.release(ctx);
 	}
-	cs.n_slots = reg[nb];
-	TRY(cs.reg_off.alloc(ctx, nb + 1));
-	TRY(h2d(ctx, cs.reg_off.p, reg.data(), sizeof(int64_t) * (nb + 1)));
-	TRY(stream_sync(ctx));                 // `reg` is pageable stack-owned memory
+	else
+	{
+		std::vector<int64_t> reg(nb + 1);
+		reg[0] = 0;
+		for(int k = 0; k < nb; k++)
+		{
+			int64_t ne = elem_off_host[k + 1] - elem_off_host[k];
+			reg[k + 1] = reg[k] + (int64_t)pow2_ceil((u32)std::max<int64_t>(2 * ne, 2));
+		}
+		cs.n_slots = reg[nb];
+		TRY(h2d(ctx, cs.reg_off.p, reg.data(), sizeof(int64_t) * (nb + 1)));
+		TRY(stream_sync(ctx));                 // `reg` is pageable stack-owned memory
+	}
 	TRY(cs.slot_word.alloc(ctx, cs.n_slots, true));
 	TRY(cs.slot_first.alloc(ctx, cs.n_slots)); TRY(cs.slot_first.fill(ctx, 0x7f));
 	TRY(cs.slot_cnt.alloc(ctx, cs.n_slots * 3, true));
@@ -510,12 +571,15 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	if(b->ltot >= ((int64_t)1 << 32) - 64) { ctx->last_error = "batch spans 2^32 or more window positions: split it"; return AGPU_ERR_CAPACITY; }
 	TRY(b->border.alloc(ctx, b->ltot / 32 + 8, true));
 	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1)); TRY(b->hit_bundle.alloc(ctx, nh + 1)); TRY(b->hit_hash.alloc(ctx, nh + 1));
+	dbuf<int32_t> n_spliced;
+	TRY(n_spliced.alloc(ctx, nb + 1, true));
 	LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_hash.p,
-			b->hit_bundle.p, b->err.p);
+			b->hit_bundle.p, n_spliced.p, b->err.p);
 	// hcst
 	chainset_state &cs = b->hcst;
 	cs.val = b->spl.p; cs.voff32 = b->h.cigar_off; cs.voff64 = NULL; cs.elem_len = b->hit_nspl.p;
-	TRY(chainset_build(ctx, b, cs, nh, b->h.bundle_hit_off, b->hit_off_host));
+	TRY(chainset_build(ctx, b, cs, nh, b->h.bundle_hit_off, b->hit_off_host, n_spliced.p));
+	n_spliced.release(ctx);
 	LAUNCH_T(ctx, k_hcst_insert, nh, b->h, b->hit_nspl.p, b->hit_hash.p, b->hit_bundle.p, b->spl.p, cs.reg_off.p, cs.slot_word.p,
 			cs.slot_first.p, cs.slot_cnt.p, cs.elem_slot.p, b->err.p);
 	TRY(cs.val_base.alloc(ctx, nb + 1));

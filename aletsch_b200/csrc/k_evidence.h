@@ -30,7 +30,8 @@ struct hits_dev
 	const int64_t *bundle_hit_off;
 	const int32_t *pos, *rpos, *mpos, *isize;
 	const uint16_t *flag;
-	const uint8_t *strand, *xs;
+	const uint8_t *strand, *xs;      // strand may be NULL: then bundle_strand[b] holds the strand all hits of bundle b share
+	const uint8_t *bundle_strand;
 	const u64 *qid;
 	const u32 *cigar_off;
 	const u32 *cigar;
@@ -64,7 +65,7 @@ KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b
 			{
 				if(h.pos[i - 1] > p) atomicAdd(&err[ERR_ORDER], 1);
 				if(h.pos[i - 1] == p && h.rpos[i - 1] == r) atomicAdd(&err[ERR_DUP], 1);
-				if(h.strand[i] != h.strand[h0]) atomicAdd(&err[ERR_STRAND], 1);
+				if(h.strand && h.strand[i] != h.strand[h0]) atomicAdd(&err[ERR_STRAND], 1);
 			}
 		}
 		atomicMin(&s_min, lmin); atomicMax(&s_max, lmax); atomicMax(&s_cov, lcov);
@@ -76,7 +77,7 @@ KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b
 			b_rpos[b] = s_max;
 			b_covhi[b] = s_cov;
 			uint8_t st = '.';
-			if(h1 > h0) st = h.strand[h0];                 // rnacore/bundle_base.cc:100
+			if(h1 > h0) st = h.strand ? h.strand[h0] : h.bundle_strand[b];      // rnacore/bundle_base.cc:100
 			if(library_type == 0)                          // bundle_base::compute_strand, rnacore/bundle_base.cc:205-225
 			{
 				if(s_np > s_nq) st = '+';
@@ -191,7 +192,7 @@ HD u64 chain_hash(const int32_t *v, int n)
 //             k_cov_add once the borders have been ranked, see the coverage section below)
 //   splices : (p - len, p) for every inner BAM_CREF_SKIP, written at spl[cigar_off[i] ...]
 KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
-		int32_t *spl, int32_t *hit_nspl, u64 *hit_hash, int32_t *hit_bundle, int *err)
+		int32_t *spl, int32_t *hit_nspl, u64 *hit_hash, int32_t *hit_bundle, int32_t *n_spliced, int *err)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
@@ -225,6 +226,38 @@ KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u
 	if(p != h.rpos[i]) atomicAdd(&err[ERR_RPOS], 1);
 	hit_nspl[i] = ns;
 	hit_hash[i] = ns > 0 ? chain_hash(out, ns) : 0;
+#ifndef AGPU_EMU
+	// hits of a bundle are neighbours: one atomic per (warp, bundle) instead of one per spliced hit
+	const unsigned act = __activemask();
+	const unsigned peers = __match_any_sync(act, ns > 0 ? b : -1);
+	if(ns > 0 && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&n_spliced[b], __popc(peers));
+#else
+	if(ns > 0) atomicAdd(&n_spliced[b], 1);
+#endif
+}
+
+// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64) when the host did not send it
+KERNEL k_hit_rpos(hits_dev h, int32_t *rpos)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
+	int32_t p = h.pos[i];
+	for(u32 k = c0; k < c1; k++)
+	{
+		u32 c = h.cigar[k];
+		if((0x3C1A7 >> ((c & 0xf) << 1)) & 2) p += (int32_t)(c >> 4);
+	}
+	rpos[i] = p;
+}
+
+// chain table region of a bundle: a power of two >= 2 x the elements that carry a chain
+KERNEL k_table_sizes(int64_t nb, const int32_t *count, int64_t *size)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= nb) return;
+	int c = 2 * count[i];
+	size[i] = (int64_t)pow2_ceil((u32)(c < 2 ? 2 : c));
 }
 
 // ---- chain table: one open-addressing region per bundle; slot word = hash32 << 32 | (rep + 1)
@@ -396,6 +429,14 @@ KERNEL k_chain_splices(const int32_t *order, int32_t n_bundles, const int64_t *e
 		if(threadIdx.x == 0) n_splices[b] = tot;
 		BLOCK_SYNC();
 	}
+}
+
+// splice lists of all bundles back to back
+KERNEL k_splices_compact(int32_t n_bundles, const int64_t *val_base, const int32_t *n_splices, const int32_t *scratch, const int64_t *out_off,
+		int32_t *out)
+{
+	for(int b = blockIdx.x; b < n_bundles; b += gridDim.x)
+		for(int i = threadIdx.x; i < n_splices[b]; i += blockDim.x) out[out_off[b] + i] = scratch[val_base[b] + i];
 }
 
 // per element: handle -> bundle-local chain index

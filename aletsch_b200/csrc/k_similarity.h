@@ -86,6 +86,65 @@ KERNEL k_sim_tiles(int32_t n_lists, int words, const u64 *bits, int32_t *out_c)
 	}
 }
 
+// ---- many small bundle groups at once: one CTA per group does dictionary, bitsets and all pairs
+struct sim_batch
+{
+	int32_t n_groups;
+	const int32_t *group_off;     // [n_groups + 1] lists of group g
+	const int64_t *list_off;      // [n_lists + 1]
+	const int32_t *val;
+	const int64_t *bits_off;      // [n_groups] u64 words of scratch: G x words_ub, zeroed
+	const int64_t *c_off;         // [n_groups] start of the group's dense G x G matrix in out_c
+	const uint8_t *skip;          // [n_groups] 1: group is handled by the tiled kernels
+	u64 *key;                     // [n_values] scratch
+	int32_t *flag, *dict;         // [n_values] scratch
+	u64 *bits;
+	int32_t *out_c;
+};
+
+KERNEL k_sim_groups(sim_batch a)
+{
+	for(int g = blockIdx.x; g < a.n_groups; g += gridDim.x)
+	{
+		if(a.skip[g]) continue;
+		const int l0 = a.group_off[g], G = a.group_off[g + 1] - l0;
+		const int64_t v0 = a.list_off[l0];
+		const int n = (int)(a.list_off[l0 + G] - v0);
+		if(G < 2 || n <= 0) continue;
+		u64 *key = a.key + v0;
+		int32_t *flag = a.flag + v0, *dict = a.dict + v0;
+		for(int i = threadIdx.x; i < n; i += blockDim.x) key[i] = (u64)(u32)a.val[v0 + i];
+		BLOCK_SYNC();
+		block_sort_u64(key, n);
+		for(int i = threadIdx.x; i < n; i += blockDim.x) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+		BLOCK_SYNC();
+		const int nd = block_excl_scan(flag, n);
+		for(int i = threadIdx.x; i < n; i += blockDim.x) if(i == 0 || key[i] != key[i - 1]) dict[flag[i]] = (int32_t)(u32)key[i];
+		BLOCK_SYNC();
+		const int words = (n + 63) / 64;                      // row stride (upper bound of the dictionary size)
+		const int used = (nd + 63) / 64;
+		u64 *bits = a.bits + a.bits_off[g];
+		for(int i = threadIdx.x; i < n; i += blockDim.x)
+		{
+			int li = find_segment(a.list_off + l0, G, v0 + i);
+			int k = lower_bound_idx(dict, nd, a.val[v0 + i]);
+			atomicOr(&bits[(int64_t)li * words + (k >> 6)], (u64)1 << (k & 63));
+		}
+		BLOCK_SYNC();
+		int32_t *out = a.out_c + a.c_off[g];
+		for(int p = threadIdx.x; p < G * G; p += blockDim.x)
+		{
+			int i = p / G, j = p % G;
+			if(i >= j) continue;
+			const u64 *x = bits + (int64_t)i * words, *y = bits + (int64_t)j * words;
+			int s = 0;
+			for(int w = 0; w < used; w++) s += __popcll(x[w] & y[w]);
+			out[p] = s;
+		}
+		BLOCK_SYNC();
+	}
+}
+
 } // namespace agpu
 
 #endif

@@ -19,6 +19,9 @@ struct agpu_ctx
 	int64_t launches;
 	std::string last_error;
 	int sm_count;
+	// side stream: runs the few-but-long launches of a size-binned kernel pair next to the bulk launch on `stream`
+	cudaStream_t side = NULL;
+	void *ev_fork = NULL, *ev_join = NULL;
 	// optional per-kernel timing (CUDA events around every launch on the ctx stream)
 	bool profiling = false;
 	std::vector<agpu_prof_rec> prof;
@@ -31,9 +34,10 @@ namespace agpu {
 #ifndef AGPU_EMU
 #define CUDA_TRY(ctx, call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_); return AGPU_ERR_CUDA; } } while(0)
 
-inline void prof_begin(agpu_ctx *ctx, const char *name)
+inline void prof_begin(agpu_ctx *ctx, const char *name, cudaStream_t st = NULL)
 {
 	if(!ctx->profiling) return;
+	if(st == NULL) st = ctx->stream;
 	agpu_prof_rec r;
 	r.name = name;
 	cudaEvent_t e[2];
@@ -43,14 +47,20 @@ inline void prof_begin(agpu_ctx *ctx, const char *name)
 		else cudaEventCreate(&e[k]);
 	}
 	r.e0 = e[0]; r.e1 = e[1];
-	cudaEventRecord(e[0], ctx->stream);
+	cudaEventRecord(e[0], st);
 	ctx->prof.push_back(r);
 }
-inline void prof_end(agpu_ctx *ctx)
+inline void prof_end(agpu_ctx *ctx, cudaStream_t st = NULL)
 {
 	if(!ctx->profiling) return;
-	cudaEventRecord((cudaEvent_t)ctx->prof.back().e1, ctx->stream);
+	cudaEventRecord((cudaEvent_t)ctx->prof.back().e1, st ? st : ctx->stream);
 }
+// side stream joins in after everything queued on the main stream so far / main stream waits for the side stream
+inline void side_fork(agpu_ctx *ctx) { cudaEventRecord((cudaEvent_t)ctx->ev_fork, ctx->stream); cudaStreamWaitEvent(ctx->side, (cudaEvent_t)ctx->ev_fork, 0); }
+inline void side_join(agpu_ctx *ctx) { cudaEventRecord((cudaEvent_t)ctx->ev_join, ctx->side); cudaStreamWaitEvent(ctx->stream, (cudaEvent_t)ctx->ev_join, 0); }
+// block-cooperative kernel on the side stream (between side_fork and side_join)
+#define LAUNCH_B_SIDE(ctx, kern, nblocks, nthreads, ...) do { int64_t n_ = (int64_t)(nblocks); if(n_ > 0) { unsigned g_ = (unsigned)(n_ > 1048576 ? 1048576 : n_); \
+	prof_begin(ctx, #kern "(side)", (ctx)->side); kern<<<g_, (nthreads), 0, (ctx)->side>>>(__VA_ARGS__); prof_end(ctx, (ctx)->side); (ctx)->launches++; } } while(0)
 // fold finished records into the per-kernel accumulators (call after a stream synchronisation)
 inline void prof_collect(agpu_ctx *ctx)
 {
@@ -117,7 +127,10 @@ template<typename F, typename... A> inline void emu_launch(bool coop, F f, int64
 		}
 	}
 }
+inline void side_fork(agpu_ctx *) {}
+inline void side_join(agpu_ctx *) {}
 #define LAUNCH_T(ctx, kern, n, ...) do { int64_t n_ = (int64_t)(n); if(n_ > 0) { emu_launch(false, kern, (n_ + 255) / 256, 256, __VA_ARGS__); (ctx)->launches++; } } while(0)
+#define LAUNCH_B_SIDE(ctx, kern, nblocks, nthreads, ...) LAUNCH_B(ctx, kern, nblocks, nthreads, __VA_ARGS__)
 #define LAUNCH_B(ctx, kern, nblocks, nthreads, ...) do { int64_t n_ = (int64_t)(nblocks); if(n_ > 0) { emu_launch(true, kern, n_, (nthreads), __VA_ARGS__); (ctx)->launches++; } } while(0)
 inline int dev_alloc_bytes(agpu_ctx *, void **p, size_t bytes, bool zero) { if(bytes == 0) bytes = 16; *p = zero ? calloc(1, bytes) : malloc(bytes); return *p ? AGPU_OK : AGPU_ERR_OOM; }
 inline void dev_free_bytes(agpu_ctx *, void *p) { free(p); }

@@ -62,7 +62,8 @@ class BridgeView(C.Structure):
 
 class Counts(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("hits", "cigar_ops", "span", "segments", "chains", "splice_ints", "junctions", "vertices",
-                                         "edges", "fragments", "clusters", "bridged", "piers")]
+                                         "edges", "fragments", "clusters", "bridged", "piers", "borders", "cluster_members",
+                                         "bridge_chain_ints", "bridge_whole_ints")]
 
 
 ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_sync", "agpu_launch_count",
@@ -70,7 +71,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_fragments", "agpu_batch_graph", "agpu_batch_cluster", "agpu_batch_bridge", "agpu_batch_update",
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
-               "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm"]
+               "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch"]
 
 
 def load(lib_path=None):
@@ -100,9 +101,12 @@ def load(lib_path=None):
     L.agpu_cluster_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ClusterView)]
     L.agpu_bridge_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BridgeView)]
     L.agpu_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Counts)]
+    L.agpu_splices_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P64), C.POINTER(P32)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.agpu_group_resolve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
     L.agpu_debug_sort_perm.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    L.agpu_similarity_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.agpu_group_resolve_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
     L.agpu_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.agpu_profile_reset.argtypes = [C.c_void_p]
     L.agpu_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
@@ -228,6 +232,27 @@ def group_resolve(ctx, lists, params):
     return out
 
 
+def group_resolve_batch(ctx, groups, params):
+    """bundle_group::resolve for many bundle groups in one call.  groups: list of lists of sorted splice lists.
+    Returns, per bundle group, its clusters (lists of list indices local to the group) in gvv order."""
+    flat = [l for grp in groups for l in grp]
+    off, val = _pack_lists(flat)
+    goff = np.zeros(len(groups) + 1, np.int32)
+    for i, grp in enumerate(groups):
+        goff[i + 1] = goff[i] + len(grp)
+    out = np.zeros(max(len(flat), 1), np.int32)
+    ng = np.zeros(max(len(groups), 1), np.int32)
+    ctx.check(ctx.L.agpu_group_resolve_batch(ctx.h, len(groups), goff.ctypes.data, off.ctypes.data, val.ctypes.data, C.byref(params),
+                                             out.ctypes.data, ng.ctypes.data), "agpu_group_resolve_batch")
+    res = []
+    for i, grp in enumerate(groups):
+        cl = [[] for _ in range(ng[i])]
+        for k in range(len(grp)):
+            cl[out[goff[i] + k]].append(k)
+        res.append(cl)
+    return res
+
+
 class Batch:
     """agpu_batch: device-resident state of a batch of bundles."""
 
@@ -321,6 +346,13 @@ class Batch:
             d.update(cs[k])
             out.append(d)
         return out
+
+    def fetch_splices(self):
+        """(splice_off[NB+1], splices) as numpy arrays: bundle::splices of every bundle"""
+        po, pv = P64(), P32()
+        self.ctx.check(self.ctx.L.agpu_splices_fetch(self.ctx.h, self.h, C.byref(po), C.byref(pv)), "agpu_splices_fetch")
+        off = _arr(po, self.nb + 1, np.int64)
+        return off, _arr(pv, int(off[self.nb]) if self.nb else 0)
 
     def fetch_graph(self):
         v = GraphView()

@@ -188,6 +188,7 @@ int packer_view(void *pkp, agpu_batch_in *out)
 	out->pos = pk.pos.data(); out->rpos = pk.rpos.data(); out->mpos = pk.mpos.data(); out->isize = pk.isize.data();
 	out->flag = pk.flag.data(); out->strand = pk.strand.data(); out->xs = pk.xs.data(); out->qid = pk.qid.data();
 	out->cigar_off = pk.cigar_off.data(); out->cigar = pk.cigar.data();
+	out->bundle_strand = NULL;
 	return 0;
 }
 

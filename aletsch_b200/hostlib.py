@@ -43,7 +43,7 @@ class BatchIn(C.Structure):
                 ("bundle_hit_off", C.c_void_p), ("bundle_tid", C.c_void_p), ("bundle_sample", C.c_void_p),
                 ("pos", C.c_void_p), ("rpos", C.c_void_p), ("mpos", C.c_void_p), ("isize", C.c_void_p),
                 ("flag", C.c_void_p), ("strand", C.c_void_p), ("xs", C.c_void_p), ("qid", C.c_void_p),
-                ("cigar_off", C.c_void_p), ("cigar", C.c_void_p)]
+                ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("bundle_strand", C.c_void_p)]
 
 
 HIT_FIELDS = [("pos", np.int32), ("rpos", np.int32), ("mpos", np.int32), ("isize", np.int32), ("flag", np.uint16),

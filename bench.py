@@ -122,25 +122,40 @@ class ClockSampler:
 
 
 def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
-    """bytes a kernel has to read + write once per launch (DESIGN.md, section 'kernels'), from the real counts"""
-    Hh, S, L, F = cnt["hits"], cnt["segments"], cnt["span"], cnt["fragments"]
+    """bytes a kernel has to read + write once per STEP (all its launches of a step together),
+    from the real counts of the batch"""
+    Hh, S, F, C = cnt["hits"], cnt["segments"], cnt["fragments"], cnt["clusters"]
+    J, V, E, NBD, M = cnt["junctions"], cnt["vertices"], cnt["edges"], cnt["borders"], cnt["cluster_members"]
+    kernel = kernel.replace("(side)", "")
     if kernel == "k_hit_cigar":
         # in: pos, rpos, cigar_off (12 B/hit) + CIGAR ops; out: nspl, hash, bundle id (16 B/hit) + splice coordinates
-        # + one 4-byte difference word and one 4-byte bitmap word per block end
+        # + one read-modify-write of a 4-byte bitmap word per block end
         return Hh * (12 + 16) + 4 * n_cigar + 8 * n_splice_pairs + 16 * n_mblocks
-    if kernel == "k_cov_scan":
-        # single pass: difference array + border bitmap read once, segments written once (12 B each)
-        return 4 * L + L // 8 + 12 * S
-    if kernel == "k_cov_tile_sum":
-        return 4 * L
+    if kernel == "k_cov_add":
+        # in: pos, cigar_off, bundle id (12 B/hit) + CIGAR ops; per block end a bitmap word, a rank word and a 4-byte RMW
+        return Hh * 12 + 4 * n_cigar + 2 * n_mblocks * (4 + 4 + 8)
+    if kernel == "k_covc_emit":
+        return NBD * 8 + 12 * S
     if kernel == "k_qid_insert":
         return Hh * (8 + 4 + 8 + 4) + Hh * 16       # qid, bundle id in; slot index, next out; one 16-byte slot touch
     if kernel == "k_pair":
-        return Hh * (8 + 4 + 4 + 4 + 4 + 4)         # slot, next, pos, mpos, isize in; mate out
+        return Hh * (8 + 4 + 16 + 4) + F * (2 * 12 + 8)   # slot index, bundle id, slot, next per hit; pos/mpos/isize of both mates, mate out
     if kernel == "k_hcst_insert":
         return Hh * (4 + 8 + 4 + 1 + 8) + 8 * n_splice_pairs
     if kernel == "k_frag_align":
         return F * (12 + 2 * (4 + 4 + 4) + 16 + 8 + 4)
+    if kernel == "k_graph_build":
+        # in: segments (12 B) and chain coordinates / counts; out: junctions (9 ints), partial exons (6 ints + 3 doubles),
+        # vertices (6 ints + 3 doubles), edges (3 ints + 1 double), both adjacency tables
+        return 12 * S + 4 * cnt["splice_ints"] + 12 * cnt["chains"] + 36 * J + 48 * (V - 2 * cnt.get("bundles", 0)) + 48 * V + 20 * E + 16 * E + 8 * V
+    if kernel == "k_vote":
+        # both passes: per cluster vp1, vp2, bundle, two chain ids, two bounds, pier (32 B) in, 8 result words (36 B) out, the pick
+        # and two offsets (20 B) back in; the coordinates of the chosen chain / whole read and written once
+        return C * (32 + 36 + 20) + 8 * cnt["bridge_whole_ints"] + 8 * cnt["bridge_chain_ints"]
+    if kernel in ("k_group_partition", "k_group_partition_warp"):
+        return M * (8 + 16 + 8)                     # h1 / h2, four keys, member + cluster flag out
+    if kernel == "k_update":
+        return 2 * (C * 24 + M * (4 + 8 + 8 + 2)) + M * 4 + cnt["bridged"] * 20
     return None
 
 
@@ -199,8 +214,6 @@ def run_ours(args):
         bt.bridge_all(gp)
     ctx.sync()
     counts = bt.counts()
-    ctx.profile(True)
-    ctx.profile_reset()
     launches0 = ctx.launches
     clocks = ClockSampler(local)
     barrier()
@@ -213,11 +226,24 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1)
-    clk = clocks.stop()
     launches = ctx.launches - launches0
+    # the same K steps again with CUDA events around every kernel launch (per-kernel durations for the roofline; the
+    # event records cost ~2% so they stay out of the region `value` is taken from)
+    ctx.profile(True)
+    ctx.profile_reset()
+    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ep0.record(stream)
+    for _ in range(args.steps):
+        bt.reset()
+        bt.bridge_all(gp)
+    ep1.record(stream)
+    barrier()
+    ms_prof = ep0.elapsed_time(ep1)
+    clk = clocks.stop()
     prof = ctx.profile_read()
     ctx.profile(False)
     counts = bt.counts()
+    stage5 = stage5_gpu(ctx, bt, batch, args) if not args.no_stage5 else None
     bt.free()
 
     # ---- end to end: pinned host buffers -> upload -> bridge_all -> counters back to the host ----------
@@ -232,14 +258,18 @@ def run_ours(args):
     h2d_bytes = 0
     for ch in chunks:
         pin = {}
-        for f in fields:
+        # lean upload: flag[] is never read on the device, rpos[] is re-derived from the CIGAR there, and the strand that all
+        # hits of a bundle share goes up once per bundle (agpu_batch_in: rpos / flag / strand may be NULL)
+        ch.a["bundle_strand"] = np.ascontiguousarray(ch.a["strand"][np.minimum(ch.a["bundle_hit_off"][:-1], max(ch.n_hits - 1, 0))])
+        lean = [f for f in fields if f not in ("rpos", "flag", "strand")] + ["bundle_strand"]
+        for f in lean:
             a = ch.a[f]
             v = a.view(np.int64) if a.dtype == np.uint64 else (a.view(np.int32) if a.dtype == np.uint32 else (a.view(np.int16) if a.dtype == np.uint16 else a))
             pin[f] = torch.from_numpy(v).pin_memory()
             h2d_bytes += pin[f].numel() * pin[f].element_size()
         b = H.BatchIn()
         b.n_bundles, b.n_hits, b.n_cigar = ch.n_bundles, ch.n_hits, ch.n_cigar
-        for f in fields:
+        for f in lean:
             setattr(b, f, pin[f].data_ptr())
         views.append((b, pin))
     pipe = Pipeline(local, n_streams=args.streams)
@@ -283,10 +313,15 @@ def run_ours(args):
             log("[bench] kernel %-22s %9.3f ms/step  (%d launches/step, %.1f%% of kernel time)" %
                 (name, ms / steps, cnt // steps, 100 * ms / max(total_k, 1e-9)))
         dom = None
-        n_pairs_spl = counts["splice_ints"]   # placeholder, replaced below
-        # splice pairs over hits: inner N ops
         n_splice_pairs = int(np.count_nonzero(ops == 3))
-        for name, (ms, cnt) in top:
+        counts["bundles"] = batch.n_bundles
+        # the dominant kernel: side-stream launches of the same kernel count with it
+        merged = {}
+        for name, (ms, cnt) in prof.items():
+            m = merged.setdefault(name.replace("(side)", ""), [0.0, 0])
+            m[0] += ms
+            m[1] += cnt
+        for name, (ms, cnt) in sorted(merged.items(), key=lambda kv: -kv[1][0]):
             ab = algorithmic_bytes(name, counts, n_cigar, n_mblocks, n_splice_pairs)
             if ab is not None:
                 dom = (name, ms, cnt, ab)
@@ -299,14 +334,15 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         roof = None
         if dom:
-            name, ms, cnt, ab = dom
+            name, ms, cnt, ab = dom          # ab: bytes per step over all launches of the kernel in a step
             per_launch_ms = ms / cnt
             launches_per_step = cnt / steps
             achieved = ab / launches_per_step / (per_launch_ms / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "algorithmic_bytes_per_launch": ab / launches_per_step, "ms_per_launch": per_launch_ms,
-                    "share_of_kernel_time": ms / max(total_k, 1e-9), "traffic": None}
+                    "launches_per_step": launches_per_step,
+                    "share_of_kernel_time": ms / max(total_k, 1e-9), "ms_per_step_profiled": ms_prof / steps, "traffic": None}
         out = {"metric": "hits_per_sec", "value": value, "unit": "hits/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
                "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
                "data": "synthetic", "impl": "ours",
@@ -320,11 +356,111 @@ def run_ours(args):
                        "ms_per_step": ms_e2e / steps, "sub_batches": len(views), "streams": args.streams,
                        "gpu_launches_per_step": int(launches_e2e // steps)},
                "roofline": roof, "clocks": clk}
+        if stage5 is not None:
+            out["stage5"] = stage5
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(batch, min(10, ncpu), args.cpu_seconds)
+            if stage5 is not None:
+                out["stage5"]["cpu_baseline"] = stage5_cpu(batch, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+REGION = 1_000_000      # region_partition_length (util/parameters.cc:42)
+
+
+def region_groups(batch):
+    """bundle groups as the reference forms them: all samples' bundles of one (chromosome, 1 Mb region, strand)
+    (meta/incubator.cc:312-314, :461-471), members in (sample, bundle) order"""
+    a = batch.a
+    first = np.minimum(a["bundle_hit_off"][:-1], max(batch.n_hits - 1, 0))
+    key = (a["bundle_tid"].astype(np.int64) << 40) | ((a["pos"][first].astype(np.int64) // REGION) << 8) | a["strand"][first].astype(np.int64)
+    order = np.lexsort((np.arange(batch.n_bundles), a["bundle_sample"], key))
+    cuts = np.nonzero(np.diff(key[order]))[0] + 1
+    return [g for g in np.split(order, cuts) if len(g)]
+
+
+def stage5_gpu(ctx, bt, batch, args):
+    """bundle_group::resolve over every region group of the batch: splice signatures compacted on the device, all groups'
+    pair counts in one launch (agpu_group_resolve_batch), size-capped union-find on the host; configs[1]: -c 20 -s 0.2"""
+    import torch
+    from aletsch_b200 import gpu as G
+    gp5 = G.default_params(library_type=H.FR_FIRST, max_group_size=20, min_grouping_similarity=0.2)
+    groups = region_groups(batch)
+    clusters = 0
+    t_all = []
+    for it in range(1 + max(1, args.steps)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        off, val = bt.fetch_splices()
+        lists = [[val[off[k]:off[k + 1]] for k in g] for g in groups]
+        res = G.group_resolve_batch(ctx, lists, gp5)
+        torch.cuda.synchronize()
+        if it > 0:
+            t_all.append(time.perf_counter() - t0)
+        clusters = sum(len(r) for r in res)
+    dt = float(np.mean(t_all))
+    pairs = int(sum(len(g) * (len(g) - 1) // 2 for g in groups))
+    return {"bundle_groups": len(groups), "bundles": int(batch.n_bundles), "pairs": pairs, "clusters": int(clusters), "ms": dt * 1e3,
+            "bundles_per_sec": batch.n_bundles / dt, "pairs_per_sec": pairs / dt, "params": "-c 20 -s 0.2",
+            "timing": "host wall clock around splice fetch + agpu_group_resolve_batch (device pair counts + host union-find), synchronised"}
+
+
+def stage5_cpu(batch, threads, budget_s):
+    """the reference's bundle_group::resolve on a bounded sample of the same region groups (bundle objects built untimed)"""
+    import orclib
+    kind = "reference"
+    try:
+        orclib.Checker("ref")
+    except (OSError, FileNotFoundError):
+        kind = "port"
+    op = orclib.default_params(library_type=H.FR_FIRST, max_group_size=20, min_grouping_similarity=0.2)
+    groups = region_groups(batch)
+    sizes = np.diff(batch.a["bundle_hit_off"])
+    target_hits = int(60_000 * threads * budget_s)          # building the bundle objects dominates; bound that
+    step = max(1, int(np.ceil(sizes.sum() / max(target_hits, 1))))
+    sample = groups[::step]
+    lock = threading.Lock()
+    nxt = [0]
+    spent = [0.0]
+
+    def worker():
+        chk = orclib.Checker("ref" if kind == "reference" else "orc")
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= len(sample):
+                return
+            hs = [chk.new_bundle(batch.bundle(int(k)), op) for k in sample[i]]
+            t0 = time.perf_counter()
+            chk.group_resolve(hs, op)
+            dt = time.perf_counter() - t0
+            for h in hs:
+                chk.free_bundle(h)
+            with lock:
+                spent[0] += dt
+    # bundle_group::resolve prints per-group statistics lines (meta/bundle_group.cc:360-393): keep them off our stdout
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        ths = [threading.Thread(target=worker) for _ in range(threads)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+    nbun = int(sum(len(g) for g in sample))
+    pairs = int(sum(len(g) * (len(g) - 1) // 2 for g in sample))
+    wall = spent[0] / threads            # thread-seconds inside bundle_group::resolve spread over the pool
+    return {"kind": kind, "cores": threads, "sample": "every %d-th region group: %d groups, %d bundles" % (step, len(sample), nbun),
+            "bundles_per_sec": nbun / max(wall, 1e-9), "pairs_per_sec": pairs / max(wall, 1e-9)}
 
 
 def cpu_baseline(batch, threads, budget_s, all_cores=False):
@@ -416,6 +552,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 5M pairs per sample (development only; 1.0 = the named config)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage5", action="store_true", help="skip the bundle_group::resolve (stage 5) leg")
     ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the end-to-end pipeline")
     ap.add_argument("--streams", type=int, default=4, help="host threads / CUDA streams of the end-to-end pipeline")
     args = ap.parse_args()

@@ -98,15 +98,17 @@ typedef struct agpu_batch_in
 	const int32_t *bundle_tid;       /* [NB] chromosome id */
 	const int32_t *bundle_sample;    /* [NB] sample id (informational; carried through) */
 	const int32_t *pos;              /* [H] hit.pos */
-	const int32_t *rpos;             /* [H] hit.rpos */
+	const int32_t *rpos;             /* [H] hit.rpos; may be NULL: derived on the device as pos + bam_cigar2rlen (rnacore/hit.cc:64) */
 	const int32_t *mpos;             /* [H] hit.mpos */
 	const int32_t *isize;            /* [H] hit.isize */
-	const uint16_t *flag;            /* [H] hit.flag */
-	const uint8_t *strand;           /* [H] hit.strand */
+	const uint16_t *flag;            /* [H] hit.flag; informational, may be NULL: no kernel reads it (the host derives strand / xs from it,
+	                                    rnacore/hit.cc:106-185) and it is not uploaded */
+	const uint8_t *strand;           /* [H] hit.strand; may be NULL if bundle_strand is given */
 	const uint8_t *xs;               /* [H] hit.xs */
 	const uint64_t *qid;             /* [H] query-name key: equal <=> same qname (rnacore/bundle_base.cc:308) */
 	const uint32_t *cigar_off;       /* [H+1] into cigar[] */
 	const uint32_t *cigar;           /* [n_cigar] raw BAM CIGAR ops (len<<4 | op) */
+	const uint8_t *bundle_strand;    /* [NB] the strand all hits of a bundle share (rnacore/bundle_base.cc:100-101); used when strand == NULL */
 } agpu_batch_in;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -221,6 +223,8 @@ typedef struct agpu_bridge_view         /* bridge_solver::opt per cluster */
 } agpu_bridge_view;
 
 int agpu_evidence_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_evidence_view *v);
+/* only bundle::splices (sorted unique splice positions per bundle): splice_off[NB+1], splices[] */
+int agpu_splices_fetch(agpu_ctx *ctx, agpu_batch *b, const int64_t **splice_off, const int32_t **splices);
 int agpu_fragments_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_fragments_view *v);
 int agpu_graph_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_graph_view *v);
 int agpu_cluster_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_cluster_view *v);
@@ -232,6 +236,7 @@ typedef struct agpu_counts
 {
 	int64_t hits, cigar_ops, span, segments, chains, splice_ints, junctions, vertices, edges;
 	int64_t fragments, clusters, bridged, piers;
+	int64_t borders, cluster_members, bridge_chain_ints, bridge_whole_ints;   /* ranked coverage borders, sum of frlist sizes, sizes of opt[].chain / opt[].whole */
 } agpu_counts;
 int agpu_batch_counts(agpu_ctx *ctx, agpu_batch *b, agpu_counts *c);
 
@@ -254,6 +259,16 @@ int agpu_debug_sort_perm(agpu_ctx *ctx, const int32_t *keys, int32_t n, int32_t 
  * splice position sorted by r descending with std::sort (ties as libstdc++ leaves them). */
 int agpu_group_resolve(agpu_ctx *ctx, int32_t n_lists, const int64_t *list_off, const int32_t *list_val, const agpu_params *p,
 		int32_t *out_group_of, int32_t *out_n_groups);
+
+/* The same for MANY bundle groups in one call (one group per (chromosome, region, strand), meta/incubator.cc:461-471):
+ * group g owns the lists [group_off[g], group_off[g + 1]).  agpu_similarity_batch fills, for every group, a dense G x G
+ * matrix of pair counts at out_c + c_off[g] (c_off[n_groups] = total); groups of up to 192 lists are resolved by one CTA
+ * each in a single launch, larger ones by the tiled kernels.  agpu_group_resolve_batch adds the host control flow of
+ * bundle_group::resolve per group: out_group_of[l] is the cluster of list l inside its bundle group. */
+int agpu_similarity_batch(agpu_ctx *ctx, int32_t n_groups, const int32_t *group_off, const int64_t *list_off, const int32_t *list_val,
+		const int64_t *c_off, int32_t *out_c);
+int agpu_group_resolve_batch(agpu_ctx *ctx, int32_t n_groups, const int32_t *group_off, const int64_t *list_off, const int32_t *list_val,
+		const agpu_params *p, int32_t *out_group_of, int32_t *out_n_groups);
 
 #ifdef __cplusplus
 }

@@ -120,3 +120,40 @@ def compare_full(ctx, batch, checker, gp, op, stats=None):
         cmp_int("seg", rbr["seg"], ev2[k]["seg"], w + " update_bridges", bad)
     bt.free()
     return bad
+
+
+def lean_view(batch):
+    """agpu_batch_in without rpos / flag / per-hit strand (all optional): rpos is re-derived on the device, the strand goes
+    up once per bundle"""
+    a = batch.a
+    if "bundle_strand" not in a:
+        a["bundle_strand"] = np.ascontiguousarray(a["strand"][np.minimum(a["bundle_hit_off"][:-1], max(batch.n_hits - 1, 0))])
+    v = batch.view()
+    v.rpos = None
+    v.flag = None
+    v.strand = None
+    v.bundle_strand = a["bundle_strand"].ctypes.data
+    return v
+
+
+def compare_lean_upload(ctx, batch, gp):
+    """the lean upload must leave exactly the state of the full upload"""
+    bad = []
+    outs = []
+    for view in (batch.view(), lean_view(batch)):
+        bt = ctx.upload(view, keepalive=batch)
+        bt.bridge_all(gp)
+        ev = bt.fetch_evidence(batch.a["bundle_hit_off"])
+        fr = bt.fetch_fragments()
+        gr = bt.fetch_graph()
+        outs.append((ev, fr, gr, bt.counts()))
+        bt.free()
+    (e0, f0, g0, c0), (e1, f1, g1, c1) = outs
+    if c0 != c1:
+        bad.append("counts differ: %s vs %s" % (c0, c1))
+    for k in range(batch.n_bundles):
+        for d0, d1 in ((e0[k], e1[k]), (f0[k], f1[k]), (g0[k], g1[k])):
+            for n in d0:
+                if not np.array_equal(d0[n], d1[n]):
+                    bad.append("bundle %d: %s differs between full and lean upload" % (k, n))
+    return bad

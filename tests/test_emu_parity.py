@@ -41,6 +41,14 @@ def test_bundle_bridge_parity(ctx, checkers, mode, templates, seed):
             assert stats["bridged"] > 0 and stats["clusters"] > 0
 
 
+def test_lean_upload_matches_full(ctx):
+    """rpos / flag / per-hit strand are optional in agpu_batch_in (include/aletsch_gpu.h)"""
+    batch, lt = parity.make_batch(H.SYNTH_PAIRED, 20000)
+    gp, _ = parity.params_pair(lt)
+    bad = parity.compare_lean_upload(ctx, batch, gp)
+    assert not bad, bad[:3]
+
+
 def test_group_resolve_parity(ctx, checkers):
     """bundle_group::resolve: device similarity + host control flow against the checker, with the size cap binding"""
     import numpy as np
@@ -65,6 +73,26 @@ def test_group_resolve_parity(ctx, checkers):
             assert cc == c[i, j]
             if cc:
                 assert abs(r[i, j] - cc / min(len(lists[i]), len(lists[j]))) <= 1e-9 * r[i, j]       # BASELINE.json tolerance
+
+
+def test_group_resolve_batch_matches_single(ctx):
+    """many bundle groups in one call (one CTA per group) == one call per group; includes an empty group, a singleton and a
+    group above the one-CTA limit"""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    groups = []
+    for gsize in (0, 1, 2, 7, 40, 200, 13):
+        pool = np.sort(rng.choice(200000, size=60, replace=False)).astype(np.int32)
+        grp = []
+        for _ in range(gsize):
+            k = int(rng.integers(0, 12)) * 2
+            grp.append(np.sort(rng.choice(pool, size=k, replace=False)).astype(np.int32))
+        groups.append(grp)
+    gp = G.default_params(max_group_size=5, min_grouping_similarity=0.2)
+    got = G.group_resolve_batch(ctx, groups, gp)
+    for grp, g in zip(groups, got):
+        want = G.group_resolve(ctx, grp, gp) if len(grp) else []
+        assert g == want
 
 
 def test_std_sort_permutation(ctx):
