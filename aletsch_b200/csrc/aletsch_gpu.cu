@@ -10,8 +10,10 @@
 #include "k_similarity.h"
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <new>
+#include <thread>
 
 #ifdef AGPU_EMU
 thread_local agpu_emu_dim threadIdx, blockIdx, blockDim, gridDim;
@@ -254,6 +256,7 @@ int agpu_create(int device, void *stream, agpu_ctx **out)
 void agpu_destroy(agpu_ctx *ctx)
 {
 	if(!ctx) return;
+	AGPU_ENTER(ctx);
 #ifndef AGPU_EMU
 	cudaStreamSynchronize(ctx->stream);
 	if(ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
@@ -265,13 +268,14 @@ void agpu_destroy(agpu_ctx *ctx)
 }
 
 const char *agpu_last_error(agpu_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
-int agpu_sync(agpu_ctx *ctx) { return ctx ? stream_sync(ctx) : AGPU_ERR_ARG; }
+int agpu_sync(agpu_ctx *ctx) { if(!ctx) return AGPU_ERR_ARG; AGPU_ENTER(ctx); return stream_sync(ctx); }
 int64_t agpu_launch_count(agpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int agpu_profile_enable(agpu_ctx *ctx, int on) { if(!ctx) return AGPU_ERR_ARG; ctx->profiling = on != 0; return AGPU_OK; }
 int agpu_profile_reset(agpu_ctx *ctx)
 {
 	if(!ctx) return AGPU_ERR_ARG;
+	AGPU_ENTER(ctx);
 	TRY(stream_sync(ctx));
 	prof_collect(ctx);
 	ctx->prof_acc.clear();
@@ -280,6 +284,7 @@ int agpu_profile_reset(agpu_ctx *ctx)
 int agpu_profile_read(agpu_ctx *ctx, char *buf, size_t cap)
 {
 	if(!ctx || !buf || cap == 0) return AGPU_ERR_ARG;
+	AGPU_ENTER(ctx);
 	TRY(stream_sync(ctx));
 	prof_collect(ctx);
 	std::string out;
@@ -334,6 +339,7 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 {
 	if(!ctx || !in || !out || in->n_bundles < 0 || in->n_hits < 0) return AGPU_ERR_ARG;
+	AGPU_ENTER(ctx);
 	*out = NULL;
 	agpu_batch *b = new (std::nothrow) agpu_batch;
 	if(!b) return AGPU_ERR_OOM;
@@ -375,6 +381,7 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 {
 	if(!ctx || !in || !out || in->n_bundles < 0 || in->n_hits < 0) return AGPU_ERR_ARG;
+	AGPU_ENTER(ctx);
 	*out = NULL;
 	agpu_batch *b = new (std::nothrow) agpu_batch;
 	if(!b) return AGPU_ERR_OOM;
@@ -420,6 +427,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 {
 	if(!ctx || !b) return;
+	AGPU_ENTER(ctx);
 	release_derived(ctx, b);
 	b->in_hit_off.release(ctx); b->in_pos.release(ctx); b->in_rpos.release(ctx); b->in_mpos.release(ctx); b->in_isize.release(ctx);
 	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_bstrand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
@@ -433,6 +441,7 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 int agpu_batch_reset(agpu_ctx *ctx, agpu_batch *b)
 {
 	if(!ctx || !b) return AGPU_ERR_ARG;
+	AGPU_ENTER(ctx);
 	release_derived(ctx, b);
 	TRY(b->err.fill(ctx, 0));
 	return AGPU_OK;
@@ -558,6 +567,7 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 {
 	if(!ctx || !b || !p) return AGPU_ERR_ARG;
+	AGPU_ENTER(ctx);
 	if(b->evidence) return AGPU_OK;
 	int nb = b->nb;
 	int64_t nh = b->nh, nc = b->nc;
@@ -593,6 +603,7 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 {
 	if(!ctx || !b || !p) return AGPU_ERR_ARG;
+	AGPU_ENTER(ctx);
 	if(!b->evidence) return AGPU_ERR_ARG;
 	if(b->cov_dirty) TRY(coverage_scan(ctx, b));
 	graph_state &gs = b->gr;

@@ -79,6 +79,9 @@ inline void prof_collect(agpu_ctx *ctx)
 	ctx->prof.clear();
 }
 
+// entry points may be called from any host thread: the CUDA current device is per thread
+#define AGPU_ENTER(ctx) do { cudaSetDevice((ctx)->device); } while(0)
+
 // per-thread kernel: grid covers n items
 #define LAUNCH_T(ctx, kern, n, ...) do { int64_t n_ = (int64_t)(n); if(n_ > 0) { unsigned g_ = (unsigned)((n_ + 255) / 256); \
 	prof_begin(ctx, #kern); kern<<<g_, 256, 0, (ctx)->stream>>>(__VA_ARGS__); prof_end(ctx); (ctx)->launches++; } } while(0)
@@ -129,6 +132,7 @@ template<typename F, typename... A> inline void emu_launch(bool coop, F f, int64
 }
 inline void side_fork(agpu_ctx *) {}
 inline void side_join(agpu_ctx *) {}
+#define AGPU_ENTER(ctx) do {} while(0)
 #define LAUNCH_T(ctx, kern, n, ...) do { int64_t n_ = (int64_t)(n); if(n_ > 0) { emu_launch(false, kern, (n_ + 255) / 256, 256, __VA_ARGS__); (ctx)->launches++; } } while(0)
 #define LAUNCH_B_SIDE(ctx, kern, nblocks, nthreads, ...) LAUNCH_B(ctx, kern, nblocks, nthreads, __VA_ARGS__)
 #define LAUNCH_B(ctx, kern, nblocks, nthreads, ...) do { int64_t n_ = (int64_t)(nblocks); if(n_ > 0) { emu_launch(true, kern, n_, (nthreads), __VA_ARGS__); (ctx)->launches++; } } while(0)

@@ -253,6 +253,29 @@ def group_resolve_batch(ctx, groups, params):
     return res
 
 
+def group_resolve_arrays(ctx, group_off, list_off, list_val, params):
+    """agpu_group_resolve_batch on packed arrays: lists ordered group by group.  Returns (cluster_of[list], n_clusters[group])."""
+    group_off = np.ascontiguousarray(group_off, np.int32)
+    list_off = np.ascontiguousarray(list_off, np.int64)
+    list_val = np.ascontiguousarray(list_val if len(list_val) else np.zeros(1, np.int32), np.int32)
+    ng = len(group_off) - 1
+    out = np.zeros(max(int(group_off[-1]), 1), np.int32)
+    ncl = np.zeros(max(ng, 1), np.int32)
+    ctx.check(ctx.L.agpu_group_resolve_batch(ctx.h, ng, group_off.ctypes.data, list_off.ctypes.data, list_val.ctypes.data, C.byref(params),
+                                             out.ctypes.data, ncl.ctypes.data), "agpu_group_resolve_batch")
+    return out, ncl
+
+
+def reorder_lists(off, val, order):
+    """packed lists (off, val) re-packed in the order `order` (vectorised gather)"""
+    order = np.asarray(order, np.int64)
+    lens = off[order + 1] - off[order]
+    noff = np.zeros(len(order) + 1, np.int64)
+    np.cumsum(lens, out=noff[1:])
+    idx = np.repeat(off[order] - noff[:-1], lens) + np.arange(int(noff[-1]), dtype=np.int64)
+    return noff, val[idx] if len(val) else val
+
+
 class Batch:
     """agpu_batch: device-resident state of a batch of bundles."""
 

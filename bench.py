@@ -362,7 +362,7 @@ def run_ours(args):
             out["cpu_baseline"] = cpu_baseline(batch, min(10, ncpu), args.cpu_seconds)
             if stage5 is not None:
                 out["stage5"]["cpu_baseline"] = stage5_cpu(batch, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -388,18 +388,21 @@ def stage5_gpu(ctx, bt, batch, args):
     from aletsch_b200 import gpu as G
     gp5 = G.default_params(library_type=H.FR_FIRST, max_group_size=20, min_grouping_similarity=0.2)
     groups = region_groups(batch)
+    order = np.concatenate(groups) if groups else np.zeros(0, np.int64)
+    group_off = np.zeros(len(groups) + 1, np.int32)
+    np.cumsum([len(g) for g in groups], out=group_off[1:])
     clusters = 0
     t_all = []
     for it in range(1 + max(1, args.steps)):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         off, val = bt.fetch_splices()
-        lists = [[val[off[k]:off[k + 1]] for k in g] for g in groups]
-        res = G.group_resolve_batch(ctx, lists, gp5)
+        loff, lval = G.reorder_lists(off, val, order)
+        _, ncl = G.group_resolve_arrays(ctx, group_off, loff, lval, gp5)
         torch.cuda.synchronize()
         if it > 0:
             t_all.append(time.perf_counter() - t0)
-        clusters = sum(len(r) for r in res)
+        clusters = int(ncl.sum())
     dt = float(np.mean(t_all))
     pairs = int(sum(len(g) * (len(g) - 1) // 2 for g in groups))
     return {"bundle_groups": len(groups), "bundles": int(batch.n_bundles), "pairs": pairs, "clusters": int(clusters), "ms": dt * 1e3,
@@ -540,10 +543,30 @@ def run_reference(args):
            "bridged_pairs_per_sec": bps,
            "cpu_baseline": {"value": value, "unit": "hits/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
            "e2e": {"value": value, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """native libraries under us write to fd 1 (NCCL's version banner, the reference's statistics lines): send fd 1 to
+    stderr for the whole run and keep the real stdout for the ONE JSON line"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -22,7 +22,7 @@ def emu_lib():
     deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(ROOT, "include", "aletsch_gpu.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DAGPU_EMU", "-x", "c++", "-w",
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-DAGPU_EMU", "-x", "c++", "-w", "-pthread",
                                "-o", out, os.path.join(src, "aletsch_gpu.cu")])
     return out
 
