@@ -706,99 +706,118 @@ KERNEL k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *c
 }
 
 // ---- update_bridges (rnacore/bundle_base.cc:420-507) for every bridged cluster, as looped in meta/bundle.cc:73-79
-// pass 0: per cluster, count accepted fragments and those that join fcst; pass 1: apply
+// One thread per cluster MEMBER (fragment of a frlist).  Pass 0 decides acceptance and counts; device-wide scans turn the
+// per-member flags into the fcst entry order (= member order, which is cluster-major, the order of the reference's loops)
+// and the offsets of the coverage stretches; pass 1 applies.
 struct update_dev
 {
-	int32_t *acc_cnt;            // accepted fragments per cluster
-	int32_t *ent_cnt;            // fcst entries per cluster (accepted fragments of clusters with a non-empty chain)
-	const int64_t *ent_off;      // scanned
+	const int64_t *crank;        // flag rank over members: cluster of member x = crank[x + 1] - 1
+	int32_t *ent_flag;           // pass 0: 0 if the member joins fcst (accepted, non-empty chain), else -1
+	int32_t *gap_cnt;            // pass 0: coverage stretches (mmap += 1) of the member, 0 if not accepted
+	int32_t *acc_flag;           // pass 0: 1 if accepted
+	const int64_t *ent_rank;     // scanned
+	const int64_t *gap_off;      // scanned
 	int32_t *ent_frag, *ent_xs, *ent_len;
 	int64_t *ent_voff;
 	int32_t *bridged;            // [NB]
-	int32_t *gap_cnt;            // coverage stretches (mmap += 1) per cluster
-	const int64_t *gap_off;      // scanned
 	int64_t *ex_s, *ex_e;        // the stretches as global window positions, appended after the earlier rounds' at ex_base
 	int64_t ex_base;
 };
 
-KERNEL k_update(int64_t n_clu, int apply, const int32_t *c_bundle, const int64_t *frg_off, const int64_t *fr_begin, const int32_t *members,
+KERNEL k_update(int64_t n_mem, int apply, const int32_t *c_bundle, const int64_t *frg_off, const int32_t *members,
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, int32_t *f_type, const int32_t *o_type, const int32_t *o_strand,
 		const int64_t *o_coff, const int32_t *o_chain, const int32_t *b_lpos, const int32_t *b_covhi, const int64_t *cov_base,
 		u32 *border, update_dev u, int *err)
 {
-	int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= n_clu) return;
-	if(!apply) { u.acc_cnt[c] = 0; u.ent_cnt[c] = 0; u.gap_cnt[c] = 0; }
-	if(o_type[c] <= 0) return;
-	int b = c_bundle[c];
-	int64_t f0 = frg_off[b], h0 = h.bundle_hit_off[b];
-	const int32_t *chain = o_chain + o_coff[c];
-	int cl = (int)(o_coff[c + 1] - o_coff[c]);
-	int strand = o_strand[c];
-	int acc = 0, ent = 0, gaps = 0;
-	int64_t cbase = cov_base[b] - (int64_t)b_lpos[b];
-	for(int64_t x = fr_begin[c]; x < fr_begin[c + 1]; x++)
+	int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(x >= n_mem) return;
+	int b = -1;
+	bool accepted = false;
+	if(apply ? u.acc_flag[x] != 0 : true)
 	{
-		int fr = members[x];
-		int64_t i1 = h0 + f_h1[f0 + fr], i2 = h0 + f_h2[f0 + fr];
-		int32_t r1 = h.rpos[i1], p2 = h.pos[i2];
-		// v1 = (h1.rpos, chain..., h2.pos) must be non-decreasing when h1.rpos < h2.pos
-		if(r1 < p2)
+		const int64_t c = u.crank[x + 1] - 1;
+		if(o_type[c] > 0)
 		{
-			bool inc = true;
-			int32_t prev = r1;
-			for(int k = 0; k < cl && inc; k++) { if(prev > chain[k]) inc = false; prev = chain[k]; }
-			if(inc && prev > p2) inc = false;
-			if(!inc) continue;
-		}
-		acc++;
-		if(cl > 0)
-		{
-			if(apply)
+			b = c_bundle[c];
+			const int64_t f0 = frg_off[b], h0 = h.bundle_hit_off[b];
+			const int32_t *chain = o_chain + o_coff[c];
+			const int cl = (int)(o_coff[c + 1] - o_coff[c]);
+			const int fr = members[x];
+			const int64_t i1 = h0 + f_h1[f0 + fr], i2 = h0 + f_h2[f0 + fr];
+			const int32_t r1 = h.rpos[i1], p2 = h.pos[i2];
+			accepted = true;
+			// v1 = (h1.rpos, chain..., h2.pos) must be non-decreasing when h1.rpos < h2.pos
+			if(!apply && r1 < p2)
 			{
-				char s = '.';
-				char x1 = (char)h.xs[i1], x2 = (char)h.xs[i2];
-				if(x1 != '.') s = x1;
-				if(x2 != '.') s = x2;
-				if(x1 != '.' && x2 != '.' && x1 != x2) s = '.';
-				char ss = '.';
-				if(strand == 1) ss = '+';
-				if(strand == 2) ss = '-';
-				char use;
-				if(s == ss) use = ss;
-				else if(s != '.' && ss == '.') use = s;
-				else if(ss != '.' && s == '.') use = ss;
-				else use = '.';
-				int64_t eo = u.ent_off[c] + ent;
-				u.ent_frag[eo] = fr;
-				u.ent_xs[eo] = use == '+' ? 1 : (use == '-' ? 2 : 0);
-				u.ent_len[eo] = cl;
-				u.ent_voff[eo] = o_coff[c];
+				int32_t prev = r1;
+				for(int k = 0; k < cl && accepted; k++) { if(prev > chain[k]) accepted = false; prev = chain[k]; }
+				if(accepted && prev > p2) accepted = false;
 			}
-			ent++;
-		}
-		if(apply) f_type[f0 + fr] = cl > 0 ? 2 : 1;
-		// mmap += 1 over every stretch (v1[2k], v1[2k+1]) with v1[2k] < v1[2k+1]: new borders + a list entry
-		int nv = cl + 2;
-		for(int k = 0; k < nv / 2; k++)
-		{
-			int32_t a = (2 * k == 0) ? r1 : chain[2 * k - 1];
-			int32_t e = (2 * k + 1 == nv - 1) ? p2 : chain[2 * k];
-			if(a >= e) continue;
-			if(a < b_lpos[b] || e > b_covhi[b]) { if(apply) atomicAdd(&err[ERR_CAP], 1); continue; }
-			if(apply)
+			if(accepted)
 			{
-				int64_t s0 = cbase + a, e0 = cbase + e;
-				int64_t at = u.ex_base + u.gap_off[c] + gaps;
-				u.ex_s[at] = s0; u.ex_e[at] = e0;
-				atomicOr(&border[s0 >> 5], 1u << (s0 & 31));
-				atomicOr(&border[e0 >> 5], 1u << (e0 & 31));
+				if(apply)
+				{
+					f_type[f0 + fr] = cl > 0 ? 2 : 1;
+					if(cl > 0)
+					{
+						char s = '.';
+						char x1 = (char)h.xs[i1], x2 = (char)h.xs[i2];
+						if(x1 != '.') s = x1;
+						if(x2 != '.') s = x2;
+						if(x1 != '.' && x2 != '.' && x1 != x2) s = '.';
+						char ss = '.';
+						const int strand = o_strand[c];
+						if(strand == 1) ss = '+';
+						if(strand == 2) ss = '-';
+						char use;
+						if(s == ss) use = ss;
+						else if(s != '.' && ss == '.') use = s;
+						else if(ss != '.' && s == '.') use = ss;
+						else use = '.';
+						const int64_t eo = u.ent_rank[x];
+						u.ent_frag[eo] = fr;
+						u.ent_xs[eo] = use == '+' ? 1 : (use == '-' ? 2 : 0);
+						u.ent_len[eo] = cl;
+						u.ent_voff[eo] = o_coff[c];
+					}
+				}
+				// mmap += 1 over every stretch (v1[2k], v1[2k+1]) with v1[2k] < v1[2k+1]: new borders + a list entry
+				const int64_t cbase = cov_base[b] - (int64_t)b_lpos[b];
+				int gaps = 0;
+				const int nv = cl + 2;
+				for(int k = 0; k < nv / 2; k++)
+				{
+					int32_t a = (2 * k == 0) ? r1 : chain[2 * k - 1];
+					int32_t e = (2 * k + 1 == nv - 1) ? p2 : chain[2 * k];
+					if(a >= e) continue;
+					if(a < b_lpos[b] || e > b_covhi[b]) { if(apply) atomicAdd(&err[ERR_CAP], 1); continue; }
+					if(apply)
+					{
+						int64_t s0 = cbase + a, e0 = cbase + e;
+						int64_t at = u.ex_base + u.gap_off[x] + gaps;
+						u.ex_s[at] = s0; u.ex_e[at] = e0;
+						atomicOr(&border[s0 >> 5], 1u << (s0 & 31));
+						atomicOr(&border[e0 >> 5], 1u << (e0 & 31));
+					}
+					gaps++;
+				}
+				if(!apply) { u.ent_flag[x] = cl > 0 ? 0 : -1; u.gap_cnt[x] = gaps; u.acc_flag[x] = 1; }
 			}
-			gaps++;
 		}
 	}
-	if(!apply) { u.acc_cnt[c] = acc; u.ent_cnt[c] = ent; u.gap_cnt[c] = gaps; }
-	else if(acc > 0) atomicAdd(&u.bridged[b], acc);
+	if(!apply)
+	{
+		if(!accepted) { u.ent_flag[x] = -1; u.gap_cnt[x] = 0; u.acc_flag[x] = 0; }
+		return;
+	}
+	// bridged count of the bundle: members of a bundle are neighbours, one atomic per (warp, bundle)
+#ifndef AGPU_EMU
+	const unsigned act = __activemask();
+	const unsigned peers = __match_any_sync(act, accepted ? b : -1);
+	if(accepted && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&u.bridged[b], __popc(peers));
+#else
+	if(accepted) atomicAdd(&u.bridged[b], 1);
+#endif
 }
 
 // fcst table insertion for the entries (elements) of all rounds so far

@@ -271,25 +271,50 @@ KERNEL k_frag_group(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hi
 #define BIG_GROUP 16            // groups above this size are partitioned by a whole warp (CUDA build)
 #define LANE_RANGE 48           // inside the warp kernel, ranges up to this size are sorted by a single lane
 
+// small_list / big_list: the leaders packed densely (any order), so that the partition kernels run with full warps
 KERNEL k_group_leaders(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, cluster_dev c, int32_t *leader, int32_t *leader_size,
-		int32_t *n_big, int32_t *big_list, int32_t big_cap)
+		int32_t *n_big, int32_t *big_list, int32_t big_cap, int32_t *n_small, int32_t *small_list)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(f >= n_frg) return;
-	leader[f] = -1;
-	leader_size[f] = 0;
-	int64_t sl = c.f_slot[f];
-	if(sl < 0) return;
-	int b = find_segment(frg_off, n_bundles, f);
-	if(c.slot_min[sl] != (int32_t)(f - frg_off[b])) return;
-	leader[f] = 1;
-	leader_size[f] = c.slot_n[sl];
+	bool lead = false;
+	int size = 0;
+	if(f < n_frg)
+	{
+		leader[f] = -1;
+		leader_size[f] = 0;
+		int64_t sl = c.f_slot[f];
+		if(sl >= 0)
+		{
+			int b = find_segment(frg_off, n_bundles, f);
+			if(c.slot_min[sl] == (int32_t)(f - frg_off[b]))
+			{
+				lead = true;
+				size = c.slot_n[sl];
+				leader[f] = 1;
+				leader_size[f] = size;
+			}
+		}
+	}
 #ifndef AGPU_EMU
-	if(c.slot_n[sl] > BIG_GROUP)
+	if(lead && size > BIG_GROUP)
 	{
 		int k = atomicAdd(n_big, 1);
 		if(k < big_cap) big_list[k] = (int32_t)f;
 	}
+	// one atomic per warp for the small groups
+	const bool small = lead && size <= BIG_GROUP;
+	const unsigned m = __ballot_sync(0xffffffffu, small);
+	if(m)
+	{
+		const int lane = threadIdx.x & 31;
+		int base = 0;
+		if(lane == __ffs((int)m) - 1) base = atomicAdd(n_small, __popc(m));
+		base = __shfl_sync(0xffffffffu, base, __ffs((int)m) - 1);
+		if(small) small_list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)f;
+	}
+#else
+	if(lead) small_list[atomicAdd(n_small, 1)] = (int32_t)f;
+	(void)n_big; (void)big_list; (void)big_cap;
 #endif
 }
 
@@ -376,18 +401,16 @@ template<> DEV void partition_rec<4>(const part_ctx &c, int lo, int hi) { (void)
 
 // ---- C3: the first fragment of every group gathers the members (ascending fragment index) and partitions them
 KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
-		cluster_dev c, const int32_t *leader, const int64_t *member_off, int32_t *members, u64 *elems, int32_t *cflag, int gap)
+		cluster_dev c, const int32_t *n_small, const int32_t *small_list, const int64_t *member_off, int32_t *members, u64 *elems,
+		int32_t *cflag, int gap)
 {
-	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(f >= n_frg) return;
-	if(leader[f] < 0) return;
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_frg || i >= *n_small) return;
+	const int64_t f = small_list[i];                 // groups above BIG_GROUP members are handled by k_group_partition_warp
 	int b = find_segment(frg_off, n_bundles, f);
 	int64_t f0 = frg_off[b];
 	int64_t sl = c.f_slot[f];
 	int n = c.slot_n[sl];
-#ifndef AGPU_EMU
-	if(n > BIG_GROUP) return;                      // handled by k_group_partition_warp
-#endif
 	int32_t *m = members + member_off[f];
 #ifndef AGPU_EMU
 	{
