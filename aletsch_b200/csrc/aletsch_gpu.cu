@@ -147,6 +147,7 @@ struct agpu_batch
 	bool cov_dirty = true;
 	dbuf<int64_t> seg_off;
 	dbuf<int32_t> seg_l, seg_r, seg_c;
+	dbuf<int64_t> seg_nhead, seg_psum;     // run structure and prefix sums of len * cov over all segments (k_graph.h seg_view)
 	int64_t n_seg = 0;
 
 	// fragments / clusters / bridges live in their own headers' state structs
@@ -419,7 +420,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx); b->hit_hash.release(ctx);
 	b->hcst.release(ctx); b->fcst.release(ctx);
 	b->seg_off.release(ctx);
-	b->seg_l.release(ctx); b->seg_r.release(ctx); b->seg_c.release(ctx);
+	b->seg_l.release(ctx); b->seg_r.release(ctx); b->seg_c.release(ctx); b->seg_nhead.release(ctx); b->seg_psum.release(ctx);
 	b->frg.release(ctx); b->gr.release(ctx); b->clu.release(ctx); b->brg.release(ctx); b->brg.release_entries(ctx);
 	b->evidence = false; b->cov_dirty = true; b->n_seg = 0; b->ltot = 0;
 }
@@ -506,6 +507,10 @@ static int chainset_finish(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int
 	return AGPU_OK;
 }
 
+// device-wide scans defined with stages 3-5 (abi_stages.inc)
+static int flag_rank(agpu_ctx *ctx, const int32_t *v, int64_t n, dbuf<int32_t> &tile_cnt, dbuf<int64_t> &tile_off, dbuf<int64_t> &rank, int64_t *total);
+static int value_scan(agpu_ctx *ctx, const int32_t *v, int64_t n, dbuf<int32_t> &tile_sum, dbuf<int64_t> &tile_off, dbuf<int64_t> &out, int64_t *total);
+
 // device-wide exclusive scan of per-tile int32 sums (at most a few 10^4 tiles): one CTA
 static int tile_scan(agpu_ctx *ctx, dbuf<int32_t> &tile_sum, dbuf<int64_t> &tile_off, int64_t nt)
 {
@@ -554,10 +559,26 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		TRY(tile_scan(ctx, ts, to, nt));
 		LAUNCH_B(ctx, k_covc_tile_cover, nt, 256, b->diffc.p, n, nt, to.p, b->covc.p, tc.p);
 		TRY(tile_scan(ctx, tc, tco, nt));
-		LAUNCH_B(ctx, k_covc_emit, nt, 256, b->covc.p, b->posc.p, n, nt, tco.p, nb, b->bord_off.p, b->seg_l.p, b->seg_r.p, b->seg_c.p, b->seg_off.p);
+		dbuf<int32_t> s_head, s_prod;
+		TRY(s_head.alloc(ctx, n + 1)); TRY(s_prod.alloc(ctx, n + 1));
+		LAUNCH_B(ctx, k_covc_emit, nt, 256, b->covc.p, b->posc.p, n, nt, tco.p, nb, b->bord_off.p, b->seg_l.p, b->seg_r.p, b->seg_c.p, b->seg_off.p,
+				s_head.p, s_prod.p);
 		TRY(d2h(ctx, &b->n_seg, tco.p + nt, sizeof(int64_t)));
 		TRY(stream_sync(ctx));
 		tc.release(ctx); tco.release(ctx);
+		// side tables of the segment list for the region walk of graph_builder (k_graph.h)
+		{
+			const int64_t ns = b->n_seg;
+			dbuf<int32_t> t1;
+			dbuf<int64_t> t2, hrank, heads;
+			TRY(flag_rank(ctx, s_head.p, ns, t1, t2, hrank, NULL));
+			TRY(value_scan(ctx, s_prod.p, ns, t1, t2, b->seg_psum, NULL));
+			TRY(heads.alloc(ctx, ns + 2)); TRY(b->seg_nhead.alloc(ctx, ns + 2));
+			LAUNCH_T(ctx, k_seg_heads, ns + 1, ns, s_head.p, hrank.p, heads.p);
+			LAUNCH_T(ctx, k_seg_nhead, ns, ns, hrank.p, heads.p, b->seg_nhead.p);
+			t1.release(ctx); t2.release(ctx); hrank.release(ctx); heads.release(ctx);
+		}
+		s_head.release(ctx); s_prod.release(ctx);
 	}
 	ts.release(ctx); to.release(ctx);
 	b->cov_dirty = false;
@@ -613,6 +634,7 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	in.n = nb; in.lpos = b->b_lpos.p; in.rpos = b->b_rpos.p; in.strand = b->b_strand.p;
 	in.hc = b->hcst.view(); in.fc = b->fcst.view();
 	in.seg_off = b->seg_off.p; in.seg_l = b->seg_l.p; in.seg_r = b->seg_r.p; in.seg_c = b->seg_c.p;
+	in.seg_nhead = b->seg_nhead.p; in.seg_psum = b->seg_psum.p;
 	for(int k = 0; k < 5; k++) { TRY(gs.ub[k].alloc(ctx, nb + 1)); TRY(gs.off[k].alloc(ctx, nb + 2)); }
 	LAUNCH_B(ctx, k_graph_bounds, nb, 128, in, gs.ub[0].p, gs.ub[1].p, gs.ub[2].p, gs.ub[3].p, gs.ub[4].p);
 	for(int k = 0; k < 5; k++)

@@ -595,114 +595,180 @@ KERNEL k_pier_bridges(int64_t n_slots, int32_t n_bundles, const int64_t *clu_off
 	br.p_nbr[slot] = m;
 }
 
+// ---- B5: vote (bridge/bridge_solver.cc:287-385)
+//   k_vote (emit = 0)  one thread per cluster: classify; clusters without a decision to take are settled at once, the
+//                      others are packed into two work lists (any order: results are addressed by cluster)
+//   k_vote_type1       one thread per listed cluster with overlapping end vertices: merge the two chains, one candidate
+//   k_vote_type2       one thread per listed cluster with a pier: the bridge candidates in refine_pier order, the first valid
+//                      one is the choice (a warp per cluster was measured slower: most piers offer 1-3 candidates)
+//   k_vote (emit = 1)  one thread per cluster writes the coordinates of the chosen chain / whole
+struct vote_lists { int32_t *n1, *list1, *n2, *list2; };
+
+struct vote_cluster              // what every vote kernel needs about a cluster
+{
+	int b, type, n1, n2;
+	int64_t slot;
+	const int32_t *ch1, *ch2;
+};
+
+DEV vote_cluster vote_load(int64_t c, int ss, int tt, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_chain1,
+		const int32_t *c_chain2, const chains_view &cv, const bridge_dev &br)
+{
+	vote_cluster v;
+	v.b = c_bundle[c];
+	v.ch1 = NULL; v.ch2 = NULL; v.n1 = 0; v.n2 = 0;
+	if(c_chain1[c] >= 0) { v.ch1 = cv.ptr(v.b, c_chain1[c]); v.n1 = cv.len(v.b, c_chain1[c]); }
+	if(c_chain2[c] >= 0) { v.ch2 = cv.ptr(v.b, c_chain2[c]); v.n2 = cv.len(v.b, c_chain2[c]); }
+	v.type = 0; v.slot = -1;
+	if(ss >= tt) v.type = 1;
+	else if(br.pier_of[c] >= 0) { v.type = 2; v.slot = clu_off[v.b] + br.pier_of[c]; }
+	return v;
+}
+
+// candidate e of a type-2 cluster: chain1 + bridge + chain2
+DEV bool vote_candidate2(const sgraph &sg, const vote_cluster &v, const bridge_dev &br, int e, int32_t bd0, int32_t bd3,
+		int &strand, double &score, int &cn, int &wn)
+{
+	const int K = br.K;
+	int bi = br.br_order[v.slot * 2 * K + e];
+	int stride = br.p_bt[v.slot] - br.p_bs[v.slot] + 1;
+	const int32_t *bc = br.chains + 2 * br.p_path_off[v.slot] + (int64_t)bi * 2 * stride;
+	int bl = br.br_clen[v.slot * 2 * K + bi];
+	seq3 w;
+	w.p[0] = v.ch1; w.n[0] = v.n1; w.p[1] = bc; w.n[1] = bl; w.p[2] = v.ch2; w.n[2] = v.n2;
+	if(!seq_increasing(w)) return false;
+	strand = check_strand(sg, w);
+	if(strand < 0) return false;
+	cn = bl;
+	score = br.br_stack[(v.slot * 2 * K + bi) * br.D];
+	wn = w.size();
+	if(wn >= 1 && w.at(0) <= bd0) return false;
+	if(wn >= 1 && w.at(wn - 1) >= bd3) return false;
+	int32_t intron = 0;
+	for(int k = 0; k < wn / 2; k++) intron += w.at(2 * k + 1) - w.at(2 * k);
+	int32_t length = bd3 - bd0 - intron;
+	if(length < br.low) return false;
+	if(length > br.high) return false;
+	return true;
+}
+
 struct vote_out
 {
 	int32_t *type, *strand, *choices;
 	double *score;
-	int32_t *pick;               // index of the chosen candidate (pass 0), -1 if none
-	int32_t *clen, *wlen;        // lengths (pass 0), then
-	const int64_t *coff, *woff;  // offsets (pass 1)
+	int32_t *pick;               // index of the chosen candidate, -1 if none
+	int32_t *clen, *wlen;        // lengths, then
+	const int64_t *coff, *woff;  // offsets (emit pass)
 	int32_t *chain, *whole;
 };
 
-// ---- B5: vote (bridge/bridge_solver.cc:287-385); emit = 0 computes the choice and the lengths, emit = 1 writes the coordinates
 KERNEL k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
-		const int32_t *c_chain2, chains_view cv, graph_dev g, const uint8_t *b_strand, bridge_dev br, vote_out o)
+		const int32_t *c_chain2, chains_view cv, graph_dev g, const uint8_t *b_strand, bridge_dev br, vote_out o, vote_lists vl)
 {
 	int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= n_clu) return;
-	const int ss = br.vp1[c], tt = br.vp2[c];
-	if(!emit)
+	int kind = 0;                    // 1 / 2: goes to the work list of that type
+	if(c < n_clu)
 	{
-		o.type[c] = -1; o.strand[c] = 0; o.choices[c] = 0; o.score[c] = 0; o.clen[c] = 0; o.wlen[c] = 0; o.pick[c] = -1;
-		if(ss < 0 || tt < 0) return;
-	}
-	else if(o.pick[c] < 0) return;
-	const int b = c_bundle[c];
-	const int K = br.K;
-	const int32_t *ch1 = NULL, *ch2 = NULL;
-	int n1 = 0, n2 = 0;
-	if(c_chain1[c] >= 0) { ch1 = cv.ptr(b, c_chain1[c]); n1 = cv.len(b, c_chain1[c]); }
-	if(c_chain2[c] >= 0) { ch2 = cv.ptr(b, c_chain2[c]); n2 = cv.len(b, c_chain2[c]); }
-	int type = 0;
-	int64_t slot = -1;
-	if(ss >= tt) type = 1;
-	else if(br.pier_of[c] >= 0) { type = 2; slot = clu_off[b] + br.pier_of[c]; }
-	if(emit)
-	{
-		// the choice is known: rebuild its coordinates only
-		seq3 w, cc;
-		cc.n[0] = cc.n[1] = cc.n[2] = 0; cc.p[0] = cc.p[1] = cc.p[2] = ch1;
-		if(type == 1) merge_intron_chains(ch1, n1, ch2, n2, w);
-		else
+		const int ss = br.vp1[c], tt = br.vp2[c];
+		if(!emit)
 		{
-			int bi = br.br_order[slot * 2 * K + o.pick[c]];
-			int stride = br.p_bt[slot] - br.p_bs[slot] + 1;
-			const int32_t *bc = br.chains + 2 * br.p_path_off[slot] + (int64_t)bi * 2 * stride;
-			int bl = br.br_clen[slot * 2 * K + bi];
-			w.p[0] = ch1; w.n[0] = n1; w.p[1] = bc; w.n[1] = bl; w.p[2] = ch2; w.n[2] = n2;
-			cc.p[0] = bc; cc.n[0] = bl;
+			o.type[c] = -1; o.strand[c] = 0; o.choices[c] = 0; o.score[c] = 0; o.clen[c] = 0; o.wlen[c] = 0; o.pick[c] = -1;
+			if(ss >= 0 && tt >= 0)
+			{
+				vote_cluster v = vote_load(c, ss, tt, c_bundle, clu_off, c_chain1, c_chain2, cv, br);
+				if(v.type == 1 && v.n1 == 0 && v.n2 == 0)
+				{
+					// both mates unspliced inside overlapping vertices: `whole` is empty, only the fragment length decides
+					int32_t length = c_bounds[4 * c + 3] - c_bounds[4 * c];
+					if(length >= br.low && length <= br.high) { o.type[c] = 1; o.choices[c] = 1; o.score[c] = 10; o.pick[c] = 0; }
+				}
+				else kind = v.type;
+			}
 		}
-		int nc = cc.size(), nw = w.size();
-		for(int k = 0; k < nc; k++) o.chain[o.coff[c] + k] = cc.at(k);
-		for(int k = 0; k < nw; k++) o.whole[o.woff[c] + k] = w.at(k);
-		return;
+		else if(o.pick[c] >= 0)
+		{
+			// the choice is known: rebuild its coordinates only
+			vote_cluster v = vote_load(c, ss, tt, c_bundle, clu_off, c_chain1, c_chain2, cv, br);
+			seq3 w, cc;
+			cc.n[0] = cc.n[1] = cc.n[2] = 0; cc.p[0] = cc.p[1] = cc.p[2] = v.ch1;
+			if(v.type == 1) merge_intron_chains(v.ch1, v.n1, v.ch2, v.n2, w);
+			else
+			{
+				const int K = br.K;
+				int bi = br.br_order[v.slot * 2 * K + o.pick[c]];
+				int stride = br.p_bt[v.slot] - br.p_bs[v.slot] + 1;
+				const int32_t *bc = br.chains + 2 * br.p_path_off[v.slot] + (int64_t)bi * 2 * stride;
+				int bl = br.br_clen[v.slot * 2 * K + bi];
+				w.p[0] = v.ch1; w.n[0] = v.n1; w.p[1] = bc; w.n[1] = bl; w.p[2] = v.ch2; w.n[2] = v.n2;
+				cc.p[0] = bc; cc.n[0] = bl;
+			}
+			int nc = cc.size(), nw = w.size();
+			for(int k = 0; k < nc; k++) o.chain[o.coff[c] + k] = cc.at(k);
+			for(int k = 0; k < nw; k++) o.whole[o.woff[c] + k] = w.at(k);
+		}
 	}
-	const int32_t bd0 = c_bounds[4 * c], bd3 = c_bounds[4 * c + 3];
-	if(type == 1 && n1 == 0 && n2 == 0)
+	if(emit) return;
+#ifndef AGPU_EMU
+	const int lane = threadIdx.x & 31;
+	for(int t = 1; t <= 2; t++)
 	{
-		// both mates unspliced inside overlapping vertices: `whole` is empty, only the fragment length decides
-		int32_t length = bd3 - bd0;
-		if(length < br.low || length > br.high) return;
-		o.type[c] = 1; o.strand[c] = 0; o.choices[c] = 1; o.score[c] = 10; o.pick[c] = 0;
-		return;
+		const unsigned m = __ballot_sync(0xffffffffu, kind == t);
+		if(!m) continue;
+		int base = 0;
+		if(lane == __ffs((int)m) - 1) base = atomicAdd(t == 1 ? vl.n1 : vl.n2, __popc(m));
+		base = __shfl_sync(0xffffffffu, base, __ffs((int)m) - 1);
+		if(kind == t) (t == 1 ? vl.list1 : vl.list2)[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)c;
 	}
-	sgraph sg = sgraph_of(g, b_strand, b);
-	int be = -1, choices = 0, best_strand = 0, best_cn = 0, best_wn = 0;
-	double best_score = 0;
-	int ncand = 0;
-	if(type == 1) ncand = 1;
-	else if(type == 2) ncand = br.p_nbr[slot];
+#else
+	if(kind == 1) vl.list1[atomicAdd(vl.n1, 1)] = (int32_t)c;
+	if(kind == 2) vl.list2[atomicAdd(vl.n2, 1)] = (int32_t)c;
+#endif
+}
+
+KERNEL k_vote_type1(int64_t n_clu, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
+		const int32_t *c_chain2, chains_view cv, graph_dev g, const uint8_t *b_strand, bridge_dev br, vote_out o, vote_lists vl)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_clu || i >= *vl.n1) return;
+	const int64_t c = vl.list1[i];
+	vote_cluster v = vote_load(c, br.vp1[c], br.vp2[c], c_bundle, clu_off, c_chain1, c_chain2, cv, br);
+	sgraph sg = sgraph_of(g, b_strand, v.b);
+	seq3 w;
+	if(!merge_intron_chains(v.ch1, v.n1, v.ch2, v.n2, w)) return;
+	if(!seq_increasing(w)) return;
+	int s = check_strand(sg, w);
+	if(s < 0) return;
+	const int32_t bd0 = c_bounds[4 * c], bd3 = c_bounds[4 * c + 3];
+	int wn = w.size();
+	if(wn >= 1 && w.at(0) <= bd0) return;
+	if(wn >= 1 && w.at(wn - 1) >= bd3) return;
+	int32_t intron = 0;
+	for(int k = 0; k < wn / 2; k++) intron += w.at(2 * k + 1) - w.at(2 * k);
+	int32_t length = bd3 - bd0 - intron;
+	if(length < br.low || length > br.high) return;
+	o.type[c] = 1; o.strand[c] = s; o.choices[c] = 1; o.score[c] = 10; o.clen[c] = 0; o.wlen[c] = wn; o.pick[c] = 0;
+}
+
+KERNEL k_vote_type2(int64_t n_clu, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
+		const int32_t *c_chain2, chains_view cv, graph_dev g, const uint8_t *b_strand, bridge_dev br, vote_out o, vote_lists vl)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_clu || i >= *vl.n2) return;
+	const int64_t c = vl.list2[i];
+	vote_cluster v = vote_load(c, br.vp1[c], br.vp2[c], c_bundle, clu_off, c_chain1, c_chain2, cv, br);
+	sgraph sg = sgraph_of(g, b_strand, v.b);
+	const int32_t bd0 = c_bounds[4 * c], bd3 = c_bounds[4 * c + 3];
+	const int ncand = br.p_nbr[v.slot];
+	int be = -1, choices = 0;
 	for(int e = 0; e < ncand; e++)
 	{
-		seq3 w;
-		int s, cn = 0;
-		double score;
-		if(type == 1)
-		{
-			if(!merge_intron_chains(ch1, n1, ch2, n2, w)) break;
-			if(!seq_increasing(w)) break;
-			s = check_strand(sg, w);
-			if(s < 0) break;
-			score = 10;
-		}
-		else
-		{
-			int bi = br.br_order[slot * 2 * K + e];
-			int stride = br.p_bt[slot] - br.p_bs[slot] + 1;
-			const int32_t *bc = br.chains + 2 * br.p_path_off[slot] + (int64_t)bi * 2 * stride;
-			int bl = br.br_clen[slot * 2 * K + bi];
-			w.p[0] = ch1; w.n[0] = n1; w.p[1] = bc; w.n[1] = bl; w.p[2] = ch2; w.n[2] = n2;
-			if(!seq_increasing(w)) continue;
-			s = check_strand(sg, w);
-			if(s < 0) continue;
-			cn = bl;
-			score = br.br_stack[(slot * 2 * K + bi) * br.D];
-		}
-		int wn = w.size();
-		if(wn >= 1 && w.at(0) <= bd0) continue;
-		if(wn >= 1 && w.at(wn - 1) >= bd3) continue;
-		int32_t intron = 0;
-		for(int k = 0; k < wn / 2; k++) intron += w.at(2 * k + 1) - w.at(2 * k);
-		int32_t length = bd3 - bd0 - intron;
-		if(length < br.low) continue;
-		if(length > br.high) continue;
-		if(be < 0) { be = e; best_cn = cn; best_wn = wn; best_strand = s; best_score = score; }
+		int s = 0, cn = 0, wn = 0;
+		double score = 0;
+		if(!vote_candidate2(sg, v, br, e, bd0, bd3, s, score, cn, wn)) continue;
+		if(be < 0) { be = e; o.type[c] = 2; o.strand[c] = s; o.score[c] = score; o.clen[c] = cn; o.wlen[c] = wn; o.pick[c] = e; }
 		choices++;
 	}
-	if(be < 0) return;
-	o.type[c] = type; o.strand[c] = best_strand; o.choices[c] = choices; o.score[c] = best_score;
-	o.clen[c] = best_cn; o.wlen[c] = best_wn; o.pick[c] = be;
+	if(be >= 0) o.choices[c] = choices;
 }
 
 // ---- update_bridges (rnacore/bundle_base.cc:420-507) for every bridged cluster, as looped in meta/bundle.cc:73-79

@@ -506,10 +506,11 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
-	const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	int nb_ = *n_big;
 	if(nb_ > big_cap) nb_ = big_cap;
-	if(w >= nb_) return;
+	const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+	for(int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nb_; w += n_warps)
+	{
 	const int64_t f = big_list[w];
 	const int b = find_segment(frg_off, n_bundles, f);
 	const int64_t f0 = frg_off[b];
@@ -589,6 +590,8 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 		__syncwarp();
 	}
 	for(int i = lane; i < n; i += 32) members[mo + i] = (int32_t)(u32)(el[i] & 0xffffffffULL);
+	__syncwarp();
+	}
 }
 #endif
 

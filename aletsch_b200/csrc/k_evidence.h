@@ -657,8 +657,10 @@ KERNEL k_covc_tile_cover(const int32_t *diffc, int64_t n, int64_t n_tiles, const
 
 // segments in order: border i with cov[i] > 0 opens [posc[i], posc[i + 1]) with value cov[i]; also seg_off[b] = number of
 // segments before the first border of bundle b
+// seg_head[o] = 0 if segment o does not touch its predecessor (it opens a run of region::build_join_interval_map), else -1;
+// seg_prod[o] = (r - l) * c in int32 arithmetic (the summand of compute_sum_overlap)
 KERNEL k_covc_emit(const int32_t *cov, const int32_t *posc, int64_t n, int64_t n_tiles, const int64_t *tile_off, int32_t n_bundles,
-		const int64_t *bord_off, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c, int64_t *seg_off)
+		const int64_t *bord_off, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c, int64_t *seg_off, int32_t *seg_head, int32_t *seg_prod)
 {
 	SHARED int f[CTILE + 1];
 	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
@@ -679,9 +681,14 @@ KERNEL k_covc_emit(const int32_t *cov, const int32_t *posc, int64_t n, int64_t n
 			int64_t g = g0 + i;
 			if(g >= n || cov[g] <= 0) continue;
 			int64_t o = o0 + f[i];
-			seg_l[o] = posc[g];
-			seg_r[o] = g + 1 < n ? posc[g + 1] : posc[g];
-			seg_c[o] = cov[g];
+			int32_t pl = posc[g], pr = g + 1 < n ? posc[g + 1] : posc[g], c = cov[g];
+			seg_l[o] = pl;
+			seg_r[o] = pr;
+			seg_c[o] = c;
+			// the previous segment ends at this border iff the previous border opened a segment (a bundle's coverage returns
+			// to 0 at its last border, so this never links two bundles)
+			seg_head[o] = (g > 0 && cov[g - 1] > 0) ? -1 : 0;
+			seg_prod[o] = (int32_t)((u32)(pr - pl) * (u32)c);
 		}
 		// bundles whose first border falls into this tile (the last tile also owns rank n)
 		int64_t hi = (t == n_tiles - 1) ? n + 1 : g0 + CTILE;
@@ -690,6 +697,23 @@ KERNEL k_covc_emit(const int32_t *cov, const int32_t *posc, int64_t n, int64_t n
 			seg_off[b] = o0 + f[bord_off[b] - g0];
 		BLOCK_SYNC();
 	}
+}
+
+// heads[k] = index of the k-th run-opening segment (heads[total] = n)
+KERNEL k_seg_heads(int64_t n, const int32_t *seg_head, const int64_t *hrank, int64_t *heads)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i > n) return;
+	if(i == n) { heads[hrank[n]] = n; return; }
+	if(seg_head[i] >= 0) heads[hrank[i]] = i;
+}
+
+// nhead[i] = first run-opening segment after i
+KERNEL k_seg_nhead(int64_t n, const int64_t *hrank, const int64_t *heads, int64_t *nhead)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	nhead[i] = heads[hrank[i + 1]];
 }
 
 } // namespace agpu

@@ -56,6 +56,7 @@ struct graph_in
 	chains_view hc, fc;
 	const int64_t *seg_off;
 	const int32_t *seg_l, *seg_r, *seg_c;
+	const int64_t *seg_nhead, *seg_psum;   // batch-wide side tables (coverage_scan): next run-opening segment, prefix sums of len * cov
 };
 
 struct graph_dev
@@ -108,7 +109,7 @@ KERNEL k_graph_bounds(graph_in in, int64_t *ub_junc, int64_t *ub_pex, int64_t *u
 			ub_junc[b] = J;
 			ub_pex[b] = P;
 			ub_edge[b] = J + 3 * P + 2;
-			ub_iarena[b] = (nh + nf) + 20 * ninst + 10 * P + 2 * S + 136;
+			ub_iarena[b] = (nh + nf) + 20 * ninst + 10 * P + 128;
 			ub_karena[b] = 6 * ninst + (J + 3 * P + 2) + 64;
 		}
 		BLOCK_SYNC();
@@ -119,8 +120,9 @@ struct seg_view
 {
 	const int32_t *l, *r, *c;
 	int n;
-	const int32_t *nhead;      // nhead[i] = first index > i whose segment does not touch its predecessor (n if none)
-	const u32 *psum;           // psum[i] = sum over segments < i of (r - l) * c in 32-bit wrap arithmetic (n + 1 entries)
+	const int64_t *nhead;      // nhead[i] - base = first index > i whose segment does not touch its predecessor (<= n)
+	const int64_t *psum;       // psum[i] = sum over the batch's segments before i of the int32 products (r - l) * c
+	int64_t base;              // index of the bundle's first segment in the batch-wide tables
 };
 
 // locate_boundary_iterators (rnacore/interval_map.cc:70-87): index range of the segments lying fully inside [x, y)
@@ -134,7 +136,7 @@ DEV bool segs_inside(const seg_view &s, int32_t x, int32_t y, int &i0, int &i1)
 }
 
 // compute_sum_overlap (rnacore/interval_map.cc:128-149) over the segments a..e: int32 arithmetic
-DEV int32_t seg_sum(const seg_view &s, int a, int e) { return (int32_t)(s.psum[e + 1] - s.psum[a]); }
+DEV int32_t seg_sum(const seg_view &s, int a, int e) { return (int32_t)(u32)(unsigned long long)(s.psum[e + 1] - s.psum[a]); }
 
 // evaluate_rectangle (rnacore/interval_map.cc:166-195) over [ll, rr) whose inside segments are a..e (none if e < a)
 DEV void evaluate_rectangle(const seg_view &s, int32_t ll, int32_t rr, int a, int e, double &ave, double &dev, double &mx)
@@ -209,7 +211,7 @@ struct run_iter
 	{
 		if(!any || i > i1) return false;
 		a = i;
-		e = s.nhead[i] - 1;                                // touching segments join (all values are 1)
+		e = (int)(s.nhead[i] - s.base) - 1;                // touching segments join (all values are 1)
 		if(e > i1) e = i1;
 		l = s.l[a]; r = s.r[e];
 		i = e + 1;
@@ -320,32 +322,8 @@ KERNEL k_graph_build(const int32_t *order, int n_order, graph_in in, graph_dev g
 		sv.n = (int)(in.seg_off[b + 1] - in.seg_off[b]);
 		const int nh = in.hc.count(b), nf = in.fc.count(b), nch = nh + nf;
 
-		// ---- segment side tables: run structure (touching segments) and prefix sums of len * cov
-		{
-			const int S = sv.n;
-			int32_t *nhead = ia; ia += S + 1;
-			u32 *psum = (u32*)ia; ia += S + 2;
-			// reverse running minimum of "next index that starts a run", as an inclusive max-scan of the negated candidates
-			for(int k = t; k < S; k += nt)
-			{
-				int i = S - 1 - k;
-				nhead[k] = (i + 1 < S && sv.l[i + 1] != sv.r[i]) ? -(i + 1) : -S;
-				psum[i] = (u32)(sv.r[i] - sv.l[i]) * (u32)sv.c[i];
-			}
-			BLOCK_SYNC();
-			block_incl_maxscan(nhead, S);
-			// un-reverse in place (pairwise swap) and negate
-			for(int k = t; k < (S + 1) / 2; k += nt)
-			{
-				int x = nhead[k], y = nhead[S - 1 - k];
-				nhead[k] = -y; nhead[S - 1 - k] = -x;
-			}
-			BLOCK_SYNC();
-			int tot = block_excl_scan((int*)psum, S);
-			if(t == 0) psum[S] = (u32)tot;
-			BLOCK_SYNC();
-			sv.nhead = nhead; sv.psum = psum;
-		}
+		sv.base = in.seg_off[b];
+		sv.nhead = in.seg_nhead + sv.base; sv.psum = in.seg_psum + sv.base;
 
 		// ---- junction instances in the order build_junctions feeds jcst: hcst chains, then fcst chains
 		int32_t *ci = ia; ia += nch + 1;
