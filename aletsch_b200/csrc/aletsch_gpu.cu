@@ -594,14 +594,16 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	int64_t nh = b->nh, nc = b->nc;
 	TRY(b->b_lpos.alloc(ctx, nb + 1)); TRY(b->b_rpos.alloc(ctx, nb + 1)); TRY(b->b_covhi.alloc(ctx, nb + 1));
 	TRY(b->b_strand.alloc(ctx, nb + 1)); TRY(b->b_span.alloc(ctx, nb + 1)); TRY(b->cov_base.alloc(ctx, nb + 2));
-	LAUNCH_B(ctx, k_bundle_bounds, nb, 128, b->h, p->library_type, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, b->b_strand.p, b->b_span.p, b->err.p);
+	TRY(b->hit_bundle.alloc(ctx, nh + 1));
+	LAUNCH_B(ctx, k_bundle_bounds, nb, 128, b->h, p->library_type, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, b->b_strand.p, b->b_span.p,
+			b->hit_bundle.p, b->err.p);
 	LAUNCH_B(ctx, k_scan_i64, 1, 1024, b->b_span.p, b->cov_base.p, nb);
 	b->ltot = 0;
 	TRY(d2h(ctx, &b->ltot, b->cov_base.p + nb, sizeof(int64_t)));
 	TRY(stream_sync(ctx));
 	if(b->ltot >= ((int64_t)1 << 32) - 64) { ctx->last_error = "batch spans 2^32 or more window positions: split it"; return AGPU_ERR_CAPACITY; }
 	TRY(b->border.alloc(ctx, b->ltot / 32 + 8, true));
-	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1)); TRY(b->hit_bundle.alloc(ctx, nh + 1)); TRY(b->hit_hash.alloc(ctx, nh + 1));
+	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1)); TRY(b->hit_hash.alloc(ctx, nh + 1));
 	dbuf<int32_t> n_spliced;
 	TRY(n_spliced.alloc(ctx, nb + 1, true));
 	LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_hash.p,

@@ -401,18 +401,39 @@ struct entry_less
 	}
 };
 
-// ---- B3: bottleneck top-K DP, one thread per (pier group, strand pass) (dynamic_programming :484-530)
-KERNEL k_bridge_dp(int64_t n_slots, int32_t n_bundles, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand, bridge_dev br)
+// dense work lists of the bridging kernels: DP jobs = (pier group, strand pass), trace-back jobs = piers
+KERNEL k_bridge_job_counts(int64_t nb, const uint8_t *b_strand, bridge_dev br, int64_t *n_dp, int64_t *n_pier)
 {
-	int64_t job = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(job >= 2 * n_slots) return;
+	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(b >= nb) return;
+	n_dp[b] = (int64_t)br.n_groups[b] * passes_of(b_strand[b]);
+	n_pier[b] = br.n_piers[b];
+}
+
+KERNEL k_bridge_job_fill(int64_t nb, const int64_t *clu_off, const uint8_t *b_strand, bridge_dev br, const int64_t *dp_off, const int64_t *pier_off,
+		int64_t *dp_job, int32_t *dp_bundle, int64_t *pier_job, int32_t *pier_bundle)
+{
+	int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(b >= nb) return;
+	int np = passes_of(b_strand[b]);
+	int64_t o = dp_off[b];
+	for(int gi = 0; gi < br.n_groups[b]; gi++)
+		for(int pass = 0; pass < np; pass++) { dp_job[o] = ((clu_off[b] + gi) << 1) | pass; dp_bundle[o] = (int32_t)b; o++; }
+	o = pier_off[b];
+	for(int pi = 0; pi < br.n_piers[b]; pi++) { pier_job[o] = clu_off[b] + pi; pier_bundle[o] = (int32_t)b; o++; }
+}
+
+// ---- B3: bottleneck top-K DP, one thread per (pier group, strand pass) (dynamic_programming :484-530)
+KERNEL k_bridge_dp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bundle, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand,
+		bridge_dev br)
+{
+	int64_t ji = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(ji >= n_jobs) return;
+	int64_t job = dp_job[ji];
 	int64_t slot = job >> 1;
 	int pass = (int)(job & 1);
-	int b = find_segment(clu_off, n_bundles, slot);
-	int gi = (int)(slot - clu_off[b]);
-	if(gi >= br.n_groups[b]) return;
+	int b = dp_bundle[ji];
 	sgraph sg = sgraph_of(g, b_strand, b);
-	if(pass >= passes_of(sg.strand)) return;
 	int strand = pass_strand(sg.strand, pass);
 	const int K = br.K, D = br.D, W = D + 3;
 	int k1 = br.g_k1[slot], k2 = br.g_k2[slot];
@@ -515,14 +536,14 @@ struct stack_greater           // compare_bridge_path_stack (bridge/bridge_path.
 };
 
 // ---- B4: trace back, build the candidate bridges of every pier and order them (nominate :224-257, refine_pier :259-274)
-KERNEL k_pier_bridges(int64_t n_slots, int32_t n_bundles, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand, bridge_dev br)
+KERNEL k_pier_bridges(int64_t n_jobs, const int64_t *pier_job, const int32_t *pier_bundle, const int64_t *clu_off, graph_dev g,
+		const uint8_t *b_strand, bridge_dev br)
 {
-	int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(slot >= n_slots) return;
-	int b = find_segment(clu_off, n_bundles, slot);
+	int64_t ji = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(ji >= n_jobs) return;
+	int64_t slot = pier_job[ji];
+	int b = pier_bundle[ji];
 	int64_t c0 = clu_off[b];
-	int pi = (int)(slot - c0);
-	if(pi >= br.n_piers[b]) return;
 	sgraph sg = sgraph_of(g, b_strand, b);
 	const int K = br.K, D = br.D;
 	int bs = br.p_bs[slot], bt = br.p_bt[slot];

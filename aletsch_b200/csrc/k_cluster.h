@@ -79,11 +79,11 @@ struct chain_paths
 // records own disjoint windows of len + 2 ints
 HD int64_t run_base(int64_t rep_elem, int64_t voff) { return voff + 2 * rep_elem; }
 
-KERNEL k_chain_paths(int64_t n_elem, int32_t n_bundles, chains_view cv, graph_dev g, chain_paths cp)
+KERNEL k_chain_paths(int64_t n_elem, const int32_t *elem_bundle, chains_view cv, graph_dev g, chain_paths cp)
 {
 	int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(e >= n_elem) return;
-	int b = find_segment(cv.elem_off, n_bundles, e);
+	int b = elem_bundle[e];
 	int k = (int)(e - cv.elem_off[b]);
 	if(k >= cv.n_chains[b]) return;
 	gview gv = graph_of(g, b);
@@ -182,7 +182,7 @@ DEV u64 path_hash(const mate_path &x, u64 h)
 }
 
 // ---- C1: align both mates of every to-be-bridged fragment; frgs[i][2] := -1, then 0 if both align
-KERNEL k_frag_align(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+KERNEL k_frag_align(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
 		int32_t *f_type, chains_view cv, chain_paths cp, const int32_t *handle_chain, graph_dev g, cluster_dev c)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,7 +191,7 @@ KERNEL k_frag_align(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hi
 	c.f_slot[f] = -1;
 	if(f_type[f] != 0) return;                    // only unbridged fragments are grouped (:37-38)
 	f_type[f] = -1;
-	int b = find_segment(frg_off, n_bundles, f);
+	int b = f_bundle[f];
 	int64_t h0 = h.bundle_hit_off[b];
 	int64_t i1 = h0 + f_h1[f], i2 = h0 + f_h2[f];
 	if(h.pos[i1] > h.pos[i2]) return;
@@ -232,13 +232,13 @@ KERNEL k_frag_align(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hi
 }
 
 // ---- C2: group by (path1, path2): per-bundle table, exact comparison against the slot's first claimer
-KERNEL k_frag_group(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+KERNEL k_frag_group(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
 		chains_view cv, chain_paths cp, const int32_t *handle_chain, cluster_dev c, int *err)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(f >= n_frg) return;
 	if(!c.f_ok[f]) return;
-	int b = find_segment(frg_off, n_bundles, f);
+	int b = f_bundle[f];
 	int64_t h0 = h.bundle_hit_off[b];
 	int64_t r0 = c.reg_off[b];
 	u32 mask = (u32)(c.reg_off[b + 1] - r0) - 1;
@@ -272,7 +272,7 @@ KERNEL k_frag_group(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hi
 #define LANE_RANGE 48           // inside the warp kernel, ranges up to this size are sorted by a single lane
 
 // small_list / big_list: the leaders packed densely (any order), so that the partition kernels run with full warps
-KERNEL k_group_leaders(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, cluster_dev c, int32_t *leader, int32_t *leader_size,
+KERNEL k_group_leaders(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, cluster_dev c, int32_t *leader, int32_t *leader_size,
 		int32_t *n_big, int32_t *big_list, int32_t big_cap, int32_t *n_small, int32_t *small_list)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -285,7 +285,7 @@ KERNEL k_group_leaders(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off,
 		int64_t sl = c.f_slot[f];
 		if(sl >= 0)
 		{
-			int b = find_segment(frg_off, n_bundles, f);
+			int b = f_bundle[f];
 			if(c.slot_min[sl] == (int32_t)(f - frg_off[b]))
 			{
 				lead = true;
@@ -400,14 +400,14 @@ template<int R> DEV void partition_rec(const part_ctx &c, int lo, int hi)
 template<> DEV void partition_rec<4>(const part_ctx &c, int lo, int hi) { (void)hi; c.cflag[lo] = 1; }
 
 // ---- C3: the first fragment of every group gathers the members (ascending fragment index) and partitions them
-KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+KERNEL k_group_partition(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
 		cluster_dev c, const int32_t *n_small, const int32_t *small_list, const int64_t *member_off, int32_t *members, u64 *elems,
 		int32_t *cflag, int gap)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n_frg || i >= *n_small) return;
 	const int64_t f = small_list[i];                 // groups above BIG_GROUP members are handled by k_group_partition_warp
-	int b = find_segment(frg_off, n_bundles, f);
+	int b = f_bundle[f];
 	int64_t f0 = frg_off[b];
 	int64_t sl = c.f_slot[f];
 	int n = c.slot_n[sl];
@@ -500,7 +500,7 @@ KERNEL k_group_partition(int64_t n_frg, int32_t n_bundles, const int64_t *frg_of
 // permutation (big ranges by the whole warp, small ones one lane each), then open a new range wherever the gap
 // between neighbours exceeds max_reads_partition_gap.  Range starts are flags by position, so the clusters come
 // out in the same left-to-right order as the reference's recursion.
-__global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_list, int32_t big_cap, int32_t n_bundles, const int64_t *frg_off,
+__global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_list, int32_t big_cap, const int32_t *f_bundle, const int64_t *frg_off,
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, cluster_dev c, const int64_t *member_off, int32_t *members, u64 *elems,
 		int32_t *cflag, int32_t *scratch, int gap)
 {
@@ -512,7 +512,7 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 	for(int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nb_; w += n_warps)
 	{
 	const int64_t f = big_list[w];
-	const int b = find_segment(frg_off, n_bundles, f);
+	const int b = f_bundle[f];
 	const int64_t f0 = frg_off[b];
 	const int nfb = (int)(frg_off[b + 1] - f0);
 	const int64_t sl = c.f_slot[f];

@@ -42,7 +42,7 @@ enum { ERR_ORDER = 0, ERR_DUP, ERR_STRAND, ERR_RPOS, ERR_LINK, ERR_QID, ERR_CAP,
 
 // ---- E0: bundle bounds (bundle_base::add_hit) + packing-contract check; one CTA per bundle
 KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b_rpos, int32_t *b_covhi,
-		uint8_t *b_strand, int64_t *b_span, int *err)
+		uint8_t *b_strand, int64_t *b_span, int32_t *hit_bundle, int *err)
 {
 	SHARED int s_min, s_max, s_cov, s_np, s_nq;
 	for(int b = blockIdx.x; b < h.n_bundles; b += gridDim.x)
@@ -54,6 +54,7 @@ KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b
 		for(int64_t i = h0 + threadIdx.x; i < h1; i += blockDim.x)
 		{
 			int p = h.pos[i], r = h.rpos[i], m = h.mpos[i];
+			hit_bundle[i] = b;
 			if(p < lmin) lmin = p;
 			int q = r;
 			if(m > r && m <= r + 500000) q = m;            // rnacore/bundle_base.cc:92
@@ -192,12 +193,11 @@ HD u64 chain_hash(const int32_t *v, int n)
 //             k_cov_add once the borders have been ranked, see the coverage section below)
 //   splices : (p - len, p) for every inner BAM_CREF_SKIP, written at spl[cigar_off[i] ...]
 KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
-		int32_t *spl, int32_t *hit_nspl, u64 *hit_hash, int32_t *hit_bundle, int32_t *n_spliced, int *err)
+		int32_t *spl, int32_t *hit_nspl, u64 *hit_hash, const int32_t *hit_bundle, int32_t *n_spliced, int *err)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
-	int b = find_segment(h.bundle_hit_off, h.n_bundles, i);
-	hit_bundle[i] = b;
+	int b = hit_bundle[i];
 	int64_t base = cov_base[b] - (int64_t)b_lpos[b];
 	u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
 	int32_t p = h.pos[i];

@@ -155,12 +155,14 @@ KERNEL k_flag_tile_rank(const int32_t *v, int64_t n, int64_t n_tiles, const int6
 	}
 }
 
-KERNEL k_frag_emit(hits_dev h, const int32_t *hit_bundle, const int32_t *mate, const int64_t *rank, int32_t *f_h1, int32_t *f_h2, int32_t *f_type)
+KERNEL k_frag_emit(hits_dev h, const int32_t *hit_bundle, const int32_t *mate, const int64_t *rank, int32_t *f_h1, int32_t *f_h2, int32_t *f_type,
+		int32_t *f_bundle)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
 	if(mate[i] < 0) return;
 	int64_t f = rank[i];
+	f_bundle[f] = hit_bundle[i];
 	f_h1[f] = (int32_t)(i - h.bundle_hit_off[hit_bundle[i]]);
 	f_h2[f] = mate[i];
 	f_type[f] = 0;
@@ -181,7 +183,7 @@ struct fragments_state
 	agpu::dbuf<agpu::u64> slots;
 	agpu::dbuf<int32_t> next, cursor, members, mate, tile_cnt;
 	agpu::dbuf<int64_t> hit_qslot, tile_off, rank, frg_off;
-	agpu::dbuf<int32_t> f_h1, f_h2, f_type, bridged;
+	agpu::dbuf<int32_t> f_h1, f_h2, f_type, f_bundle, bridged;
 	int64_t n_frg = 0;
 	std::vector<int64_t> frg_off_host;
 
@@ -190,7 +192,7 @@ struct fragments_state
 		slots.release(ctx); next.release(ctx);
 		cursor.release(ctx); members.release(ctx); mate.release(ctx); tile_cnt.release(ctx);
 		hit_qslot.release(ctx); tile_off.release(ctx); rank.release(ctx); frg_off.release(ctx);
-		f_h1.release(ctx); f_h2.release(ctx); f_type.release(ctx); bridged.release(ctx);
+		f_h1.release(ctx); f_h2.release(ctx); f_type.release(ctx); f_bundle.release(ctx); bridged.release(ctx);
 		built = false; n_frg = 0;
 	}
 };
