@@ -243,6 +243,7 @@ def run_ours(args):
     prof = ctx.profile_read()
     ctx.profile(False)
     counts = bt.counts()
+    per_bundle = bt.bundle_counts()          # [NB, 4]: segments, fragments, clusters, bridged pairs
     stage5 = stage5_gpu(ctx, bt, batch, args) if not args.no_stage5 else None
     bt.free()
 
@@ -359,7 +360,7 @@ def run_ours(args):
         if stage5 is not None:
             out["stage5"] = stage5
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(batch, min(10, ncpu), args.cpu_seconds)
+            out["cpu_baseline"] = cpu_baseline(batch, min(10, ncpu), args.cpu_seconds, gpu_bridged=per_bundle[:, 3])
             if stage5 is not None:
                 out["stage5"]["cpu_baseline"] = stage5_cpu(batch, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
         emit(out)
@@ -466,7 +467,7 @@ def stage5_cpu(batch, threads, budget_s):
             "bundles_per_sec": nbun / max(wall, 1e-9), "pairs_per_sec": pairs / max(wall, 1e-9)}
 
 
-def cpu_baseline(batch, threads, budget_s, all_cores=False):
+def cpu_baseline(batch, threads, budget_s, all_cores=False, gpu_bridged=None):
     """the reference's own C++ (oracle/_ref) over a bounded sample of the same bundles, one bundle per task
     on a pool of `threads` workers (the granularity of aletsch -t N, meta/incubator.cc:615-635)"""
     import orclib
@@ -488,6 +489,7 @@ def cpu_baseline(batch, threads, budget_s, all_cores=False):
     lock = threading.Lock()
     nxt = [0]
     bridged = [0]
+    per = [0] * len(bundles)
 
     def worker():
         chk = orclib.Checker("ref" if kind == "reference" else "orc")
@@ -501,6 +503,7 @@ def cpu_baseline(batch, threads, budget_s, all_cores=False):
             chk.run_quiet(h, "fragments")
             c = chk.run_quiet(h, "bridge")
             chk.free_bundle(h)
+            per[i] = max(c, 0)
             with lock:
                 bridged[0] += max(c, 0)
 
@@ -511,9 +514,14 @@ def cpu_baseline(batch, threads, budget_s, all_cores=False):
     for t in ths:
         t.join()
     dt = time.time() - t0
-    return {"value": hits / dt, "unit": "hits/s", "cores": threads, "kind": kind,
-            "sample": "every %d-th bundle of the same batch: %d bundles, %d hits, %.1f s wall" % (step, len(bundles), hits, dt),
-            "bridged_pairs_per_sec": bridged[0] / dt}
+    out = {"value": hits / dt, "unit": "hits/s", "cores": threads, "kind": kind,
+           "sample": "every %d-th bundle of the same batch: %d bundles, %d hits, %.1f s wall" % (step, len(bundles), hits, dt),
+           "bridged_pairs_per_sec": bridged[0] / dt}
+    if gpu_bridged is not None:
+        # full-size cross-check: the bridged-pair count of every sampled bundle, CUDA path vs this CPU run
+        bad = [int(k) for k, c in zip(sample, per) if int(gpu_bridged[k]) != int(c)]
+        out["bridged_count_check"] = {"bundles": len(sample), "mismatches": len(bad), "first": bad[:5]}
+    return out
 
 
 def run_reference(args):

@@ -239,6 +239,9 @@ typedef struct agpu_counts
 	int64_t borders, cluster_members, bridge_chain_ints, bridge_whole_ints;   /* ranked coverage borders, sum of frlist sizes, sizes of opt[].chain / opt[].whole */
 } agpu_counts;
 int agpu_batch_counts(agpu_ctx *ctx, agpu_batch *b, agpu_counts *c);
+/* per bundle: out[4k..4k+3] = coverage segments (0 while the coverage map awaits its rebuild after agpu_batch_update), fragments,
+ * paired-read clusters, bridged pairs (sum of the update_bridges return values, rnacore/bundle_base.cc:460) */
+int agpu_batch_bundle_counts(agpu_ctx *ctx, agpu_batch *b, int64_t *out);
 
 /* ---- stage 5: junction-set similarity ------------------------------------------------ */
 /* G sorted splice lists (bundle::splices); for every pair i<j: c = |splices_i ∩ splices_j| and

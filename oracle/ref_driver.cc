@@ -144,7 +144,8 @@ void dump_frgs(bundle_base &bd, orc_bag &bag, const std::string &name)
 	}
 }
 
-void dump_builder(graph_builder &gb, parameters &cfg, orc_bag &bag, const std::string &pre)
+// returns, per partial exon, whether it is one of the 1-bp stubs whose `max` the reference never sets
+std::vector<char> dump_builder(graph_builder &gb, parameters &cfg, orc_bag &bag, const std::string &pre)
 {
 	std::vector<int32_t> &jc = bag.ints(pre + "junc");
 	jc.clear();
@@ -158,6 +159,7 @@ void dump_builder(graph_builder &gb, parameters &cfg, orc_bag &bag, const std::s
 	std::vector<int32_t> &pe = bag.ints(pre + "pexon");
 	std::vector<double> &pd = bag.reals(pre + "pexon_d");
 	pe.clear(); pd.clear();
+	std::vector<char> stubs(gb.pexons.size(), 0);
 	for(size_t i = 0; i < gb.pexons.size(); i++)
 	{
 		const partial_exon &p = gb.pexons[i];
@@ -166,11 +168,14 @@ void dump_builder(graph_builder &gb, parameters &cfg, orc_bag &bag, const std::s
 		// partial_exon::max is left uninitialised for the 1-bp stub pexons
 		// (rnacore/region.cc:118-121, :135-138, :162-165): report -1 there
 		bool stub = (p.rpos - p.lpos == 1 && p.ave == cfg.min_guaranteed_edge_weight && p.dev == 1.0);
+		stubs[i] = stub ? 1 : 0;
 		pd.push_back(p.ave); pd.push_back(p.dev); pd.push_back(stub ? -1.0 : p.max); pd.push_back(p.pvalue);
 	}
+	return stubs;
 }
 
-void dump_graph(splice_graph &gr, parameters &cfg, orc_bag &bag, const std::string &pre)
+// vertex i (inner) is partial exon i - 1 (rnacore/graph_builder.cc:305-341): its maxcov is unset exactly when the pexon's max is
+void dump_graph(splice_graph &gr, parameters &cfg, orc_bag &bag, const std::string &pre, const std::vector<char> &stubs)
 {
 	std::vector<int32_t> &vi = bag.ints(pre + "vert");
 	std::vector<double> &vd = bag.reals(pre + "vert_d");
@@ -184,7 +189,7 @@ void dump_graph(splice_graph &gr, parameters &cfg, orc_bag &bag, const std::stri
 		double w = gr.get_vertex_weight(i);
 		vi.push_back(v.lpos); vi.push_back(v.rpos); vi.push_back(v.length); vi.push_back(v.type);
 		vi.push_back(v.regional ? 1 : 0);
-		bool stub = (i != 0 && i != n - 1 && v.rpos - v.lpos == 1 && w == cfg.min_guaranteed_edge_weight && v.stddev == 1.0);
+		bool stub = (i != 0 && i != n - 1 && (size_t)(i - 1) < stubs.size() && stubs[i - 1]);
 		vd.push_back(w); vd.push_back(v.stddev); vd.push_back(stub ? -1.0 : v.maxcov);
 	}
 	for(int i = 0; i < n; i++)
@@ -340,8 +345,7 @@ int ref_bundle_graph(void *b, void *bagp)
 	graph_builder gb(h->bd, h->cfg, h->sp);
 	gb.build(gr);
 	gr.build_vertex_index();
-	dump_builder(gb, h->cfg, bag, "");
-	dump_graph(gr, h->cfg, bag, "");
+	dump_graph(gr, h->cfg, bag, "", dump_builder(gb, h->cfg, bag, ""));
 	return 0;
 }
 
@@ -353,8 +357,7 @@ int ref_bundle_bridge(void *b, void *bagp)
 	graph_builder gb(h->bd, h->cfg, h->sp);
 	gb.build(gr);
 	gr.build_vertex_index();
-	dump_builder(gb, h->cfg, bag, "");
-	dump_graph(gr, h->cfg, bag, "");
+	dump_graph(gr, h->cfg, bag, "", dump_builder(gb, h->cfg, bag, ""));
 	return cluster_solve_update(gr, h->bd, h->cfg, bag, "", false);
 }
 
@@ -392,8 +395,7 @@ int ref_group_bridge(void **bs, int n, void *bagp)
 	graph_builder gb(cb, h0->cfg, cb.sp);
 	gb.build(gr);
 	gr.build_vertex_index();
-	dump_builder(gb, h0->cfg, bag, "cb_");
-	dump_graph(gr, h0->cfg, bag, "cb_");
+	dump_graph(gr, h0->cfg, bag, "cb_", dump_builder(gb, h0->cfg, bag, "cb_"));
 
 	int total = 0;
 	for(int k = 0; k < n; k++)

@@ -95,6 +95,14 @@ def test_group_resolve_batch_matches_single(ctx):
         assert g == want
 
 
+def test_fuzz_bundles(ctx, checkers):
+    """adversarial random bundles (tests/fuzz.py), small and large (big qname / cluster groups reach the warp kernels)"""
+    import test_fuzz
+    test_fuzz.run_seeds(ctx, checkers, range(24))
+    test_fuzz.run_seeds(ctx, checkers, range(100, 104), big=True)
+    test_fuzz.run_degenerate(ctx, checkers)
+
+
 def test_std_sort_permutation(ctx):
     """the device re-implementation of libstdc++'s introsort against the real std::sort on heavily tied keys"""
     import ctypes as C
