@@ -327,6 +327,15 @@ def run_ours(args):
             if ab is not None:
                 dom = (name, ms, cnt, ab)
                 break
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this build (profiles/), if any
+        traffic = {}
+        try:
+            import glob
+            tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+            if tf:
+                traffic = json.load(open(tf[-1]))
+        except (OSError, ValueError):
+            traffic = {}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -339,11 +348,14 @@ def run_ours(args):
             per_launch_ms = ms / cnt
             launches_per_step = cnt / steps
             achieved = ab / launches_per_step / (per_launch_ms / 1e3) / 1e9
+            tk = traffic.get("kernels", {}).get(name)
+            traffic_per_launch = (tk["dram_read_bytes"] + tk["dram_write_bytes"]) / tk["launches"] if tk else None
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "algorithmic_bytes_per_launch": ab / launches_per_step, "ms_per_launch": per_launch_ms,
                     "launches_per_step": launches_per_step,
-                    "share_of_kernel_time": ms / max(total_k, 1e-9), "ms_per_step_profiled": ms_prof / steps, "traffic": None}
+                    "share_of_kernel_time": ms / max(total_k, 1e-9), "ms_per_step_profiled": ms_prof / steps, "traffic": traffic_per_launch,
+                    "traffic_source": os.path.basename(tf[-1]) if (tk and tf) else None}
         out = {"metric": "hits_per_sec", "value": value, "unit": "hits/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
                "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
                "data": "synthetic", "impl": "ours",
