@@ -260,6 +260,8 @@ void agpu_destroy(agpu_ctx *ctx)
 	AGPU_ENTER(ctx);
 #ifndef AGPU_EMU
 	cudaStreamSynchronize(ctx->stream);
+	arena_destroy(ctx);
+	cudaStreamSynchronize(ctx->stream);
 	if(ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
 	if(ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
 	if(ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
@@ -368,6 +370,7 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.pos = b->in_pos.p; b->h.rpos = b->in_rpos.p; b->h.mpos = b->in_mpos.p; b->h.isize = b->in_isize.p;
 	b->h.flag = NULL; b->h.strand = b->in_strand.p; b->h.bundle_strand = b->in_bstrand.p; b->h.xs = b->in_xs.p; b->h.qid = (const u64*)b->in_qid.p;
 	b->h.cigar_off = b->in_cigar_off.p; b->h.cigar = b->in_cigar.p;
+	if(ctx->arena_owner == NULL) ctx->arena_owner = b;
 	if(!in->rpos)
 	{
 		// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), derived on the device
@@ -401,6 +404,7 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.flag = in->flag; b->h.strand = in->strand; b->h.bundle_strand = in->bundle_strand; b->h.xs = in->xs; b->h.qid = (const u64*)in->qid;
 	b->h.cigar_off = in->cigar_off; b->h.cigar = in->cigar;
 	if(!in->strand && !in->bundle_strand) { agpu_batch_free(ctx, b); return AGPU_ERR_ARG; }
+	if(ctx->arena_owner == NULL) ctx->arena_owner = b;
 	if(!in->rpos)
 	{
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
@@ -435,6 +439,7 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 	b->in_cigar_off.release(ctx); b->in_cigar.release(ctx);
 	b->err.release(ctx); b->order.release(ctx); b->qreg_off.release(ctx);
 	stream_sync(ctx);
+	if(ctx->arena_owner == b) { ctx->arena.rewind(); ctx->arena_owner = NULL; }
 	for(auto &r : b->pinned) r.second.release();
 	delete b;
 }
@@ -444,6 +449,7 @@ int agpu_batch_reset(agpu_ctx *ctx, agpu_batch *b)
 	if(!ctx || !b) return AGPU_ERR_ARG;
 	AGPU_ENTER(ctx);
 	release_derived(ctx, b);
+	if(ctx->arena_owner == b) ctx->arena.rewind();
 	TRY(b->err.fill(ctx, 0));
 	return AGPU_OK;
 }
@@ -589,6 +595,7 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 {
 	if(!ctx || !b || !p) return AGPU_ERR_ARG;
 	AGPU_ENTER(ctx);
+	AGPU_BATCH_SCOPE(ctx, b);
 	if(b->evidence) return AGPU_OK;
 	int nb = b->nb;
 	int64_t nh = b->nh, nc = b->nc;
@@ -627,6 +634,7 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 {
 	if(!ctx || !b || !p) return AGPU_ERR_ARG;
 	AGPU_ENTER(ctx);
+	AGPU_BATCH_SCOPE(ctx, b);
 	if(!b->evidence) return AGPU_ERR_ARG;
 	if(b->cov_dirty) TRY(coverage_scan(ctx, b));
 	graph_state &gs = b->gr;

@@ -9,7 +9,25 @@
 #include <string>
 #include <vector>
 
+struct agpu_batch;
 struct agpu_prof_rec { const char *name; void *e0, *e1; };
+
+// Bump arena for the derived state of ONE batch per context: a few large slabs taken from the stream-ordered pool once and
+// kept for the context's lifetime.  The stages allocate ~150 arrays per step; bumping a pointer instead of going through
+// cudaMallocAsync / cudaFreeAsync removes that API time and, with several contexts working side by side (pipeline.py), the
+// cross-stream reuse dependencies of the shared pool.  Individual frees are no-ops; the arena rewinds at batch reset / free.
+struct agpu_arena
+{
+	struct slab { char *base; size_t size; };
+	std::vector<slab> slabs;
+	size_t cur = 0, off = 0;
+	bool contains(const void *p) const
+	{
+		for(size_t k = 0; k < slabs.size(); k++) if((const char*)p >= slabs[k].base && (const char*)p < slabs[k].base + slabs[k].size) return true;
+		return false;
+	}
+	void rewind() { cur = 0; off = 0; }
+};
 
 struct agpu_ctx
 {
@@ -19,6 +37,9 @@ struct agpu_ctx
 	int64_t launches;
 	std::string last_error;
 	int sm_count;
+	agpu_arena arena;
+	agpu_batch *arena_owner = NULL;     // the batch whose stages allocate from the arena
+	bool arena_on = false;              // set while a stage of the owner runs
 	// side stream: runs the few-but-long launches of a size-binned kernel pair next to the bulk launch on `stream`
 	cudaStream_t side = NULL;
 	void *ev_fork = NULL, *ev_join = NULL;
@@ -89,16 +110,59 @@ inline void prof_collect(agpu_ctx *ctx)
 #define LAUNCH_B(ctx, kern, nblocks, nthreads, ...) do { int64_t n_ = (int64_t)(nblocks); if(n_ > 0) { unsigned g_ = (unsigned)(n_ > 1048576 ? 1048576 : n_); \
 	prof_begin(ctx, #kern); kern<<<g_, (nthreads), 0, (ctx)->stream>>>(__VA_ARGS__); prof_end(ctx); (ctx)->launches++; } } while(0)
 
+#define AGPU_SLAB_BYTES ((size_t)1 << 30)
+inline void *arena_alloc(agpu_ctx *ctx, size_t bytes)
+{
+	agpu_arena &a = ctx->arena;
+	bytes = (bytes + 255) & ~(size_t)255;
+	while(true)
+	{
+		if(a.cur < a.slabs.size())
+		{
+			if(a.off + bytes <= a.slabs[a.cur].size) { void *p = a.slabs[a.cur].base + a.off; a.off += bytes; return p; }
+			a.cur++; a.off = 0;
+			continue;
+		}
+		agpu_arena::slab s;
+		s.size = bytes > AGPU_SLAB_BYTES ? bytes : AGPU_SLAB_BYTES;
+		void *base = NULL;
+		if(cudaMallocAsync(&base, s.size, ctx->stream) != cudaSuccess) { cudaGetLastError(); return NULL; }
+		s.base = (char*)base;
+		a.slabs.push_back(s);
+	}
+}
 inline int dev_alloc_bytes(agpu_ctx *ctx, void **p, size_t bytes, bool zero)
 {
 	*p = NULL;
 	if(bytes == 0) bytes = 16;
-	cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
-	if(e != cudaSuccess) { ctx->last_error = std::string("cudaMallocAsync: ") + cudaGetErrorString(e); cudaGetLastError(); return AGPU_ERR_OOM; }
+	cudaError_t e = cudaSuccess;
+	if(ctx->arena_on)
+	{
+		*p = arena_alloc(ctx, bytes);
+		if(!*p) { ctx->last_error = "arena slab allocation failed"; return AGPU_ERR_OOM; }
+	}
+	else
+	{
+		e = cudaMallocAsync(p, bytes, ctx->stream);
+		if(e != cudaSuccess) { ctx->last_error = std::string("cudaMallocAsync: ") + cudaGetErrorString(e); cudaGetLastError(); return AGPU_ERR_OOM; }
+	}
 	if(zero) { e = cudaMemsetAsync(*p, 0, bytes, ctx->stream); if(e != cudaSuccess) { ctx->last_error = cudaGetErrorString(e); return AGPU_ERR_CUDA; } }
 	return AGPU_OK;
 }
-inline void dev_free_bytes(agpu_ctx *ctx, void *p) { if(p) cudaFreeAsync(p, ctx->stream); }
+inline void dev_free_bytes(agpu_ctx *ctx, void *p) { if(p && !ctx->arena.contains(p)) cudaFreeAsync(p, ctx->stream); }
+inline void arena_destroy(agpu_ctx *ctx)
+{
+	for(size_t k = 0; k < ctx->arena.slabs.size(); k++) cudaFreeAsync(ctx->arena.slabs[k].base, ctx->stream);
+	ctx->arena.slabs.clear(); ctx->arena.rewind();
+}
+// stage entry / exit of a batch: its allocations come from the arena while it owns it
+struct arena_scope
+{
+	agpu_ctx *ctx;
+	arena_scope(agpu_ctx *c, agpu_batch *b) : ctx(c) { c->arena_on = (b != NULL && c->arena_owner == b); }
+	~arena_scope() { ctx->arena_on = false; }
+};
+#define AGPU_BATCH_SCOPE(ctx, b) arena_scope arena_scope_(ctx, b)
 inline int dev_fill(agpu_ctx *ctx, void *p, int byte, size_t bytes) { if(bytes == 0) return AGPU_OK; return cudaMemsetAsync(p, byte, bytes, ctx->stream) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA; }
 inline int h2d(agpu_ctx *ctx, void *d, const void *h, size_t bytes) { if(bytes == 0) return AGPU_OK; return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA; }
 inline int d2h(agpu_ctx *ctx, void *h, const void *d, size_t bytes) { if(bytes == 0) return AGPU_OK; return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA; }
@@ -132,7 +196,9 @@ template<typename F, typename... A> inline void emu_launch(bool coop, F f, int64
 }
 inline void side_fork(agpu_ctx *) {}
 inline void side_join(agpu_ctx *) {}
+inline void arena_destroy(agpu_ctx *) {}
 #define AGPU_ENTER(ctx) do {} while(0)
+#define AGPU_BATCH_SCOPE(ctx, b) do {} while(0)
 #define LAUNCH_T(ctx, kern, n, ...) do { int64_t n_ = (int64_t)(n); if(n_ > 0) { emu_launch(false, kern, (n_ + 255) / 256, 256, __VA_ARGS__); (ctx)->launches++; } } while(0)
 #define LAUNCH_B_SIDE(ctx, kern, nblocks, nthreads, ...) LAUNCH_B(ctx, kern, nblocks, nthreads, __VA_ARGS__)
 #define LAUNCH_B(ctx, kern, nblocks, nthreads, ...) do { int64_t n_ = (int64_t)(nblocks); if(n_ > 0) { emu_launch(true, kern, n_, (nthreads), __VA_ARGS__); (ctx)->launches++; } } while(0)

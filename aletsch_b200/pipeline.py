@@ -26,10 +26,10 @@ class Pipeline:
         for c in self.ctxs:
             c.sync()
 
-    def run(self, views, params, consume=None):
+    def run(self, views, params, consume=None, resident=False):
         """views: list of (agpu_batch_in with HOST pointers, keepalive).  Each batch goes through upload + bridge_all;
         consume(i, batch) may fetch results while the batch is still resident (default: the counters).  Returns the list of
-        per-batch results in input order."""
+        per-batch results in input order.  resident=True: the views hold DEVICE pointers (agpu_batch_adopt, no copy)."""
         out = [None] * len(views)
         nxt = [0]
         lock = threading.Lock()
@@ -44,7 +44,7 @@ class Pipeline:
                     if i >= len(views) or errs:
                         return
                     v, keep = views[i]
-                    bt = ctx.upload(v, keepalive=keep)
+                    bt = ctx.adopt(v, keepalive=keep) if resident else ctx.upload(v, keepalive=keep)
                     try:
                         bt.bridge_all(params)
                         out[i] = consume(i, bt) if consume else bt.counts()
