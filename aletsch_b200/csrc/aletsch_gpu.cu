@@ -8,6 +8,7 @@
 #include "k_cluster.h"
 #include "k_bridge.h"
 #include "k_similarity.h"
+#include "k_group.h"
 
 #include <algorithm>
 #include <atomic>
@@ -36,6 +37,12 @@ struct chainset_state
 	dbuf<u64> slot_word, key_scratch, key_scratch2;
 	dbuf<int32_t> slot_first, slot_cnt, slot_chain, n_chains, n_splices, c_rep, c_cnt, c_grp, handle_chain, splices_scratch;
 	int64_t n_slots = 0;
+	// combined chain sets (k_group.h) own their element arrays: coordinates offset / length / AI3 counts per element and the
+	// element offsets per combined bundle
+	dbuf<int64_t> ext_voff, ext_goff;
+	dbuf<int32_t> ext_len, ext_cnt3;
+	std::vector<int64_t> ext_goff_host;
+	int64_t ext_nval = 0;                 // size of the (shared) coordinate array `val` points into
 
 	void release(agpu_ctx *ctx)
 	{
@@ -43,6 +50,7 @@ struct chainset_state
 		slot_word.release(ctx); key_scratch.release(ctx); key_scratch2.release(ctx);
 		slot_first.release(ctx); slot_cnt.release(ctx); slot_chain.release(ctx); n_chains.release(ctx); n_splices.release(ctx);
 		c_rep.release(ctx); c_cnt.release(ctx); c_grp.release(ctx); handle_chain.release(ctx); splices_scratch.release(ctx);
+		ext_voff.release(ctx); ext_goff.release(ctx); ext_len.release(ctx); ext_cnt3.release(ctx); ext_goff_host.clear(); ext_nval = 0;
 		built = false;
 	}
 
@@ -100,6 +108,7 @@ struct graph_state
 		g.e_s = e_i[0].p; g.e_t = e_i[1].p; g.e_strand = e_i[2].p; g.e_w = e_w.p;
 		g.in_off = in_off.p; g.in_src = in_src.p; g.in_eid = in_eid.p;
 		g.out_off = out_off.p; g.out_dst = out_dst.p; g.out_eid = out_eid.p;
+		g.remap = NULL;
 		g.err = err;
 		return g;
 	}
@@ -140,6 +149,10 @@ struct agpu_batch
 	dbuf<int32_t> diffc, posc, covc;
 	dbuf<int64_t> bord_off, ex_s, ex_e;
 	int64_t n_bord = 0, n_extra = 0;
+	// a combined bundle's coverage sources: the borders of its members as weighted window positions (k_group.h)
+	dbuf<int64_t> pt_g;
+	dbuf<int32_t> pt_d;
+	int64_t n_pts = 0;
 	dbuf<int32_t> spl, hit_nspl, hit_bundle;
 	dbuf<u64> hit_hash;
 	chainset_state hcst, fcst;
@@ -155,6 +168,13 @@ struct agpu_batch
 	graph_state gr;
 	cluster_state clu;
 	bridge_state brg;
+
+	// group-level re-bridge (assembler::bridge): the combined bundles of the clusters as a batch of their own
+	agpu_batch *cb = NULL;
+	dbuf<int32_t> g_remap, g_members, g_first;
+	dbuf<int64_t> g_member_off;
+	std::vector<int32_t> g_order_host;     // members of every cluster in combine order (flattened like the input)
+	bool group_pass = false;               // cluster / bridge stages work against cb's graphs
 
 	// pinned result mirrors, by name
 	std::map<std::string, hbuf<char> > pinned;
@@ -421,6 +441,10 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	b->b_span.release(ctx); b->cov_base.release(ctx); b->border.release(ctx); b->wrank.release(ctx);
 	b->diffc.release(ctx); b->posc.release(ctx); b->covc.release(ctx); b->bord_off.release(ctx); b->ex_s.release(ctx); b->ex_e.release(ctx);
 	b->n_bord = 0; b->n_extra = 0;
+	b->pt_g.release(ctx); b->pt_d.release(ctx); b->n_pts = 0;
+	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
+	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
+	b->group_pass = false;
 	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx); b->hit_hash.release(ctx);
 	b->hcst.release(ctx); b->fcst.release(ctx);
 	b->seg_off.release(ctx);
@@ -556,6 +580,7 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
 		LAUNCH_T(ctx, k_cov_add, b->nh, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
+		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);
 		// coverage = prefix sum of the differences; segments = borders with positive coverage
 		int64_t nt = (n + CTILE - 1) / CTILE;
 		dbuf<int32_t> tc;
@@ -674,5 +699,6 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 
 #include "abi_stages.inc"
 #include "abi_fetch.inc"
+#include "abi_group.inc"
 
 }

@@ -33,11 +33,12 @@ DEV sgraph sgraph_of(const graph_dev &g, const uint8_t *b_strand, int b)
 {
 	sgraph s;
 	s.gv = graph_of(g, b);
+	s.strand = b_strand[b];                 // members of a cluster of bundles share the combined bundle's strand (meta/bundle.cc:93)
+	b = graph_index(g, b);
 	int64_t vo = voff_base(g, b), e0 = g.edge_off[b];
 	s.in_off = g.in_off + vo; s.out_off = g.out_off + vo;
 	s.in_src = g.in_src + e0; s.in_eid = g.in_eid + e0; s.out_dst = g.out_dst + e0; s.out_eid = g.out_eid + e0;
 	s.e_strand = g.e_strand + e0; s.e_w = g.e_w + e0;
-	s.strand = b_strand[b];
 	return s;
 }
 
@@ -296,9 +297,11 @@ KERNEL k_piers(const int32_t *order, int32_t n_bundles, const int64_t *clu_off, 
 			key[k] = ((u64)(u32)v1 << 32) | (u64)(u32)v2;
 		}
 		// largest in-degree, for the candidate scratch of the DP
+		if(graph_index(g, b) >= 0)
 		{
-			int nv = g.n_pex[b] + 2;
-			const int32_t *io = g.in_off + voff_base(g, b);
+			const int gb = graph_index(g, b);
+			int nv = g.n_pex[gb] + 2;
+			const int32_t *io = g.in_off + voff_base(g, gb);
 			int m = 0;
 			for(int v = threadIdx.x; v < nv; v += blockDim.x) { int d = io[v + 1] - io[v]; if(d > m) m = d; }
 			atomicMax(&s_max, m);

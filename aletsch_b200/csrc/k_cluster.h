@@ -28,6 +28,7 @@ struct gview                     // read-only view of the graph of one bundle
 DEV gview graph_of(const graph_dev &g, int b)
 {
 	gview v;
+	b = graph_index(g, b);
 	int64_t v0 = vert_base(g, b);
 	v.nv = g.n_pex[b] + 2;
 	v.v_l = g.v_l + v0; v.v_r = g.v_r + v0; v.v_brk = g.v_brk + v0;
@@ -86,6 +87,7 @@ KERNEL k_chain_paths(int64_t n_elem, const int32_t *elem_bundle, chains_view cv,
 	int b = elem_bundle[e];
 	int k = (int)(e - cv.elem_off[b]);
 	if(k >= cv.n_chains[b]) return;
+	if(graph_index(g, b) < 0) return;             // bundle outside every cluster of bundles (group pass only)
 	gview gv = graph_of(g, b);
 	int len = cv.len(b, k);
 	const int32_t *v = cv.ptr(b, k);
@@ -189,9 +191,10 @@ KERNEL k_frag_align(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_o
 	if(f >= n_frg) return;
 	c.f_ok[f] = 0;
 	c.f_slot[f] = -1;
+	int b = f_bundle[f];
+	if(graph_index(g, b) < 0) return;             // bundle outside every cluster of bundles (group pass only)
 	if(f_type[f] != 0) return;                    // only unbridged fragments are grouped (:37-38)
 	f_type[f] = -1;
-	int b = f_bundle[f];
 	int64_t h0 = h.bundle_hit_off[b];
 	int64_t i1 = h0 + f_h1[f], i2 = h0 + f_h2[f];
 	if(h.pos[i1] > h.pos[i2]) return;

@@ -78,9 +78,13 @@ struct graph_dev
 	int32_t *in_off, *in_src, *in_eid;
 	// alive edges sorted by (source, target): out_off likewise
 	int32_t *out_off, *out_dst, *out_eid;
+	// bundle -> graph index when the graphs belong to another batch (assembler::bridge: every member bundle of a cluster works
+	// against the graph of the combined bundle, meta/assembler.cc:989-998); NULL: graph b belongs to bundle b; < 0: no graph
+	const int32_t *remap;
 	int *err;
 };
 
+HD int graph_index(const graph_dev &g, int b) { return g.remap ? g.remap[b] : b; }
 HD int64_t vert_base(const graph_dev &g, int b) { return g.pex_off[b] + 2 * (int64_t)b; }
 HD int64_t voff_base(const graph_dev &g, int b) { return g.pex_off[b] + 3 * (int64_t)b; }
 

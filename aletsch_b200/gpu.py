@@ -71,7 +71,8 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_fragments", "agpu_batch_graph", "agpu_batch_cluster", "agpu_batch_bridge", "agpu_batch_update",
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
-               "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts"]
+               "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
+               "agpu_batch_group_bridge", "agpu_group_fetch"]
 
 
 def load(lib_path=None):
@@ -103,6 +104,8 @@ def load(lib_path=None):
     L.agpu_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Counts)]
     L.agpu_splices_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P64), C.POINTER(P32)]
     L.agpu_batch_bundle_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.agpu_batch_group_bridge.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params)]
+    L.agpu_group_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EvidenceView), C.POINTER(ChainsetView), C.POINTER(GraphView), C.POINTER(P32)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.agpu_group_resolve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
     L.agpu_debug_sort_perm.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -369,6 +372,53 @@ class Batch:
                  "seg": seg[3 * int(so[k]):3 * int(so[k + 1])], "splices": spv[int(spo[k]):int(spo[k + 1])]}
             d.update(cs[k])
             out.append(d)
+        return out
+
+    def group_bridge(self, groups, p):
+        """assembler::bridge over clusters of bundles: groups = list of lists of bundle indices (the reference's gv order)"""
+        off = np.zeros(len(groups) + 1, np.int32)
+        for i, grp in enumerate(groups):
+            off[i + 1] = off[i] + len(grp)
+        mem = np.ascontiguousarray(np.concatenate([np.asarray(x, np.int32) for x in groups]) if groups else np.zeros(1, np.int32), np.int32)
+        self._groups = [list(map(int, x)) for x in groups]
+        self.ctx.check(self.ctx.L.agpu_batch_group_bridge(self.ctx.h, self.h, len(groups), off.ctypes.data, mem.ctypes.data, C.byref(p)),
+                       "agpu_batch_group_bridge")
+
+    def fetch_group(self):
+        """per cluster of the last group_bridge: dict with the oracle's cb_* arrays (tests/orclib.py naming) + combine_order"""
+        ev, fc, gv, po = EvidenceView(), ChainsetView(), GraphView(), P32()
+        self.ctx.check(self.ctx.L.agpu_group_fetch(self.ctx.h, self.h, C.byref(ev), C.byref(fc), C.byref(gv), C.byref(po)), "agpu_group_fetch")
+        ng = len(self._groups)
+        nmem = sum(len(x) for x in self._groups)
+        order = _arr(po, nmem)
+        lpos, rpos, strand = _arr(ev.lpos, ng), _arr(ev.rpos, ng), _arr(ev.strand, ng, np.uint8)
+        so = _arr(ev.seg_off, ng + 1, np.int64)
+        seg = _arr(ev.seg, 3 * int(so[ng]) if ng else 0)
+        hc = self._chainset(ev.hcst, ng, None, "cb_hcst", None)
+        fcs = self._chainset(fc, ng, None, "cb_fcst", None)
+        jo, pox, vo, eo = (_arr(x, ng + 1) for x in (gv.junc_off, gv.pexon_off, gv.vert_off, gv.edge_off))
+        junc, pex, vert, edge = _arr(gv.junc, 9 * int(jo[ng])), _arr(gv.pexon, 5 * int(pox[ng])), _arr(gv.vert, 5 * int(vo[ng])), _arr(gv.edge, 3 * int(eo[ng]))
+        pexd, vertd, edged = _arr(gv.pexon_d, 4 * int(pox[ng]), np.float64), _arr(gv.vert_d, 3 * int(vo[ng]), np.float64), _arr(gv.edge_d, int(eo[ng]), np.float64)
+        out = []
+        m0 = 0
+        for k in range(ng):
+            n = len(self._groups[k])
+            d = {"combine_order": np.array([self._groups[k].index(int(m)) for m in order[m0:m0 + n]], np.int32),
+                 "cb_bundle": np.array([lpos[k], rpos[k], strand[k]], np.int32), "cb_seg": seg[3 * int(so[k]):3 * int(so[k + 1])],
+                 "cb_junc": junc[9 * int(jo[k]):9 * int(jo[k + 1])], "cb_pexon": pex[5 * int(pox[k]):5 * int(pox[k + 1])],
+                 "cb_pexon_d": pexd[4 * int(pox[k]):4 * int(pox[k + 1])], "cb_vert": vert[5 * int(vo[k]):5 * int(vo[k + 1])],
+                 "cb_vert_d": vertd[3 * int(vo[k]):3 * int(vo[k + 1])]}
+            e = edge[3 * int(eo[k]):3 * int(eo[k + 1])].reshape(-1, 3)
+            ew = edged[int(eo[k]):int(eo[k + 1])]
+            alive = e[:, 0] >= 0
+            ea, wa = e[alive], ew[alive]
+            o2 = np.lexsort((ea[:, 1], ea[:, 0])) if len(ea) else np.zeros(0, np.int64)
+            d["cb_edge"] = ea[o2].reshape(-1).astype(np.int32)
+            d["cb_edge_d"] = wa[o2]
+            d.update(hc[k])
+            d.update(fcs[k])
+            out.append(d)
+            m0 += n
         return out
 
     def bundle_counts(self):

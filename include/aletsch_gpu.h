@@ -263,6 +263,23 @@ int agpu_debug_sort_perm(agpu_ctx *ctx, const int32_t *keys, int32_t n, int32_t 
 int agpu_group_resolve(agpu_ctx *ctx, int32_t n_lists, const int64_t *list_off, const int32_t *list_val, const agpu_params *p,
 		int32_t *out_group_of, int32_t *out_n_groups);
 
+/* ---- group-level re-bridge: assembler::bridge (meta/assembler.cc:977-1018) for many clusters of bundles at once ----
+ * Cluster g holds the bundles group_bundles[group_off[g] .. group_off[g+1]) in the order of the reference's `gv` (>= 2
+ * members of one chromosome and strand; a bundle may appear in at most one cluster).  Per cluster: the members are merged
+ * into a combined bundle in the order of combine_bundles (descending segment count, std::sort; meta/assembler.cc:152-175) --
+ * chain sets added, coverage maps added, bounds joined (bundle::combine, meta/bundle.cc:90-107) --, its splice graph is built
+ * (transform(cb, gr, false), meta/assembler.cc:930-944), and every member is clustered, bridged and updated against that
+ * graph (graph_cluster, bridge_solver, update_bridges).  Needs evidence and fragments of the batch (normally after
+ * agpu_batch_bridge_all).  Afterwards the fragments / fcst / coverage of the member bundles are updated, and
+ * agpu_cluster_fetch / agpu_bridge_fetch describe this pass (bundles outside every cluster have no clusters). */
+int agpu_batch_group_bridge(agpu_ctx *ctx, agpu_batch *b, int32_t n_groups, const int32_t *group_off, const int32_t *group_bundles,
+		const agpu_params *p);
+/* the combined bundles of the last agpu_batch_group_bridge, one per cluster: evidence view (bounds, strand, mmap, splices,
+ * combined hcst; its handles are the member chains in combine order), combined fcst, splice graph, and the combine order of
+ * the members (flattened like group_bundles).  Any of the outputs may be NULL. */
+int agpu_group_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_evidence_view *cev, agpu_chainset_view *cfcst, agpu_graph_view *cgr,
+		const int32_t **combine_order);
+
 /* The same for MANY bundle groups in one call (one group per (chromosome, region, strand), meta/incubator.cc:461-471):
  * group g owns the lists [group_off[g], group_off[g + 1]).  agpu_similarity_batch fills, for every group, a dense G x G
  * matrix of pair counts at out_c + c_off[g] (c_off[n_groups] = total); groups of up to 192 lists are resolved by one CTA

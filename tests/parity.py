@@ -157,3 +157,73 @@ def compare_lean_upload(ctx, batch, gp):
                 if not np.array_equal(d0[n], d1[n]):
                     bad.append("bundle %d: %s differs between full and lean upload" % (k, n))
     return bad
+
+
+def locus_groups(batch, width=50000, max_groups=12):
+    """bundles of different samples over the same locus and side: candidate clusters for assembler::bridge"""
+    a = batch.a
+    loci = {}
+    for k in range(batch.n_bundles):
+        h0 = int(a["bundle_hit_off"][k])
+        key = (int(a["bundle_side"][k]), int(a["pos"][h0]) // width)
+        loci.setdefault(key, []).append(k)
+    return [ks for ks in loci.values() if len(ks) >= 2][:max_groups]
+
+
+CB_INT = ("combine_order", "cb_bundle", "cb_seg", "cb_hcst_off", "cb_hcst_val", "cb_hcst_cnt", "cb_hcst_grp", "cb_fcst_off", "cb_fcst_val",
+          "cb_fcst_cnt", "cb_fcst_grp", "cb_junc", "cb_pexon", "cb_vert", "cb_edge")
+CB_F64 = ("cb_pexon_d", "cb_vert_d", "cb_edge_d")
+
+
+def compare_group_bridge(ctx, batch, checker, gp, op, groups, stats=None, first_round=True):
+    """assembler::bridge (meta/assembler.cc:977-1018) on clusters of bundles: per-bundle bridge first (as assembler::resolve
+    does), then the group pass; the combined bundles and every member's clusters / bridges / updated state are compared"""
+    bad = []
+    hit_off = batch.a["bundle_hit_off"]
+    bt = ctx.upload(batch.view(), keepalive=batch)
+    if first_round:
+        bt.bridge_all(gp)
+    else:
+        bt.evidence(gp)            # no per-bundle bridging first: the group pass has every fragment to work on
+        bt.fragments()
+    before = bt.bundle_counts()[:, 3].copy()
+    bt.group_bridge(groups, gp)
+    cb = bt.fetch_group()
+    ev = bt.fetch_evidence(hit_off)
+    fr = bt.fetch_fragments()
+    cl = bt.fetch_clusters(ev)
+    br = bt.fetch_bridge(bt.cluster_offsets())
+    after = bt.bundle_counts()[:, 3]
+    if stats is not None:
+        stats["group_bridged"] = int((after - before).sum())
+    for gi, ks in enumerate(groups):
+        hs = [checker.new_bundle(batch.bundle(k), op) for k in ks]
+        for h in hs:
+            checker.run(h, "fragments")
+            if first_round:
+                checker.run(h, "bridge")
+        tot, ref = checker.group_bridge(hs)
+        for h in hs:
+            checker.free_bundle(h)
+        w = "cluster %s" % ks
+        for n in CB_INT:
+            cmp_int(n, ref[n], cb[gi][n], w, bad)
+        for n in CB_F64:
+            cmp_f64(n, ref[n], cb[gi][n], w, bad)
+        for j, k in enumerate(ks):
+            pre = "b%d_" % j
+            wk = "%s member %d (bundle %d)" % (w, j, k)
+            for n in INT_CLUSTER:
+                cmp_int(n, ref[pre + n], cl[k][n], wk, bad)
+            for n in INT_BRIDGE:
+                cmp_int(n, ref[pre + n], br[k][n], wk, bad)
+            cmp_f64("opt_score", ref[pre + "opt_score"], br[k]["opt_score"], wk, bad)
+            cmp_int("frgs", ref[pre + "frgs"], fr[k]["frgs"], wk, bad)
+            for n in INT_FCST:
+                cmp_int(n, ref[pre + n], fr[k][n], wk, bad)
+            cmp_int("seg", ref[pre + "seg"], ev[k]["seg"], wk, bad)
+            cmp_int("bridged", ref[pre + "bridged"], np.array([after[k] - before[k]], np.int32), wk, bad)
+        if stats is not None:
+            stats["ref_group_bridged"] = stats.get("ref_group_bridged", 0) + int(tot)
+    bt.free()
+    return bad

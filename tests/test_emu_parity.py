@@ -41,6 +41,24 @@ def test_bundle_bridge_parity(ctx, checkers, mode, templates, seed):
             assert stats["bridged"] > 0 and stats["clusters"] > 0
 
 
+@pytest.mark.parametrize("first_round", [True, False])
+def test_group_bridge_parity(ctx, checkers, first_round):
+    """assembler::bridge: clusters of bundles merged into combined bundles (chain sets, coverage maps, bounds), the combined
+    splice graph, and every member re-clustered / re-bridged / updated against it"""
+    assert checkers
+    batch, lt = parity.make_batch(H.SYNTH_PAIRED, 30000, samples=4)
+    gp, op = parity.params_pair(lt)
+    groups = parity.locus_groups(batch)
+    assert len(groups) >= 4
+    for name, chk in checkers.items():
+        stats = {}
+        bad = parity.compare_group_bridge(ctx, batch, chk, gp, op, groups, stats, first_round=first_round)
+        assert not bad, "%s: %d mismatches, first: %s" % (name, len(bad), bad[:3])
+        assert stats["group_bridged"] == stats["ref_group_bridged"]
+        if not first_round:
+            assert stats["group_bridged"] > 0
+
+
 def test_lean_upload_matches_full(ctx):
     """rpos / flag / per-hit strand are optional in agpu_batch_in (include/aletsch_gpu.h)"""
     batch, lt = parity.make_batch(H.SYNTH_PAIRED, 20000)
