@@ -40,7 +40,7 @@ struct chainset_state
 	// combined chain sets (k_group.h) own their element arrays: coordinates offset / length / AI3 counts per element and the
 	// element offsets per combined bundle
 	dbuf<int64_t> ext_voff, ext_goff;
-	dbuf<int32_t> ext_len, ext_cnt3;
+	dbuf<int32_t> ext_len, ext_cnt3, ext_val;
 	std::vector<int64_t> ext_goff_host;
 	int64_t ext_nval = 0;                 // size of the (shared) coordinate array `val` points into
 
@@ -50,7 +50,7 @@ struct chainset_state
 		slot_word.release(ctx); key_scratch.release(ctx); key_scratch2.release(ctx);
 		slot_first.release(ctx); slot_cnt.release(ctx); slot_chain.release(ctx); n_chains.release(ctx); n_splices.release(ctx);
 		c_rep.release(ctx); c_cnt.release(ctx); c_grp.release(ctx); handle_chain.release(ctx); splices_scratch.release(ctx);
-		ext_voff.release(ctx); ext_goff.release(ctx); ext_len.release(ctx); ext_cnt3.release(ctx); ext_goff_host.clear(); ext_nval = 0;
+		ext_voff.release(ctx); ext_goff.release(ctx); ext_len.release(ctx); ext_cnt3.release(ctx); ext_val.release(ctx); ext_goff_host.clear(); ext_nval = 0;
 		built = false;
 	}
 

@@ -94,6 +94,18 @@ KERNEL k_cb_chain_fill(int64_t n_members, const int32_t *gm, chains_view cv, con
 	}
 }
 
+// the combined chain set keeps its own copy of the element coordinates (the members' arrays are replaced by later
+// update rounds): element e moves from src[src_off[e] ..] to dst[dst_off[e] ..], and src_off[e] becomes dst_off[e]
+KERNEL k_cb_chain_copy(int64_t n_elem, const int32_t *src, int64_t *e_voff, const int32_t *e_len, const int64_t *dst_off, int32_t *dst)
+{
+	int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(e >= n_elem) return;
+	const int32_t *s = src + e_voff[e];
+	int32_t *d = dst + dst_off[e];
+	for(int i = 0; i < e_len[e]; i++) d[i] = s[i];
+	e_voff[e] = dst_off[e];
+}
+
 KERNEL k_diff_i64_to_i32(int64_t n, const int64_t *off, int32_t *out)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -245,6 +245,7 @@ def run_ours(args):
     counts = bt.counts()
     per_bundle = bt.bundle_counts()          # [NB, 4]: segments, fragments, clusters, bridged pairs
     stage5 = stage5_gpu(ctx, bt, batch, args) if not args.no_stage5 else None
+    group_leg = group_bridge_gpu(ctx, bt, gp, stage5_gpu.clusters, args) if stage5 is not None else None
     bt.free()
 
     # ---- end to end: pinned host buffers -> upload -> bridge_all -> counters back to the host ----------
@@ -371,10 +372,14 @@ def run_ours(args):
                "roofline": roof, "clocks": clk}
         if stage5 is not None:
             out["stage5"] = stage5
+        if group_leg is not None:
+            out["group_bridge"] = group_leg
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(batch, min(10, ncpu), args.cpu_seconds, gpu_bridged=per_bundle[:, 3])
             if stage5 is not None:
                 out["stage5"]["cpu_baseline"] = stage5_cpu(batch, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
+            if group_leg is not None:
+                out["group_bridge"]["cpu_baseline"] = group_bridge_cpu(batch, stage5_gpu.clusters, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
         emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -397,6 +402,7 @@ def region_groups(batch):
 def stage5_gpu(ctx, bt, batch, args):
     """bundle_group::resolve over every region group of the batch: splice signatures compacted on the device, all groups'
     pair counts in one launch (agpu_group_resolve_batch), size-capped union-find on the host; configs[1]: -c 20 -s 0.2"""
+    stage5_gpu.clusters = []
     import torch
     from aletsch_b200 import gpu as G
     gp5 = G.default_params(library_type=H.FR_FIRST, max_group_size=20, min_grouping_similarity=0.2)
@@ -411,16 +417,102 @@ def stage5_gpu(ctx, bt, batch, args):
         t0 = time.perf_counter()
         off, val = bt.fetch_splices()
         loff, lval = G.reorder_lists(off, val, order)
-        _, ncl = G.group_resolve_arrays(ctx, group_off, loff, lval, gp5)
+        cl_of, ncl = G.group_resolve_arrays(ctx, group_off, loff, lval, gp5)
         torch.cuda.synchronize()
         if it > 0:
             t_all.append(time.perf_counter() - t0)
         clusters = int(ncl.sum())
+    # the clusters with at least two bundles (input of assembler::bridge), members in gset order
+    multi = []
+    for gi, g in enumerate(groups):
+        a, b = int(group_off[gi]), int(group_off[gi + 1])
+        byc = {}
+        for l in range(a, b):
+            byc.setdefault(int(cl_of[l]), []).append(int(order[l]))
+        multi.extend(v for _, v in sorted(byc.items()) if len(v) >= 2)
+    stage5_gpu.clusters = multi
     dt = float(np.mean(t_all))
     pairs = int(sum(len(g) * (len(g) - 1) // 2 for g in groups))
     return {"bundle_groups": len(groups), "bundles": int(batch.n_bundles), "pairs": pairs, "clusters": int(clusters), "ms": dt * 1e3,
             "bundles_per_sec": batch.n_bundles / dt, "pairs_per_sec": pairs / dt, "params": "-c 20 -s 0.2",
             "timing": "host wall clock around splice fetch + agpu_group_resolve_batch (device pair counts + host union-find), synchronised"}
+
+
+def group_bridge_gpu(ctx, bt, gp, clusters, args):
+    """assembler::bridge (meta/assembler.cc:977-1018) over the clusters stage 5 found: combined bundles, their splice graphs,
+    every member re-clustered / re-bridged / updated against them.  Timed after a fresh per-bundle pass, host wall clock
+    (the call ends with a stream synchronisation)."""
+    import torch
+    if not clusters:
+        return None
+    t_all = []
+    extra = 0
+    for it in range(1 + max(1, min(args.steps, 3))):
+        bt.reset()
+        bt.bridge_all(gp)
+        before = int(bt.bundle_counts()[:, 3].sum())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bt.group_bridge(clusters, gp)
+        torch.cuda.synchronize()
+        if it > 0:
+            t_all.append(time.perf_counter() - t0)
+        extra = int(bt.bundle_counts()[:, 3].sum()) - before
+    dt = float(np.mean(t_all))
+    members = int(sum(len(c) for c in clusters))
+    return {"clusters": len(clusters), "member_bundles": members, "ms": dt * 1e3, "member_bundles_per_sec": members / dt,
+            "bridged_pairs_added": extra}
+
+
+def group_bridge_cpu(batch, clusters, threads, budget_s):
+    """the reference's assembler::bridge on a bounded sample of the same clusters (per-bundle bridging done untimed first)"""
+    import orclib
+    kind = "reference"
+    try:
+        orclib.Checker("ref")
+    except (OSError, FileNotFoundError):
+        kind = "port"
+    op = orclib.default_params(library_type=H.FR_FIRST)
+    sizes = np.diff(batch.a["bundle_hit_off"])
+    total = int(sum(int(sizes[k]) for c in clusters for k in c))
+    target_hits = int(60_000 * threads * budget_s)
+    step = max(1, int(np.ceil(total / max(target_hits, 1))))
+    sample = clusters[::step]
+    lock = threading.Lock()
+    nxt = [0]
+    spent = [0.0]
+    added = [0]
+
+    def worker():
+        chk = orclib.Checker("ref" if kind == "reference" else "orc")
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= len(sample):
+                return
+            hs = [chk.new_bundle(batch.bundle(int(k)), op) for k in sample[i]]
+            for h in hs:
+                chk.run_quiet(h, "fragments")
+                chk.run_quiet(h, "bridge")
+            t0 = time.perf_counter()
+            tot, _ = chk.group_bridge(hs)
+            dt = time.perf_counter() - t0
+            for h in hs:
+                chk.free_bundle(h)
+            with lock:
+                spent[0] += dt
+                added[0] += max(int(tot), 0)
+    ths = [threading.Thread(target=worker) for _ in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    members = int(sum(len(c) for c in sample))
+    wall = spent[0] / threads
+    return {"kind": kind, "cores": threads, "sample": "every %d-th cluster: %d clusters, %d member bundles" % (step, len(sample), members),
+            "member_bundles_per_sec": members / max(wall, 1e-9), "bridged_pairs_added": added[0],
+            "note": "includes copying the checker's result arrays out (chk.group_bridge dumps the combined bundle and every member)"}
 
 
 def stage5_cpu(batch, threads, budget_s):

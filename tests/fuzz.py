@@ -138,3 +138,20 @@ def random_batch(seed, n_bundles=12, max_hits=60, empty_every=0, exon_grid=True)
     arr["bundle_sample"] = np.zeros(len(parts), np.int32)
     arr["bundle_side"] = np.zeros(len(parts), np.uint8)
     return H.PackedBatch(arr)
+
+
+def strand_clusters(batch, rng):
+    """random clusters of 2-5 bundles of one strand (assembler::bridge asserts equal strands, meta/bundle.cc:93)"""
+    a = batch.a
+    st = [int(a["strand"][int(a["bundle_hit_off"][k])]) for k in range(batch.n_bundles)]
+    groups = []
+    for s in sorted(set(st)):
+        ks = [k for k in range(batch.n_bundles) if st[k] == s]
+        rng.shuffle(ks)
+        while len(ks) >= 2:
+            n = min(len(ks), int(rng.integers(2, 5)))
+            if len(ks) - n == 1:
+                n += 1
+            groups.append([int(x) for x in ks[:n]])
+            ks = ks[n:]
+    return groups

@@ -23,6 +23,19 @@ def run_seeds(ctx, checkers, seeds, big=False):
             assert not bad, "seed %d vs %s: %d mismatches, first: %s" % (seed, name, len(bad), bad[:3])
 
 
+def run_group_seeds(ctx, checkers, seeds):
+    """assembler::bridge on random clusters of random bundles, with and without a per-bundle bridging round before"""
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        batch = fuzz.random_batch(seed, n_bundles=9, max_hits=(60 if seed % 3 else 200), exon_grid=True)
+        groups = fuzz.strand_clusters(batch, rng)
+        gp, op = parity.params_pair(H.FR_FIRST)
+        for name, chk in checkers.items():
+            for first_round in (True, False):
+                bad = parity.compare_group_bridge(ctx, batch, chk, gp, op, groups, {}, first_round=first_round)
+                assert not bad, "seed %d vs %s (first_round=%s): %d mismatches, first: %s" % (seed, name, first_round, len(bad), bad[:3])
+
+
 def run_degenerate(ctx, checkers):
     gp, op = parity.params_pair(H.UNSTRANDED)
     # an empty batch: every stage must accept it
@@ -48,6 +61,10 @@ def ctx(emu_lib):
 
 def test_fuzz_bundles(ctx, checkers):
     run_seeds(ctx, checkers, range(14))
+
+
+def test_fuzz_group_bridge(ctx, checkers):
+    run_group_seeds(ctx, checkers, range(8))
 
 
 def test_degenerate_batches(ctx, checkers):

@@ -119,6 +119,7 @@ def test_fuzz_bundles(ctx, checkers):
     test_fuzz.run_seeds(ctx, checkers, range(24))
     test_fuzz.run_seeds(ctx, checkers, range(100, 104), big=True)
     test_fuzz.run_degenerate(ctx, checkers)
+    test_fuzz.run_group_seeds(ctx, checkers, range(16))
 
 
 def test_std_sort_permutation(ctx):
