@@ -9,7 +9,7 @@ namespace agpu {
 
 #define AGPU_MAX_BLOCK 256        // largest CTA of the block-cooperative per-bundle kernels
 
-#define SORT_SMEM_CAP 1024
+#define SORT_SMEM_CAP 512
 
 // Normalised bitonic network (all compare-exchanges ascending; the first step of every merge
 // pairs i with i ^ (k - 1)).  With this form, virtual +inf padding beyond n never moves, so

@@ -147,7 +147,7 @@ struct cluster_dev
 	int32_t *m_a1, *m_a2;                // [2F] per mate
 	u64 *f_hash;
 	int64_t *f_slot;
-	int32_t *f_next;
+	int32_t *f_next;                     // arrival rank of the fragment inside its group (0 .. slot_n - 1, any order)
 	// group table
 	const int64_t *reg_off;
 	u64 *slot_word;
@@ -265,14 +265,26 @@ KERNEL k_frag_group(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_o
 	if(sl < 0) { atomicAdd(&err[ERR_CAP], 1); c.f_ok[f] = 0; return; }
 	c.f_slot[f] = sl;
 	int32_t lf = (int32_t)(f - frg_off[b]);
-	c.f_next[f] = atomicExch(&c.slot_head[sl], lf);
 	atomicMin(&c.slot_min[sl], lf);
-	atomicAdd(&c.slot_n[sl], 1);
+	c.f_next[f] = atomicAdd(&c.slot_n[sl], 1);
+}
+
+// members of every group side by side (unordered inside the group): fragment f goes to its group's window at its arrival rank
+KERNEL k_members_scatter(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, cluster_dev c, const int64_t *member_off, int32_t *members)
+{
+	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(f >= n_frg) return;
+	int64_t sl = c.f_slot[f];
+	if(sl < 0) return;
+	int64_t f0 = frg_off[f_bundle[f]];
+	members[member_off[f0 + c.slot_min[sl]] + c.f_next[f]] = (int32_t)(f - f0);
 }
 
 // leader[f] = group size if f is the first fragment of its group, else -1 (input of the flag scans)
-#define BIG_GROUP 16            // groups above this size are partitioned by a whole warp (CUDA build)
-#define LANE_RANGE 48           // inside the warp kernel, ranges up to this size are sorted by a single lane
+#define BIG_GROUP 16            // groups up to this size: one thread, insertion sorts only (std::sort on <= 16 elements); above: a whole
+                                // warp (CUDA build).  One thread replaying introsort in local memory for 17 .. 48 members was measured 2x slower.
+#define LANE_RANGE 16           // inside the warp kernel, ranges up to this size are sorted by a single lane
+#define WARP_EL_CAP 128         // groups up to this size are partitioned in shared memory (4 warps x 1 KB per CTA)
 
 // small_list / big_list: the leaders packed densely (any order), so that the partition kernels run with full warps
 KERNEL k_group_leaders(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, cluster_dev c, int32_t *leader, int32_t *leader_size,
@@ -422,8 +434,7 @@ KERNEL k_group_partition(int64_t n_frg, const int32_t *f_bundle, const int64_t *
 		const int32_t *fh1 = f_h1 + f0, *fh2 = f_h2 + f0;
 		const int32_t *hp = h.pos + h.bundle_hit_off[b], *hr = h.rpos + h.bundle_hit_off[b];
 		u64 e[BIG_GROUP];
-		int k = 0;
-		for(int32_t x = c.slot_head[sl]; x >= 0 && k < n; x = c.f_next[f0 + x]) e[k++] = (u64)(u32)x;
+		for(int k = 0; k < n; k++) e[k] = (u64)(u32)m[k];
 		for(int a = 1; a < n; a++)              // ascending fragment index
 		{
 			u64 v = e[a];
@@ -456,8 +467,6 @@ KERNEL k_group_partition(int64_t n_frg, const int32_t *f_bundle, const int64_t *
 		return;
 	}
 #else
-	int k = 0;
-	for(int32_t x = c.slot_head[sl]; x >= 0 && k < n; x = c.f_next[f0 + x]) m[k++] = x;
 	// ascending fragment index = the order group_pereads appended them (heap sort, keys are distinct)
 	for(int i = n / 2 - 1; i >= 0; i--)
 	{
@@ -507,6 +516,9 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, cluster_dev c, const int64_t *member_off, int32_t *members, u64 *elems,
 		int32_t *cflag, int32_t *scratch, int gap)
 {
+	// the element array of a group of up to WARP_EL_CAP members lives in shared memory while its four levels are sorted:
+	// the per-lane std::sort replays are chains of dependent element reads and moves
+	__shared__ u64 s_el[4][WARP_EL_CAP];
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	int nb_ = *n_big;
@@ -521,7 +533,7 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 	const int64_t sl = c.f_slot[f];
 	const int n = c.slot_n[sl];
 	const int64_t mo = member_off[f];
-	u64 *el = elems + mo;
+	u64 *el = n <= WARP_EL_CAP ? s_el[(threadIdx.x >> 5) & 3] : elems + mo;
 	int32_t *flag = cflag + mo;
 	int32_t *rl = scratch + 4 * mo;              // range list (n ints), then 3n ints of sort scratch
 	int32_t *ss = rl + n;
@@ -531,11 +543,12 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 	pc.pos = h.pos + h.bundle_hit_off[b]; pc.rpos = h.rpos + h.bundle_hit_off[b];
 	pc.gap = gap;
 	// members in ascending fragment index
-	if(n <= 1024 && n * 8 < nfb)
+	if(n <= 1024 && (int64_t)n * n < (int64_t)nfb * 4)
 	{
-		// moderate group inside a big bundle: walk the group's list, then order by counting smaller members
+		// moderate group inside a big bundle (n^2 / 32 steps beat the nfb / 32 steps of the scan below): order the scattered
+	// window by counting smaller members
 		u64 *tmp = (u64*)rl;                 // 4n ints of scratch are free at this point (8-byte aligned: 4 * mo ints)
-		if(lane == 0) { int k = 0; for(int32_t x = c.slot_head[sl]; x >= 0 && k < n; x = c.f_next[f0 + x]) tmp[k++] = (u64)(u32)x; }
+		for(int i = lane; i < n; i += 32) tmp[i] = (u64)(u32)members[mo + i];      // the group's window, unordered
 		__syncwarp();
 		for(int i = lane; i < n; i += 32)
 		{

@@ -314,6 +314,10 @@ def run_ours(args):
         for name, (ms, cnt) in top[:14]:
             log("[bench] kernel %-22s %9.3f ms/step  (%d launches/step, %.1f%% of kernel time)" %
                 (name, ms / steps, cnt // steps, 100 * ms / max(total_k, 1e-9)))
+        # bridged pairs / time of stage 4 + update = the bridging kernels' accumulated time (rank 0's batch)
+        stage4 = ("k_bridge_vertices", "k_piers", "k_cluster_pier", "k_group_cand", "k_bridge_job_counts", "k_bridge_job_fill", "k_bridge_dp",
+                  "k_pier_bridges", "k_vote", "k_vote_type1", "k_vote_type2", "k_update", "k_fcst_insert", "k_merge_entries", "k_scatter_handle")
+        stage4_ms = sum(ms for name, (ms, cnt) in prof.items() if name.replace("(side)", "") in stage4) / steps
         dom = None
         n_splice_pairs = int(np.count_nonzero(ops == 3))
         counts["bundles"] = batch.n_bundles
@@ -365,6 +369,7 @@ def run_ours(args):
                           "records_per_gpu": n_records, "admitted_hits_per_gpu": n_hits, "bundles_per_gpu": batch.n_bundles,
                           "l2": "inputs (%.1f GB) and scratch far larger than the 126 MB L2, no flush needed" % (h2d_bytes / 1e9), "scale": args.scale},
                "bridged_pairs_per_sec": bridged_all * steps / (ms_dev / 1e3), "bridged_pairs_per_step": bridged_all,
+               "bridged_pairs_per_sec_stage4": bridged_all / max(stage4_ms / 1e3, 1e-12), "stage4_ms_per_step": stage4_ms,
                "counts": counts, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": "hits/s", "h2d_bytes_per_step": float(tot[2]), "d2h_bytes_per_step": float(tot[3]),
                        "ms_per_step": ms_e2e / steps, "sub_batches": len(views), "streams": args.streams,
