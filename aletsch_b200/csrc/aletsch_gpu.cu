@@ -9,6 +9,7 @@
 #include "k_bridge.h"
 #include "k_similarity.h"
 #include "k_group.h"
+#include "k_phase.h"
 
 #include <algorithm>
 #include <atomic>
@@ -168,6 +169,12 @@ struct agpu_batch
 	graph_state gr;
 	cluster_state clu;
 	bridge_state brg;
+
+	// phasing paths (bundle_base::build_phase_set): distinct coordinate lists in element order + counts
+	bool phase_built = false;
+	int64_t n_phase = 0, n_phase_val = 0;
+	dbuf<int32_t> ph_val, ph_len, ph_cnt;
+	dbuf<int64_t> ph_off, ph_boff;
 
 	// group-level re-bridge (assembler::bridge): the combined bundles of the clusters as a batch of their own
 	agpu_batch *cb = NULL;
@@ -442,6 +449,8 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	b->diffc.release(ctx); b->posc.release(ctx); b->covc.release(ctx); b->bord_off.release(ctx); b->ex_s.release(ctx); b->ex_e.release(ctx);
 	b->n_bord = 0; b->n_extra = 0;
 	b->pt_g.release(ctx); b->pt_d.release(ctx); b->n_pts = 0;
+	b->ph_val.release(ctx); b->ph_len.release(ctx); b->ph_cnt.release(ctx); b->ph_off.release(ctx); b->ph_boff.release(ctx);
+	b->phase_built = false; b->n_phase = 0; b->n_phase_val = 0;
 	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
 	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
 	b->group_pass = false;
@@ -700,5 +709,6 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 #include "abi_stages.inc"
 #include "abi_fetch.inc"
 #include "abi_group.inc"
+#include "abi_phase.inc"
 
 }

@@ -60,6 +60,10 @@ class BridgeView(C.Structure):
                 ("whole_off", P64), ("whole", P32)]
 
 
+class PhaseView(C.Structure):
+    _fields_ = [("phase_off", P64), ("coord_off", P64), ("coords", P32), ("count", P32), ("n_phases", C.c_int64)]
+
+
 class Counts(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("hits", "cigar_ops", "span", "segments", "chains", "splice_ints", "junctions", "vertices",
                                          "edges", "fragments", "clusters", "bridged", "piers", "borders", "cluster_members",
@@ -72,7 +76,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
-               "agpu_batch_group_bridge", "agpu_group_fetch"]
+               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch"]
 
 
 def load(lib_path=None):
@@ -104,6 +108,8 @@ def load(lib_path=None):
     L.agpu_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Counts)]
     L.agpu_splices_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P64), C.POINTER(P32)]
     L.agpu_batch_bundle_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.agpu_batch_phase_set.argtypes = [C.c_void_p, C.c_void_p]
+    L.agpu_phase_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PhaseView)]
     L.agpu_batch_group_bridge.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params)]
     L.agpu_group_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EvidenceView), C.POINTER(ChainsetView), C.POINTER(GraphView), C.POINTER(P32)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -372,6 +378,22 @@ class Batch:
                  "seg": seg[3 * int(so[k]):3 * int(so[k + 1])], "splices": spv[int(spo[k]):int(spo[k + 1])]}
             d.update(cs[k])
             out.append(d)
+        return out
+
+    def phase_set(self):
+        """bundle_base::build_phase_set against the current graphs; per bundle the oracle's phase_off / phase_val / phase_cnt"""
+        self._run("phase_set")
+        v = PhaseView()
+        self.ctx.check(self.ctx.L.agpu_phase_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_phase_fetch")
+        nb, npz = self.nb, int(v.n_phases)
+        po = _arr(v.phase_off, nb + 1, np.int64)
+        co = _arr(v.coord_off, npz + 1, np.int64)
+        cv = _arr(v.coords, int(co[npz]) if npz else 0)
+        cc = _arr(v.count, npz)
+        out = []
+        for k in range(nb):
+            a, b = int(po[k]), int(po[k + 1])
+            out.append({"phase_off": (co[a:b + 1] - co[a]).astype(np.int32), "phase_val": cv[int(co[a]):int(co[b])], "phase_cnt": cc[a:b]})
         return out
 
     def group_bridge(self, groups, p):

@@ -263,6 +263,22 @@ int agpu_debug_sort_perm(agpu_ctx *ctx, const int32_t *keys, int32_t n, int32_t 
 int agpu_group_resolve(agpu_ctx *ctx, int32_t n_lists, const int64_t *list_off, const int32_t *list_val, const agpu_params *p,
 		int32_t *out_group_of, int32_t *out_n_groups);
 
+/* ---- phasing paths: bundle_base::build_phase_set (rnacore/bundle_base.cc:338-418) against the bundles' current splice
+ * graphs (those of the last agpu_batch_graph, i.e. transform(bd, gr, false)).  Every bridged fragment and every hit outside a
+ * paired fragment contributes [lpos(vertex of its start), intron chain ..., rpos(vertex of its end)] when non-decreasing;
+ * equal lists are counted (phase_set::add, rnacore/phase_set.cc:12-25).  The view lists the distinct coordinate lists of every
+ * bundle in the order of phase_set::pmap (lexicographic). */
+typedef struct agpu_phase_view
+{
+	const int64_t *phase_off;           /* [NB+1] phases of bundle b: [off[b], off[b+1]) */
+	const int64_t *coord_off;           /* [P+1] into coords */
+	const int32_t *coords;              /* exon coordinate lists (even length) */
+	const int32_t *count;               /* [P] multiplicity */
+	int64_t n_phases;
+} agpu_phase_view;
+int agpu_batch_phase_set(agpu_ctx *ctx, agpu_batch *b);
+int agpu_phase_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_phase_view *v);
+
 /* ---- group-level re-bridge: assembler::bridge (meta/assembler.cc:977-1018) for many clusters of bundles at once ----
  * Cluster g holds the bundles group_bundles[group_off[g] .. group_off[g+1]) in the order of the reference's `gv` (>= 2
  * members of one chromosome and strand; a bundle may appear in at most one cluster).  Per cluster: the members are merged

@@ -72,6 +72,7 @@ const void *orc_bag_data(void *bag, int i);
 	int P##_bundle_fragments(void *b, void *bag); \
 	int P##_bundle_graph(void *b, void *bag); \
 	int P##_bundle_bridge(void *b, void *bag); \
+	int P##_bundle_phase(void *b, void *bag); \
 	int P##_group_bridge(void **bs, int n, void *bag); \
 	int P##_group_resolve(void **bs, int n, const orc_params *prm, void *bag);
 

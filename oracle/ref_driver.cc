@@ -21,6 +21,7 @@
 #include "bridge_solver.h"
 #include "essential.h"
 #include "parameters.h"
+#include "phase_set.h"
 #include "sample_profile.h"
 
 #include <cmath>
@@ -359,6 +360,32 @@ int ref_bundle_bridge(void *b, void *bagp)
 	gr.build_vertex_index();
 	dump_graph(gr, h->cfg, bag, "", dump_builder(gb, h->cfg, bag, ""));
 	return cluster_solve_update(gr, h->bd, h->cfg, bag, "", false);
+}
+
+// bundle_base::build_phase_set (rnacore/bundle_base.cc:338-418) against the bundle's own (unrevised) splice graph, i.e. the
+// graph of transform(bd, gr, false); the map is dumped in its own (lexicographic) order
+int ref_bundle_phase(void *b, void *bagp)
+{
+	ref_handle *h = (ref_handle*)b;
+	orc_bag &bag = *(orc_bag*)bagp;
+	splice_graph gr;
+	graph_builder gb(h->bd, h->cfg, h->sp);
+	gb.build(gr);
+	gr.build_vertex_index();
+	phase_set ps;
+	h->bd.build_phase_set(ps, gr);
+	std::vector<int32_t> &po = bag.ints("phase_off");
+	std::vector<int32_t> &pv = bag.ints("phase_val");
+	std::vector<int32_t> &pc = bag.ints("phase_cnt");
+	po.clear(); pv.clear(); pc.clear();
+	po.push_back(0);
+	for(MVII::const_iterator it = ps.pmap.begin(); it != ps.pmap.end(); it++)
+	{
+		pv.insert(pv.end(), it->first.begin(), it->first.end());
+		po.push_back((int32_t)pv.size());
+		pc.push_back(it->second);
+	}
+	return (int)pc.size();
 }
 
 int ref_group_bridge(void **bs, int n, void *bagp)

@@ -259,6 +259,30 @@ int orc_bundle_bridge(void *b, void *bagp)
 	return cluster_solve_update(gr, bd, bd.prm, bag, "", false);
 }
 
+// bundle_base::build_phase_set against the bundle's own splice graph (transform(bd, gr, false))
+int orc_bundle_phase(void *b, void *bagp)
+{
+	bundle &bd = *(bundle*)b;
+	orc_bag &bag = *(orc_bag*)bagp;
+	graph gr;
+	builder_out bo;
+	build_graph(bd, gr, bo);
+	std::map<chain_t, int> ps;
+	build_phase_set(bd, gr, ps);
+	std::vector<int32_t> &po = bag.ints("phase_off");
+	std::vector<int32_t> &pv = bag.ints("phase_val");
+	std::vector<int32_t> &pc = bag.ints("phase_cnt");
+	po.clear(); pv.clear(); pc.clear();
+	po.push_back(0);
+	for(std::map<chain_t, int>::const_iterator it = ps.begin(); it != ps.end(); it++)
+	{
+		pv.insert(pv.end(), it->first.begin(), it->first.end());
+		po.push_back((int32_t)pv.size());
+		pc.push_back(it->second);
+	}
+	return (int)pc.size();
+}
+
 // assembler::bridge (meta/assembler.cc:977-1018) with combine_bundles (:152-175) and bundle::combine (meta/bundle.cc:90-107)
 int orc_group_bridge(void **bs, int n, void *bagp)
 {

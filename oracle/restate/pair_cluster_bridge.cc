@@ -620,4 +620,53 @@ int update_bridges(bundle &bd, const std::vector<int> &frlist, const chain_t &ch
 	return cnt;
 }
 
+
+// bundle_base::build_phase_set (rnacore/bundle_base.cc:338-418): phasing paths (exon coordinate lists) with multiplicities,
+// keyed and ordered like phase_set::pmap (rnacore/phase_set.h:23-27)
+void build_phase_set(const bundle &bd, const graph &gr, std::map<chain_t, int> &ps)
+{
+	static const chain_t none;
+	std::vector<int> fb(bd.hits.size(), -1);
+	for(size_t i = 0; i < bd.frgs.size(); i++)
+	{
+		if(bd.frgs[i][2] <= -1) continue;
+		int h1 = bd.frgs[i][0], h2 = bd.frgs[i][1];
+		if(bd.frgs[i][2] == 0) { fb[h1] = 0; fb[h2] = 0; continue; }
+		int u1 = gr.locate_vertex(bd.hits[h1].pos), u2 = gr.locate_vertex(bd.hits[h2].rpos - 1);
+		if(u1 < 0 || u2 < 0) continue;
+		int32_t p1 = gr.vl[u1], p2 = gr.vr[u2];
+		const chain_t *c1 = bd.hcst.get(h1), *c2 = bd.hcst.get(h2);
+		const chain_t &v1 = c1 ? *c1 : none, &v2 = c2 ? *c2 : none;
+		chain_t xy;
+		if(bd.frgs[i][2] == 1)
+		{
+			if(!merge_intron_chains(v1, v2, xy)) continue;
+		}
+		if(bd.frgs[i][2] >= 2)
+		{
+			const chain_t *cv = bd.fcst.get((int)i);
+			xy.insert(xy.end(), v1.begin(), v1.end());
+			if(cv) xy.insert(xy.end(), cv->begin(), cv->end());
+			xy.insert(xy.end(), v2.begin(), v2.end());
+		}
+		xy.insert(xy.begin(), p1);
+		xy.insert(xy.end(), p2);
+		if(!increasing(xy)) continue;
+		fb[h1] = 1; fb[h2] = 1;
+		ps[xy] += 1;
+	}
+	for(size_t i = 0; i < bd.hits.size(); i++)
+	{
+		if(fb[i] >= 0) continue;
+		int u1 = gr.locate_vertex(bd.hits[i].pos), u2 = gr.locate_vertex(bd.hits[i].rpos - 1);
+		if(u1 < 0 || u2 < 0) continue;
+		const chain_t *c = bd.hcst.get((int)i);
+		chain_t xy = c ? *c : none;
+		xy.insert(xy.begin(), gr.vl[u1]);
+		xy.insert(xy.end(), gr.vr[u2]);
+		if(!increasing(xy)) continue;
+		ps[xy] += 1;
+	}
+}
+
 } // namespace orc

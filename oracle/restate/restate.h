@@ -109,6 +109,7 @@ struct bridge_path
 struct builder_out { std::vector<junction> junctions; std::vector<pexon> pexons; };
 
 void build_graph(const bundle &bd, graph &gr, builder_out &bo);
+void build_phase_set(const bundle &bd, const graph &gr, std::map<chain_t, int> &ps);
 void build_fragments(bundle &bd);
 void cluster_fragments(graph &gr, bundle &bd, std::vector<cluster> &vc);
 void bridge_clusters(graph &gr, std::vector<cluster> &vc, const orc_params &prm, std::vector<bridge_path> &opt);

@@ -143,9 +143,10 @@ def random_batch(seed, n_bundles=12, max_hits=60, empty_every=0, exon_grid=True)
 def strand_clusters(batch, rng):
     """random clusters of 2-5 bundles of one strand (assembler::bridge asserts equal strands, meta/bundle.cc:93)"""
     a = batch.a
-    st = [int(a["strand"][int(a["bundle_hit_off"][k])]) for k in range(batch.n_bundles)]
+    off = a["bundle_hit_off"]
+    st = [int(a["strand"][int(off[k])]) if off[k + 1] > off[k] else -1 for k in range(batch.n_bundles)]      # -1: empty bundle, left out
     groups = []
-    for s in sorted(set(st)):
+    for s in sorted(set(st) - {-1}):
         ks = [k for k in range(batch.n_bundles) if st[k] == s]
         rng.shuffle(ks)
         while len(ks) >= 2:

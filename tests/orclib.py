@@ -61,7 +61,7 @@ class Checker:
         f("bundle_new").restype = C.c_void_p
         f("bundle_new").argtypes = [C.POINTER(BundleIn), C.POINTER(Params)]
         f("bundle_free").argtypes = [C.c_void_p]
-        for n in ("bundle_evidence", "bundle_fragments", "bundle_graph", "bundle_bridge"):
+        for n in ("bundle_evidence", "bundle_fragments", "bundle_graph", "bundle_bridge", "bundle_phase"):
             f(n).argtypes = [C.c_void_p, C.c_void_p]
         f("group_bridge").argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
         f("group_resolve").argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_void_p]

@@ -227,3 +227,27 @@ def compare_group_bridge(ctx, batch, checker, gp, op, groups, stats=None, first_
             stats["ref_group_bridged"] = stats.get("ref_group_bridged", 0) + int(tot)
     bt.free()
     return bad
+
+
+def compare_phase_set(ctx, batch, checker, gp, op, stats=None):
+    """bundle_base::build_phase_set (rnacore/bundle_base.cc:338-418) after bundle::bridge, against the bundles' own splice
+    graphs rebuilt from the updated evidence (transform(bd, gr, false))"""
+    bad = []
+    bt = ctx.upload(batch.view(), keepalive=batch)
+    bt.bridge_all(gp)
+    bt.graph(gp)
+    ph = bt.phase_set()
+    bt.free()
+    total = 0
+    for k in range(batch.n_bundles):
+        h = checker.new_bundle(batch.bundle(k), op)
+        checker.run(h, "fragments")
+        checker.run(h, "bridge")
+        n, ref = checker.run(h, "phase")
+        checker.free_bundle(h)
+        total += int(ref["phase_cnt"].sum())
+        for name in ("phase_off", "phase_val", "phase_cnt"):
+            cmp_int(name, ref[name], ph[k][name], "bundle %d" % k, bad)
+    if stats is not None:
+        stats["phase_count"] = total
+    return bad

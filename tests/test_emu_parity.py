@@ -59,6 +59,19 @@ def test_group_bridge_parity(ctx, checkers, first_round):
             assert stats["group_bridged"] > 0
 
 
+@pytest.mark.parametrize("mode,templates", [(H.SYNTH_PAIRED, 40000), (H.SYNTH_SINGLE, 20000), (H.SYNTH_LONG, 3000)])
+def test_phase_set_parity(ctx, checkers, mode, templates):
+    """build_phase_set: phasing paths of bridged fragments and unpaired hits, counted and in phase_set::pmap order"""
+    assert checkers
+    batch, lt = parity.make_batch(mode, templates)
+    gp, op = parity.params_pair(lt)
+    for name, chk in checkers.items():
+        stats = {}
+        bad = parity.compare_phase_set(ctx, batch, chk, gp, op, stats)
+        assert not bad, "%s: %d mismatches, first: %s" % (name, len(bad), bad[:3])
+        assert stats["phase_count"] > 0
+
+
 def test_lean_upload_matches_full(ctx):
     """rpos / flag / per-hit strand are optional in agpu_batch_in (include/aletsch_gpu.h)"""
     batch, lt = parity.make_batch(H.SYNTH_PAIRED, 20000)

@@ -21,6 +21,9 @@ def run_seeds(ctx, checkers, seeds, big=False):
         for name, chk in checkers.items():
             bad = parity.compare_full(ctx, batch, chk, gp, op, {})
             assert not bad, "seed %d vs %s: %d mismatches, first: %s" % (seed, name, len(bad), bad[:3])
+            if lt != H.UNSTRANDED:
+                bad = parity.compare_phase_set(ctx, batch, chk, gp, op)
+                assert not bad, "seed %d vs %s (phase set): %d mismatches, first: %s" % (seed, name, len(bad), bad[:3])
 
 
 def run_group_seeds(ctx, checkers, seeds):
