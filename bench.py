@@ -246,6 +246,7 @@ def run_ours(args):
     per_bundle = bt.bundle_counts()          # [NB, 4]: segments, fragments, clusters, bridged pairs
     stage5 = stage5_gpu(ctx, bt, batch, args) if not args.no_stage5 else None
     group_leg = group_bridge_gpu(ctx, bt, gp, stage5_gpu.clusters, args) if stage5 is not None else None
+    phase_leg = phase_set_gpu(ctx, bt, gp, args) if stage5 is not None else None
     bt.free()
 
     # ---- end to end: pinned host buffers -> upload -> bridge_all -> counters back to the host ----------
@@ -379,6 +380,8 @@ def run_ours(args):
             out["stage5"] = stage5
         if group_leg is not None:
             out["group_bridge"] = group_leg
+        if phase_leg is not None:
+            out["phase_set"] = phase_leg
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(batch, min(10, ncpu), args.cpu_seconds, gpu_bridged=per_bundle[:, 3])
             if stage5 is not None:
@@ -467,6 +470,28 @@ def group_bridge_gpu(ctx, bt, gp, clusters, args):
     members = int(sum(len(c) for c in clusters))
     return {"clusters": len(clusters), "member_bundles": members, "ms": dt * 1e3, "member_bundles_per_sec": members / dt,
             "bridged_pairs_added": extra}
+
+
+def phase_set_gpu(ctx, bt, gp, args):
+    """bundle_base::build_phase_set (rnacore/bundle_base.cc:338-418) for every bundle: graphs rebuilt from the bridged evidence,
+    then the phasing paths; device part only (agpu_batch_phase_set ends with a stream synchronisation)"""
+    import torch
+    t_all = []
+    for it in range(1 + max(1, min(args.steps, 3))):
+        bt.reset()
+        bt.bridge_all(gp)
+        bt.graph(gp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bt._run("phase_set")
+        torch.cuda.synchronize()
+        if it > 0:
+            t_all.append(time.perf_counter() - t0)
+    ph = bt.phase_set()
+    dt = float(np.mean(t_all))
+    n_ph = int(sum(len(p["phase_cnt"]) for p in ph))
+    n_el = int(sum(int(p["phase_cnt"].sum()) for p in ph))
+    return {"ms": dt * 1e3, "distinct_phases": n_ph, "phase_elements": n_el, "phase_elements_per_sec": n_el / dt}
 
 
 def group_bridge_cpu(batch, clusters, threads, budget_s):
