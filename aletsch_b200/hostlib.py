@@ -53,13 +53,13 @@ HIT_FIELDS = [("pos", np.int32), ("rpos", np.int32), ("mpos", np.int32), ("isize
 def build():
     """compile libaletsch_host.so in-tree (g++)."""
     import subprocess
-    src = [os.path.join(_HERE, "host", f) for f in ("synth.cc", "packer.cc")]
+    src = [os.path.join(_HERE, "host", f) for f in ("synth.cc", "packer.cc", "bamio.cc")]
     out = os.path.join(_HERE, "libaletsch_host.so")
-    deps = src + [os.path.join(_HERE, "host", f) for f in ("synth.h", "packer.h")] + \
+    deps = src + [os.path.join(_HERE, "host", f) for f in ("synth.h", "packer.h", "bamio.h")] + \
         [os.path.join(_HERE, "..", "include", "aletsch_gpu.h")]
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
         return out
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", out] + src + ["-lpthread"])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", out] + src + ["-lpthread", "-lz"])
     return out
 
 
@@ -77,6 +77,8 @@ def lib():
         L.synth_generate.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.POINTER(SynthRecords)]
         L.synth_default_config.argtypes = [C.POINTER(SynthConfig), C.c_int]
         L.synth_records_free.argtypes = [C.POINTER(SynthRecords)]
+        L.bam_write_records.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.POINTER(SynthRecords), C.c_int]
+        L.bam_read_records.argtypes = [C.c_char_p, C.POINTER(SynthRecords), C.POINTER(C.c_int32), C.c_void_p, C.c_int32]
         L.packer_create.restype = C.c_void_p
         L.packer_destroy.argtypes = [C.c_void_p]
         L.packer_add_sample.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
@@ -134,6 +136,49 @@ class Synth:
                "cigar_off": _np(r.cigar_off, n + 1, np.uint32), "cigar": _np(r.cigar, nc, np.uint32)}
         lib().synth_records_free(C.byref(r))
         return out
+
+
+_REC_FIELDS = [("tid", np.int32), ("pos", np.int32), ("rpos", np.int32), ("mpos", np.int32), ("isize", np.int32), ("flag", np.uint16),
+               ("mapq", np.uint8), ("xs", np.uint8), ("qid", np.uint64)]
+
+
+def _records_struct(rec, keep):
+    r = SynthRecords()
+    r.n = rec["n"]
+    r.n_cigar = len(rec["cigar"])
+    for k, dt in _REC_FIELDS + [("cigar_off", np.uint32), ("cigar", np.uint32)]:
+        a = np.ascontiguousarray(rec[k], dt)
+        keep.append(a)
+        setattr(r, k, a.ctypes.data_as(C.POINTER(np.ctypeslib.as_ctypes_type(dt))))
+    return r
+
+
+def write_bam(path, rec, chrom_len, tag_mode=0):
+    """records of one sample (Synth.sample layout) -> coordinate-sorted BAM file (host/bamio.h); tag_mode 1 writes ts:A"""
+    keep = []
+    r = _records_struct(rec, keep)
+    cl = np.ascontiguousarray(chrom_len, np.int32)
+    rc = lib().bam_write_records(path.encode(), len(cl), cl.ctypes.data, C.byref(r), tag_mode)
+    if rc != 0:
+        raise RuntimeError("bam_write_records(%s) failed with %d" % (path, rc))
+
+
+def read_bam(path):
+    """BAM file -> (records in Synth.sample layout, chromosome lengths): the host ingest in front of the packer"""
+    r = SynthRecords()
+    n_chrom = C.c_int32(0)
+    cl = np.zeros(4096, np.int32)
+    rc = lib().bam_read_records(path.encode(), C.byref(r), C.byref(n_chrom), cl.ctypes.data, len(cl))
+    if rc != 0:
+        raise RuntimeError("bam_read_records(%s) failed with %d" % (path, rc))
+    n, nc = r.n, r.n_cigar
+    out = {"n": n}
+    for k, dt in _REC_FIELDS:
+        out[k] = _np(getattr(r, k), n, dt)
+    out["cigar_off"] = _np(r.cigar_off, n + 1, np.uint32)
+    out["cigar"] = _np(r.cigar, nc, np.uint32)
+    lib().synth_records_free(C.byref(r))
+    return out, cl[:min(n_chrom.value, len(cl))].copy()
 
 
 def default_packer_params(library_type=FR_FIRST, **kw):
