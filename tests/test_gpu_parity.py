@@ -135,6 +135,39 @@ def test_fuzz_bundles(ctx, checkers):
     test_fuzz.run_group_seeds(ctx, checkers, range(16))
 
 
+def test_long_read_scale_parity(ctx, checkers):
+    """configs[4]-style input at a larger scale: many-junction long reads (junction / coverage-heavy path), ONT junction support"""
+    batch, lt = parity.make_batch(H.SYNTH_LONG, 20000, chrom_len=4_000_000, seed=20260105)
+    gp, op = parity.params_pair(lt, min_junction_support=2)
+    chk = checkers.get("ref") or next(iter(checkers.values()))
+    stats = {}
+    bad = parity.compare_full(ctx, batch, chk, gp, op, stats)
+    assert not bad, bad[:3]
+    assert stats["junctions"] > 100
+
+
+def test_bam_file_to_device(ctx, tmp_path):
+    """BAM file -> host ingest -> packer -> CUDA path (python -m aletsch_b200.run does the same): identical to the direct path"""
+    import numpy as np
+    cfg = H.default_config(H.SYNTH_PAIRED, chrom_len=1_000_000, seed=20260113)
+    syn = H.Synth(cfg)
+    recs = [syn.sample(k, 8000, threads=2) for k in range(2)]
+    back = []
+    for k, r in enumerate(recs):
+        path = str(tmp_path / ("s%d.bam" % k))
+        H.write_bam(path, r, [cfg.chrom_len] * cfg.n_chrom)
+        back.append(H.read_bam(path)[0])
+    pp = H.default_packer_params(H.FR_FIRST)
+    gp, _ = parity.params_pair(H.FR_FIRST)
+    outs = []
+    for b in (H.pack(recs, pp), H.pack(back, pp)):
+        bt = ctx.upload(b.view(), keepalive=b)
+        bt.bridge_all(gp)
+        outs.append((bt.counts(), bt.bundle_counts().copy()))
+        bt.free()
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and outs[0][0]["bridged"] > 0
+
+
 def test_std_sort_permutation(ctx):
     """the device re-implementation of libstdc++'s introsort against the real std::sort on heavily tied keys"""
     import ctypes as C
