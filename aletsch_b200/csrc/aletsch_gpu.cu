@@ -301,6 +301,37 @@ const char *agpu_last_error(agpu_ctx *ctx) { return ctx ? ctx->last_error.c_str(
 int agpu_sync(agpu_ctx *ctx) { if(!ctx) return AGPU_ERR_ARG; AGPU_ENTER(ctx); return stream_sync(ctx); }
 int64_t agpu_launch_count(agpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+// arena of the context (runtime.h): bytes held, and growth ahead of time so that a steady-state pipeline never has to take a
+// new slab (a cudaMallocAsync that misses the pool synchronises the device) in the middle of its work
+int64_t agpu_reserved(agpu_ctx *ctx)
+{
+	if(!ctx) return 0;
+	int64_t tot = 0;
+#ifndef AGPU_EMU
+	for(size_t k = 0; k < ctx->arena.slabs.size(); k++) tot += (int64_t)ctx->arena.slabs[k].size;
+#endif
+	return tot;
+}
+
+int agpu_reserve(agpu_ctx *ctx, int64_t bytes)
+{
+	if(!ctx || bytes < 0) return AGPU_ERR_ARG;
+	AGPU_ENTER(ctx);
+#ifndef AGPU_EMU
+	while(agpu_reserved(ctx) < bytes)
+	{
+		agpu_arena::slab s;
+		s.size = AGPU_SLAB_BYTES;
+		void *base = NULL;
+		if(cudaMallocAsync(&base, s.size, ctx->stream) != cudaSuccess) { cudaGetLastError(); ctx->last_error = "agpu_reserve: slab allocation failed"; return AGPU_ERR_OOM; }
+		s.base = (char*)base;
+		ctx->arena.slabs.push_back(s);
+	}
+	TRY(stream_sync(ctx));
+#endif
+	return AGPU_OK;
+}
+
 int agpu_profile_enable(agpu_ctx *ctx, int on) { if(!ctx) return AGPU_ERR_ARG; ctx->profiling = on != 0; return AGPU_OK; }
 int agpu_profile_reset(agpu_ctx *ctx)
 {

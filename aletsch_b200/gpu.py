@@ -76,7 +76,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
-               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch"]
+               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_reserved", "agpu_reserve"]
 
 
 def load(lib_path=None):
@@ -92,6 +92,9 @@ def load(lib_path=None):
     L.agpu_launch_count.restype = C.c_int64
     L.agpu_launch_count.argtypes = [C.c_void_p]
     L.agpu_default_params.argtypes = [C.POINTER(Params)]
+    L.agpu_reserved.restype = C.c_int64
+    L.agpu_reserved.argtypes = [C.c_void_p]
+    L.agpu_reserve.argtypes = [C.c_void_p, C.c_int64]
     L.agpu_batch_upload.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
     L.agpu_batch_adopt.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
     L.agpu_batch_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -176,6 +179,13 @@ class Context:
     @property
     def launches(self):
         return self.L.agpu_launch_count(self.h)
+
+    @property
+    def reserved(self):
+        return self.L.agpu_reserved(self.h)
+
+    def reserve(self, nbytes):
+        self.check(self.L.agpu_reserve(self.h, int(nbytes)), "agpu_reserve")
 
     def profile(self, on=True):
         self.check(self.L.agpu_profile_enable(self.h, 1 if on else 0), "agpu_profile_enable")

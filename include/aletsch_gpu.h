@@ -120,6 +120,12 @@ int agpu_sync(agpu_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t agpu_launch_count(agpu_ctx *ctx);
 
+/* Scratch arena of the context: a batch's derived state is bump-allocated from a few large slabs the context keeps.
+ * agpu_reserved = bytes held now; agpu_reserve grows the arena ahead of time (e.g. to the largest size any context of a
+ * stream pool has needed) so that steady-state work never allocates. */
+int64_t agpu_reserved(agpu_ctx *ctx);
+int agpu_reserve(agpu_ctx *ctx, int64_t bytes);
+
 /* optional per-kernel timing: CUDA events around every launch of this context.  agpu_profile_read
  * synchronises and writes "kernel_name\tms\tlaunches\n" lines (cumulative since the last reset). */
 int agpu_profile_enable(agpu_ctx *ctx, int on);
