@@ -60,10 +60,10 @@ class Pipeline:
             t.join()
         if errs:
             raise errs[0]
-        # every context keeps as much scratch as the hungriest one has needed (+ one slab): whichever sub-batch a thread
-        # takes next, it will not have to grow its arena in the middle of the pipeline
+        # every context keeps as much scratch as the hungriest one has needed so far: whichever sub-batch a thread takes
+        # next, it will not have to grow its arena in the middle of the pipeline (idempotent once the sizes agree)
         need = max(c.reserved for c in self.ctxs)
-        if need > 0:
-            for c in self.ctxs:
-                c.reserve(need + (1 << 30))
+        for c in self.ctxs:
+            if c.reserved < need:
+                c.reserve(need)
         return out
