@@ -410,6 +410,10 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->tid_host.assign(in->bundle_tid, in->bundle_tid + b->nb);
 	if(in->bundle_sample) b->sample_host.assign(in->bundle_sample, in->bundle_sample + b->nb);
 	int rc = AGPU_OK;
+	// the uploaded inputs live at the bottom of the context's arena too (below the mark a reset rewinds to): a pipeline in
+	// steady state then makes no allocator call at all
+	if(ctx->arena_owner == NULL) { ctx->arena_owner = b; ctx->arena.rewind(); }
+	arena_scope input_scope(ctx, b);
 #define UP(buf, src, count) do { if(rc == AGPU_OK) rc = b->buf.alloc(ctx, (size_t)(count) + 1); if(rc == AGPU_OK) rc = h2d(ctx, b->buf.p, src, sizeof(*(src)) * (size_t)(count)); } while(0)
 	UP(in_hit_off, in->bundle_hit_off, b->nb + 1);
 	UP(in_pos, in->pos, b->nh); UP(in_mpos, in->mpos, b->nh); UP(in_isize, in->isize, b->nh);
@@ -428,7 +432,6 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.pos = b->in_pos.p; b->h.rpos = b->in_rpos.p; b->h.mpos = b->in_mpos.p; b->h.isize = b->in_isize.p;
 	b->h.flag = NULL; b->h.strand = b->in_strand.p; b->h.bundle_strand = b->in_bstrand.p; b->h.xs = b->in_xs.p; b->h.qid = (const u64*)b->in_qid.p;
 	b->h.cigar_off = b->in_cigar_off.p; b->h.cigar = b->in_cigar.p;
-	if(ctx->arena_owner == NULL) ctx->arena_owner = b;
 	if(!in->rpos)
 	{
 		// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), derived on the device
@@ -436,6 +439,7 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 		b->h.rpos = b->in_rpos.p;
 		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
 	}
+	if(ctx->arena_owner == b) ctx->arena.set_mark();
 	*out = b;
 	return AGPU_OK;
 }
@@ -451,6 +455,8 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->owns_input = false;
 	b->hit_off_host.resize(b->nb + 1);
 	b->tid_host.resize(b->nb);
+	if(ctx->arena_owner == NULL) { ctx->arena_owner = b; ctx->arena.rewind(); }
+	arena_scope input_scope(ctx, b);
 	int rc = d2h(ctx, b->hit_off_host.data(), in->bundle_hit_off, sizeof(int64_t) * (b->nb + 1));
 	if(rc == AGPU_OK) rc = d2h(ctx, b->tid_host.data(), in->bundle_tid, sizeof(int32_t) * b->nb);
 	if(rc == AGPU_OK) rc = stream_sync(ctx);
@@ -462,13 +468,13 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.flag = in->flag; b->h.strand = in->strand; b->h.bundle_strand = in->bundle_strand; b->h.xs = in->xs; b->h.qid = (const u64*)in->qid;
 	b->h.cigar_off = in->cigar_off; b->h.cigar = in->cigar;
 	if(!in->strand && !in->bundle_strand) { agpu_batch_free(ctx, b); return AGPU_ERR_ARG; }
-	if(ctx->arena_owner == NULL) ctx->arena_owner = b;
 	if(!in->rpos)
 	{
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 		b->h.rpos = b->in_rpos.p;
 		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
 	}
+	if(ctx->arena_owner == b) ctx->arena.set_mark();
 	*out = b;
 	return AGPU_OK;
 }
@@ -513,7 +519,7 @@ int agpu_batch_reset(agpu_ctx *ctx, agpu_batch *b)
 	if(!ctx || !b) return AGPU_ERR_ARG;
 	AGPU_ENTER(ctx);
 	release_derived(ctx, b);
-	if(ctx->arena_owner == b) ctx->arena.rewind();
+	if(ctx->arena_owner == b) ctx->arena.rewind_to_mark();
 	TRY(b->err.fill(ctx, 0));
 	return AGPU_OK;
 }

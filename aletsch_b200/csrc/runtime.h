@@ -21,12 +21,15 @@ struct agpu_arena
 	struct slab { char *base; size_t size; };
 	std::vector<slab> slabs;
 	size_t cur = 0, off = 0;
+	size_t mark_cur = 0, mark_off = 0;       // end of the batch's uploaded inputs: a reset rewinds to here, a free to 0
 	bool contains(const void *p) const
 	{
 		for(size_t k = 0; k < slabs.size(); k++) if((const char*)p >= slabs[k].base && (const char*)p < slabs[k].base + slabs[k].size) return true;
 		return false;
 	}
-	void rewind() { cur = 0; off = 0; }
+	void set_mark() { mark_cur = cur; mark_off = off; }
+	void rewind_to_mark() { cur = mark_cur; off = mark_off; }
+	void rewind() { cur = 0; off = 0; mark_cur = 0; mark_off = 0; }
 };
 
 struct agpu_ctx
@@ -197,6 +200,7 @@ template<typename F, typename... A> inline void emu_launch(bool coop, F f, int64
 inline void side_fork(agpu_ctx *) {}
 inline void side_join(agpu_ctx *) {}
 inline void arena_destroy(agpu_ctx *) {}
+struct arena_scope { arena_scope(agpu_ctx *, agpu_batch *) {} };
 #define AGPU_ENTER(ctx) do {} while(0)
 #define AGPU_BATCH_SCOPE(ctx, b) do {} while(0)
 #define LAUNCH_T(ctx, kern, n, ...) do { int64_t n_ = (int64_t)(n); if(n_ > 0) { emu_launch(false, kern, (n_ + 255) / 256, 256, __VA_ARGS__); (ctx)->launches++; } } while(0)
