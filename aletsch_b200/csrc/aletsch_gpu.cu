@@ -268,6 +268,8 @@ int agpu_create(int device, void *stream, agpu_ctx **out)
 				cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e2, cudaEventDisableTiming) != cudaSuccess)
 		{ delete ctx; return AGPU_ERR_CUDA; }
 		ctx->ev_fork = e1; ctx->ev_join = e2;
+		cudaEvent_t e3;
+		if(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess) ctx->ev_sync = e3;
 	}
 	// keep freed blocks in the pool: the stages allocate and free stream-ordered scratch all the time
 	cudaMemPool_t pool;
@@ -292,6 +294,7 @@ void agpu_destroy(agpu_ctx *ctx)
 	if(ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
 	if(ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
 	if(ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
+	if(ctx->ev_sync) cudaEventDestroy((cudaEvent_t)ctx->ev_sync);
 	if(ctx->own_stream) cudaStreamDestroy(ctx->stream);
 #endif
 	delete ctx;
@@ -328,6 +331,17 @@ int agpu_reserve(agpu_ctx *ctx, int64_t bytes)
 		ctx->arena.slabs.push_back(s);
 	}
 	TRY(stream_sync(ctx));
+#endif
+	return AGPU_OK;
+}
+
+int agpu_blocking_sync(agpu_ctx *ctx, int on)
+{
+	if(!ctx) return AGPU_ERR_ARG;
+#ifndef AGPU_EMU
+	ctx->blocking_sync = on != 0;
+#else
+	(void)on;
 #endif
 	return AGPU_OK;
 }

@@ -46,6 +46,10 @@ struct agpu_ctx
 	// side stream: runs the few-but-long launches of a size-binned kernel pair next to the bulk launch on `stream`
 	cudaStream_t side = NULL;
 	void *ev_fork = NULL, *ev_join = NULL;
+	// host waits: spin on the stream (lowest latency) or sleep on an event created with cudaEventBlockingSync (many host threads
+	// per core, e.g. eight ranks with a stream pool each on one box)
+	bool blocking_sync = false;
+	void *ev_sync = NULL;
 	// optional per-kernel timing (CUDA events around every launch on the ctx stream)
 	bool profiling = false;
 	std::vector<agpu_prof_rec> prof;
@@ -172,7 +176,13 @@ inline int d2h(agpu_ctx *ctx, void *h, const void *d, size_t bytes) { if(bytes =
 inline int d2d(agpu_ctx *ctx, void *d, const void *s, size_t bytes) { if(bytes == 0) return AGPU_OK; return cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, ctx->stream) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA; }
 inline int stream_sync(agpu_ctx *ctx)
 {
-	cudaError_t e = cudaStreamSynchronize(ctx->stream);
+	cudaError_t e;
+	if(ctx->blocking_sync && ctx->ev_sync)
+	{
+		e = cudaEventRecord((cudaEvent_t)ctx->ev_sync, ctx->stream);
+		if(e == cudaSuccess) e = cudaEventSynchronize((cudaEvent_t)ctx->ev_sync);
+	}
+	else e = cudaStreamSynchronize(ctx->stream);
 	if(e != cudaSuccess) { ctx->last_error = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e); return AGPU_ERR_CUDA; }
 	e = cudaGetLastError();
 	if(e != cudaSuccess) { ctx->last_error = std::string("kernel launch: ") + cudaGetErrorString(e); return AGPU_ERR_CUDA; }

@@ -76,7 +76,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
-               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_reserved", "agpu_reserve"]
+               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync"]
 
 
 def load(lib_path=None):
@@ -95,6 +95,7 @@ def load(lib_path=None):
     L.agpu_reserved.restype = C.c_int64
     L.agpu_reserved.argtypes = [C.c_void_p]
     L.agpu_reserve.argtypes = [C.c_void_p, C.c_int64]
+    L.agpu_blocking_sync.argtypes = [C.c_void_p, C.c_int]
     L.agpu_batch_upload.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
     L.agpu_batch_adopt.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
     L.agpu_batch_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -186,6 +187,9 @@ class Context:
 
     def reserve(self, nbytes):
         self.check(self.L.agpu_reserve(self.h, int(nbytes)), "agpu_reserve")
+
+    def blocking_sync(self, on=True):
+        self.check(self.L.agpu_blocking_sync(self.h, 1 if on else 0), "agpu_blocking_sync")
 
     def profile(self, on=True):
         self.check(self.L.agpu_profile_enable(self.h, 1 if on else 0), "agpu_profile_enable")

@@ -4,14 +4,22 @@ here a few host threads each own an agpu_ctx (= one CUDA stream) and take whole 
 of a region) from a queue: upload from pinned host memory -> agpu_batch_bridge_all -> results back.  While one
 stream computes, another stream's host->device copy is in flight on the copy engine, so the PCIe transfer of
 batch i+1 hides behind the kernels of batch i.  The ABI is re-entrant across contexts."""
+import os
 import threading
 
 from . import gpu as G
 
 
 class Pipeline:
-    def __init__(self, device=0, n_streams=3, lib_path=None):
+    def __init__(self, device=0, n_streams=3, lib_path=None, blocking_sync=None):
         self.ctxs = [G.Context(device, lib_path=lib_path) for _ in range(max(1, n_streams))]
+        if blocking_sync is None:
+            # spinning waits are the fastest as long as every waiting thread has a core of its own; with one stream pool per
+            # rank and several ranks per box they do not
+            ranks = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+            blocking_sync = ranks * (len(self.ctxs) + 1) > (os.cpu_count() or 1) // 2
+        for c in self.ctxs:
+            c.blocking_sync(blocking_sync)
 
     def close(self):
         for c in self.ctxs:

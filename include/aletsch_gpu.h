@@ -126,6 +126,10 @@ int64_t agpu_launch_count(agpu_ctx *ctx);
 int64_t agpu_reserved(agpu_ctx *ctx);
 int agpu_reserve(agpu_ctx *ctx, int64_t bytes);
 
+/* how the host waits for the stream inside the stages: 0 (default) spins, lowest latency; 1 sleeps on a blocking event, for
+ * boxes where the host threads of all contexts outnumber the cores */
+int agpu_blocking_sync(agpu_ctx *ctx, int on);
+
 /* optional per-kernel timing: CUDA events around every launch of this context.  agpu_profile_read
  * synchronises and writes "kernel_name\tms\tlaunches\n" lines (cumulative since the last reset). */
 int agpu_profile_enable(agpu_ctx *ctx, int on);
