@@ -93,8 +93,8 @@ def lib():
 
 
 def _np(ptr, n, dtype):
-    if n == 0:
-        return np.zeros(0, dtype=dtype)
+    if n == 0 or not ptr:
+        return np.zeros(n, dtype=dtype)       # e.g. the one-entry cigar_off of a sample without records
     return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(n,)).copy()
 
 

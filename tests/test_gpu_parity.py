@@ -168,6 +168,24 @@ def test_bam_file_to_device(ctx, tmp_path):
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and outs[0][0]["bridged"] > 0
 
 
+def test_single_cell_group_resolve(ctx, checkers):
+    """configs[3]-style input: many cells, each expressing a fraction of the genes, clustered with a large -c: one bundle group
+    of many hundred small graphs (beyond the one-CTA limit of the batched kernel -> the tiled AND-popcount kernels)"""
+    batch, lt = parity.make_batch(H.SYNTH_SINGLE, 1200, samples=500, chrom_len=400_000, expressed_fraction=0.3)
+    gp, op = parity.params_pair(lt, max_group_size=2000, min_grouping_similarity=0.2)
+    chk = checkers.get("ref") or next(iter(checkers.values()))
+    hs = [chk.new_bundle(batch.bundle(k), op) for k in range(batch.n_bundles)]
+    lists = [chk.run(h, "evidence")[1]["splices"] for h in hs]
+    _, gr = chk.group_resolve(hs, op)
+    for h in hs:
+        chk.free_bundle(h)
+    want = [gr["gvv_val"][gr["gvv_off"][i]:gr["gvv_off"][i + 1]].tolist() for i in range(len(gr["gvv_off"]) - 1)]
+    assert batch.n_bundles > 700
+    assert G.group_resolve(ctx, lists, gp) == want
+    assert G.group_resolve_batch(ctx, [lists], gp)[0] == want
+    assert max(len(g) for g in want) > 20
+
+
 def test_std_sort_permutation(ctx):
     """the device re-implementation of libstdc++'s introsort against the real std::sort on heavily tied keys"""
     import ctypes as C
