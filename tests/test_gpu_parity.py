@@ -186,6 +186,38 @@ def test_single_cell_group_resolve(ctx, checkers):
     assert max(len(g) for g in want) > 20
 
 
+def test_packing_contract_violations_are_reported(ctx):
+    """agpu_batch_evidence verifies the packing contract of agpu_batch_in on the device and returns AGPU_ERR_INPUT (-4)"""
+    import numpy as np
+    import fuzz
+    gp, _ = parity.params_pair(H.FR_FIRST)
+
+    def run(mutate, rpos=True):
+        b = fuzz.random_batch(5, n_bundles=3, max_hits=30)
+        mutate(b.a)
+        v = b.view()
+        if not rpos:
+            v.rpos = None
+        bt = ctx.upload(v, keepalive=b)
+        try:
+            bt.evidence(gp)
+        finally:
+            bt.free()
+
+    run(lambda a: None)                                                   # the untouched batch is fine
+    cases = {"hit order": lambda a: a["pos"].__setitem__(1, a["pos"][0] - 5),
+             "duplicate": lambda a: (a["pos"].__setitem__(1, a["pos"][0]), a["rpos"].__setitem__(1, a["rpos"][0]),
+                                     a["cigar"].__setitem__(slice(int(a["cigar_off"][1]), int(a["cigar_off"][2])), 0)),
+             "strand": lambda a: a["strand"].__setitem__(1, ord("-") if a["strand"][0] == ord("+") else ord("+")),
+             "rpos": lambda a: a["rpos"].__setitem__(0, a["rpos"][0] + 1)}
+    for name, mut in cases.items():
+        with pytest.raises(G.AgpuError) as e:
+            run(mut)
+        assert "failed with -4" in str(e.value), (name, str(e.value))
+    # a wrong rpos cannot happen when the device derives it
+    run(cases["rpos"], rpos=False)
+
+
 def test_std_sort_permutation(ctx):
     """the device re-implementation of libstdc++'s introsort against the real std::sort on heavily tied keys"""
     import ctypes as C
