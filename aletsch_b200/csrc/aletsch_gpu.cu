@@ -155,7 +155,6 @@ struct agpu_batch
 	dbuf<int32_t> pt_d;
 	int64_t n_pts = 0;
 	dbuf<int32_t> spl, hit_nspl, hit_bundle;
-	dbuf<u64> hit_hash;
 	chainset_state hcst, fcst;
 	// segments
 	bool cov_dirty = true;
@@ -505,7 +504,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
 	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
 	b->group_pass = false;
-	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx); b->hit_hash.release(ctx);
+	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx);
 	b->hcst.release(ctx); b->fcst.release(ctx);
 	b->seg_off.release(ctx);
 	b->seg_l.release(ctx); b->seg_r.release(ctx); b->seg_c.release(ctx); b->seg_nhead.release(ctx); b->seg_psum.release(ctx);
@@ -695,17 +694,17 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(stream_sync(ctx));
 	if(b->ltot >= ((int64_t)1 << 32) - 64) { ctx->last_error = "batch spans 2^32 or more window positions: split it"; return AGPU_ERR_CAPACITY; }
 	TRY(b->border.alloc(ctx, b->ltot / 32 + 8, true));
-	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1)); TRY(b->hit_hash.alloc(ctx, nh + 1));
+	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1));
 	dbuf<int32_t> n_spliced;
 	TRY(n_spliced.alloc(ctx, nb + 1, true));
-	LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_hash.p,
+	LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p,
 			b->hit_bundle.p, n_spliced.p, b->err.p);
 	// hcst
 	chainset_state &cs = b->hcst;
 	cs.val = b->spl.p; cs.voff32 = b->h.cigar_off; cs.voff64 = NULL; cs.elem_len = b->hit_nspl.p;
 	TRY(chainset_build(ctx, b, cs, nh, b->h.bundle_hit_off, b->hit_off_host, n_spliced.p));
 	n_spliced.release(ctx);
-	LAUNCH_T(ctx, k_hcst_insert, nh, b->h, b->hit_nspl.p, b->hit_hash.p, b->hit_bundle.p, b->spl.p, cs.reg_off.p, cs.slot_word.p,
+	LAUNCH_T(ctx, k_hcst_insert, nh, b->h, b->hit_nspl.p, b->hit_bundle.p, b->spl.p, cs.reg_off.p, cs.slot_word.p,
 			cs.slot_first.p, cs.slot_cnt.p, cs.elem_slot.p, b->err.p);
 	TRY(cs.val_base.alloc(ctx, nb + 1));
 	LAUNCH_T(ctx, k_gather_off, nb + 1, nb + 1, b->h.bundle_hit_off, b->h.cigar_off, cs.val_base.p);

@@ -193,7 +193,7 @@ HD u64 chain_hash(const int32_t *v, int n)
 //             k_cov_add once the borders have been ranked, see the coverage section below)
 //   splices : (p - len, p) for every inner BAM_CREF_SKIP, written at spl[cigar_off[i] ...]
 KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
-		int32_t *spl, int32_t *hit_nspl, u64 *hit_hash, const int32_t *hit_bundle, int32_t *n_spliced, int *err)
+		int32_t *spl, int32_t *hit_nspl, const int32_t *hit_bundle, int32_t *n_spliced, int *err)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
@@ -225,7 +225,6 @@ KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u
 	}
 	if(p != h.rpos[i]) atomicAdd(&err[ERR_RPOS], 1);
 	hit_nspl[i] = ns;
-	hit_hash[i] = ns > 0 ? chain_hash(out, ns) : 0;
 #ifndef AGPU_EMU
 	// hits of a bundle are neighbours: one atomic per (warp, bundle) instead of one per spliced hit
 	const unsigned act = __activemask();
@@ -302,7 +301,7 @@ DEV int64_t chain_table_insert(u64 *slot_word, int64_t reg0, u32 reg_size, const
 }
 
 // ---- E3: one thread per hit with splices: insert into hcst table, count xs class, track first hit
-KERNEL k_hcst_insert(hits_dev h, const int32_t *hit_nspl, const u64 *hit_hash, const int32_t *hit_bundle, const int32_t *spl,
+KERNEL k_hcst_insert(hits_dev h, const int32_t *hit_nspl, const int32_t *hit_bundle, const int32_t *spl,
 		const int64_t *reg_off, u64 *slot_word, int32_t *slot_first, int32_t *slot_cnt, int64_t *hit_slot, int *err)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -314,7 +313,7 @@ KERNEL k_hcst_insert(hits_dev h, const int32_t *hit_nspl, const u64 *hit_hash, c
 	s.val = spl; s.off = NULL; s.off32 = h.cigar_off; s.len = hit_nspl;
 	int64_t r0 = reg_off[b];
 	u32 rs = (u32)(reg_off[b + 1] - r0);
-	int64_t sl = chain_table_insert(slot_word, r0, rs, s, i, hit_hash[i]);
+	int64_t sl = chain_table_insert(slot_word, r0, rs, s, i, chain_hash(spl + h.cigar_off[i], hit_nspl[i]));
 	if(sl < 0) { atomicAdd(&err[ERR_CAP], 1); return; }
 	hit_slot[i] = sl;
 	int x = 0;

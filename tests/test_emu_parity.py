@@ -176,6 +176,19 @@ def test_packing_contract_violations_are_reported(ctx):
     run(cases["rpos"], rpos=False)
 
 
+def test_huge_bundle_parity(ctx, checkers):
+    """two bundles of ~190,000 hits each over overlapping genes (graphs of thousands of vertices, thousands of piers): the wide
+    CTA paths of the per-bundle kernels, big qname / cluster groups, long DP jobs"""
+    batch, lt = parity.make_batch(H.SYNTH_PAIRED, 500000, chrom_len=1_000_000, seed=5, gene_spacing=1500)
+    assert batch.n_bundles <= 4 and batch.n_hits > 300000
+    gp, op = parity.params_pair(lt)
+    chk = checkers.get("ref") or next(iter(checkers.values()))
+    stats = {}
+    bad = parity.compare_full(ctx, batch, chk, gp, op, stats)
+    assert not bad, bad[:3]
+    assert stats["vertices"] > 3000 and stats["piers"] > 3000 and stats["bridged"] > 50000
+
+
 def test_std_sort_permutation(ctx):
     """the device re-implementation of libstdc++'s introsort against the real std::sort on heavily tied keys"""
     import ctypes as C
