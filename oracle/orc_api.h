@@ -32,6 +32,21 @@ typedef struct orc_bundle_in
 	const uint32_t *cigar;       /* raw BAM CIGAR ops, len<<4|op */
 } orc_bundle_in;
 
+/* decoded, coordinate-sorted records of one sample (what the BAM file holds), for the record loop of generator::resolve */
+typedef struct orc_records_in
+{
+	int64_t n;
+	int32_t n_chrom;
+	const int32_t *chrom_len;
+	const int32_t *tid, *pos, *mpos, *isize;
+	const uint16_t *flag;
+	const uint8_t *mapq;
+	const uint8_t *xs;           /* goes into the record as an XS:A tag ('.': no tag) */
+	const uint64_t *qid;
+	const uint32_t *cigar_off;
+	const uint32_t *cigar;
+} orc_records_in;
+
 /* the values of util/parameters.h + rnacore/sample_profile.h that the path reads */
 typedef struct orc_params
 {
@@ -75,6 +90,11 @@ const void *orc_bag_data(void *bag, int i);
 	int P##_bundle_phase(void *b, void *bag); \
 	int P##_group_bridge(void **bs, int n, void *bag); \
 	int P##_group_resolve(void **bs, int n, const orc_params *prm, void *bag);
+
+/* reference build only: generator::resolve (meta/generator.cc:51-227) over the records served through the htslib stand-in;
+ * dumps the bundles it creates (gen_off, gen_bundle = tid lpos rpos strand per bundle, gen_pos / rpos / mpos / isize / flag /
+ * strand / xs per stored hit).  Returns the number of bundles. */
+int ref_generate(const orc_records_in *in, const orc_params *prm, int use_second_alignment, void *bag);
 
 ORC_DECLARE(ref)
 ORC_DECLARE(orc)

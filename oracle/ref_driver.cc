@@ -16,6 +16,7 @@
 
 #include "bundle.h"
 #include "bundle_group.h"
+#include "generator.h"
 #include "graph_builder.h"
 #include "graph_cluster.h"
 #include "bridge_solver.h"
@@ -386,6 +387,71 @@ int ref_bundle_phase(void *b, void *bagp)
 		pc.push_back(it->second);
 	}
 	return (int)pc.size();
+}
+
+// generator::resolve + generator::generate (meta/generator.cc:51-227) on an in-memory file behind the htslib stand-in: one
+// region per chromosome that starts at its first record (start_off is a record index in the stand-in's bgzf_seek)
+int ref_generate(const orc_records_in *in, const orc_params *prm, int use_second_alignment, void *bagp)
+{
+	orc_bag &bag = *(orc_bag*)bagp;
+	parameters cfg;
+	sample_profile sp(0, 1000000);
+	apply_params(prm, cfg, sp);
+	cfg.use_second_alignment = use_second_alignment != 0;
+	hts_shim_file file;
+	for(int k = 0; k < in->n_chrom; k++)
+	{
+		file.target_name.push_back("chr" + std::to_string(k + 1));
+		file.target_len.push_back((uint32_t)in->chrom_len[k]);
+	}
+	std::vector<int64_t> first(in->n_chrom, -1);
+	for(int64_t i = 0; i < in->n; i++)
+	{
+		uint32_t c0 = in->cigar_off[i], c1 = in->cigar_off[i + 1];
+		file.records.push_back(hts_shim_make_record(in->tid[i], in->pos[i], in->mapq[i], in->flag[i], in->tid[i], in->mpos[i], in->isize[i],
+				qname_of(in->qid[i]), in->cigar + c0, c1 - c0, (char)in->xs[i], '.', 1, 1, -1));
+		if(in->tid[i] >= 0 && in->tid[i] < in->n_chrom && first[in->tid[i]] < 0) first[in->tid[i]] = i;
+	}
+	char name[64];
+	snprintf(name, sizeof(name), "mem:%p", (const void*)in);
+	hts_shim_register(name, file);
+	sp.align_file = name;
+	sp.start1.assign(in->n_chrom, std::vector<int32_t>(1, 0));
+	sp.start2.assign(in->n_chrom, std::vector<int32_t>(1, 0));
+	sp.end1.assign(in->n_chrom, std::vector<int32_t>(1, 0x7fffffff));
+	sp.end2.assign(in->n_chrom, std::vector<int32_t>(1, 0x7fffffff));
+	sp.start_off.assign(in->n_chrom, std::vector<off_t>(1, 0));
+	std::vector<int32_t> &off = bag.ints("gen_off"), &gb = bag.ints("gen_bundle");
+	std::vector<int32_t> &gp = bag.ints("gen_pos"), &gr = bag.ints("gen_rpos"), &gm = bag.ints("gen_mpos"), &gi = bag.ints("gen_isize");
+	std::vector<int32_t> &gf = bag.ints("gen_flag"), &gs = bag.ints("gen_strand"), &gx = bag.ints("gen_xs");
+	off.clear(); gb.clear(); gp.clear(); gr.clear(); gm.clear(); gi.clear(); gf.clear(); gs.clear(); gx.clear();
+	off.push_back(0);
+	int nb = 0;
+	for(int t = 0; t < in->n_chrom; t++)
+	{
+		if(first[t] < 0) continue;
+		sp.start_off[t][0] = (off_t)first[t];
+		std::vector<bundle> vcb;
+		{
+			generator gt(sp, vcb, cfg, t, 0);
+			gt.resolve();
+		}
+		for(size_t k = 0; k < vcb.size(); k++)
+		{
+			bundle &bd = vcb[k];
+			gb.push_back(bd.tid); gb.push_back(bd.lpos); gb.push_back(bd.rpos); gb.push_back((int32_t)bd.strand);
+			for(size_t i = 0; i < bd.hits.size(); i++)
+			{
+				const hit &h = bd.hits[i];
+				gp.push_back(h.pos); gr.push_back(h.rpos); gm.push_back(h.mpos); gi.push_back(h.isize); gf.push_back(h.flag);
+				gs.push_back((int32_t)h.strand); gx.push_back((int32_t)h.xs);
+			}
+			off.push_back((int32_t)gp.size());
+			nb++;
+		}
+	}
+	hts_shim_clear();
+	return nb;
 }
 
 int ref_group_bridge(void **bs, int n, void *bagp)
