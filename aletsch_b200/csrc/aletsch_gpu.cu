@@ -10,6 +10,7 @@
 #include "k_similarity.h"
 #include "k_group.h"
 #include "k_phase.h"
+#include "k_revise.h"
 
 #include <algorithm>
 #include <atomic>
@@ -175,6 +176,12 @@ struct agpu_batch
 	dbuf<int32_t> ph_val, ph_len, ph_cnt;
 	dbuf<int64_t> ph_off, ph_boff;
 
+	// boundary revision (identify_boundaries / remove_false_boundaries): added edges and vertex annotations, in the vertex
+	// layout of the graphs
+	bool revise_built = false;
+	dbuf<int32_t> rv_nstart, rv_nend, rv_addv, rv_leave, rv_come;
+	dbuf<double> rv_addw, rv_lratio, rv_cratio;
+
 	// group-level re-bridge (assembler::bridge): the combined bundles of the clusters as a batch of their own
 	agpu_batch *cb = NULL;
 	dbuf<int32_t> g_remap, g_members, g_first;
@@ -237,6 +244,7 @@ void agpu_default_params(agpu_params *p)
 	p->min_guaranteed_edge_weight = 0.01;
 	p->min_grouping_similarity = 0.10;
 	p->max_grouping_similarity = 0.80;
+	p->min_boundary_log_ratio = 2.0;
 }
 
 int agpu_create(int device, void *stream, agpu_ctx **out)
@@ -501,6 +509,8 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	b->pt_g.release(ctx); b->pt_d.release(ctx); b->n_pts = 0;
 	b->ph_val.release(ctx); b->ph_len.release(ctx); b->ph_cnt.release(ctx); b->ph_off.release(ctx); b->ph_boff.release(ctx);
 	b->phase_built = false; b->n_phase = 0; b->n_phase_val = 0;
+	b->rv_nstart.release(ctx); b->rv_nend.release(ctx); b->rv_addv.release(ctx); b->rv_leave.release(ctx); b->rv_come.release(ctx);
+	b->rv_addw.release(ctx); b->rv_lratio.release(ctx); b->rv_cratio.release(ctx); b->revise_built = false;
 	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
 	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
 	b->group_pass = false;
@@ -760,5 +770,6 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 #include "abi_fetch.inc"
 #include "abi_group.inc"
 #include "abi_phase.inc"
+#include "abi_revise.inc"
 
 }

@@ -22,7 +22,8 @@ class Params(C.Structure):
                 ("bridge_dp_solution_size", C.c_int32), ("bridge_dp_stack_size", C.c_int32), ("insertsize_low", C.c_int32),
                 ("insertsize_high", C.c_int32), ("max_group_size", C.c_int32), ("max_num_junctions_to_combine", C.c_int32),
                 ("min_subregion_overlap", C.c_double), ("min_guaranteed_edge_weight", C.c_double),
-                ("min_grouping_similarity", C.c_double), ("max_grouping_similarity", C.c_double)]
+                ("min_grouping_similarity", C.c_double), ("max_grouping_similarity", C.c_double),
+                ("min_boundary_log_ratio", C.c_double)]
 
 
 P32 = C.POINTER(C.c_int32)
@@ -60,6 +61,11 @@ class BridgeView(C.Structure):
                 ("whole_off", P64), ("whole", P32)]
 
 
+class ReviseView(C.Structure):
+    _fields_ = [("edge_off", P64), ("edge", P32), ("edge_w", PF), ("vert_off", P64), ("unbridge", P32), ("unbridge_ratio", PF),
+                ("n_edges", C.c_int64), ("n_vertices", C.c_int64)]
+
+
 class PhaseView(C.Structure):
     _fields_ = [("phase_off", P64), ("coord_off", P64), ("coords", P32), ("count", P32), ("n_phases", C.c_int64)]
 
@@ -76,7 +82,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
-               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync"]
+               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync"]
 
 
 def load(lib_path=None):
@@ -114,6 +120,8 @@ def load(lib_path=None):
     L.agpu_batch_bundle_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.agpu_batch_phase_set.argtypes = [C.c_void_p, C.c_void_p]
     L.agpu_phase_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PhaseView)]
+    L.agpu_batch_revise.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params)]
+    L.agpu_revise_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ReviseView)]
     L.agpu_batch_group_bridge.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params)]
     L.agpu_group_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EvidenceView), C.POINTER(ChainsetView), C.POINTER(GraphView), C.POINTER(P32)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -136,6 +144,7 @@ def default_params(**kw):
     p.max_group_size, p.max_num_junctions_to_combine = 200, 500
     p.min_subregion_overlap, p.min_guaranteed_edge_weight = 1.5, 0.01
     p.min_grouping_similarity, p.max_grouping_similarity = 0.10, 0.80
+    p.min_boundary_log_ratio = 2.0
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -408,6 +417,24 @@ class Batch:
         for k in range(nb):
             a, b = int(po[k]), int(po[k + 1])
             out.append({"phase_off": (co[a:b + 1] - co[a]).astype(np.int32), "phase_val": cv[int(co[a]):int(co[b])], "phase_cnt": cc[a:b]})
+        return out
+
+    def revise(self, p, fetch=True):
+        """identify_boundaries + remove_false_boundaries on the bundles' graphs; per bundle the oracle's rev_edge / rev_edge_d /
+        rev_vert / rev_vert_d"""
+        self._run("revise", p)
+        if not fetch:
+            return None
+        v = ReviseView()
+        self.ctx.check(self.ctx.L.agpu_revise_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_revise_fetch")
+        nb, ne, nv = self.nb, int(v.n_edges), int(v.n_vertices)
+        eo, vo = _arr(v.edge_off, nb + 1, np.int64), _arr(v.vert_off, nb + 1, np.int64)
+        e, ew = _arr(v.edge, 2 * ne), _arr(v.edge_w, ne, np.float64)
+        c, r = _arr(v.unbridge, 2 * nv), _arr(v.unbridge_ratio, 2 * nv, np.float64)
+        out = []
+        for k in range(nb):
+            a, b, x, y = int(eo[k]), int(eo[k + 1]), int(vo[k]), int(vo[k + 1])
+            out.append({"rev_edge": e[2 * a:2 * b], "rev_edge_d": ew[a:b], "rev_vert": c[2 * x:2 * y], "rev_vert_d": r[2 * x:2 * y]})
         return out
 
     def group_bridge(self, groups, p):

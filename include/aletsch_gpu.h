@@ -73,6 +73,7 @@ typedef struct agpu_params
 	double min_guaranteed_edge_weight;     /* 0.01 */
 	double min_grouping_similarity;        /* -s, 0.10 */
 	double max_grouping_similarity;        /* 0.80 */
+	double min_boundary_log_ratio;         /* 2.0 (identify_boundaries, util/parameters.cc:82) */
 } agpu_params;
 
 #define AGPU_MAX_DP_SOLUTIONS 16
@@ -288,6 +289,28 @@ typedef struct agpu_phase_view
 } agpu_phase_view;
 int agpu_batch_phase_set(agpu_ctx *ctx, agpu_batch *b);
 int agpu_phase_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_phase_view *v);
+
+/* ---- boundary revision: the revising half of assembler::transform(bd, gr, true) (meta/assembler.cc:930-944) on the bundles'
+ * own splice graphs.  identify_boundaries (rnacore/graph_reviser.cc:1068-1283) adds a start edge 0 -> a / an end edge b -> n
+ * wherever log(2 + maxcov) / log(2 + weight entering / leaving) of a continuous run of vertices reaches
+ * min_boundary_log_ratio, best ratio first, until none is left; remove_false_boundaries (:1285-1377) then records, for the
+ * vertices that carry an end (start) edge, how many paired fragments that are still unbridged (type 0) leave (enter) there,
+ * and log(1 + count + w) - log(1 + w).  The graph keeps its vertices, so locate_vertex and the phase set are unaffected; the
+ * refine_splice_graph that follows in the reference removes nothing.  Call after agpu_batch_graph and the bridging calls.
+ * The view lists, per bundle, the added edges in the order the reference adds them (src dst, vertex numbers of
+ * agpu_graph_view) with their weights, and the four annotations of every vertex. */
+typedef struct agpu_revise_view
+{
+	const int64_t *edge_off;            /* [NB+1] */
+	const int32_t *edge;                /* [2E'] src dst */
+	const double *edge_w;               /* [E'] maxcov - entering (leaving) weight */
+	const int64_t *vert_off;            /* [NB+1]; V = P + 2 per bundle */
+	const int32_t *unbridge;            /* [2V] unbridge_leaving_count unbridge_coming_count (rnacore/vertex_info.h:38-41) */
+	const double *unbridge_ratio;       /* [2V] unbridge_leaving_ratio unbridge_coming_ratio */
+	int64_t n_edges, n_vertices;
+} agpu_revise_view;
+int agpu_batch_revise(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p);
+int agpu_revise_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_revise_view *v);
 
 /* ---- group-level re-bridge: assembler::bridge (meta/assembler.cc:977-1018) for many clusters of bundles at once ----
  * Cluster g holds the bundles group_bundles[group_off[g] .. group_off[g+1]) in the order of the reference's `gv` (>= 2

@@ -68,6 +68,7 @@ typedef struct orc_params
 	double min_guaranteed_edge_weight;
 	double min_grouping_similarity;
 	double max_grouping_similarity;
+	double min_boundary_log_ratio;
 } orc_params;
 
 /* result bag: named flat arrays, kind 0 = int32, 1 = float64 */
@@ -88,6 +89,7 @@ const void *orc_bag_data(void *bag, int i);
 	int P##_bundle_graph(void *b, void *bag); \
 	int P##_bundle_bridge(void *b, void *bag); \
 	int P##_bundle_phase(void *b, void *bag); \
+	int P##_bundle_revise(void *b, void *bag); \
 	int P##_group_bridge(void **bs, int n, void *bag); \
 	int P##_group_resolve(void **bs, int n, const orc_params *prm, void *bag);
 

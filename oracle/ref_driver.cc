@@ -19,6 +19,7 @@
 #include "generator.h"
 #include "graph_builder.h"
 #include "graph_cluster.h"
+#include "graph_reviser.h"
 #include "bridge_solver.h"
 #include "essential.h"
 #include "parameters.h"
@@ -26,6 +27,7 @@
 #include "sample_profile.h"
 
 #include <cmath>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -58,6 +60,7 @@ void apply_params(const orc_params *p, parameters &cfg, sample_profile &sp)
 	cfg.max_num_junctions_to_combine = p->max_num_junctions_to_combine;
 	cfg.min_grouping_similarity = p->min_grouping_similarity;
 	cfg.max_grouping_similarity = p->max_grouping_similarity;
+	cfg.min_boundary_log_ratio = p->min_boundary_log_ratio;
 	sp.library_type = p->library_type;
 	sp.insertsize_low = p->insertsize_low;
 	sp.insertsize_high = p->insertsize_high;
@@ -387,6 +390,80 @@ int ref_bundle_phase(void *b, void *bagp)
 		pc.push_back(it->second);
 	}
 	return (int)pc.size();
+}
+
+// the revising half of assembler::transform(bd, gr, true) (meta/assembler.cc:930-944) on the bundle in its current state
+// (call after ref_bundle_bridge, as assembler::assemble does): identify_boundaries, remove_false_boundaries,
+// refine_splice_graph.  The loop of identify_boundaries is restated here around the reference's own
+// identify_start_boundary / identify_end_boundary so that the order in which the edges are added can be dumped
+// (rev_edge = src dst per added edge, rev_edge_d = weight); rev_graph_edge / rev_graph_edge_d is the whole revised graph in
+// out-edge order, rev_vert / rev_vert_d the unbridge_* annotations of every vertex.
+int ref_bundle_revise(void *b, void *bagp)
+{
+	ref_handle *h = (ref_handle*)b;
+	orc_bag &bag = *(orc_bag*)bagp;
+	splice_graph gr;
+	graph_builder gb(h->bd, h->cfg, h->sp);
+	gb.build(gr);
+	gr.build_vertex_index();
+	std::vector<int32_t> &re = bag.ints("rev_edge");
+	std::vector<double> &rw = bag.reals("rev_edge_d");
+	re.clear(); rw.clear();
+	int n = (int)gr.num_vertices() - 1;
+	std::set<std::pair<int, int> > seen;
+	for(int i = 0; i <= n; i++)
+	{
+		PEEI pe = gr.out_edges(i);
+		for(edge_iterator it = pe.first; it != pe.second; ++it) seen.insert(std::make_pair((*it)->source(), (*it)->target()));
+	}
+	while(true)
+	{
+		bool b1 = identify_start_boundary(gr, h->cfg.min_boundary_log_ratio);
+		if(b1)
+		{
+			PEEI pe = gr.out_edges(0);
+			for(edge_iterator it = pe.first; it != pe.second; ++it)
+			{
+				std::pair<int, int> k((*it)->source(), (*it)->target());
+				if(seen.find(k) != seen.end()) continue;
+				seen.insert(k);
+				re.push_back(k.first); re.push_back(k.second); rw.push_back(gr.get_edge_weight(*it));
+			}
+		}
+		bool b2 = identify_end_boundary(gr, h->cfg.min_boundary_log_ratio);
+		if(b2)
+		{
+			PEEI pe = gr.in_edges(n);
+			for(edge_iterator it = pe.first; it != pe.second; ++it)
+			{
+				std::pair<int, int> k((*it)->source(), (*it)->target());
+				if(seen.find(k) != seen.end()) continue;
+				seen.insert(k);
+				re.push_back(k.first); re.push_back(k.second); rw.push_back(gr.get_edge_weight(*it));
+			}
+		}
+		if(b1 == false && b2 == false) break;
+	}
+	remove_false_boundaries(gr, h->bd, h->cfg);
+	refine_splice_graph(gr);
+	std::vector<int32_t> &ge = bag.ints("rev_graph_edge");
+	std::vector<double> &gw = bag.reals("rev_graph_edge_d");
+	std::vector<int32_t> &vc = bag.ints("rev_vert");
+	std::vector<double> &vr = bag.reals("rev_vert_d");
+	ge.clear(); gw.clear(); vc.clear(); vr.clear();
+	for(int i = 0; i <= n; i++)
+	{
+		PEEI pe = gr.out_edges(i);
+		for(edge_iterator it = pe.first; it != pe.second; ++it)
+		{
+			ge.push_back((*it)->source()); ge.push_back((*it)->target());
+			gw.push_back(gr.get_edge_weight(*it));
+		}
+		const vertex_info &vi = gr.get_vertex_info(i);
+		vc.push_back(vi.unbridge_leaving_count); vc.push_back(vi.unbridge_coming_count);
+		vr.push_back(vi.unbridge_leaving_ratio); vr.push_back(vi.unbridge_coming_ratio);
+	}
+	return (int)rw.size();
 }
 
 // generator::resolve + generator::generate (meta/generator.cc:51-227) on an in-memory file behind the htslib stand-in: one

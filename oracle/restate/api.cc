@@ -283,6 +283,33 @@ int orc_bundle_phase(void *b, void *bagp)
 	return (int)pc.size();
 }
 
+// identify_boundaries + remove_false_boundaries on the bundle's own splice graph, bundle in its current state
+int orc_bundle_revise(void *b, void *bagp)
+{
+	bundle &bd = *(bundle*)b;
+	orc_bag &bag = *(orc_bag*)bagp;
+	graph gr;
+	builder_out bo;
+	build_graph(bd, gr, bo);
+	revision rv;
+	revise_graph(bd, gr, rv);
+	std::vector<int32_t> &re = bag.ints("rev_edge");
+	std::vector<double> &rw = bag.reals("rev_edge_d");
+	std::vector<int32_t> &ge = bag.ints("rev_graph_edge");
+	std::vector<double> &gw = bag.reals("rev_graph_edge_d");
+	std::vector<int32_t> &vc = bag.ints("rev_vert");
+	std::vector<double> &vr = bag.reals("rev_vert_d");
+	re.clear(); rw.clear(); ge.clear(); gw.clear(); vc.clear(); vr.clear();
+	for(size_t i = 0; i < rv.added.size(); i++) { re.push_back(rv.added[i][0]); re.push_back(rv.added[i][1]); rw.push_back(rv.added_w[i]); }
+	for(int i = 0; i < gr.nv(); i++)
+	{
+		for(auto &pr : gr.out[i]) { ge.push_back(i); ge.push_back(pr.first); gw.push_back(gr.edges[pr.second].w); }
+		vc.push_back(rv.leave_cnt[i]); vc.push_back(rv.come_cnt[i]);
+		vr.push_back(rv.leave_ratio[i]); vr.push_back(rv.come_ratio[i]);
+	}
+	return (int)rw.size();
+}
+
 // assembler::bridge (meta/assembler.cc:977-1018) with combine_bundles (:152-175) and bundle::combine (meta/bundle.cc:90-107)
 int orc_group_bridge(void **bs, int n, void *bagp)
 {

@@ -106,10 +106,19 @@ struct bridge_path
 	bridge_path() : type(0), strand(0), choices(0), score(0) {}
 };
 
+struct revision
+{
+	std::vector<std::array<int, 2> > added;                  // boundary edges in the order they are added
+	std::vector<double> added_w;
+	std::vector<int> leave_cnt, come_cnt;                    // vertex_info::unbridge_* (rnacore/vertex_info.h:38-41)
+	std::vector<double> leave_ratio, come_ratio;
+};
+
 struct builder_out { std::vector<junction> junctions; std::vector<pexon> pexons; };
 
 void build_graph(const bundle &bd, graph &gr, builder_out &bo);
 void build_phase_set(const bundle &bd, const graph &gr, std::map<chain_t, int> &ps);
+void revise_graph(const bundle &bd, graph &gr, revision &rv);
 void build_fragments(bundle &bd);
 void cluster_fragments(graph &gr, bundle &bd, std::vector<cluster> &vc);
 void bridge_clusters(graph &gr, std::vector<cluster> &vc, const orc_params &prm, std::vector<bridge_path> &opt);

@@ -22,7 +22,8 @@ class Params(C.Structure):
                 ("bridge_dp_solution_size", C.c_int32), ("bridge_dp_stack_size", C.c_int32), ("insertsize_low", C.c_int32),
                 ("insertsize_high", C.c_int32), ("max_group_size", C.c_int32), ("max_num_junctions_to_combine", C.c_int32),
                 ("min_subregion_overlap", C.c_double), ("min_guaranteed_edge_weight", C.c_double),
-                ("min_grouping_similarity", C.c_double), ("max_grouping_similarity", C.c_double)]
+                ("min_grouping_similarity", C.c_double), ("max_grouping_similarity", C.c_double),
+                ("min_boundary_log_ratio", C.c_double)]
 
 
 def default_params(**kw):
@@ -31,7 +32,7 @@ def default_params(**kw):
                min_subregion_gap=15, min_subregion_length=15, max_reads_partition_gap=10, bridge_end_relaxing=10,
                bridge_dp_solution_size=10, bridge_dp_stack_size=5, insertsize_low=80, insertsize_high=500,
                max_group_size=200, max_num_junctions_to_combine=500, min_subregion_overlap=1.5,
-               min_guaranteed_edge_weight=0.01, min_grouping_similarity=0.10, max_grouping_similarity=0.80)
+               min_guaranteed_edge_weight=0.01, min_grouping_similarity=0.10, max_grouping_similarity=0.80, min_boundary_log_ratio=2.0)
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -61,7 +62,7 @@ class Checker:
         f("bundle_new").restype = C.c_void_p
         f("bundle_new").argtypes = [C.POINTER(BundleIn), C.POINTER(Params)]
         f("bundle_free").argtypes = [C.c_void_p]
-        for n in ("bundle_evidence", "bundle_fragments", "bundle_graph", "bundle_bridge", "bundle_phase"):
+        for n in ("bundle_evidence", "bundle_fragments", "bundle_graph", "bundle_bridge", "bundle_phase", "bundle_revise"):
             f(n).argtypes = [C.c_void_p, C.c_void_p]
         f("group_bridge").argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
         f("group_resolve").argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(Params), C.c_void_p]

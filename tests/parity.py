@@ -229,6 +229,42 @@ def compare_group_bridge(ctx, batch, checker, gp, op, groups, stats=None, first_
     return bad
 
 
+def compare_revise(ctx, batch, checker, gp, op, stats=None):
+    """identify_boundaries + remove_false_boundaries (rnacore/graph_reviser.cc:1068-1377) after bundle::bridge, as
+    assembler::assemble runs transform(bd, gr, true); also the whole revised graph = built edges + added ones"""
+    bad = []
+    bt = ctx.upload(batch.view(), keepalive=batch)
+    bt.bridge_all(gp)
+    bt.graph(gp)
+    gr = bt.fetch_graph()
+    rv = bt.revise(gp)
+    bt.free()
+    added = marked = 0
+    for k in range(batch.n_bundles):
+        h = checker.new_bundle(batch.bundle(k), op)
+        checker.run(h, "fragments")
+        checker.run(h, "bridge")
+        n, ref = checker.run(h, "revise")
+        checker.free_bundle(h)
+        wk = "bundle %d" % k
+        added += len(ref["rev_edge_d"])
+        marked += int((ref["rev_vert"] > 0).sum())
+        cmp_int("rev_edge", ref["rev_edge"], rv[k]["rev_edge"], wk, bad)
+        cmp_f64("rev_edge_d", ref["rev_edge_d"], rv[k]["rev_edge_d"], wk, bad)
+        cmp_int("rev_vert", ref["rev_vert"], rv[k]["rev_vert"], wk, bad)
+        cmp_f64("rev_vert_d", ref["rev_vert_d"], rv[k]["rev_vert_d"], wk, bad)
+        # the revised graph in out-edge order: alive built edges + added edges, sorted by (src, dst)
+        st = np.concatenate([gr[k]["edge_ins"].reshape(-1, 3)[:, :2], rv[k]["rev_edge"].reshape(-1, 2)])
+        w = np.concatenate([gr[k]["edge_ins_d"], rv[k]["rev_edge_d"]])
+        o = np.lexsort((st[:, 1], st[:, 0]))
+        cmp_int("rev_graph_edge", ref["rev_graph_edge"], st[o].reshape(-1).astype(np.int32), wk, bad)
+        cmp_f64("rev_graph_edge_d", ref["rev_graph_edge_d"], w[o], wk, bad)
+    if stats is not None:
+        stats["rev_added"] = added
+        stats["rev_marked"] = marked
+    return bad
+
+
 def compare_phase_set(ctx, batch, checker, gp, op, stats=None):
     """bundle_base::build_phase_set (rnacore/bundle_base.cc:338-418) after bundle::bridge, against the bundles' own splice
     graphs rebuilt from the updated evidence (transform(bd, gr, false))"""

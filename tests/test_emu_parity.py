@@ -72,6 +72,23 @@ def test_phase_set_parity(ctx, checkers, mode, templates):
         assert stats["phase_count"] > 0
 
 
+@pytest.mark.parametrize("mode,templates", [(H.SYNTH_PAIRED, 40000), (H.SYNTH_SINGLE, 20000), (H.SYNTH_LONG, 3000)])
+def test_revise_parity(ctx, checkers, mode, templates):
+    """identify_boundaries + remove_false_boundaries: added boundary edges in order, the revised graph, vertex annotations"""
+    assert checkers
+    batch, lt = parity.make_batch(mode, templates)
+    # 2.0 is the reference's default (few runs qualify in the synthetic transcriptome); lower thresholds make the rounds long
+    for ratio in (2.0, 1.1, 0.6):
+        gp, op = parity.params_pair(lt, min_boundary_log_ratio=ratio)
+        for name, chk in checkers.items():
+            stats = {}
+            bad = parity.compare_revise(ctx, batch, chk, gp, op, stats)
+            assert not bad, "%s ratio %.1f: %d mismatches, first: %s" % (name, ratio, len(bad), bad[:3])
+            assert ratio > 1.5 or stats["rev_added"] > 10
+            if mode == H.SYNTH_PAIRED:
+                assert stats["rev_marked"] > 0
+
+
 def test_lean_upload_matches_full(ctx):
     """rpos / flag / per-hit strand are optional in agpu_batch_in (include/aletsch_gpu.h)"""
     batch, lt = parity.make_batch(H.SYNTH_PAIRED, 20000)

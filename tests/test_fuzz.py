@@ -24,6 +24,9 @@ def run_seeds(ctx, checkers, seeds, big=False):
             if lt != H.UNSTRANDED:
                 bad = parity.compare_phase_set(ctx, batch, chk, gp, op)
                 assert not bad, "seed %d vs %s (phase set): %d mismatches, first: %s" % (seed, name, len(bad), bad[:3])
+                gr, orr = parity.params_pair(lt, min_boundary_log_ratio=(2.0 if seed % 2 else 0.9))
+                bad = parity.compare_revise(ctx, batch, chk, gr, orr)
+                assert not bad, "seed %d vs %s (revision): %d mismatches, first: %s" % (seed, name, len(bad), bad[:3])
 
 
 def run_group_seeds(ctx, checkers, seeds):
