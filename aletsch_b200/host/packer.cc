@@ -32,6 +32,9 @@ struct packer
 	std::vector<uint32_t> cigar_off{0};
 	std::vector<uint32_t> cigar;
 	int64_t seen = 0;
+	// region table of the sample added last (sample_profile::start1 / start2 / end1 / start_off, flattened over tid, rid)
+	std::vector<int64_t> reg_off{0}, reg_rec;
+	std::vector<int32_t> reg_start1, reg_start2, reg_end1;
 };
 
 // hit::set_strand (rnacore/hit.cc:152-185)
@@ -124,15 +127,15 @@ void packer_destroy(void *pk) { delete (packer*)pk; }
 int64_t packer_records_seen(void *pk) { return ((packer*)pk)->seen; }
 const uint8_t *packer_bundle_side(void *pk) { return ((packer*)pk)->b_side.data(); }
 
-int packer_add_sample(void *pkp, const packer_records *rp, const packer_params *pp, int32_t sample)
+// the record loop of one generator::resolve call: records [begin, ...) until the file ends or, with a region (target >= 0),
+// until a record lies at or behind end1 or on another chromosome (meta/generator.cc:80-81)
+static void resolve_records(packer &pk, const packer_records &r, const packer_params &p, int32_t sample, int64_t begin, int32_t target, int32_t end1)
 {
-	packer &pk = *(packer*)pkp;
-	const packer_records &r = *rp;
-	const packer_params &p = *pp;
 	side bb1, bb2;
 	int32_t pre_lpos = -1, pre_rpos = -1;
-	for(int64_t i = 0; i < r.n; i++)
+	for(int64_t i = begin; i < r.n; i++)
 	{
+		if(target >= 0 && (r.pos[i] >= end1 || r.tid[i] != target)) break;
 		pk.seen++;
 		uint16_t fl = r.flag[i];
 		uint32_t nc = r.cigar_off[i + 1] - r.cigar_off[i];
@@ -173,6 +176,76 @@ int packer_add_sample(void *pkp, const packer_records *rp, const packer_params *
 	}
 	flush(pk, bb1, r, p, sample, 0);
 	flush(pk, bb2, r, p, sample, 1);
+}
+
+int packer_add_sample(void *pkp, const packer_records *rp, const packer_params *pp, int32_t sample)
+{
+	resolve_records(*(packer*)pkp, *rp, *pp, sample, 0, -1, 0);
+	return 0;
+}
+
+// sample_profile::set_batch_boundaries (rnacore/sample_profile.cc:167-252): one pass over the mapped records cuts every
+// chromosome into regions that start where a gap of more than min_bundle_gap crosses a multiple of region_length.  The
+// table keeps the reference's quirks: the offset of a region is taken AFTER its first hit was read, so that hit is
+// never seen by generator::resolve; end1 is written only when a later region or chromosome starts, so the last region of the
+// last chromosome with records stays closed (start1 >= end1); regions that never start have start1 = end1 = 0.
+int64_t packer_region_table(void *pkp, const packer_records *rp, int32_t n_chrom, const int32_t *chrom_len, int32_t region_length,
+		const packer_params *pp)
+{
+	packer &pk = *(packer*)pkp;
+	const packer_records &r = *rp;
+	pk.reg_off.assign(1, 0);
+	for(int t = 0; t < n_chrom; t++) pk.reg_off.push_back(pk.reg_off.back() + chrom_len[t] / region_length + 1);
+	const int64_t nr = pk.reg_off.back();
+	pk.reg_rec.assign(nr, 0); pk.reg_start1.assign(nr, 0); pk.reg_start2.assign(nr, 0); pk.reg_end1.assign(nr, 0);
+	int32_t tid = -1, rid = 0, rpos = 0;
+	for(int64_t i = 0; i < r.n; i++)
+	{
+		if((r.flag[i] & 0x4) >= 1) continue;
+		if(std::fabs((double)r.pos[i] - (double)r.rpos[i]) >= pp->max_read_span) continue;
+		if(r.tid[i] < 0 || r.tid[i] >= n_chrom) return -1;
+		if(r.tid[i] != tid)
+		{
+			if(tid >= 0) pk.reg_end1[pk.reg_off[tid] + rid] = rpos;
+			tid = r.tid[i];
+			rid = 0;
+			int64_t k = pk.reg_off[tid];
+			pk.reg_start1[k] = r.pos[i]; pk.reg_start2[k] = r.rpos[i]; pk.reg_rec[k] = i + 1;
+			rpos = r.rpos[i];
+		}
+		if(r.pos[i] > rpos + pp->min_bundle_gap && (int64_t)r.pos[i] >= (int64_t)region_length * (1 + rid))
+		{
+			pk.reg_end1[pk.reg_off[tid] + rid] = rpos;
+			rid = r.pos[i] / region_length;
+			if(pk.reg_off[tid] + rid >= pk.reg_off[tid + 1]) return -1;       // a record behind the end of its chromosome
+			int64_t k = pk.reg_off[tid] + rid;
+			pk.reg_start1[k] = r.pos[i]; pk.reg_start2[k] = r.rpos[i]; pk.reg_rec[k] = i + 1;
+		}
+		if(r.rpos[i] > rpos) rpos = r.rpos[i];
+	}
+	return nr;
+}
+
+int packer_regions(void *pkp, const int64_t **reg_off, const int32_t **start1, const int32_t **start2, const int32_t **end1, const int64_t **start_rec)
+{
+	packer &pk = *(packer*)pkp;
+	*reg_off = pk.reg_off.data(); *start1 = pk.reg_start1.data(); *start2 = pk.reg_start2.data(); *end1 = pk.reg_end1.data();
+	*start_rec = pk.reg_rec.data();
+	return (int)pk.reg_off.size() - 1;
+}
+
+// what incubator::generate posts per sample (meta/incubator.cc:355-380): one generator::resolve per region of the table
+// whose start1 < end1, chromosome by chromosome; the bundles of a region never see the records of another
+int packer_add_sample_regions(void *pkp, const packer_records *rp, const packer_params *pp, int32_t sample)
+{
+	packer &pk = *(packer*)pkp;
+	const int nt = (int)pk.reg_off.size() - 1;
+	for(int t = 0; t < nt; t++)
+		for(int64_t k = pk.reg_off[t]; k < pk.reg_off[t + 1]; k++)
+		{
+			if(pk.reg_start1[k] >= pk.reg_end1[k]) continue;
+			resolve_records(pk, *rp, *pp, sample, pk.reg_rec[k], t, pk.reg_end1[k]);
+		}
 	return 0;
 }
 

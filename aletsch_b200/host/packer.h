@@ -41,6 +41,16 @@ void *packer_create(void);
 void packer_destroy(void *pk);
 // run the record loop over one sample and append its bundles to the batch under construction
 int packer_add_sample(void *pk, const packer_records *r, const packer_params *p, int32_t sample);
+// sample_profile::set_batch_boundaries (rnacore/sample_profile.cc:167-252) over the records of one sample: regions per
+// chromosome (chrom_len / region_length + 1 each; region_partition_length is 1,000,000, util/parameters.cc:42) with the
+// reference's start1 / start2 / end1 and, in place of the BGZF offset, the index of the record that FOLLOWS the region's
+// first hit (bgzf_tell is taken after that hit was read).  Returns the number of regions, < 0 on a record outside its chromosome.
+int64_t packer_region_table(void *pk, const packer_records *r, int32_t n_chrom, const int32_t *chrom_len, int32_t region_length,
+		const packer_params *p);
+// the table built last: reg_off[n_chrom + 1] and one entry per region; returns n_chrom
+int packer_regions(void *pk, const int64_t **reg_off, const int32_t **start1, const int32_t **start2, const int32_t **end1, const int64_t **start_rec);
+// one record loop per region of that table with start1 < end1 (meta/incubator.cc:355-380, meta/generator.cc:51-81)
+int packer_add_sample_regions(void *pk, const packer_records *r, const packer_params *p, int32_t sample);
 // view of everything appended so far (pointers stay valid until the next add / destroy)
 int packer_view(void *pk, agpu_batch_in *out);
 int64_t packer_records_seen(void *pk);

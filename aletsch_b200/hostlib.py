@@ -83,6 +83,10 @@ def lib():
         L.packer_destroy.argtypes = [C.c_void_p]
         L.packer_add_sample.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
         L.packer_view.argtypes = [C.c_void_p, C.POINTER(BatchIn)]
+        L.packer_region_table.restype = C.c_int64
+        L.packer_region_table.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.c_int32, C.c_void_p, C.c_int32, C.POINTER(PackerParams)]
+        L.packer_regions.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5
+        L.packer_add_sample_regions.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
         L.packer_default_params.argtypes = [C.POINTER(PackerParams)]
         L.packer_records_seen.restype = C.c_int64
         L.packer_records_seen.argtypes = [C.c_void_p]
@@ -263,8 +267,10 @@ class PackedBatch:
         return PackedBatch(arr)
 
 
-def pack(samples, params, sample_ids=None):
-    """run the record loop (meta/generator.cc:77-201) over each sample's records and pack all bundles."""
+def pack(samples, params, sample_ids=None, chrom_len=None, region_length=1000000, tables=None):
+    """run the record loop (meta/generator.cc:77-201) over each sample's records and pack all bundles.  With chrom_len the
+    records go through the region table first (sample_profile::set_batch_boundaries) and every region gets its own record loop,
+    as in the reference's end-to-end run; `tables` (a list) then receives each sample's table."""
     L = lib()
     pk = L.packer_create()
     try:
@@ -277,6 +283,20 @@ def pack(samples, params, sample_ids=None):
                 keep.append(arr)
                 setattr(r, k, arr.ctypes.data)
             sid = si if sample_ids is None else sample_ids[si]
+            if chrom_len is not None:
+                cl = np.ascontiguousarray(chrom_len, np.int32)
+                nr = L.packer_region_table(pk, C.byref(r), len(cl), cl.ctypes.data, region_length, C.byref(params))
+                if nr < 0:
+                    raise RuntimeError("packer_region_table: a record lies outside its chromosome")
+                if tables is not None:
+                    ptr = [C.c_void_p() for _ in range(5)]
+                    L.packer_regions(pk, *[C.byref(x) for x in ptr])
+                    tables.append({"reg_off": _np(ptr[0].value, len(cl) + 1, np.int64), "start1": _np(ptr[1].value, nr, np.int32),
+                                   "start2": _np(ptr[2].value, nr, np.int32), "end1": _np(ptr[3].value, nr, np.int32),
+                                   "start_rec": _np(ptr[4].value, nr, np.int64)})
+                if L.packer_add_sample_regions(pk, C.byref(r), C.byref(params), sid) != 0:
+                    raise RuntimeError("packer_add_sample_regions failed")
+                continue
             if L.packer_add_sample(pk, C.byref(r), C.byref(params), sid) != 0:
                 raise RuntimeError("packer_add_sample failed")
         v = BatchIn()

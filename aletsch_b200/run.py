@@ -29,15 +29,21 @@ def main(argv=None):
     ap.add_argument("--clusters", action="store_true", help="cross-sample clustering (-c 20 -s 0.2 style) + group-level re-bridge")
     ap.add_argument("--max-group-size", type=int, default=200)
     ap.add_argument("--min-grouping-similarity", type=float, default=0.10)
+    ap.add_argument("--whole-file", action="store_true",
+                    help="one record loop per file instead of the reference's region table (sample_profile::set_batch_boundaries), "
+                         "which drops every region's first hit and the last region of the last chromosome")
     args = ap.parse_args(argv)
     lt = {"unstranded": H.UNSTRANDED, "first": H.FR_FIRST, "second": H.FR_SECOND}[args.library_type]
     t0 = time.time()
-    recs = []
+    recs, chrom_len = [], None
     for path in args.bams:
-        r, _ = H.read_bam(path)
+        r, cl = H.read_bam(path)
+        if chrom_len is not None and not np.array_equal(cl, chrom_len):
+            raise SystemExit("%s: reference dictionary differs from the first file's" % path)
+        chrom_len = cl
         recs.append(r)
         print("%s: %d records" % (path, r["n"]), file=sys.stderr)
-    batch = H.pack(recs, H.default_packer_params(lt))
+    batch = H.pack(recs, H.default_packer_params(lt), chrom_len=None if args.whole_file else chrom_len, region_length=REGION)
     t1 = time.time()
     gp = G.default_params(library_type=lt, max_group_size=args.max_group_size, min_grouping_similarity=args.min_grouping_similarity)
     ctx = G.Context(args.device)

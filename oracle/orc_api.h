@@ -98,6 +98,8 @@ const void *orc_bag_data(void *bag, int i);
  * strand / xs per stored hit).  Returns the number of bundles. */
 int ref_generate(const orc_records_in *in, const orc_params *prm, int use_second_alignment, void *bag);
 
+int ref_generate_regions(const orc_records_in *in, const orc_params *prm, int use_second_alignment, int region_length, void *bag);
+
 ORC_DECLARE(ref)
 ORC_DECLARE(orc)
 

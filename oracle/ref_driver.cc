@@ -470,9 +470,17 @@ int ref_bundle_revise(void *b, void *bagp)
 // region per chromosome that starts at its first record (start_off is a record index in the stand-in's bgzf_seek)
 int ref_generate(const orc_records_in *in, const orc_params *prm, int use_second_alignment, void *bagp)
 {
+	return ref_generate_regions(in, prm, use_second_alignment, 0, bagp);
+}
+
+// region_length > 0: the table comes from the reference's own sample_profile::set_batch_boundaries (dumped as reg_off /
+// reg_start1 / reg_start2 / reg_end1 / reg_start_off) and one generator::resolve runs per region with start1 < end1, like
+// incubator::generate (meta/incubator.cc:355-380)
+int ref_generate_regions(const orc_records_in *in, const orc_params *prm, int use_second_alignment, int region_length, void *bagp)
+{
 	orc_bag &bag = *(orc_bag*)bagp;
 	parameters cfg;
-	sample_profile sp(0, 1000000);
+	sample_profile sp(0, region_length > 0 ? region_length : 1000000);
 	apply_params(prm, cfg, sp);
 	cfg.use_second_alignment = use_second_alignment != 0;
 	hts_shim_file file;
@@ -504,13 +512,34 @@ int ref_generate(const orc_records_in *in, const orc_params *prm, int use_second
 	off.clear(); gb.clear(); gp.clear(); gr.clear(); gm.clear(); gi.clear(); gf.clear(); gs.clear(); gx.clear();
 	off.push_back(0);
 	int nb = 0;
-	for(int t = 0; t < in->n_chrom; t++)
+	if(region_length > 0)
 	{
-		if(first[t] < 0) continue;
-		sp.start_off[t][0] = (off_t)first[t];
+		sp.set_batch_boundaries(cfg.min_bundle_gap, cfg.max_read_span);
+		std::vector<int32_t> &ro = bag.ints("reg_off"), &r1 = bag.ints("reg_start1"), &r2 = bag.ints("reg_start2"), &re = bag.ints("reg_end1");
+		std::vector<int32_t> &rs = bag.ints("reg_start_off");
+		ro.clear(); r1.clear(); r2.clear(); re.clear(); rs.clear();
+		ro.push_back(0);
+		for(size_t t = 0; t < sp.start1.size(); t++)
+		{
+			for(size_t k = 0; k < sp.start1[t].size(); k++)
+			{
+				r1.push_back(sp.start1[t][k]); r2.push_back(sp.start2[t][k]); re.push_back(sp.end1[t][k]); rs.push_back((int32_t)sp.start_off[t][k]);
+			}
+			ro.push_back((int32_t)r1.size());
+		}
+	}
+	for(int t = 0; t < in->n_chrom; t++)
+	for(size_t rid = 0; rid < sp.start1[t].size(); rid++)
+	{
+		if(region_length <= 0)
+		{
+			if(first[t] < 0) continue;
+			sp.start_off[t][0] = (off_t)first[t];
+		}
+		else if(sp.start1[t][rid] >= sp.end1[t][rid]) continue;
 		std::vector<bundle> vcb;
 		{
-			generator gt(sp, vcb, cfg, t, 0);
+			generator gt(sp, vcb, cfg, t, (int)rid);
 			gt.resolve();
 		}
 		for(size_t k = 0; k < vcb.size(); k++)
