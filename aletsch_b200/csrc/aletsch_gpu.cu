@@ -181,6 +181,8 @@ struct agpu_batch
 	bool revise_built = false;
 	dbuf<int32_t> rv_nstart, rv_nend, rv_addv, rv_leave, rv_come;
 	dbuf<double> rv_addw, rv_lratio, rv_cratio;
+	dbuf<int64_t> rv_voff;
+	int64_t rv_nvert = 0;
 
 	// group-level re-bridge (assembler::bridge): the combined bundles of the clusters as a batch of their own
 	agpu_batch *cb = NULL;
@@ -510,7 +512,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	b->ph_val.release(ctx); b->ph_len.release(ctx); b->ph_cnt.release(ctx); b->ph_off.release(ctx); b->ph_boff.release(ctx);
 	b->phase_built = false; b->n_phase = 0; b->n_phase_val = 0;
 	b->rv_nstart.release(ctx); b->rv_nend.release(ctx); b->rv_addv.release(ctx); b->rv_leave.release(ctx); b->rv_come.release(ctx);
-	b->rv_addw.release(ctx); b->rv_lratio.release(ctx); b->rv_cratio.release(ctx); b->revise_built = false;
+	b->rv_addw.release(ctx); b->rv_lratio.release(ctx); b->rv_cratio.release(ctx); b->rv_voff.release(ctx); b->revise_built = false;
 	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
 	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
 	b->group_pass = false;

@@ -21,14 +21,15 @@ namespace agpu {
 
 struct revise_dev
 {
-	// per vertex (the layout of graph_dev::v_*)
+	// per vertex, compact: the vertices of bundle b start at voff[b] (scan of n_pex + 2)
+	const int64_t *voff;
 	int32_t *run;                    // a(x) of the start candidates, then reused for b(x) of the end candidates
 	double *ratio, *weight;          // log(2 + maxcov) / log(2 + sum), maxcov - sum
 	int32_t *open;                   // candidate still usable
 	int32_t *has_s, *has_e;          // edge 0 -> x / x -> n present (built graph, then the added ones)
 	int32_t *leave_cnt, *come_cnt;   // fb1 / fb2 of remove_false_boundaries (filled by k_revise_unbridged)
 	double *leave_ratio, *come_ratio;
-	// per bundle, up to 2 (V - 2) added edges at 2 * vert_base: starts from the front, ends from the middle
+	// per bundle, up to 2 (V - 2) added edges at 2 * voff[b]: starts from the front, ends from the middle
 	int32_t *add_v;                  // the inner vertex of the added edge
 	double *add_w;
 	int32_t *n_start, *n_end;
@@ -46,9 +47,15 @@ KERNEL k_revise_unbridged(int64_t n_frg, hits_dev h, graph_dev g, const int32_t 
 	gview gv = graph_of(g, b);
 	int u1 = locate_vertex(gv, h.rpos[h0 + f_h1[f]] - 1), u2 = locate_vertex(gv, h.pos[h0 + f_h2[f]]);
 	if(u1 < 0 || u2 < 0 || u1 >= u2) return;
-	const int64_t v0 = vert_base(g, b);
+	const int64_t v0 = r.voff[b];
 	atomicAdd(&r.leave_cnt[v0 + u1], 1);
 	atomicAdd(&r.come_cnt[v0 + u2], 1);
+}
+
+KERNEL k_revise_nv(int n_bundles, const int32_t *n_pex, int32_t *nv)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if(b < n_bundles) nv[b] = n_pex[b] + 2;
 }
 
 // is k a distant in-vertex of a vertex in (k, x] (left) -- i.e. has left_continuous_extend put k into its set by the time
@@ -104,8 +111,8 @@ KERNEL k_revise(int n_bundles, graph_dev gd, const uint8_t *b_strand, revise_dev
 	{
 		sgraph g = sgraph_of(gd, b_strand, b);
 		const int nv = g.gv.nv, n = nv - 1;
-		const int64_t v0 = vert_base(gd, b);
-		const double *v_w = gd.v_w + v0;
+		const int64_t v0 = r.voff[b];
+		const double *v_w = gd.v_w + vert_base(gd, b);
 		int32_t *run = r.run + v0, *open = r.open + v0, *has_s = r.has_s + v0, *has_e = r.has_e + v0;
 		double *ratio = r.ratio + v0, *weight = r.weight + v0;
 		int32_t *add_v = r.add_v + 2 * v0;
