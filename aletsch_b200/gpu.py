@@ -419,6 +419,15 @@ class Batch:
             out.append({"phase_off": (co[a:b + 1] - co[a]).astype(np.int32), "phase_val": cv[int(co[a]):int(co[b])], "phase_cnt": cc[a:b]})
         return out
 
+    def raw_views(self):
+        """the C structs of agpu_graph_fetch / agpu_revise_fetch / agpu_phase_fetch as a foreign caller sees them (pointers
+        stay valid until the next fetch of the same kind); the stages must have run"""
+        g, r, p = GraphView(), ReviseView(), PhaseView()
+        self.ctx.check(self.ctx.L.agpu_graph_fetch(self.ctx.h, self.h, C.byref(g)), "agpu_graph_fetch")
+        self.ctx.check(self.ctx.L.agpu_revise_fetch(self.ctx.h, self.h, C.byref(r)), "agpu_revise_fetch")
+        self.ctx.check(self.ctx.L.agpu_phase_fetch(self.ctx.h, self.h, C.byref(p)), "agpu_phase_fetch")
+        return g, r, p
+
     def revise(self, p, fetch=True):
         """identify_boundaries + remove_false_boundaries on the bundles' graphs; per bundle the oracle's rev_edge / rev_edge_d /
         rev_vert / rev_vert_d"""

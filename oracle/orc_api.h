@@ -98,6 +98,11 @@ const void *orc_bag_data(void *bag, int i);
  * strand / xs per stored hit).  Returns the number of bundles. */
 int ref_generate(const orc_records_in *in, const orc_params *prm, int use_second_alignment, void *bag);
 
+/* reference build only: assembler::assemble(bundle&) end to end (transcripts: trst_off, trst_exon, trst_meta, trst_cov), and the
+ * same with graph + phase set rebuilt from the C-ABI views through integration/adapter.cc (declared in ref_driver.cc; takes
+ * agpu_graph_view / agpu_revise_view / agpu_phase_view pointers) */
+int ref_bundle_assemble(void *b, void *bag);
+
 int ref_generate_regions(const orc_records_in *in, const orc_params *prm, int use_second_alignment, int region_length, void *bag);
 
 ORC_DECLARE(ref)

@@ -17,6 +17,8 @@
 #include "bundle.h"
 #include "bundle_group.h"
 #include "generator.h"
+#include "assembler.h"
+#include "../integration/adapter.h"
 #include "graph_builder.h"
 #include "graph_cluster.h"
 #include "graph_reviser.h"
@@ -464,6 +466,149 @@ int ref_bundle_revise(void *b, void *bagp)
 		vr.push_back(vi.unbridge_leaving_ratio); vr.push_back(vi.unbridge_coming_ratio);
 	}
 	return (int)rw.size();
+}
+
+namespace {
+
+// transcripts of a transcript_set, sorted by (strand, exons) so that the dump does not depend on hash order:
+// trst_off / trst_exon (l r per exon), trst_meta (strand, count of samples), trst_cov (coverage)
+void dump_transcripts(transcript_set &tm, orc_bag &bag)
+{
+	std::vector<transcript> v = tm.get_transcripts(0);
+	std::sort(v.begin(), v.end(), [](const transcript &x, const transcript &y)
+	{
+		if(x.strand != y.strand) return x.strand < y.strand;
+		if(x.exons != y.exons) return x.exons < y.exons;
+		return x.coverage < y.coverage;
+	});
+	std::vector<int32_t> &off = bag.ints("trst_off"), &ex = bag.ints("trst_exon"), &me = bag.ints("trst_meta");
+	std::vector<double> &cv = bag.reals("trst_cov");
+	off.clear(); ex.clear(); me.clear(); cv.clear();
+	off.push_back(0);
+	for(size_t i = 0; i < v.size(); i++)
+	{
+		for(size_t k = 0; k < v[i].exons.size(); k++) { ex.push_back(v[i].exons[k].first); ex.push_back(v[i].exons[k].second); }
+		off.push_back((int32_t)ex.size() / 2);
+		me.push_back((int32_t)v[i].strand);
+		cv.push_back(v[i].coverage);
+	}
+}
+
+// the lines of assembler::assemble(bundle&) between transform and assemble(gr, ps, sid) (meta/assembler.cc:113-141)
+void seed_edge_support(splice_graph &gr, int sample_id)
+{
+	PEEI pei = gr.edges();
+	for(edge_iterator it = pei.first; it != pei.second; it++)
+	{
+		edge_descriptor e = (*it);
+		edge_info &ei = gr.get_editable_edge_info(e);
+		ei.samples.insert(sample_id);
+		ei.spAbd.insert(std::make_pair(sample_id, gr.get_edge_weight(e)));
+		ei.abd = gr.get_edge_weight(e);
+		ei.count = 1;
+	}
+}
+
+} // namespace
+
+// the reference end to end for one bundle that went through build_fragments + bridge (assembler::resolve, meta/assembler.cc:33-49):
+// assembler::assemble(bundle&) = transform(bd, gr, true), build_phase_set, scallop.  Clears the bundle.
+int ref_bundle_assemble(void *b, void *bagp)
+{
+	ref_handle *h = (ref_handle*)b;
+	orc_bag &bag = *(orc_bag*)bagp;
+	transcript_set tm(h->bd.chrm, 0, h->cfg.min_single_exon_clustering_overlap);
+	std::mutex lock;
+	assembler as(h->cfg, tm, lock, 0, 0, 0);
+	as.assemble(h->bd);
+	dump_transcripts(tm, bag);
+	return (int)bag.reals("trst_cov").size();
+}
+
+// everything scallop reads: the reference's own transform(bd, gr, true) + build_phase_set on the handle's bundle against the
+// graph and phase set the adapter rebuilds from the views, field by field.  Returns the number of differences (first few on
+// stderr); the stub vertices' maxcov, which the reference leaves uninitialised, is not compared.
+int ref_adapter_compare(void *hb, const agpu_graph_view *g, const agpu_revise_view *r, const agpu_phase_view *p, int b)
+{
+	ref_handle *h = (ref_handle*)hb;
+	transcript_set tm(h->bd.chrm, 0, h->cfg.min_single_exon_clustering_overlap);
+	std::mutex lock;
+	assembler as(h->cfg, tm, lock, 0, 0, 0);
+	h->bd.set_gid(0, 0, 0, 0);
+	splice_graph g1, g2;
+	as.transform(h->bd, g1, true);
+	phase_set p1, p2;
+	h->bd.build_phase_set(p1, g1);
+	if(agpu_adapter_graph(g, r, b, h->bd.chrm, h->bd.gid, g2) != 0) return -1;
+	agpu_adapter_phase_set(p, b, p2);
+	int bad = 0;
+#define DIFF(cond, ...) do { if(cond) { if(bad < 5) { fprintf(stderr, "adapter_compare bundle %d: ", b); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } bad++; } } while(0)
+	auto far = [](double x, double y) { return fabs(x - y) > 1e-9 * std::max(fabs(x), 1e-300) && x != y; };
+	DIFF(g1.strand != g2.strand, "strand %c vs %c", g1.strand, g2.strand);
+	DIFF(g1.chrm != g2.chrm || g1.gid != g2.gid, "chrm / gid");
+	DIFF(g1.num_vertices() != g2.num_vertices(), "vertices %d vs %d", (int)g1.num_vertices(), (int)g2.num_vertices());
+	DIFF(g1.num_edges() != g2.num_edges(), "edges %d vs %d", (int)g1.num_edges(), (int)g2.num_edges());
+	if(bad) return bad;
+	const int v0 = g->vert_off[b];
+	for(int x = 0; x < (int)g1.num_vertices(); x++)
+	{
+		const vertex_info &a = g1.get_vertex_info(x), &c = g2.get_vertex_info(x);
+		DIFF(far(g1.get_vertex_weight(x), g2.get_vertex_weight(x)), "vertex %d weight", x);
+		DIFF(a.lpos != c.lpos || a.rpos != c.rpos || a.length != c.length || a.type != c.type || a.regional != c.regional, "vertex %d ints", x);
+		DIFF(a.pos != c.pos || a.sdist != c.sdist || a.tdist != c.tdist || a.count != c.count || a.lstrand != c.lstrand || a.rstrand != c.rstrand,
+				"vertex %d defaults", x);
+		DIFF(far(a.stddev, c.stddev), "vertex %d stddev", x);
+		if(g->vert_d[3 * (size_t)(v0 + x) + 2] >= 0) DIFF(far(a.maxcov, c.maxcov), "vertex %d maxcov %f vs %f", x, a.maxcov, c.maxcov);
+		DIFF(a.unbridge_leaving_count != c.unbridge_leaving_count || a.unbridge_coming_count != c.unbridge_coming_count, "vertex %d unbridge counts", x);
+		DIFF(far(a.unbridge_leaving_ratio, c.unbridge_leaving_ratio) || far(a.unbridge_coming_ratio, c.unbridge_coming_ratio), "vertex %d unbridge ratios", x);
+		DIFF(far(a.boundary_loss1, c.boundary_loss1) || far(a.boundary_loss2, c.boundary_loss2) || far(a.boundary_loss3, c.boundary_loss3)
+				|| far(a.boundary_merged_loss, c.boundary_merged_loss), "vertex %d boundary_loss", x);
+		DIFF(g1.in_degree(x) != g2.in_degree(x) || g1.out_degree(x) != g2.out_degree(x), "vertex %d degrees", x);
+	}
+	// splice_graph::edges() is ordered by edge address; the out-edge sets are ordered by (source, target)
+	for(int x = 0; x < (int)g1.num_vertices(); x++)
+	{
+	PEEI e1 = g1.out_edges(x), e2 = g2.out_edges(x);
+	edge_iterator i1 = e1.first, i2 = e2.first;
+	for(; i1 != e1.second && i2 != e2.second; ++i1, ++i2)
+	{
+		const edge_info &a = g1.get_edge_info(*i1), &c = g2.get_edge_info(*i2);
+		DIFF((*i1)->source() != (*i2)->source() || (*i1)->target() != (*i2)->target(), "edge %d->%d vs %d->%d", (*i1)->source(), (*i1)->target(),
+				(*i2)->source(), (*i2)->target());
+		DIFF(far(g1.get_edge_weight(*i1), g2.get_edge_weight(*i2)), "edge %d->%d weight", (*i1)->source(), (*i1)->target());
+		DIFF(far(a.weight, c.weight) || a.strand != c.strand, "edge %d->%d info weight %f vs %f strand %d vs %d", (*i1)->source(), (*i1)->target(),
+				a.weight, c.weight, a.strand, c.strand);
+		DIFF(a.length != c.length || a.type != c.type || a.jid != c.jid || a.count != c.count || far(a.stddev, c.stddev) || far(a.abd, c.abd)
+				|| far(a.confidence, c.confidence), "edge %d->%d info defaults", (*i1)->source(), (*i1)->target());
+	}
+	}
+	DIFF(p1.pmap != p2.pmap, "phase set: %d vs %d lists", (int)p1.pmap.size(), (int)p2.pmap.size());
+#undef DIFF
+	return bad;
+}
+
+// the same with the graph and the phase set rebuilt from the C-ABI views by integration/adapter.cc: what the reference's
+// assembler does once transform / build_phase_set are replaced by the adapter calls
+int ref_adapter_assemble(const agpu_graph_view *g, const agpu_revise_view *r, const agpu_phase_view *p, int b, int n_frgs, int sample_id,
+		const orc_params *prm, void *bagp)
+{
+	orc_bag &bag = *(orc_bag*)bagp;
+	parameters cfg;
+	sample_profile sp(sample_id, 1000000);
+	apply_params(prm, cfg, sp);
+	transcript_set tm("chr", 0, cfg.min_single_exon_clustering_overlap);
+	std::mutex lock;
+	assembler as(cfg, tm, lock, 0, 0, 0);
+	splice_graph gr;
+	if(agpu_adapter_graph(g, r, b, "chr", "instance.0.0.0.0", gr) != 0) return -1;
+	gr.reads = n_frgs;
+	gr.subgraph = 1;
+	seed_edge_support(gr, sample_id);
+	phase_set ps;
+	agpu_adapter_phase_set(p, b, ps);
+	as.assemble(gr, ps, sample_id);
+	dump_transcripts(tm, bag);
+	return (int)bag.reals("trst_cov").size();
 }
 
 // generator::resolve + generator::generate (meta/generator.cc:51-227) on an in-memory file behind the htslib stand-in: one

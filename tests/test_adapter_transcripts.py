@@ -1,0 +1,96 @@
+"""Drop-in check at the consumer (integration/adapter.cc, the binding a maintainer adds next to meta/assembler.cc):
+1. everything scallop reads -- the splice graph of assembler::transform(bd, gr, true) with every vertex_info / edge_info field,
+   and the phase set of build_phase_set -- rebuilt from the C-ABI views must equal what the reference builds from the same
+   bundle itself, field by field (hard requirement, every bundle);
+2. the reference's OWN assembler + scallop (compiled unchanged into oracle/_ref) run on the rebuilt graphs, and the transcripts
+   are compared with the reference's end-to-end result (assembler::resolve -> assemble(bundle&), meta/assembler.cc:33-49,
+   107-150).  Scallop iterates containers keyed by edge POINTERS, so two runs of the reference on one bundle can differ with
+   the heap layout; a bundle only counts when the reference agrees with itself.
+CPU tier: kernel-logic build; the -m gpu tier repeats it on the CUDA path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orclib
+import parity
+from aletsch_b200 import gpu as G
+from aletsch_b200 import hostlib as H
+
+
+def transcripts_match(ctx, chk, batch, gp, op, stats):
+    L = chk.lib
+    L.ref_adapter_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(orclib.Params), C.c_void_p]
+    L.ref_bundle_assemble.argtypes = [C.c_void_p, C.c_void_p]
+    L.orc_bag_new.restype = C.c_void_p
+    bt = ctx.upload(batch.view(), keepalive=batch)
+    bt.bridge_all(gp)
+    bt.graph(gp)
+    bt._run("phase_set")
+    bt.revise(gp, fetch=False)
+    nfr = bt.bundle_counts()[:, 1]
+    g, r, p = bt.raw_views()
+    L.ref_adapter_compare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    bad = []
+
+    def reference_run(k, compare=False):
+        h = chk.new_bundle(batch.bundle(k), op)
+        chk.run(h, "fragments")
+        chk.run(h, "bridge")
+        if compare:
+            nd = L.ref_adapter_compare(h, C.byref(g), C.byref(r), C.byref(p), k)
+            if nd != 0:
+                bad.append("bundle %d: %d fields of the rebuilt graph / phase set differ" % (k, nd))
+        bag = L.orc_bag_new()
+        n = L.ref_bundle_assemble(h, bag)
+        d = chk.bag_to_dict(bag)
+        L.orc_bag_free(bag)
+        chk.free_bundle(h)
+        return n, d
+
+    for k in range(batch.n_bundles):
+        bag = L.orc_bag_new()
+        n_ours = L.ref_adapter_assemble(C.byref(g), C.byref(r), C.byref(p), k, int(nfr[k]), 0, C.byref(op), bag)
+        ours = chk.bag_to_dict(bag)
+        L.orc_bag_free(bag)
+        n_ref, ref = reference_run(k, compare=True)
+        n_again, again = reference_run(k)
+        stats["bundles"] = stats.get("bundles", 0) + 1
+        if n_again != n_ref or any(not np.array_equal(ref[x], again[x]) for x in ref):
+            stats["reference_unstable"] = stats.get("reference_unstable", 0) + 1
+            continue
+        wk = "bundle %d" % k
+        if n_ours != n_ref:
+            bad.append("%s: %d transcripts vs %d" % (wk, n_ref, n_ours))
+            continue
+        stats["transcripts"] = stats.get("transcripts", 0) + n_ref
+        stats["multi_exon"] = stats.get("multi_exon", 0) + int((np.diff(ref["trst_off"]) > 1).sum())
+        for name in ("trst_off", "trst_exon", "trst_meta"):
+            parity.cmp_int(name, ref[name], ours[name], wk, bad)
+        parity.cmp_f64("trst_cov", ref["trst_cov"], ours["trst_cov"], wk, bad)
+    bt.free()
+    return bad
+
+
+def run_case(ctx, checkers, mode, templates):
+    if "ref" not in checkers:
+        pytest.skip("needs oracle/_ref/libaletsch_ref.so")
+    batch, lt = parity.make_batch(mode, templates)
+    gp, op = parity.params_pair(lt)
+    stats = {}
+    bad = transcripts_match(ctx, checkers["ref"], batch, gp, op, stats)
+    assert not bad, "%d mismatches, first: %s" % (len(bad), bad[:3])
+    assert stats["transcripts"] > 10 and stats["multi_exon"] > 5, stats
+    assert stats.get("reference_unstable", 0) * 4 < stats["bundles"], stats
+
+
+@pytest.fixture(scope="module")
+def ctx(emu_lib):
+    c = G.Context(0, lib_path=emu_lib)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("mode,templates", [(H.SYNTH_PAIRED, 30000), (H.SYNTH_LONG, 2000)])
+def test_reference_scallop_on_adapter_graphs(ctx, checkers, mode, templates):
+    run_case(ctx, checkers, mode, templates)

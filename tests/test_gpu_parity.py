@@ -89,6 +89,14 @@ def test_revise_parity(ctx, checkers, mode, templates):
                 assert stats["rev_marked"] > 0
 
 
+@pytest.mark.parametrize("mode,templates", [(H.SYNTH_PAIRED, 60000), (H.SYNTH_SINGLE, 20000), (H.SYNTH_LONG, 3000)])
+def test_reference_scallop_on_adapter_graphs(ctx, checkers, mode, templates):
+    """the reference's own assembler + scallop fed from the C-ABI views through integration/adapter.cc: rebuilt graph / phase
+    set equal to the reference's field by field; identical transcripts wherever the reference agrees with itself"""
+    import test_adapter_transcripts as T
+    T.run_case(ctx, checkers, mode, templates)
+
+
 def test_lean_upload_matches_full(ctx):
     """rpos / flag / per-hit strand are optional in agpu_batch_in (include/aletsch_gpu.h)"""
     batch, lt = parity.make_batch(H.SYNTH_PAIRED, 20000)
