@@ -11,6 +11,7 @@
 #include "k_group.h"
 #include "k_phase.h"
 #include "k_revise.h"
+#include "k_unpack.h"
 
 #include <algorithm>
 #include <atomic>
@@ -202,8 +203,8 @@ static int check_err(agpu_ctx *ctx, agpu_batch *b, const char *stage)
 	TRY(d2h(ctx, e, b->err.p, sizeof(e)));
 	TRY(stream_sync(ctx));
 	const char *names[] = {"hit order", "duplicate (pos,rpos)", "mixed strand", "rpos != pos + cigar2rlen", "junction without partial exon",
-		"reserved qid", "scratch capacity"};
-	for(int k = 0; k < 7; k++)
+		"reserved qid", "scratch capacity", "compact input without the escape entry a sentinel announces"};
+	for(int k = 0; k < 8; k++)
 	{
 		if(e[k] == 0) continue;
 		char buf[256];
@@ -773,5 +774,6 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 #include "abi_group.inc"
 #include "abi_phase.inc"
 #include "abi_revise.inc"
+#include "abi_packed.inc"
 
 }

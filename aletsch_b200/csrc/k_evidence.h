@@ -38,7 +38,7 @@ struct hits_dev
 };
 
 // error / statistics words shared by all kernels of a batch
-enum { ERR_ORDER = 0, ERR_DUP, ERR_STRAND, ERR_RPOS, ERR_LINK, ERR_QID, ERR_CAP, ERR_WORDS = 16 };
+enum { ERR_ORDER = 0, ERR_DUP, ERR_STRAND, ERR_RPOS, ERR_LINK, ERR_QID, ERR_CAP, ERR_PACKED, ERR_WORDS = 16 };
 
 // ---- E0: bundle bounds (bundle_base::add_hit) + packing-contract check; one CTA per bundle
 KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b_rpos, int32_t *b_covhi,

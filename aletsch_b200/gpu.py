@@ -82,7 +82,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
-               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync"]
+               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_batch_upload_packed", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync"]
 
 
 def load(lib_path=None):
@@ -104,6 +104,7 @@ def load(lib_path=None):
     L.agpu_blocking_sync.argtypes = [C.c_void_p, C.c_int]
     L.agpu_batch_upload.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
     L.agpu_batch_adopt.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
+    L.agpu_batch_upload_packed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     L.agpu_batch_free.argtypes = [C.c_void_p, C.c_void_p]
     L.agpu_batch_reset.argtypes = [C.c_void_p, C.c_void_p]
     for n in ("evidence", "graph", "cluster", "bridge", "bridge_all"):
@@ -217,6 +218,7 @@ class Context:
         return out
 
     def upload(self, batch_in, keepalive=None):
+        """agpu_batch_upload, or agpu_batch_upload_packed when handed the compact form (hostlib.BatchPacked)"""
         return Batch(self, batch_in, False, keepalive)
 
     def adopt(self, batch_in_device, keepalive=None):
@@ -318,8 +320,8 @@ class Batch:
         self.nb = bin_struct.n_bundles
         self.hit_off = None
         h = C.c_void_p()
-        fn = ctx.L.agpu_batch_adopt if adopt else ctx.L.agpu_batch_upload
-        ctx.check(fn(ctx.h, C.byref(bin_struct), C.byref(h)), "agpu_batch_adopt" if adopt else "agpu_batch_upload")
+        name = "agpu_batch_adopt" if adopt else ("agpu_batch_upload_packed" if hasattr(bin_struct, "hit_units") else "agpu_batch_upload")
+        ctx.check(getattr(ctx.L, name)(ctx.h, C.byref(bin_struct), C.byref(h)), name)
         self.h = h
 
     def free(self):

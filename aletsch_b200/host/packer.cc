@@ -265,4 +265,72 @@ int packer_view(void *pkp, agpu_batch_in *out)
 	return 0;
 }
 
+
+// ---- compact form for the host -> device link (agpu_batch_packed, include/aletsch_gpu.h) --------------------------------
+struct compact
+{
+	agpu_batch_packed v;
+	std::vector<int32_t> pos0, ev_pos, ev_mpos, ev_isize;
+	std::vector<uint16_t> dpos, nun, units;
+	std::vector<int16_t> dmpos, is16;
+	std::vector<int64_t> ei_pos, ei_mpos, ei_isize;
+	std::vector<uint8_t> bstrand;
+};
+
+void *packer_compact_create(const agpu_batch_in *in)
+{
+	if(!in || (!in->strand && !in->bundle_strand)) return NULL;
+	compact *c = new compact;
+	const int nb = in->n_bundles;
+	const int64_t nh = in->n_hits;
+	c->pos0.assign(nb, 0); c->bstrand.assign(nb, (uint8_t)'.');
+	c->dpos.resize(nh); c->dmpos.resize(nh); c->is16.resize(nh); c->nun.resize(nh);
+	c->units.reserve((size_t)in->n_cigar + (size_t)in->n_cigar / 4);
+	for(int b = 0; b < nb; b++)
+	{
+		const int64_t h0 = in->bundle_hit_off[b], h1 = in->bundle_hit_off[b + 1];
+		if(in->bundle_strand) c->bstrand[b] = in->bundle_strand[b];
+		else if(h1 > h0) c->bstrand[b] = in->strand[h0];
+		if(h1 > h0) c->pos0[b] = in->pos[h0];
+		for(int64_t i = h0; i < h1; i++)
+		{
+			int64_t d = i == h0 ? 0 : (int64_t)in->pos[i] - (int64_t)in->pos[i - 1];
+			if(d < 0 || d > 0x7fffffff) { delete c; return NULL; }        // the packing contract: pos is non-decreasing in a bundle
+			if(d >= 0xFFFF) { c->dpos[i] = 0xFFFF; c->ei_pos.push_back(i); c->ev_pos.push_back((int32_t)d); }
+			else c->dpos[i] = (uint16_t)d;
+			int64_t m = (int64_t)in->mpos[i] - (int64_t)in->pos[i];
+			if(m <= -32768 || m > 32767) { c->dmpos[i] = (int16_t)-32768; c->ei_mpos.push_back(i); c->ev_mpos.push_back(in->mpos[i]); }
+			else c->dmpos[i] = (int16_t)m;
+			int32_t s = in->isize[i];
+			if(s <= -32768 || s > 32767) { c->is16[i] = (int16_t)-32768; c->ei_isize.push_back(i); c->ev_isize.push_back(s); }
+			else c->is16[i] = (int16_t)s;
+			size_t u0 = c->units.size();
+			for(uint32_t k = in->cigar_off[i]; k < in->cigar_off[i + 1]; k++)
+			{
+				uint32_t op = in->cigar[k] & 0xf, len = in->cigar[k] >> 4;
+				if(op == 15 || len >= (1u << 24)) { delete c; return NULL; }
+				if(len < 4096) c->units.push_back((uint16_t)(len << 4 | op));
+				else { c->units.push_back((uint16_t)((len & 0xfff) << 4 | 15)); c->units.push_back((uint16_t)((len >> 12) << 4 | op)); }
+			}
+			if(c->units.size() - u0 > 0xFFFF) { delete c; return NULL; }
+			c->nun[i] = (uint16_t)(c->units.size() - u0);
+		}
+	}
+	agpu_batch_packed &v = c->v;
+	memset(&v, 0, sizeof(v));
+	v.n_bundles = nb; v.n_hits = nh; v.n_cigar = in->n_cigar; v.n_units = (int64_t)c->units.size();
+	v.bundle_hit_off = in->bundle_hit_off; v.bundle_tid = in->bundle_tid; v.bundle_sample = in->bundle_sample;
+	v.bundle_strand = c->bstrand.data(); v.bundle_pos0 = c->pos0.data();
+	v.dpos = c->dpos.data(); v.dmpos = c->dmpos.data(); v.isize16 = c->is16.data(); v.xs = in->xs; v.qid = in->qid;
+	v.hit_units = c->nun.data(); v.units = c->units.data();
+	v.n_esc_pos = (int64_t)c->ei_pos.size(); v.n_esc_mpos = (int64_t)c->ei_mpos.size(); v.n_esc_isize = (int64_t)c->ei_isize.size();
+	v.esc_pos_idx = c->ei_pos.data(); v.esc_pos_val = c->ev_pos.data();
+	v.esc_mpos_idx = c->ei_mpos.data(); v.esc_mpos_val = c->ev_mpos.data();
+	v.esc_isize_idx = c->ei_isize.data(); v.esc_isize_val = c->ev_isize.data();
+	return c;
+}
+
+const agpu_batch_packed *packer_compact_view(void *c) { return c ? &((compact*)c)->v : NULL; }
+void packer_compact_destroy(void *c) { delete (compact*)c; }
+
 }

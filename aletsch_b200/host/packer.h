@@ -51,6 +51,12 @@ int64_t packer_region_table(void *pk, const packer_records *r, int32_t n_chrom, 
 int packer_regions(void *pk, const int64_t **reg_off, const int32_t **start1, const int32_t **start2, const int32_t **end1, const int64_t **start_rec);
 // one record loop per region of that table with start1 < end1 (meta/incubator.cc:355-380, meta/generator.cc:51-81)
 int packer_add_sample_regions(void *pk, const packer_records *r, const packer_params *p, int32_t sample);
+// the compact form of a batch for the host -> device link (agpu_batch_packed); the view points into the handle (and, for
+// bundle_hit_off / bundle_tid / bundle_sample / xs / qid, into `in`).  NULL if `in` breaks the packing contract (pos
+// decreasing inside a bundle) or holds an operation the units cannot express (length >= 2^24, more than 65535 units per hit).
+void *packer_compact_create(const agpu_batch_in *in);
+const agpu_batch_packed *packer_compact_view(void *c);
+void packer_compact_destroy(void *c);
 // view of everything appended so far (pointers stay valid until the next add / destroy)
 int packer_view(void *pk, agpu_batch_in *out);
 int64_t packer_records_seen(void *pk);

@@ -46,6 +46,35 @@ class BatchIn(C.Structure):
                 ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("bundle_strand", C.c_void_p)]
 
 
+class BatchPacked(C.Structure):
+    """agpu_batch_packed (include/aletsch_gpu.h): the compact form of a batch for the host -> device link."""
+    _fields_ = [("n_bundles", C.c_int32), ("n_hits", C.c_int64), ("n_cigar", C.c_int64), ("n_units", C.c_int64),
+                ("bundle_hit_off", C.c_void_p), ("bundle_tid", C.c_void_p), ("bundle_sample", C.c_void_p), ("bundle_strand", C.c_void_p),
+                ("bundle_pos0", C.c_void_p), ("dpos", C.c_void_p), ("dmpos", C.c_void_p), ("isize16", C.c_void_p), ("xs", C.c_void_p),
+                ("qid", C.c_void_p), ("hit_units", C.c_void_p), ("units", C.c_void_p),
+                ("n_esc_pos", C.c_int64), ("n_esc_mpos", C.c_int64), ("n_esc_isize", C.c_int64),
+                ("esc_pos_idx", C.c_void_p), ("esc_mpos_idx", C.c_void_p), ("esc_isize_idx", C.c_void_p),
+                ("esc_pos_val", C.c_void_p), ("esc_mpos_val", C.c_void_p), ("esc_isize_val", C.c_void_p)]
+
+
+COMPACT_ARRAYS = [("bundle_hit_off", np.int64, "nb1"), ("bundle_tid", np.int32, "nb"), ("bundle_sample", np.int32, "nb"),
+                  ("bundle_strand", np.uint8, "nb"), ("bundle_pos0", np.int32, "nb"), ("dpos", np.uint16, "nh"), ("dmpos", np.int16, "nh"),
+                  ("isize16", np.int16, "nh"), ("xs", np.uint8, "nh"), ("qid", np.uint64, "nh"), ("hit_units", np.uint16, "nh"),
+                  ("units", np.uint16, "nu"), ("esc_pos_idx", np.int64, "ep"), ("esc_mpos_idx", np.int64, "em"), ("esc_isize_idx", np.int64, "ei"),
+                  ("esc_pos_val", np.int32, "ep"), ("esc_mpos_val", np.int32, "em"), ("esc_isize_val", np.int32, "ei")]
+
+
+def compact_struct(arrays, n_cigar, ptr=lambda a: a.ctypes.data):
+    """agpu_batch_packed over a dict of arrays (numpy, or anything `ptr` can turn into an address, e.g. pinned tensors)"""
+    p = BatchPacked()
+    p.n_bundles, p.n_hits = len(arrays["bundle_tid"]), len(arrays["dpos"])
+    p.n_cigar, p.n_units = n_cigar, len(arrays["units"])
+    p.n_esc_pos, p.n_esc_mpos, p.n_esc_isize = len(arrays["esc_pos_idx"]), len(arrays["esc_mpos_idx"]), len(arrays["esc_isize_idx"])
+    for name, _, _ in COMPACT_ARRAYS:
+        setattr(p, name, ptr(arrays[name]))
+    return p
+
+
 HIT_FIELDS = [("pos", np.int32), ("rpos", np.int32), ("mpos", np.int32), ("isize", np.int32), ("flag", np.uint16),
               ("strand", np.uint8), ("xs", np.uint8), ("qid", np.uint64)]
 
@@ -83,6 +112,11 @@ def lib():
         L.packer_destroy.argtypes = [C.c_void_p]
         L.packer_add_sample.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
         L.packer_view.argtypes = [C.c_void_p, C.POINTER(BatchIn)]
+        L.packer_compact_create.restype = C.c_void_p
+        L.packer_compact_create.argtypes = [C.POINTER(BatchIn)]
+        L.packer_compact_view.restype = C.POINTER(BatchPacked)
+        L.packer_compact_view.argtypes = [C.c_void_p]
+        L.packer_compact_destroy.argtypes = [C.c_void_p]
         L.packer_region_table.restype = C.c_int64
         L.packer_region_table.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.c_int32, C.c_void_p, C.c_int32, C.POINTER(PackerParams)]
         L.packer_regions.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5
@@ -210,6 +244,27 @@ class PackedBatch:
                   "qid", "cigar_off", "cigar"):
             setattr(b, k, self.a[k].ctypes.data)
         return b
+
+    def compact(self):
+        """the compact form (agpu_batch_packed) as a dict of numpy arrays; compact_struct() turns it into the C struct"""
+        L = lib()
+        v = self.view()
+        if "bundle_strand" in self.a:
+            v.bundle_strand = self.a["bundle_strand"].ctypes.data
+        c = L.packer_compact_create(C.byref(v))
+        if not c:
+            raise ValueError("batch cannot be expressed in the compact form (pos decreasing in a bundle, or an oversized CIGAR)")
+        try:
+            p = L.packer_compact_view(c).contents
+            n = {"nb": p.n_bundles, "nb1": p.n_bundles + 1, "nh": p.n_hits, "nu": p.n_units, "ep": p.n_esc_pos, "em": p.n_esc_mpos,
+                 "ei": p.n_esc_isize}
+            out = {}
+            for name, dt, size in COMPACT_ARRAYS:
+                ptr = getattr(p, name)
+                out[name] = _np(ptr, n[size], dt) if ptr else np.zeros(n[size], dt)
+            return out
+        finally:
+            L.packer_compact_destroy(c)
 
     def bundle(self, k):
         """arrays of bundle k alone (cigar offsets rebased)."""

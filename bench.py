@@ -261,6 +261,17 @@ def run_ours(args):
     h2d_bytes = 0
     for ch in chunks:
         pin = {}
+        if args.upload == "compact":
+            # the compact link format (agpu_batch_packed): 16-bit position deltas / mate offsets / insert sizes / CIGAR units
+            # with escape lists, decoded on the device into the arrays of the plain upload (include/aletsch_gpu.h)
+            ch.a["bundle_strand"] = np.ascontiguousarray(ch.a["strand"][np.minimum(ch.a["bundle_hit_off"][:-1], max(ch.n_hits - 1, 0))])
+            arrays = ch.compact()
+            for f, a in arrays.items():
+                v = a.view(np.int64) if a.dtype == np.uint64 else (a.view(np.int16) if a.dtype == np.uint16 else a)
+                pin[f] = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+                h2d_bytes += pin[f].numel() * pin[f].element_size()
+            views.append((H.compact_struct(pin, ch.n_cigar, ptr=lambda t: t.data_ptr()), pin))
+            continue
         # lean upload: flag[] is never read on the device, rpos[] is re-derived from the CIGAR there, and the strand that all
         # hits of a bundle share goes up once per bundle (agpu_batch_in: rpos / flag / strand may be NULL)
         ch.a["bundle_strand"] = np.ascontiguousarray(ch.a["strand"][np.minimum(ch.a["bundle_hit_off"][:-1], max(ch.n_hits - 1, 0))])
@@ -373,7 +384,7 @@ def run_ours(args):
                "bridged_pairs_per_sec_stage4": bridged_all / max(stage4_ms / 1e3, 1e-12), "stage4_ms_per_step": stage4_ms,
                "counts": counts, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": "hits/s", "h2d_bytes_per_step": float(tot[2]), "d2h_bytes_per_step": float(tot[3]),
-                       "ms_per_step": ms_e2e / steps, "sub_batches": len(views), "streams": args.streams,
+                       "ms_per_step": ms_e2e / steps, "upload": args.upload, "sub_batches": len(views), "streams": args.streams,
                        "gpu_launches_per_step": int(launches_e2e // steps)},
                "roofline": roof, "clocks": clk}
         if stage5 is not None:
@@ -731,6 +742,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage5", action="store_true", help="skip the bundle_group::resolve (stage 5) leg")
     ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the end-to-end pipeline")
+    ap.add_argument("--upload", choices=["compact", "lean"], default="compact",
+                    help="host->device format of the end-to-end leg: agpu_batch_packed (default) or the lean agpu_batch_in")
     ap.add_argument("--streams", type=int, default=4, help="host threads / CUDA streams of the end-to-end pipeline")
     args = ap.parse_args()
     if args.impl == "reference":

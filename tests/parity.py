@@ -159,6 +159,41 @@ def compare_lean_upload(ctx, batch, gp):
     return bad
 
 
+def compare_compact_upload(ctx, batch, gp, stats=None):
+    """the compact upload (agpu_batch_packed, decoded on the device) must leave exactly the state of the full upload; also
+    after a reset (the decoded arrays outlive the scratch the decoding used)"""
+    bad = []
+    arrays = batch.compact()
+    cv = H.compact_struct(arrays, batch.n_cigar)
+    if stats is not None:
+        stats["bytes_full"] = sum(batch.a[f].nbytes for f in ("pos", "mpos", "isize", "xs", "qid", "cigar_off", "cigar"))
+        stats["bytes_compact"] = sum(a.nbytes for n, a in arrays.items() if not n.startswith("bundle_"))
+        stats["escapes"] = len(arrays["esc_pos_idx"]) + len(arrays["esc_mpos_idx"]) + len(arrays["esc_isize_idx"])
+        stats["long_ops"] = int(len(arrays["units"]) - batch.n_cigar)
+    outs = []
+    for view, keep, again in ((batch.view(), batch, False), (cv, (arrays, batch), False), (cv, (arrays, batch), True)):
+        bt = ctx.upload(view, keepalive=keep)
+        bt.bridge_all(gp)
+        if again:
+            bt.reset()
+            bt.bridge_all(gp)
+        ev = bt.fetch_evidence(batch.a["bundle_hit_off"])
+        fr = bt.fetch_fragments()
+        gr = bt.fetch_graph()
+        outs.append((ev, fr, gr, bt.counts()))
+        bt.free()
+    for which, (e1, f1, g1, c1) in (("compact", outs[1]), ("compact after reset", outs[2])):
+        e0, f0, g0, c0 = outs[0]
+        if c0 != c1:
+            bad.append("%s: counts differ: %s vs %s" % (which, c0, c1))
+        for k in range(batch.n_bundles):
+            for d0, d1 in ((e0[k], e1[k]), (f0[k], f1[k]), (g0[k], g1[k])):
+                for n in d0:
+                    if not np.array_equal(d0[n], d1[n]):
+                        bad.append("bundle %d: %s differs between full and %s upload" % (k, n, which))
+    return bad
+
+
 def locus_groups(batch, width=50000, max_groups=12):
     """bundles of different samples over the same locus and side: candidate clusters for assembler::bridge"""
     a = batch.a

@@ -1,6 +1,7 @@
 """CPU tier: the kernel bodies, compiled for the host with a serial thread model (test-only build,
 see aletsch_b200/csrc/dev.h), against the CPU checkers.  This checks orderings, tie-breaks and index
 arithmetic of the kernels without a GPU; the -m gpu tier repeats it on the real CUDA path."""
+import numpy as np
 import pytest
 
 import parity
@@ -87,6 +88,45 @@ def test_revise_parity(ctx, checkers, mode, templates):
             assert ratio > 1.5 or stats["rev_added"] > 10
             if mode == H.SYNTH_PAIRED:
                 assert stats["rev_marked"] > 0
+
+
+@pytest.mark.parametrize("mode,templates", [(H.SYNTH_PAIRED, 30000), (H.SYNTH_LONG, 3000)])
+def test_compact_upload_matches_full(ctx, mode, templates):
+    """agpu_batch_upload_packed: 16-bit deltas / offsets / CIGAR units with escapes, decoded on the device"""
+    batch, lt = parity.make_batch(mode, templates)
+    stats = {}
+    bad = parity.compare_compact_upload(ctx, batch, G.default_params(library_type=lt), stats)
+    assert not bad, bad[:3]
+    assert stats["bytes_compact"] < 0.75 * stats["bytes_full"], stats
+    assert stats["long_ops"] > 0, stats
+
+
+def test_compact_upload_escapes_and_errors(ctx):
+    """values that do not fit 16 bits travel through the escape lists; a sentinel without its entry is an input error"""
+    import fuzz
+    batch = fuzz.random_batch(5, n_bundles=6, max_hits=80)
+    a = batch.a
+    rng = np.random.default_rng(5)
+    far = rng.choice(batch.n_hits, 12, replace=False)
+    a["mpos"][far[:6]] += 70000                      # mate far away
+    a["isize"][far[6:]] = 40000 + np.arange(6, dtype=np.int32)
+    # a jump of more than 65534 bases inside a bundle: shift the tail of the largest bundle
+    k = int(np.argmax(np.diff(a["bundle_hit_off"])))
+    h0, h1 = int(a["bundle_hit_off"][k]), int(a["bundle_hit_off"][k + 1])
+    mid = (h0 + h1) // 2
+    for f in ("pos", "rpos", "mpos"):
+        a[f][mid:h1] += 100000
+    gp = G.default_params(library_type=H.FR_FIRST)
+    stats = {}
+    bad = parity.compare_compact_upload(ctx, batch, gp, stats)
+    assert not bad, bad[:3]
+    assert stats["escapes"] >= 13, stats
+    arrays = batch.compact()
+    arrays["esc_isize_idx"] = arrays["esc_isize_idx"][:-1].copy()          # drop an entry a sentinel points to
+    arrays["esc_isize_val"] = arrays["esc_isize_val"][:-1].copy()
+    with pytest.raises(G.AgpuError) as e:
+        ctx.upload(H.compact_struct(arrays, batch.n_cigar), keepalive=(arrays, batch))
+    assert "escape entry" in str(e.value) and "-4" in str(e.value)          # AGPU_ERR_INPUT
 
 
 def test_lean_upload_matches_full(ctx):
