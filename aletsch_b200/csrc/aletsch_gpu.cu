@@ -179,6 +179,7 @@ struct agpu_batch
 
 	// boundary revision (identify_boundaries / remove_false_boundaries): added edges and vertex annotations, in the vertex
 	// layout of the graphs
+	bool defer_check = false;
 	bool revise_built = false;
 	dbuf<int32_t> rv_nstart, rv_nend, rv_addv, rv_leave, rv_come;
 	dbuf<double> rv_addw, rv_lratio, rv_cratio;
@@ -199,6 +200,7 @@ struct agpu_batch
 
 static int check_err(agpu_ctx *ctx, agpu_batch *b, const char *stage)
 {
+	if(b->defer_check) return AGPU_OK;        // the caller checks at its next read-back (errors are sticky counters)
 	int e[ERR_WORDS];
 	TRY(d2h(ctx, e, b->err.p, sizeof(e)));
 	TRY(stream_sync(ctx));
@@ -307,12 +309,14 @@ void agpu_destroy(agpu_ctx *ctx)
 	if(ctx->ev_sync) cudaEventDestroy((cudaEvent_t)ctx->ev_sync);
 	if(ctx->own_stream) cudaStreamDestroy(ctx->stream);
 #endif
+	pinned_free(ctx->stage_pin);
 	delete ctx;
 }
 
 const char *agpu_last_error(agpu_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
 int agpu_sync(agpu_ctx *ctx) { if(!ctx) return AGPU_ERR_ARG; AGPU_ENTER(ctx); return stream_sync(ctx); }
 int64_t agpu_launch_count(agpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t agpu_sync_count(agpu_ctx *ctx) { return ctx ? ctx->syncs : 0; }
 
 // arena of the context (runtime.h): bytes held, and growth ahead of time so that a steady-state pipeline never has to take a
 // new slab (a cudaMallocAsync that misses the pool synchronises the device) in the middle of its work
@@ -395,9 +399,20 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ho[x + 1] - ho[x] > ho[y + 1] - ho[y]; });
 	b->n_large = 0;
 	while(b->n_large < b->nb && ho[ord[b->n_large] + 1] - ho[ord[b->n_large]] >= LARGE_BUNDLE_HITS) b->n_large++;
+	// staged through the context's pinned area: asynchronous copies, no stream drain here
+	const size_t need = sizeof(int64_t) * ((size_t)b->nb + 2) + sizeof(int32_t) * ((size_t)b->nb + 2);
+	if(need > ctx->stage_cap)
+	{
+		pinned_free(ctx->stage_pin);
+		ctx->stage_cap = need * 2 + 4096;
+		ctx->stage_pin = (char*)pinned_alloc(ctx->stage_cap);
+		if(!ctx->stage_pin) { ctx->stage_cap = 0; return AGPU_ERR_OOM; }
+	}
+	int64_t *qreg = (int64_t*)ctx->stage_pin;
+	int32_t *ord_pin = (int32_t*)(ctx->stage_pin + sizeof(int64_t) * ((size_t)b->nb + 2));
+	memcpy(ord_pin, ord.data(), sizeof(int32_t) * b->nb);
 	TRY(b->order.alloc(ctx, b->nb + 1));
-	TRY(h2d(ctx, b->order.p, ord.data(), sizeof(int32_t) * b->nb));
-	std::vector<int64_t> qreg(b->nb + 1);
+	TRY(h2d(ctx, b->order.p, ord_pin, sizeof(int32_t) * b->nb));
 	qreg[0] = 0;
 	for(int k = 0; k < b->nb; k++)
 	{
@@ -406,8 +421,7 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	}
 	b->q_slots = qreg[b->nb];
 	TRY(b->qreg_off.alloc(ctx, b->nb + 2));
-	TRY(h2d(ctx, b->qreg_off.p, qreg.data(), sizeof(int64_t) * (b->nb + 1)));
-	TRY(stream_sync(ctx));
+	TRY(h2d(ctx, b->qreg_off.p, qreg, sizeof(int64_t) * (b->nb + 1)));
 	return AGPU_OK;
 }
 
@@ -464,6 +478,8 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
+	// the caller's buffers (and the context's staging area) are free again when this returns
+	if(stream_sync(ctx) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
 	*out = b;
 	return AGPU_OK;
 }
@@ -499,6 +515,7 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
+	if(stream_sync(ctx) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }      // frees the context's staging area
 	*out = b;
 	return AGPU_OK;
 }
@@ -553,8 +570,10 @@ int agpu_batch_reset(agpu_ctx *ctx, agpu_batch *b)
 // ---- chain set construction shared by hcst (elements = hits) and fcst (elements = fragments)
 // Table regions: a power of two >= 2 x the elements that will be inserted.  `d_count` (device, per bundle) gives that number
 // when only some elements carry a chain (hcst: the spliced hits); otherwise every element of the bundle counts.
-static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int64_t n_elem, const int64_t *d_elem_off,
-		const std::vector<int64_t> &elem_off_host, const int32_t *d_count = NULL)
+// table regions: a power of two >= 2 x the bundle's count.  With per-bundle counts (d_count: the spliced hits, far fewer than the
+// elements) the total is read back; without, the regions are sized from the element offsets on the device and the table is
+// allocated by its bound (a power of two below 4 x count), with no read-back at all
+static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int64_t n_elem, const int64_t *d_elem_off, const int32_t *d_count = NULL)
 {
 	int nb = b->nb;
 	cs.n_elem = n_elem;
@@ -572,16 +591,12 @@ static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int6
 	}
 	else
 	{
-		std::vector<int64_t> reg(nb + 1);
-		reg[0] = 0;
-		for(int k = 0; k < nb; k++)
-		{
-			int64_t ne = elem_off_host[k + 1] - elem_off_host[k];
-			reg[k + 1] = reg[k] + (int64_t)pow2_ceil((u32)std::max<int64_t>(2 * ne, 2));
-		}
-		cs.n_slots = reg[nb];
-		TRY(h2d(ctx, cs.reg_off.p, reg.data(), sizeof(int64_t) * (nb + 1)));
-		TRY(stream_sync(ctx));                 // `reg` is pageable stack-owned memory
+		dbuf<int64_t> sz;
+		TRY(sz.alloc(ctx, nb + 1));
+		LAUNCH_T(ctx, k_table_sizes_off, nb, nb, d_elem_off, sz.p);
+		LAUNCH_B(ctx, k_scan_i64, 1, 1024, sz.p, cs.reg_off.p, nb);
+		cs.n_slots = 4 * n_elem + 2 * (int64_t)nb;
+		sz.release(ctx);
 	}
 	TRY(cs.slot_word.alloc(ctx, cs.n_slots, true));
 	TRY(cs.slot_first.alloc(ctx, cs.n_slots)); TRY(cs.slot_first.fill(ctx, 0x7f));
@@ -715,7 +730,7 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	// hcst
 	chainset_state &cs = b->hcst;
 	cs.val = b->spl.p; cs.voff32 = b->h.cigar_off; cs.voff64 = NULL; cs.elem_len = b->hit_nspl.p;
-	TRY(chainset_build(ctx, b, cs, nh, b->h.bundle_hit_off, b->hit_off_host, n_spliced.p));
+	TRY(chainset_build(ctx, b, cs, nh, b->h.bundle_hit_off, n_spliced.p));
 	n_spliced.release(ctx);
 	LAUNCH_T(ctx, k_hcst_insert, nh, b->h, b->hit_nspl.p, b->hit_bundle.p, b->spl.p, cs.reg_off.p, cs.slot_word.p,
 			cs.slot_first.p, cs.slot_cnt.p, cs.elem_slot.p, b->err.p);

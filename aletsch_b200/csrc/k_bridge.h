@@ -985,7 +985,6 @@ struct bridge_state
 	agpu::dbuf<int32_t> ent_frag, ent_xs, ent_len, fc_val, frag_chain;
 	agpu::dbuf<int64_t> ent_voff, ent_boff;
 	int64_t n_ent = 0;
-	std::vector<int64_t> ent_boff_host;
 	bool updated = false;
 
 	void release(agpu_ctx *ctx)
@@ -1006,7 +1005,7 @@ struct bridge_state
 	{
 		ent_frag.release(ctx); ent_xs.release(ctx); ent_len.release(ctx); fc_val.release(ctx); frag_chain.release(ctx);
 		ent_voff.release(ctx); ent_boff.release(ctx);
-		n_ent = 0; n_chain_val = 0; ent_boff_host.clear();
+		n_ent = 0; n_chain_val = 0;
 	}
 };
 

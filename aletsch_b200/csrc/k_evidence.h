@@ -259,6 +259,22 @@ KERNEL k_table_sizes(int64_t nb, const int32_t *count, int64_t *size)
 	size[i] = (int64_t)pow2_ceil((u32)(c < 2 ? 2 : c));
 }
 
+// the same from an offset array: count = off[i + 1] - off[i]
+KERNEL k_table_sizes_off(int64_t nb, const int64_t *off, int64_t *size)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= nb) return;
+	int64_t c = 2 * (off[i + 1] - off[i]);
+	size[i] = (int64_t)pow2_ceil((u32)(c < 2 ? 2 : c));
+}
+
+KERNEL k_add_i64(int64_t n, const int64_t *a, const int64_t *b, int64_t *out)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	out[i] = a[i] + b[i];
+}
+
 // ---- chain table: one open-addressing region per bundle; slot word = hash32 << 32 | (rep + 1)
 // `rep` is the global index of the element that claimed the slot; equality is verified on the
 // actual coordinates, so hash collisions only cost a probe.

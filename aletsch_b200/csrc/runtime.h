@@ -50,6 +50,11 @@ struct agpu_ctx
 	// per core, e.g. eight ranks with a stream pool each on one box)
 	bool blocking_sync = false;
 	void *ev_sync = NULL;
+	// small pinned staging area for the per-bundle tables an upload derives on the host (grown on demand, reused by every batch
+	// of the context: a batch's upload ends with a stream synchronisation, so the area is free again when the next one starts)
+	char *stage_pin = NULL;
+	size_t stage_cap = 0;
+	int64_t syncs = 0;
 	// optional per-kernel timing (CUDA events around every launch on the ctx stream)
 	bool profiling = false;
 	std::vector<agpu_prof_rec> prof;
@@ -177,6 +182,7 @@ inline int d2d(agpu_ctx *ctx, void *d, const void *s, size_t bytes) { if(bytes =
 inline int stream_sync(agpu_ctx *ctx)
 {
 	cudaError_t e;
+	ctx->syncs++;
 	if(ctx->blocking_sync && ctx->ev_sync)
 	{
 		e = cudaEventRecord((cudaEvent_t)ctx->ev_sync, ctx->stream);
@@ -222,7 +228,7 @@ inline int dev_fill(agpu_ctx *, void *p, int byte, size_t bytes) { memset(p, byt
 inline int h2d(agpu_ctx *, void *d, const void *h, size_t bytes) { memcpy(d, h, bytes); return AGPU_OK; }
 inline int d2h(agpu_ctx *, void *h, const void *d, size_t bytes) { memcpy(h, d, bytes); return AGPU_OK; }
 inline int d2d(agpu_ctx *, void *d, const void *s, size_t bytes) { memcpy(d, s, bytes); return AGPU_OK; }
-inline int stream_sync(agpu_ctx *) { return AGPU_OK; }
+inline int stream_sync(agpu_ctx *ctx) { ctx->syncs++; return AGPU_OK; }
 inline void prof_collect(agpu_ctx *) {}
 inline void *pinned_alloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
 inline void pinned_free(void *p) { free(p); }

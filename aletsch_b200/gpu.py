@@ -76,7 +76,7 @@ class Counts(C.Structure):
                                          "bridge_chain_ints", "bridge_whole_ints")]
 
 
-ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_sync", "agpu_launch_count",
+ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_sync", "agpu_launch_count", "agpu_sync_count",
                "agpu_batch_upload", "agpu_batch_adopt", "agpu_batch_free", "agpu_batch_reset", "agpu_batch_evidence",
                "agpu_batch_fragments", "agpu_batch_graph", "agpu_batch_cluster", "agpu_batch_bridge", "agpu_batch_update",
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
@@ -97,6 +97,8 @@ def load(lib_path=None):
     L.agpu_sync.argtypes = [C.c_void_p]
     L.agpu_launch_count.restype = C.c_int64
     L.agpu_launch_count.argtypes = [C.c_void_p]
+    L.agpu_sync_count.restype = C.c_int64
+    L.agpu_sync_count.argtypes = [C.c_void_p]
     L.agpu_default_params.argtypes = [C.POINTER(Params)]
     L.agpu_reserved.restype = C.c_int64
     L.agpu_reserved.argtypes = [C.c_void_p]
@@ -190,6 +192,11 @@ class Context:
     @property
     def launches(self):
         return self.L.agpu_launch_count(self.h)
+
+    @property
+    def syncs(self):
+        """host waits on the stream so far (each one drains it)"""
+        return self.L.agpu_sync_count(self.h)
 
     @property
     def reserved(self):

@@ -118,6 +118,8 @@ int agpu_create(int device, void *stream, agpu_ctx **out);
 void agpu_destroy(agpu_ctx *ctx);
 const char *agpu_last_error(agpu_ctx *ctx);
 int agpu_sync(agpu_ctx *ctx);
+/* number of times this context has waited for its stream so far (every wait drains the stream: the figure to keep low) */
+int64_t agpu_sync_count(agpu_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t agpu_launch_count(agpu_ctx *ctx);
 

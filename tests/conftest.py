@@ -17,6 +17,8 @@ def pytest_configure(config):
 def emu_lib():
     """host build of the kernel bodies with a serial thread model (see aletsch_b200/csrc/dev.h):
     test-only, lets the CPU tier check kernel logic; the product never loads it."""
+    if os.environ.get("ALETSCH_EMU_LIB"):          # e.g. an AddressSanitizer build of the same sources (tools/asan_emu.sh)
+        return os.environ["ALETSCH_EMU_LIB"]
     out = os.path.join(ROOT, "tests", "emu", "libaletsch_emu.so")
     src = os.path.join(ROOT, "aletsch_b200", "csrc")
     deps = [os.path.join(src, f) for f in os.listdir(src)] + [os.path.join(ROOT, "include", "aletsch_gpu.h")]
