@@ -198,9 +198,18 @@ struct agpu_batch
 	template<typename T> T *host(const std::string &name, size_t count) { return (T*)pinned[name].ensure((count + 2) * sizeof(T)); }
 };
 
+// AGPU_DEBUG_SYNC: bit mask that puts individual stream drains back (diagnosis of ordering problems)
+static int debug_sync_mask()
+{
+	static int m = -1;
+	if(m < 0) { const char *e = getenv("AGPU_DEBUG_SYNC"); m = e ? atoi(e) : 0; }
+	return m;
+}
+#define DEBUG_SYNC(bit) do { if(debug_sync_mask() & (bit)) TRY(stream_sync(ctx)); } while(0)
+
 static int check_err(agpu_ctx *ctx, agpu_batch *b, const char *stage)
 {
-	if(b->defer_check) return AGPU_OK;        // the caller checks at its next read-back (errors are sticky counters)
+	if(b->defer_check && !(debug_sync_mask() & 2)) return AGPU_OK;        // the caller checks at its next read-back (errors are sticky counters)
 	int e[ERR_WORDS];
 	TRY(d2h(ctx, e, b->err.p, sizeof(e)));
 	TRY(stream_sync(ctx));
@@ -422,6 +431,7 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	b->q_slots = qreg[b->nb];
 	TRY(b->qreg_off.alloc(ctx, b->nb + 2));
 	TRY(h2d(ctx, b->qreg_off.p, qreg, sizeof(int64_t) * (b->nb + 1)));
+	DEBUG_SYNC(1);
 	return AGPU_OK;
 }
 
@@ -596,6 +606,7 @@ static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int6
 		LAUNCH_T(ctx, k_table_sizes_off, nb, nb, d_elem_off, sz.p);
 		LAUNCH_B(ctx, k_scan_i64, 1, 1024, sz.p, cs.reg_off.p, nb);
 		cs.n_slots = 4 * n_elem + 2 * (int64_t)nb;
+		DEBUG_SYNC(16);
 		sz.release(ctx);
 	}
 	TRY(cs.slot_word.alloc(ctx, cs.n_slots, true));

@@ -30,6 +30,10 @@ class Pipeline:
     def launches(self):
         return sum(c.launches for c in self.ctxs)
 
+    @property
+    def syncs(self):
+        return sum(c.syncs for c in self.ctxs)
+
     def sync(self):
         for c in self.ctxs:
             c.sync()

@@ -292,6 +292,7 @@ def run_ours(args):
     pipe.sync()
     barrier()
     launches_e2e0 = pipe.launches
+    syncs_e2e0 = pipe.syncs
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     d2h_bytes = 0
@@ -304,6 +305,7 @@ def run_ours(args):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     launches_e2e = pipe.launches - launches_e2e0
+    syncs_e2e = pipe.syncs - syncs_e2e0
     assert sum(r["hits"] for r in res) == n_hits * args.steps and sum(r["bridged"] for r in res) == counts["bridged"] * args.steps, "pipelined result differs"
     pipe.close()
 
@@ -384,7 +386,7 @@ def run_ours(args):
                "bridged_pairs_per_sec_stage4": bridged_all / max(stage4_ms / 1e3, 1e-12), "stage4_ms_per_step": stage4_ms,
                "counts": counts, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": "hits/s", "h2d_bytes_per_step": float(tot[2]), "d2h_bytes_per_step": float(tot[3]),
-                       "ms_per_step": ms_e2e / steps, "upload": args.upload, "sub_batches": len(views), "streams": args.streams,
+                       "ms_per_step": ms_e2e / steps, "upload": args.upload, "stream_drains_per_step": syncs_e2e / steps, "sub_batches": len(views), "streams": args.streams,
                        "gpu_launches_per_step": int(launches_e2e // steps)},
                "roofline": roof, "clocks": clk}
         if stage5 is not None:
