@@ -358,6 +358,13 @@ int agpu_reserve(agpu_ctx *ctx, int64_t bytes)
 	return AGPU_OK;
 }
 
+int agpu_upload_async(agpu_ctx *ctx, int on)
+{
+	if(!ctx) return AGPU_ERR_ARG;
+	ctx->async_upload = on != 0;
+	return AGPU_OK;
+}
+
 int agpu_blocking_sync(agpu_ctx *ctx, int on)
 {
 	if(!ctx) return AGPU_ERR_ARG;
@@ -488,8 +495,9 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
-	// the caller's buffers (and the context's staging area) are free again when this returns
-	if(stream_sync(ctx) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
+	// the caller's buffers (and the context's staging area) are free again when this returns -- unless the context uploads
+	// asynchronously (agpu_upload_async): then they are when the batch's first stage call returns
+	if(!ctx->async_upload && stream_sync(ctx) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
 	*out = b;
 	return AGPU_OK;
 }

@@ -96,6 +96,11 @@ KERNEL k_unpack_cigar(packed_dev p, const int64_t *unit_off, const int64_t *op_o
 	}
 }
 
+KERNEL k_unpack_check_total(const int64_t *total, int64_t expect, int *err)
+{
+	if(blockIdx.x == 0 && threadIdx.x == 0 && *total != expect) atomicAdd(err, 1);
+}
+
 } // namespace agpu
 
 #endif

@@ -55,6 +55,8 @@ struct agpu_ctx
 	char *stage_pin = NULL;
 	size_t stage_cap = 0;
 	int64_t syncs = 0;
+	// agpu_upload_async: the uploads of this context return as soon as their copies and decode kernels are queued
+	bool async_upload = false;
 	// optional per-kernel timing (CUDA events around every launch on the ctx stream)
 	bool profiling = false;
 	std::vector<agpu_prof_rec> prof;

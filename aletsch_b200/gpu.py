@@ -82,7 +82,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
-               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_batch_upload_packed", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync"]
+               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_batch_upload_packed", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync", "agpu_upload_async"]
 
 
 def load(lib_path=None):
@@ -104,6 +104,7 @@ def load(lib_path=None):
     L.agpu_reserved.argtypes = [C.c_void_p]
     L.agpu_reserve.argtypes = [C.c_void_p, C.c_int64]
     L.agpu_blocking_sync.argtypes = [C.c_void_p, C.c_int]
+    L.agpu_upload_async.argtypes = [C.c_void_p, C.c_int]
     L.agpu_batch_upload.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
     L.agpu_batch_adopt.argtypes = [C.c_void_p, C.POINTER(BatchIn), C.POINTER(C.c_void_p)]
     L.agpu_batch_upload_packed.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -204,6 +205,10 @@ class Context:
 
     def reserve(self, nbytes):
         self.check(self.L.agpu_reserve(self.h, int(nbytes)), "agpu_reserve")
+
+    def upload_async(self, on=True):
+        """uploads of this context return once queued; the host buffers must outlive the batch's first stage call"""
+        self.check(self.L.agpu_upload_async(self.h, 1 if on else 0), "agpu_upload_async")
 
     def blocking_sync(self, on=True):
         self.check(self.L.agpu_blocking_sync(self.h, 1 if on else 0), "agpu_blocking_sync")

@@ -11,13 +11,20 @@ from . import gpu as G
 
 
 class Pipeline:
-    def __init__(self, device=0, n_streams=3, lib_path=None, blocking_sync=None):
-        self.ctxs = [G.Context(device, lib_path=lib_path) for _ in range(max(1, n_streams))]
+    def __init__(self, device=0, n_streams=3, lib_path=None, blocking_sync=None, prefetch=True):
+        """n_streams host threads.  prefetch: every thread owns a second context and queues the upload of its next batch there
+        (agpu_upload_async) before it runs the stages of the current one, so its copy hides behind its own kernels too."""
+        self.n_threads = max(1, n_streams)
+        self.prefetch = prefetch
+        self.ctxs = [G.Context(device, lib_path=lib_path) for _ in range(self.n_threads * (2 if prefetch else 1))]
+        if prefetch:
+            for c in self.ctxs:
+                c.upload_async(True)
         if blocking_sync is None:
             # spinning waits are the fastest as long as every waiting thread has a core of its own; with one stream pool per
             # rank and several ranks per box they do not
             ranks = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-            blocking_sync = ranks * (len(self.ctxs) + 1) > (os.cpu_count() or 1) // 2
+            blocking_sync = ranks * (self.n_threads + 1) > (os.cpu_count() or 1) // 2
         for c in self.ctxs:
             c.blocking_sync(blocking_sync)
 
@@ -47,25 +54,48 @@ class Pipeline:
         lock = threading.Lock()
         errs = []
 
-        def work(ctx):
+        def claim():
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            return i if i < len(views) and not errs else None
+
+        def begin(ctx, i):
+            v, keep = views[i]
+            return ctx.adopt(v, keepalive=keep) if resident else ctx.upload(v, keepalive=keep)
+
+        def work(mine):
+            pending = None
             try:
-                while True:
-                    with lock:
-                        i = nxt[0]
-                        nxt[0] += 1
-                    if i >= len(views) or errs:
-                        return
-                    v, keep = views[i]
-                    bt = ctx.adopt(v, keepalive=keep) if resident else ctx.upload(v, keepalive=keep)
+                i = claim()
+                if i is None:
+                    return
+                turn = 0
+                cur = (i, begin(mine[0], i))
+                while cur is not None:
+                    if len(mine) > 1:
+                        # queue the next batch's upload on the other context, then run this one's stages
+                        j = claim()
+                        pending = (j, begin(mine[1 - turn], j)) if j is not None else None
+                    i, bt = cur
                     try:
                         bt.bridge_all(params)
                         out[i] = consume(i, bt) if consume else bt.counts()
                     finally:
                         bt.free()
+                    if len(mine) > 1:
+                        cur, pending, turn = pending, None, 1 - turn
+                    else:
+                        j = claim()
+                        cur = (j, begin(mine[0], j)) if j is not None else None
             except Exception as e:      # noqa: BLE001 -- re-raised on the caller's thread
                 errs.append(e)
+                if pending is not None:
+                    pending[1].free()
 
-        ths = [threading.Thread(target=work, args=(c,)) for c in self.ctxs[:max(1, min(len(self.ctxs), len(views)))]]
+        per = 2 if self.prefetch and not resident else 1
+        groups = [self.ctxs[k * per:(k + 1) * per] for k in range(self.n_threads)] if per == 2 else [[c] for c in self.ctxs[:self.n_threads]]
+        ths = [threading.Thread(target=work, args=(g,)) for g in groups[:max(1, min(len(groups), len(views)))]]
         for t in ths:
             t.start()
         for t in ths:

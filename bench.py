@@ -286,7 +286,7 @@ def run_ours(args):
         for f in lean:
             setattr(b, f, pin[f].data_ptr())
         views.append((b, pin))
-    pipe = Pipeline(local, n_streams=args.streams)
+    pipe = Pipeline(local, n_streams=args.streams, prefetch=not args.no_prefetch)
     for _ in range(min(args.warmup, 2)):
         pipe.run(views, gp)
     pipe.sync()
@@ -386,7 +386,7 @@ def run_ours(args):
                "bridged_pairs_per_sec_stage4": bridged_all / max(stage4_ms / 1e3, 1e-12), "stage4_ms_per_step": stage4_ms,
                "counts": counts, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": "hits/s", "h2d_bytes_per_step": float(tot[2]), "d2h_bytes_per_step": float(tot[3]),
-                       "ms_per_step": ms_e2e / steps, "upload": args.upload, "stream_drains_per_step": syncs_e2e / steps, "sub_batches": len(views), "streams": args.streams,
+                       "ms_per_step": ms_e2e / steps, "upload": args.upload, "prefetch": not args.no_prefetch, "stream_drains_per_step": syncs_e2e / steps, "sub_batches": len(views), "streams": args.streams,
                        "gpu_launches_per_step": int(launches_e2e // steps)},
                "roofline": roof, "clocks": clk}
         if stage5 is not None:
@@ -744,6 +744,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage5", action="store_true", help="skip the bundle_group::resolve (stage 5) leg")
     ap.add_argument("--chunks", type=int, default=4, help="sub-batches of the end-to-end pipeline")
+    ap.add_argument("--no-prefetch", action="store_true", help="end-to-end leg without the double-buffered asynchronous upload")
     ap.add_argument("--upload", choices=["compact", "lean"], default="compact",
                     help="host->device format of the end-to-end leg: agpu_batch_packed (default) or the lean agpu_batch_in")
     ap.add_argument("--streams", type=int, default=4, help="host threads / CUDA streams of the end-to-end pipeline")

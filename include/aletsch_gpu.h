@@ -129,6 +129,12 @@ int64_t agpu_launch_count(agpu_ctx *ctx);
 int64_t agpu_reserved(agpu_ctx *ctx);
 int agpu_reserve(agpu_ctx *ctx, int64_t bytes);
 
+/* on = 1: agpu_batch_upload / agpu_batch_upload_packed of this context return as soon as the copies (and the decode kernels) are
+ * queued on the context's stream.  The caller's host buffers must then stay untouched until the first stage call on the batch
+ * has returned (every stage ends with a wait on the stream), and input errors the upload would have reported surface there.
+ * This lets one host thread queue the next batch's upload on a second context before it runs the stages of the current one
+ * (aletsch_b200/pipeline.py). */
+int agpu_upload_async(agpu_ctx *ctx, int on);
 /* how the host waits for the stream inside the stages: 0 (default) spins, lowest latency; 1 sleeps on a blocking event, for
  * boxes where the host threads of all contexts outnumber the cores */
 int agpu_blocking_sync(agpu_ctx *ctx, int on);
