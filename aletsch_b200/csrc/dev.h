@@ -32,7 +32,7 @@
 #define HD inline
 #define DEV inline
 #define KERNEL static void
-#define SHARED static
+#define SHARED static thread_local
 #define BLOCK_SYNC() do {} while(0)
 struct agpu_emu_dim { unsigned x, y, z; };
 extern thread_local agpu_emu_dim threadIdx, blockIdx, blockDim, gridDim;

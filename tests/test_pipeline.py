@@ -47,9 +47,8 @@ def run_variants(lib_path, n_threads, device=0):
 
 
 def test_pipeline_variants_agree(emu_lib):
-    # one host thread: the kernel-logic build keeps "shared memory" in statics and is not re-entrant; with prefetch the thread
-    # still alternates between its two contexts
-    run_variants(emu_lib, 1)
+    # the kernel-logic build keeps a kernel's "shared memory" in thread-local statics, so host threads can run side by side
+    run_variants(emu_lib, 3)
 
 
 @pytest.mark.gpu
