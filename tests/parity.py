@@ -122,6 +122,61 @@ def compare_full(ctx, batch, checker, gp, op, stats=None):
     return bad
 
 
+def compare_golden(ctx, golden_dir):
+    """the device path against the COMMITTED fixtures (tests/golden, generated from the reference build by make_golden.py): no
+    checker library involved.  v1: evidence, graph, clusters, bridging, update; v2: phase set and boundary revision."""
+    import json
+    import os
+    g1 = json.load(open(os.path.join(golden_dir, "bundles_v1.json")))
+    g2 = json.load(open(os.path.join(golden_dir, "bundles_v2.json")))
+    batch, lt = make_batch(g1["mode"], g1["templates"], seed=g1["seed"], chrom_len=g1["chrom_len"])
+    assert batch.n_bundles == g1["n_bundles"] == g2["n_bundles"]
+    gp = G.default_params(library_type=lt)
+    gp2 = G.default_params(library_type=lt, min_boundary_log_ratio=g2["min_boundary_log_ratio"])
+    hit_off = batch.a["bundle_hit_off"]
+    bt = ctx.upload(batch.view(), keepalive=batch)
+    bt.evidence(gp)
+    ev = bt.fetch_evidence(hit_off)
+    bt.fragments()
+    bt.graph(gp)
+    gr = bt.fetch_graph()
+    bt.cluster(gp)
+    cl = bt.fetch_clusters(ev)
+    bt.bridge(gp)
+    br = bt.fetch_bridge(bt.cluster_offsets())
+    bt.update()
+    fr = bt.fetch_fragments()
+    ev2 = bt.fetch_evidence(hit_off)
+    bt.graph(gp2)
+    ph = bt.phase_set()
+    rv = bt.revise(gp2)
+    bt.free()
+    bad = []
+    n_checked = 0
+    for k in range(batch.n_bundles):
+        w = "bundle %d" % k
+        have = {}
+        have.update(ev[k])
+        have.update(gr[k])
+        have.update(cl[k])
+        have.update(br[k])
+        have.update({n: fr[k][n] for n in ("frgs", "fcst_val", "fcst_cnt")})
+        have["seg"] = ev2[k]["seg"]
+        for n, want in g1["bundles"][k]["arrays"].items():
+            want = np.array(want, np.float64 if have[n].dtype == np.float64 else np.int32)
+            (cmp_f64 if have[n].dtype == np.float64 else cmp_int)(n, want, have[n], w, bad)
+            n_checked += 1
+        if int(fr[k]["bridged"][0]) != g1["bundles"][k]["bridged"]:
+            bad.append("%s: bridged %d vs fixture %d" % (w, int(fr[k]["bridged"][0]), g1["bundles"][k]["bridged"]))
+        have2 = dict(ph[k])
+        have2.update(rv[k])
+        for n, want in g2["bundles"][k]["arrays"].items():
+            want = np.array(want, np.float64 if have2[n].dtype == np.float64 else np.int32)
+            (cmp_f64 if have2[n].dtype == np.float64 else cmp_int)(n, want, have2[n], w, bad)
+            n_checked += 1
+    return bad, n_checked
+
+
 def lean_view(batch):
     """agpu_batch_in without rpos / flag / per-hit strand (all optional): rpos is re-derived on the device, the strand goes
     up once per bundle"""

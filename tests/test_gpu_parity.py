@@ -137,6 +137,14 @@ def test_compact_upload_escapes_and_errors(ctx):
     assert "escape entry" in str(e.value) and "-4" in str(e.value)          # AGPU_ERR_INPUT
 
 
+def test_device_path_matches_committed_fixtures(ctx):
+    """no checker library in the loop: the fixtures under tests/golden were written by the reference build"""
+    import os
+    bad, n = parity.compare_golden(ctx, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    assert not bad, bad[:3]
+    assert n > 300
+
+
 def test_lean_upload_matches_full(ctx):
     """rpos / flag / per-hit strand are optional in agpu_batch_in (include/aletsch_gpu.h)"""
     batch, lt = parity.make_batch(H.SYNTH_PAIRED, 20000)

@@ -106,6 +106,29 @@ def test_group_bridge_and_resolve_match_reference_build(checkers):
     assert not bad, bad[:5]
 
 
+def test_golden_fixtures_v2(checkers):
+    """phase set and boundary revision fixtures (tests/golden/bundles_v2.json) pin whichever checker is present"""
+    path = os.path.join(os.path.dirname(__file__), "golden", "bundles_v2.json")
+    gold = json.load(open(path))
+    batch, lt = parity.make_batch(gold["mode"], gold["templates"], seed=gold["seed"], chrom_len=gold["chrom_len"])
+    _, op = parity.params_pair(lt, min_boundary_log_ratio=gold["min_boundary_log_ratio"])
+    assert batch.n_bundles == gold["n_bundles"]
+    for name, chk in checkers.items():
+        for k, g in enumerate(gold["bundles"]):
+            h = chk.new_bundle(batch.bundle(k), op)
+            chk.run(h, "fragments")
+            chk.run(h, "bridge")
+            _, ph = chk.run(h, "phase")
+            _, rv = chk.run(h, "revise")
+            chk.free_bundle(h)
+            for n, want in g["arrays"].items():
+                got = ph[n] if n in ph else rv[n]
+                if got.dtype == np.float64:
+                    np.testing.assert_allclose(got, np.array(want), rtol=1e-9, atol=0, err_msg="%s bundle %d %s" % (name, k, n))
+                else:
+                    assert got.tolist() == want, "%s bundle %d %s" % (name, k, n)
+
+
 def test_golden_fixtures(checkers):
     """fixtures generated from the reference build (tests/golden/make_golden.py) pin whichever checker is present"""
     path = os.path.join(os.path.dirname(__file__), "golden", "bundles_v1.json")
