@@ -13,6 +13,7 @@ namespace agpu {
 #define PACK_ESC_U16 0xFFFFu
 #define PACK_ESC_I16 (-32768)
 #define PACK_LONG_OP 15u
+#define PACK_ESC_UNITS 63u
 
 struct packed_dev
 {
@@ -22,10 +23,11 @@ struct packed_dev
 	const int32_t *bundle_pos0;
 	const uint16_t *dpos;
 	const int16_t *dmpos, *isize16;
-	const uint16_t *hit_units, *units;
-	int64_t n_esc_pos, n_esc_mpos, n_esc_isize;
-	const int64_t *esc_pos_idx, *esc_mpos_idx, *esc_isize_idx;
-	const int32_t *esc_pos_val, *esc_mpos_val, *esc_isize_val;
+	const uint8_t *hit_meta;
+	const uint16_t *units;
+	int64_t n_esc_pos, n_esc_mpos, n_esc_isize, n_esc_units;
+	const int64_t *esc_pos_idx, *esc_mpos_idx, *esc_isize_idx, *esc_units_idx;
+	const int32_t *esc_pos_val, *esc_mpos_val, *esc_isize_val, *esc_units_val;
 };
 
 DEV int32_t packed_escape(const int64_t *idx, const int32_t *val, int64_t n, int64_t i, int *err)
@@ -41,14 +43,19 @@ DEV int32_t packed_escape(const int64_t *idx, const int32_t *val, int64_t n, int
 	return 0;
 }
 
-// per hit: position delta and unit count as int32 (the inputs of the two device-wide scans)
-KERNEL k_unpack_widen(packed_dev p, int32_t *d32, int32_t *nun32, int *err)
+// per hit: position delta and unit count as int32 (the inputs of the two device-wide scans), and xs
+KERNEL k_unpack_widen(packed_dev p, int32_t *d32, int32_t *nun32, uint8_t *xs, int *err)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= p.n_hits) return;
 	u32 d = p.dpos[i];
 	d32[i] = d == PACK_ESC_U16 ? packed_escape(p.esc_pos_idx, p.esc_pos_val, p.n_esc_pos, i, err) : (int32_t)d;
-	nun32[i] = p.hit_units[i];
+	const u32 m = p.hit_meta[i];
+	const u32 n = m & PACK_ESC_UNITS;
+	nun32[i] = n == PACK_ESC_UNITS ? packed_escape(p.esc_units_idx, p.esc_units_val, p.n_esc_units, i, err) : (int32_t)n;
+	const u32 x = m >> 6;
+	if(x == 3) atomicAdd(err, 1);
+	xs[i] = x == 1 ? '+' : (x == 2 ? '-' : '.');
 }
 
 // pos = pos of the bundle's first hit + the deltas up to the hit; mpos, isize

@@ -332,7 +332,7 @@ class Batch:
         self.nb = bin_struct.n_bundles
         self.hit_off = None
         h = C.c_void_p()
-        name = "agpu_batch_adopt" if adopt else ("agpu_batch_upload_packed" if hasattr(bin_struct, "hit_units") else "agpu_batch_upload")
+        name = "agpu_batch_adopt" if adopt else ("agpu_batch_upload_packed" if hasattr(bin_struct, "hit_meta") else "agpu_batch_upload")
         ctx.check(getattr(ctx.L, name)(ctx.h, C.byref(bin_struct), C.byref(h)), name)
         self.h = h
 

@@ -270,11 +270,11 @@ int packer_view(void *pkp, agpu_batch_in *out)
 struct compact
 {
 	agpu_batch_packed v;
-	std::vector<int32_t> pos0, ev_pos, ev_mpos, ev_isize;
-	std::vector<uint16_t> dpos, nun, units;
+	std::vector<int32_t> pos0, ev_pos, ev_mpos, ev_isize, ev_units;
+	std::vector<uint16_t> dpos, units;
 	std::vector<int16_t> dmpos, is16;
-	std::vector<int64_t> ei_pos, ei_mpos, ei_isize;
-	std::vector<uint8_t> bstrand;
+	std::vector<int64_t> ei_pos, ei_mpos, ei_isize, ei_units;
+	std::vector<uint8_t> bstrand, meta;
 };
 
 void *packer_compact_create(const agpu_batch_in *in)
@@ -284,7 +284,7 @@ void *packer_compact_create(const agpu_batch_in *in)
 	const int nb = in->n_bundles;
 	const int64_t nh = in->n_hits;
 	c->pos0.assign(nb, 0); c->bstrand.assign(nb, (uint8_t)'.');
-	c->dpos.resize(nh); c->dmpos.resize(nh); c->is16.resize(nh); c->nun.resize(nh);
+	c->dpos.resize(nh); c->dmpos.resize(nh); c->is16.resize(nh); c->meta.resize(nh);
 	c->units.reserve((size_t)in->n_cigar + (size_t)in->n_cigar / 4);
 	for(int b = 0; b < nb; b++)
 	{
@@ -312,8 +312,11 @@ void *packer_compact_create(const agpu_batch_in *in)
 				if(len < 4096) c->units.push_back((uint16_t)(len << 4 | op));
 				else { c->units.push_back((uint16_t)((len & 0xfff) << 4 | 15)); c->units.push_back((uint16_t)((len >> 12) << 4 | op)); }
 			}
-			if(c->units.size() - u0 > 0xFFFF) { delete c; return NULL; }
-			c->nun[i] = (uint16_t)(c->units.size() - u0);
+			const size_t nu = c->units.size() - u0;
+			const uint8_t x = in->xs[i] == '+' ? 1 : (in->xs[i] == '-' ? 2 : (in->xs[i] == '.' ? 0 : 3));
+			if(nu > 0x7fffffff || x == 3) { delete c; return NULL; }
+			if(nu >= 63) { c->meta[i] = (uint8_t)(63 | x << 6); c->ei_units.push_back(i); c->ev_units.push_back((int32_t)nu); }
+			else c->meta[i] = (uint8_t)(nu | x << 6);
 		}
 	}
 	agpu_batch_packed &v = c->v;
@@ -321,9 +324,10 @@ void *packer_compact_create(const agpu_batch_in *in)
 	v.n_bundles = nb; v.n_hits = nh; v.n_cigar = in->n_cigar; v.n_units = (int64_t)c->units.size();
 	v.bundle_hit_off = in->bundle_hit_off; v.bundle_tid = in->bundle_tid; v.bundle_sample = in->bundle_sample;
 	v.bundle_strand = c->bstrand.data(); v.bundle_pos0 = c->pos0.data();
-	v.dpos = c->dpos.data(); v.dmpos = c->dmpos.data(); v.isize16 = c->is16.data(); v.xs = in->xs; v.qid = in->qid;
-	v.hit_units = c->nun.data(); v.units = c->units.data();
+	v.dpos = c->dpos.data(); v.dmpos = c->dmpos.data(); v.isize16 = c->is16.data(); v.qid = in->qid;
+	v.hit_meta = c->meta.data(); v.units = c->units.data();
 	v.n_esc_pos = (int64_t)c->ei_pos.size(); v.n_esc_mpos = (int64_t)c->ei_mpos.size(); v.n_esc_isize = (int64_t)c->ei_isize.size();
+	v.n_esc_units = (int64_t)c->ei_units.size(); v.esc_units_idx = c->ei_units.data(); v.esc_units_val = c->ev_units.data();
 	v.esc_pos_idx = c->ei_pos.data(); v.esc_pos_val = c->ev_pos.data();
 	v.esc_mpos_idx = c->ei_mpos.data(); v.esc_mpos_val = c->ev_mpos.data();
 	v.esc_isize_idx = c->ei_isize.data(); v.esc_isize_val = c->ev_isize.data();

@@ -53,7 +53,7 @@ int packer_regions(void *pk, const int64_t **reg_off, const int32_t **start1, co
 int packer_add_sample_regions(void *pk, const packer_records *r, const packer_params *p, int32_t sample);
 // the compact form of a batch for the host -> device link (agpu_batch_packed); the view points into the handle (and, for
 // bundle_hit_off / bundle_tid / bundle_sample / xs / qid, into `in`).  NULL if `in` breaks the packing contract (pos
-// decreasing inside a bundle) or holds an operation the units cannot express (length >= 2^24, more than 65535 units per hit).
+// decreasing inside a bundle) or holds an operation the units cannot express (length >= 2^24), or xs is not one of '+', '-', '.'.
 void *packer_compact_create(const agpu_batch_in *in);
 const agpu_batch_packed *packer_compact_view(void *c);
 void packer_compact_destroy(void *c);

@@ -50,18 +50,19 @@ class BatchPacked(C.Structure):
     """agpu_batch_packed (include/aletsch_gpu.h): the compact form of a batch for the host -> device link."""
     _fields_ = [("n_bundles", C.c_int32), ("n_hits", C.c_int64), ("n_cigar", C.c_int64), ("n_units", C.c_int64),
                 ("bundle_hit_off", C.c_void_p), ("bundle_tid", C.c_void_p), ("bundle_sample", C.c_void_p), ("bundle_strand", C.c_void_p),
-                ("bundle_pos0", C.c_void_p), ("dpos", C.c_void_p), ("dmpos", C.c_void_p), ("isize16", C.c_void_p), ("xs", C.c_void_p),
-                ("qid", C.c_void_p), ("hit_units", C.c_void_p), ("units", C.c_void_p),
-                ("n_esc_pos", C.c_int64), ("n_esc_mpos", C.c_int64), ("n_esc_isize", C.c_int64),
-                ("esc_pos_idx", C.c_void_p), ("esc_mpos_idx", C.c_void_p), ("esc_isize_idx", C.c_void_p),
-                ("esc_pos_val", C.c_void_p), ("esc_mpos_val", C.c_void_p), ("esc_isize_val", C.c_void_p)]
+                ("bundle_pos0", C.c_void_p), ("dpos", C.c_void_p), ("dmpos", C.c_void_p), ("isize16", C.c_void_p),
+                ("qid", C.c_void_p), ("hit_meta", C.c_void_p), ("units", C.c_void_p),
+                ("n_esc_pos", C.c_int64), ("n_esc_mpos", C.c_int64), ("n_esc_isize", C.c_int64), ("n_esc_units", C.c_int64),
+                ("esc_pos_idx", C.c_void_p), ("esc_mpos_idx", C.c_void_p), ("esc_isize_idx", C.c_void_p), ("esc_units_idx", C.c_void_p),
+                ("esc_pos_val", C.c_void_p), ("esc_mpos_val", C.c_void_p), ("esc_isize_val", C.c_void_p), ("esc_units_val", C.c_void_p)]
 
 
 COMPACT_ARRAYS = [("bundle_hit_off", np.int64, "nb1"), ("bundle_tid", np.int32, "nb"), ("bundle_sample", np.int32, "nb"),
                   ("bundle_strand", np.uint8, "nb"), ("bundle_pos0", np.int32, "nb"), ("dpos", np.uint16, "nh"), ("dmpos", np.int16, "nh"),
-                  ("isize16", np.int16, "nh"), ("xs", np.uint8, "nh"), ("qid", np.uint64, "nh"), ("hit_units", np.uint16, "nh"),
+                  ("isize16", np.int16, "nh"), ("qid", np.uint64, "nh"), ("hit_meta", np.uint8, "nh"),
                   ("units", np.uint16, "nu"), ("esc_pos_idx", np.int64, "ep"), ("esc_mpos_idx", np.int64, "em"), ("esc_isize_idx", np.int64, "ei"),
-                  ("esc_pos_val", np.int32, "ep"), ("esc_mpos_val", np.int32, "em"), ("esc_isize_val", np.int32, "ei")]
+                  ("esc_units_idx", np.int64, "eu"), ("esc_pos_val", np.int32, "ep"), ("esc_mpos_val", np.int32, "em"),
+                  ("esc_isize_val", np.int32, "ei"), ("esc_units_val", np.int32, "eu")]
 
 
 def compact_struct(arrays, n_cigar, ptr=lambda a: a.ctypes.data):
@@ -70,6 +71,7 @@ def compact_struct(arrays, n_cigar, ptr=lambda a: a.ctypes.data):
     p.n_bundles, p.n_hits = len(arrays["bundle_tid"]), len(arrays["dpos"])
     p.n_cigar, p.n_units = n_cigar, len(arrays["units"])
     p.n_esc_pos, p.n_esc_mpos, p.n_esc_isize = len(arrays["esc_pos_idx"]), len(arrays["esc_mpos_idx"]), len(arrays["esc_isize_idx"])
+    p.n_esc_units = len(arrays["esc_units_idx"])
     for name, _, _ in COMPACT_ARRAYS:
         setattr(p, name, ptr(arrays[name]))
     return p
@@ -257,7 +259,7 @@ class PackedBatch:
         try:
             p = L.packer_compact_view(c).contents
             n = {"nb": p.n_bundles, "nb1": p.n_bundles + 1, "nh": p.n_hits, "nu": p.n_units, "ep": p.n_esc_pos, "em": p.n_esc_mpos,
-                 "ei": p.n_esc_isize}
+                 "ei": p.n_esc_isize, "eu": p.n_esc_units}
             out = {}
             for name, dt, size in COMPACT_ARRAYS:
                 ptr = getattr(p, name)

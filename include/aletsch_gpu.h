@@ -148,13 +148,14 @@ int agpu_profile_read(agpu_ctx *ctx, char *buf, size_t cap);
 /* ---- batch life cycle ---------------------------------------------------------------- */
 /* host -> device copy of the packed batch (cudaMemcpyAsync per array on the ctx stream) */
 int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out);
-/* Compact form of the same input for the host -> device link (about two thirds of the bytes of the lean agpu_batch_in).  It
+/* Compact form of the same input for the host -> device link (about 60 % of the bytes of the lean agpu_batch_in).  It
  * is decoded on the device into exactly the arrays agpu_batch_upload would have copied; every later call behaves the same.
  *   pos    : bundle_pos0[b] for a bundle's first hit, then 16-bit deltas to the previous hit (pos is non-decreasing inside a
  *            bundle); 0xFFFF announces an entry (hit index, delta) in the esc_pos list
  *   mpos   : 16-bit offset from pos; -32768 announces an entry (hit index, mpos) in esc_mpos
  *   isize  : 16 bits; -32768 announces an entry in esc_isize
- *   CIGAR  : hit_units[i] 16-bit units per hit; an operation of length < 4096 is one unit, the low 16 bits of its BAM encoding
+ *   xs     : two bits of hit_meta[i] (bits 6-7: 0 '.', 1 '+', 2 '-')
+ *   CIGAR  : bits 0-5 of hit_meta[i] 16-bit units per hit (63 announces an entry (hit index, units) in esc_units); an operation of length < 4096 is one unit, the low 16 bits of its BAM encoding
  *            (len << 4 | op); a longer one (len < 2^24) is two units: 15 | (len & 0xfff) << 4, then op | (len >> 12) << 4
  *   rpos / flag / strand are not sent (see agpu_batch_in); bundle_strand is required.
  * The escape lists are sorted by hit index.  aletsch_b200/host/packer.h: packer_compact_create builds this from an
@@ -173,13 +174,12 @@ typedef struct agpu_batch_packed
 	const uint16_t *dpos;            /* [H] */
 	const int16_t *dmpos;            /* [H] */
 	const int16_t *isize16;          /* [H] */
-	const uint8_t *xs;               /* [H] */
 	const uint64_t *qid;             /* [H] */
-	const uint16_t *hit_units;       /* [H] */
+	const uint8_t *hit_meta;         /* [H] */
 	const uint16_t *units;           /* [n_units] */
-	int64_t n_esc_pos, n_esc_mpos, n_esc_isize;
-	const int64_t *esc_pos_idx, *esc_mpos_idx, *esc_isize_idx;
-	const int32_t *esc_pos_val, *esc_mpos_val, *esc_isize_val;
+	int64_t n_esc_pos, n_esc_mpos, n_esc_isize, n_esc_units;
+	const int64_t *esc_pos_idx, *esc_mpos_idx, *esc_isize_idx, *esc_units_idx;
+	const int32_t *esc_pos_val, *esc_mpos_val, *esc_isize_val, *esc_units_val;
 } agpu_batch_packed;
 int agpu_batch_upload_packed(agpu_ctx *ctx, const agpu_batch_packed *in, agpu_batch **out);
 /* same, but the arrays of `in` are DEVICE pointers already resident in HBM (no copy) */

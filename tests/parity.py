@@ -224,6 +224,7 @@ def compare_compact_upload(ctx, batch, gp, stats=None):
         stats["bytes_full"] = sum(batch.a[f].nbytes for f in ("pos", "mpos", "isize", "xs", "qid", "cigar_off", "cigar"))
         stats["bytes_compact"] = sum(a.nbytes for n, a in arrays.items() if not n.startswith("bundle_"))
         stats["escapes"] = len(arrays["esc_pos_idx"]) + len(arrays["esc_mpos_idx"]) + len(arrays["esc_isize_idx"])
+        stats["unit_escapes"] = len(arrays["esc_units_idx"])
         stats["long_ops"] = int(len(arrays["units"]) - batch.n_cigar)
     outs = []
     for view, keep, again in ((batch.view(), batch, False), (cv, (arrays, batch), False), (cv, (arrays, batch), True)):
