@@ -91,10 +91,10 @@ HD int64_t voff_base(const graph_dev &g, int b) { return g.pex_off[b] + 3 * (int
 // per bundle upper bounds for the scratch / output layout
 KERNEL k_graph_bounds(graph_in in, int64_t *ub_junc, int64_t *ub_pex, int64_t *ub_edge, int64_t *ub_iarena, int64_t *ub_karena)
 {
-	SHARED int s_inst, s_nch;
+	SHARED int s_inst;
 	for(int b = blockIdx.x; b < in.n; b += gridDim.x)
 	{
-		if(threadIdx.x == 0) { s_inst = 0; s_nch = 0; }
+		if(threadIdx.x == 0) s_inst = 0;
 		BLOCK_SYNC();
 		int nh = in.hc.count(b), nf = in.fc.count(b);
 		int acc = 0;
