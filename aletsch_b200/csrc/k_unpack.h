@@ -14,6 +14,7 @@ namespace agpu {
 #define PACK_ESC_I16 (-32768)
 #define PACK_LONG_OP 15u
 #define PACK_ESC_UNITS 63u
+#define PACK_DEFAULT_UNIT 62u
 
 struct packed_dev
 {
@@ -25,6 +26,7 @@ struct packed_dev
 	const int16_t *dmpos, *isize16;
 	const uint8_t *hit_meta;
 	const uint16_t *units;
+	u32 default_unit;
 	int64_t n_esc_pos, n_esc_mpos, n_esc_isize, n_esc_units;
 	const int64_t *esc_pos_idx, *esc_mpos_idx, *esc_isize_idx, *esc_units_idx;
 	const int32_t *esc_pos_val, *esc_mpos_val, *esc_isize_val, *esc_units_val;
@@ -52,7 +54,8 @@ KERNEL k_unpack_widen(packed_dev p, int32_t *d32, int32_t *nun32, uint8_t *xs, i
 	d32[i] = d == PACK_ESC_U16 ? packed_escape(p.esc_pos_idx, p.esc_pos_val, p.n_esc_pos, i, err) : (int32_t)d;
 	const u32 m = p.hit_meta[i];
 	const u32 n = m & PACK_ESC_UNITS;
-	nun32[i] = n == PACK_ESC_UNITS ? packed_escape(p.esc_units_idx, p.esc_units_val, p.n_esc_units, i, err) : (int32_t)n;
+	nun32[i] = n == PACK_ESC_UNITS ? packed_escape(p.esc_units_idx, p.esc_units_val, p.n_esc_units, i, err)
+			: (n == PACK_DEFAULT_UNIT ? 0 : (int32_t)n);
 	const u32 x = m >> 6;
 	if(x == 3) atomicAdd(err, 1);
 	xs[i] = x == 1 ? '+' : (x == 2 ? '-' : '.');
@@ -78,7 +81,7 @@ KERNEL k_unpack_count_ops(packed_dev p, const int64_t *unit_off, int32_t *nops)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= p.n_hits) return;
-	int n = 0;
+	int n = (p.hit_meta[i] & PACK_ESC_UNITS) == PACK_DEFAULT_UNIT ? 1 : 0;
 	for(int64_t u = unit_off[i]; u < unit_off[i + 1]; u++, n++)
 		if((p.units[u] & 0xf) == PACK_LONG_OP) u++;
 	nops[i] = n;
@@ -91,6 +94,7 @@ KERNEL k_unpack_cigar(packed_dev p, const int64_t *unit_off, const int64_t *op_o
 	cigar_off[i] = (u32)op_off[i];
 	if(i == p.n_hits) return;
 	int64_t o = op_off[i];
+	if((p.hit_meta[i] & PACK_ESC_UNITS) == PACK_DEFAULT_UNIT) cigar[o++] = p.default_unit;
 	for(int64_t u = unit_off[i]; u < unit_off[i + 1]; u++)
 	{
 		u32 a = p.units[u];

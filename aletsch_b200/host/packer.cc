@@ -1,6 +1,7 @@
 // Host-side SoA packer; see packer.h.
 #include "packer.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -286,6 +287,24 @@ void *packer_compact_create(const agpu_batch_in *in)
 	c->pos0.assign(nb, 0); c->bstrand.assign(nb, (uint8_t)'.');
 	c->dpos.resize(nh); c->dmpos.resize(nh); c->is16.resize(nh); c->meta.resize(nh);
 	c->units.reserve((size_t)in->n_cigar + (size_t)in->n_cigar / 4);
+	// the most common one-operation CIGAR of the batch travels once (default_unit) instead of once per hit
+	uint32_t def_unit = 0;
+	{
+		std::vector<uint32_t> singles;
+		for(int64_t i = 0; i < nh; i++)
+			if(in->cigar_off[i + 1] - in->cigar_off[i] == 1 && (in->cigar[in->cigar_off[i]] >> 4) < 4096 && (in->cigar[in->cigar_off[i]] & 0xf) != 15)
+				singles.push_back(in->cigar[in->cigar_off[i]]);
+		std::sort(singles.begin(), singles.end());
+		size_t best = 0;
+		for(size_t x = 0; x < singles.size(); )
+		{
+			size_t y = x;
+			while(y < singles.size() && singles[y] == singles[x]) y++;
+			if(y - x > best) { best = y - x; def_unit = singles[x]; }
+			x = y;
+		}
+		if(best == 0) def_unit = 0xFFFFFFFFu;      // no hit uses it
+	}
 	for(int b = 0; b < nb; b++)
 	{
 		const int64_t h0 = in->bundle_hit_off[b], h1 = in->bundle_hit_off[b + 1];
@@ -305,7 +324,8 @@ void *packer_compact_create(const agpu_batch_in *in)
 			if(s <= -32768 || s > 32767) { c->is16[i] = (int16_t)-32768; c->ei_isize.push_back(i); c->ev_isize.push_back(s); }
 			else c->is16[i] = (int16_t)s;
 			size_t u0 = c->units.size();
-			for(uint32_t k = in->cigar_off[i]; k < in->cigar_off[i + 1]; k++)
+			const bool is_default = in->cigar_off[i + 1] - in->cigar_off[i] == 1 && in->cigar[in->cigar_off[i]] == def_unit;
+			for(uint32_t k = in->cigar_off[i]; k < in->cigar_off[i + 1] && !is_default; k++)
 			{
 				uint32_t op = in->cigar[k] & 0xf, len = in->cigar[k] >> 4;
 				if(op == 15 || len >= (1u << 24)) { delete c; return NULL; }
@@ -315,13 +335,15 @@ void *packer_compact_create(const agpu_batch_in *in)
 			const size_t nu = c->units.size() - u0;
 			const uint8_t x = in->xs[i] == '+' ? 1 : (in->xs[i] == '-' ? 2 : (in->xs[i] == '.' ? 0 : 3));
 			if(nu > 0x7fffffff || x == 3) { delete c; return NULL; }
-			if(nu >= 63) { c->meta[i] = (uint8_t)(63 | x << 6); c->ei_units.push_back(i); c->ev_units.push_back((int32_t)nu); }
+			if(is_default) c->meta[i] = (uint8_t)(62 | x << 6);
+			else if(nu >= 62) { c->meta[i] = (uint8_t)(63 | x << 6); c->ei_units.push_back(i); c->ev_units.push_back((int32_t)nu); }
 			else c->meta[i] = (uint8_t)(nu | x << 6);
 		}
 	}
 	agpu_batch_packed &v = c->v;
 	memset(&v, 0, sizeof(v));
 	v.n_bundles = nb; v.n_hits = nh; v.n_cigar = in->n_cigar; v.n_units = (int64_t)c->units.size();
+	v.default_unit = def_unit == 0xFFFFFFFFu ? 0 : def_unit;
 	v.bundle_hit_off = in->bundle_hit_off; v.bundle_tid = in->bundle_tid; v.bundle_sample = in->bundle_sample;
 	v.bundle_strand = c->bstrand.data(); v.bundle_pos0 = c->pos0.data();
 	v.dpos = c->dpos.data(); v.dmpos = c->dmpos.data(); v.isize16 = c->is16.data(); v.qid = in->qid;

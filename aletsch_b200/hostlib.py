@@ -49,7 +49,7 @@ class BatchIn(C.Structure):
 class BatchPacked(C.Structure):
     """agpu_batch_packed (include/aletsch_gpu.h): the compact form of a batch for the host -> device link."""
     _fields_ = [("n_bundles", C.c_int32), ("n_hits", C.c_int64), ("n_cigar", C.c_int64), ("n_units", C.c_int64),
-                ("bundle_hit_off", C.c_void_p), ("bundle_tid", C.c_void_p), ("bundle_sample", C.c_void_p), ("bundle_strand", C.c_void_p),
+                ("default_unit", C.c_uint32), ("bundle_hit_off", C.c_void_p), ("bundle_tid", C.c_void_p), ("bundle_sample", C.c_void_p), ("bundle_strand", C.c_void_p),
                 ("bundle_pos0", C.c_void_p), ("dpos", C.c_void_p), ("dmpos", C.c_void_p), ("isize16", C.c_void_p),
                 ("qid", C.c_void_p), ("hit_meta", C.c_void_p), ("units", C.c_void_p),
                 ("n_esc_pos", C.c_int64), ("n_esc_mpos", C.c_int64), ("n_esc_isize", C.c_int64), ("n_esc_units", C.c_int64),
@@ -65,13 +65,14 @@ COMPACT_ARRAYS = [("bundle_hit_off", np.int64, "nb1"), ("bundle_tid", np.int32, 
                   ("esc_isize_val", np.int32, "ei"), ("esc_units_val", np.int32, "eu")]
 
 
-def compact_struct(arrays, n_cigar, ptr=lambda a: a.ctypes.data):
+def compact_struct(arrays, n_cigar, ptr=lambda a: a.ctypes.data, default_unit=None):
     """agpu_batch_packed over a dict of arrays (numpy, or anything `ptr` can turn into an address, e.g. pinned tensors)"""
     p = BatchPacked()
     p.n_bundles, p.n_hits = len(arrays["bundle_tid"]), len(arrays["dpos"])
     p.n_cigar, p.n_units = n_cigar, len(arrays["units"])
     p.n_esc_pos, p.n_esc_mpos, p.n_esc_isize = len(arrays["esc_pos_idx"]), len(arrays["esc_mpos_idx"]), len(arrays["esc_isize_idx"])
     p.n_esc_units = len(arrays["esc_units_idx"])
+    p.default_unit = int(arrays["default_unit"][0]) if default_unit is None else default_unit
     for name, _, _ in COMPACT_ARRAYS:
         setattr(p, name, ptr(arrays[name]))
     return p
@@ -264,6 +265,7 @@ class PackedBatch:
             for name, dt, size in COMPACT_ARRAYS:
                 ptr = getattr(p, name)
                 out[name] = _np(ptr, n[size], dt) if ptr else np.zeros(n[size], dt)
+            out["default_unit"] = np.array([p.default_unit], np.int64)        # a scalar of the struct, carried with the arrays
             return out
         finally:
             L.packer_compact_destroy(c)

@@ -155,7 +155,9 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out);
  *   mpos   : 16-bit offset from pos; -32768 announces an entry (hit index, mpos) in esc_mpos
  *   isize  : 16 bits; -32768 announces an entry in esc_isize
  *   xs     : two bits of hit_meta[i] (bits 6-7: 0 '.', 1 '+', 2 '-')
- *   CIGAR  : bits 0-5 of hit_meta[i] 16-bit units per hit (63 announces an entry (hit index, units) in esc_units); an operation of length < 4096 is one unit, the low 16 bits of its BAM encoding
+ *   CIGAR  : bits 0-5 of hit_meta[i] 16-bit units per hit; 62 = the hit's CIGAR is the single unit default_unit (the batch's most
+ *            common one-operation CIGAR, e.g. 100M) and takes no entry in units[]; 63 announces an entry (hit index, units) in
+ *            esc_units; an operation of length < 4096 is one unit, the low 16 bits of its BAM encoding
  *            (len << 4 | op); a longer one (len < 2^24) is two units: 15 | (len & 0xfff) << 4, then op | (len >> 12) << 4
  *   rpos / flag / strand are not sent (see agpu_batch_in); bundle_strand is required.
  * The escape lists are sorted by hit index.  aletsch_b200/host/packer.h: packer_compact_create builds this from an
@@ -166,6 +168,7 @@ typedef struct agpu_batch_packed
 	int64_t n_hits;
 	int64_t n_cigar;                 /* CIGAR operations the units decode to */
 	int64_t n_units;
+	uint32_t default_unit;           /* see hit_meta */
 	const int64_t *bundle_hit_off;   /* [NB+1] */
 	const int32_t *bundle_tid;       /* [NB] */
 	const int32_t *bundle_sample;    /* [NB] may be NULL */

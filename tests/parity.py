@@ -225,7 +225,8 @@ def compare_compact_upload(ctx, batch, gp, stats=None):
         stats["bytes_compact"] = sum(a.nbytes for n, a in arrays.items() if not n.startswith("bundle_"))
         stats["escapes"] = len(arrays["esc_pos_idx"]) + len(arrays["esc_mpos_idx"]) + len(arrays["esc_isize_idx"])
         stats["unit_escapes"] = len(arrays["esc_units_idx"])
-        stats["long_ops"] = int(len(arrays["units"]) - batch.n_cigar)
+        stats["default_cigars"] = int(((arrays["hit_meta"] & 63) == 62).sum())
+        stats["long_ops"] = int(len(arrays["units"]) - (batch.n_cigar - stats["default_cigars"]))
     outs = []
     for view, keep, again in ((batch.view(), batch, False), (cv, (arrays, batch), False), (cv, (arrays, batch), True)):
         bt = ctx.upload(view, keepalive=keep)

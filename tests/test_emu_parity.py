@@ -99,6 +99,7 @@ def test_compact_upload_matches_full(ctx, mode, templates):
     assert not bad, bad[:3]
     assert stats["bytes_compact"] < 0.75 * stats["bytes_full"], stats
     assert stats["long_ops"] > 0, stats
+    assert mode != H.SYNTH_PAIRED or stats["default_cigars"] > batch.n_hits // 4, stats
 
 
 def test_compact_upload_escapes_and_errors(ctx):
