@@ -267,6 +267,56 @@ int packer_view(void *pkp, agpu_batch_in *out)
 }
 
 
+// previewer::infer_library_type (meta/previewer.cc:29-148): a pass over the first records that are primary, mapped and carry an
+// XS / ts strand; every spliced one votes "first" when the strand its flags predict under fr-firststrand equals the tag,
+// "second" when it is the opposite.  out[0] = library type, out[1] = bam_with_xs, out[2] = reads looked at, out[3] = spliced,
+// out[4] = with xs, out[5] = used (spn), out[6] = first, out[7] = second
+int packer_infer_library_type(const packer_records *rp, const packer_params *pp, int32_t max_preview_reads, int32_t max_preview_spliced_reads,
+		int32_t min_preview_spliced_reads, double preview_infer_ratio, int32_t *out)
+{
+	const packer_records &r = *rp;
+	int total = 0, spliced = 0, num_xs = 0, first = 0, second = 0;
+	int64_t n1 = 0, n2 = 0;
+	for(int64_t i = 0; i < r.n; i++)
+	{
+		if(total >= max_preview_reads) break;
+		if(n1 >= max_preview_spliced_reads && n2 >= max_preview_spliced_reads) break;
+		const uint16_t fl = r.flag[i];
+		const uint32_t nc = r.cigar_off[i + 1] - r.cigar_off[i];
+		if((fl & 0x4) >= 1) continue;
+		if((fl & 0x100) >= 1) continue;
+		if((int64_t)nc > (int64_t)pp->max_num_cigar) continue;
+		if((int32_t)r.mapq[i] < pp->min_mapping_quality) continue;
+		if(nc < 1) continue;
+		total++;
+		if(!has_inner_splice(r.cigar + r.cigar_off[i], nc)) continue;
+		spliced++;
+		const char xs = (char)r.xs[i];
+		if(xs == '.') continue;
+		num_xs++;
+		if(xs == '+' && n1 >= max_preview_spliced_reads) continue;
+		if(xs == '-' && n2 >= max_preview_spliced_reads) continue;
+		const bool paired = (fl & 0x1) != 0, rev = (fl & 0x10) != 0, mrev = (fl & 0x20) != 0, r1 = (fl & 0x40) != 0, r2 = (fl & 0x80) != 0;
+		char p = '.';
+		if(paired && !rev && mrev && r1 && !r2) p = '-';
+		if(paired && rev && !mrev && !r1 && r2) p = '-';
+		if(paired && rev && !mrev && r1 && !r2) p = '+';
+		if(paired && !rev && mrev && !r1 && r2) p = '+';
+		if(!paired && !rev) p = '-';
+		if(!paired && rev) p = '+';
+		if(p == '+') { n1++; if(p == xs) first++; else second++; }
+		if(p == '-') { n2++; if(p == xs) first++; else second++; }
+	}
+	const int spn = (int)((n1 + n2) / 2.0);
+	int lt = AGPU_UNSTRANDED;
+	if(spn >= min_preview_spliced_reads && first > preview_infer_ratio * 2.0 * spn) lt = AGPU_FR_FIRST;
+	if(spn >= min_preview_spliced_reads && second > preview_infer_ratio * 2.0 * spn) lt = AGPU_FR_SECOND;
+	out[0] = lt;
+	out[1] = (spliced > 0 && num_xs * 1.0 / spliced > preview_infer_ratio) ? 1 : 0;
+	out[2] = total; out[3] = spliced; out[4] = num_xs; out[5] = spn; out[6] = first; out[7] = second;
+	return 0;
+}
+
 // ---- compact form for the host -> device link (agpu_batch_packed, include/aletsch_gpu.h) --------------------------------
 struct compact
 {

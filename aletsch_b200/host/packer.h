@@ -51,6 +51,10 @@ int64_t packer_region_table(void *pk, const packer_records *r, int32_t n_chrom, 
 int packer_regions(void *pk, const int64_t **reg_off, const int32_t **start1, const int32_t **start2, const int32_t **end1, const int64_t **start_rec);
 // one record loop per region of that table with start1 < end1 (meta/incubator.cc:355-380, meta/generator.cc:51-81)
 int packer_add_sample_regions(void *pk, const packer_records *r, const packer_params *p, int32_t sample);
+// previewer::infer_library_type (meta/previewer.cc:29-148) over decoded records; defaults of util/parameters.cc:65-68 are
+// 2000000, 50000, 100, 0.8.  out[8]: library type, bam_with_xs, reads, spliced, with xs, used, first, second
+int packer_infer_library_type(const packer_records *r, const packer_params *p, int32_t max_preview_reads, int32_t max_preview_spliced_reads,
+		int32_t min_preview_spliced_reads, double preview_infer_ratio, int32_t *out);
 // the compact form of a batch for the host -> device link (agpu_batch_packed); the view points into the handle (and, for
 // bundle_hit_off / bundle_tid / bundle_sample / xs / qid, into `in`).  NULL if `in` breaks the packing contract (pos
 // decreasing inside a bundle) or holds an operation the units cannot express (length >= 2^24), or xs is not one of '+', '-', '.'.

@@ -115,6 +115,8 @@ def lib():
         L.packer_destroy.argtypes = [C.c_void_p]
         L.packer_add_sample.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
         L.packer_view.argtypes = [C.c_void_p, C.POINTER(BatchIn)]
+        L.packer_infer_library_type.argtypes = [C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                                C.c_void_p]
         L.packer_compact_create.restype = C.c_void_p
         L.packer_compact_create.argtypes = [C.POINTER(BatchIn)]
         L.packer_compact_view.restype = C.POINTER(BatchPacked)
@@ -324,6 +326,23 @@ class PackedBatch:
         arr["bundle_sample"] = np.array([p["sample"] for p in parts], np.int32)
         arr["bundle_side"] = np.array([a["bundle_side"][k] for k in ks], np.uint8) if "bundle_side" in a else np.zeros(len(parts), np.uint8)
         return PackedBatch(arr)
+
+
+def infer_library_type(sample, params, max_preview_reads=2000000, max_preview_spliced_reads=50000, min_preview_spliced_reads=100,
+                       preview_infer_ratio=0.8):
+    """previewer::infer_library_type over one sample's records -> dict (library_type, bam_with_xs, reads, spliced, with_xs, used,
+    first, second)"""
+    r = PackerRecords()
+    r.n = sample["n"]
+    keep = []
+    for k in ("tid", "pos", "rpos", "mpos", "isize", "flag", "mapq", "xs", "qid", "cigar_off", "cigar"):
+        arr = np.ascontiguousarray(sample[k])
+        keep.append(arr)
+        setattr(r, k, arr.ctypes.data)
+    out = np.zeros(8, np.int32)
+    lib().packer_infer_library_type(C.byref(r), C.byref(params), max_preview_reads, max_preview_spliced_reads, min_preview_spliced_reads,
+                                    preview_infer_ratio, out.ctypes.data)
+    return dict(zip(("library_type", "bam_with_xs", "reads", "spliced", "with_xs", "used", "first", "second"), (int(x) for x in out)))
 
 
 def pack(samples, params, sample_ids=None, chrom_len=None, region_length=1000000, tables=None):

@@ -24,7 +24,8 @@ REGION = 1_000_000
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m aletsch_b200.run")
     ap.add_argument("bams", nargs="+")
-    ap.add_argument("--library-type", default="first", choices=["unstranded", "first", "second"])
+    ap.add_argument("--library-type", default="first", choices=["unstranded", "first", "second", "auto"],
+                    help="auto: previewer::infer_library_type over the first file's records")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--clusters", action="store_true", help="cross-sample clustering (-c 20 -s 0.2 style) + group-level re-bridge")
     ap.add_argument("--max-group-size", type=int, default=200)
@@ -33,7 +34,7 @@ def main(argv=None):
                     help="one record loop per file instead of the reference's region table (sample_profile::set_batch_boundaries), "
                          "which drops every region's first hit and the last region of the last chromosome")
     args = ap.parse_args(argv)
-    lt = {"unstranded": H.UNSTRANDED, "first": H.FR_FIRST, "second": H.FR_SECOND}[args.library_type]
+    lt = {"unstranded": H.UNSTRANDED, "first": H.FR_FIRST, "second": H.FR_SECOND, "auto": None}[args.library_type]
     t0 = time.time()
     recs, chrom_len = [], None
     for path in args.bams:
@@ -43,6 +44,10 @@ def main(argv=None):
         chrom_len = cl
         recs.append(r)
         print("%s: %d records" % (path, r["n"]), file=sys.stderr)
+        if lt is None:
+            pv = H.infer_library_type(r, H.default_packer_params(H.UNSTRANDED))
+            lt = pv["library_type"]
+            print("inferred library type %d from %s: %s" % (lt, path, pv), file=sys.stderr)
     batch = H.pack(recs, H.default_packer_params(lt), chrom_len=None if args.whole_file else chrom_len, region_length=REGION)
     t1 = time.time()
     gp = G.default_params(library_type=lt, max_group_size=args.max_group_size, min_grouping_similarity=args.min_grouping_similarity)

@@ -103,6 +103,9 @@ int ref_generate(const orc_records_in *in, const orc_params *prm, int use_second
  * agpu_graph_view / agpu_revise_view / agpu_phase_view pointers) */
 int ref_bundle_assemble(void *b, void *bag);
 
+/* reference build only: previewer::infer_library_type over the same records; "preview" = library_type, bam_with_xs, num_xs, spn */
+int ref_infer_library_type(const orc_records_in *in, const orc_params *prm, int max_preview_reads, int max_preview_spliced_reads,
+		int min_preview_spliced_reads, double preview_infer_ratio, void *bag);
 int ref_generate_regions(const orc_records_in *in, const orc_params *prm, int use_second_alignment, int region_length, void *bag);
 
 ORC_DECLARE(ref)

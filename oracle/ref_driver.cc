@@ -17,6 +17,7 @@
 #include "bundle.h"
 #include "bundle_group.h"
 #include "generator.h"
+#include "previewer.h"
 #include "assembler.h"
 #include "../integration/adapter.h"
 #include "graph_builder.h"
@@ -609,6 +610,42 @@ int ref_adapter_assemble(const agpu_graph_view *g, const agpu_revise_view *r, co
 	as.assemble(gr, ps, sample_id);
 	dump_transcripts(tm, bag);
 	return (int)bag.reals("trst_cov").size();
+}
+
+// previewer::infer_library_type (meta/previewer.cc:29-148) over the records served by the htslib stand-in; dumps "preview" =
+// library_type, bam_with_xs, num_xs, spn
+int ref_infer_library_type(const orc_records_in *in, const orc_params *prm, int max_preview_reads, int max_preview_spliced_reads,
+		int min_preview_spliced_reads, double preview_infer_ratio, void *bagp)
+{
+	orc_bag &bag = *(orc_bag*)bagp;
+	parameters cfg;
+	sample_profile sp(0, 1000000);
+	apply_params(prm, cfg, sp);
+	cfg.max_preview_reads = max_preview_reads; cfg.max_preview_spliced_reads = max_preview_spliced_reads;
+	cfg.min_preview_spliced_reads = min_preview_spliced_reads; cfg.preview_infer_ratio = preview_infer_ratio;
+	hts_shim_file file;
+	for(int k = 0; k < in->n_chrom; k++)
+	{
+		file.target_name.push_back("chr" + std::to_string(k + 1));
+		file.target_len.push_back((uint32_t)in->chrom_len[k]);
+	}
+	for(int64_t i = 0; i < in->n; i++)
+	{
+		uint32_t c0 = in->cigar_off[i], c1 = in->cigar_off[i + 1];
+		file.records.push_back(hts_shim_make_record(in->tid[i], in->pos[i], in->mapq[i], in->flag[i], in->tid[i], in->mpos[i], in->isize[i],
+				qname_of(in->qid[i]), in->cigar + c0, c1 - c0, (char)in->xs[i], '.', 1, 1, -1));
+	}
+	char name[64];
+	snprintf(name, sizeof(name), "mem:prev:%p", (const void*)in);
+	hts_shim_register(name, file);
+	sp.align_file = name;
+	previewer pv(cfg, sp);
+	pv.infer_library_type();
+	std::vector<int32_t> &o = bag.ints("preview");
+	o.clear();
+	o.push_back(sp.library_type); o.push_back(sp.bam_with_xs); o.push_back(sp.num_xs); o.push_back(sp.spn);
+	hts_shim_clear();
+	return sp.library_type;
 }
 
 // generator::resolve + generator::generate (meta/generator.cc:51-227) on an in-memory file behind the htslib stand-in: one

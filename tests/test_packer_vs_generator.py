@@ -106,3 +106,35 @@ def test_region_table_matches_reference(checkers, mode, lt, region_length):
     for name, key in (("gen_pos", "pos"), ("gen_rpos", "rpos"), ("gen_mpos", "mpos"), ("gen_isize", "isize"), ("gen_flag", "flag"),
                       ("gen_strand", "strand"), ("gen_xs", "xs")):
         assert np.array_equal(gen[name], batch.a[key].astype(np.int32)), name
+
+
+@pytest.mark.parametrize("mode,flip,caps", [(H.SYNTH_PAIRED, False, (2000000, 50000, 100)), (H.SYNTH_PAIRED, True, (2000000, 50000, 100)),
+                                             (H.SYNTH_PAIRED, False, (5000, 200, 100)), (H.SYNTH_PAIRED, False, (2000000, 300, 100)),
+                                             (H.SYNTH_SINGLE, False, (2000000, 50000, 100)), (H.SYNTH_LONG, False, (2000000, 50000, 100)),
+                                             (H.SYNTH_PAIRED, False, (2000000, 50000, 1000000))])
+def test_infer_library_type_matches_reference_previewer(checkers, mode, flip, caps):
+    """previewer::infer_library_type (meta/previewer.cc:29-148), the first half of the reference's preview pass, on the host"""
+    if "ref" not in checkers:
+        pytest.skip("needs oracle/_ref/libaletsch_ref.so")
+    chk = checkers["ref"]
+    cfg = H.default_config(mode, chrom_len=2_000_000, seed=20260123, n_chrom=2)
+    rec = H.Synth(cfg).sample(0, 25000 if mode != H.SYNTH_LONG else 3000, threads=4)
+    if flip:                                  # the same reads as an fr-secondstrand library would tag them
+        x = rec["xs"].copy()
+        rec["xs"] = np.where(x == ord("+"), ord("-"), np.where(x == ord("-"), ord("+"), x)).astype(np.uint8)
+    pp = H.default_packer_params(H.UNSTRANDED)
+    ours = H.infer_library_type(rec, pp, caps[0], caps[1], caps[2], 0.8)
+    r, keep = records_in(rec, [cfg.chrom_len] * cfg.n_chrom)
+    f = chk.lib.ref_infer_library_type
+    f.argtypes = [C.POINTER(RecordsIn), C.POINTER(orclib.Params), C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p]
+    chk.lib.orc_bag_new.restype = C.c_void_p
+    bag = chk.lib.orc_bag_new()
+    lt = f(C.byref(r), C.byref(orclib.default_params()), caps[0], caps[1], caps[2], 0.8, bag)
+    ref = chk.bag_to_dict(bag)["preview"]
+    chk.lib.orc_bag_free(bag)
+    assert [ours["library_type"], ours["bam_with_xs"], ours["with_xs"], ours["used"]] == [int(x) for x in ref], (ours, ref)
+    assert lt == ours["library_type"]
+    if caps == (2000000, 50000, 100) and mode == H.SYNTH_PAIRED:
+        assert ours["library_type"] == (H.FR_SECOND if flip else H.FR_FIRST), ours
+    if caps[2] == 1000000:
+        assert ours["library_type"] == H.UNSTRANDED
