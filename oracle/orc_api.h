@@ -106,6 +106,13 @@ int ref_bundle_assemble(void *b, void *bag);
 /* reference build only: previewer::infer_library_type over the same records; "preview" = library_type, bam_with_xs, num_xs, spn */
 int ref_infer_library_type(const orc_records_in *in, const orc_params *prm, int max_preview_reads, int max_preview_spliced_reads,
 		int min_preview_spliced_reads, double preview_infer_ratio, void *bag);
+/* reference build only (no restatement yet -- "parity unpinned" for this step, nothing in the product implements it): sample id
+ * of a bundle handle (sample_profile::sample_id), and the cross-sample support features of assembler::assemble(vector<bundle*>)
+ * (meta/assembler.cc:177-373) on bundles that went through fragments, bridge and group_bridge; the loops of that function around
+ * the reference's own member functions, member k dumped at the point where the reference assembles it.  See ref_driver.cc
+ * (dump_support) for the arrays. */
+int ref_bundle_set_sample(void *b, int sample_id);
+int ref_group_support(void **bs, int n, void *bag);
 int ref_generate_regions(const orc_records_in *in, const orc_params *prm, int use_second_alignment, int region_length, void *bag);
 
 ORC_DECLARE(ref)

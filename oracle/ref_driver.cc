@@ -31,6 +31,8 @@
 
 #include <cmath>
 #include <set>
+#include <unordered_map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -787,6 +789,160 @@ int ref_group_bridge(void **bs, int n, void *bagp)
 		total += cluster_solve_update(gr, h->bd, h0->cfg, bag, pre, true);
 	}
 	return total;
+}
+
+int ref_bundle_set_sample(void *b, int sample_id)
+{
+	((ref_handle*)b)->sp.sample_id = sample_id;
+	return 0;
+}
+
+namespace {
+
+// per-edge support and per-vertex boundary losses of one graph, edges in out-edge order:
+// <pre>sup_edge = src dst count per edge, <pre>sup_abd = abd per edge, <pre>sup_off / <pre>sup_sample / <pre>sup_sabd = the
+// (sample, abundance) entries of spAbd per edge sorted by sample, <pre>sup_set_off / <pre>sup_set = ei.samples per edge,
+// <pre>sup_loss = boundary_loss1 boundary_loss2 boundary_loss3 boundary_merged_loss per vertex
+void dump_support(splice_graph &gr, orc_bag &bag, const std::string &pre)
+{
+	std::vector<int32_t> &se = bag.ints(pre + "sup_edge"), &so = bag.ints(pre + "sup_off"), &ss = bag.ints(pre + "sup_sample");
+	std::vector<int32_t> &to = bag.ints(pre + "sup_set_off"), &ts = bag.ints(pre + "sup_set");
+	std::vector<double> &sa = bag.reals(pre + "sup_abd"), &sb = bag.reals(pre + "sup_sabd"), &sl = bag.reals(pre + "sup_loss");
+	se.clear(); so.clear(); ss.clear(); to.clear(); ts.clear(); sa.clear(); sb.clear(); sl.clear();
+	so.push_back(0); to.push_back(0);
+	for(int i = 0; i < (int)gr.num_vertices(); i++)
+	{
+		const vertex_info &vi = gr.get_vertex_info(i);
+		sl.push_back(vi.boundary_loss1); sl.push_back(vi.boundary_loss2); sl.push_back(vi.boundary_loss3); sl.push_back(vi.boundary_merged_loss);
+		PEEI pe = gr.out_edges(i);
+		for(edge_iterator it = pe.first; it != pe.second; ++it)
+		{
+			const edge_info &ei = gr.get_edge_info(*it);
+			se.push_back((*it)->source()); se.push_back((*it)->target()); se.push_back(ei.count);
+			sa.push_back(ei.abd);
+			std::map<int, double> m(ei.spAbd.begin(), ei.spAbd.end());
+			for(std::map<int, double>::iterator z = m.begin(); z != m.end(); ++z) { ss.push_back(z->first); sb.push_back(z->second); }
+			so.push_back((int32_t)ss.size());
+			ts.insert(ts.end(), ei.samples.begin(), ei.samples.end());
+			to.push_back((int32_t)ts.size());
+		}
+	}
+}
+
+} // namespace
+
+// the cross-sample support features of assembler::assemble(vector<bundle*>) (meta/assembler.cc:177-373) on bundles that went
+// through build_fragments, bundle::bridge and assembler::bridge: the loops of that function restated around the reference's own
+// transform / junction_support / start_end_support / non_splicing_support / boundary_extend / fix_missing_edges / assemble.
+// Member k is dumped ("m<k>_" prefix) at the point where the reference assembles it, the combined graph ("x_") at the end.
+// ORC_SUPPORT_NO_ASSEMBLE=1 leaves the assemble(gr, ps, sid) calls out (to show what they change for the later members).
+int ref_group_support(void **bs, int n, void *bagp)
+{
+	orc_bag &bag = *(orc_bag*)bagp;
+	if(n < 2) return -1;
+	ref_handle *h0 = (ref_handle*)bs[0];
+	std::vector<bundle*> gv;
+	for(int k = 0; k < n; k++) gv.push_back(&((ref_handle*)bs[k])->bd);
+	transcript_set tm(h0->bd.chrm, 0, h0->cfg.min_single_exon_clustering_overlap);
+	std::mutex lock;
+	assembler as(h0->cfg, tm, lock, 0, 0, 0);
+	int subindex = 0;
+	bundle bx(h0->cfg, gv[0]->sp);
+	bx.copy_meta_information(*(gv[0]));
+	as.combine_bundles(bx, gv);
+	bx.set_gid(0, 0, 0, subindex++);
+	splice_graph gx;
+	as.transform(bx, gx, false);
+	gx.reads = bx.frgs.size();
+	gx.subgraph = gv.size();
+	std::unordered_map<int64_t, std::set<int> > junc2sup;
+	std::unordered_map<int64_t, std::unordered_map<int, double> > sup2abd;
+	phase_set px;
+	{
+		PEEI pei = gx.edges();
+		for(edge_iterator it = pei.first; it != pei.second; it++)
+		{
+			edge_descriptor e = *it;
+			int s = e->source(), t = e->target();
+			edge_info &ei = gx.get_editable_edge_info(e);
+			ei.samples.clear(); ei.spAbd.clear();
+			ei.samples.insert(-1);
+			ei.spAbd.insert(std::make_pair(-1, gx.get_edge_weight(e)));
+			ei.abd = gx.get_edge_weight(e);
+			ei.count = 1;
+			if(s == 0 || t == (int)gx.num_vertices() - 1) continue;
+			if(gx.get_vertex_info(s).rpos == gx.get_vertex_info(t).lpos) continue;
+			int64_t p = pack(gx.get_vertex_info(s).rpos, gx.get_vertex_info(t).lpos);
+			junc2sup[p].insert(-1);
+			sup2abd[p].insert(std::make_pair(-1, gx.get_edge_weight(e)));
+		}
+	}
+	std::vector<splice_graph*> grv;
+	for(int k = 0; k < n; k++)
+	{
+		bundle &bd = *(gv[k]);
+		bd.set_gid(0, 0, 0, subindex++);
+		splice_graph *grp = new splice_graph();
+		grv.push_back(grp);
+		splice_graph &gr = *grp;
+		as.transform(bd, gr, true);
+		gr.reads = bd.frgs.size();
+		gr.subgraph = gv.size();
+		PEEI pei = gr.edges();
+		for(edge_iterator it = pei.first; it != pei.second; it++)
+		{
+			edge_descriptor e = *it;
+			int s = e->source(), t = e->target();
+			edge_info &ei = gr.get_editable_edge_info(e);
+			ei.samples.clear(); ei.spAbd.clear();
+			ei.samples.insert(bd.sp.sample_id);
+			ei.spAbd.insert(std::make_pair(bd.sp.sample_id, gr.get_edge_weight(e)));
+			ei.abd = gr.get_edge_weight(e);
+			ei.count = 1;
+			if(s == 0 || t == (int)gr.num_vertices() - 1) continue;
+			if(gr.get_vertex_info(s).rpos == gr.get_vertex_info(t).lpos) continue;
+			int64_t p = pack(gr.get_vertex_info(s).rpos, gr.get_vertex_info(t).lpos);
+			junc2sup[p].insert(bd.sp.sample_id);
+			sup2abd[p].insert(std::make_pair(bd.sp.sample_id, gr.get_edge_weight(e)));
+		}
+	}
+	for(int k = 0; k < n; k++)
+	{
+		bundle &bd = *(gv[k]);
+		splice_graph &gr = *(grv[k]);
+		as.fix_missing_edges(gr, gx);
+		as.junction_support(gr, junc2sup, sup2abd);
+		for(int j = 0; j < n; j++)
+		{
+			bundle &bd1 = *(gv[j]);
+			splice_graph &gr1 = *(grv[j]);
+			as.start_end_support(bd1.sp.sample_id, gr1, gr);
+			as.non_splicing_support(bd1.sp.sample_id, gr1, gr);
+			as.boundary_extend(bd1.sp.sample_id, gr, gr1, 1);
+			as.boundary_extend(bd1.sp.sample_id, gr, gr1, 2);
+			as.boundary_extend(bd1.sp.sample_id, gr, gr1, 3);
+		}
+		as.start_end_support(bd.sp.sample_id, gr, gx);
+		as.non_splicing_support(bd.sp.sample_id, gr, gx);
+		as.boundary_extend(-1, gr, gx, 1);
+		char pre[32];
+		snprintf(pre, sizeof(pre), "m%d_", k);
+		dump_support(gr, bag, pre);
+		// the reference assembles the member here; assemble(gr, ps, sid) regroups the start / end boundaries of gr
+		// (group_start_boundaries / group_end_boundaries, rnacore/graph_reviser.cc:916-1066) and extends its strands, so the
+		// members after k see a MODIFIED graph of member k in their own rounds
+		if(getenv("ORC_SUPPORT_NO_ASSEMBLE") == NULL)
+		{
+			phase_set ps;
+			bd.build_phase_set(ps, gr);
+			px.combine(ps);
+			as.assemble(gr, ps, bd.sp.sample_id);
+		}
+	}
+	as.junction_support(gx, junc2sup, sup2abd);
+	dump_support(gx, bag, "x_");
+	for(int k = 0; k < n; k++) delete grv[k];
+	return 0;
 }
 
 int ref_group_resolve(void **bs, int n, const orc_params *prm, void *bagp)
