@@ -106,13 +106,19 @@ int ref_bundle_assemble(void *b, void *bag);
 /* reference build only: previewer::infer_library_type over the same records; "preview" = library_type, bam_with_xs, num_xs, spn */
 int ref_infer_library_type(const orc_records_in *in, const orc_params *prm, int max_preview_reads, int max_preview_spliced_reads,
 		int min_preview_spliced_reads, double preview_infer_ratio, void *bag);
-/* reference build only (no restatement yet -- "parity unpinned" for this step, nothing in the product implements it): sample id
- * of a bundle handle (sample_profile::sample_id), and the cross-sample support features of assembler::assemble(vector<bundle*>)
- * (meta/assembler.cc:177-373) on bundles that went through fragments, bridge and group_bridge; the loops of that function around
- * the reference's own member functions, member k dumped at the point where the reference assembles it.  See ref_driver.cc
- * (dump_support) for the arrays. */
+/* Groundwork for SURVEY 8f-3 (nothing in the product implements this step yet).  <P>_bundle_set_sample: sample id of a bundle
+ * handle (sample_profile::sample_id).  <P>_group_support: the cross-sample support features of assembler::assemble(vector<bundle*>)
+ * (meta/assembler.cc:177-373) on bundles that went through fragments, bridge and group_bridge; member k is dumped at the point
+ * where the reference assembles it (see dump_support in ref_driver.cc for the arrays).
+ * ref_: the loops of that function around the reference's own member functions, INCLUDING assemble(gr, ps, sid) after every
+ * member -- which hands the member's graph to scallop by reference, so the later members see it decomposed.  With
+ * ORC_SUPPORT_GROUP_ONLY=1 only the graph changes assemble makes before scallop are applied (extend_strands,
+ * group_start_boundaries, group_end_boundaries); with ORC_SUPPORT_NO_ASSEMBLE=1 none.
+ * orc_: the restatement (restate/support.cc); it restates the GROUP_ONLY variant and is pinned against it. */
 int ref_bundle_set_sample(void *b, int sample_id);
 int ref_group_support(void **bs, int n, void *bag);
+int orc_bundle_set_sample(void *b, int sample_id);
+int orc_group_support(void **bs, int n, void *bag);
 int ref_generate_regions(const orc_records_in *in, const orc_params *prm, int use_second_alignment, int region_length, void *bag);
 
 ORC_DECLARE(ref)

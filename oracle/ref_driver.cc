@@ -931,7 +931,15 @@ int ref_group_support(void **bs, int n, void *bagp)
 		// the reference assembles the member here; assemble(gr, ps, sid) regroups the start / end boundaries of gr
 		// (group_start_boundaries / group_end_boundaries, rnacore/graph_reviser.cc:916-1066) and extends its strands, so the
 		// members after k see a MODIFIED graph of member k in their own rounds
-		if(getenv("ORC_SUPPORT_NO_ASSEMBLE") == NULL)
+		if(getenv("ORC_SUPPORT_GROUP_ONLY") != NULL)
+		{
+			// only the graph changes assemble(gr, ps, sid) makes BEFORE it hands gr to scallop (which then decomposes it in place)
+			gr.extend_strands();
+			std::map<int32_t, int32_t> smap, tmap;
+			group_start_boundaries(gr, smap, h0->cfg.max_group_boundary_distance);
+			group_end_boundaries(gr, tmap, h0->cfg.max_group_boundary_distance);
+		}
+		else if(getenv("ORC_SUPPORT_NO_ASSEMBLE") == NULL)
 		{
 			phase_set ps;
 			bd.build_phase_set(ps, gr);

@@ -310,6 +310,55 @@ int orc_bundle_revise(void *b, void *bagp)
 	return (int)rw.size();
 }
 
+int orc_bundle_set_sample(void *b, int sample_id)
+{
+	((bundle*)b)->sample = sample_id;
+	return 0;
+}
+
+static void dump_support(const graph &gr, const support &s, orc_bag &bag, const std::string &pre)
+{
+	std::vector<int32_t> &se = bag.ints(pre + "sup_edge"), &so = bag.ints(pre + "sup_off"), &ss = bag.ints(pre + "sup_sample");
+	std::vector<int32_t> &to = bag.ints(pre + "sup_set_off"), &ts = bag.ints(pre + "sup_set");
+	std::vector<double> &sa = bag.reals(pre + "sup_abd"), &sb = bag.reals(pre + "sup_sabd"), &sl = bag.reals(pre + "sup_loss");
+	se.clear(); so.clear(); ss.clear(); to.clear(); ts.clear(); sa.clear(); sb.clear(); sl.clear();
+	so.push_back(0); to.push_back(0);
+	for(int i = 0; i < gr.nv(); i++)
+	{
+		for(int x = 0; x < 4; x++) sl.push_back(s.loss[i][x]);
+		for(auto &pr : gr.out[i])
+		{
+			const int e = pr.second;
+			se.push_back(i); se.push_back(pr.first); se.push_back(s.count[e]);
+			sa.push_back(s.abd[e]);
+			for(auto &z : s.spabd[e]) { ss.push_back(z.first); sb.push_back(z.second); }
+			so.push_back((int32_t)ss.size());
+			ts.insert(ts.end(), s.samples[e].begin(), s.samples[e].end());
+			to.push_back((int32_t)ts.size());
+		}
+	}
+}
+
+// the cross-sample support features of assembler::assemble(vector<bundle*>) (meta/assembler.cc:177-373)
+int orc_group_support(void **bs, int n, void *bagp)
+{
+	orc_bag &bag = *(orc_bag*)bagp;
+	if(n < 2) return -1;
+	std::vector<graph> grs;
+	std::vector<support> sups;
+	graph gx;
+	support sx;
+	group_support((bundle**)bs, n, grs, sups, gx, sx);
+	for(int k = 0; k < n; k++)
+	{
+		char pre[32];
+		snprintf(pre, sizeof(pre), "m%d_", k);
+		dump_support(grs[k], sups[k], bag, pre);
+	}
+	dump_support(gx, sx, bag, "x_");
+	return 0;
+}
+
 // assembler::bridge (meta/assembler.cc:977-1018) with combine_bundles (:152-175) and bundle::combine (meta/bundle.cc:90-107)
 int orc_group_bridge(void **bs, int n, void *bagp)
 {

@@ -66,6 +66,7 @@ struct bundle
 	chain_set hcst, fcst;
 	coverage_map mmap;
 	orc_params prm;
+	int sample = 0;                        // sample_profile::sample_id
 };
 
 struct junction { int32_t lpos, rpos; int count, xs0, xs1, xs2; char strand; int lexon, rexon; };
@@ -119,6 +120,19 @@ struct builder_out { std::vector<junction> junctions; std::vector<pexon> pexons;
 void build_graph(const bundle &bd, graph &gr, builder_out &bo);
 void build_phase_set(const bundle &bd, const graph &gr, std::map<chain_t, int> &ps);
 void revise_graph(const bundle &bd, graph &gr, revision &rv);
+void combine_bundles(bundle **bs, int n, bundle &cb, std::vector<int> *order);
+
+// edge_info::samples / spAbd / abd / count and vertex_info::boundary_loss* of one graph (edges indexed like graph::edges)
+struct support
+{
+	std::vector<std::set<int> > samples;
+	std::vector<std::map<int, double> > spabd;
+	std::vector<double> abd;
+	std::vector<int> count;
+	std::vector<std::array<double, 4> > loss;           // boundary_loss1, 2, 3, boundary_merged_loss per vertex
+};
+// one entry per member in grs / sups: the state at the point where the reference assembles that member
+void group_support(bundle **bs, int n, std::vector<graph> &grs, std::vector<support> &sups, graph &gx, support &sx);
 void build_fragments(bundle &bd);
 void cluster_fragments(graph &gr, bundle &bd, std::vector<cluster> &vc);
 void bridge_clusters(graph &gr, std::vector<cluster> &vc, const orc_params &prm, std::vector<bridge_path> &opt);
