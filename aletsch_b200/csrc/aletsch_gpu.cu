@@ -12,6 +12,7 @@
 #include "k_phase.h"
 #include "k_revise.h"
 #include "k_unpack.h"
+#include "k_fetch.h"
 
 #include <algorithm>
 #include <atomic>
@@ -193,9 +194,11 @@ struct agpu_batch
 	std::vector<int32_t> g_order_host;     // members of every cluster in combine order (flattened like the input)
 	bool group_pass = false;               // cluster / bridge stages work against cb's graphs
 
-	// pinned result mirrors, by name
-	std::map<std::string, hbuf<char> > pinned;
-	template<typename T> T *host(const std::string &name, size_t count) { return (T*)pinned[name].ensure((count + 2) * sizeof(T)); }
+	// pinned result mirrors, by name: owned by the context (reused by every batch it processes); the combined bundles of a group
+	// pass are a batch of their own on the same context and prefix their names
+	agpu_ctx *pin_ctx = NULL;
+	std::string pin_tag;
+	template<typename T> T *host(const std::string &name, size_t count) { return (T*)pin_ctx->pinned[pin_tag + name].ensure((count + 2) * sizeof(T)); }
 };
 
 // AGPU_DEBUG_SYNC: bit mask that puts individual stream drains back (diagnosis of ordering problems)
@@ -232,6 +235,7 @@ template<typename T> static int pull(agpu_ctx *ctx, agpu_batch *b, const std::st
 	if(!h) return AGPU_ERR_OOM;
 	*out = h;
 	if(n == 0 || dev == NULL) return AGPU_OK;
+	ctx->d2h_result_bytes += (int64_t)(n * sizeof(T));
 	return d2h(ctx, h, dev, n * sizeof(T));
 }
 
@@ -291,6 +295,8 @@ int agpu_create(int device, void *stream, agpu_ctx **out)
 		ctx->ev_fork = e1; ctx->ev_join = e2;
 		cudaEvent_t e3;
 		if(cudaEventCreateWithFlags(&e3, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess) ctx->ev_sync = e3;
+		cudaEvent_t e4;
+		if(cudaEventCreateWithFlags(&e4, cudaEventDisableTiming) == cudaSuccess) ctx->ev_stage = e4;
 	}
 	// keep freed blocks in the pool: the stages allocate and free stream-ordered scratch all the time
 	cudaMemPool_t pool;
@@ -316,9 +322,11 @@ void agpu_destroy(agpu_ctx *ctx)
 	if(ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
 	if(ctx->ev_join) cudaEventDestroy((cudaEvent_t)ctx->ev_join);
 	if(ctx->ev_sync) cudaEventDestroy((cudaEvent_t)ctx->ev_sync);
+	if(ctx->ev_stage) cudaEventDestroy((cudaEvent_t)ctx->ev_stage);
 	if(ctx->own_stream) cudaStreamDestroy(ctx->stream);
 #endif
 	pinned_free(ctx->stage_pin);
+	for(auto &r : ctx->pinned) r.second.release();
 	delete ctx;
 }
 
@@ -326,6 +334,7 @@ const char *agpu_last_error(agpu_ctx *ctx) { return ctx ? ctx->last_error.c_str(
 int agpu_sync(agpu_ctx *ctx) { if(!ctx) return AGPU_ERR_ARG; AGPU_ENTER(ctx); return stream_sync(ctx); }
 int64_t agpu_launch_count(agpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t agpu_sync_count(agpu_ctx *ctx) { return ctx ? ctx->syncs : 0; }
+int64_t agpu_d2h_bytes(agpu_ctx *ctx) { return ctx ? ctx->d2h_result_bytes : 0; }
 
 // arena of the context (runtime.h): bytes held, and growth ahead of time so that a steady-state pipeline never has to take a
 // new slab (a cudaMallocAsync that misses the pool synchronises the device) in the middle of its work
@@ -406,6 +415,16 @@ int agpu_profile_read(agpu_ctx *ctx, char *buf, size_t cap)
 
 #define LARGE_BUNDLE_HITS 4096
 
+// the offsets index every per-hit array: reject anything but 0 = off[0] <= ... <= off[NB] = n_hits before a kernel sees it
+static int check_hit_offsets(agpu_ctx *ctx, agpu_batch *b)
+{
+	const std::vector<int64_t> &o = b->hit_off_host;
+	bool ok = (int64_t)o.size() == (int64_t)b->nb + 1 && o[0] == 0 && o[b->nb] == b->nh;
+	for(int k = 0; ok && k < b->nb; k++) ok = o[k] <= o[k + 1];
+	if(!ok) { ctx->last_error = "bundle_hit_off is not a non-decreasing offset array from 0 to n_hits"; return AGPU_ERR_INPUT; }
+	return AGPU_OK;
+}
+
 static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 {
 	TRY(b->err.alloc(ctx, ERR_WORDS, true));
@@ -417,6 +436,11 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	while(b->n_large < b->nb && ho[ord[b->n_large] + 1] - ho[ord[b->n_large]] >= LARGE_BUNDLE_HITS) b->n_large++;
 	// staged through the context's pinned area: asynchronous copies, no stream drain here
 	const size_t need = sizeof(int64_t) * ((size_t)b->nb + 2) + sizeof(int32_t) * ((size_t)b->nb + 2);
+#ifndef AGPU_EMU
+	// the area may still feed the asynchronous copies of the previous batch of this context (agpu_upload_async, or a group
+	// pass queued behind an upload): wait for those copies -- not for the stream -- before overwriting it
+	if(ctx->stage_busy && ctx->ev_stage) { cudaEventSynchronize((cudaEvent_t)ctx->ev_stage); ctx->stage_busy = false; }
+#endif
 	if(need > ctx->stage_cap)
 	{
 		pinned_free(ctx->stage_pin);
@@ -438,6 +462,10 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	b->q_slots = qreg[b->nb];
 	TRY(b->qreg_off.alloc(ctx, b->nb + 2));
 	TRY(h2d(ctx, b->qreg_off.p, qreg, sizeof(int64_t) * (b->nb + 1)));
+#ifndef AGPU_EMU
+	if(ctx->ev_stage && cudaEventRecord((cudaEvent_t)ctx->ev_stage, ctx->stream) == cudaSuccess) ctx->stage_busy = true;
+	else TRY(stream_sync(ctx));
+#endif
 	DEBUG_SYNC(1);
 	return AGPU_OK;
 }
@@ -460,11 +488,13 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	agpu_batch *b = new (std::nothrow) agpu_batch;
 	if(!b) return AGPU_ERR_OOM;
 	b->nb = in->n_bundles; b->nh = in->n_hits; b->nc = in->n_cigar;
+	b->pin_ctx = ctx;
 	b->owns_input = true;
 	b->hit_off_host.assign(in->bundle_hit_off, in->bundle_hit_off + b->nb + 1);
 	b->tid_host.assign(in->bundle_tid, in->bundle_tid + b->nb);
 	if(in->bundle_sample) b->sample_host.assign(in->bundle_sample, in->bundle_sample + b->nb);
-	int rc = AGPU_OK;
+	int rc = check_hit_offsets(ctx, b);
+	if(rc != AGPU_OK) { delete b; return rc; }
 	// the uploaded inputs live at the bottom of the context's arena too (below the mark a reset rewinds to): a pipeline in
 	// steady state then makes no allocator call at all
 	if(ctx->arena_owner == NULL) { ctx->arena_owner = b; ctx->arena.rewind(); }
@@ -510,6 +540,7 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	agpu_batch *b = new (std::nothrow) agpu_batch;
 	if(!b) return AGPU_ERR_OOM;
 	b->nb = in->n_bundles; b->nh = in->n_hits; b->nc = in->n_cigar;
+	b->pin_ctx = ctx;
 	b->owns_input = false;
 	b->hit_off_host.resize(b->nb + 1);
 	b->tid_host.resize(b->nb);
@@ -518,6 +549,7 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	int rc = d2h(ctx, b->hit_off_host.data(), in->bundle_hit_off, sizeof(int64_t) * (b->nb + 1));
 	if(rc == AGPU_OK) rc = d2h(ctx, b->tid_host.data(), in->bundle_tid, sizeof(int32_t) * b->nb);
 	if(rc == AGPU_OK) rc = stream_sync(ctx);
+	if(rc == AGPU_OK) rc = check_hit_offsets(ctx, b);
 	if(rc == AGPU_OK) rc = batch_common(ctx, b);
 	if(rc != AGPU_OK) { agpu_batch_free(ctx, b); return rc; }
 	b->h.n_hits = b->nh; b->h.n_bundles = b->nb;
@@ -571,7 +603,6 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 	b->err.release(ctx); b->order.release(ctx); b->qreg_off.release(ctx);
 	stream_sync(ctx);
 	if(ctx->arena_owner == b) { ctx->arena.rewind(); ctx->arena_owner = NULL; }
-	for(auto &r : b->pinned) r.second.release();
 	delete b;
 }
 

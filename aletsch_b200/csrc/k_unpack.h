@@ -30,6 +30,7 @@ struct packed_dev
 	int64_t n_esc_pos, n_esc_mpos, n_esc_isize, n_esc_units;
 	const int64_t *esc_pos_idx, *esc_mpos_idx, *esc_isize_idx, *esc_units_idx;
 	const int32_t *esc_pos_val, *esc_mpos_val, *esc_isize_val, *esc_units_val;
+	int64_t n_units, n_cigar;       // sizes of units[] and of the decoded cigar[]: every index below is clamped against them
 };
 
 DEV int32_t packed_escape(const int64_t *idx, const int32_t *val, int64_t n, int64_t i, int *err)
@@ -54,8 +55,10 @@ KERNEL k_unpack_widen(packed_dev p, int32_t *d32, int32_t *nun32, uint8_t *xs, i
 	d32[i] = d == PACK_ESC_U16 ? packed_escape(p.esc_pos_idx, p.esc_pos_val, p.n_esc_pos, i, err) : (int32_t)d;
 	const u32 m = p.hit_meta[i];
 	const u32 n = m & PACK_ESC_UNITS;
-	nun32[i] = n == PACK_ESC_UNITS ? packed_escape(p.esc_units_idx, p.esc_units_val, p.n_esc_units, i, err)
+	int32_t nu = n == PACK_ESC_UNITS ? packed_escape(p.esc_units_idx, p.esc_units_val, p.n_esc_units, i, err)
 			: (n == PACK_DEFAULT_UNIT ? 0 : (int32_t)n);
+	if(nu < 0 || (int64_t)nu > p.n_units) { atomicAdd(err, 1); nu = 0; }     // a hostile escape value must not wrap the scan
+	nun32[i] = nu;
 	const u32 x = m >> 6;
 	if(x == 3) atomicAdd(err, 1);
 	xs[i] = x == 1 ? '+' : (x == 2 ? '-' : '.');
@@ -77,29 +80,41 @@ KERNEL k_unpack_pos(packed_dev p, const int64_t *dsum, const int32_t *d32, int32
 }
 
 // CIGAR operations of a hit: a unit is op | len << 4 (len < 4096), or 15 | (len & 0xfff) << 4 followed by op | (len >> 12) << 4
-KERNEL k_unpack_count_ops(packed_dev p, const int64_t *unit_off, int32_t *nops)
+// Inputs are untrusted: the unit range of a hit is clamped to units[0, n_units) and a long operation whose second unit
+// would lie outside it counts as a violation (ERR_PACKED) instead of being read.
+KERNEL k_unpack_count_ops(packed_dev p, const int64_t *unit_off, int32_t *nops, int *err)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= p.n_hits) return;
 	int n = (p.hit_meta[i] & PACK_ESC_UNITS) == PACK_DEFAULT_UNIT ? 1 : 0;
-	for(int64_t u = unit_off[i]; u < unit_off[i + 1]; u++, n++)
-		if((p.units[u] & 0xf) == PACK_LONG_OP) u++;
+	int64_t u1 = unit_off[i + 1];
+	if(u1 > p.n_units) { u1 = p.n_units; atomicAdd(err, 1); }
+	if(i + 1 == p.n_hits && unit_off[i + 1] != p.n_units) atomicAdd(err, 1);
+	for(int64_t u = unit_off[i]; u < u1; u++, n++)
+		if((p.units[u] & 0xf) == PACK_LONG_OP) { if(u + 1 >= u1) { atomicAdd(err, 1); break; } u++; }
 	nops[i] = n;
 }
 
+// The scatter is a no-op for the whole batch unless the decoded operation total equals n_cigar (the size cigar[] was
+// allocated with): a disagreeing batch is reported (k_unpack_check_total / the host check) and never written.
 KERNEL k_unpack_cigar(packed_dev p, const int64_t *unit_off, const int64_t *op_off, u32 *cigar_off, u32 *cigar)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i > p.n_hits) return;
-	cigar_off[i] = (u32)op_off[i];
-	if(i == p.n_hits) return;
+	const bool sane = op_off[p.n_hits] == p.n_cigar;
+	cigar_off[i] = sane ? (u32)op_off[i] : 0u;
+	if(i == p.n_hits || !sane) return;
 	int64_t o = op_off[i];
-	if((p.hit_meta[i] & PACK_ESC_UNITS) == PACK_DEFAULT_UNIT) cigar[o++] = p.default_unit;
-	for(int64_t u = unit_off[i]; u < unit_off[i + 1]; u++)
+	const int64_t o1 = op_off[i + 1];
+	int64_t u1 = unit_off[i + 1];
+	if(u1 > p.n_units) u1 = p.n_units;
+	if((p.hit_meta[i] & PACK_ESC_UNITS) == PACK_DEFAULT_UNIT && o < o1) cigar[o++] = p.default_unit;
+	for(int64_t u = unit_off[i]; u < u1 && o < o1; u++)
 	{
 		u32 a = p.units[u];
 		if((a & 0xf) == PACK_LONG_OP)
 		{
+			if(u + 1 >= u1) break;
 			u32 c = p.units[++u];
 			cigar[o++] = (((c >> 4) << 12 | (a >> 4)) << 4) | (c & 0xf);
 		}

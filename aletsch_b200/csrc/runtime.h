@@ -12,6 +12,15 @@
 struct agpu_batch;
 struct agpu_prof_rec { const char *name; void *e0, *e1; };
 
+// pinned host array (results): grown on demand, kept by the context
+struct agpu_pinbuf
+{
+	char *p = NULL;
+	size_t cap = 0;
+	char *ensure(size_t bytes);
+	void release();
+};
+
 // Bump arena for the derived state of ONE batch per context: a few large slabs taken from the stream-ordered pool once and
 // kept for the context's lifetime.  The stages allocate ~150 arrays per step; bumping a pointer instead of going through
 // cudaMallocAsync / cudaFreeAsync removes that API time and, with several contexts working side by side (pipeline.py), the
@@ -51,10 +60,16 @@ struct agpu_ctx
 	bool blocking_sync = false;
 	void *ev_sync = NULL;
 	// small pinned staging area for the per-bundle tables an upload derives on the host (grown on demand, reused by every batch
-	// of the context: a batch's upload ends with a stream synchronisation, so the area is free again when the next one starts)
+	// of the context).  The copies out of it are asynchronous: ev_stage is recorded behind them and the next user of the area
+	// waits for that event first, so a second upload / group pass on the same context cannot overwrite tables still in flight.
 	char *stage_pin = NULL;
 	size_t stage_cap = 0;
+	void *ev_stage = NULL;
+	bool stage_busy = false;
+	// pinned result mirrors of the fetches, by name (see agpu_batch::host)
+	std::map<std::string, agpu_pinbuf> pinned;
 	int64_t syncs = 0;
+	int64_t d2h_result_bytes = 0;       // bytes the result fetches copied device -> host (agpu_d2h_bytes)
 	// agpu_upload_async: the uploads of this context return as soon as their copies and decode kernels are queued
 	bool async_upload = false;
 	// optional per-kernel timing (CUDA events around every launch on the ctx stream)
@@ -251,18 +266,14 @@ template<typename T> struct dbuf
 	int fill(agpu_ctx *ctx, int byte) { return dev_fill(ctx, p, byte, n * sizeof(T)); }
 };
 
-// pinned host array (results)
-template<typename T> struct hbuf
+} // namespace agpu
+inline char *agpu_pinbuf::ensure(size_t bytes)
 {
-	T *p = NULL;
-	size_t cap = 0;
-	T *ensure(size_t count)
-	{
-		if(count + 1 > cap) { pinned_free(p); cap = (count + 1) * 5 / 4 + 16; p = (T*)pinned_alloc(cap * sizeof(T)); }
-		return p;
-	}
-	void release() { pinned_free(p); p = NULL; cap = 0; }
-};
+	if(bytes + 1 > cap) { agpu::pinned_free(p); cap = (bytes + 1) * 5 / 4 + 64; p = (char*)agpu::pinned_alloc(cap); if(!p) cap = 0; }
+	return p;
+}
+inline void agpu_pinbuf::release() { agpu::pinned_free(p); p = NULL; cap = 0; }
+namespace agpu {
 
 #define TRY(x) do { int rc_ = (x); if(rc_ != AGPU_OK) return rc_; } while(0)
 

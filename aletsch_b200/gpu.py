@@ -61,6 +61,15 @@ class BridgeView(C.Structure):
                 ("whole_off", P64), ("whole", P32)]
 
 
+class Results(C.Structure):
+    """agpu_results"""
+    _fields_ = [("evidence", EvidenceView), ("fragments", FragmentsView), ("graph", GraphView), ("clusters", ClusterView),
+                ("bridges", BridgeView), ("bytes", C.c_int64)]
+
+
+RESULT_EVIDENCE, RESULT_FRAGMENTS, RESULT_GRAPH, RESULT_CLUSTERS, RESULT_BRIDGES, RESULT_ALL = 1, 2, 4, 8, 16, 31
+
+
 class ReviseView(C.Structure):
     _fields_ = [("edge_off", P64), ("edge", P32), ("edge_w", PF), ("vert_off", P64), ("unbridge", P32), ("unbridge_ratio", PF),
                 ("n_edges", C.c_int64), ("n_vertices", C.c_int64)]
@@ -82,7 +91,8 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_batch_bridge_all", "agpu_evidence_fetch", "agpu_fragments_fetch", "agpu_graph_fetch", "agpu_cluster_fetch",
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
-               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_batch_upload_packed", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync", "agpu_upload_async"]
+               "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_batch_upload_packed", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync", "agpu_upload_async",
+               "agpu_batch_results", "agpu_d2h_bytes"]
 
 
 def load(lib_path=None):
@@ -120,6 +130,9 @@ def load(lib_path=None):
     L.agpu_cluster_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ClusterView)]
     L.agpu_bridge_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(BridgeView)]
     L.agpu_batch_counts.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Counts)]
+    L.agpu_batch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Results)]
+    L.agpu_d2h_bytes.restype = C.c_int64
+    L.agpu_d2h_bytes.argtypes = [C.c_void_p]
     L.agpu_splices_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P64), C.POINTER(P32)]
     L.agpu_batch_bundle_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.agpu_batch_phase_set.argtypes = [C.c_void_p, C.c_void_p]
@@ -198,6 +211,11 @@ class Context:
     def syncs(self):
         """host waits on the stream so far (each one drains it)"""
         return self.L.agpu_sync_count(self.h)
+
+    @property
+    def d2h_bytes(self):
+        """device -> host bytes the result fetches of this context have copied so far"""
+        return self.L.agpu_d2h_bytes(self.h)
 
     @property
     def reserved(self):
@@ -372,6 +390,14 @@ class Batch:
 
     def bridge_all(self, p):
         self._run("bridge_all", p)
+
+    def results(self, what=RESULT_ALL):
+        """agpu_batch_results: every structure bundle::bridge leaves behind, packed on the device and copied into the context's
+        pinned host buffers.  Returns the C struct of views (pointers into pinned memory, valid until the next fetch on this
+        context); `.bytes` is the device -> host traffic of the call."""
+        r = Results()
+        self.ctx.check(self.ctx.L.agpu_batch_results(self.ctx.h, self.h, what, C.byref(r)), "agpu_batch_results")
+        return r
 
     def counts(self):
         c = Counts()

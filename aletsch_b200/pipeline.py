@@ -45,10 +45,13 @@ class Pipeline:
         for c in self.ctxs:
             c.sync()
 
-    def run(self, views, params, consume=None, resident=False):
-        """views: list of (agpu_batch_in with HOST pointers, keepalive).  Each batch goes through upload + bridge_all;
-        consume(i, batch) may fetch results while the batch is still resident (default: the counters).  Returns the list of
-        per-batch results in input order.  resident=True: the views hold DEVICE pointers (agpu_batch_adopt, no copy)."""
+    def run(self, views, params, consume=None, resident=False, results=G.RESULT_ALL):
+        """views: list of (agpu_batch_in with HOST pointers, keepalive).  Each batch goes through upload + bridge_all and its
+        results come back to the host: by default agpu_batch_results(results) -- everything bundle::bridge leaves behind
+        (mmap, hcst, frgs, fcst, splice graph, pereads clusters, bridge paths) packed on the device and copied into the context's
+        pinned buffers -- handed to consume(i, batch, agpu_results) while the views are valid (default: keep the counters and the
+        device -> host byte count).  results=0 skips the fetch (counters only).  Returns the per-batch results in input order.
+        resident=True: the views hold DEVICE pointers (agpu_batch_adopt, no copy)."""
         out = [None] * len(views)
         nxt = [0]
         lock = threading.Lock()
@@ -65,7 +68,7 @@ class Pipeline:
             return ctx.adopt(v, keepalive=keep) if resident else ctx.upload(v, keepalive=keep)
 
         def work(mine):
-            pending = None
+            pending = cur = None
             try:
                 i = claim()
                 if i is None:
@@ -80,9 +83,16 @@ class Pipeline:
                     i, bt = cur
                     try:
                         bt.bridge_all(params)
-                        out[i] = consume(i, bt) if consume else bt.counts()
+                        cnt = None if consume else bt.counts()
+                        res = bt.results(results) if results else None
+                        if consume:
+                            out[i] = consume(i, bt, res)
+                        else:
+                            out[i] = cnt
+                            out[i]["d2h_bytes"] = int(res.bytes) if res is not None else 0
                     finally:
                         bt.free()
+                        cur = None
                     if len(mine) > 1:
                         cur, pending, turn = pending, None, 1 - turn
                     else:
@@ -90,8 +100,14 @@ class Pipeline:
                         cur = (j, begin(mine[0], j)) if j is not None else None
             except Exception as e:      # noqa: BLE001 -- re-raised on the caller's thread
                 errs.append(e)
-                if pending is not None:
-                    pending[1].free()
+            finally:
+                # nothing stays resident on an error path: the prefetched batch and a current one whose stages never ran
+                for x in (pending, cur):
+                    if x is not None:
+                        try:
+                            x[1].free()
+                        except Exception:       # noqa: BLE001
+                            pass
 
         per = 2 if self.prefetch and not resident else 1
         groups = [self.ctxs[k * per:(k + 1) * per] for k in range(self.n_threads)] if per == 2 else [[c] for c in self.ctxs[:self.n_threads]]
@@ -104,8 +120,12 @@ class Pipeline:
             raise errs[0]
         # every context keeps as much scratch as the hungriest one has needed so far: whichever sub-batch a thread takes
         # next, it will not have to grow its arena in the middle of the pipeline (idempotent once the sizes agree)
+        # (best effort: a failed reservation must not lose the finished results)
         need = max(c.reserved for c in self.ctxs)
         for c in self.ctxs:
             if c.reserved < need:
-                c.reserve(need)
+                try:
+                    c.reserve(need)
+                except G.AgpuError:
+                    break
         return out

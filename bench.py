@@ -28,46 +28,113 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from aletsch_b200 import hostlib as H   # noqa: E402
 
-SAMPLES = 10
-PAIRS = 5_000_000
-CHROM_LEN = 100_000_000
-SEED = 20260101 + 1          # synth-v1, config index 1
+SEED0 = 20260101             # synth-v1: seed = SEED0 + config index
+
+# BASELINE.json configs.  `templates` = pairs / reads per sample PER GPU; `n_chrom` chromosomes of `chrom_len` per GPU.
+# configs[2] is the 8-GPU job (100 samples x 20M pairs over a 24-chromosome genome): each GPU owns 24 / 8 = 3 chromosomes, i.e.
+# 20M / 8 = 2.5M pairs per sample; `scale` (default below) shrinks the depth so that generation + run stay within minutes.
+CONFIGS = {
+    0: dict(what="1 synthetic paired_end sample x %d pairs, 1 chromosome of %d bp per GPU, bridging on", mode="paired", samples=1,
+            templates=2_000_000, n_chrom=1, chrom_len=100_000_000, scale=1.0, group=dict(max_group_size=200, min_grouping_similarity=0.10),
+            group_str="-c 200 -s 0.1 (defaults)"),
+    1: dict(what="10 synthetic paired_end samples x %d pairs, 1 chromosome of %d bp per GPU, bridging on", mode="paired", samples=10,
+            templates=5_000_000, n_chrom=1, chrom_len=100_000_000, scale=1.0, group=dict(max_group_size=20, min_grouping_similarity=0.2),
+            group_str="-c 20 -s 0.2"),
+    2: dict(what="100 synthetic paired_end samples x %d pairs on this GPU's 3 of 24 chromosomes (%d bp each): the per-GPU shard of the "
+                 "8-GPU job at depth scale", mode="paired", samples=100, templates=2_500_000, n_chrom=3, chrom_len=100_000_000, scale=0.1,
+            group=dict(max_group_size=200, min_grouping_similarity=0.10), group_str="-c 200 -s 0.1 (defaults)"),
+    3: dict(what="single-cell style: 1000 cells x %d single_end reads, 1 chromosome of %d bp per GPU, each cell expressing 10%% of the genes",
+            mode="single", samples=1000, templates=200_000, n_chrom=1, chrom_len=100_000_000, scale=1.0, expressed_fraction=0.1,
+            group=dict(max_group_size=2000, min_grouping_similarity=0.10), group_str="-c 2000 -s 0.1"),
+    4: dict(what="20 synthetic long-read samples x %d reads (ont preset: min_junction_support 2), 1 chromosome of %d bp per GPU",
+            mode="long", samples=20, templates=500_000, n_chrom=1, chrom_len=100_000_000, scale=1.0, min_junction_support=2,
+            group=dict(max_group_size=200, min_grouping_similarity=0.10), group_str="-c 200 -s 0.1 (defaults)"),
+}
+MAX_BATCH_SPAN = 3_000_000_000     # window positions per device batch: the ABI's coverage index is 32-bit (AGPU_ERR_CAPACITY above 2^32)
+MAX_BATCH_HITS = 60_000_000
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def build_workload(rank, scale, threads):
-    """records of SAMPLES samples on this rank's chromosome, packed into one batch of bundles"""
+def config_of(args):
+    c = dict(CONFIGS[args.config])
+    c["scale_used"] = args.scale if args.scale is not None else c["scale"]
+    c["per_sample"] = max(1000, int(c["templates"] * c["scale_used"]))
+    c["mode_id"] = {"paired": H.SYNTH_PAIRED, "single": H.SYNTH_SINGLE, "long": H.SYNTH_LONG}[c["mode"]]
+    c["library_type"] = H.FR_FIRST if c["mode"] == "paired" else H.UNSTRANDED
+    c["seed"] = SEED0 + args.config
+    return c
+
+
+def workload_string(c, index):
+    return "configs[%d]: " % index + c["what"] % (c["per_sample"], c["chrom_len"])
+
+
+def build_workload(cfg, rank, threads):
+    """records of all samples on this rank's chromosome(s), packed into one host batch of bundles"""
     t0 = time.time()
-    cfg = H.default_config(H.SYNTH_PAIRED, chrom_len=CHROM_LEN, seed=SEED + 1000 * rank)
-    syn = H.Synth(cfg)
-    pairs = max(1000, int(PAIRS * scale))
-    recs = [None] * SAMPLES
-    n_records = [0] * SAMPLES
-
-    def work(k):
-        recs[k] = syn.sample(k, pairs, threads=2)
-        n_records[k] = recs[k]["n"]
-
+    kw = {}
+    if "expressed_fraction" in cfg:
+        kw["expressed_fraction"] = cfg["expressed_fraction"]
+    sc = H.default_config(cfg["mode_id"], chrom_len=cfg["chrom_len"], n_chrom=cfg["n_chrom"], seed=cfg["seed"] + 1000 * rank, **kw)
+    syn = H.Synth(sc)
+    ns = cfg["samples"]
+    recs = [None] * ns
+    n_records = [0] * ns
     sem = threading.Semaphore(max(1, threads // 2))
 
     def guarded(k):
         with sem:
-            work(k)
+            recs[k] = syn.sample(k, cfg["per_sample"], threads=2)
+            n_records[k] = recs[k]["n"]
 
-    ths = [threading.Thread(target=guarded, args=(k,)) for k in range(SAMPLES)]
-    for t in ths:
-        t.start()
-    for t in ths:
-        t.join()
+    # a bounded number of generator threads at a time (1000 cells do not get 1000 threads)
+    pending = list(range(ns))
+    while pending:
+        wave, pending = pending[:4 * threads], pending[4 * threads:]
+        ths = [threading.Thread(target=guarded, args=(k,)) for k in wave]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
     t1 = time.time()
-    batch = H.pack(recs, H.default_packer_params(H.FR_FIRST))
+    batch = H.pack(recs, H.default_packer_params(cfg["library_type"]))
     t2 = time.time()
     log("[bench] rank %d: %d records generated in %.1fs, packed %d bundles / %d admitted hits in %.1fs" %
         (rank, sum(n_records), t1 - t0, batch.n_bundles, batch.n_hits, t2 - t1))
-    return batch, sum(n_records), pairs
+    return batch, sum(n_records)
+
+
+def device_batches(batch):
+    """The batching rule of the ABI: one device batch holds < 2^32 coverage-window positions (the border bitmap is indexed with 32
+    bits, agpu_batch_evidence returns AGPU_ERR_CAPACITY otherwise) -- cut the host batch into contiguous runs of whole bundles
+    below MAX_BATCH_SPAN window positions and MAX_BATCH_HITS hits.  configs[0], [1], [4] fit one batch."""
+    a = batch.a
+    off = a["bundle_hit_off"]
+    nb = batch.n_bundles
+    if nb == 0:
+        return [batch]
+    first = np.minimum(off[:-1], max(batch.n_hits - 1, 0))
+    last = np.maximum(off[1:] - 1, first)
+    # window of a bundle: [lpos, rpos) grown to 128-base alignment; rpos may be a mate position up to 500 kb further (add_hit)
+    hi = np.maximum.reduceat(np.maximum(a["rpos"], np.where((a["mpos"] > a["rpos"]) & (a["mpos"] <= a["rpos"] + 500000), a["mpos"], 0)), first) \
+        if batch.n_hits else np.zeros(nb, np.int64)
+    span = np.where(off[1:] > off[:-1], (hi.astype(np.int64) - a["pos"][first].astype(np.int64)) + 512, 256)
+    cuts = [0]
+    s = h = 0
+    for k in range(nb):
+        nh = int(off[k + 1] - off[k])
+        if k > cuts[-1] and (s + int(span[k]) > MAX_BATCH_SPAN or h + nh > MAX_BATCH_HITS):
+            cuts.append(k)
+            s = h = 0
+        s += int(span[k])
+        h += nh
+    cuts.append(nb)
+    if len(cuts) == 2:
+        return [batch]
+    return [batch.slice(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
 
 
 class ClockSampler:
@@ -126,6 +193,7 @@ def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
     from the real counts of the batch"""
     Hh, S, F, C = cnt["hits"], cnt["segments"], cnt["fragments"], cnt["clusters"]
     J, V, E, NBD, M = cnt["junctions"], cnt["vertices"], cnt["edges"], cnt["borders"], cnt["cluster_members"]
+    Mbig = cnt.get("big_group_members", 0)
     kernel = kernel.replace("(side)", "")
     if kernel == "k_hit_cigar":
         # in: pos, rpos, cigar_off (12 B/hit) + CIGAR ops; out: nspl, hash, bundle id (16 B/hit) + splice coordinates
@@ -140,6 +208,9 @@ def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
         return Hh * (8 + 4 + 8 + 4) + Hh * 16       # qid, bundle id in; slot index, next out; one 16-byte slot touch
     if kernel == "k_pair":
         return Hh * (8 + 4 + 16 + 4) + F * (2 * 12 + 8)   # slot index, bundle id, slot, next per hit; pos/mpos/isize of both mates, mate out
+    if kernel == "k_pair_bundle":
+        # per hit: qid (8) + pos, mpos, isize (12) in, mate (4) out
+        return Hh * (8 + 12 + 4)
     if kernel == "k_hcst_insert":
         return Hh * (4 + 8 + 4 + 1 + 8) + 8 * n_splice_pairs
     if kernel == "k_frag_align":
@@ -152,11 +223,38 @@ def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
         # both passes: per cluster vp1, vp2, bundle, two chain ids, two bounds, pier (32 B) in, 8 result words (36 B) out, the pick
         # and two offsets (20 B) back in; the coordinates of the chosen chain / whole read and written once
         return C * (32 + 36 + 20) + 8 * cnt["bridge_whole_ints"] + 8 * cnt["bridge_chain_ints"]
-    if kernel in ("k_group_partition", "k_group_partition_warp"):
-        return M * (8 + 16 + 8)                     # h1 / h2, four keys, member + cluster flag out
+    # the two partition kernels split the cluster members between them: the groups of more than 16 fragments (Mbig members) go
+    # to the warp kernel, the rest to the thread-per-group kernel; h1 / h2, four keys, member + cluster flag out = 32 B/member
+    if kernel == "k_group_partition_warp":
+        return Mbig * (8 + 16 + 8)
+    if kernel == "k_group_partition":
+        return (M - Mbig) * (8 + 16 + 8)
     if kernel == "k_update":
         return 2 * (C * 24 + M * (4 + 8 + 8 + 2)) + M * 4 + cnt["bridged"] * 20
     return None
+
+
+def step_bytes(cnt, n_cigar):
+    """whole-step algorithmic bytes (stages 1-3 of SURVEY.md section 8(d) + the graph / cluster headers from the real counts).
+    `survey`: the formula as the survey wrote it, with a per-base difference array (8.25 B per base of bundle span L).
+    `layout`: the same with this implementation's border-compacted coverage map (3 bits per base for the border bitmap + 16 B per
+    border instead of the per-base array) -- the smaller, stricter denominator."""
+    Hh, S, F, C, L = cnt["hits"], cnt["segments"], cnt["fragments"], cnt["clusters"], cnt["span"]
+    J, V, E, NBD, M = cnt["junctions"], cnt["vertices"], cnt["edges"], cnt["borders"], cnt["cluster_members"]
+    common = 76 * Hh + 4 * n_cigar + 12 * S + 16 * J + 4 * cnt["splice_ints"] + 48 * max(V - 2 * cnt.get("bundles", 0), 0) + 56 * V + 20 * E \
+        + 12 * F + 16 * F + 32 * C + 4 * M + 8 * cnt["bridge_whole_ints"] + 8 * cnt["bridge_chain_ints"]
+    return {"survey": common + 8.25 * L, "layout": common + 3 * L / 8 + 16 * NBD}
+
+
+def gpu_params(cfg, G):
+    return G.default_params(library_type=cfg["library_type"], min_junction_support=cfg.get("min_junction_support", 1))
+
+
+FIELDS = ["bundle_hit_off", "bundle_tid", "bundle_sample", "pos", "rpos", "mpos", "isize", "flag", "strand", "xs", "qid", "cigar_off", "cigar"]
+
+
+def _tview(a):
+    return a.view(np.int64) if a.dtype == np.uint64 else (a.view(np.int32) if a.dtype == np.uint32 else (a.view(np.int16) if a.dtype == np.uint16 else a))
 
 
 def run_ours(args):
@@ -173,31 +271,29 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ncpu = os.cpu_count() or 8
-    batch, n_records, pairs = build_workload(rank, args.scale, max(2, ncpu // max(1, world)))
-    gp = G.default_params(library_type=H.FR_FIRST)
-
+    cfg = config_of(args)
+    batch, n_records = build_workload(cfg, rank, max(2, ncpu // max(1, world)))
+    parts = device_batches(batch)
+    gp = gpu_params(cfg, G)
     stream = torch.cuda.current_stream()
-    ctx = G.Context(local, stream=stream.cuda_stream)
 
-    # pinned host copies (e2e path) and device-resident copies (kernel path)
-    fields = ["bundle_hit_off", "bundle_tid", "bundle_sample", "pos", "rpos", "mpos", "isize", "flag", "strand", "xs", "qid", "cigar_off", "cigar"]
-    dev = {}
-    for f in fields:
-        a = batch.a[f]
-        v = a.view(np.int64) if a.dtype == np.uint64 else (a.view(np.int32) if a.dtype == np.uint32 else (a.view(np.int16) if a.dtype == np.uint16 else a))
-        dev[f] = torch.from_numpy(v).to("cuda")
-    torch.cuda.synchronize()
-
-    def view_of(tensors):
+    # ---- device-resident timing: inputs already in HBM, a step = (reset + bridge_all) over every device batch ---------------
+    ctxs, bts, devs = [], [], []
+    for part in parts:
+        dev = {f: torch.from_numpy(_tview(part.a[f])).to("cuda") for f in FIELDS}
         b = H.BatchIn()
-        b.n_bundles, b.n_hits, b.n_cigar = batch.n_bundles, batch.n_hits, batch.n_cigar
-        for f in fields:
-            setattr(b, f, tensors[f].data_ptr())
-        return b
+        b.n_bundles, b.n_hits, b.n_cigar = part.n_bundles, part.n_hits, part.n_cigar
+        for f in FIELDS:
+            setattr(b, f, dev[f].data_ptr())
+        c = G.Context(local, stream=stream.cuda_stream)
+        ctxs.append(c)
+        bts.append(c.adopt(b, keepalive=dev))
+        devs.append(dev)
+    torch.cuda.synchronize()
+    ctx, bt = ctxs[0], bts[0]
 
     n_hits = batch.n_hits
-    cig = batch.a["cigar"]
-    ops = cig & 0xF
+    ops = batch.a["cigar"] & 0xF
     n_mblocks = int(np.count_nonzero(ops == 0))
     n_cigar = int(batch.n_cigar)
 
@@ -206,65 +302,82 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: inputs already in HBM, a step = reset + bridge_all -------------------
-    bt = ctx.adopt(view_of(dev), keepalive=dev)
-    counts = None
+    def one_step():
+        for x in bts:
+            x.reset()
+            x.bridge_all(gp)
+
+    def sum_counts():
+        tot = {}
+        for x in bts:
+            for k, v in x.counts().items():
+                tot[k] = tot.get(k, 0) + v
+        return tot
+
     for _ in range(args.warmup):
-        bt.reset()
-        bt.bridge_all(gp)
-    ctx.sync()
-    counts = bt.counts()
-    launches0 = ctx.launches
+        one_step()
+    for c in ctxs:
+        c.sync()
+    launches0 = sum(c.launches for c in ctxs)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        bt.reset()
-        bt.bridge_all(gp)
+        one_step()
     e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1)
-    launches = ctx.launches - launches0
+    launches = sum(c.launches for c in ctxs) - launches0
     # the same K steps again with CUDA events around every kernel launch (per-kernel durations for the roofline; the
     # event records cost ~2% so they stay out of the region `value` is taken from)
-    ctx.profile(True)
-    ctx.profile_reset()
+    for c in ctxs:
+        c.profile(True)
+        c.profile_reset()
     ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ep0.record(stream)
     for _ in range(args.steps):
-        bt.reset()
-        bt.bridge_all(gp)
+        one_step()
     ep1.record(stream)
     barrier()
     ms_prof = ep0.elapsed_time(ep1)
     clk = clocks.stop()
-    prof = ctx.profile_read()
-    ctx.profile(False)
-    counts = bt.counts()
-    per_bundle = bt.bundle_counts()          # [NB, 4]: segments, fragments, clusters, bridged pairs
-    stage5 = stage5_gpu(ctx, bt, batch, args) if not args.no_stage5 else None
-    group_leg = group_bridge_gpu(ctx, bt, gp, stage5_gpu.clusters, args) if stage5 is not None else None
-    phase_leg = phase_set_gpu(ctx, bt, gp, args) if stage5 is not None else None
-    bt.free()
+    prof = {}
+    for c in ctxs:
+        for name, (ms, cnt) in c.profile_read().items():
+            m = prof.setdefault(name, [0.0, 0])
+            m[0] += ms
+            m[1] += cnt
+        c.profile(False)
+    counts = sum_counts()
+    per_bundle = np.concatenate([x.bundle_counts() for x in bts]) if bts else np.zeros((0, 4), np.int64)   # [NB, 4]: segments, fragments, clusters, bridged
+    stage5 = stage5_gpu(ctx, bts, batch, parts, cfg, args) if not args.no_stage5 else None
+    single = len(parts) == 1
+    group_leg = group_bridge_gpu(ctx, bt, gp, stage5_gpu.clusters, args) if (stage5 is not None and single and cfg["mode"] == "paired") else None
+    phase_leg = phase_set_gpu(bts, gp, args) if stage5 is not None else None
+    for x in bts:
+        x.free()
+    for c in ctxs:
+        c.close()
+    del devs, bts, ctxs
 
-    # ---- end to end: pinned host buffers -> upload -> bridge_all -> counters back to the host ----------
-    # the public call: aletsch_b200.pipeline.Pipeline.run over the batch cut into contiguous sub-batches, a few
-    # host threads with one CUDA stream each, so the H2D copy of one sub-batch overlaps the kernels of another
+    # ---- end to end: pinned host buffers -> upload -> bridge_all -> EVERY result structure back in host memory ----------------
+    # the public call: aletsch_b200.pipeline.Pipeline.run over the batch cut into contiguous sub-batches, a few host threads
+    # with one CUDA stream each, so the H2D copy of one sub-batch overlaps the kernels (and the D2H copies) of another
     from aletsch_b200.pipeline import Pipeline
     torch.cuda.synchronize()
-    del dev
     torch.cuda.empty_cache()
-    chunks = batch.split(args.chunks)
+    per_part = max(1, -(-args.chunks // len(parts)))
+    chunks = [ch for part in parts for ch in part.split(per_part)]
     views = []
     h2d_bytes = 0
     for ch in chunks:
         pin = {}
+        ch.a["bundle_strand"] = np.ascontiguousarray(ch.a["strand"][np.minimum(ch.a["bundle_hit_off"][:-1], max(ch.n_hits - 1, 0))])
         if args.upload == "compact":
             # the compact link format (agpu_batch_packed): 16-bit position deltas / mate offsets / insert sizes / CIGAR units
             # with escape lists, decoded on the device into the arrays of the plain upload (include/aletsch_gpu.h)
-            ch.a["bundle_strand"] = np.ascontiguousarray(ch.a["strand"][np.minimum(ch.a["bundle_hit_off"][:-1], max(ch.n_hits - 1, 0))])
             arrays = ch.compact()
             for f, a in arrays.items():
                 v = a.view(np.int64) if a.dtype == np.uint64 else (a.view(np.int16) if a.dtype == np.uint16 else a)
@@ -274,39 +387,38 @@ def run_ours(args):
             continue
         # lean upload: flag[] is never read on the device, rpos[] is re-derived from the CIGAR there, and the strand that all
         # hits of a bundle share goes up once per bundle (agpu_batch_in: rpos / flag / strand may be NULL)
-        ch.a["bundle_strand"] = np.ascontiguousarray(ch.a["strand"][np.minimum(ch.a["bundle_hit_off"][:-1], max(ch.n_hits - 1, 0))])
-        lean = [f for f in fields if f not in ("rpos", "flag", "strand")] + ["bundle_strand"]
+        lean = [f for f in FIELDS if f not in ("rpos", "flag", "strand")] + ["bundle_strand"]
         for f in lean:
-            a = ch.a[f]
-            v = a.view(np.int64) if a.dtype == np.uint64 else (a.view(np.int32) if a.dtype == np.uint32 else (a.view(np.int16) if a.dtype == np.uint16 else a))
-            pin[f] = torch.from_numpy(v).pin_memory()
+            pin[f] = torch.from_numpy(_tview(ch.a[f])).pin_memory()
             h2d_bytes += pin[f].numel() * pin[f].element_size()
         b = H.BatchIn()
         b.n_bundles, b.n_hits, b.n_cigar = ch.n_bundles, ch.n_hits, ch.n_cigar
         for f in lean:
             setattr(b, f, pin[f].data_ptr())
         views.append((b, pin))
+    what = {"full": G.RESULT_ALL, "bundle": G.RESULT_EVIDENCE | G.RESULT_FRAGMENTS, "counts": 0}[args.results]
     pipe = Pipeline(local, n_streams=args.streams, prefetch=not args.no_prefetch)
     for _ in range(min(args.warmup, 2)):
-        pipe.run(views, gp)
+        pipe.run(views, gp, results=what)
     pipe.sync()
     barrier()
     launches_e2e0 = pipe.launches
     syncs_e2e0 = pipe.syncs
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
-    d2h_bytes = 0
-    # all K steps' sub-batches go through the stream pool back to back (every step uploads its inputs again and reads its
-    # counters back; there is no barrier between steps, the K steps are bracketed as a whole)
-    res = pipe.run(views * args.steps, gp)
-    d2h_bytes = 6 * 4 * batch.n_bundles
+    # all K steps' sub-batches go through the stream pool back to back (every step uploads its inputs again and brings its
+    # results back; there is no barrier between steps, the K steps are bracketed as a whole)
+    res = pipe.run(views * args.steps, gp, results=what)
     pipe.sync()
     e3.record(stream)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    d2h_bytes = sum(r["d2h_bytes"] for r in res) / args.steps + 17 * 8 * len(views)     # result views + the counter struct of every sub-batch
     launches_e2e = pipe.launches - launches_e2e0
     syncs_e2e = pipe.syncs - syncs_e2e0
     assert sum(r["hits"] for r in res) == n_hits * args.steps and sum(r["bridged"] for r in res) == counts["bridged"] * args.steps, "pipelined result differs"
+    # one more pass, untimed: how long the reference-side adapter input (graph view) of every sub-batch takes to rebuild is the
+    # host's business (integration/adapter.cc); here only the device -> host part is timed.  Per-view split of the traffic:
     pipe.close()
 
     # max over ranks, totals over ranks
@@ -325,12 +437,12 @@ def run_ours(args):
         # dominant kernel by accumulated device time
         total_k = sum(v[0] for v in prof.values())
         top = sorted(prof.items(), key=lambda kv: -kv[1][0])
-        for name, (ms, cnt) in top[:14]:
-            log("[bench] kernel %-22s %9.3f ms/step  (%d launches/step, %.1f%% of kernel time)" %
+        for name, (ms, cnt) in top[:16]:
+            log("[bench] kernel %-26s %9.3f ms/step  (%d launches/step, %.1f%% of kernel time)" %
                 (name, ms / steps, cnt // steps, 100 * ms / max(total_k, 1e-9)))
         # bridged pairs / time of stage 4 + update = the bridging kernels' accumulated time (rank 0's batch)
         stage4 = ("k_bridge_vertices", "k_piers", "k_cluster_pier", "k_group_cand", "k_bridge_job_counts", "k_bridge_job_fill", "k_bridge_dp",
-                  "k_pier_bridges", "k_vote", "k_vote_type1", "k_vote_type2", "k_update", "k_fcst_insert", "k_merge_entries", "k_scatter_handle")
+                  "k_bridge_dp_warp", "k_pier_bridges", "k_vote", "k_vote_type1", "k_vote_type2", "k_update", "k_fcst_insert", "k_merge_entries", "k_scatter_handle")
         stage4_ms = sum(ms for name, (ms, cnt) in prof.items() if name.replace("(side)", "") in stage4) / steps
         dom = None
         n_splice_pairs = int(np.count_nonzero(ops == 3))
@@ -347,7 +459,7 @@ def run_ours(args):
                 dom = (name, ms, cnt, ab)
                 break
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture of this build (profiles/), if any
-        traffic = {}
+        traffic, tf = {}, []
         try:
             import glob
             tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
@@ -369,24 +481,37 @@ def run_ours(args):
             achieved = ab / launches_per_step / (per_launch_ms / 1e3) / 1e9
             tk = traffic.get("kernels", {}).get(name)
             traffic_per_launch = (tk["dram_read_bytes"] + tk["dram_write_bytes"]) / tk["launches"] if tk else None
+            sb = step_bytes(counts, n_cigar)
+            step_s = ms_dev / steps / 1e3
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     "algorithmic_bytes_per_launch": ab / launches_per_step, "ms_per_launch": per_launch_ms,
                     "launches_per_step": launches_per_step,
                     "share_of_kernel_time": ms / max(total_k, 1e-9), "ms_per_step_profiled": ms_prof / steps, "traffic": traffic_per_launch,
-                    "traffic_source": os.path.basename(tf[-1]) if (tk and tf) else None}
+                    "traffic_source": os.path.basename(tf[-1]) if (tk and tf) else None,
+                    # the whole step against the same peak: sum of the algorithmic bytes of all stages / ms_per_step
+                    "step": {"algorithmic_bytes_survey": sb["survey"], "algorithmic_bytes_layout": sb["layout"],
+                             "achieved_survey": sb["survey"] / step_s / 1e9, "achieved_layout": sb["layout"] / step_s / 1e9,
+                             "frac_survey": sb["survey"] / step_s / 1e9 / peak, "frac_layout": sb["layout"] / step_s / 1e9 / peak,
+                             "note": "survey = SURVEY 8(d) formula with a per-base difference array (8.25 B/base); layout = the same with the "
+                                     "border-compacted coverage map this implementation stores (3 bits/base + 16 B/border)"}}
+        config = reference_config(cfg, args)
+        config.update({"records_per_gpu": n_records, "admitted_hits_per_gpu": n_hits, "bundles_per_gpu": batch.n_bundles,
+                       "device_batches": len(parts),
+                       "l2": "inputs (%.2f GB) and scratch far larger than the 126 MB L2, no flush needed" % (h2d_bytes / 1e9)})
         out = {"metric": "hits_per_sec", "value": value, "unit": "hits/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
                "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-               "data": "synthetic", "impl": "ours",
-               "config": {"workload": "configs[1]: %d synthetic paired_end samples x %d pairs, 1 chromosome of %d bp per GPU, bridging on"
-                          % (SAMPLES, pairs, CHROM_LEN), "generator": "synth-v1 seed %d" % SEED,
-                          "records_per_gpu": n_records, "admitted_hits_per_gpu": n_hits, "bundles_per_gpu": batch.n_bundles,
-                          "l2": "inputs (%.1f GB) and scratch far larger than the 126 MB L2, no flush needed" % (h2d_bytes / 1e9), "scale": args.scale},
+               "data": "synthetic", "impl": "ours", "config": config,
                "bridged_pairs_per_sec": bridged_all * steps / (ms_dev / 1e3), "bridged_pairs_per_step": bridged_all,
                "bridged_pairs_per_sec_stage4": bridged_all / max(stage4_ms / 1e3, 1e-12), "stage4_ms_per_step": stage4_ms,
                "counts": counts, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": "hits/s", "h2d_bytes_per_step": float(tot[2]), "d2h_bytes_per_step": float(tot[3]),
-                       "ms_per_step": ms_e2e / steps, "upload": args.upload, "prefetch": not args.no_prefetch, "stream_drains_per_step": syncs_e2e / steps, "sub_batches": len(views), "streams": args.streams,
+                       "ms_per_step": ms_e2e / steps, "upload": args.upload, "results": args.results,
+                       "results_note": {"full": "agpu_batch_results(ALL): mmap segments, hcst + hit handles, frgs, fcst + fragment handles, splice graphs, "
+                                                "pereads clusters, bridge paths of every bundle in pinned host memory",
+                                        "bundle": "evidence + fragments views only (what bundle::bridge leaves in bundle_base)",
+                                        "counts": "counters only"}[args.results],
+                       "prefetch": not args.no_prefetch, "stream_drains_per_step": syncs_e2e / steps, "sub_batches": len(views), "streams": args.streams,
                        "gpu_launches_per_step": int(launches_e2e // steps)},
                "roofline": roof, "clocks": clk}
         if stage5 is not None:
@@ -396,14 +521,20 @@ def run_ours(args):
         if phase_leg is not None:
             out["phase_set"] = phase_leg
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(batch, min(10, ncpu), args.cpu_seconds, gpu_bridged=per_bundle[:, 3])
+            out["cpu_baseline"] = cpu_baseline(batch, cfg, min(10, ncpu), args.cpu_seconds, gpu_bridged=per_bundle[:, 3])
             if stage5 is not None:
-                out["stage5"]["cpu_baseline"] = stage5_cpu(batch, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
+                out["stage5"]["cpu_baseline"] = stage5_cpu(batch, cfg, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
             if group_leg is not None:
-                out["group_bridge"]["cpu_baseline"] = group_bridge_cpu(batch, stage5_gpu.clusters, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
+                out["group_bridge"]["cpu_baseline"] = group_bridge_cpu(batch, cfg, stage5_gpu.clusters, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
         emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_config(cfg, args):
+    """the `config` keys both arms print (same workload string, generator and seed: the driver compares them)"""
+    return {"workload": workload_string(cfg, args.config), "generator": "synth-v1 seed %d" % cfg["seed"], "scale": cfg["scale_used"],
+            "samples": cfg["samples"], "templates_per_sample_per_gpu": cfg["per_sample"], "chromosomes_per_gpu": cfg["n_chrom"]}
 
 
 REGION = 1_000_000      # region_partition_length (util/parameters.cc:42)
@@ -413,30 +544,49 @@ def region_groups(batch):
     """bundle groups as the reference forms them: all samples' bundles of one (chromosome, 1 Mb region, strand)
     (meta/incubator.cc:312-314, :461-471), members in (sample, bundle) order"""
     a = batch.a
-    first = np.minimum(a["bundle_hit_off"][:-1], max(batch.n_hits - 1, 0))
-    key = (a["bundle_tid"].astype(np.int64) << 40) | ((a["pos"][first].astype(np.int64) // REGION) << 8) | a["strand"][first].astype(np.int64)
+    off = a["bundle_hit_off"]
+    first = np.minimum(off[:-1], max(batch.n_hits - 1, 0))
+    strand = a["strand"][first].astype(np.int64)
+    if batch.n_hits and np.any(strand == ord(".")):
+        # unstranded libraries: the bundle's strand is the majority of its hits' XS tags (bundle_base::compute_strand,
+        # rnacore/bundle_base.cc:206-224); the reference groups '+', '-' and '.' bundles separately
+        cp = np.concatenate([[0], np.cumsum(a["xs"] == ord("+"))])
+        cm = np.concatenate([[0], np.cumsum(a["xs"] == ord("-"))])
+        npl, nmi = cp[off[1:]] - cp[off[:-1]], cm[off[1:]] - cm[off[:-1]]
+        maj = np.where(npl > nmi, ord("+"), np.where(npl < nmi, ord("-"), ord(".")))
+        strand = np.where(strand == ord("."), maj, strand)
+    key = (a["bundle_tid"].astype(np.int64) << 40) | ((a["pos"][first].astype(np.int64) // REGION) << 8) | strand
     order = np.lexsort((np.arange(batch.n_bundles), a["bundle_sample"], key))
     cuts = np.nonzero(np.diff(key[order]))[0] + 1
     return [g for g in np.split(order, cuts) if len(g)]
 
 
-def stage5_gpu(ctx, bt, batch, args):
+def stage5_gpu(ctx, bts, batch, parts, cfg, args):
     """bundle_group::resolve over every region group of the batch: splice signatures compacted on the device, all groups'
-    pair counts in one launch (agpu_group_resolve_batch), size-capped union-find on the host; configs[1]: -c 20 -s 0.2"""
+    pair counts in one launch (agpu_group_resolve_batch), size-capped union-find on the host; -c / -s of the config"""
     stage5_gpu.clusters = []
     import torch
     from aletsch_b200 import gpu as G
-    gp5 = G.default_params(library_type=H.FR_FIRST, max_group_size=20, min_grouping_similarity=0.2)
+    gp5 = G.default_params(library_type=cfg["library_type"], **cfg["group"])
     groups = region_groups(batch)
     order = np.concatenate(groups) if groups else np.zeros(0, np.int64)
     group_off = np.zeros(len(groups) + 1, np.int32)
     np.cumsum([len(g) for g in groups], out=group_off[1:])
     clusters = 0
     t_all = []
-    for it in range(1 + max(1, args.steps)):
+    cl_of = np.zeros(0, np.int32)
+    for it in range(1 + max(1, min(args.steps, 3))):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        off, val = bt.fetch_splices()
+        # the bundles' splice lists from every device batch, in bundle order
+        offs, vals, base = [np.zeros(1, np.int64)], [], 0
+        for x in bts:
+            o, v = x.fetch_splices()
+            offs.append(o[1:] + base)
+            vals.append(v)
+            base += int(o[-1]) if len(o) else 0
+        off = np.concatenate(offs)
+        val = np.concatenate(vals) if vals else np.zeros(0, np.int32)
         loff, lval = G.reorder_lists(off, val, order)
         cl_of, ncl = G.group_resolve_arrays(ctx, group_off, loff, lval, gp5)
         torch.cuda.synchronize()
@@ -454,8 +604,9 @@ def stage5_gpu(ctx, bt, batch, args):
     stage5_gpu.clusters = multi
     dt = float(np.mean(t_all))
     pairs = int(sum(len(g) * (len(g) - 1) // 2 for g in groups))
-    return {"bundle_groups": len(groups), "bundles": int(batch.n_bundles), "pairs": pairs, "clusters": int(clusters), "ms": dt * 1e3,
-            "bundles_per_sec": batch.n_bundles / dt, "pairs_per_sec": pairs / dt, "params": "-c 20 -s 0.2",
+    return {"bundle_groups": len(groups), "bundles": int(batch.n_bundles), "largest_group": int(max((len(g) for g in groups), default=0)),
+            "pairs": pairs, "clusters": int(clusters), "ms": dt * 1e3,
+            "bundles_per_sec": batch.n_bundles / dt, "pairs_per_sec": pairs / dt, "params": cfg["group_str"],
             "timing": "host wall clock around splice fetch + agpu_group_resolve_batch (device pair counts + host union-find), synchronised"}
 
 
@@ -485,49 +636,65 @@ def group_bridge_gpu(ctx, bt, gp, clusters, args):
             "bridged_pairs_added": extra}
 
 
-def phase_set_gpu(ctx, bt, gp, args):
+def phase_set_gpu(bts, gp, args):
     """bundle_base::build_phase_set (rnacore/bundle_base.cc:338-418) for every bundle: graphs rebuilt from the bridged evidence,
     then the phasing paths; device part only (agpu_batch_phase_set ends with a stream synchronisation)"""
     import torch
-    t_all = []
+    t_all, t_rv = [], []
+    n_ph = n_el = n_add = n_mark = 0
     for it in range(1 + max(1, min(args.steps, 3))):
-        bt.reset()
-        bt.bridge_all(gp)
-        bt.graph(gp)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        bt._run("phase_set")
-        torch.cuda.synchronize()
+        dt = drv = 0.0
+        n_ph = n_el = n_add = n_mark = 0
+        for bt in bts:
+            bt.reset()
+            bt.bridge_all(gp)
+            bt.graph(gp)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            bt._run("phase_set")
+            torch.cuda.synchronize()
+            dt += time.perf_counter() - t0
+            # the boundary revision of the same transform(bd, gr, true) call (identify_boundaries + remove_false_boundaries)
+            t0 = time.perf_counter()
+            bt.revise(gp, fetch=False)
+            torch.cuda.synchronize()
+            drv += time.perf_counter() - t0
+            if it == 0:
+                continue
         if it > 0:
-            t_all.append(time.perf_counter() - t0)
-    ph = bt.phase_set()
+            t_all.append(dt)
+            t_rv.append(drv)
+    for bt in bts:
+        ph = bt.phase_set()
+        n_ph += int(sum(len(p["phase_cnt"]) for p in ph))
+        n_el += int(sum(int(p["phase_cnt"].sum()) for p in ph))
+        rv = bt.revise(gp)
+        n_add += int(sum(len(r["rev_edge_d"]) for r in rv))
+        n_mark += int(sum(int((r["rev_vert"] > 0).sum()) for r in rv))
     dt = float(np.mean(t_all))
-    n_ph = int(sum(len(p["phase_cnt"]) for p in ph))
-    n_el = int(sum(int(p["phase_cnt"].sum()) for p in ph))
-    # the boundary revision of the same transform(bd, gr, true) call (identify_boundaries + remove_false_boundaries)
-    t_rv = []
-    for it in range(1 + max(1, min(args.steps, 3))):
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        bt.revise(gp, fetch=False)
-        torch.cuda.synchronize()
-        if it > 0:
-            t_rv.append(time.perf_counter() - t0)
-    rv = bt.revise(gp)
-    return {"ms": dt * 1e3, "distinct_phases": n_ph, "phase_elements": n_el, "phase_elements_per_sec": n_el / dt,
-            "revise_ms": float(np.mean(t_rv)) * 1e3, "revise_edges_added": int(sum(len(r["rev_edge_d"]) for r in rv)),
-            "revise_vertices_marked": int(sum(int((r["rev_vert"] > 0).sum()) for r in rv))}
+    return {"ms": dt * 1e3, "distinct_phases": n_ph, "phase_elements": n_el, "phase_elements_per_sec": n_el / max(dt, 1e-12),
+            "revise_ms": float(np.mean(t_rv)) * 1e3, "revise_edges_added": n_add, "revise_vertices_marked": n_mark}
 
 
-def group_bridge_cpu(batch, clusters, threads, budget_s):
-    """the reference's assembler::bridge on a bounded sample of the same clusters (per-bundle bridging done untimed first)"""
+def _checker_kind():
     import orclib
-    kind = "reference"
     try:
         orclib.Checker("ref")
+        return "reference"
     except (OSError, FileNotFoundError):
-        kind = "port"
-    op = orclib.default_params(library_type=H.FR_FIRST)
+        return "port"
+
+
+def _orc_params(cfg, **kw):
+    import orclib
+    return orclib.default_params(library_type=cfg["library_type"], min_junction_support=cfg.get("min_junction_support", 1), **kw)
+
+
+def group_bridge_cpu(batch, cfg, clusters, threads, budget_s):
+    """the reference's assembler::bridge on a bounded sample of the same clusters (per-bundle bridging done untimed first)"""
+    import orclib
+    kind = _checker_kind()
+    op = _orc_params(cfg)
     sizes = np.diff(batch.a["bundle_hit_off"])
     total = int(sum(int(sizes[k]) for c in clusters for k in c))
     target_hits = int(60_000 * threads * budget_s)
@@ -570,15 +737,11 @@ def group_bridge_cpu(batch, clusters, threads, budget_s):
             "note": "includes copying the checker's result arrays out (chk.group_bridge dumps the combined bundle and every member)"}
 
 
-def stage5_cpu(batch, threads, budget_s):
+def stage5_cpu(batch, cfg, threads, budget_s):
     """the reference's bundle_group::resolve on a bounded sample of the same region groups (bundle objects built untimed)"""
     import orclib
-    kind = "reference"
-    try:
-        orclib.Checker("ref")
-    except (OSError, FileNotFoundError):
-        kind = "port"
-    op = orclib.default_params(library_type=H.FR_FIRST, max_group_size=20, min_grouping_similarity=0.2)
+    kind = _checker_kind()
+    op = _orc_params(cfg, **cfg["group"])
     groups = region_groups(batch)
     sizes = np.diff(batch.a["bundle_hit_off"])
     target_hits = int(60_000 * threads * budget_s)          # building the bundle objects dominates; bound that
@@ -626,20 +789,98 @@ def stage5_cpu(batch, threads, budget_s):
             "bundles_per_sec": nbun / max(wall, 1e-9), "pairs_per_sec": pairs / max(wall, 1e-9)}
 
 
-def cpu_baseline(batch, threads, budget_s, all_cores=False, gpu_bridged=None):
-    """the reference's own C++ (oracle/_ref) over a bounded sample of the same bundles, one bundle per task
-    on a pool of `threads` workers (the granularity of aletsch -t N, meta/incubator.cc:615-635)"""
+class RefTimer:
+    """oracle/_ref's timing entry (ref_driver.cc: ref_timing_*): a bounded sample of the batch's bundles; the BAM records and the
+    `hit` objects are built once, BEFORE any clock; every pass then runs add_hit_intervals + build_fragments + the reference's own
+    bundle::bridge() per bundle on a pool of `threads` workers (one bundle per task, like aletsch -t N) with no checker dumps."""
+
+    def __init__(self, batch, cfg, threads, budget_s, rate=150_000, calibrate=True):
+        self._build(batch, cfg, threads, budget_s, rate)
+        if calibrate and self.step > 1:
+            # the hits/s per core depend on the depth of the bundles: one untimed pass, then resize the sample once so that a
+            # pass lasts about `budget_s`
+            sec, _ = self.run()
+            if sec < 0.7 * budget_s or sec > 1.5 * budget_s:
+                measured = self.hits / max(sec, 1e-6) / threads
+                self.close()
+                self._build(batch, cfg, threads, budget_s, measured)
+
+    def _build(self, batch, cfg, threads, budget_s, rate):
+        import orclib
+        self.lib = L = C.CDLL(orclib.REF_SO)
+        L.ref_timing_new.restype = C.c_void_p
+        L.ref_timing_new.argtypes = [C.c_int, C.c_void_p, C.POINTER(orclib.Params)]
+        L.ref_timing_free.argtypes = [C.c_void_p]
+        L.ref_timing_hits.restype = C.c_int64
+        L.ref_timing_hits.argtypes = [C.c_void_p]
+        L.ref_timing_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p]
+        self.threads = threads
+        sizes = np.diff(batch.a["bundle_hit_off"])
+        # bounded sample: every k-th bundle until the estimated work of ONE pass fits the budget (~`rate` hits/s per core)
+        target_hits = int(rate * threads * budget_s)
+        self.step = max(1, int(np.ceil(sizes.sum() / max(target_hits, 1))))
+        self.sample = list(range(0, batch.n_bundles, self.step))
+        n = len(self.sample)
+        arr = (orclib.BundleIn * max(n, 1))()
+        self.keep = []
+        for j, k in enumerate(self.sample):
+            bd = batch.bundle(k)
+            arr[j].n_hits = len(bd["pos"])
+            arr[j].tid = bd["tid"]
+            for f in ("pos", "mpos", "isize", "flag", "strand", "xs", "qid", "cigar_off", "cigar"):
+                a = np.ascontiguousarray(bd[f])
+                self.keep.append(a)
+                setattr(arr[j], f, a.ctypes.data)
+        op = _orc_params(cfg)
+        self.h = L.ref_timing_new(n, C.cast(arr, C.c_void_p), C.byref(op))
+        self.keep = None          # the handle owns its records and hits now
+        self.hits = int(L.ref_timing_hits(self.h))
+        self.per = np.zeros(max(n, 1), np.int32)
+
+    def run(self):
+        sec, br = C.c_double(0), C.c_int64(0)
+        self.lib.ref_timing_run(self.h, self.threads, C.byref(sec), C.byref(br), self.per.ctypes.data)
+        return sec.value, int(br.value)
+
+    def describe(self, sec):
+        return "every %d-th bundle of the same batch: %d bundles, %d hits, %.2f s per pass" % (self.step, len(self.sample), self.hits, sec)
+
+    def close(self):
+        if self.h:
+            self.lib.ref_timing_free(self.h)
+            self.h = None
+
+
+def cpu_baseline(batch, cfg, threads, budget_s, gpu_bridged=None):
+    """the reference's own C++ (oracle/_ref) over a bounded sample of the same bundles (RefTimer), one untimed warm-up pass and
+    then passes until the budget is used; the restatement (oracle/liboracle.so, kind "port") only if the reference build is absent"""
+    if _checker_kind() != "reference":
+        return cpu_baseline_port(batch, cfg, threads, budget_s, gpu_bridged)
+    rt = RefTimer(batch, cfg, threads, max(2.0, budget_s / 3))
+    rt.run()
+    secs, bridged = [], 0
+    t_end = time.time() + budget_s
+    while not secs or (time.time() < t_end and len(secs) < 5):
+        s_, bridged = rt.run()
+        secs.append(s_)
+    sec = float(np.mean(secs))
+    out = {"value": rt.hits / sec, "unit": "hits/s", "cores": threads, "kind": "reference",
+           "sample": rt.describe(sec), "passes": len(secs), "spread": float((max(secs) - min(secs)) / sec),
+           "timed": "add_hit_intervals + build_fragments + bundle::bridge() per bundle (ref_timing_run); records and hit objects built before the clock, no dumps",
+           "bridged_pairs_per_sec": bridged / sec}
+    if gpu_bridged is not None:
+        # full-size cross-check: the bridged-pair count of every sampled bundle, CUDA path vs this CPU run
+        bad = [int(k) for k, c in zip(rt.sample, rt.per) if int(gpu_bridged[k]) != int(c)]
+        out["bridged_count_check"] = {"bundles": len(rt.sample), "mismatches": len(bad), "first": bad[:5]}
+    rt.close()
+    return out
+
+
+def cpu_baseline_port(batch, cfg, threads, budget_s, gpu_bridged=None):
+    """fallback when oracle/_ref is absent: the CPU restatement through the checker interface (includes its result dumps)"""
     import orclib
-    kind = "reference"
-    try:
-        chk0 = orclib.Checker("ref")
-    except (OSError, FileNotFoundError):
-        chk0 = orclib.Checker("orc")
-        kind = "port"
-    del chk0
-    op = orclib.default_params(library_type=H.FR_FIRST)
+    op = _orc_params(cfg)
     sizes = np.diff(batch.a["bundle_hit_off"])
-    # bounded sample: every k-th bundle until the estimated work fits the budget (~60k hits/s per core)
     target_hits = int(60_000 * threads * budget_s)
     step = max(1, int(np.ceil(sizes.sum() / max(target_hits, 1))))
     sample = list(range(0, batch.n_bundles, step))
@@ -647,11 +888,10 @@ def cpu_baseline(batch, threads, budget_s, all_cores=False, gpu_bridged=None):
     hits = int(sum(len(b["pos"]) for b in bundles))
     lock = threading.Lock()
     nxt = [0]
-    bridged = [0]
     per = [0] * len(bundles)
 
     def worker():
-        chk = orclib.Checker("ref" if kind == "reference" else "orc")
+        chk = orclib.Checker("orc")
         while True:
             with lock:
                 i = nxt[0]
@@ -660,11 +900,8 @@ def cpu_baseline(batch, threads, budget_s, all_cores=False, gpu_bridged=None):
                 return
             h = chk.new_bundle(bundles[i], op)
             chk.run_quiet(h, "fragments")
-            c = chk.run_quiet(h, "bridge")
+            per[i] = max(chk.run_quiet(h, "bridge"), 0)
             chk.free_bundle(h)
-            per[i] = max(c, 0)
-            with lock:
-                bridged[0] += max(c, 0)
 
     t0 = time.time()
     ths = [threading.Thread(target=worker) for _ in range(threads)]
@@ -673,42 +910,51 @@ def cpu_baseline(batch, threads, budget_s, all_cores=False, gpu_bridged=None):
     for t in ths:
         t.join()
     dt = time.time() - t0
-    out = {"value": hits / dt, "unit": "hits/s", "cores": threads, "kind": kind,
+    out = {"value": hits / dt, "unit": "hits/s", "cores": threads, "kind": "port",
            "sample": "every %d-th bundle of the same batch: %d bundles, %d hits, %.1f s wall" % (step, len(bundles), hits, dt),
-           "bridged_pairs_per_sec": bridged[0] / dt}
+           "bridged_pairs_per_sec": sum(per) / dt}
     if gpu_bridged is not None:
-        # full-size cross-check: the bridged-pair count of every sampled bundle, CUDA path vs this CPU run
         bad = [int(k) for k, c in zip(sample, per) if int(gpu_bridged[k]) != int(c)]
         out["bridged_count_check"] = {"bundles": len(sample), "mismatches": len(bad), "first": bad[:5]}
     return out
 
 
 def run_reference(args):
-    """reference arm: the reference's own CPU implementation of the path on all host cores"""
+    """reference arm: the reference's own CPU implementation of the path on all host cores.  A step = one pass of
+    ref_timing_run over a bounded sample of the workload's bundles sized for >= ~2 s of wall time; the sample is built once."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     ncpu = os.cpu_count() or 8
-    batch, n_records, pairs = build_workload(0, args.scale, ncpu)
-    per_step = max(2.0, args.cpu_seconds / max(1, args.steps + args.warmup))
-    vals = []
-    last = None
-    for i in range(args.warmup + args.steps):
-        r = cpu_baseline(batch, ncpu, per_step)
-        if i >= args.warmup:
-            vals.append(r)
-        last = r
-    value = float(np.mean([v["value"] for v in vals]))
-    bps = float(np.mean([v["bridged_pairs_per_sec"] for v in vals]))
-    hits_sample = float(last["sample"].split("bundles, ")[1].split(" hits")[0])
+    cfg = config_of(args)
+    batch, n_records = build_workload(cfg, 0, ncpu)
+    if _checker_kind() != "reference":
+        r = cpu_baseline_port(batch, cfg, ncpu, max(2.0, args.cpu_seconds))
+        vals, secs, hits_sample, kind, sample, bps = [r["value"]], [0.0], 0, "port", r["sample"], r["bridged_pairs_per_sec"]
+    else:
+        per_step = max(2.5, args.cpu_seconds / max(1, args.steps + args.warmup))
+        rt = RefTimer(batch, cfg, ncpu, per_step)
+        secs, br = [], 0
+        for i in range(args.warmup + args.steps):
+            s_, br = rt.run()
+            if i >= args.warmup:
+                secs.append(s_)
+        hits_sample, kind = rt.hits, "reference"
+        vals = [hits_sample / s_ for s_ in secs]
+        sample = rt.describe(float(np.mean(secs)))
+        bps = br / float(np.mean(secs))
+        rt.close()
+    value = float(np.mean(vals))
+    config = reference_config(cfg, args)
     out = {"metric": "hits_per_sec", "value": value, "unit": "hits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * hits_sample / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-           "data": "synthetic", "impl": "reference",
-           "config": {"workload": "configs[1]: %d synthetic paired_end samples x %d pairs, 1 chromosome of %d bp per GPU, bridging on"
-                      % (SAMPLES, pairs, CHROM_LEN), "generator": "synth-v1 seed %d" % SEED, "scale": args.scale},
+           "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+           "data": "synthetic", "impl": "reference", "config": config,
            "bridged_pairs_per_sec": bps,
-           "cpu_baseline": {"value": value, "unit": "hits/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+           "ranks": "rank 0 only: one CPU pool of %d threads whatever N is (the GPU arm's value is the sum over N GPUs)" % ncpu,
+           "spread": float((max(vals) - min(vals)) / value) if vals else 0.0,
+           "cpu_baseline": {"value": value, "unit": "hits/s", "cores": ncpu, "kind": kind, "sample": sample,
+                            "timed": "add_hit_intervals + build_fragments + bundle::bridge() per bundle; records and hit objects built before the clock, no dumps"},
            "e2e": {"value": value, "unit": "hits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 
@@ -739,7 +985,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 5M pairs per sample (development only; 1.0 = the named config)")
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="index into BASELINE.json configs (default 1: the config the metric is quoted on)")
+    ap.add_argument("--scale", type=float, default=None, help="fraction of the config's templates per sample (default: the config's own, 1.0 except configs[2])")
+    ap.add_argument("--results", choices=["full", "bundle", "counts"], default="full",
+                    help="what the end-to-end leg brings back to host memory per sub-batch (default: every result structure)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage5", action="store_true", help="skip the bundle_group::resolve (stage 5) leg")

@@ -286,6 +286,30 @@ int agpu_graph_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_graph_view *v);
 int agpu_cluster_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_cluster_view *v);
 int agpu_bridge_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_bridge_view *v);
 
+/* Everything bundle::bridge leaves behind (meta/bundle.cc:55-88), in one call: the bundle_base members it updates (mmap, hcst,
+ * frgs, fcst: evidence + fragments views) and its locals (splice_graph gr, vector<pereads_cluster> vc, bridge_solver::opt:
+ * graph, cluster and bridge views), packed on the device and copied into the context's pinned buffers.  `what` selects the
+ * views; `bytes` returns the device -> host bytes this call copied.  The views stay valid until the next fetch of the same
+ * kind on this context. */
+#define AGPU_RESULT_EVIDENCE  1u
+#define AGPU_RESULT_FRAGMENTS 2u
+#define AGPU_RESULT_GRAPH     4u
+#define AGPU_RESULT_CLUSTERS  8u
+#define AGPU_RESULT_BRIDGES  16u
+#define AGPU_RESULT_ALL      31u
+typedef struct agpu_results
+{
+	agpu_evidence_view evidence;
+	agpu_fragments_view fragments;
+	agpu_graph_view graph;
+	agpu_cluster_view clusters;
+	agpu_bridge_view bridges;
+	int64_t bytes;
+} agpu_results;
+int agpu_batch_results(agpu_ctx *ctx, agpu_batch *b, uint32_t what, agpu_results *out);
+/* device -> host bytes the fetches of this context have copied so far */
+int64_t agpu_d2h_bytes(agpu_ctx *ctx);
+
 /* counters of the batch (host copies, synchronises): hits, cigar ops, coverage span L,
  * segments S, chains, junctions J, vertices V, edges E, fragments F, clusters C, bridged pairs */
 typedef struct agpu_counts

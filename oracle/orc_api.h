@@ -121,6 +121,14 @@ int orc_bundle_set_sample(void *b, int sample_id);
 int orc_group_support(void **bs, int n, void *bag);
 int ref_generate_regions(const orc_records_in *in, const orc_params *prm, int use_second_alignment, int region_length, void *bag);
 
+/* reference build only -- timing entry for bench.py (cpu_baseline, --impl reference): records and hit objects are built by
+ * ref_timing_new before any clock starts; ref_timing_run times add_hit_intervals + build_fragments + bundle::bridge() per bundle
+ * on `threads` workers, no result dumps (see ref_driver.cc) */
+void *ref_timing_new(int n_bundles, const orc_bundle_in *ins, const orc_params *prm);
+void ref_timing_free(void *t);
+int64_t ref_timing_hits(void *t);
+int ref_timing_run(void *t, int threads, double *seconds, int64_t *bridged, int32_t *per_bundle_bridged);
+
 ORC_DECLARE(ref)
 ORC_DECLARE(orc)
 

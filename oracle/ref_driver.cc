@@ -29,7 +29,10 @@
 #include "phase_set.h"
 #include "sample_profile.h"
 
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <thread>
 #include <set>
 #include <unordered_map>
 #include <mutex>
@@ -332,6 +335,111 @@ void *ref_bundle_new(const orc_bundle_in *in, const orc_params *prm)
 }
 
 void ref_bundle_free(void *b) { delete (ref_handle*)b; }
+
+
+// ---- timing entry (bench.py --impl reference, cpu_baseline): the reference's own bundle path with nothing of the checker in
+// the timed region.  ref_timing_new fabricates the BAM records and constructs the `hit` objects (hit::hit + set_tags + the
+// generator's strand fix-up) BEFORE any clock starts -- the GPU arm starts from packed hits too.  ref_timing_run then does, per
+// bundle and on a pool of `threads` workers (one bundle per task, the granularity of aletsch -t N, meta/incubator.cc:615-635):
+// add_hit_intervals per hit + the end of generator::generate (meta/generator.cc:203-227) + build_fragments + the reference's
+// own bundle::bridge() (meta/bundle.cc:55-88), on a fresh bundle object, and returns the wall time of the pool.
+struct ref_timing_bundle
+{
+	std::vector<hts_shim_record> recs;
+	std::vector<hit> hits;
+};
+struct ref_timing
+{
+	parameters cfg;
+	sample_profile sp;
+	std::vector<ref_timing_bundle> bundles;
+	ref_timing() : sp(0, 1000000) {}
+};
+
+void *ref_timing_new(int n_bundles, const orc_bundle_in *ins, const orc_params *prm)
+{
+	ref_timing *t = new ref_timing;
+	apply_params(prm, t->cfg, t->sp);
+	t->bundles.resize(n_bundles);
+	for(int k = 0; k < n_bundles; k++)
+	{
+		const orc_bundle_in *in = ins + k;
+		ref_timing_bundle &tb = t->bundles[k];
+		tb.recs.reserve(in->n_hits);
+		tb.hits.reserve(in->n_hits);
+		for(int i = 0; i < in->n_hits; i++)
+		{
+			uint32_t c0 = in->cigar_off[i], c1 = in->cigar_off[i + 1];
+			tb.recs.push_back(hts_shim_make_record(in->tid, in->pos[i], 60, in->flag[i], in->tid, in->mpos[i], in->isize[i],
+					qname_of(in->qid[i]), in->cigar + c0, c1 - c0, (char)in->xs[i], '.', 1, 1, -1));
+		}
+		for(int i = 0; i < in->n_hits; i++)
+		{
+			bam1_t b1t;
+			hts_shim_view(tb.recs[i], &b1t);
+			hit ht(&b1t, i);
+			ht.set_tags(&b1t);
+			ht.strand = (char)in->strand[i];
+			tb.hits.push_back(ht);
+		}
+	}
+	return t;
+}
+
+void ref_timing_free(void *t) { delete (ref_timing*)t; }
+
+int64_t ref_timing_hits(void *tp)
+{
+	ref_timing *t = (ref_timing*)tp;
+	int64_t n = 0;
+	for(size_t k = 0; k < t->bundles.size(); k++) n += (int64_t)t->bundles[k].hits.size();
+	return n;
+}
+
+// one pass over all bundles; per_bundle_bridged (may be NULL) receives the number of bridged fragments of every bundle
+// (frgs of type 1 / 2 after bundle::bridge, i.e. the sum of the update_bridges return values)
+int ref_timing_run(void *tp, int threads, double *seconds, int64_t *bridged, int32_t *per_bundle_bridged)
+{
+	ref_timing *t = (ref_timing*)tp;
+	const int n = (int)t->bundles.size();
+	if(threads < 1) threads = 1;
+	std::atomic<int> next(0);
+	std::atomic<long long> total(0);
+	auto work = [&]()
+	{
+		while(true)
+		{
+			int k = next.fetch_add(1);
+			if(k >= n) return;
+			ref_timing_bundle &tb = t->bundles[k];
+			bundle bd(t->cfg, t->sp);
+			bam1_t b1t;
+			for(size_t i = 0; i < tb.hits.size(); i++)
+			{
+				hts_shim_view(tb.recs[i], &b1t);
+				bd.add_hit_intervals(tb.hits[i], &b1t);
+			}
+			bd.add_buf_intervals();
+			bd.splices = bd.hcst.get_splices();
+			bd.chrm = "chr";
+			bd.compute_strand(t->sp.library_type);
+			bd.build_fragments();
+			bd.bridge();
+			int cnt = 0;
+			for(size_t f = 0; f < bd.frgs.size(); f++) if(bd.frgs[f][2] == 1 || bd.frgs[f][2] == 2) cnt++;
+			if(per_bundle_bridged) per_bundle_bridged[k] = cnt;
+			total += cnt;
+		}
+	};
+	auto t0 = std::chrono::steady_clock::now();
+	std::vector<std::thread> pool;
+	for(int i = 0; i < threads; i++) pool.push_back(std::thread(work));
+	for(size_t i = 0; i < pool.size(); i++) pool[i].join();
+	auto t1 = std::chrono::steady_clock::now();
+	if(seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+	if(bridged) *bridged = total.load();
+	return 0;
+}
 
 int ref_bundle_evidence(void *b, void *bag)
 {

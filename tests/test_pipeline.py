@@ -40,9 +40,13 @@ def run_variants(lib_path, n_threads, device=0):
         for prefetch in (False, True):
             pipe = Pipeline(device, n_streams=n_threads, lib_path=lib_path, prefetch=prefetch)
             for rep in range(2):
-                res = pipe.run(views * 2, gp)
+                res = pipe.run(views * 2, gp, results=G.RESULT_ALL if rep else 0)
                 for k in keys:
                     assert sum(r[k] for r in res) == 2 * whole[k], (compact, prefetch, rep, k)
+                # rep 1 brings every structure bundle::bridge leaves behind back to the host: at least the fragments (12 B each)
+                # and the hit -> chain handles (4 B per hit) have to show up in the byte count
+                d2h = sum(r["d2h_bytes"] for r in res)
+                assert (d2h >= 2 * (12 * whole["fragments"] + 4 * whole["hits"])) if rep else d2h == 0, (compact, prefetch, rep, d2h)
             pipe.close()
 
 

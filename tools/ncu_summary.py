@@ -9,7 +9,16 @@ import sys
 COLS = [("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs"),
         ("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "DRAM read"), ("dram__bytes_write.sum", "DRAM write"),
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %peak"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %peak"),
-        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"), ("lts__t_sector_hit_rate.pct", "L2 hit %")]
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+        # the counters BASELINE.json's north_star names: shared-memory bank conflicts, sectors per global request (32 B sectors:
+        # 4 = fully coalesced 128 B per warp request for 4-byte loads), achieved occupancy
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "smem conflicts ld"),
+        ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "smem conflicts st"),
+        ("l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio", "sectors/req ld"),
+        ("l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_st.ratio", "sectors/req st"),
+        ("sm__maximum_warps_per_active_cycle_pct", "theoretical occ %"),
+        ("smsp__cycles_active.avg", "SMSP active cycles")]
 SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
 
 
