@@ -229,6 +229,18 @@ static int check_err(agpu_ctx *ctx, agpu_batch *b, const char *stage)
 	return AGPU_OK;
 }
 
+// device-wide exclusive prefix sums, one launch each (lookback.h): out[i] = sum of v[0..i), out[n] = total
+static int lb_scan32(agpu_ctx *ctx, const int32_t *v, int64_t n, int mode, int64_t *out)
+{
+	LAUNCH_LB(ctx, k_lb_scan_i32, (n + 1 + LB_TILE - 1) / LB_TILE, v, n, mode, out);
+	return AGPU_OK;
+}
+static int lb_scan64(agpu_ctx *ctx, const int64_t *v, int64_t n, int64_t *out)
+{
+	LAUNCH_LB(ctx, k_lb_scan_i64, (n + 1 + LB_TILE - 1) / LB_TILE, v, n, out);
+	return AGPU_OK;
+}
+
 template<typename T> static int pull(agpu_ctx *ctx, agpu_batch *b, const std::string &name, const T *dev, size_t n, T **out)
 {
 	T *h = b->host<T>(name, n);
@@ -327,6 +339,7 @@ void agpu_destroy(agpu_ctx *ctx)
 #endif
 	pinned_free(ctx->stage_pin);
 	for(auto &r : ctx->pinned) r.second.release();
+	lb_destroy(ctx);
 	delete ctx;
 }
 
@@ -633,7 +646,7 @@ static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int6
 		dbuf<int64_t> sz;
 		TRY(sz.alloc(ctx, nb + 1));
 		LAUNCH_T(ctx, k_table_sizes, nb, nb, d_count, sz.p);
-		LAUNCH_B(ctx, k_scan_i64, 1, 1024, sz.p, cs.reg_off.p, nb);
+		TRY(lb_scan64(ctx, sz.p, nb, cs.reg_off.p));
 		TRY(d2h(ctx, &cs.n_slots, cs.reg_off.p + nb, sizeof(int64_t)));
 		TRY(stream_sync(ctx));
 		sz.release(ctx);
@@ -643,7 +656,7 @@ static int chainset_build(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int6
 		dbuf<int64_t> sz;
 		TRY(sz.alloc(ctx, nb + 1));
 		LAUNCH_T(ctx, k_table_sizes_off, nb, nb, d_elem_off, sz.p);
-		LAUNCH_B(ctx, k_scan_i64, 1, 1024, sz.p, cs.reg_off.p, nb);
+		TRY(lb_scan64(ctx, sz.p, nb, cs.reg_off.p));
 		cs.n_slots = 4 * n_elem + 2 * (int64_t)nb;
 		DEBUG_SYNC(16);
 		sz.release(ctx);
@@ -681,7 +694,7 @@ static int value_scan(agpu_ctx *ctx, const int32_t *v, int64_t n, dbuf<int32_t> 
 static int tile_scan(agpu_ctx *ctx, dbuf<int32_t> &tile_sum, dbuf<int64_t> &tile_off, int64_t nt)
 {
 	TRY(tile_off.alloc(ctx, nt + 2));
-	LAUNCH_B(ctx, k_scan_i32_to_i64, 1, 1024, tile_sum.p, tile_off.p, nt);
+	TRY(lb_scan32(ctx, tile_sum.p, nt, 0, tile_off.p));
 	return AGPU_OK;
 }
 
@@ -692,18 +705,14 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 	TRY(b->seg_off.alloc(ctx, nb + 2, true));
 	b->n_seg = 0; b->n_bord = 0;
 	const int64_t nw = b->ltot / 32;
-	dbuf<int32_t> ts;
-	dbuf<int64_t> to;
+	dbuf<int64_t> tot;
+	TRY(tot.alloc(ctx, 4, true));
 	if(nw > 0)
 	{
-		// rank the borders
-		int64_t nt = (nw + 1 + CTILE - 1) / CTILE;
-		TRY(ts.alloc(ctx, nt + 1));
+		// rank the borders: one look-back pass over the bitmap words
 		TRY(b->wrank.alloc(ctx, nw + 2));
-		LAUNCH_B(ctx, k_bord_tile_sum, nt, 256, b->border.p, nw, nt, ts.p);
-		TRY(tile_scan(ctx, ts, to, nt));
-		LAUNCH_B(ctx, k_bord_tile_rank, nt, 256, b->border.p, nw, nt, to.p, b->wrank.p);
-		TRY(d2h(ctx, &b->n_bord, to.p + nt, sizeof(int64_t)));
+		LAUNCH_LB(ctx, k_lb_bord_rank, (nw + 1 + LB_TILE - 1) / LB_TILE, b->border.p, nw, b->wrank.p, tot.p);
+		TRY(d2h(ctx, &b->n_bord, tot.p, sizeof(int64_t)));
 		TRY(stream_sync(ctx));
 	}
 	const int64_t n = b->n_bord;
@@ -717,37 +726,29 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		LAUNCH_T(ctx, k_cov_add, b->nh, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);
-		// coverage = prefix sum of the differences; segments = borders with positive coverage
-		int64_t nt = (n + CTILE - 1) / CTILE;
-		dbuf<int32_t> tc;
-		dbuf<int64_t> tco;
-		TRY(ts.alloc(ctx, nt + 1)); TRY(tc.alloc(ctx, nt + 1));
-		LAUNCH_B(ctx, k_covc_tile_sum, nt, 256, b->diffc.p, n, nt, ts.p);
-		TRY(tile_scan(ctx, ts, to, nt));
-		LAUNCH_B(ctx, k_covc_tile_cover, nt, 256, b->diffc.p, n, nt, to.p, b->covc.p, tc.p);
-		TRY(tile_scan(ctx, tc, tco, nt));
-		dbuf<int32_t> s_head, s_prod;
-		TRY(s_head.alloc(ctx, n + 1)); TRY(s_prod.alloc(ctx, n + 1));
-		LAUNCH_B(ctx, k_covc_emit, nt, 256, b->covc.p, b->posc.p, n, nt, tco.p, nb, b->bord_off.p, b->seg_l.p, b->seg_r.p, b->seg_c.p, b->seg_off.p,
-				s_head.p, s_prod.p);
-		TRY(d2h(ctx, &b->n_seg, tco.p + nt, sizeof(int64_t)));
+		// coverage = prefix sum of the differences; segments = borders with positive coverage; prefix sums of len * cov:
+		// one launch, three chained look-backs
+		dbuf<int32_t> s_head;
+		TRY(s_head.alloc(ctx, n + 1)); TRY(b->seg_psum.alloc(ctx, n + 2));
+		LAUNCH_LB(ctx, k_lb_cov_segments, (n + 1 + LB_TILE - 1) / LB_TILE, b->diffc.p, b->posc.p, n, nb, b->bord_off.p, b->covc.p,
+				b->seg_l.p, b->seg_r.p, b->seg_c.p, b->seg_off.p, s_head.p, b->seg_psum.p, tot.p + 1);
+		TRY(d2h(ctx, &b->n_seg, tot.p + 1, sizeof(int64_t)));
 		TRY(stream_sync(ctx));
-		tc.release(ctx); tco.release(ctx);
-		// side tables of the segment list for the region walk of graph_builder (k_graph.h)
+		// run structure of the segment list for the region walk of graph_builder (k_graph.h)
 		{
 			const int64_t ns = b->n_seg;
 			dbuf<int32_t> t1;
 			dbuf<int64_t> t2, hrank, heads;
 			TRY(flag_rank(ctx, s_head.p, ns, t1, t2, hrank, NULL));
-			TRY(value_scan(ctx, s_prod.p, ns, t1, t2, b->seg_psum, NULL));
 			TRY(heads.alloc(ctx, ns + 2)); TRY(b->seg_nhead.alloc(ctx, ns + 2));
 			LAUNCH_T(ctx, k_seg_heads, ns + 1, ns, s_head.p, hrank.p, heads.p);
 			LAUNCH_T(ctx, k_seg_nhead, ns, ns, hrank.p, heads.p, b->seg_nhead.p);
-			t1.release(ctx); t2.release(ctx); hrank.release(ctx); heads.release(ctx);
+			hrank.release(ctx); heads.release(ctx);
 		}
-		s_head.release(ctx); s_prod.release(ctx);
+		s_head.release(ctx);
 	}
-	ts.release(ctx); to.release(ctx);
+	else TRY(b->seg_psum.alloc(ctx, 2, true));
+	tot.release(ctx);
 	b->cov_dirty = false;
 	return AGPU_OK;
 }
@@ -765,7 +766,7 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(b->hit_bundle.alloc(ctx, nh + 1));
 	LAUNCH_B(ctx, k_bundle_bounds, nb, 128, b->h, p->library_type, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, b->b_strand.p, b->b_span.p,
 			b->hit_bundle.p, b->err.p);
-	LAUNCH_B(ctx, k_scan_i64, 1, 1024, b->b_span.p, b->cov_base.p, nb);
+	TRY(lb_scan64(ctx, b->b_span.p, nb, b->cov_base.p));
 	b->ltot = 0;
 	TRY(d2h(ctx, &b->ltot, b->cov_base.p + nb, sizeof(int64_t)));
 	TRY(stream_sync(ctx));
@@ -810,7 +811,7 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	LAUNCH_B(ctx, k_graph_bounds, nb, 128, in, gs.ub[0].p, gs.ub[1].p, gs.ub[2].p, gs.ub[3].p, gs.ub[4].p);
 	for(int k = 0; k < 5; k++)
 	{
-		LAUNCH_B(ctx, k_scan_i64, 1, 1024, gs.ub[k].p, gs.off[k].p, nb);
+		TRY(lb_scan64(ctx, gs.ub[k].p, nb, gs.off[k].p));
 		TRY(d2h(ctx, &gs.tot[k], gs.off[k].p + nb, sizeof(int64_t)));
 	}
 	TRY(stream_sync(ctx));

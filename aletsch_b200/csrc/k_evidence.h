@@ -14,6 +14,7 @@
 
 #include "dev.h"
 #include "blockops.h"
+#include "lookback.h"
 
 namespace agpu {
 
@@ -731,6 +732,109 @@ KERNEL k_seg_nhead(int64_t n, const int64_t *hrank, const int64_t *heads, int64_
 	nhead[i] = heads[hrank[i + 1]];
 }
 
+// ---- single-pass versions (decoupled look-back, lookback.h) of the coverage scans ------------------------------------------
+
+// wrank[w] = number of borders before bitmap word w (wrank[n_words] = total); *total gets the number of borders
+KERNEL k_lb_bord_rank(lb_ctl c, const u32 *border, int64_t n_words, u32 *wrank, int64_t *total)
+{
+	SHARED int f[LB_TILE];
+	const int64_t n_tiles = (n_words + 1 + LB_TILE - 1) / LB_TILE;
+	for(int64_t t = lb_next_tile(c, n_tiles); t >= 0; t = lb_next_tile(c, n_tiles))
+	{
+		const int64_t g0 = t * LB_TILE;
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x)
+		{
+			const int64_t w = g0 + i;
+			f[i] = w < n_words ? __popc(border[w]) : 0;
+		}
+		BLOCK_SYNC();
+		const int tot = block_excl_scan(f, LB_TILE);
+		const int64_t pre = lb_tile_prefix(c, 0, t, tot);
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x)
+		{
+			const int64_t w = g0 + i;
+			if(w <= n_words) wrank[w] = (u32)(pre + f[i]);
+			if(w == n_words) *total = pre + f[i];
+		}
+	}
+}
+
+// differences -> coverage -> segments, one launch.  Three chained look-backs per tile of borders:
+//   chain 0: sum of the differences        -> cov[i] = coverage right of border i
+//   chain 1: number of borders with cov > 0 -> position of every segment in the compact list
+//   chain 2: sum of the products (r - l) * c of the tile's segments, int32 wrap-around arithmetic -> seg_psum
+// Outputs as k_covc_emit: seg_l / seg_r / seg_c, seg_head (0 = opens a run, -1 = touches its predecessor), seg_psum[o] = sum of
+// the products of the segments before o (seg_psum[n_seg] = total), seg_off[b] per bundle, *n_seg.
+KERNEL k_lb_cov_segments(lb_ctl c, const int32_t *diffc, const int32_t *posc, int64_t n, int32_t n_bundles, const int64_t *bord_off,
+		int32_t *cov, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c, int64_t *seg_off, int32_t *seg_head, int64_t *seg_psum, int64_t *n_seg)
+{
+	SHARED int f[LB_TILE + 1];       // local prefix of the differences, then of the segment flags
+	SHARED int cv[LB_TILE + 1];      // coverage of the tile's borders; cv[LB_TILE]: coverage of the border before the tile
+	SHARED int pr[LB_TILE];          // products, then their local prefix
+	const int64_t n_tiles = (n + 1 + LB_TILE - 1) / LB_TILE;
+	for(int64_t t = lb_next_tile(c, n_tiles); t >= 0; t = lb_next_tile(c, n_tiles))
+	{
+		const int64_t g0 = t * LB_TILE;
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x)
+		{
+			const int64_t g = g0 + i;
+			f[i] = g < n ? diffc[g] : 0;
+		}
+		BLOCK_SYNC();
+		const int dsum = block_excl_scan(f, LB_TILE);
+		const int pre = (int)lb_tile_prefix(c, 0, t, dsum);
+		// coverage; flags of the segments
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x)
+		{
+			const int64_t g = g0 + i;
+			const int cc = g < n ? pre + f[i] + diffc[g] : 0;
+			cv[i] = cc;
+			if(g < n) cov[g] = cc;
+		}
+		if(threadIdx.x == 0) cv[LB_TILE] = pre;      // coverage right of border g0 - 1 = sum of all differences before the tile
+		BLOCK_SYNC();
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x)
+		{
+			const int64_t g = g0 + i;
+			const int on = (g < n && cv[i] > 0) ? 1 : 0;
+			f[i] = on;
+			int32_t p = 0;
+			if(on)
+			{
+				const int32_t pl = posc[g], prr = g + 1 < n ? posc[g + 1] : posc[g];
+				p = (int32_t)((u32)(prr - pl) * (u32)cv[i]);
+			}
+			pr[i] = p;
+		}
+		BLOCK_SYNC();
+		const int cnt = block_excl_scan(f, LB_TILE);
+		if(threadIdx.x == 0) f[LB_TILE] = cnt;
+		const int psum = block_excl_scan(pr, LB_TILE);
+		const int64_t o0 = lb_tile_prefix(c, 1, t, cnt);
+		const int64_t q0 = lb_tile_prefix(c, 2, t, psum);
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x)
+		{
+			const int64_t g = g0 + i;
+			if(g >= n || cv[i] <= 0) continue;
+			const int64_t o = o0 + f[i];
+			const int32_t pl = posc[g], prr = g + 1 < n ? posc[g + 1] : posc[g];
+			seg_l[o] = pl; seg_r[o] = prr; seg_c[o] = cv[i];
+			const int before = i > 0 ? cv[i - 1] : cv[LB_TILE];
+			seg_head[o] = (g > 0 && before > 0) ? -1 : 0;
+			seg_psum[o] = q0 + pr[i];
+		}
+		const bool last = t == n_tiles - 1;
+		if(last && threadIdx.x == 0) { seg_psum[o0 + cnt] = q0 + psum; *n_seg = o0 + cnt; }
+		// bundles whose first border falls into this tile (the last tile also owns rank n)
+		const int64_t hi = last ? n + 1 : g0 + LB_TILE;
+		const int b0 = lower_bound_idx(bord_off, n_bundles + 1, g0);
+		for(int b = b0 + (int)threadIdx.x; b <= n_bundles && bord_off[b] < hi; b += blockDim.x)
+			seg_off[b] = o0 + f[bord_off[b] - g0];
+		BLOCK_SYNC();
+	}
+}
+
 } // namespace agpu
+
 
 #endif

@@ -1,0 +1,159 @@
+// Single-pass device-wide prefix sums (decoupled look-back): every device-wide scan of the path is ONE launch instead of the
+// tile-sum / single-CTA scan / apply triple.
+//
+// A CTA takes the next tile from a ticket counter (tiles are therefore started in index order, which is what makes waiting for
+// a predecessor safe), scans it in shared memory, publishes the tile's aggregate in a 64-bit status word, then walks back over
+// its predecessors' words until it meets one that already holds an inclusive prefix.  Status word:
+//     [63:62] 0 = nothing yet, 1 = tile aggregate, 2 = inclusive prefix   [61:48] launch epoch   [47:0] value (two's complement)
+// The epoch makes words of earlier launches read as "nothing yet", so the status array is never cleared between launches; the
+// ticket counter is never reset either: every launch consumes exactly n_tiles + gridDim.x tickets and the host passes the
+// running total (lb_launch below).  Values are exact up to 2^47 in magnitude.
+//
+// Kernel-logic test build: CTAs run one after the other with blockDim.x == 1, so the first "CTA" takes every ticket in order
+// and every look-back finds its predecessor complete.
+#ifndef ALETSCH_B200_CSRC_LOOKBACK_H
+#define ALETSCH_B200_CSRC_LOOKBACK_H
+
+#include "dev.h"
+#include "blockops.h"
+
+namespace agpu {
+
+#define LB_TILE 2048
+#define LB_AGG 1ULL
+#define LB_INC 2ULL
+#define LB_CHAINS 4              // independent status arrays a kernel may chain (e.g. coverage sum -> segment count -> product sum)
+
+// what a look-back kernel needs from the host: status words of LB_CHAINS chains of `stride` tiles each, the ticket counter, this
+// launch's epoch and the tickets consumed before it
+struct lb_ctl
+{
+	u64 *status;
+	unsigned long long *ticket;
+	int64_t stride;
+	unsigned long long ticket_base;
+	u32 epoch;
+};
+
+HD u64 lb_pack(u64 flag, u32 epoch, int64_t v) { return (flag << 62) | ((u64)(epoch & 0x3fffu) << 48) | ((u64)v & 0xffffffffffffULL); }
+HD int64_t lb_value(u64 w) { return ((int64_t)(w << 16)) >> 16; }
+
+DEV u64 lb_load(const u64 *p)
+{
+#ifndef AGPU_EMU
+	return *(const volatile u64*)p;
+#else
+	return *p;
+#endif
+}
+DEV void lb_store(u64 *p, u64 w)
+{
+#ifndef AGPU_EMU
+	*(volatile u64*)p = w;
+#else
+	*p = w;
+#endif
+}
+
+// next tile of this launch for the CTA, or -1 when the launch is exhausted (all threads get the same answer)
+DEV int64_t lb_next_tile(const lb_ctl &c, int64_t n_tiles)
+{
+	SHARED long long s_tile;
+	BLOCK_SYNC();
+	if(threadIdx.x == 0)
+	{
+		unsigned long long t = atomicAdd(c.ticket, 1ULL) - c.ticket_base;
+		s_tile = t < (unsigned long long)n_tiles ? (long long)t : -1;
+	}
+	BLOCK_SYNC();
+	return (int64_t)s_tile;
+}
+
+// called by ONE thread of the CTA: publish the aggregate of `tile` on chain `chain`, return the sum of all earlier tiles
+DEV int64_t lb_resolve(const lb_ctl &c, int chain, int64_t tile, int64_t aggregate)
+{
+	u64 *st = c.status + (int64_t)chain * c.stride;
+	if(tile == 0) { lb_store(&st[0], lb_pack(LB_INC, c.epoch, aggregate)); return 0; }
+	lb_store(&st[tile], lb_pack(LB_AGG, c.epoch, aggregate));
+	int64_t run = 0;
+	int64_t p = tile - 1;
+	while(true)
+	{
+		const u64 w = lb_load(&st[p]);
+		const u64 flag = w >> 62;
+		if(flag == 0 || ((u32)(w >> 48) & 0x3fffu) != (c.epoch & 0x3fffu)) continue;      // not published in this launch yet
+		run += lb_value(w);
+		if(flag == LB_INC) break;
+		p--;
+	}
+	lb_store(&st[tile], lb_pack(LB_INC, c.epoch, run + aggregate));
+	return run;
+}
+
+// CTA-wide: exclusive prefix of the tile on `chain` broadcast to every thread (aggregate must be the same in all threads)
+DEV int64_t lb_tile_prefix(const lb_ctl &c, int chain, int64_t tile, int64_t aggregate)
+{
+	SHARED long long s_pre[LB_CHAINS];
+	if(threadIdx.x == 0) s_pre[chain] = lb_resolve(c, chain, tile, aggregate);
+	BLOCK_SYNC();
+	return (int64_t)s_pre[chain];
+}
+
+// ---- generic scans ---------------------------------------------------------------------------------------------------------
+// exclusive prefix sum of int32 values (mode 0) or of the flags (v[i] >= 0) (mode 1) into int64: out[i], out[n] = total
+KERNEL k_lb_scan_i32(lb_ctl c, const int32_t *v, int64_t n, int mode, int64_t *out)
+{
+	SHARED int f[LB_TILE];
+	const int64_t n_tiles = (n + 1 + LB_TILE - 1) / LB_TILE;
+	for(int64_t t = lb_next_tile(c, n_tiles); t >= 0; t = lb_next_tile(c, n_tiles))
+	{
+		const int64_t g0 = t * LB_TILE;
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x)
+		{
+			const int64_t g = g0 + i;
+			f[i] = g < n ? (mode ? (v[g] >= 0 ? 1 : 0) : v[g]) : 0;
+		}
+		BLOCK_SYNC();
+		const int tot = block_excl_scan(f, LB_TILE);
+		const int64_t pre = lb_tile_prefix(c, 0, t, tot);
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x)
+		{
+			const int64_t g = g0 + i;
+			if(g <= n) out[g] = pre + f[i];
+		}
+	}
+}
+
+// the same over int64 values
+KERNEL k_lb_scan_i64(lb_ctl c, const int64_t *v, int64_t n, int64_t *out)
+{
+	SHARED long long f[LB_TILE];
+	SHARED long long part[AGPU_MAX_BLOCK];
+	const int64_t n_tiles = (n + 1 + LB_TILE - 1) / LB_TILE;
+	for(int64_t t = lb_next_tile(c, n_tiles); t >= 0; t = lb_next_tile(c, n_tiles))
+	{
+		const int64_t g0 = t * LB_TILE;
+		const int nt = blockDim.x, th = threadIdx.x;
+		const int chunk = (LB_TILE + nt - 1) / nt;
+		int lo = th * chunk, hi = lo + chunk;
+		if(lo > LB_TILE) lo = LB_TILE;
+		if(hi > LB_TILE) hi = LB_TILE;
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x) { const int64_t g = g0 + i; f[i] = g < n ? v[g] : 0; }
+		BLOCK_SYNC();
+		long long sm = 0;
+		for(int i = lo; i < hi; i++) sm += f[i];
+		part[th] = sm;
+		BLOCK_SYNC();
+		long long tot = 0, mine = 0;
+		for(int k = 0; k < nt; k++) { if(k == th) mine = tot; tot += part[k]; }
+		const int64_t pre = lb_tile_prefix(c, 0, t, tot);
+		long long run = pre + mine;
+		for(int i = lo; i < hi; i++) { const long long x = f[i]; f[i] = run; run += x; }
+		BLOCK_SYNC();
+		for(int i = threadIdx.x; i < LB_TILE; i += blockDim.x) { const int64_t g = g0 + i; if(g <= n) out[g] = f[i]; }
+	}
+}
+
+} // namespace agpu
+
+#endif

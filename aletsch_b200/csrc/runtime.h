@@ -3,6 +3,7 @@
 #define ALETSCH_B200_CSRC_RUNTIME_H
 
 #include "dev.h"
+#include "lookback.h"
 #include "../../include/aletsch_gpu.h"
 
 #include <map>
@@ -66,6 +67,11 @@ struct agpu_ctx
 	size_t stage_cap = 0;
 	void *ev_stage = NULL;
 	bool stage_busy = false;
+	// decoupled look-back scans (lookback.h): status words, ticket counter, launch epoch, tickets consumed so far
+	unsigned long long *lb_status = NULL, *lb_ticket = NULL;
+	int64_t lb_stride = 0;
+	unsigned long long lb_tickets = 0;
+	unsigned lb_epoch = 0;
 	// pinned result mirrors of the fetches, by name (see agpu_batch::host)
 	std::map<std::string, agpu_pinbuf> pinned;
 	int64_t syncs = 0;
@@ -249,6 +255,71 @@ inline int stream_sync(agpu_ctx *ctx) { ctx->syncs++; return AGPU_OK; }
 inline void prof_collect(agpu_ctx *) {}
 inline void *pinned_alloc(size_t bytes) { return malloc(bytes ? bytes : 16); }
 inline void pinned_free(void *p) { free(p); }
+#endif
+
+// ---- launch of a decoupled look-back kernel (lookback.h): kern(lb_ctl, args...) over n_tiles tiles
+#define LB_STATUS_CHAINS 4
+inline int lb_prepare(agpu_ctx *ctx, int64_t n_tiles, unsigned grid, unsigned long long *ticket_base, unsigned *epoch)
+{
+	if(n_tiles > ctx->lb_stride || ctx->lb_status == NULL || ((ctx->lb_epoch + 1) & 0x3fffu) == 0)
+	{
+		// (re)allocate and clear: first use, more tiles than ever before, or the 14-bit epoch is about to wrap
+		int64_t stride = ctx->lb_stride > 0 ? ctx->lb_stride : ((int64_t)1 << 16);
+		while(stride < n_tiles) stride *= 2;
+		const size_t bytes = sizeof(unsigned long long) * (size_t)stride * LB_STATUS_CHAINS;
+#ifndef AGPU_EMU
+		if(stride != ctx->lb_stride || ctx->lb_status == NULL)
+		{
+			if(ctx->lb_status) cudaFreeAsync(ctx->lb_status, ctx->stream);
+			void *p = NULL;
+			if(cudaMallocAsync(&p, bytes, ctx->stream) != cudaSuccess) { cudaGetLastError(); ctx->lb_status = NULL; ctx->lb_stride = 0; return AGPU_ERR_OOM; }
+			ctx->lb_status = (unsigned long long*)p;
+		}
+		if(cudaMemsetAsync(ctx->lb_status, 0, bytes, ctx->stream) != cudaSuccess) return AGPU_ERR_CUDA;
+		if(ctx->lb_ticket == NULL)
+		{
+			void *p = NULL;
+			if(cudaMallocAsync(&p, 64, ctx->stream) != cudaSuccess) { cudaGetLastError(); return AGPU_ERR_OOM; }
+			ctx->lb_ticket = (unsigned long long*)p;
+			cudaMemsetAsync(ctx->lb_ticket, 0, 64, ctx->stream);
+			ctx->lb_tickets = 0;
+		}
+#else
+		if(stride != ctx->lb_stride || ctx->lb_status == NULL) { free(ctx->lb_status); ctx->lb_status = (unsigned long long*)malloc(bytes); }
+		memset(ctx->lb_status, 0, bytes);
+		if(ctx->lb_ticket == NULL) { ctx->lb_ticket = (unsigned long long*)calloc(8, 8); ctx->lb_tickets = 0; }
+#endif
+		ctx->lb_stride = stride;
+		ctx->lb_epoch = (ctx->lb_epoch + 1) & 0x3fffu;
+		if(ctx->lb_epoch == 0) ctx->lb_epoch = 1;
+	}
+	else ctx->lb_epoch++;
+	*epoch = ctx->lb_epoch & 0x3fffu;
+	*ticket_base = ctx->lb_tickets;
+	ctx->lb_tickets += (unsigned long long)n_tiles + grid;
+	return AGPU_OK;
+}
+inline void lb_destroy(agpu_ctx *ctx)
+{
+#ifndef AGPU_EMU
+	if(ctx->lb_status) cudaFreeAsync(ctx->lb_status, ctx->stream);
+	if(ctx->lb_ticket) cudaFreeAsync(ctx->lb_ticket, ctx->stream);
+#else
+	free(ctx->lb_status); free(ctx->lb_ticket);
+#endif
+	ctx->lb_status = NULL; ctx->lb_ticket = NULL; ctx->lb_stride = 0;
+}
+#ifndef AGPU_EMU
+#define LB_GRID(ctx, n_tiles) ((unsigned)((n_tiles) < (int64_t)(ctx)->sm_count * 8 ? (n_tiles) : (int64_t)(ctx)->sm_count * 8))
+#define LAUNCH_LB(ctx, kern, n_tiles, ...) do { int64_t nt_ = (int64_t)(n_tiles); if(nt_ > 0) { unsigned g_ = LB_GRID(ctx, nt_); agpu::lb_ctl lc_; \
+	unsigned ep_; unsigned long long tb_; TRY(lb_prepare(ctx, nt_, g_, &tb_, &ep_)); \
+	lc_.status = (agpu::u64*)(ctx)->lb_status; lc_.ticket = (ctx)->lb_ticket; lc_.stride = (ctx)->lb_stride; lc_.ticket_base = tb_; lc_.epoch = ep_; \
+	prof_begin(ctx, #kern); kern<<<g_, 256, 0, (ctx)->stream>>>(lc_, __VA_ARGS__); prof_end(ctx); (ctx)->launches++; } } while(0)
+#else
+#define LAUNCH_LB(ctx, kern, n_tiles, ...) do { int64_t nt_ = (int64_t)(n_tiles); if(nt_ > 0) { unsigned g_ = 2; agpu::lb_ctl lc_; \
+	unsigned ep_; unsigned long long tb_; TRY(lb_prepare(ctx, nt_, g_, &tb_, &ep_)); \
+	lc_.status = (agpu::u64*)(ctx)->lb_status; lc_.ticket = (ctx)->lb_ticket; lc_.stride = (ctx)->lb_stride; lc_.ticket_base = tb_; lc_.epoch = ep_; \
+	emu_launch(true, kern, g_, 256, lc_, __VA_ARGS__); (ctx)->launches++; } } while(0)
 #endif
 
 // stream-ordered device array
