@@ -158,6 +158,7 @@ struct agpu_batch
 	dbuf<int32_t> pt_d;
 	int64_t n_pts = 0;
 	dbuf<int32_t> spl, hit_nspl, hit_bundle;
+	dbuf<u32> ev_s;                        // window position of the start of every BAM_CMATCH block (k_cigar_tile -> k_cov_add_ops)
 	chainset_state hcst, fcst;
 	// segments
 	bool cov_dirty = true;
@@ -329,6 +330,7 @@ void agpu_destroy(agpu_ctx *ctx)
 #ifndef AGPU_EMU
 	cudaStreamSynchronize(ctx->stream);
 	arena_destroy(ctx);
+	lb_destroy(ctx);                      // stream-ordered frees: before the stream goes
 	cudaStreamSynchronize(ctx->stream);
 	if(ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
 	if(ctx->ev_fork) cudaEventDestroy((cudaEvent_t)ctx->ev_fork);
@@ -339,7 +341,9 @@ void agpu_destroy(agpu_ctx *ctx)
 #endif
 	pinned_free(ctx->stage_pin);
 	for(auto &r : ctx->pinned) r.second.release();
+#ifdef AGPU_EMU
 	lb_destroy(ctx);
+#endif
 	delete ctx;
 }
 
@@ -535,7 +539,8 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 		// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), derived on the device
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 		b->h.rpos = b->in_rpos.p;
-		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
+		if(d2d(ctx, b->in_rpos.p, b->h.pos, sizeof(int32_t) * (size_t)b->nh) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
+		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->in_rpos.p);
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
 	// the caller's buffers (and the context's staging area) are free again when this returns -- unless the context uploads
@@ -575,7 +580,8 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	{
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 		b->h.rpos = b->in_rpos.p;
-		LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
+		if(d2d(ctx, b->in_rpos.p, b->h.pos, sizeof(int32_t) * (size_t)b->nh) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
+		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->in_rpos.p);
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
 	if(stream_sync(ctx) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }      // frees the context's staging area
@@ -597,7 +603,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
 	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
 	b->group_pass = false;
-	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx);
+	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx); b->ev_s.release(ctx);
 	b->hcst.release(ctx); b->fcst.release(ctx);
 	b->seg_off.release(ctx);
 	b->seg_l.release(ctx); b->seg_r.release(ctx); b->seg_c.release(ctx); b->seg_nhead.release(ctx); b->seg_psum.release(ctx);
@@ -723,7 +729,7 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		TRY(b->bord_off.alloc(ctx, nb + 2));
 		LAUNCH_T(ctx, k_bord_off, nb + 1, nb, b->cov_base.p, b->wrank.p, b->bord_off.p);
 		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
-		LAUNCH_T(ctx, k_cov_add, b->nh, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p);
+		LAUNCH_T(ctx, k_cov_add_ops, b->nc, b->nc, b->h.cigar, b->ev_s.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);
 		// coverage = prefix sum of the differences; segments = borders with positive coverage; prefix sums of len * cov:
@@ -772,11 +778,13 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(stream_sync(ctx));
 	if(b->ltot >= ((int64_t)1 << 32) - 64) { ctx->last_error = "batch spans 2^32 or more window positions: split it"; return AGPU_ERR_CAPACITY; }
 	TRY(b->border.alloc(ctx, b->ltot / 32 + 8, true));
-	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1));
+	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1, true));
 	dbuf<int32_t> n_spliced;
 	TRY(n_spliced.alloc(ctx, nb + 1, true));
-	LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p,
-			b->hit_bundle.p, n_spliced.p, b->err.p);
+	// one thread per CIGAR operation, tiles of CG_TILE operations, persistent grid
+	TRY(b->ev_s.alloc(ctx, nc + 1));
+	LAUNCH_B(ctx, k_cigar_tile, std::min<int64_t>((nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 6), 256, b->h, nc, b->hit_bundle.p, b->b_lpos.p,
+			b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, n_spliced.p, b->ev_s.p, b->err.p);
 	// hcst
 	chainset_state &cs = b->hcst;
 	cs.val = b->spl.p; cs.voff32 = b->h.cigar_off; cs.voff64 = NULL; cs.elem_len = b->hit_nspl.p;

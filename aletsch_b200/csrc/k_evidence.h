@@ -834,7 +834,223 @@ KERNEL k_lb_cov_segments(lb_ctl c, const int32_t *diffc, const int32_t *posc, in
 	}
 }
 
+// ---- CIGAR walk, one thread per OPERATION (replaces the thread-per-hit walks k_hit_cigar / k_cov_add / k_hit_rpos) ----------
+// A CTA takes a tile of CG_TILE consecutive entries of cigar[] -- whatever hits they belong to -- with 128-bit loads into shared
+// memory.  The reference position of every operation is pos[hit] + (exclusive prefix of the reference-consuming lengths inside
+// the hit): one plain block scan over the tile, minus its value at the hit's first operation; the rank of an inner N operation
+// among the hit's splices is the same with a second scan; the hit of every operation is a running maximum over the marks the
+// tile's hits leave at their first operation.  A hit that starts before the tile gets its carry (consumed length, inner N count)
+// from a cooperative loop over its earlier operations.  So long-read CIGARs (tens of operations per hit) and short-read ones
+// (two per hit) cost the same per operation, every global access is coalesced, and the border bits of the tile -- which lie
+// within a few kilobases because hits are position-sorted -- are collected in a shared-memory bitmap window and leave the CTA as
+// one atomicOr per non-empty word.
+#define CG_TILE 1024
+#define CG_WIN_WORDS 4096        // shared bitmap window: 131072 window positions from the first hit of the tile
+
+struct cg_tile
+{
+	int64_t g0;        // first operation of the tile
+	int m;             // operations in the tile
+	int64_t h0;        // hit owning operation g0
+	int carry_len;     // reference length the operations of h0 before the tile consume
+	int carry_n;       // inner N operations of h0 before the tile
+};
+
+// hit owning operation k: the h with cigar_off[h] <= k < cigar_off[h + 1]
+DEV int64_t cg_owner(const u32 *cigar_off, int64_t n_hits, int64_t k)
+{
+	int64_t lo = 0, hi = n_hits - 1;
+	while(lo < hi)
+	{
+		int64_t mid = (lo + hi) >> 1;
+		if((int64_t)cigar_off[mid + 1] <= k) lo = mid + 1; else hi = mid;
+	}
+	return lo;
+}
+
+// loads the tile, fills hid[i] = hit of operation i, P[i] = exclusive prefix of the reference-consuming lengths, and (if R)
+// R[i] = exclusive prefix of the inner-N flags; returns the tile descriptor to every thread
+DEV cg_tile cg_tile_load(const hits_dev &h, int64_t n_ops, int64_t t, u32 *ops, int *hid, int *P, int *R)
+{
+	SHARED long long s_h0, s_h1;
+	SHARED int s_cl, s_cn;
+	cg_tile T;
+	T.g0 = t * CG_TILE;
+	T.m = (int)((n_ops - T.g0) < CG_TILE ? (n_ops - T.g0) : CG_TILE);
+	BLOCK_SYNC();
+	if(threadIdx.x == 0)
+	{
+		s_h0 = cg_owner(h.cigar_off, h.n_hits, T.g0);
+		s_h1 = cg_owner(h.cigar_off, h.n_hits, T.g0 + T.m - 1);
+		s_cl = 0; s_cn = 0;
+	}
+	// operations: 128-bit loads (tiles start at multiples of 1024 entries, the array base is 256-byte aligned)
+#ifndef AGPU_EMU
+	if((((size_t)(h.cigar + T.g0)) & 15) == 0)
+	{
+		const uint4 *src = (const uint4*)(h.cigar + T.g0);
+		for(int i = threadIdx.x; 4 * i < T.m; i += blockDim.x)
+		{
+			if(4 * i + 3 < T.m) { uint4 v = src[i]; ops[4 * i] = v.x; ops[4 * i + 1] = v.y; ops[4 * i + 2] = v.z; ops[4 * i + 3] = v.w; }
+			else for(int j = 4 * i; j < T.m; j++) ops[j] = h.cigar[T.g0 + j];
+		}
+	}
+	else
+#endif
+		for(int i = threadIdx.x; i < T.m; i += blockDim.x) ops[i] = h.cigar[T.g0 + i];
+	for(int i = threadIdx.x; i < T.m; i += blockDim.x) hid[i] = -1;
+	BLOCK_SYNC();
+	T.h0 = (int64_t)s_h0;
+	const int64_t h1 = (int64_t)s_h1;
+	// marks: every hit of the tile at its first operation (hits without operations share an offset with their successor: the
+	// maximum wins, and that is the hit that owns the operation); hit indices relative to h0 keep the marks in 31 bits
+	if(threadIdx.x == 0) hid[0] = 0;
+	BLOCK_SYNC();
+	for(int64_t hh = T.h0 + 1 + threadIdx.x; hh <= h1; hh += blockDim.x)
+	{
+		const int64_t o = (int64_t)h.cigar_off[hh] - T.g0;
+		if(o >= 0 && o < T.m) atomicMax(&hid[o], (int)(hh - T.h0));
+	}
+	BLOCK_SYNC();
+	block_incl_maxscan(hid, T.m);
+	for(int i = threadIdx.x; i < T.m; i += blockDim.x)
+	{
+		const u32 c = ops[i];
+		const u32 op = c & 0xf;
+		P[i] = ((0x3C1A7 >> (op << 1)) & 2) ? (int)(c >> 4) : 0;
+		if(R)
+		{
+			const int64_t hh = T.h0 + hid[i], k = T.g0 + i;
+			R[i] = (op == 3 && k != (int64_t)h.cigar_off[hh] && k != (int64_t)h.cigar_off[hh + 1] - 1) ? 1 : 0;
+		}
+	}
+	// carry of the hit that started before the tile
+	const int64_t c00 = (int64_t)h.cigar_off[T.h0];
+	for(int64_t k = c00 + threadIdx.x; k < T.g0; k += blockDim.x)
+	{
+		const u32 c = h.cigar[k];
+		const u32 op = c & 0xf;
+		if((0x3C1A7 >> (op << 1)) & 2) atomicAdd(&s_cl, (int)(c >> 4));
+		if(op == 3 && k != c00) atomicAdd(&s_cn, 1);
+	}
+	BLOCK_SYNC();
+	block_excl_scan(P, T.m);
+	if(R) block_excl_scan(R, T.m);
+	T.carry_len = s_cl; T.carry_n = s_cn;
+	return T;
+}
+
+// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64) when the host did not send it; rpos[] must be pre-filled with pos[]
+// (hits without operations keep it)
+KERNEL k_cigar_rpos(hits_dev h, int64_t n_ops, int32_t *rpos)
+{
+	SHARED u32 ops[CG_TILE];
+	SHARED int hid[CG_TILE], P[CG_TILE];
+	const int64_t n_tiles = (n_ops + CG_TILE - 1) / CG_TILE;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		const cg_tile T = cg_tile_load(h, n_ops, t, ops, hid, P, (int*)NULL);
+		for(int i = threadIdx.x; i < T.m; i += blockDim.x)
+		{
+			const int64_t hh = T.h0 + hid[i], k = T.g0 + i;
+			if(k != (int64_t)h.cigar_off[hh + 1] - 1) continue;          // the hit's last operation writes
+			const int64_t c0 = (int64_t)h.cigar_off[hh];
+			const bool carried = c0 < T.g0;
+			const int ib = carried ? 0 : (int)(c0 - T.g0);
+			const u32 c = ops[i];
+			const int own = ((0x3C1A7 >> ((c & 0xf) << 1)) & 2) ? (int)(c >> 4) : 0;
+			rpos[hh] = h.pos[hh] + (carried ? T.carry_len : 0) + (P[i] - P[ib]) + own;
+		}
+		BLOCK_SYNC();
+	}
+}
+
+// evidence pass over the operations: border bits of every BAM_CMATCH block (bundle_base::add_intervals: only op M adds
+// coverage), splice coordinates (hit::extract_splices: every N that is neither the first nor the last operation), per-hit splice
+// count, per-bundle number of spliced hits, the rpos contract check, and ev_s[k] = window position of the start of block k for
+// the second pass (k_cov_add_ops).  hit_nspl must be zeroed by the caller (hits without operations).
+KERNEL k_cigar_tile(hits_dev h, int64_t n_ops, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
+		int32_t *spl, int32_t *hit_nspl, int32_t *n_spliced, u32 *ev_s, int *err)
+{
+	SHARED u32 ops[CG_TILE];
+	SHARED int hid[CG_TILE], P[CG_TILE], R[CG_TILE];
+	SHARED u32 win[CG_WIN_WORDS];
+	SHARED int s_hi;
+	const int64_t n_tiles = (n_ops + CG_TILE - 1) / CG_TILE;
+	for(int i = threadIdx.x; i < CG_WIN_WORDS; i += blockDim.x) win[i] = 0;
+	if(threadIdx.x == 0) s_hi = -1;
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		const cg_tile T = cg_tile_load(h, n_ops, t, ops, hid, P, R);
+		// window of the shared bitmap: from the word of the first hit's start (hits are position-sorted inside a bundle and the
+		// bundles' windows follow one another, so nothing of the tile lies before it)
+		const int b00 = hit_bundle[T.h0];
+		const int64_t wword = (cov_base[b00] - (int64_t)b_lpos[b00] + (int64_t)h.pos[T.h0]) >> 5;
+		for(int i = threadIdx.x; i < T.m; i += blockDim.x)
+		{
+			const int64_t hh = T.h0 + hid[i], k = T.g0 + i;
+			const int64_t c0 = (int64_t)h.cigar_off[hh], c1 = (int64_t)h.cigar_off[hh + 1];
+			const bool carried = c0 < T.g0;
+			const int ib = carried ? 0 : (int)(c0 - T.g0);
+			const u32 c = ops[i];
+			const u32 op = c & 0xf, len = c >> 4;
+			const int own = ((0x3C1A7 >> (op << 1)) & 2) ? (int)len : 0;
+			const int32_t p0 = h.pos[hh] + (carried ? T.carry_len : 0) + (P[i] - P[ib]);      // reference position before the operation
+			const int32_t p1 = p0 + own;
+			const int rank = (carried ? T.carry_n : 0) + (R[i] - R[ib]);
+			const int b = hit_bundle[hh];
+			if(op == 0 && len > 0)
+			{
+				const int64_t base = cov_base[b] - (int64_t)b_lpos[b];
+				const int64_t s = base + p0, e = base + p1;
+				ev_s[k] = (u32)s;
+				const int64_t ws = (s >> 5) - wword, we = (e >> 5) - wword;
+				if(ws >= 0 && ws < CG_WIN_WORDS) { atomicOr(&win[ws], 1u << (s & 31)); atomicMax(&s_hi, (int)ws); }
+				else atomicOr(&border[s >> 5], 1u << (s & 31));
+				if(we >= 0 && we < CG_WIN_WORDS) { atomicOr(&win[we], 1u << (e & 31)); atomicMax(&s_hi, (int)we); }
+				else atomicOr(&border[e >> 5], 1u << (e & 31));
+			}
+			const bool inner_n = op == 3 && k != c0 && k != c1 - 1;
+			if(inner_n)
+			{
+				// a hit's splices live in its own stretch of spl[] (as many ints as it has operations)
+				if(2 * rank + 2 <= (int)(c1 - c0)) { spl[c0 + 2 * rank] = p1 - (int32_t)len; spl[c0 + 2 * rank + 1] = p1; }
+				else atomicAdd(&err[ERR_CAP], 1);
+			}
+			if(k == c1 - 1)
+			{
+				const int ns = 2 * rank;           // the last operation is never an inner N
+				hit_nspl[hh] = ns;
+				if(p1 != h.rpos[hh]) atomicAdd(&err[ERR_RPOS], 1);
+				if(ns > 0) atomicAdd(&n_spliced[b], 1);
+			}
+		}
+		BLOCK_SYNC();
+		const int hi = s_hi;
+		for(int w = threadIdx.x; w <= hi; w += blockDim.x)
+		{
+			const u32 bits = win[w];
+			if(bits) { atomicOr(&border[wword + w], bits); win[w] = 0; }
+		}
+		BLOCK_SYNC();
+		if(threadIdx.x == 0) s_hi = -1;
+	}
+}
+
+// second pass, one thread per operation: +1 at the start and -1 at the end of every BAM_CMATCH block, at the borders' ranks
+KERNEL k_cov_add_ops(int64_t n_ops, const u32 *cigar, const u32 *ev_s, const u32 *border, const u32 *wrank, int32_t *diffc)
+{
+	int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(k >= n_ops) return;
+	const u32 c = cigar[k];
+	if((c & 0xf) != 0 || (c >> 4) == 0) return;
+	const int64_t s = (int64_t)ev_s[k], e = s + (int64_t)(c >> 4);
+	atomicAdd(&diffc[border_rank(border, wrank, s)], 1);
+	atomicAdd(&diffc[border_rank(border, wrank, e)], -1);
+}
+
 } // namespace agpu
+
 
 
 #endif

@@ -161,7 +161,18 @@ inline void *arena_alloc(agpu_ctx *ctx, size_t bytes)
 		agpu_arena::slab s;
 		s.size = bytes > AGPU_SLAB_BYTES ? bytes : AGPU_SLAB_BYTES;
 		void *base = NULL;
-		if(cudaMallocAsync(&base, s.size, ctx->stream) != cudaSuccess) { cudaGetLastError(); return NULL; }
+		if(cudaMallocAsync(&base, s.size, ctx->stream) != cudaSuccess)
+		{
+			cudaGetLastError();
+			size_t fr = 0, tot = 0, held = 0;
+			cudaMemGetInfo(&fr, &tot);
+			for(size_t k = 0; k < a.slabs.size(); k++) held += a.slabs[k].size;
+			char buf[256];
+			snprintf(buf, sizeof(buf), "arena slab allocation of %zu MB failed: context holds %zu slabs / %zu MB, device free %zu MB of %zu MB",
+					s.size >> 20, a.slabs.size(), held >> 20, fr >> 20, tot >> 20);
+			ctx->last_error = buf;
+			return NULL;
+		}
 		s.base = (char*)base;
 		a.slabs.push_back(s);
 	}
@@ -174,7 +185,7 @@ inline int dev_alloc_bytes(agpu_ctx *ctx, void **p, size_t bytes, bool zero)
 	if(ctx->arena_on)
 	{
 		*p = arena_alloc(ctx, bytes);
-		if(!*p) { ctx->last_error = "arena slab allocation failed"; return AGPU_ERR_OOM; }
+		if(!*p) return AGPU_ERR_OOM;       // arena_alloc left the details in last_error
 	}
 	else
 	{

@@ -52,6 +52,7 @@ CONFIGS = {
 }
 MAX_BATCH_SPAN = 3_000_000_000     # window positions per device batch: the ABI's coverage index is 32-bit (AGPU_ERR_CAPACITY above 2^32)
 MAX_BATCH_HITS = 60_000_000
+E2E_CHUNK_HITS = 8_000_000
 
 
 def log(*a):
@@ -368,8 +369,12 @@ def run_ours(args):
     from aletsch_b200.pipeline import Pipeline
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
-    per_part = max(1, -(-args.chunks // len(parts)))
-    chunks = [ch for part in parts for ch in part.split(per_part)]
+    # sub-batches of at most ~E2E_CHUNK_HITS hits: each of the pool's contexts keeps an arena as large as the hungriest sub-batch
+    # it has seen, so the sub-batch size bounds the device memory of the pipeline (2 x streams contexts)
+    chunks = []
+    for part in parts:
+        per_part = max(1, -(-args.chunks // len(parts)), -(-part.n_hits // E2E_CHUNK_HITS))
+        chunks.extend(part.split(per_part))
     views = []
     h2d_bytes = 0
     for ch in chunks:
