@@ -135,7 +135,9 @@ struct agpu_batch
 	std::vector<int32_t> tid_host, sample_host;
 	// bundles by descending hit count: [0, n_large) get wide CTAs, the rest one warp each
 	dbuf<int32_t> order;
+	dbuf<int32_t> tile_owner;              // hit owning the first operation of every tile of CG_TILE CIGAR operations
 	int32_t n_large = 0;
+	int32_t n_pair_big = 0;               // [0, n_pair_big) of `order`: qname table too large for shared memory
 	// regions of the per-bundle qname tables (mate pairing): a power of two >= 1.5 x the bundle's hits
 	dbuf<int64_t> qreg_off;
 	int64_t q_slots = 0;
@@ -233,11 +235,13 @@ static int check_err(agpu_ctx *ctx, agpu_batch *b, const char *stage)
 // device-wide exclusive prefix sums, one launch each (lookback.h): out[i] = sum of v[0..i), out[n] = total
 static int lb_scan32(agpu_ctx *ctx, const int32_t *v, int64_t n, int mode, int64_t *out)
 {
+	if(mode == 0 && n <= SMALL_SCAN_MAX) { LAUNCH_B(ctx, k_small_scan_i32, 1, 1024, v, n, out); return AGPU_OK; }
 	LAUNCH_LB(ctx, k_lb_scan_i32, (n + 1 + LB_TILE - 1) / LB_TILE, v, n, mode, out);
 	return AGPU_OK;
 }
 static int lb_scan64(agpu_ctx *ctx, const int64_t *v, int64_t n, int64_t *out)
 {
+	if(n <= SMALL_SCAN_MAX) { LAUNCH_B(ctx, k_small_scan_i64, 1, 1024, v, n, out); return AGPU_OK; }
 	LAUNCH_LB(ctx, k_lb_scan_i64, (n + 1 + LB_TILE - 1) / LB_TILE, v, n, out);
 	return AGPU_OK;
 }
@@ -352,6 +356,15 @@ int agpu_sync(agpu_ctx *ctx) { if(!ctx) return AGPU_ERR_ARG; AGPU_ENTER(ctx); re
 int64_t agpu_launch_count(agpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t agpu_sync_count(agpu_ctx *ctx) { return ctx ? ctx->syncs : 0; }
 int64_t agpu_d2h_bytes(agpu_ctx *ctx) { return ctx ? ctx->d2h_result_bytes : 0; }
+int agpu_pinned_match(agpu_ctx *dst, agpu_ctx *src)
+{
+	if(!dst || !src) return AGPU_ERR_ARG;
+	if(dst == src) return AGPU_OK;
+	AGPU_ENTER(dst);
+	for(auto &r : src->pinned)
+		if(r.second.cap > 0 && !dst->pinned[r.first].reserve_exact(r.second.cap)) return AGPU_ERR_OOM;
+	return AGPU_OK;
+}
 
 // arena of the context (runtime.h): bytes held, and growth ahead of time so that a steady-state pipeline never has to take a
 // new slab (a cudaMallocAsync that misses the pool synchronises the device) in the middle of its work
@@ -442,6 +455,15 @@ static int check_hit_offsets(agpu_ctx *ctx, agpu_batch *b)
 	return AGPU_OK;
 }
 
+// owner hit of every tile of CG_TILE CIGAR operations (k_tile_owner): once per batch, below the arena mark
+static int batch_tile_owner(agpu_ctx *ctx, agpu_batch *b)
+{
+	const int64_t n_tiles = (b->nc + CG_TILE - 1) / CG_TILE;
+	if(b->tile_owner.p == NULL) TRY(b->tile_owner.alloc(ctx, n_tiles + 2, true));      // (the compact upload allocates it below its arena mark)
+	LAUNCH_T(ctx, k_tile_owner, b->nh, b->nh, b->h.cigar_off, n_tiles, b->tile_owner.p);
+	return AGPU_OK;
+}
+
 static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 {
 	TRY(b->err.alloc(ctx, ERR_WORDS, true));
@@ -451,6 +473,14 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ho[x + 1] - ho[x] > ho[y + 1] - ho[y]; });
 	b->n_large = 0;
 	while(b->n_large < b->nb && ho[ord[b->n_large] + 1] - ho[ord[b->n_large]] >= LARGE_BUNDLE_HITS) b->n_large++;
+	// bundles whose qname table (a power of two >= 1.5 x hits) does not fit the shared-memory table of k_pair_bundle
+	b->n_pair_big = 0;
+	while(b->n_pair_big < b->nb)
+	{
+		const int64_t ne = ho[ord[b->n_pair_big] + 1] - ho[ord[b->n_pair_big]];
+		if((int64_t)pow2_ceil((u32)std::max<int64_t>(ne + ne / 2, 2)) <= PAIR_SMEM_SLOTS) break;
+		b->n_pair_big++;
+	}
 	// staged through the context's pinned area: asynchronous copies, no stream drain here
 	const size_t need = sizeof(int64_t) * ((size_t)b->nb + 2) + sizeof(int32_t) * ((size_t)b->nb + 2);
 #ifndef AGPU_EMU
@@ -534,13 +564,14 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.pos = b->in_pos.p; b->h.rpos = b->in_rpos.p; b->h.mpos = b->in_mpos.p; b->h.isize = b->in_isize.p;
 	b->h.flag = NULL; b->h.strand = b->in_strand.p; b->h.bundle_strand = b->in_bstrand.p; b->h.xs = b->in_xs.p; b->h.qid = (const u64*)b->in_qid.p;
 	b->h.cigar_off = b->in_cigar_off.p; b->h.cigar = b->in_cigar.p;
+	if(batch_tile_owner(ctx, b) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 	if(!in->rpos)
 	{
 		// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), derived on the device
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 		b->h.rpos = b->in_rpos.p;
 		if(d2d(ctx, b->in_rpos.p, b->h.pos, sizeof(int32_t) * (size_t)b->nh) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
-		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->in_rpos.p);
+		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->tile_owner.p, b->in_rpos.p);
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
 	// the caller's buffers (and the context's staging area) are free again when this returns -- unless the context uploads
@@ -576,12 +607,13 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.flag = in->flag; b->h.strand = in->strand; b->h.bundle_strand = in->bundle_strand; b->h.xs = in->xs; b->h.qid = (const u64*)in->qid;
 	b->h.cigar_off = in->cigar_off; b->h.cigar = in->cigar;
 	if(!in->strand && !in->bundle_strand) { agpu_batch_free(ctx, b); return AGPU_ERR_ARG; }
+	if(batch_tile_owner(ctx, b) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 	if(!in->rpos)
 	{
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 		b->h.rpos = b->in_rpos.p;
 		if(d2d(ctx, b->in_rpos.p, b->h.pos, sizeof(int32_t) * (size_t)b->nh) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
-		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->in_rpos.p);
+		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->tile_owner.p, b->in_rpos.p);
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
 	if(stream_sync(ctx) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }      // frees the context's staging area
@@ -619,7 +651,7 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 	b->in_hit_off.release(ctx); b->in_pos.release(ctx); b->in_rpos.release(ctx); b->in_mpos.release(ctx); b->in_isize.release(ctx);
 	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_bstrand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
 	b->in_cigar_off.release(ctx); b->in_cigar.release(ctx);
-	b->err.release(ctx); b->order.release(ctx); b->qreg_off.release(ctx);
+	b->err.release(ctx); b->order.release(ctx); b->qreg_off.release(ctx); b->tile_owner.release(ctx);
 	stream_sync(ctx);
 	if(ctx->arena_owner == b) { ctx->arena.rewind(); ctx->arena_owner = NULL; }
 	delete b;
@@ -729,7 +761,7 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		TRY(b->bord_off.alloc(ctx, nb + 2));
 		LAUNCH_T(ctx, k_bord_off, nb + 1, nb, b->cov_base.p, b->wrank.p, b->bord_off.p);
 		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
-		LAUNCH_T(ctx, k_cov_add_ops, b->nc, b->nc, b->h.cigar, b->ev_s.p, b->border.p, b->wrank.p, b->diffc.p);
+		LAUNCH_B(ctx, k_cov_add_tile, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->nc, b->h.cigar, b->ev_s.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);
 		// coverage = prefix sum of the differences; segments = borders with positive coverage; prefix sums of len * cov:
@@ -783,7 +815,7 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(n_spliced.alloc(ctx, nb + 1, true));
 	// one thread per CIGAR operation, tiles of CG_TILE operations, persistent grid
 	TRY(b->ev_s.alloc(ctx, nc + 1));
-	LAUNCH_B(ctx, k_cigar_tile, std::min<int64_t>((nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 6), 256, b->h, nc, b->hit_bundle.p, b->b_lpos.p,
+	LAUNCH_B(ctx, k_cigar_tile, std::min<int64_t>((nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 6), 256, b->h, nc, b->tile_owner.p, b->hit_bundle.p, b->b_lpos.p,
 			b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, n_spliced.p, b->ev_s.p, b->err.p);
 	// hcst
 	chainset_state &cs = b->hcst;

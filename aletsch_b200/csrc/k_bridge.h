@@ -377,14 +377,14 @@ KERNEL k_cluster_pier(int64_t n_clu, const int32_t *c_bundle, const int64_t *clu
 	if(lo < np && br.p_bs[c0 + lo] == v1 && br.p_bt[c0 + lo] == v2) br.pier_of[c] = lo;
 }
 
-// candidate scratch of every group: (max in-degree + 1) * K entries per pass
+// candidate scratch of every group: (max in-degree + 1) * K entries for each of the two strand passes
 KERNEL k_group_cand(int64_t n_slots, int32_t n_bundles, const int64_t *clu_off, bridge_dev br, int64_t *cand_need)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n_slots) return;
 	int b = find_segment(clu_off, n_bundles, i);
 	int gi = (int)(i - clu_off[b]);
-	cand_need[i] = gi < br.n_groups[b] ? (int64_t)br.maxin[b] * br.K : 0;
+	cand_need[i] = gi < br.n_groups[b] ? (int64_t)2 * br.maxin[b] * br.K : 0;       // one stretch per strand pass: the passes run side by side
 }
 
 struct entry_less
@@ -442,8 +442,9 @@ KERNEL k_bridge_dp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bund
 	int k1 = br.g_k1[slot], k2 = br.g_k2[slot];
 	int nrow = k2 - k1 + 1;
 	int64_t row0 = br.g_row_off[slot] + (int64_t)pass * nrow;
-	int32_t *cand = br.cand + br.g_cand_off[slot] * W;
-	int32_t *cidx = br.cand_idx + br.g_cand_off[slot];
+	const int64_t poff = (int64_t)pass * br.maxin[b] * K;
+	int32_t *cand = br.cand + (br.g_cand_off[slot] + poff) * W;
+	int32_t *cidx = br.cand_idx + br.g_cand_off[slot] + poff;
 	// table[k1]: one entry, stack of D times 999999, length of the vertex, no trace
 	br.t_cnt[row0] = 1;
 	for(int d = 0; d < D; d++) br.t_stack[row0 * K * D + d] = 999999;
@@ -501,6 +502,257 @@ KERNEL k_bridge_dp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bund
 			br.t_len[row * K + i] = ce[D];
 			br.t_tr1[row * K + i] = ce[D + 1];
 			br.t_tr2[row * K + i] = ce[D + 2];
+		}
+	}
+}
+
+// ---- B3 (device build): the same DP with one WARP per (pier group, strand pass).  Per vertex the warp's lanes take the
+// in-edges (coalesced reads of the CSR row), a warp scan places every edge's candidates, the lanes then build the candidates
+// -- update_stack of one predecessor entry each -- into the warp's shared-memory slice, and rank them by counting under
+// entry_compare (rank = number of smaller candidates + number of equal ones generated earlier: the stable order).  std::sort of
+// the reference is stable for up to 16 elements (pure insertion sort) and, whatever its internals, yields THE sorted order when
+// no two candidates compare equal; only a vertex with more than 16 candidates AND a tie is handed to one lane for the exact
+// libstdc++ replay (stdsort.h), on the shared-memory copy.  The K best go to the table row in global memory (the trace-back
+// needs every row), written by the lanes that own them.
+#ifndef AGPU_EMU
+#define DPW_WS 32
+#else
+#define DPW_WS 1                 // kernel-logic build: a "warp" of one lane runs the same code
+#endif
+#define DPW_WARPS 4              // warps per CTA
+#define DPW_CMAX 128             // candidates per vertex kept in shared memory (more: the job falls back to the scratch in global memory)
+#define DPW_EMAX 64              // in-edges per vertex kept in shared memory
+#define DPW_W (AGPU_MAX_DP_STACK + 3)
+
+DEV int dpw_excl_scan(int v, int lane, int *total)
+{
+#ifndef AGPU_EMU
+	int inc = v;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+	*total = __shfl_sync(0xffffffffu, inc, 31);
+	return inc - v;
+#else
+	(void)lane;
+	*total = v;
+	return 0;
+#endif
+}
+DEV void dpw_sync()
+{
+#ifndef AGPU_EMU
+	__syncwarp();
+#endif
+}
+DEV int dpw_any(int p)
+{
+#ifndef AGPU_EMU
+	return __any_sync(0xffffffffu, p);
+#else
+	return p;
+#endif
+}
+
+// a < b under entry_compare (bridge/bridge_solver.cc:21-30) on shared-memory candidates of stride DPW_W
+DEV int dpw_cmp(const int32_t *a, const int32_t *b, int D)
+{
+	for(int i = 0; i < D; i++)
+	{
+		if(a[i] > b[i]) return -1;
+		if(a[i] < b[i]) return 1;
+	}
+	if(a[D] < b[D]) return -1;
+	if(a[D] > b[D]) return 1;
+	return 0;
+}
+
+KERNEL k_bridge_dp_warp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bundle, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand,
+		bridge_dev br)
+{
+	SHARED int32_t s_cand[DPW_WARPS][DPW_CMAX * DPW_W];
+	SHARED int32_t s_rank[DPW_WARPS][DPW_CMAX];
+	SHARED int32_t s_ej[DPW_WARPS][DPW_EMAX], s_ew[DPW_WARPS][DPW_EMAX], s_eo[DPW_WARPS][DPW_EMAX + 1];
+	const int WS = DPW_WS;
+	const int lane = threadIdx.x % WS, wid = threadIdx.x / WS, wpc = blockDim.x / WS > 0 ? blockDim.x / WS : 1;
+	int32_t *cand = s_cand[wid], *rank = s_rank[wid], *ej = s_ej[wid], *ew = s_ew[wid], *eo = s_eo[wid];
+	for(int64_t ji = (int64_t)blockIdx.x * wpc + wid; ji < n_jobs; ji += (int64_t)gridDim.x * wpc)
+	{
+		const int64_t job = dp_job[ji];
+		const int64_t slot = job >> 1;
+		const int pass = (int)(job & 1);
+		const int b = dp_bundle[ji];
+		const sgraph sg = sgraph_of(g, b_strand, b);
+		const int strand = pass_strand(sg.strand, pass);
+		const int K = br.K, D = br.D, W = D + 3;
+		const int k1 = br.g_k1[slot], k2 = br.g_k2[slot];
+		const int nrow = k2 - k1 + 1;
+		const int64_t row0 = br.g_row_off[slot] + (int64_t)pass * nrow;
+		const int64_t poff = (int64_t)pass * br.maxin[b] * K;
+		int32_t *gcand = br.cand + (br.g_cand_off[slot] + poff) * W;
+		int32_t *gcidx = br.cand_idx + br.g_cand_off[slot] + poff;
+		if(lane == 0)
+		{
+			// table[k1]: one entry, stack of D times 999999, length of the vertex, no trace
+			br.t_cnt[row0] = 1;
+			for(int d = 0; d < D; d++) br.t_stack[row0 * K * D + d] = 999999;
+			br.t_len[row0 * K] = sg.gv.v_r[k1] - sg.gv.v_l[k1];
+			br.t_tr1[row0 * K] = -1; br.t_tr2[row0 * K] = -1;
+		}
+		dpw_sync();
+		for(int k = k1 + 1; k <= k2; k++)
+		{
+			const int64_t row = row0 + (k - k1);
+			const int32_t len = sg.gv.v_r[k] - sg.gv.v_l[k];
+			const int lo = sg.in_off[k], hi = sg.in_off[k + 1];
+			const int ne = hi - lo + (pseudo_edge(sg, k - 1) ? 1 : 0);
+			if(ne > DPW_EMAX)
+			{
+				// more in-edges than the shared slice holds: the sequential form of the reference on the global scratch (one lane)
+				if(lane == 0)
+				{
+					int nc = 0;
+					for(int x = lo; x < lo + ne; x++)
+					{
+						int j, w, s;
+						if(x < hi) { int e = sg.in_eid[x]; j = sg.in_src[x]; s = sg.e_strand[e]; w = (int)sg.e_w[e]; }
+						else { j = k - 1; s = 0; w = 0; }
+						if(s != 0 && s != strand) continue;
+						if(j < k1) continue;
+						const int64_t jr = row0 + (j - k1);
+						const int nj = br.t_cnt[jr];
+						for(int i = 0; i < nj; i++)
+						{
+							int32_t *ce = gcand + (int64_t)nc * W;
+							const int32_t *v = br.t_stack + (jr * K + i) * D;
+							for(int q = 0; q < D; q++) ce[q] = 0;
+							for(int a = 0, q = 0; a < D && q < D; a++, q++)
+							{
+								if(a == q && v[a] > w) { ce[q] = w; q++; if(q >= D) break; }
+								ce[q] = v[a];
+							}
+							ce[D] = br.t_len[jr * K + i] + len; ce[D + 1] = j; ce[D + 2] = i;
+							gcidx[nc] = nc;
+							nc++;
+						}
+					}
+					entry_less less;
+					less.cand = gcand; less.D = D; less.W = W;
+					std_sort_handles(gcidx, nc, less);
+					const int keep = nc > K ? K : nc;
+					br.t_cnt[row] = keep;
+					for(int i = 0; i < keep; i++)
+					{
+						const int32_t *ce = gcand + (int64_t)gcidx[i] * W;
+						for(int d = 0; d < D; d++) br.t_stack[(row * K + i) * D + d] = ce[d];
+						br.t_len[row * K + i] = ce[D]; br.t_tr1[row * K + i] = ce[D + 1]; br.t_tr2[row * K + i] = ce[D + 2];
+					}
+				}
+				dpw_sync();
+				continue;
+			}
+			// in-edges in (source, target) order; the pseudo edge from k - 1, if any, has the largest source
+			int carry = 0;
+			for(int x0 = 0; x0 < ne; x0 += WS)
+			{
+				const int x = x0 + lane;
+				int j = -1, w = 0, nj = 0;
+				if(x < ne)
+				{
+					int s;
+					if(lo + x < hi) { const int e = sg.in_eid[lo + x]; j = sg.in_src[lo + x]; s = sg.e_strand[e]; w = (int)sg.e_w[e]; }
+					else { j = k - 1; s = 0; w = 0; }            // (int)0.5
+					if((s == 0 || s == strand) && j >= k1) nj = br.t_cnt[row0 + (j - k1)];
+				}
+				int tot;
+				const int off = carry + dpw_excl_scan(nj, lane, &tot);
+				if(x < ne) { ej[x] = j; ew[x] = w; eo[x] = off; }
+				carry += tot;
+			}
+			if(lane == 0) eo[ne] = carry;
+			const int nc = carry;
+			dpw_sync();
+			const bool in_smem = nc <= DPW_CMAX;
+			int32_t *cd = in_smem ? cand : gcand;
+			const int CW = in_smem ? DPW_W : W;
+			for(int c = lane; c < nc; c += WS)
+			{
+				// edge of candidate c: last e with eo[e] <= c
+				int e = 0;
+				{
+					int a = 0, z = ne;
+					while(a < z) { int m = (a + z) >> 1; if(eo[m + 1] <= c) a = m + 1; else z = m; }
+					e = a;
+				}
+				const int j = ej[e], w = ew[e], i = c - eo[e];
+				const int64_t jr = row0 + (j - k1);
+				int32_t *ce = cd + (int64_t)c * CW;
+				const int32_t *v = br.t_stack + (jr * K + i) * D;
+				// update_stack (:532-546)
+				for(int q = 0; q < D; q++) ce[q] = 0;
+				for(int a = 0, q = 0; a < D && q < D; a++, q++)
+				{
+					if(a == q && v[a] > w) { ce[q] = w; q++; if(q >= D) break; }
+					ce[q] = v[a];
+				}
+				ce[D] = br.t_len[jr * K + i] + len; ce[D + 1] = j; ce[D + 2] = i;
+			}
+			dpw_sync();
+			const int keep = nc > K ? K : nc;
+			if(in_smem)
+			{
+				int tie = 0;
+				for(int c = lane; c < nc; c += WS)
+				{
+					const int32_t *me = cd + c * CW;
+					int r = 0;
+					for(int o = 0; o < nc; o++)
+					{
+						if(o == c) continue;
+						const int q = dpw_cmp(cd + o * CW, me, D);
+						if(q < 0 || (q == 0 && o < c)) r++;
+						if(q == 0) tie = 1;
+					}
+					rank[c] = r;
+				}
+				if(nc > 16 && dpw_any(tie))
+				{
+					// more than 16 candidates with a tie: the reference's introsort decides the order of the equal ones
+					dpw_sync();
+					if(lane == 0)
+					{
+						int32_t *idx = gcidx;
+						for(int c = 0; c < nc; c++) idx[c] = c;
+						entry_less less;
+						less.cand = cd; less.D = D; less.W = CW;
+						std_sort_handles(idx, nc, less);
+						for(int r = 0; r < nc; r++) rank[idx[r]] = r;
+					}
+					dpw_sync();
+				}
+				for(int c = lane; c < nc; c += WS)
+				{
+					const int r = rank[c];
+					if(r >= keep) continue;
+					const int32_t *ce = cd + c * CW;
+					for(int d = 0; d < D; d++) br.t_stack[(row * K + r) * D + d] = ce[d];
+					br.t_len[row * K + r] = ce[D]; br.t_tr1[row * K + r] = ce[D + 1]; br.t_tr2[row * K + r] = ce[D + 2];
+				}
+			}
+			else if(lane == 0)
+			{
+				for(int c = 0; c < nc; c++) gcidx[c] = c;
+				entry_less less;
+				less.cand = cd; less.D = D; less.W = CW;
+				std_sort_handles(gcidx, nc, less);
+				for(int i = 0; i < keep; i++)
+				{
+					const int32_t *ce = cd + (int64_t)gcidx[i] * CW;
+					for(int d = 0; d < D; d++) br.t_stack[(row * K + i) * D + d] = ce[d];
+					br.t_len[row * K + i] = ce[D]; br.t_tr1[row * K + i] = ce[D + 1]; br.t_tr2[row * K + i] = ce[D + 2];
+				}
+			}
+			if(lane == 0) br.t_cnt[row] = keep;
+			dpw_sync();
 		}
 	}
 }

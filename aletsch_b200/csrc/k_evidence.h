@@ -868,9 +868,21 @@ DEV int64_t cg_owner(const u32 *cigar_off, int64_t n_hits, int64_t k)
 	return lo;
 }
 
+// tile_owner[t] = hit owning operation t * CG_TILE (one thread per hit: a hit writes every tile boundary its operations cover);
+// tile_owner[n_tiles] = n_hits - 1 closes the last tile.  cigar_off never changes, so a batch computes this once.
+KERNEL k_tile_owner(int64_t n_hits, const u32 *cigar_off, int64_t n_tiles, int32_t *tile_owner)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_hits) return;
+	const int64_t c0 = cigar_off[i], c1 = cigar_off[i + 1];
+	if(i == n_hits - 1) tile_owner[n_tiles] = (int32_t)i;
+	if(c1 <= c0) return;
+	for(int64_t t = (c0 + CG_TILE - 1) / CG_TILE; t * CG_TILE < c1; t++) tile_owner[t] = (int32_t)i;
+}
+
 // loads the tile, fills hid[i] = hit of operation i, P[i] = exclusive prefix of the reference-consuming lengths, and (if R)
 // R[i] = exclusive prefix of the inner-N flags; returns the tile descriptor to every thread
-DEV cg_tile cg_tile_load(const hits_dev &h, int64_t n_ops, int64_t t, u32 *ops, int *hid, int *P, int *R)
+DEV cg_tile cg_tile_load(const hits_dev &h, int64_t n_ops, const int32_t *tile_owner, int64_t t, u32 *ops, int *hid, int *P, int *R)
 {
 	SHARED long long s_h0, s_h1;
 	SHARED int s_cl, s_cn;
@@ -880,8 +892,8 @@ DEV cg_tile cg_tile_load(const hits_dev &h, int64_t n_ops, int64_t t, u32 *ops, 
 	BLOCK_SYNC();
 	if(threadIdx.x == 0)
 	{
-		s_h0 = cg_owner(h.cigar_off, h.n_hits, T.g0);
-		s_h1 = cg_owner(h.cigar_off, h.n_hits, T.g0 + T.m - 1);
+		s_h0 = tile_owner[t];
+		s_h1 = tile_owner[t + 1];       // owner of the next tile's first operation: no hit of this tile lies beyond it
 		s_cl = 0; s_cn = 0;
 	}
 	// operations: 128-bit loads (tiles start at multiples of 1024 entries, the array base is 256-byte aligned)
@@ -942,14 +954,14 @@ DEV cg_tile cg_tile_load(const hits_dev &h, int64_t n_ops, int64_t t, u32 *ops, 
 
 // hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64) when the host did not send it; rpos[] must be pre-filled with pos[]
 // (hits without operations keep it)
-KERNEL k_cigar_rpos(hits_dev h, int64_t n_ops, int32_t *rpos)
+KERNEL k_cigar_rpos(hits_dev h, int64_t n_ops, const int32_t *tile_owner, int32_t *rpos)
 {
 	SHARED u32 ops[CG_TILE];
 	SHARED int hid[CG_TILE], P[CG_TILE];
 	const int64_t n_tiles = (n_ops + CG_TILE - 1) / CG_TILE;
 	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
 	{
-		const cg_tile T = cg_tile_load(h, n_ops, t, ops, hid, P, (int*)NULL);
+		const cg_tile T = cg_tile_load(h, n_ops, tile_owner, t, ops, hid, P, (int*)NULL);
 		for(int i = threadIdx.x; i < T.m; i += blockDim.x)
 		{
 			const int64_t hh = T.h0 + hid[i], k = T.g0 + i;
@@ -969,7 +981,7 @@ KERNEL k_cigar_rpos(hits_dev h, int64_t n_ops, int32_t *rpos)
 // coverage), splice coordinates (hit::extract_splices: every N that is neither the first nor the last operation), per-hit splice
 // count, per-bundle number of spliced hits, the rpos contract check, and ev_s[k] = window position of the start of block k for
 // the second pass (k_cov_add_ops).  hit_nspl must be zeroed by the caller (hits without operations).
-KERNEL k_cigar_tile(hits_dev h, int64_t n_ops, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
+KERNEL k_cigar_tile(hits_dev h, int64_t n_ops, const int32_t *tile_owner, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
 		int32_t *spl, int32_t *hit_nspl, int32_t *n_spliced, u32 *ev_s, int *err)
 {
 	SHARED u32 ops[CG_TILE];
@@ -981,7 +993,7 @@ KERNEL k_cigar_tile(hits_dev h, int64_t n_ops, const int32_t *hit_bundle, const 
 	if(threadIdx.x == 0) s_hi = -1;
 	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
 	{
-		const cg_tile T = cg_tile_load(h, n_ops, t, ops, hid, P, R);
+		const cg_tile T = cg_tile_load(h, n_ops, tile_owner, t, ops, hid, P, R);
 		// window of the shared bitmap: from the word of the first hit's start (hits are position-sorted inside a bundle and the
 		// bundles' windows follow one another, so nothing of the tile lies before it)
 		const int b00 = hit_bundle[T.h0];
@@ -1037,16 +1049,51 @@ KERNEL k_cigar_tile(hits_dev h, int64_t n_ops, const int32_t *hit_bundle, const 
 	}
 }
 
-// second pass, one thread per operation: +1 at the start and -1 at the end of every BAM_CMATCH block, at the borders' ranks
-KERNEL k_cov_add_ops(int64_t n_ops, const u32 *cigar, const u32 *ev_s, const u32 *border, const u32 *wrank, int32_t *diffc)
+// second pass over the operations: +1 at the start and -1 at the end of every BAM_CMATCH block, at the borders' ranks.  The
+// hits of a tile start within a few kilobases of one another and share exon ends, so a tile's events are first summed per
+// position in a shared-memory hash table; every distinct position then costs one border_rank lookup and ONE global atomic.
+#define CA_SLOTS 4096            // >= 2 x the events of a tile (two per operation)
+KERNEL k_cov_add_tile(int64_t n_ops, const u32 *cigar, const u32 *ev_s, const u32 *border, const u32 *wrank, int32_t *diffc)
 {
-	int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(k >= n_ops) return;
-	const u32 c = cigar[k];
-	if((c & 0xf) != 0 || (c >> 4) == 0) return;
-	const int64_t s = (int64_t)ev_s[k], e = s + (int64_t)(c >> 4);
-	atomicAdd(&diffc[border_rank(border, wrank, s)], 1);
-	atomicAdd(&diffc[border_rank(border, wrank, e)], -1);
+	SHARED u32 s_key[CA_SLOTS];
+	SHARED int s_cnt[CA_SLOTS];
+	const int64_t n_tiles = (n_ops + CG_TILE - 1) / CG_TILE;
+	for(int i = threadIdx.x; i < CA_SLOTS; i += blockDim.x) { s_key[i] = 0xffffffffu; s_cnt[i] = 0; }
+	BLOCK_SYNC();
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		const int64_t g0 = t * CG_TILE;
+		for(int i = threadIdx.x; i < CG_TILE; i += blockDim.x)
+		{
+			const int64_t k = g0 + i;
+			if(k >= n_ops) break;
+			const u32 c = cigar[k];
+			if((c & 0xf) != 0 || (c >> 4) == 0) continue;
+			const u32 s0 = ev_s[k];
+			for(int side = 0; side < 2; side++)
+			{
+				const u32 key = side ? s0 + (c >> 4) : s0;          // window positions stay below 2^32 - 64 (agpu_batch_evidence)
+				u32 p = (key * 2654435761u) >> 20;                    // 12 bits
+				while(true)
+				{
+					const u32 cur = atomicCAS(&s_key[p], 0xffffffffu, key);
+					if(cur == 0xffffffffu || cur == key) break;
+					p = (p + 1) & (CA_SLOTS - 1);
+				}
+				atomicAdd(&s_cnt[p], side ? -1 : 1);
+			}
+		}
+		BLOCK_SYNC();
+		for(int i = threadIdx.x; i < CA_SLOTS; i += blockDim.x)
+		{
+			const u32 key = s_key[i];
+			if(key == 0xffffffffu) continue;
+			const int d = s_cnt[i];
+			if(d != 0) atomicAdd(&diffc[border_rank(border, wrank, (int64_t)key)], d);
+			s_key[i] = 0xffffffffu; s_cnt[i] = 0;
+		}
+		BLOCK_SYNC();
+	}
 }
 
 } // namespace agpu

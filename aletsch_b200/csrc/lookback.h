@@ -154,6 +154,49 @@ KERNEL k_lb_scan_i64(lb_ctl c, const int64_t *v, int64_t n, int64_t *out)
 	}
 }
 
+// ---- per-bundle sized arrays (a few 10^4 elements): one CTA, no look-back machinery.  Every thread owns a contiguous chunk; the
+// chunk sums are scanned with warp shuffles (two levels), then every thread writes its chunk.
+#define SMALL_SCAN_MAX 65536
+template<typename T> DEV void small_scan(const T *in, int64_t n, int64_t *out)
+{
+	SHARED long long wtot[32];
+	const int nt = blockDim.x, t = threadIdx.x;
+	const int64_t chunk = (n + nt - 1) / nt;
+	int64_t lo = t * chunk, hi = lo + chunk;
+	if(lo > n) lo = n;
+	if(hi > n) hi = n;
+	long long s = 0;
+	for(int64_t i = lo; i < hi; i++) s += (long long)in[i];
+	long long pre = 0, total = 0;
+#ifndef AGPU_EMU
+	const int lane = t & 31, w = t >> 5, nw = (nt + 31) >> 5;
+	long long inc = s;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+	if(lane == 31) wtot[w] = inc;
+	__syncthreads();
+	if(w == 0)
+	{
+		long long v = lane < nw ? wtot[lane] : 0, vi = v;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, vi, o); if(lane >= o) vi += y; }
+		wtot[lane] = vi - v;                      // exclusive prefix of the warp totals (32 warps at most)
+	}
+	__syncthreads();
+	pre = wtot[w] + inc - s;
+	// total = prefix of the last thread + its sum: only the last thread needs it
+	if(t == nt - 1) total = pre + s;
+#else
+	(void)wtot;
+	pre = 0; total = s;
+#endif
+	long long run = pre;
+	for(int64_t i = lo; i < hi; i++) { const long long x = (long long)in[i]; out[i] = run; run += x; }
+	if(t == nt - 1) out[n] = total;
+}
+KERNEL k_small_scan_i32(const int32_t *in, int64_t n, int64_t *out) { small_scan<int32_t>(in, n, out); }
+KERNEL k_small_scan_i64(const int64_t *in, int64_t n, int64_t *out) { small_scan<int64_t>(in, n, out); }
+
 } // namespace agpu
 
 #endif

@@ -19,6 +19,7 @@ struct agpu_pinbuf
 	char *p = NULL;
 	size_t cap = 0;
 	char *ensure(size_t bytes);
+	bool reserve_exact(size_t bytes);     // grow to exactly `bytes` if smaller (contents are not kept)
 	void release();
 };
 
@@ -353,6 +354,15 @@ inline char *agpu_pinbuf::ensure(size_t bytes)
 {
 	if(bytes + 1 > cap) { agpu::pinned_free(p); cap = (bytes + 1) * 5 / 4 + 64; p = (char*)agpu::pinned_alloc(cap); if(!p) cap = 0; }
 	return p;
+}
+inline bool agpu_pinbuf::reserve_exact(size_t bytes)
+{
+	if(bytes <= cap) return true;
+	agpu::pinned_free(p);
+	cap = bytes;
+	p = (char*)agpu::pinned_alloc(cap);
+	if(!p) { cap = 0; return false; }
+	return true;
 }
 inline void agpu_pinbuf::release() { agpu::pinned_free(p); p = NULL; cap = 0; }
 namespace agpu {

@@ -92,7 +92,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
                "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_batch_upload_packed", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync", "agpu_upload_async",
-               "agpu_batch_results", "agpu_d2h_bytes"]
+               "agpu_batch_results", "agpu_d2h_bytes", "agpu_pinned_match"]
 
 
 def load(lib_path=None):
@@ -133,6 +133,7 @@ def load(lib_path=None):
     L.agpu_batch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Results)]
     L.agpu_d2h_bytes.restype = C.c_int64
     L.agpu_d2h_bytes.argtypes = [C.c_void_p]
+    L.agpu_pinned_match.argtypes = [C.c_void_p, C.c_void_p]
     L.agpu_splices_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P64), C.POINTER(P32)]
     L.agpu_batch_bundle_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.agpu_batch_phase_set.argtypes = [C.c_void_p, C.c_void_p]
@@ -223,6 +224,10 @@ class Context:
 
     def reserve(self, nbytes):
         self.check(self.L.agpu_reserve(self.h, int(nbytes)), "agpu_reserve")
+
+    def pinned_match(self, other):
+        """grow this context's pinned result buffers to the sizes of `other`'s (both idle)"""
+        self.check(self.L.agpu_pinned_match(self.h, other.h), "agpu_pinned_match")
 
     def upload_async(self, on=True):
         """uploads of this context return once queued; the host buffers must outlive the batch's first stage call"""

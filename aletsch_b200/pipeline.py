@@ -128,4 +128,13 @@ class Pipeline:
                     c.reserve(need)
                 except G.AgpuError:
                     break
+        # the same for the pinned result buffers (growing one in the middle of a run synchronises the device)
+        if results:
+            try:
+                for c in self.ctxs[1:]:
+                    self.ctxs[0].pinned_match(c)
+                for c in self.ctxs[1:]:
+                    c.pinned_match(self.ctxs[0])
+            except G.AgpuError:
+                pass
         return out

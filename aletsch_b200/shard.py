@@ -87,3 +87,82 @@ def resolve_groups(ctx, lists, params, keys=None):
     order = sorted(range(len(all_lists)), key=lambda i: (int(all_keys[i]), int(owner[i]), i))
     groups = G.group_resolve(ctx, [all_lists[i] for i in order], params)
     return [[(int(owner[order[i]]), int(all_keys[order[i]])) for i in g] for g in groups]
+
+
+REGION = 1_000_000      # region_partition_length (util/parameters.cc:42)
+
+
+def gather_packed(off, val, keys, extra=None):
+    """all-gather of packed variable-length int32 lists (vectorised: no per-list Python work).
+
+    off[n+1] / val: this rank's lists; keys[n] (int64) and extra[n] (int64, optional) travel with them.  Two collectives: the
+    per-rank (n_lists, n_values) header, then one padded int64 payload [lengths | keys | extra | values].  Returns
+    (off_all, val_all, keys_all, extra_all, owner_rank) concatenated in rank order, identical on every rank, plus the bytes this
+    rank received."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    off = np.asarray(off, np.int64)
+    val = np.asarray(val, np.int32)
+    n = len(off) - 1
+    keys = np.asarray(keys, np.int64)
+    extra = np.zeros(n, np.int64) if extra is None else np.asarray(extra, np.int64)
+    lens = np.diff(off)
+    if world == 1:
+        return off, val, keys, extra, np.zeros(n, np.int32), 0
+    dev = _device()
+    head = torch.tensor([n, int(lens.sum())], dtype=torch.int64, device=dev)
+    heads = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(heads, head)
+    heads = [h.cpu().numpy() for h in heads]
+    cap = max(int(3 * h[0] + h[1]) for h in heads)
+    payload = np.concatenate([lens, keys, extra, val.astype(np.int64)])
+    mine = torch.zeros(max(cap, 1), dtype=torch.int64, device=dev)
+    if len(payload):
+        mine[:len(payload)] = torch.from_numpy(payload).to(dev)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    lens_all, keys_all, extra_all, vals_all, owner = [], [], [], [], []
+    for r in range(world):
+        nr, nv = int(heads[r][0]), int(heads[r][1])
+        p = parts[r].cpu().numpy()
+        lens_all.append(p[:nr]); keys_all.append(p[nr:2 * nr]); extra_all.append(p[2 * nr:3 * nr])
+        vals_all.append(p[3 * nr:3 * nr + nv].astype(np.int32))
+        owner.append(np.full(nr, r, np.int32))
+    lens_all = np.concatenate(lens_all)
+    off_all = np.zeros(len(lens_all) + 1, np.int64)
+    np.cumsum(lens_all, out=off_all[1:])
+    return off_all, np.concatenate(vals_all), np.concatenate(keys_all), np.concatenate(extra_all), np.concatenate(owner), int(8 * cap * world)
+
+
+def resolve_region_groups(ctx, off, val, keys, region_key, params):
+    """bundle_group::resolve for a job whose SAMPLES are ingested on different ranks (meta/incubator.cc:461-471: a bundle group
+    holds the bundles of ALL samples of one (chromosome, region, strand)).  Every rank contributes the splice signatures of its
+    own bundles with their global keys (e.g. sample << 32 | bundle-in-sample) and region keys; after ONE all-gather every rank
+    orders the bundles canonically -- (region key, key): the gset order must not depend on the rank count -- and runs the
+    identical agpu_group_resolve_batch on its own GPU.  Returns (keys_sorted, region_sorted, cluster_of, owner_sorted,
+    bytes_received): cluster_of[i] is the cluster of bundle keys_sorted[i] inside its region group."""
+    from . import gpu as G
+    off_all, val_all, keys_all, reg_all, owner, nbytes = gather_packed(off, val, keys, region_key)
+    order = np.lexsort((keys_all, reg_all))
+    loff, lval = G.reorder_lists(off_all, val_all, order)
+    reg_s = reg_all[order]
+    cuts = np.concatenate([[0], np.nonzero(np.diff(reg_s))[0] + 1, [len(reg_s)]]) if len(reg_s) else np.zeros(1, np.int64)
+    group_off = np.asarray(cuts, np.int32)
+    cl_of, _ = G.group_resolve_arrays(ctx, group_off, loff, lval, params)
+    return keys_all[order], reg_s, cl_of[:len(order)], owner[order], nbytes
+
+
+def bundle_region_keys(batch):
+    """(chromosome, 1 Mb region, strand) key of every bundle of a packed host batch; for unstranded libraries the strand is the
+    majority of the hits' XS tags (bundle_base::compute_strand, rnacore/bundle_base.cc:206-224)"""
+    a = batch.a
+    off = a["bundle_hit_off"]
+    if batch.n_bundles == 0:
+        return np.zeros(0, np.int64)
+    first = np.minimum(off[:-1], max(batch.n_hits - 1, 0))
+    strand = a["strand"][first].astype(np.int64)
+    if batch.n_hits and np.any(strand == ord(".")):
+        cp = np.concatenate([[0], np.cumsum(a["xs"] == ord("+"))])
+        cm = np.concatenate([[0], np.cumsum(a["xs"] == ord("-"))])
+        npl, nmi = cp[off[1:]] - cp[off[:-1]], cm[off[1:]] - cm[off[:-1]]
+        strand = np.where(strand == ord("."), np.where(npl > nmi, ord("+"), np.where(npl < nmi, ord("-"), ord("."))), strand)
+    return (a["bundle_tid"].astype(np.int64) << 40) | ((a["pos"][first].astype(np.int64) // REGION) << 8) | strand

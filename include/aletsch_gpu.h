@@ -307,6 +307,10 @@ typedef struct agpu_results
 	int64_t bytes;
 } agpu_results;
 int agpu_batch_results(agpu_ctx *ctx, agpu_batch *b, uint32_t what, agpu_results *out);
+/* Pinned result buffers belong to the context and grow on demand (a pinned allocation synchronises the device).  A pool of
+ * contexts that share a queue of batches calls this after a warm-up pass so that every context's buffers are at least as large
+ * as the largest any of them has needed: dst's buffers grow to src's sizes, nothing shrinks.  Both contexts must be idle. */
+int agpu_pinned_match(agpu_ctx *dst, agpu_ctx *src);
 /* device -> host bytes the fetches of this context have copied so far */
 int64_t agpu_d2h_bytes(agpu_ctx *ctx);
 
