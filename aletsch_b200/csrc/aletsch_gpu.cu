@@ -137,7 +137,6 @@ struct agpu_batch
 	dbuf<int32_t> order;
 	dbuf<int32_t> tile_owner;              // hit owning the first operation of every tile of CG_TILE CIGAR operations
 	int32_t n_large = 0;
-	int32_t n_pair_big = 0;               // [0, n_pair_big) of `order`: qname table too large for shared memory
 	// regions of the per-bundle qname tables (mate pairing): a power of two >= 1.5 x the bundle's hits
 	dbuf<int64_t> qreg_off;
 	int64_t q_slots = 0;
@@ -160,6 +159,7 @@ struct agpu_batch
 	dbuf<int32_t> pt_d;
 	int64_t n_pts = 0;
 	dbuf<int32_t> spl, hit_nspl, hit_bundle;
+	bool op_tiles = false;                 // this batch's evidence pass runs on the per-operation tile kernels
 	dbuf<u32> ev_s;                        // window position of the start of every BAM_CMATCH block (k_cigar_tile -> k_cov_add_ops)
 	chainset_state hcst, fcst;
 	// segments
@@ -455,12 +455,36 @@ static int check_hit_offsets(agpu_ctx *ctx, agpu_batch *b)
 	return AGPU_OK;
 }
 
+// average CIGAR operations per hit from which the evidence pass switches to the per-operation tile kernels (k_cigar_tile,
+// k_cov_add_tile).  Measured on B200 (profiles/r02_evidence_tiles.md) the thread-per-hit walk is faster at 2 operations per hit
+// (0.67 + 0.40 ms vs 1.16 + 0.75 ms at configs[1]) and still at 35 (6.3 + 3.7 ms vs 8.1 + 4.7 ms at configs[4]): the tile kernels
+// pay ~20 us of barrier-separated phases per tile.  They stay selectable (AGPU_TILE_MIN_OPS=<n>) and are parity-tested.
+static double tile_min_ops()
+{
+	static double v = -1;
+	if(v < 0) { const char *e = getenv("AGPU_TILE_MIN_OPS"); v = e ? atof(e) : 1e30; }
+	return v;
+}
+
 // owner hit of every tile of CG_TILE CIGAR operations (k_tile_owner): once per batch, below the arena mark
 static int batch_tile_owner(agpu_ctx *ctx, agpu_batch *b)
 {
 	const int64_t n_tiles = (b->nc + CG_TILE - 1) / CG_TILE;
+	if(!(b->nh > 0 && (double)b->nc / (double)b->nh >= tile_min_ops())) return AGPU_OK;       // thread-per-hit walks: no tiles
 	if(b->tile_owner.p == NULL) TRY(b->tile_owner.alloc(ctx, n_tiles + 2, true));      // (the compact upload allocates it below its arena mark)
 	LAUNCH_T(ctx, k_tile_owner, b->nh, b->nh, b->h.cigar_off, n_tiles, b->tile_owner.p);
+	return AGPU_OK;
+}
+
+// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64) on the device, when the host did not send it
+static int derive_rpos(agpu_ctx *ctx, agpu_batch *b)
+{
+	if(b->nh > 0 && (double)b->nc / (double)b->nh >= tile_min_ops())
+	{
+		TRY(d2d(ctx, b->in_rpos.p, b->h.pos, sizeof(int32_t) * (size_t)b->nh));
+		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->tile_owner.p, b->in_rpos.p);
+	}
+	else LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
 	return AGPU_OK;
 }
 
@@ -473,14 +497,6 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ho[x + 1] - ho[x] > ho[y + 1] - ho[y]; });
 	b->n_large = 0;
 	while(b->n_large < b->nb && ho[ord[b->n_large] + 1] - ho[ord[b->n_large]] >= LARGE_BUNDLE_HITS) b->n_large++;
-	// bundles whose qname table (a power of two >= 1.5 x hits) does not fit the shared-memory table of k_pair_bundle
-	b->n_pair_big = 0;
-	while(b->n_pair_big < b->nb)
-	{
-		const int64_t ne = ho[ord[b->n_pair_big] + 1] - ho[ord[b->n_pair_big]];
-		if((int64_t)pow2_ceil((u32)std::max<int64_t>(ne + ne / 2, 2)) <= PAIR_SMEM_SLOTS) break;
-		b->n_pair_big++;
-	}
 	// staged through the context's pinned area: asynchronous copies, no stream drain here
 	const size_t need = sizeof(int64_t) * ((size_t)b->nb + 2) + sizeof(int32_t) * ((size_t)b->nb + 2);
 #ifndef AGPU_EMU
@@ -570,8 +586,7 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 		// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), derived on the device
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 		b->h.rpos = b->in_rpos.p;
-		if(d2d(ctx, b->in_rpos.p, b->h.pos, sizeof(int32_t) * (size_t)b->nh) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
-		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->tile_owner.p, b->in_rpos.p);
+		if(derive_rpos(ctx, b) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
 	// the caller's buffers (and the context's staging area) are free again when this returns -- unless the context uploads
@@ -612,8 +627,7 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	{
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 		b->h.rpos = b->in_rpos.p;
-		if(d2d(ctx, b->in_rpos.p, b->h.pos, sizeof(int32_t) * (size_t)b->nh) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
-		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->tile_owner.p, b->in_rpos.p);
+		if(derive_rpos(ctx, b) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }
 	}
 	if(ctx->arena_owner == b) ctx->arena.set_mark();
 	if(stream_sync(ctx) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_CUDA; }      // frees the context's staging area
@@ -761,7 +775,8 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		TRY(b->bord_off.alloc(ctx, nb + 2));
 		LAUNCH_T(ctx, k_bord_off, nb + 1, nb, b->cov_base.p, b->wrank.p, b->bord_off.p);
 		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
-		LAUNCH_B(ctx, k_cov_add_tile, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->nc, b->h.cigar, b->ev_s.p, b->border.p, b->wrank.p, b->diffc.p);
+		if(b->op_tiles) LAUNCH_B(ctx, k_cov_add_tile, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->nc, b->h.cigar, b->ev_s.p, b->border.p, b->wrank.p, b->diffc.p);
+		else LAUNCH_T(ctx, k_cov_add, b->nh, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);
 		// coverage = prefix sum of the differences; segments = borders with positive coverage; prefix sums of len * cov:
@@ -813,10 +828,16 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1, true));
 	dbuf<int32_t> n_spliced;
 	TRY(n_spliced.alloc(ctx, nb + 1, true));
-	// one thread per CIGAR operation, tiles of CG_TILE operations, persistent grid
-	TRY(b->ev_s.alloc(ctx, nc + 1));
-	LAUNCH_B(ctx, k_cigar_tile, std::min<int64_t>((nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 6), 256, b->h, nc, b->tile_owner.p, b->hit_bundle.p, b->b_lpos.p,
-			b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, n_spliced.p, b->ev_s.p, b->err.p);
+	// CIGAR walk.  Default: one thread per hit (k_hit_cigar here, k_cov_add after the borders are ranked).  For batches of long
+	// CIGARs (AGPU_TILE_MIN_OPS operations per hit on average, default off) the per-operation tile kernels: see k_evidence.h
+	b->op_tiles = nh > 0 && (double)nc / (double)nh >= tile_min_ops();
+	if(b->op_tiles)
+	{
+		TRY(b->ev_s.alloc(ctx, nc + 1));
+		LAUNCH_B(ctx, k_cigar_tile, std::min<int64_t>((nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 6), 256, b->h, nc, b->tile_owner.p, b->hit_bundle.p, b->b_lpos.p,
+				b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, n_spliced.p, b->ev_s.p, b->err.p);
+	}
+	else LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_bundle.p, n_spliced.p, b->err.p);
 	// hcst
 	chainset_state &cs = b->hcst;
 	cs.val = b->spl.p; cs.voff32 = b->h.cigar_off; cs.voff64 = NULL; cs.elem_len = b->hit_nspl.p;

@@ -19,13 +19,19 @@ namespace agpu {
 
 // qname table slot: two 64-bit words, [0] = qname key (QID_EMPTY when free), [1] low half = head of the member list
 // (bundle-local hit index, -1 when empty).  A memset with 0xff initialises both.
-KERNEL k_qid_insert(hits_dev h, const int32_t *hit_bundle, const int64_t *reg_off, u64 *slots, int64_t *hit_qslot, int32_t *next, int *err)
+// Both kernels work on one WAVE of bundles at a time: the hits [hit_lo, hit_hi) of a run of consecutive bundles whose table
+// regions together fit PAIR_WAVE_SLOTS slots (64 MB), at slot_base in the batch's region offsets.  The same 64 MB of table are
+// cleared, filled and read wave after wave, so they live in the 126 MB L2 and the 16-byte slots never travel to DRAM (with
+// one table for the whole batch -- 750 MB at configs[1] -- every slot crossed the DRAM bus three times).
+#define PAIR_WAVE_SLOTS ((int64_t)1 << 22)
+KERNEL k_qid_insert(hits_dev h, int64_t hit_lo, int64_t hit_hi, int64_t slot_base, const int32_t *hit_bundle, const int64_t *reg_off, u64 *slots,
+		int64_t *hit_qslot, int32_t *next, int *err)
 {
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= h.n_hits) return;
+	int64_t i = hit_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= hit_hi) return;
 	int b = hit_bundle[i];
-	int64_t r0 = reg_off[b];
-	u32 mask = (u32)(reg_off[b + 1] - r0) - 1;
+	int64_t r0 = reg_off[b] - slot_base;
+	u32 mask = (u32)(reg_off[b + 1] - reg_off[b]) - 1;
 	u64 key = h.qid[i];
 	if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); hit_qslot[i] = -1; return; }
 	u32 pos = (u32)(mix64(key) >> 11) & mask;
@@ -66,11 +72,11 @@ DEV void pair_group(const hits_dev &h, int64_t h0, const int32_t *m, int n, int3
 // one thread per qname group (the hit at the head of the group's member list) runs the greedy; frgs order is by
 // discoverer index, so which member runs it does not matter
 #define PAIR_LOCAL 8
-KERNEL k_pair(hits_dev h, const int32_t *hit_bundle, const int64_t *hit_qslot, const u64 *slots, const int32_t *next,
+KERNEL k_pair(hits_dev h, int64_t hit_lo, int64_t hit_hi, const int32_t *hit_bundle, const int64_t *hit_qslot, const u64 *slots, const int32_t *next,
 		int32_t *cursor, int32_t *members, int32_t *mate)
 {
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= h.n_hits) return;
+	int64_t i = hit_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= hit_hi) return;
 	int64_t sl = hit_qslot[i];
 	if(sl < 0) return;
 	int b = hit_bundle[i];
@@ -110,102 +116,6 @@ KERNEL k_pair(hits_dev h, const int32_t *hit_bundle, const int64_t *hit_qslot, c
 		m[c + 1] = v;
 	}
 	pair_group(h, h0, m, n, mate);
-}
-
-// ---- the whole of build_fragments for one bundle per CTA: clear the qname table, insert, pair -- one launch, and the table never
-// leaves the chip.  Bundles whose table fits PAIR_SMEM_SLOTS slots (up to 2730 hits) keep it in shared memory; the deeper ones
-// use their region of the global table, which the same CTA clears, fills and reads back to back, i.e. out of L2.  (The former
-// memset + thread-per-hit insert + thread-per-hit pair moved the 16-byte slots through DRAM three times.)
-#define PAIR_SMEM_SLOTS 4096
-
-// qname group whose member list starts at bundle-local hit `li`: the reference's greedy
-DEV void pair_from_head(const hits_dev &h, int b, int64_t h0, int32_t li, const int32_t *next, int32_t *cursor, int32_t *members, int32_t *mate)
-{
-	int32_t x1 = next[h0 + li];
-	if(x1 < 0) return;                       // group of one
-	int32_t x2 = next[h0 + x1];
-	if(x2 < 0)
-	{
-		// the common case, a group of two: members (lo, hi) in index order
-		int32_t lo = li < x1 ? li : x1, hi = li < x1 ? x1 : li;
-		int64_t ia = h0 + lo, ic = h0 + hi;
-		int32_t sum = h.isize[ia] + h.isize[ic];
-		if(sum != 0) return;
-		if(h.pos[ic] == h.mpos[ia]) { mate[ia] = hi; mate[ic] = -2 - lo; }
-		else if(h.pos[ia] == h.mpos[ic]) { mate[ic] = lo; mate[ia] = -2 - hi; }
-		return;
-	}
-	int32_t loc[PAIR_LOCAL];
-	int n = 0;
-	for(int32_t x = li; x >= 0; x = next[h0 + x]) { if(n < PAIR_LOCAL) loc[n] = x; n++; }
-	int32_t *m = loc;
-	if(n > PAIR_LOCAL)
-	{
-		m = members + h0 + atomicAdd(&cursor[b], n);
-		int k = 0;
-		for(int32_t x = li; x >= 0 && k < n; x = next[h0 + x]) m[k++] = x;
-	}
-	// ascending hit index (insertion sort; groups are tiny)
-	for(int a = 1; a < n; a++)
-	{
-		int32_t v = m[a];
-		int c = a - 1;
-		while(c >= 0 && m[c] > v) { m[c + 1] = m[c]; c--; }
-		m[c + 1] = v;
-	}
-	pair_group(h, h0, m, n, mate);
-}
-
-KERNEL k_pair_bundle(const int32_t *order, int32_t n_bundles, hits_dev h, const int64_t *reg_off, u64 *gslots, int use_smem,
-		int32_t *next, int32_t *cursor, int32_t *members, int32_t *mate, int *err)
-{
-#ifndef AGPU_EMU
-	extern __shared__ u64 pair_smem[];
-#else
-	static thread_local u64 pair_smem[2 * PAIR_SMEM_SLOTS];
-#endif
-	for(int bi = blockIdx.x; bi < n_bundles; bi += gridDim.x)
-	{
-		const int b = order[bi];
-		const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
-		const int64_t r0 = reg_off[b];
-		const u32 rs = (u32)(reg_off[b + 1] - r0), mask = rs - 1;
-		u64 *slots = use_smem ? pair_smem : gslots + 2 * r0;
-		for(u32 i = threadIdx.x; i < 2 * rs; i += blockDim.x) slots[i] = QID_EMPTY;
-		for(int64_t i = h0 + threadIdx.x; i < h1; i += blockDim.x) mate[i] = -1;
-		BLOCK_SYNC();
-		for(int64_t i = h0 + threadIdx.x; i < h1; i += blockDim.x)
-		{
-			const u64 key = h.qid[i];
-			if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); next[i] = -1; continue; }
-			u32 pos = (u32)(mix64(key) >> 11) & mask;
-			int64_t sl = -1;
-			for(u32 probe = 0; probe <= mask; probe++)
-			{
-				u64 cur = atomicCAS(&slots[2 * pos], (u64)QID_EMPTY, key);
-				if(cur == QID_EMPTY || cur == key) { sl = pos; break; }
-				pos = (pos + 1) & mask;
-			}
-			if(sl < 0) { atomicAdd(&err[ERR_CAP], 1); next[i] = -1; continue; }
-			next[i] = atomicExch((int32_t*)&slots[2 * sl + 1], (int32_t)(i - h0));
-		}
-		BLOCK_SYNC();
-		for(u32 s = threadIdx.x; s < rs; s += blockDim.x)
-		{
-			// the table was filled with atomics (L2 for the global regions): read it past L1
-#ifndef AGPU_EMU
-			const u64 k0 = use_smem ? slots[2 * s] : __ldcg(&slots[2 * s]);
-			if(k0 == QID_EMPTY) continue;
-			const u64 k1 = use_smem ? slots[2 * s + 1] : __ldcg(&slots[2 * s + 1]);
-#else
-			const u64 k0 = slots[2 * s];
-			if(k0 == QID_EMPTY) continue;
-			const u64 k1 = slots[2 * s + 1];
-#endif
-			pair_from_head(h, b, h0, (int32_t)(u32)(k1 & 0xffffffffULL), next, cursor, members, mate);
-		}
-		BLOCK_SYNC();
-	}
 }
 
 // ---- generic device-wide exclusive scan of 0/1 flags derived from an int array (flag = v[i] >= 0)

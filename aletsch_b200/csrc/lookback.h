@@ -154,48 +154,53 @@ KERNEL k_lb_scan_i64(lb_ctl c, const int64_t *v, int64_t n, int64_t *out)
 	}
 }
 
-// ---- per-bundle sized arrays (a few 10^4 elements): one CTA, no look-back machinery.  Every thread owns a contiguous chunk; the
-// chunk sums are scanned with warp shuffles (two levels), then every thread writes its chunk.
-#define SMALL_SCAN_MAX 65536
+// ---- per-bundle sized arrays (a few 10^4 elements): one CTA of 1024 threads, no look-back machinery.  Thread t owns the
+// elements t, t + 1024, t + 2048, ... (coalesced rows); all of them are loaded into registers up front, so the global-memory
+// latency is paid once; every row is then scanned with warp shuffles and the 32 warp totals, with a running carry.
+#define SMALL_SCAN_ROWS 32
+#define SMALL_SCAN_MAX (SMALL_SCAN_ROWS * 1024)
 template<typename T> DEV void small_scan(const T *in, int64_t n, int64_t *out)
 {
-	SHARED long long wtot[32];
-	const int nt = blockDim.x, t = threadIdx.x;
-	const int64_t chunk = (n + nt - 1) / nt;
-	int64_t lo = t * chunk, hi = lo + chunk;
-	if(lo > n) lo = n;
-	if(hi > n) hi = n;
-	long long s = 0;
-	for(int64_t i = lo; i < hi; i++) s += (long long)in[i];
-	long long pre = 0, total = 0;
 #ifndef AGPU_EMU
-	const int lane = t & 31, w = t >> 5, nw = (nt + 31) >> 5;
-	long long inc = s;
+	__shared__ long long wtot[2][32];
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+	long long v[SMALL_SCAN_ROWS];
+	const int rows = (int)((n + 1023) / 1024);
 #pragma unroll
-	for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
-	if(lane == 31) wtot[w] = inc;
-	__syncthreads();
-	if(w == 0)
+	for(int r = 0; r < SMALL_SCAN_ROWS; r++) { const int64_t i = (int64_t)r * 1024 + t; v[r] = (r < rows && i < n) ? (long long)in[i] : 0; }
+	long long carry = 0;
+#pragma unroll
+	for(int r = 0; r < SMALL_SCAN_ROWS; r++)
 	{
-		long long v = lane < nw ? wtot[lane] : 0, vi = v;
+		if(r >= rows) break;
+		long long inc = v[r];
 #pragma unroll
-		for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, vi, o); if(lane >= o) vi += y; }
-		wtot[lane] = vi - v;                      // exclusive prefix of the warp totals (32 warps at most)
+		for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+		if(lane == 31) wtot[r & 1][w] = inc;
+		__syncthreads();
+		long long x = wtot[r & 1][lane], xi = x;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, xi, o); if(lane >= o) xi += y; }
+		const long long wpre = __shfl_sync(0xffffffffu, xi - x, w), total = __shfl_sync(0xffffffffu, xi, 31);
+		const int64_t i = (int64_t)r * 1024 + t;
+		if(i < n) out[i] = carry + wpre + inc - v[r];
+		carry += total;
 	}
-	__syncthreads();
-	pre = wtot[w] + inc - s;
-	// total = prefix of the last thread + its sum: only the last thread needs it
-	if(t == nt - 1) total = pre + s;
+	if(t == 0) out[n] = carry;
 #else
-	(void)wtot;
-	pre = 0; total = s;
+	if(threadIdx.x != 0) return;
+	long long run = 0;
+	for(int64_t i = 0; i < n; i++) { out[i] = run; run += (long long)in[i]; }
+	out[n] = run;
 #endif
-	long long run = pre;
-	for(int64_t i = lo; i < hi; i++) { const long long x = (long long)in[i]; out[i] = run; run += x; }
-	if(t == nt - 1) out[n] = total;
 }
-KERNEL k_small_scan_i32(const int32_t *in, int64_t n, int64_t *out) { small_scan<int32_t>(in, n, out); }
-KERNEL k_small_scan_i64(const int64_t *in, int64_t n, int64_t *out) { small_scan<int64_t>(in, n, out); }
+#ifndef AGPU_EMU
+#define SMALL_SCAN_KERNEL __global__ void __launch_bounds__(1024)
+#else
+#define SMALL_SCAN_KERNEL KERNEL
+#endif
+SMALL_SCAN_KERNEL k_small_scan_i32(const int32_t *in, int64_t n, int64_t *out) { small_scan<int32_t>(in, n, out); }
+SMALL_SCAN_KERNEL k_small_scan_i64(const int64_t *in, int64_t n, int64_t *out) { small_scan<int64_t>(in, n, out); }
 
 } // namespace agpu
 
