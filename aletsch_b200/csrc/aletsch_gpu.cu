@@ -11,6 +11,7 @@
 #include "k_group.h"
 #include "k_phase.h"
 #include "k_revise.h"
+#include "k_support.h"
 #include "k_unpack.h"
 #include "k_fetch.h"
 
@@ -118,6 +119,27 @@ struct graph_state
 	}
 };
 
+// cross-sample support features (k_support.h): the graphs of all cluster members + combined graphs in one layout, and the result rows
+struct support_state
+{
+	bool built = false;
+	int32_t n_groups = 0, n_members = 0;
+	int64_t n_vert = 0, n_ecap = 0, nnz = 0;
+	dbuf<int64_t> voff, eoff, row_off;
+	dbuf<int32_t> ne, vl, vr, out_off, in_off, in_eid, es, et, count, row_slot;
+	dbuf<double> vwA, vwB, ewA, ewB, abd, loss, row_val;
+	dbuf<uint8_t> aliveB;
+	std::vector<int32_t> ne_host, slot_off_host, slot_sample_host, member_group_host;
+	void release(agpu_ctx *ctx)
+	{
+		voff.release(ctx); eoff.release(ctx); row_off.release(ctx); ne.release(ctx); vl.release(ctx); vr.release(ctx); out_off.release(ctx);
+		in_off.release(ctx); in_eid.release(ctx); es.release(ctx); et.release(ctx); count.release(ctx); row_slot.release(ctx);
+		vwA.release(ctx); vwB.release(ctx); ewA.release(ctx); ewB.release(ctx); abd.release(ctx); loss.release(ctx); row_val.release(ctx);
+		aliveB.release(ctx);
+		built = false; n_groups = n_members = 0; n_vert = n_ecap = nnz = 0;
+	}
+};
+
 struct agpu_batch
 {
 	int32_t nb = 0;
@@ -190,6 +212,7 @@ struct agpu_batch
 	dbuf<int64_t> rv_voff;
 	int64_t rv_nvert = 0;
 
+	support_state sup;
 	// group-level re-bridge (assembler::bridge): the combined bundles of the clusters as a batch of their own
 	agpu_batch *cb = NULL;
 	dbuf<int32_t> g_remap, g_members, g_first;
@@ -280,6 +303,7 @@ void agpu_default_params(agpu_params *p)
 	p->min_grouping_similarity = 0.10;
 	p->max_grouping_similarity = 0.80;
 	p->min_boundary_log_ratio = 2.0;
+	p->max_group_boundary_distance = 10000;
 }
 
 int agpu_create(int device, void *stream, agpu_ctx **out)
@@ -646,6 +670,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	b->phase_built = false; b->n_phase = 0; b->n_phase_val = 0;
 	b->rv_nstart.release(ctx); b->rv_nend.release(ctx); b->rv_addv.release(ctx); b->rv_leave.release(ctx); b->rv_come.release(ctx);
 	b->rv_addw.release(ctx); b->rv_lratio.release(ctx); b->rv_cratio.release(ctx); b->rv_voff.release(ctx); b->revise_built = false;
+	b->sup.release(ctx);
 	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
 	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
 	b->group_pass = false;
@@ -900,6 +925,7 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 #include "abi_group.inc"
 #include "abi_phase.inc"
 #include "abi_revise.inc"
+#include "abi_support.inc"
 #include "abi_packed.inc"
 
 }

@@ -19,11 +19,12 @@ namespace agpu {
 
 // qname table slot: two 64-bit words, [0] = qname key (QID_EMPTY when free), [1] low half = head of the member list
 // (bundle-local hit index, -1 when empty).  A memset with 0xff initialises both.
-// Both kernels work on one WAVE of bundles at a time: the hits [hit_lo, hit_hi) of a run of consecutive bundles whose table
-// regions together fit PAIR_WAVE_SLOTS slots (64 MB), at slot_base in the batch's region offsets.  The same 64 MB of table are
-// cleared, filled and read wave after wave, so they live in the 126 MB L2 and the 16-byte slots never travel to DRAM (with
-// one table for the whole batch -- 750 MB at configs[1] -- every slot crossed the DRAM bus three times).
-#define PAIR_WAVE_SLOTS ((int64_t)1 << 22)
+// Both kernels work on one WAVE of bundles at a time: the hits [hit_lo, hit_hi) of a run of consecutive bundles, whose table
+// regions start at slot_base in the batch's region offsets.  Default: ONE wave, one table for the whole batch.  With
+// AGPU_PAIR_WAVE_SLOTS=<n> (e.g. 4194304 = 64 MB of slots) the same table is cleared, filled and read wave after wave and stays
+// in the 126 MB L2, so the 16-byte slots never travel to DRAM (one table for the whole batch, 750 MB at configs[1], crosses the
+// DRAM bus three times).  Measured on B200 at configs[1]: 13 waves 0.78 + 0.61 ms, one wave 0.62 + 0.43 ms -- the launch tails of
+// 26 short kernels cost more than the DRAM traffic they save, so the waves are off by default (profiles/r02_notes.md).
 KERNEL k_qid_insert(hits_dev h, int64_t hit_lo, int64_t hit_hi, int64_t slot_base, const int32_t *hit_bundle, const int64_t *reg_off, u64 *slots,
 		int64_t *hit_qslot, int32_t *next, int *err)
 {

@@ -23,7 +23,7 @@ class Params(C.Structure):
                 ("insertsize_high", C.c_int32), ("max_group_size", C.c_int32), ("max_num_junctions_to_combine", C.c_int32),
                 ("min_subregion_overlap", C.c_double), ("min_guaranteed_edge_weight", C.c_double),
                 ("min_grouping_similarity", C.c_double), ("max_grouping_similarity", C.c_double),
-                ("min_boundary_log_ratio", C.c_double)]
+                ("min_boundary_log_ratio", C.c_double), ("max_group_boundary_distance", C.c_int32)]
 
 
 P32 = C.POINTER(C.c_int32)
@@ -70,6 +70,11 @@ class Results(C.Structure):
 RESULT_EVIDENCE, RESULT_FRAGMENTS, RESULT_GRAPH, RESULT_CLUSTERS, RESULT_BRIDGES, RESULT_ALL = 1, 2, 4, 8, 16, 31
 
 
+class SupportView(C.Structure):
+    _fields_ = [("n_graphs", C.c_int32), ("vert_off", P64), ("loss", PF), ("edge_off", P64), ("edge", P32), ("abd", PF),
+                ("sample_off", P64), ("sample", P32), ("sample_abd", PF)]
+
+
 class ReviseView(C.Structure):
     _fields_ = [("edge_off", P64), ("edge", P32), ("edge_w", PF), ("vert_off", P64), ("unbridge", P32), ("unbridge_ratio", PF),
                 ("n_edges", C.c_int64), ("n_vertices", C.c_int64)]
@@ -92,7 +97,8 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_bridge_fetch", "agpu_batch_counts", "agpu_similarity", "agpu_profile_enable", "agpu_profile_reset",
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
                "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_batch_upload_packed", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync", "agpu_upload_async",
-               "agpu_batch_results", "agpu_d2h_bytes", "agpu_pinned_match"]
+               "agpu_batch_results", "agpu_d2h_bytes", "agpu_pinned_match",
+               "agpu_batch_group_support", "agpu_support_fetch"]
 
 
 def load(lib_path=None):
@@ -141,6 +147,8 @@ def load(lib_path=None):
     L.agpu_batch_revise.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params)]
     L.agpu_revise_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(ReviseView)]
     L.agpu_batch_group_bridge.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params)]
+    L.agpu_batch_group_support.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params)]
+    L.agpu_support_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SupportView)]
     L.agpu_group_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EvidenceView), C.POINTER(ChainsetView), C.POINTER(GraphView), C.POINTER(P32)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.agpu_group_resolve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
@@ -163,6 +171,7 @@ def default_params(**kw):
     p.min_subregion_overlap, p.min_guaranteed_edge_weight = 1.5, 0.01
     p.min_grouping_similarity, p.max_grouping_similarity = 0.10, 0.80
     p.min_boundary_log_ratio = 2.0
+    p.max_group_boundary_distance = 10000
     for k, v in kw.items():
         setattr(p, k, v)
     return p
@@ -500,6 +509,44 @@ class Batch:
         self._groups = [list(map(int, x)) for x in groups]
         self.ctx.check(self.ctx.L.agpu_batch_group_bridge(self.ctx.h, self.h, len(groups), off.ctypes.data, mem.ctypes.data, C.byref(p)),
                        "agpu_batch_group_bridge")
+
+    def group_support(self, groups, p, fetch=True):
+        """the cross-sample support features of assembler::assemble(vector<bundle*>) over clusters of bundles (lists of bundle
+        indices in the reference's gv order).  Returns, per cluster, a dict in the oracle's naming (tests/orclib.py): m<k>_sup_* for
+        member k, x_sup_* for the combined graph."""
+        off = np.zeros(len(groups) + 1, np.int32)
+        for i, grp in enumerate(groups):
+            off[i + 1] = off[i] + len(grp)
+        mem = np.ascontiguousarray(np.concatenate([np.asarray(x, np.int32) for x in groups]) if groups else np.zeros(1, np.int32), np.int32)
+        self.ctx.check(self.ctx.L.agpu_batch_group_support(self.ctx.h, self.h, len(groups), off.ctypes.data, mem.ctypes.data, C.byref(p)),
+                       "agpu_batch_group_support")
+        if not fetch:
+            return None
+        v = SupportView()
+        self.ctx.check(self.ctx.L.agpu_support_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_support_fetch")
+        G = int(v.n_graphs)
+        vo, eo = _arr(v.vert_off, G + 1, np.int64), _arr(v.edge_off, G + 1, np.int64)
+        V, E = (int(vo[G]), int(eo[G])) if G else (0, 0)
+        loss, edge, abd = _arr(v.loss, 4 * V, np.float64), _arr(v.edge, 3 * E), _arr(v.abd, E, np.float64)
+        so = _arr(v.sample_off, E + 1, np.int64)
+        nnz = int(so[E]) if E else 0
+        smp, sabd = _arr(v.sample, nnz), _arr(v.sample_abd, nnz, np.float64)
+        nm = int(off[-1])
+
+        def rows(g, pre):
+            a, b, x, y = int(eo[g]), int(eo[g + 1]), int(vo[g]), int(vo[g + 1])
+            r0, r1 = (int(so[a]), int(so[b])) if b > a else (0, 0)
+            return {pre + "sup_edge": edge[3 * a:3 * b], pre + "sup_abd": abd[a:b], pre + "sup_loss": loss[4 * x:4 * y],
+                    pre + "sup_off": (so[a:b + 1] - so[a]).astype(np.int32), pre + "sup_sample": smp[r0:r1], pre + "sup_sabd": sabd[r0:r1],
+                    pre + "sup_set_off": (so[a:b + 1] - so[a]).astype(np.int32), pre + "sup_set": smp[r0:r1]}
+        out = []
+        for i, grp in enumerate(groups):
+            d = {}
+            for k in range(len(grp)):
+                d.update(rows(int(off[i]) + k, "m%d_" % k))
+            d.update(rows(nm + i, "x_"))
+            out.append(d)
+        return out
 
     def fetch_group(self):
         """per cluster of the last group_bridge: dict with the oracle's cb_* arrays (tests/orclib.py naming) + combine_order"""

@@ -6,6 +6,7 @@ stream computes, another stream's host->device copy is in flight on the copy eng
 batch i+1 hides behind the kernels of batch i.  The ABI is re-entrant across contexts."""
 import os
 import threading
+import time
 
 from . import gpu as G
 
@@ -16,6 +17,8 @@ class Pipeline:
         (agpu_upload_async) before it runs the stages of the current one, so its copy hides behind its own kernels too."""
         self.n_threads = max(1, n_streams)
         self.prefetch = prefetch
+        # AGPU_PIPE_TRACE=1: wall times of every phase of every sub-batch (upload, stages, results, free) in self.trace
+        self.trace = [] if os.environ.get("AGPU_PIPE_TRACE") else None
         self.ctxs = [G.Context(device, lib_path=lib_path) for _ in range(self.n_threads * (2 if prefetch else 1))]
         if prefetch:
             for c in self.ctxs:
@@ -63,9 +66,15 @@ class Pipeline:
                 nxt[0] += 1
             return i if i < len(views) and not errs else None
 
+        tr = self.trace
+
         def begin(ctx, i):
             v, keep = views[i]
-            return ctx.adopt(v, keepalive=keep) if resident else ctx.upload(v, keepalive=keep)
+            t0 = time.perf_counter()
+            bt = ctx.adopt(v, keepalive=keep) if resident else ctx.upload(v, keepalive=keep)
+            if tr is not None:
+                tr.append((i, "upload", threading.get_ident(), t0, time.perf_counter()))
+            return bt
 
         def work(mine):
             pending = cur = None
@@ -82,16 +91,24 @@ class Pipeline:
                         pending = (j, begin(mine[1 - turn], j)) if j is not None else None
                     i, bt = cur
                     try:
+                        t0 = time.perf_counter()
                         bt.bridge_all(params)
+                        t1 = time.perf_counter()
                         cnt = None if consume else bt.counts()
                         res = bt.results(results) if results else None
+                        if tr is not None:
+                            tr.append((i, "stages", threading.get_ident(), t0, t1))
+                            tr.append((i, "results", threading.get_ident(), t1, time.perf_counter()))
                         if consume:
                             out[i] = consume(i, bt, res)
                         else:
                             out[i] = cnt
                             out[i]["d2h_bytes"] = int(res.bytes) if res is not None else 0
                     finally:
+                        t0 = time.perf_counter()
                         bt.free()
+                        if tr is not None:
+                            tr.append((i, "free", threading.get_ident(), t0, time.perf_counter()))
                         cur = None
                     if len(mine) > 1:
                         cur, pending, turn = pending, None, 1 - turn

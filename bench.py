@@ -424,6 +424,10 @@ def run_ours(args):
     assert sum(r["hits"] for r in res) == n_hits * args.steps and sum(r["bridged"] for r in res) == counts["bridged"] * args.steps, "pipelined result differs"
     # one more pass, untimed: how long the reference-side adapter input (graph view) of every sub-batch takes to rebuild is the
     # host's business (integration/adapter.cc); here only the device -> host part is timed.  Per-view split of the traffic:
+    if pipe.trace is not None:
+        t00 = min(x[3] for x in pipe.trace[-4 * len(views) * args.steps:])
+        for i, what, tid, a, b in pipe.trace[-4 * len(views) * args.steps:]:
+            log("[trace] sub-batch %2d %-8s thread %x  %8.2f -> %8.2f ms (%7.2f)" % (i, what, tid & 0xffff, 1e3 * (a - t00), 1e3 * (b - t00), 1e3 * (b - a)))
     pipe.close()
 
     # max over ranks, totals over ranks
@@ -442,7 +446,7 @@ def run_ours(args):
         # dominant kernel by accumulated device time
         total_k = sum(v[0] for v in prof.values())
         top = sorted(prof.items(), key=lambda kv: -kv[1][0])
-        for name, (ms, cnt) in top[:16]:
+        for name, (ms, cnt) in top[:48]:
             log("[bench] kernel %-26s %9.3f ms/step  (%d launches/step, %.1f%% of kernel time)" %
                 (name, ms / steps, cnt // steps, 100 * ms / max(total_k, 1e-9)))
         # bridged pairs / time of stage 4 + update = the bridging kernels' accumulated time (rank 0's batch)

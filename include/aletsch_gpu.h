@@ -74,6 +74,7 @@ typedef struct agpu_params
 	double min_grouping_similarity;        /* -s, 0.10 */
 	double max_grouping_similarity;        /* 0.80 */
 	double min_boundary_log_ratio;         /* 2.0 (identify_boundaries, util/parameters.cc:82) */
+	int32_t max_group_boundary_distance;   /* 10000 (group_start_boundaries / group_end_boundaries, util/parameters.cc:77) */
 } agpu_params;
 
 #define AGPU_MAX_DP_SOLUTIONS 16
@@ -401,6 +402,40 @@ int agpu_batch_group_bridge(agpu_ctx *ctx, agpu_batch *b, int32_t n_groups, cons
  * the members (flattened like group_bundles).  Any of the outputs may be NULL. */
 int agpu_group_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_evidence_view *cev, agpu_chainset_view *cfcst, agpu_graph_view *cgr,
 		const int32_t **combine_order);
+
+/* ---- cross-sample support features: the support passes of assembler::assemble(vector<bundle*>) (meta/assembler.cc:177-373) ----
+ * For every cluster (same layout as agpu_batch_group_bridge; members in the order of the reference's `gv`; bundle_sample is
+ * required): the members' graphs are rebuilt and revised (transform(bd, gr, true), meta/assembler.cc:930-944), the updated
+ * members are combined again and the combined graph gx built (transform(bx, gx, false), :190-203), every edge starts with its
+ * own sample and weight and the junctions are entered into the cluster's junction -> samples map (:205-293); then, member by
+ * member in order: junction_support (:375-417), and against every member j of the cluster start_end_support (:678-779),
+ * non_splicing_support (:419-462) and boundary_extend for the three position types (:781-880), then the same against gx; gx
+ * itself collects start_end / non_splicing support from every member and finally its junction support (:296-330).
+ * ORDER: the reference assembles member k right after its own round, and assemble(gr, ps, sid) (:1075-1134) regroups the start /
+ * end boundaries of k's graph (group_start_boundaries / group_end_boundaries, rnacore/graph_reviser.cc:916-1066) -- so the
+ * members after k see k's graph regrouped; that is reproduced.  It then hands the graph to scallop BY REFERENCE, which
+ * decomposes it in place; what the later members would read out of a decomposed graph is NOT reproduced here (it cannot be
+ * without running scallop between the rounds): a host that needs it calls this once per cluster prefix, or -- equivalently for
+ * member 0 and for every cluster whose members do not overlap -- uses these rows as they are.  The parity tests compare
+ * against the reference's own functions driven in this order (oracle/ref_driver.cc: ref_group_support, ORC_SUPPORT_GROUP_ONLY).
+ * Call after agpu_batch_bridge_all and agpu_batch_group_bridge.  The member graphs of the batch (agpu_graph_fetch,
+ * agpu_revise_fetch) and the combined graphs (agpu_group_fetch) afterwards describe the graphs the rows refer to.
+ * Returns AGPU_ERR_CAPACITY when the (edge x sample) scratch of the clusters passed in one call exceeds 12 GB: split the list. */
+typedef struct agpu_support_view
+{
+	int32_t n_graphs;                   /* the members of all clusters in the caller's order, then one combined graph per cluster */
+	const int64_t *vert_off;            /* [n_graphs + 1] */
+	const double *loss;                 /* [4V] vertex_info::boundary_loss1, 2, 3, boundary_merged_loss */
+	const int64_t *edge_off;            /* [n_graphs + 1]; edges of a graph in (source, target) order, added boundary edges included */
+	const int32_t *edge;                /* [3E] source target edge_info::count */
+	const double *abd;                  /* [E] edge_info::abd */
+	const int64_t *sample_off;          /* [E + 1] */
+	const int32_t *sample;              /* edge_info::samples = keys of edge_info::spAbd, ascending; -1 is the combined graph */
+	const double *sample_abd;           /* edge_info::spAbd values */
+} agpu_support_view;
+int agpu_batch_group_support(agpu_ctx *ctx, agpu_batch *b, int32_t n_groups, const int32_t *group_off, const int32_t *group_bundles,
+		const agpu_params *p);
+int agpu_support_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_support_view *v);
 
 /* The same for MANY bundle groups in one call (one group per (chromosome, region, strand), meta/incubator.cc:461-471):
  * group g owns the lists [group_off[g], group_off[g + 1]).  agpu_similarity_batch fills, for every group, a dense G x G

@@ -379,3 +379,75 @@ def compare_phase_set(ctx, batch, checker, gp, op, stats=None):
     if stats is not None:
         stats["phase_count"] = total
     return bad
+
+
+def checker_group_support(chk, batch, op, g):
+    """the checker's side of the cross-sample support features for one cluster: per-bundle bridging, the group pass, then
+    <prefix>_group_support (reference build: its own member functions in the reference's order, scallop left out --
+    ORC_SUPPORT_GROUP_ONLY; restatement: oracle/restate/support.cc)"""
+    import ctypes as C
+    import os
+    L = chk.lib
+    fs = getattr(L, chk.prefix + "_group_support")
+    fs.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    ss = getattr(L, chk.prefix + "_bundle_set_sample")
+    ss.argtypes = [C.c_void_p, C.c_int]
+    L.orc_bag_new.restype = C.c_void_p
+    hs = []
+    for k in g:
+        h = chk.new_bundle(batch.bundle(k), op)
+        chk.run(h, "fragments")
+        chk.run(h, "bridge")
+        ss(h, int(batch.a["bundle_sample"][k]))
+        hs.append(h)
+    chk.group_bridge(hs)
+    bag = L.orc_bag_new()
+    arr = (C.c_void_p * len(hs))(*hs)
+    old = os.environ.get("ORC_SUPPORT_GROUP_ONLY")
+    os.environ["ORC_SUPPORT_GROUP_ONLY"] = "1"
+    try:
+        rc = fs(arr, len(hs), bag)
+    finally:
+        if old is None:
+            os.environ.pop("ORC_SUPPORT_GROUP_ONLY", None)
+        else:
+            os.environ["ORC_SUPPORT_GROUP_ONLY"] = old
+    d = chk.bag_to_dict(bag)
+    L.orc_bag_free(bag)
+    for h in hs:
+        chk.free_bundle(h)
+    assert rc == 0
+    return d
+
+
+def compare_group_support(ctx, batch, checker, gp, op, groups, stats=None):
+    """agpu_batch_group_support (meta/assembler.cc:177-373: junction / start-end / non-splicing support, boundary_extend) on
+    clusters of bundles against the checker: every member's and the combined graph's edge rows (source, target, count), abd,
+    per-sample abd lists and the four boundary losses per vertex"""
+    bad = []
+    bt = ctx.upload(batch.view(), keepalive=batch)
+    bt.bridge_all(gp)
+    bt.group_bridge(groups, gp)
+    got = bt.group_support(groups, gp)
+    bt.free()
+    edges = multi = 0
+    for gi, g in enumerate(groups):
+        ref = checker_group_support(checker, batch, op, g)
+        d = got[gi]
+        where = "cluster %d %s" % (gi, g)
+        for name in sorted(ref):
+            if name not in d:
+                bad.append("%s: %s missing" % (where, name))
+                continue
+            a, b = ref[name], d[name]
+            if a.dtype == np.float64:
+                cmp_f64(name, a, np.asarray(b, np.float64), where, bad)
+            else:
+                cmp_int(name, a, np.asarray(b, np.int32), where, bad)
+        e = ref["x_sup_edge"].reshape(-1, 3)
+        edges += len(e)
+        multi += int((e[:, 2] > 1).sum())
+    if stats is not None:
+        stats["support_edges"] = edges
+        stats["support_multi"] = multi
+    return bad

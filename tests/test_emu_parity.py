@@ -60,6 +60,24 @@ def test_group_bridge_parity(ctx, checkers, first_round):
             assert stats["group_bridged"] > 0
 
 
+@pytest.mark.parametrize("mode,templates,samples", [(H.SYNTH_PAIRED, 60000, 4), (H.SYNTH_PAIRED, 60000, 6), (H.SYNTH_SINGLE, 30000, 4)])
+def test_group_support_parity(ctx, checkers, mode, templates, samples):
+    """the cross-sample support features of assembler::assemble(vector<bundle*>) (meta/assembler.cc:177-373): junction_support,
+    start_end_support, non_splicing_support and boundary_extend over the members' revised graphs and the combined graph, with the
+    boundary regrouping of the members already assembled -- against the reference's own functions driven in its order (scallop
+    left out) and against the restatement"""
+    assert checkers
+    batch, lt = parity.make_batch(mode, templates, samples=samples)
+    gp, op = parity.params_pair(lt)
+    groups = parity.locus_groups(batch, max_groups=30)
+    assert len(groups) >= 5
+    for name, chk in checkers.items():
+        stats = {}
+        bad = parity.compare_group_support(ctx, batch, chk, gp, op, groups, stats)
+        assert not bad, "%s: %d mismatches, first: %s" % (name, len(bad), bad[:3])
+        assert stats["support_edges"] > 100 and stats["support_multi"] > 0
+
+
 @pytest.mark.parametrize("mode,templates", [(H.SYNTH_PAIRED, 40000), (H.SYNTH_SINGLE, 20000), (H.SYNTH_LONG, 3000)])
 def test_phase_set_parity(ctx, checkers, mode, templates):
     """build_phase_set: phasing paths of bridged fragments and unpaired hits, counted and in phase_set::pmap order"""
