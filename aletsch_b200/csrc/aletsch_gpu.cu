@@ -258,13 +258,13 @@ static int check_err(agpu_ctx *ctx, agpu_batch *b, const char *stage)
 // device-wide exclusive prefix sums, one launch each (lookback.h): out[i] = sum of v[0..i), out[n] = total
 static int lb_scan32(agpu_ctx *ctx, const int32_t *v, int64_t n, int mode, int64_t *out)
 {
-	if(mode == 0 && n <= SMALL_SCAN_MAX) { LAUNCH_B(ctx, k_small_scan_i32, 1, 1024, v, n, out); return AGPU_OK; }
+	if(mode == 0 && n <= SMALL_SCAN_MAX) { LAUNCH_B(ctx, k_small_scan_i32, 1, SMALL_SCAN_THREADS, v, n, out); return AGPU_OK; }
 	LAUNCH_LB(ctx, k_lb_scan_i32, (n + 1 + LB_TILE - 1) / LB_TILE, v, n, mode, out);
 	return AGPU_OK;
 }
 static int lb_scan64(agpu_ctx *ctx, const int64_t *v, int64_t n, int64_t *out)
 {
-	if(n <= SMALL_SCAN_MAX) { LAUNCH_B(ctx, k_small_scan_i64, 1, 1024, v, n, out); return AGPU_OK; }
+	if(n <= SMALL_SCAN_MAX) { LAUNCH_B(ctx, k_small_scan_i64, 1, SMALL_SCAN_THREADS, v, n, out); return AGPU_OK; }
 	LAUNCH_LB(ctx, k_lb_scan_i64, (n + 1 + LB_TILE - 1) / LB_TILE, v, n, out);
 	return AGPU_OK;
 }
@@ -636,6 +636,7 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	arena_scope input_scope(ctx, b);
 	int rc = d2h(ctx, b->hit_off_host.data(), in->bundle_hit_off, sizeof(int64_t) * (b->nb + 1));
 	if(rc == AGPU_OK) rc = d2h(ctx, b->tid_host.data(), in->bundle_tid, sizeof(int32_t) * b->nb);
+	if(rc == AGPU_OK && in->bundle_sample) { b->sample_host.resize(b->nb); rc = d2h(ctx, b->sample_host.data(), in->bundle_sample, sizeof(int32_t) * b->nb); }
 	if(rc == AGPU_OK) rc = stream_sync(ctx);
 	if(rc == AGPU_OK) rc = check_hit_offsets(ctx, b);
 	if(rc == AGPU_OK) rc = batch_common(ctx, b);

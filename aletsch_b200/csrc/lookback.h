@@ -154,37 +154,44 @@ KERNEL k_lb_scan_i64(lb_ctl c, const int64_t *v, int64_t n, int64_t *out)
 	}
 }
 
-// ---- per-bundle sized arrays (a few 10^4 elements): one CTA of 1024 threads, no look-back machinery.  Thread t owns the
-// elements t, t + 1024, t + 2048, ... (coalesced rows); all of them are loaded into registers up front, so the global-memory
-// latency is paid once; every row is then scanned with warp shuffles and the 32 warp totals, with a running carry.
-#define SMALL_SCAN_ROWS 32
-#define SMALL_SCAN_MAX (SMALL_SCAN_ROWS * 1024)
+// ---- per-bundle sized arrays (a few 10^4 elements): one CTA of 512 threads, no look-back machinery.  Thread t owns the
+// elements t, t + 512, t + 1024, ... (coalesced rows); eight rows at a time are loaded into registers, so the global-memory
+// latency is paid once per eight rows; every row is then scanned with warp shuffles and the 16 warp totals, with a running
+// carry.  (A CTA that needs a whole SM's registers would starve next to the long kernels of the other streams of a pipeline.)
+#define SMALL_SCAN_THREADS 512
+#define SMALL_SCAN_RB 8
+#define SMALL_SCAN_MAX 65536
 template<typename T> DEV void small_scan(const T *in, int64_t n, int64_t *out)
 {
 #ifndef AGPU_EMU
 	__shared__ long long wtot[2][32];
-	const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-	long long v[SMALL_SCAN_ROWS];
-	const int rows = (int)((n + 1023) / 1024);
-#pragma unroll
-	for(int r = 0; r < SMALL_SCAN_ROWS; r++) { const int64_t i = (int64_t)r * 1024 + t; v[r] = (r < rows && i < n) ? (long long)in[i] : 0; }
+	const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = SMALL_SCAN_THREADS / 32;
+	const int rows = (int)((n + SMALL_SCAN_THREADS - 1) / SMALL_SCAN_THREADS);
 	long long carry = 0;
-#pragma unroll
-	for(int r = 0; r < SMALL_SCAN_ROWS; r++)
+	int flip = 0;
+	for(int r0 = 0; r0 < rows; r0 += SMALL_SCAN_RB)
 	{
-		if(r >= rows) break;
-		long long inc = v[r];
+		long long v[SMALL_SCAN_RB];
 #pragma unroll
-		for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
-		if(lane == 31) wtot[r & 1][w] = inc;
-		__syncthreads();
-		long long x = wtot[r & 1][lane], xi = x;
+		for(int k = 0; k < SMALL_SCAN_RB; k++) { const int64_t i = (int64_t)(r0 + k) * SMALL_SCAN_THREADS + t; v[k] = (r0 + k < rows && i < n) ? (long long)in[i] : 0; }
 #pragma unroll
-		for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, xi, o); if(lane >= o) xi += y; }
-		const long long wpre = __shfl_sync(0xffffffffu, xi - x, w), total = __shfl_sync(0xffffffffu, xi, 31);
-		const int64_t i = (int64_t)r * 1024 + t;
-		if(i < n) out[i] = carry + wpre + inc - v[r];
-		carry += total;
+		for(int k = 0; k < SMALL_SCAN_RB; k++)
+		{
+			if(r0 + k >= rows) break;
+			long long inc = v[k];
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+			if(lane == 31) wtot[flip][w] = inc;
+			__syncthreads();
+			long long x = lane < nw ? wtot[flip][lane] : 0, xi = x;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1) { long long y = __shfl_up_sync(0xffffffffu, xi, o); if(lane >= o) xi += y; }
+			const long long wpre = __shfl_sync(0xffffffffu, xi - x, w), total = __shfl_sync(0xffffffffu, xi, 31);
+			const int64_t i = (int64_t)(r0 + k) * SMALL_SCAN_THREADS + t;
+			if(i < n) out[i] = carry + wpre + inc - v[k];
+			carry += total;
+			flip ^= 1;
+		}
 	}
 	if(t == 0) out[n] = carry;
 #else
@@ -195,7 +202,7 @@ template<typename T> DEV void small_scan(const T *in, int64_t n, int64_t *out)
 #endif
 }
 #ifndef AGPU_EMU
-#define SMALL_SCAN_KERNEL __global__ void __launch_bounds__(1024)
+#define SMALL_SCAN_KERNEL __global__ void __launch_bounds__(SMALL_SCAN_THREADS)
 #else
 #define SMALL_SCAN_KERNEL KERNEL
 #endif

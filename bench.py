@@ -356,6 +356,7 @@ def run_ours(args):
     stage5 = stage5_gpu(ctx, bts, batch, parts, cfg, args) if not args.no_stage5 else None
     single = len(parts) == 1
     group_leg = group_bridge_gpu(ctx, bt, gp, stage5_gpu.clusters, args) if (stage5 is not None and single and cfg["mode"] == "paired") else None
+    support_leg = support_gpu(ctx, bt, gp, stage5_gpu.clusters, args) if (stage5 is not None and single) else None
     phase_leg = phase_set_gpu(bts, gp, args) if stage5 is not None else None
     for x in bts:
         x.free()
@@ -527,6 +528,8 @@ def run_ours(args):
             out["stage5"] = stage5
         if group_leg is not None:
             out["group_bridge"] = group_leg
+        if support_leg is not None:
+            out["support"] = support_leg
         if phase_leg is not None:
             out["phase_set"] = phase_leg
         if world == 1 and not args.no_cpu_baseline:
@@ -535,6 +538,8 @@ def run_ours(args):
                 out["stage5"]["cpu_baseline"] = stage5_cpu(batch, cfg, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
             if group_leg is not None:
                 out["group_bridge"]["cpu_baseline"] = group_bridge_cpu(batch, cfg, stage5_gpu.clusters, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
+            if support_leg is not None:
+                out["support"]["cpu_baseline"] = support_cpu(batch, cfg, stage5_gpu.clusters, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
         emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -643,6 +648,99 @@ def group_bridge_gpu(ctx, bt, gp, clusters, args):
     members = int(sum(len(c) for c in clusters))
     return {"clusters": len(clusters), "member_bundles": members, "ms": dt * 1e3, "member_bundles_per_sec": members / dt,
             "bridged_pairs_added": extra}
+
+
+def support_gpu(ctx, bt, gp, clusters, args):
+    """the cross-sample support features of assembler::assemble(vector<bundle*>) (meta/assembler.cc:177-373) over the clusters stage
+    5 found, after the per-bundle and the group bridging: members' graphs rebuilt + revised, combined graphs rebuilt, the four
+    support passes (agpu_batch_group_support); host wall clock, the call ends with a stream synchronisation"""
+    import torch
+    if not clusters:
+        return None
+    t_all = []
+    for it in range(1 + max(1, min(args.steps, 3))):
+        bt.reset()
+        bt.bridge_all(gp)
+        bt.group_bridge(clusters, gp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bt.group_support(clusters, gp, fetch=False)
+        torch.cuda.synchronize()
+        if it > 0:
+            t_all.append(time.perf_counter() - t0)
+    rows = bt.group_support(clusters[:64], gp)
+    edges = int(sum(len(d["x_sup_abd"]) for d in rows))
+    multi = int(sum(int((d["x_sup_edge"].reshape(-1, 3)[:, 2] > 1).sum()) for d in rows))
+    dt = float(np.mean(t_all))
+    members = int(sum(len(c) for c in clusters))
+    pairs = int(sum(len(c) * len(c) for c in clusters))
+    return {"clusters": len(clusters), "member_bundles": members, "member_pairs": pairs, "ms": dt * 1e3, "member_bundles_per_sec": members / dt,
+            "member_pairs_per_sec": pairs / dt, "first_64_clusters": {"combined_edges": edges, "edges_with_several_samples": multi}}
+
+
+def support_cpu(batch, cfg, clusters, threads, budget_s):
+    """the reference's own support functions driven in its order (oracle/ref_driver.cc: ref_group_support, scallop left out) on a
+    bounded sample of the same clusters; per-bundle and group bridging done untimed first.  The timed call also rebuilds the
+    members' and the combined graphs, like the device call, and fills the checker's result bag."""
+    import orclib
+    import parity
+    kind = _checker_kind()
+    op = _orc_params(cfg)
+    sizes = np.diff(batch.a["bundle_hit_off"])
+    total = int(sum(int(sizes[k]) for c in clusters for k in c))
+    target_hits = int(60_000 * threads * budget_s)
+    step = max(1, int(np.ceil(total / max(target_hits, 1))))
+    sample = clusters[::step]
+    lock = threading.Lock()
+    nxt = [0]
+    spent = [0.0]
+
+    def worker():
+        chk = orclib.Checker("ref" if kind == "reference" else "orc")
+        L = chk.lib
+        fs = getattr(L, chk.prefix + "_group_support")
+        fs.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+        ss = getattr(L, chk.prefix + "_bundle_set_sample")
+        ss.argtypes = [C.c_void_p, C.c_int]
+        L.orc_bag_new.restype = C.c_void_p
+        while True:
+            with lock:
+                i = nxt[0]
+                nxt[0] += 1
+            if i >= len(sample):
+                return
+            hs = []
+            for k in sample[i]:
+                h = chk.new_bundle(batch.bundle(int(k)), op)
+                chk.run_quiet(h, "fragments")
+                chk.run_quiet(h, "bridge")
+                ss(h, int(batch.a["bundle_sample"][int(k)]))
+                hs.append(h)
+            chk.group_bridge(hs)
+            bag = L.orc_bag_new()
+            arr = (C.c_void_p * len(hs))(*hs)
+            t0 = time.perf_counter()
+            fs(arr, len(hs), bag)
+            dt = time.perf_counter() - t0
+            L.orc_bag_free(bag)
+            for h in hs:
+                chk.free_bundle(h)
+            with lock:
+                spent[0] += dt
+    os.environ["ORC_SUPPORT_GROUP_ONLY"] = "1"
+    try:
+        ths = [threading.Thread(target=worker) for _ in range(threads)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+    finally:
+        os.environ.pop("ORC_SUPPORT_GROUP_ONLY", None)
+    members = int(sum(len(c) for c in sample))
+    pairs = int(sum(len(c) * len(c) for c in sample))
+    wall = spent[0] / threads
+    return {"kind": kind, "cores": threads, "sample": "every %d-th cluster: %d clusters, %d member bundles" % (step, len(sample), members),
+            "member_bundles_per_sec": members / max(wall, 1e-9), "member_pairs_per_sec": pairs / max(wall, 1e-9)}
 
 
 def phase_set_gpu(bts, gp, args):
