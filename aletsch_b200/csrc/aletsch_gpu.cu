@@ -181,6 +181,14 @@ struct agpu_batch
 	dbuf<int32_t> pt_d;
 	int64_t n_pts = 0;
 	dbuf<int32_t> spl, hit_nspl, hit_bundle;
+	// coverage edits of the insert-size preview (agpu_batch_coverage_edit): blocks without coverage, foreign intervals; part of the
+	// batch's INPUT (kept across agpu_batch_reset)
+	dbuf<uint16_t> cov_skip;
+	dbuf<int32_t> cov_ex_bundle, cov_ex_l, cov_ex_r, cov_ex_cnt;
+	int64_t n_cov_extra = 0;
+	// insert-size preview result: fragment length per cluster (INT32_MIN: not counted)
+	dbuf<int32_t> pv_isize;
+	bool preview_built = false;
 	bool op_tiles = false;                 // this batch's evidence pass runs on the per-operation tile kernels
 	dbuf<u32> ev_s;                        // window position of the start of every BAM_CMATCH block (k_cigar_tile -> k_cov_add_ops)
 	chainset_state hcst, fcst;
@@ -410,7 +418,7 @@ int agpu_reserve(agpu_ctx *ctx, int64_t bytes)
 	while(agpu_reserved(ctx) < bytes)
 	{
 		agpu_arena::slab s;
-		s.size = AGPU_SLAB_BYTES;
+		s.size = AGPU_SLAB_BYTES; s.off = 0; s.mark = 0;
 		void *base = NULL;
 		if(cudaMallocAsync(&base, s.size, ctx->stream) != cudaSuccess) { cudaGetLastError(); ctx->last_error = "agpu_reserve: slab allocation failed"; return AGPU_ERR_OOM; }
 		s.base = (char*)base;
@@ -672,6 +680,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	b->rv_nstart.release(ctx); b->rv_nend.release(ctx); b->rv_addv.release(ctx); b->rv_leave.release(ctx); b->rv_come.release(ctx);
 	b->rv_addw.release(ctx); b->rv_lratio.release(ctx); b->rv_cratio.release(ctx); b->rv_voff.release(ctx); b->revise_built = false;
 	b->sup.release(ctx);
+	b->pv_isize.release(ctx); b->preview_built = false;
 	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
 	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
 	b->group_pass = false;
@@ -692,6 +701,7 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_bstrand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
 	b->in_cigar_off.release(ctx); b->in_cigar.release(ctx);
 	b->err.release(ctx); b->order.release(ctx); b->qreg_off.release(ctx); b->tile_owner.release(ctx);
+	b->cov_skip.release(ctx); b->cov_ex_bundle.release(ctx); b->cov_ex_l.release(ctx); b->cov_ex_r.release(ctx); b->cov_ex_cnt.release(ctx);
 	stream_sync(ctx);
 	if(ctx->arena_owner == b) { ctx->arena.rewind(); ctx->arena_owner = NULL; }
 	delete b;
@@ -802,7 +812,7 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		LAUNCH_T(ctx, k_bord_off, nb + 1, nb, b->cov_base.p, b->wrank.p, b->bord_off.p);
 		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
 		if(b->op_tiles) LAUNCH_B(ctx, k_cov_add_tile, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->nc, b->h.cigar, b->ev_s.p, b->border.p, b->wrank.p, b->diffc.p);
-		else LAUNCH_T(ctx, k_cov_add, b->nh, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p);
+		else LAUNCH_T(ctx, k_cov_add, b->nh, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p, b->cov_skip.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);
 		// coverage = prefix sum of the differences; segments = borders with positive coverage; prefix sums of len * cov:
@@ -856,14 +866,22 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(n_spliced.alloc(ctx, nb + 1, true));
 	// CIGAR walk.  Default: one thread per hit (k_hit_cigar here, k_cov_add after the borders are ranked).  For batches of long
 	// CIGARs (AGPU_TILE_MIN_OPS operations per hit on average, default off) the per-operation tile kernels: see k_evidence.h
-	b->op_tiles = nh > 0 && (double)nc / (double)nh >= tile_min_ops();
+	b->op_tiles = nh > 0 && (double)nc / (double)nh >= tile_min_ops() && b->cov_skip.p == NULL;
 	if(b->op_tiles)
 	{
 		TRY(b->ev_s.alloc(ctx, nc + 1));
 		LAUNCH_B(ctx, k_cigar_tile, std::min<int64_t>((nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 6), 256, b->h, nc, b->tile_owner.p, b->hit_bundle.p, b->b_lpos.p,
 				b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, n_spliced.p, b->ev_s.p, b->err.p);
 	}
-	else LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_bundle.p, n_spliced.p, b->err.p);
+	else LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_bundle.p, n_spliced.p, b->err.p, b->cov_skip.p);
+	if(b->n_cov_extra > 0)
+	{
+		// foreign intervals of the insert-size preview (agpu_batch_coverage_edit): border bits now, weights with the ranked borders
+		b->n_pts = 2 * b->n_cov_extra;
+		TRY(b->pt_g.alloc(ctx, b->n_pts + 1)); TRY(b->pt_d.alloc(ctx, b->n_pts + 1));
+		LAUNCH_T(ctx, k_extra_intervals, b->n_cov_extra, b->n_cov_extra, b->cov_ex_bundle.p, b->cov_ex_l.p, b->cov_ex_r.p, b->cov_ex_cnt.p, b->b_lpos.p,
+				b->b_covhi.p, b->cov_base.p, b->border.p, b->pt_g.p, b->pt_d.p);
+	}
 	// hcst
 	chainset_state &cs = b->hcst;
 	cs.val = b->spl.p; cs.voff32 = b->h.cigar_off; cs.voff64 = NULL; cs.elem_len = b->hit_nspl.p;
@@ -927,6 +945,7 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 #include "abi_phase.inc"
 #include "abi_revise.inc"
 #include "abi_support.inc"
+#include "abi_preview.inc"
 #include "abi_packed.inc"
 
 }

@@ -193,8 +193,10 @@ HD u64 chain_hash(const int32_t *v, int n)
 //   coverage: a border bit at the start and at the end of every BAM_CMATCH block (the +1 / -1 are added by
 //             k_cov_add once the borders have been ranked, see the coverage section below)
 //   splices : (p - len, p) for every inner BAM_CREF_SKIP, written at spl[cigar_off[i] ...]
+//   skip    : optional per-hit mask (insert-size preview, agpu_batch_coverage_edit): bit z set = the hit's z-th BAM_CMATCH
+//             operation adds no coverage
 KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
-		int32_t *spl, int32_t *hit_nspl, const int32_t *hit_bundle, int32_t *n_spliced, int *err)
+		int32_t *spl, int32_t *hit_nspl, const int32_t *hit_bundle, int32_t *n_spliced, int *err, const uint16_t *skip)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
@@ -202,7 +204,8 @@ KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u
 	int64_t base = cov_base[b] - (int64_t)b_lpos[b];
 	u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
 	int32_t p = h.pos[i];
-	int ns = 0;
+	int ns = 0, z = 0;
+	const u32 sk = skip ? skip[i] : 0u;
 	int32_t *out = spl + c0;
 	for(u32 k = c0; k < c1; k++)
 	{
@@ -212,7 +215,9 @@ KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u
 		if(op == 0)                                            // BAM_CMATCH
 		{
 			int64_t s = base + p - (int32_t)len, e = base + p;
-			if(len > 0)
+			const bool skipped = z < 16 && ((sk >> z) & 1u);
+			z++;
+			if(len > 0 && !skipped)
 			{
 				atomicOr(&border[s >> 5], 1u << (s & 31));
 				atomicOr(&border[e >> 5], 1u << (e & 31));
@@ -587,7 +592,7 @@ KERNEL k_bord_off(int32_t nb, const int64_t *cov_base, const u32 *wrank, int64_t
 // one thread per hit: +1 at the start and -1 at the end of every BAM_CMATCH block (bundle_base::add_intervals,
 // rnacore/bundle_base.cc:106-158: only op M adds coverage)
 KERNEL k_cov_add(hits_dev h, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, const u32 *border,
-		const u32 *wrank, int32_t *diffc)
+		const u32 *wrank, int32_t *diffc, const uint16_t *skip)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
@@ -595,12 +600,16 @@ KERNEL k_cov_add(hits_dev h, const int32_t *hit_bundle, const int32_t *b_lpos, c
 	int64_t base = cov_base[b] - (int64_t)b_lpos[b];
 	u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
 	int32_t p = h.pos[i];
+	int z = 0;
+	const u32 sk = skip ? skip[i] : 0u;
 	for(u32 k = c0; k < c1; k++)
 	{
 		u32 c = h.cigar[k];
 		u32 op = c & 0xf, len = c >> 4;
 		if((0x3C1A7 >> (op << 1)) & 2) p += (int32_t)len;
-		if(op == 0 && len > 0)
+		const bool skipped = op == 0 && z < 16 && ((sk >> z) & 1u);
+		if(op == 0) z++;
+		if(op == 0 && len > 0 && !skipped)
 		{
 			atomicAdd(&diffc[border_rank(border, wrank, base + p - (int32_t)len)], 1);
 			atomicAdd(&diffc[border_rank(border, wrank, base + p)], -1);
@@ -1096,7 +1105,30 @@ KERNEL k_cov_add_tile(int64_t n_ops, const u32 *cigar, const u32 *ev_s, const u3
 	}
 }
 
+// extra coverage intervals of a bundle (insert-size preview: runs of earlier bundles flushed into this one): clipped to the bundle's
+// window [lpos, covhi], a border bit at either end and a weighted point each (k_cov_add_points adds them by rank); intervals that
+// miss the window get weight 0
+KERNEL k_extra_intervals(int64_t n, const int32_t *ex_bundle, const int32_t *ex_l, const int32_t *ex_r, const int32_t *ex_cnt, const int32_t *b_lpos,
+		const int32_t *b_covhi, const int64_t *cov_base, u32 *border, int64_t *pt_g, int32_t *pt_d)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const int b = ex_bundle[i];
+	int32_t l = ex_l[i], r = ex_r[i];
+	if(l < b_lpos[b]) l = b_lpos[b];
+	if(r > b_covhi[b]) r = b_covhi[b];
+	pt_g[2 * i] = cov_base[b]; pt_g[2 * i + 1] = cov_base[b];
+	pt_d[2 * i] = 0; pt_d[2 * i + 1] = 0;
+	if(l >= r) return;
+	const int64_t s = cov_base[b] + (l - b_lpos[b]), e = cov_base[b] + (r - b_lpos[b]);
+	atomicOr(&border[s >> 5], 1u << (s & 31));
+	atomicOr(&border[e >> 5], 1u << (e & 31));
+	pt_g[2 * i] = s; pt_d[2 * i] = ex_cnt[i];
+	pt_g[2 * i + 1] = e; pt_d[2 * i + 1] = -ex_cnt[i];
+}
+
 } // namespace agpu
+
 
 
 

@@ -29,18 +29,21 @@ struct agpu_pinbuf
 // cross-stream reuse dependencies of the shared pool.  Individual frees are no-ops; the arena rewinds at batch reset / free.
 struct agpu_arena
 {
-	struct slab { char *base; size_t size; };
+	// First fit over all slabs: a request goes to the first slab with room for it, so the tail a large request could not use is
+	// still filled by the smaller ones that follow, and a batch whose big arrays are a little larger than the previous batch's
+	// does not strand the slabs sized for those (a strictly forward-moving cursor did: the pool's contexts kept adding slabs
+	// until the device was full).
+	struct slab { char *base; size_t size; size_t off; size_t mark; };
 	std::vector<slab> slabs;
-	size_t cur = 0, off = 0;
-	size_t mark_cur = 0, mark_off = 0;       // end of the batch's uploaded inputs: a reset rewinds to here, a free to 0
 	bool contains(const void *p) const
 	{
 		for(size_t k = 0; k < slabs.size(); k++) if((const char*)p >= slabs[k].base && (const char*)p < slabs[k].base + slabs[k].size) return true;
 		return false;
 	}
-	void set_mark() { mark_cur = cur; mark_off = off; }
-	void rewind_to_mark() { cur = mark_cur; off = mark_off; }
-	void rewind() { cur = 0; off = 0; mark_cur = 0; mark_off = 0; }
+	// end of the batch's uploaded inputs: a reset rewinds to here, a free to 0
+	void set_mark() { for(size_t k = 0; k < slabs.size(); k++) slabs[k].mark = slabs[k].off; }
+	void rewind_to_mark() { for(size_t k = 0; k < slabs.size(); k++) slabs[k].off = slabs[k].mark; }
+	void rewind() { for(size_t k = 0; k < slabs.size(); k++) slabs[k].off = slabs[k].mark = 0; }
 };
 
 struct agpu_ctx
@@ -151,32 +154,31 @@ inline void *arena_alloc(agpu_ctx *ctx, size_t bytes)
 {
 	agpu_arena &a = ctx->arena;
 	bytes = (bytes + 255) & ~(size_t)255;
-	while(true)
+	for(size_t k = 0; k < a.slabs.size(); k++)
+		if(a.slabs[k].off + bytes <= a.slabs[k].size) { void *p = a.slabs[k].base + a.slabs[k].off; a.slabs[k].off += bytes; return p; }
+	agpu_arena::slab s;
+	// an oversize request gets a slab of its own with 1/8 of headroom, rounded to 256 MB: the next batch's array of the same kind
+	// is rarely exactly as large
+	s.size = AGPU_SLAB_BYTES;
+	if(bytes > AGPU_SLAB_BYTES) s.size = (bytes + bytes / 8 + ((size_t)1 << 28) - 1) & ~(((size_t)1 << 28) - 1);
+	s.off = 0; s.mark = 0;
+	void *base = NULL;
+	if(cudaMallocAsync(&base, s.size, ctx->stream) != cudaSuccess)
 	{
-		if(a.cur < a.slabs.size())
-		{
-			if(a.off + bytes <= a.slabs[a.cur].size) { void *p = a.slabs[a.cur].base + a.off; a.off += bytes; return p; }
-			a.cur++; a.off = 0;
-			continue;
-		}
-		agpu_arena::slab s;
-		s.size = bytes > AGPU_SLAB_BYTES ? bytes : AGPU_SLAB_BYTES;
-		void *base = NULL;
-		if(cudaMallocAsync(&base, s.size, ctx->stream) != cudaSuccess)
-		{
-			cudaGetLastError();
-			size_t fr = 0, tot = 0, held = 0;
-			cudaMemGetInfo(&fr, &tot);
-			for(size_t k = 0; k < a.slabs.size(); k++) held += a.slabs[k].size;
-			char buf[256];
-			snprintf(buf, sizeof(buf), "arena slab allocation of %zu MB failed: context holds %zu slabs / %zu MB, device free %zu MB of %zu MB",
-					s.size >> 20, a.slabs.size(), held >> 20, fr >> 20, tot >> 20);
-			ctx->last_error = buf;
-			return NULL;
-		}
-		s.base = (char*)base;
-		a.slabs.push_back(s);
+		cudaGetLastError();
+		size_t fr = 0, tot = 0, held = 0;
+		cudaMemGetInfo(&fr, &tot);
+		for(size_t k = 0; k < a.slabs.size(); k++) held += a.slabs[k].size;
+		char buf[256];
+		snprintf(buf, sizeof(buf), "arena slab allocation of %zu MB failed: context holds %zu slabs / %zu MB, device free %zu MB of %zu MB",
+				s.size >> 20, a.slabs.size(), held >> 20, fr >> 20, tot >> 20);
+		ctx->last_error = buf;
+		return NULL;
 	}
+	s.base = (char*)base;
+	s.off = bytes;
+	a.slabs.push_back(s);
+	return s.base;
 }
 inline int dev_alloc_bytes(agpu_ctx *ctx, void **p, size_t bytes, bool zero)
 {

@@ -75,6 +75,10 @@ class SupportView(C.Structure):
                 ("sample_off", P64), ("sample", P32), ("sample_abd", PF)]
 
 
+class PreviewView(C.Structure):
+    _fields_ = [("clu_off", P64), ("isize", P32), ("n_clusters", C.c_int64)]
+
+
 class ReviseView(C.Structure):
     _fields_ = [("edge_off", P64), ("edge", P32), ("edge_w", PF), ("vert_off", P64), ("unbridge", P32), ("unbridge_ratio", PF),
                 ("n_edges", C.c_int64), ("n_vertices", C.c_int64)]
@@ -98,7 +102,7 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
                "agpu_profile_read", "agpu_group_resolve", "agpu_debug_sort_perm", "agpu_similarity_batch", "agpu_group_resolve_batch", "agpu_splices_fetch", "agpu_batch_bundle_counts",
                "agpu_batch_group_bridge", "agpu_group_fetch", "agpu_batch_phase_set", "agpu_phase_fetch", "agpu_batch_revise", "agpu_revise_fetch", "agpu_batch_upload_packed", "agpu_reserved", "agpu_reserve", "agpu_blocking_sync", "agpu_upload_async",
                "agpu_batch_results", "agpu_d2h_bytes", "agpu_pinned_match",
-               "agpu_batch_group_support", "agpu_support_fetch"]
+               "agpu_batch_group_support", "agpu_support_fetch", "agpu_batch_coverage_edit", "agpu_batch_preview", "agpu_preview_fetch"]
 
 
 def load(lib_path=None):
@@ -149,6 +153,9 @@ def load(lib_path=None):
     L.agpu_batch_group_bridge.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params)]
     L.agpu_batch_group_support.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params)]
     L.agpu_support_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(SupportView)]
+    L.agpu_batch_coverage_edit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.agpu_batch_preview.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params)]
+    L.agpu_preview_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(PreviewView)]
     L.agpu_group_fetch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EvidenceView), C.POINTER(ChainsetView), C.POINTER(GraphView), C.POINTER(P32)]
     L.agpu_similarity.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.agpu_group_resolve.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]
@@ -509,6 +516,22 @@ class Batch:
         self._groups = [list(map(int, x)) for x in groups]
         self.ctx.check(self.ctx.L.agpu_batch_group_bridge(self.ctx.h, self.h, len(groups), off.ctypes.data, mem.ctypes.data, C.byref(p)),
                        "agpu_batch_group_bridge")
+
+    def coverage_edit(self, skip=None, extra=None):
+        """agpu_batch_coverage_edit (insert-size preview): per-hit masks of the BAM_CMATCH blocks without coverage, extra intervals"""
+        sk = np.ascontiguousarray(skip, np.uint16) if skip is not None else None
+        ex = [np.ascontiguousarray(x, np.int32) for x in extra] if extra is not None and len(extra[0]) else None
+        self.ctx.check(self.ctx.L.agpu_batch_coverage_edit(self.ctx.h, self.h, sk.ctypes.data if sk is not None and len(sk) else None,
+                                                           len(ex[0]) if ex else 0, *([x.ctypes.data for x in ex] if ex else [None] * 4)),
+                       "agpu_batch_coverage_edit")
+
+    def preview(self, p):
+        """previewer::process for every bundle: (clu_off[NB + 1], isize[C]) -- the fragment length the previewer enters into its
+        histogram per paired-read cluster, INT32_MIN where it enters none"""
+        self._run("preview", p)
+        v = PreviewView()
+        self.ctx.check(self.ctx.L.agpu_preview_fetch(self.ctx.h, self.h, C.byref(v)), "agpu_preview_fetch")
+        return _arr(v.clu_off, self.nb + 1, np.int64), _arr(v.isize, int(v.n_clusters))
 
     def group_support(self, groups, p, fetch=True):
         """the cross-sample support features of assembler::assemble(vector<bundle*>) over clusters of bundles (lists of bundle

@@ -33,6 +33,10 @@ struct packer
 	std::vector<uint32_t> cigar_off{0};
 	std::vector<uint32_t> cigar;
 	int64_t seen = 0;
+	// insert-size preview (packer_preview_add): per bundle the triggering record, per hit the blocks without coverage, extra intervals
+	std::vector<int64_t> pv_event;
+	std::vector<uint16_t> pv_skip;
+	std::vector<int32_t> pv_ex_bundle, pv_ex_l, pv_ex_r, pv_ex_cnt;
 	// region table of the sample added last (sample_profile::start1 / start2 / end1 / start_off, flattened over tid, rid)
 	std::vector<int64_t> reg_off{0}, reg_rec;
 	std::vector<int32_t> reg_start1, reg_start2, reg_end1;
@@ -314,6 +318,194 @@ int packer_infer_library_type(const packer_records *rp, const packer_params *pp,
 	out[0] = lt;
 	out[1] = (spliced > 0 && num_xs * 1.0 / spliced > preview_infer_ratio) ? 1 : 0;
 	out[2] = total; out[3] = spliced; out[4] = num_xs; out[5] = spn; out[6] = first; out[7] = second;
+	return 0;
+}
+
+// ---- insert-size preview: previewer::infer_insertsize (meta/previewer.cc:151-304) --------------------------------------------
+namespace {
+
+struct preview_side
+{
+	// bundle_base as the previewer uses it
+	int32_t tid = -1, rpos = 0;
+	std::vector<int64_t> recs;
+	std::vector<uint8_t> strand;
+	std::vector<uint8_t> nblk;             // BAM_CMATCH operations of every stored hit
+	int32_t last_pos = 0, last_rpos = 0;
+	// interval_buf / interval_cnt (rnacore/bundle_base.h:43-44): never flushed, never cleared by the previewer
+	int32_t buf[10][2], cnt[10];
+	int64_t run_owner[10];                 // serial number of the bundle the buffered run belongs to
+	int run_first[10];                     // index (in recs) of the first hit of the run
+	int64_t serial = 0;                    // serial number of the bundle being filled
+	std::vector<int32_t> ex_l, ex_r, ex_cnt;   // runs of earlier bundles flushed into this one
+	preview_side() { for(int z = 0; z < 10; z++) { buf[z][0] = buf[z][1] = -1; cnt[z] = 0; run_owner[z] = -1; run_first[z] = 0; } }
+	void clear() { tid = -1; rpos = 0; recs.clear(); strand.clear(); nblk.clear(); ex_l.clear(); ex_r.clear(); ex_cnt.clear(); serial++; }
+};
+
+// bundle_base::add_hit_intervals as far as the preview needs it: add_hit + the buffer bookkeeping of add_intervals
+void preview_admit(preview_side &s, const packer_records &r, int64_t i, char strand)
+{
+	if(!s.recs.empty() && s.last_pos == r.pos[i] && s.last_rpos == r.rpos[i]) return;
+	s.recs.push_back(i);
+	s.strand.push_back((uint8_t)strand);
+	s.last_pos = r.pos[i]; s.last_rpos = r.rpos[i];
+	int32_t q = r.rpos[i];
+	if(r.mpos[i] > r.rpos[i] && r.mpos[i] <= r.rpos[i] + 500000) q = r.mpos[i];
+	if(q > s.rpos) s.rpos = q;
+	if(s.tid == -1) s.tid = r.tid[i];
+	int32_t p = r.pos[i];
+	int z = 0;
+	for(uint32_t k = r.cigar_off[i]; k < r.cigar_off[i + 1]; k++)
+	{
+		const uint32_t c = r.cigar[k], op = c & 0xf, len = c >> 4;
+		if((0x3C1A7 >> (op << 1)) & 2) p += (int32_t)len;
+		if(op != 0) continue;
+		const int32_t b0 = p - (int32_t)len;
+		if(z < 10)
+		{
+			if(b0 == s.buf[z][0] && p == s.buf[z][1]) s.cnt[z]++;
+			else
+			{
+				// the buffered run goes into the map of the bundle being filled NOW: its own blocks simply become coverage; a run of
+				// an earlier bundle is a foreign interval
+				if(s.buf[z][0] != -1 && s.buf[z][1] != -1 && s.run_owner[z] != s.serial)
+				{ s.ex_l.push_back(s.buf[z][0]); s.ex_r.push_back(s.buf[z][1]); s.ex_cnt.push_back(s.cnt[z]); }
+				s.buf[z][0] = b0; s.buf[z][1] = p; s.cnt[z] = 1;
+				s.run_owner[z] = s.serial; s.run_first[z] = (int)s.recs.size() - 1;
+			}
+		}
+		z++;
+	}
+	s.nblk.push_back((uint8_t)(z > 255 ? 255 : z));
+}
+
+// previewer::process as far as the host decides it: size limits; the bundle goes to the batch with its skip masks
+void preview_flush(packer &pk, preview_side &s, const packer_records &r, int32_t min_hits, int64_t event, int which, int64_t &added)
+{
+	if((int64_t)s.recs.size() < (int64_t)min_hits || s.recs.size() > 20000 || s.tid < 0) return;
+	const int32_t bundle = (int32_t)pk.b_tid.size();
+	for(size_t k = 0; k < s.recs.size(); k++)
+	{
+		const int64_t i = s.recs[k];
+		pk.pos.push_back(r.pos[i]); pk.rpos.push_back(r.rpos[i]); pk.mpos.push_back(r.mpos[i]); pk.isize.push_back(r.isize[i]);
+		pk.flag.push_back(r.flag[i]); pk.strand.push_back(s.strand[k]); pk.xs.push_back(r.xs[i]); pk.qid.push_back(r.qid[i]);
+		pk.cigar.insert(pk.cigar.end(), r.cigar + r.cigar_off[i], r.cigar + r.cigar_off[i + 1]);
+		pk.cigar_off.push_back((uint32_t)pk.cigar.size());
+		uint16_t mask = 0;
+		for(int z = 0; z < 10; z++)
+			if(s.run_owner[z] == s.serial && (int)k >= s.run_first[z] && s.nblk[k] > z) mask |= (uint16_t)(1u << z);   // still in the buffer
+		pk.pv_skip.push_back(mask);
+	}
+	pk.hit_off.push_back((int64_t)pk.pos.size());
+	pk.b_tid.push_back(s.tid);
+	pk.b_sample.push_back(0);
+	pk.b_side.push_back((uint8_t)which);
+	pk.pv_event.push_back(event);
+	for(size_t x = 0; x < s.ex_l.size(); x++)
+	{ pk.pv_ex_bundle.push_back(bundle); pk.pv_ex_l.push_back(s.ex_l[x]); pk.pv_ex_r.push_back(s.ex_r[x]); pk.pv_ex_cnt.push_back(s.ex_cnt[x]); }
+	added++;
+}
+
+} // namespace
+
+int64_t packer_preview_add(void *pkp, const packer_records *rp, const packer_params *pp, int32_t min_num_hits_in_bundle)
+{
+	packer &pk = *(packer*)pkp;
+	const packer_records &r = *rp;
+	const packer_params &p = *pp;
+	preview_side bb1, bb2;
+	int64_t added = 0;
+	// hits that were given no skip entry by earlier (ordinary) additions keep a zero mask
+	pk.pv_skip.resize(pk.pos.size(), 0);
+	pk.pv_event.resize(pk.b_tid.size(), -1);
+	for(int64_t i = 0; i < r.n; i++)
+	{
+		const uint16_t fl = r.flag[i];
+		const uint32_t nc = r.cigar_off[i + 1] - r.cigar_off[i];
+		if((fl & 0x4) >= 1) continue;
+		if((fl & 0x100) >= 1) continue;
+		if((int64_t)nc > (int64_t)p.max_num_cigar) continue;
+		if((int32_t)r.mapq[i] < p.min_mapping_quality) continue;
+		if(nc < 1) continue;
+		char strand = strand_of(fl, p.library_type);
+		const char xs = (char)r.xs[i];
+		// truncate (meta/previewer.cc:178-189): process() on a closed bundle, bb1 first
+		if(r.tid[i] != bb1.tid || r.pos[i] > bb1.rpos + p.min_bundle_gap) { preview_flush(pk, bb1, r, min_num_hits_in_bundle, i, 0, added); bb1.clear(); }
+		if(r.tid[i] != bb2.tid || r.pos[i] > bb2.rpos + p.min_bundle_gap) { preview_flush(pk, bb2, r, min_num_hits_in_bundle, i, 1, added); bb2.clear(); }
+		// (the `cnt >= max_preview_reads` break needs the device's counts: packer_insertsize_profile replays it over the events)
+		if(p.library_type != AGPU_UNSTRANDED && strand == '+' && xs == '-') continue;
+		if(p.library_type != AGPU_UNSTRANDED && strand == '-' && xs == '+') continue;
+		if(p.library_type != AGPU_UNSTRANDED && strand == '.' && xs != '.') strand = xs;
+		if(p.library_type != AGPU_UNSTRANDED && strand == '+') preview_admit(bb1, r, i, strand);
+		if(p.library_type != AGPU_UNSTRANDED && strand == '-') preview_admit(bb2, r, i, strand);
+		if(p.library_type == AGPU_UNSTRANDED && xs == '.') { preview_admit(bb1, r, i, strand); preview_admit(bb2, r, i, strand); }
+		if(p.library_type == AGPU_UNSTRANDED && xs == '+') preview_admit(bb1, r, i, strand);
+		if(p.library_type == AGPU_UNSTRANDED && xs == '-') preview_admit(bb2, r, i, strand);
+	}
+	// the bundles still open when the file ends are never processed (meta/previewer.cc:206-208)
+	return added;
+}
+
+int packer_preview_view(void *pkp, const int64_t **event, const uint16_t **skip, int64_t *n_extra, const int32_t **ex_bundle,
+		const int32_t **ex_l, const int32_t **ex_r, const int32_t **ex_cnt)
+{
+	packer &pk = *(packer*)pkp;
+	pk.pv_skip.resize(pk.pos.size(), 0);
+	pk.pv_event.resize(pk.b_tid.size(), -1);
+	*event = pk.pv_event.data(); *skip = pk.pv_skip.data();
+	*n_extra = (int64_t)pk.pv_ex_l.size();
+	*ex_bundle = pk.pv_ex_bundle.data(); *ex_l = pk.pv_ex_l.data(); *ex_r = pk.pv_ex_r.data(); *ex_cnt = pk.pv_ex_cnt.data();
+	return 0;
+}
+
+int packer_insertsize_profile(int64_t n_bundles, const int64_t *d_off, const int32_t *d, const int64_t *event, int32_t max_preview_reads,
+		int32_t min_preview_spliced_reads, int32_t *out_i, double *out_d)
+{
+	// the histogram m of previewer::infer_insertsize, filled bundle by bundle until the break (checked once per record, i.e.
+	// after all the bundles one record closed)
+	std::vector<std::pair<int32_t, int> > vv;
+	{
+		std::vector<int32_t> all;
+		int64_t cnt = 0;
+		for(int64_t b = 0; b < n_bundles; )
+		{
+			int64_t e = b;
+			while(e < n_bundles && event[e] == event[b]) e++;
+			for(int64_t x = d_off[b]; x < d_off[e]; x++) all.push_back(d[x]);
+			cnt += d_off[e] - d_off[b];
+			b = e;
+			if(cnt >= max_preview_reads) break;
+		}
+		std::sort(all.begin(), all.end());
+		for(size_t i = 0; i < all.size(); )
+		{
+			size_t j = i;
+			while(j < all.size() && all[j] == all[i]) j++;
+			vv.push_back(std::make_pair(all[i], (int)(j - i)));
+			i = j;
+		}
+	}
+	int total = 0;
+	for(size_t k = 0; k < vv.size(); k++) total += vv[k].second;
+	out_i[0] = total;
+	if(total < min_preview_spliced_reads) return 0;
+	int n = 0;
+	double sx2 = 0, ave = 0;
+	int low = -1, high = -1, median = -1;
+	for(size_t k = 0; k < vv.size(); k++)
+	{
+		n += vv[k].second;
+		if(n >= 0.5 * total && median < 0) median = vv[k].first;
+		ave += vv[k].second * vv[k].first;
+		sx2 += vv[k].second * vv[k].first * vv[k].first;
+		if(low == -1 && n >= 0.005 * total) low = vv[k].first;
+		if(high == -1 && n >= 0.990 * total) high = vv[k].first;
+		if(n >= 0.998 * total) break;
+	}
+	ave = ave * 1.0 / n;
+	out_i[1] = low; out_i[2] = high; out_i[3] = median;
+	out_d[0] = ave;
+	out_d[1] = sqrt((sx2 - n * ave * ave) * 1.0 / n);
 	return 0;
 }
 

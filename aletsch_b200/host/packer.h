@@ -55,6 +55,26 @@ int packer_add_sample_regions(void *pk, const packer_records *r, const packer_pa
 // 2000000, 50000, 100, 0.8.  out[8]: library type, bam_with_xs, reads, spliced, with xs, used, first, second
 int packer_infer_library_type(const packer_records *r, const packer_params *p, int32_t max_preview_reads, int32_t max_preview_spliced_reads,
 		int32_t min_preview_spliced_reads, double preview_infer_ratio, int32_t *out);
+// ---- previewer::infer_insertsize (meta/previewer.cc:151-304): the record loop of the insert-size preview.  Appends to the batch
+// under construction the bundles previewer::process would work on (10 .. 20000 stored hits; both strand streams, in the order of
+// the process() calls) and records what makes the reference's preview bundles differ from ordinary ones:
+//   * previewer never calls add_buf_intervals and bundle_base::clear() does not reset interval_buf (rnacore/bundle_base.cc:106-204):
+//     the last run of identical blocks in each of the ten buffer slots is missing from the bundle's coverage map when process()
+//     looks at it -- skip[h] bit z set = the z-th BAM_CMATCH block of hit h adds no coverage;
+//   * a run left in the buffer is flushed into whichever LATER bundle displaces it; on the same chromosome it lies left of that
+//     bundle and is never looked at, after a chromosome change it can fall inside it -- extra (bundle, l, r, count) intervals.
+// event[b] = index of the record whose arrival triggered process() on bundle b (both streams can share one): the host replays the
+// `cnt >= max_preview_reads` break of the reference with it.  Returns the number of bundles appended.
+int64_t packer_preview_add(void *pk, const packer_records *r, const packer_params *p, int32_t min_num_hits_in_bundle);
+// arrays of the preview bundles appended so far: event[NB], skip[H] (aligned with the batch's hits), extra intervals
+int packer_preview_view(void *pk, const int64_t **event, const uint16_t **skip, int64_t *n_extra, const int32_t **ex_bundle,
+		const int32_t **ex_l, const int32_t **ex_r, const int32_t **ex_cnt);
+// the insert-size profile from the fragment lengths the device found (meta/previewer.cc:214-249): d[] grouped by bundle
+// (d_off[NB + 1], in cluster order, invalid clusters already removed and at most 1000 per bundle), the bundles' events, the
+// break at max_preview_reads.  out_i[4] = insert_total, insertsize_low, insertsize_high, insertsize_median (low / high / median
+// stay untouched, i.e. as passed in, when total < min_preview_spliced_reads); out_d[2] = insertsize_ave, insertsize_std
+int packer_insertsize_profile(int64_t n_bundles, const int64_t *d_off, const int32_t *d, const int64_t *event, int32_t max_preview_reads,
+		int32_t min_preview_spliced_reads, int32_t *out_i, double *out_d);
 // the compact form of a batch for the host -> device link (agpu_batch_packed); the view points into the handle (and, for
 // bundle_hit_off / bundle_tid / bundle_sample / xs / qid, into `in`).  NULL if `in` breaks the packing contract (pos
 // decreasing inside a bundle) or holds an operation the units cannot express (length >= 2^24), or xs is not one of '+', '-', '.'.

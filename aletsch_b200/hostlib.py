@@ -127,6 +127,10 @@ def lib():
         L.packer_regions.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5
         L.packer_add_sample_regions.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
         L.packer_default_params.argtypes = [C.POINTER(PackerParams)]
+        L.packer_preview_add.restype = C.c_int64
+        L.packer_preview_add.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
+        L.packer_preview_view.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 2 + [C.POINTER(C.c_int64)] + [C.POINTER(C.c_void_p)] * 4
+        L.packer_insertsize_profile.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.packer_records_seen.restype = C.c_int64
         L.packer_records_seen.argtypes = [C.c_void_p]
         L.packer_bundle_side.restype = C.POINTER(C.c_uint8)
@@ -343,6 +347,77 @@ def infer_library_type(sample, params, max_preview_reads=2000000, max_preview_sp
     lib().packer_infer_library_type(C.byref(r), C.byref(params), max_preview_reads, max_preview_spliced_reads, min_preview_spliced_reads,
                                     preview_infer_ratio, out.ctypes.data)
     return dict(zip(("library_type", "bam_with_xs", "reads", "spliced", "with_xs", "used", "first", "second"), (int(x) for x in out)))
+
+
+def _records_in(s, keep):
+    r = PackerRecords()
+    r.n = s["n"]
+    for k in ("tid", "pos", "rpos", "mpos", "isize", "flag", "mapq", "xs", "qid", "cigar_off", "cigar"):
+        arr = np.ascontiguousarray(s[k])
+        keep.append(arr)
+        setattr(r, k, arr.ctypes.data)
+    return r
+
+
+def _batch_of(L, pk):
+    v = BatchIn()
+    L.packer_view(pk, C.byref(v))
+    nb, nh, nc = v.n_bundles, v.n_hits, v.n_cigar
+    arr = {"bundle_hit_off": _np(v.bundle_hit_off, nb + 1, np.int64), "bundle_tid": _np(v.bundle_tid, nb, np.int32),
+           "bundle_sample": _np(v.bundle_sample, nb, np.int32),
+           "cigar_off": _np(v.cigar_off, nh + 1, np.uint32), "cigar": _np(v.cigar, nc, np.uint32)}
+    for f, dt in HIT_FIELDS:
+        arr[f] = _np(getattr(v, f), nh, dt)
+    arr["bundle_side"] = _np(L.packer_bundle_side(pk), nb, np.uint8)
+    return PackedBatch(arr)
+
+
+def preview_pack(sample, params, min_num_hits_in_bundle=10):
+    """the record loop of previewer::infer_insertsize (meta/previewer.cc:151-208) over one sample's records: the bundles
+    previewer::process works on, packed, plus what the reference's never-flushed interval buffer does to their coverage maps.
+    Returns (PackedBatch, event[NB], skip[H] uint16, extra = (bundle, l, r, count) int32 arrays)."""
+    L = lib()
+    pk = L.packer_create()
+    try:
+        keep = []
+        r = _records_in(sample, keep)
+        L.packer_preview_add(pk, C.byref(r), C.byref(params), min_num_hits_in_bundle)
+        batch = _batch_of(L, pk)
+        ev, sk, eb, el, er, ec = (C.c_void_p() for _ in range(6))
+        ne = C.c_int64(0)
+        L.packer_preview_view(pk, C.byref(ev), C.byref(sk), C.byref(ne), C.byref(eb), C.byref(el), C.byref(er), C.byref(ec))
+        event = _np(ev.value, batch.n_bundles, np.int64)
+        skip = _np(sk.value, batch.n_hits, np.uint16)
+        extra = tuple(_np(x.value, ne.value, np.int32) for x in (eb, el, er, ec))
+        return batch, event, skip, extra
+    finally:
+        L.packer_destroy(pk)
+
+
+def insertsize_profile(clu_off, isize, event, max_preview_reads=2000000, min_preview_spliced_reads=100):
+    """the tail of previewer::infer_insertsize (meta/previewer.cc:209-249) from the per-cluster fragment lengths of the device
+    (agpu_preview_view): at most 1000 counted clusters per bundle (previewer::process), the break at max_preview_reads, then the
+    percentiles.  Returns dict(insert_total, insertsize_low, insertsize_high, insertsize_median, insertsize_ave, insertsize_std);
+    low / high / median / ave / std are None when fewer than min_preview_spliced_reads fragments were collected."""
+    nb = len(clu_off) - 1
+    valid = isize != np.iinfo(np.int32).min
+    csum = np.concatenate([[0], np.cumsum(valid)])
+    rank = csum[:-1] - np.repeat(csum[clu_off[:-1]], np.diff(clu_off))          # rank of a counted cluster inside its bundle
+    keep = valid & (rank < 1000)
+    kc = np.concatenate([[0], np.cumsum(keep)])
+    d_off = np.ascontiguousarray(kc[clu_off], np.int64)
+    d = np.ascontiguousarray(isize[keep], np.int32)
+    ev = np.ascontiguousarray(event, np.int64)
+    oi = np.full(4, -1, np.int32)
+    od = np.zeros(2, np.float64)
+    lib().packer_insertsize_profile(nb, d_off.ctypes.data, d.ctypes.data if len(d) else None, ev.ctypes.data if nb else None, max_preview_reads,
+                                    min_preview_spliced_reads, oi.ctypes.data, od.ctypes.data)
+    out = {"insert_total": int(oi[0])}
+    ok = oi[0] >= min_preview_spliced_reads
+    out.update({"insertsize_low": int(oi[1]) if ok else None, "insertsize_high": int(oi[2]) if ok else None,
+                "insertsize_median": int(oi[3]) if ok else None, "insertsize_ave": float(od[0]) if ok else None,
+                "insertsize_std": float(od[1]) if ok else None})
+    return out
 
 
 def pack(samples, params, sample_ids=None, chrom_len=None, region_length=1000000, tables=None):

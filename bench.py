@@ -410,6 +410,10 @@ def run_ours(args):
     barrier()
     launches_e2e0 = pipe.launches
     syncs_e2e0 = pipe.syncs
+    if os.environ.get("AGPU_PIPE_PROFILE"):        # diagnosis: per-kernel CUDA-event times inside the pipelined run
+        for c in pipe.ctxs:
+            c.profile(True)
+            c.profile_reset()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     # all K steps' sub-batches go through the stream pool back to back (every step uploads its inputs again and brings its
@@ -425,6 +429,15 @@ def run_ours(args):
     assert sum(r["hits"] for r in res) == n_hits * args.steps and sum(r["bridged"] for r in res) == counts["bridged"] * args.steps, "pipelined result differs"
     # one more pass, untimed: how long the reference-side adapter input (graph view) of every sub-batch takes to rebuild is the
     # host's business (integration/adapter.cc); here only the device -> host part is timed.  Per-view split of the traffic:
+    if os.environ.get("AGPU_PIPE_PROFILE"):
+        acc = {}
+        for c in pipe.ctxs:
+            for name, (ms, cnt) in c.profile_read().items():
+                m = acc.setdefault(name, [0.0, 0])
+                m[0] += ms
+                m[1] += cnt
+        for name, (ms, cnt) in sorted(acc.items(), key=lambda kv: -kv[1][0])[:25]:
+            log("[pipe-profile] %-28s %10.3f ms total  %6d launches  %9.3f ms/launch" % (name, ms, cnt, ms / max(cnt, 1)))
     if pipe.trace is not None:
         t00 = min(x[3] for x in pipe.trace[-4 * len(views) * args.steps:])
         for i, what, tid, a, b in pipe.trace[-4 * len(views) * args.steps:]:

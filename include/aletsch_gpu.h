@@ -403,6 +403,30 @@ int agpu_batch_group_bridge(agpu_ctx *ctx, agpu_batch *b, int32_t n_groups, cons
 int agpu_group_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_evidence_view *cev, agpu_chainset_view *cfcst, agpu_graph_view *cgr,
 		const int32_t **combine_order);
 
+/* ---- insert-size preview: previewer::infer_insertsize (meta/previewer.cc:151-304) ----
+ * The host runs the record loop (aletsch_b200/host/packer.h: packer_preview_add) and uploads the preview bundles like any batch.
+ * Two things make the reference's preview bundles differ from ordinary ones, both consequences of bundle_base::interval_buf
+ * (rnacore/bundle_base.cc:106-204: the previewer never flushes it and clear() does not reset it); agpu_batch_coverage_edit hands
+ * them to the device before the evidence stage:
+ *   skip_mblocks[H]   bit z set: the z-th BAM_CMATCH operation of the hit adds no coverage (it is still in the buffer when
+ *                     previewer::process looks at the bundle); may be NULL
+ *   extra intervals   (bundle, l, r, count): blocks of an earlier bundle flushed into this one's map (matters after a
+ *                     chromosome change only); clipped to the bundle's coverage window
+ * agpu_batch_preview then is previewer::process for every bundle of the batch: build_fragments, graph_builder::build,
+ * graph_cluster with a partition gap of 2, and per paired-read cluster the fragment length the previewer enters into its
+ * histogram (INT32_MIN where it enters none).  The cap of 1000 clusters per bundle, the break at max_preview_reads and the
+ * percentiles are the host's (packer_insertsize_profile). */
+typedef struct agpu_preview_view
+{
+	const int64_t *clu_off;             /* [NB + 1] clusters of bundle b in vector<pereads_cluster> order */
+	const int32_t *isize;               /* [C] bounds[3] - bounds[0] - intron length, or INT32_MIN */
+	int64_t n_clusters;
+} agpu_preview_view;
+int agpu_batch_coverage_edit(agpu_ctx *ctx, agpu_batch *b, const uint16_t *skip_mblocks, int64_t n_extra, const int32_t *extra_bundle,
+		const int32_t *extra_l, const int32_t *extra_r, const int32_t *extra_count);
+int agpu_batch_preview(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p);
+int agpu_preview_fetch(agpu_ctx *ctx, agpu_batch *b, agpu_preview_view *v);
+
 /* ---- cross-sample support features: the support passes of assembler::assemble(vector<bundle*>) (meta/assembler.cc:177-373) ----
  * For every cluster (same layout as agpu_batch_group_bridge; members in the order of the reference's `gv`; bundle_sample is
  * required): the members' graphs are rebuilt and revised (transform(bd, gr, true), meta/assembler.cc:930-944), the updated

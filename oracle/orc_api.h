@@ -106,6 +106,10 @@ int ref_bundle_assemble(void *b, void *bag);
 /* reference build only: previewer::infer_library_type over the same records; "preview" = library_type, bam_with_xs, num_xs, spn */
 int ref_infer_library_type(const orc_records_in *in, const orc_params *prm, int max_preview_reads, int max_preview_spliced_reads,
 		int min_preview_spliced_reads, double preview_infer_ratio, void *bag);
+/* reference build only: previewer::infer_insertsize over the same records; "isize" = insert_total, low, high, median; "isize_d" =
+ * ave, std */
+int ref_infer_insertsize(const orc_records_in *in, const orc_params *prm, int max_preview_reads, int min_preview_spliced_reads,
+		int min_num_hits_in_bundle, void *bag);
 /* Groundwork for SURVEY 8f-3 (nothing in the product implements this step yet).  <P>_bundle_set_sample: sample id of a bundle
  * handle (sample_profile::sample_id).  <P>_group_support: the cross-sample support features of assembler::assemble(vector<bundle*>)
  * (meta/assembler.cc:177-373) on bundles that went through fragments, bridge and group_bridge; member k is dumped at the point

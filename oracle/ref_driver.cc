@@ -758,6 +758,48 @@ int ref_infer_library_type(const orc_records_in *in, const orc_params *prm, int 
 	return sp.library_type;
 }
 
+// previewer::infer_insertsize (meta/previewer.cc:151-304) over the same records through the htslib stand-in: the reference's own
+// record loop, bundle_base (with its never-flushed interval buffer), build_fragments, graph_builder, graph_cluster and histogram.
+// "isize" = insert_total, insertsize_low, insertsize_high, insertsize_median; "isize_d" = insertsize_ave, insertsize_std
+int ref_infer_insertsize(const orc_records_in *in, const orc_params *prm, int max_preview_reads, int min_preview_spliced_reads,
+		int min_num_hits_in_bundle, void *bagp)
+{
+	orc_bag &bag = *(orc_bag*)bagp;
+	parameters cfg;
+	sample_profile sp(0, 1000000);
+	apply_params(prm, cfg, sp);
+	cfg.max_preview_reads = max_preview_reads; cfg.min_preview_spliced_reads = min_preview_spliced_reads;
+	cfg.min_num_hits_in_bundle = min_num_hits_in_bundle;
+	hts_shim_file file;
+	for(int k = 0; k < in->n_chrom; k++)
+	{
+		file.target_name.push_back("chr" + std::to_string(k + 1));
+		file.target_len.push_back((uint32_t)in->chrom_len[k]);
+	}
+	for(int64_t i = 0; i < in->n; i++)
+	{
+		uint32_t c0 = in->cigar_off[i], c1 = in->cigar_off[i + 1];
+		file.records.push_back(hts_shim_make_record(in->tid[i], in->pos[i], in->mapq[i], in->flag[i], in->tid[i], in->mpos[i], in->isize[i],
+				qname_of(in->qid[i]), in->cigar + c0, c1 - c0, (char)in->xs[i], '.', 1, 1, -1));
+	}
+	char name[64];
+	snprintf(name, sizeof(name), "mem:isz:%p", (const void*)in);
+	hts_shim_register(name, file);
+	sp.align_file = name;
+	sp.insert_total = 0;
+	previewer pv(cfg, sp);
+	pv.infer_insertsize();
+	std::vector<int32_t> &o = bag.ints("isize");
+	o.clear();
+	o.push_back(sp.insert_total); o.push_back(sp.insertsize_low); o.push_back(sp.insertsize_high); o.push_back(sp.insertsize_median);
+	std::vector<double> &d = bag.reals("isize_d");
+	d.clear();
+	d.push_back(sp.insertsize_ave); d.push_back(sp.insertsize_std);
+	hts_shim_clear();
+	return sp.insert_total;
+}
+
+
 // generator::resolve + generator::generate (meta/generator.cc:51-227) on an in-memory file behind the htslib stand-in: one
 // region per chromosome that starts at its first record (start_off is a record index in the stand-in's bgzf_seek)
 int ref_generate(const orc_records_in *in, const orc_params *prm, int use_second_alignment, void *bagp)
