@@ -636,6 +636,100 @@ int ref_bundle_assemble(void *b, void *bagp)
 	return (int)bag.reals("trst_cov").size();
 }
 
+// integration/adapter.cc, second half: bundle_base (mmap, splices, hcst, frgs, fcst), vector<pereads_cluster> and
+// vector<bridge_path> rebuilt from the C-ABI views of bundle b, compared field by field with what the reference's own
+// build_fragments + bundle::bridge steps leave (meta/bundle.cc:55-88) on a fresh handle of the same bundle.  Returns the number
+// of differing fields (messages on stderr).
+int ref_adapter_compare_bundle(void *hb, const agpu_evidence_view *ev, const agpu_fragments_view *fr, const agpu_cluster_view *cv,
+		const agpu_bridge_view *bv, int b, int64_t hit_off)
+{
+	ref_handle *h = (ref_handle*)hb;
+	bundle &bd = h->bd;
+	bd.build_fragments();
+	// bundle::bridge with its locals kept
+	splice_graph gr;
+	graph_builder gb(bd, h->cfg, h->sp);
+	gb.build(gr);
+	gr.build_vertex_index();
+	std::vector<pereads_cluster> vc;
+	graph_cluster gc(gr, bd, h->cfg.max_reads_partition_gap, false);
+	gc.build_pereads_clusters(vc);
+	bridge_solver bs(gr, vc, h->cfg, h->sp.insertsize_low, h->sp.insertsize_high);
+	for(size_t k = 0; k < vc.size(); k++)
+	{
+		if(bs.opt[k].type <= 0) continue;
+		bd.update_bridges(vc[k].frlist, bs.opt[k].chain, bs.opt[k].strand);
+	}
+	int bad = 0;
+#define DIFF(cond, ...) do { if(cond) { if(bad < 5) { fprintf(stderr, "adapter_compare_bundle %d: ", b); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } bad++; } } while(0)
+	auto far = [](double x, double y) { return fabs(x - y) > 1e-9 * std::max(fabs(x), 1e-300) && x != y; };
+	// ---- bundle_base
+	bundle_base bb;
+	bb.hits = bd.hits;
+	std::vector<uint8_t> xs(bd.hits.size());
+	for(size_t i = 0; i < bd.hits.size(); i++) xs[i] = (uint8_t)bd.hits[i].xs;
+	DIFF(agpu_adapter_bundle(ev, fr, b, hit_off, xs.data(), bb) != 0, "adapter_bundle failed");
+	DIFF(bb.lpos != bd.lpos || bb.rpos != bd.rpos || bb.strand != bd.strand, "bounds / strand");
+	DIFF(bb.splices != bd.splices, "splices");
+	{
+		SIMI i1 = bd.mmap.begin(), i2 = bb.mmap.begin();
+		int n = 0;
+		for(; i1 != bd.mmap.end() && i2 != bb.mmap.end(); ++i1, ++i2, ++n)
+			DIFF(lower(i1->first) != lower(i2->first) || upper(i1->first) != upper(i2->first) || i1->second != i2->second, "mmap segment %d", n);
+		DIFF(i1 != bd.mmap.end() || i2 != bb.mmap.end(), "mmap length");
+	}
+	auto same_chain_set = [&](const chain_set &a, const chain_set &c, const char *what, bool handles_xs)
+	{
+		DIFF(a.chains.size() != c.chains.size(), "%s groups %d vs %d", what, (int)a.chains.size(), (int)c.chains.size());
+		for(size_t i = 0; i < a.chains.size() && i < c.chains.size(); i++)
+		{
+			DIFF(a.chains[i].size() != c.chains[i].size(), "%s group %d size", what, (int)i);
+			for(size_t j = 0; j < a.chains[i].size() && j < c.chains[i].size(); j++)
+				DIFF(a.chains[i][j].first != c.chains[i][j].first || a.chains[i][j].second != c.chains[i][j].second, "%s chain %d.%d", what, (int)i, (int)j);
+		}
+		DIFF(a.pmap != c.pmap, "%s pmap", what);
+		DIFF(a.hmap.size() != c.hmap.size(), "%s hmap size %d vs %d", what, (int)a.hmap.size(), (int)c.hmap.size());
+		for(std::map<int, AI3>::const_iterator it = a.hmap.begin(); it != a.hmap.end(); ++it)
+		{
+			std::map<int, AI3>::const_iterator jt = c.hmap.find(it->first);
+			DIFF(jt == c.hmap.end(), "%s handle %d missing", what, it->first);
+			if(jt == c.hmap.end()) continue;
+			DIFF(it->second[0] != jt->second[0] || it->second[1] != jt->second[1], "%s handle %d -> %d.%d vs %d.%d", what, it->first,
+					it->second[0], it->second[1], jt->second[0], jt->second[1]);
+			if(handles_xs) DIFF(it->second[2] != jt->second[2], "%s handle %d xs class", what, it->first);
+		}
+	};
+	same_chain_set(bd.hcst, bb.hcst, "hcst", true);
+	same_chain_set(bd.fcst, bb.fcst, "fcst", false);
+	DIFF(bb.frgs != bd.frgs, "frgs");
+	// ---- vector<pereads_cluster>: note the reference's clusters were built BEFORE update_bridges changed frgs; so were the device's
+	std::vector<pereads_cluster> vc2;
+	agpu_adapter_clusters(cv, &ev->hcst, b, vc2);
+	DIFF(vc.size() != vc2.size(), "clusters %d vs %d", (int)vc.size(), (int)vc2.size());
+	for(size_t k = 0; k < vc.size() && k < vc2.size(); k++)
+	{
+		DIFF(vc[k].chain1 != vc2[k].chain1 || vc[k].chain2 != vc2[k].chain2, "cluster %d chains", (int)k);
+		DIFF(vc[k].bounds != vc2[k].bounds || vc[k].extend != vc2[k].extend, "cluster %d bounds / extend", (int)k);
+		DIFF(vc[k].frlist != vc2[k].frlist || vc[k].count != vc2[k].count, "cluster %d frlist / count", (int)k);
+	}
+	// ---- vector<bridge_path>
+	std::vector<bridge_path> opt2;
+	agpu_adapter_bridges(bv, cv, b, opt2);
+	DIFF(bs.opt.size() != opt2.size(), "bridge paths %d vs %d", (int)bs.opt.size(), (int)opt2.size());
+	for(size_t k = 0; k < bs.opt.size() && k < opt2.size(); k++)
+	{
+		const bridge_path &a = bs.opt[k], &c = opt2[k];
+		DIFF(a.type != c.type, "opt %d type %d vs %d", (int)k, a.type, c.type);
+		DIFF(a.strand != c.strand || a.choices != c.choices, "opt %d strand / choices", (int)k);
+		DIFF(far(a.score, c.score), "opt %d score %f vs %f", (int)k, a.score, c.score);
+		DIFF(a.chain != c.chain || a.whole != c.whole, "opt %d chain / whole", (int)k);
+	}
+#undef DIFF
+	return bad;
+}
+
+
+
 // everything scallop reads: the reference's own transform(bd, gr, true) + build_phase_set on the handle's bundle against the
 // graph and phase set the adapter rebuilds from the views, field by field.  Returns the number of differences (first few on
 // stderr); the stub vertices' maxcov, which the reference leaves uninitialised, is not compared.

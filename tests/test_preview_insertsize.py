@@ -95,13 +95,12 @@ def test_interval_buffer_quirk_matters(emu_lib, checkers):
                 bt.coverage_edit(skip, extra)
             clu_off, isize = bt.preview(gp)
             bt.free()
-            res.append(H.insertsize_profile(clu_off, isize, event))
+            res.append((H.insertsize_profile(clu_off, isize, event), isize))
         want = reference_profile(checkers["ref"], s, 2, 1_000_000, op, 2000000, 100, 10)
-        assert res[0]["insert_total"] == int(want["isize"][0]), seed
-        differ += int(res[0] != res[1])
+        assert res[0][0]["insert_total"] == int(want["isize"][0]), seed
+        differ += int(len(res[0][1]) != len(res[1][1]) or not np.array_equal(res[0][1], res[1][1]))
     ctx.close()
-    # (informational when 0: on inputs where the dropped blocks never change a graph the two agree)
-    assert differ >= 0
+    assert differ >= 1          # the dropped blocks change graphs / clusters on this data: the quirk is observable
 
 
 @pytest.mark.gpu
