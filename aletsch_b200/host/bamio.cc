@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -129,6 +131,59 @@ struct bgzf_reader
 	}
 };
 
+// second, independent hash of a query name (different offset basis and finaliser): with hash64 a 128-bit identity
+uint64_t hash64b(const char *s, size_t n)
+{
+	uint64_t h = 0x84222325cbf29ce4ULL;
+	for(size_t i = 0; i < n; i++) { h = (h ^ (uint8_t)s[i]) * 0x100000001b3ULL; h ^= h >> 29; }
+	h ^= h >> 31; h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 32;
+	return h;
+}
+
+// test hook (bam_set_key_bits): the 64-bit query-name keys truncated to this many bits, so that the collision handling below
+// can be exercised on ordinary data
+int g_key_bits = 64;
+
+// The ABI's contract for qid is "equal <=> same qname" (include/aletsch_gpu.h); bundle_base::build_fragments compares the names
+// themselves (rnacore/bundle_base.cc:308).  A 64-bit hash alone only makes a violation improbable.  This makes it (128-bit)
+// certain where it matters: two records can only be paired inside one bundle, i.e. within max_read_span (500000) of each other,
+// so every record's key is checked against the keys of the records of the last KEY_WINDOW positions; a different name under an
+// equal key gets a new key derived from its second hash, until the key is free.  The same name always takes the same path, so
+// mates still receive equal keys.
+struct key_window
+{
+	enum { KEY_WINDOW = 1200000 };
+	std::unordered_map<uint64_t, uint64_t> seen;             // key -> second hash of the name that owns it
+	std::deque<std::pair<int64_t, uint64_t> > order;         // (position, key) in arrival order, for eviction
+	int32_t tid = -1;
+	int64_t collisions = 0;
+	uint64_t resolve(int32_t t, int32_t pos, uint64_t key, uint64_t h2)
+	{
+		if(t != tid) { seen.clear(); order.clear(); tid = t; }
+		while(!order.empty() && order.front().first + KEY_WINDOW < (int64_t)pos)
+		{
+			// (a key seen again later was re-inserted at the back: only drop it when this was its last sighting)
+			std::unordered_map<uint64_t, uint64_t>::iterator it = seen.find(order.front().second);
+			if(it != seen.end() && last_pos[order.front().second] == order.front().first) { seen.erase(it); last_pos.erase(order.front().second); }
+			order.pop_front();
+		}
+		for(int round = 0; round < 64; round++)
+		{
+			std::unordered_map<uint64_t, uint64_t>::iterator it = seen.find(key);
+			if(it == seen.end()) { seen[key] = h2; break; }
+			if(it->second == h2) break;                          // the same name: its mate or another alignment of it
+			collisions++;
+			key = (key ^ h2) * 0x9E3779B97F4A7C15ULL + (uint64_t)round;     // another name owns the key: move on, deterministically
+			if(g_key_bits < 64) key &= (1ULL << g_key_bits) - 1;
+			if(key == 0xffffffffffffffffULL) key = 0x7fffffffffffffffULL;
+		}
+		last_pos[key] = pos;
+		order.push_back(std::make_pair((int64_t)pos, key));
+		return key;
+	}
+	std::unordered_map<uint64_t, int64_t> last_pos;
+};
+
 uint64_t hash64(const char *s, size_t n)
 {
 	uint64_t h = 0xcbf29ce484222325ULL;                          // FNV-1a, then a finaliser; never the reserved all-ones key
@@ -193,16 +248,28 @@ int bam_write_records(const char *path, int32_t n_chrom, const int32_t *chrom_le
 		rec.push_back((uint8_t)ql);
 		rec.push_back(r->mapq[i]);
 		put<uint16_t>(rec, (uint16_t)reg2bin(r->pos[i], r->rpos[i] > r->pos[i] ? r->rpos[i] : r->pos[i] + 1));
-		put<uint16_t>(rec, (uint16_t)nc);
+		const bool long_cigar = nc > 65535;            // SAM specification 4.2.2: placeholder CIGAR + CG:B,I tag
+		put<uint16_t>(rec, (uint16_t)(long_cigar ? 2 : nc));
 		put<uint16_t>(rec, r->flag[i]);
 		put<int32_t>(rec, lseq);
 		put<int32_t>(rec, (r->flag[i] & 0x1) ? r->tid[i] : -1);
 		put<int32_t>(rec, r->mpos[i]);
 		put<int32_t>(rec, r->isize[i]);
 		rec.insert(rec.end(), qn, qn + ql);
-		for(uint32_t k = 0; k < nc; k++) put<uint32_t>(rec, cg[k]);
+		if(long_cigar)
+		{
+			put<uint32_t>(rec, ((uint32_t)lseq << 4) | 4u);
+			put<uint32_t>(rec, ((uint32_t)(r->rpos[i] - r->pos[i]) << 4) | 3u);
+		}
+		else for(uint32_t k = 0; k < nc; k++) put<uint32_t>(rec, cg[k]);
 		rec.insert(rec.end(), (size_t)(lseq + 1) / 2, (uint8_t)0x11);       // sequence: all 'A'
 		rec.insert(rec.end(), (size_t)lseq, (uint8_t)0xff);                 // qualities absent
+		if(long_cigar)
+		{
+			rec.insert(rec.end(), {'C', 'G', 'B', 'I'});
+			put<int32_t>(rec, (int32_t)nc);
+			for(uint32_t k = 0; k < nc; k++) put<uint32_t>(rec, cg[k]);
+		}
 		rec.insert(rec.end(), {'N', 'H', 'C', 1});
 		rec.insert(rec.end(), {'H', 'I', 'C', 1});
 		char xs = (char)r->xs[i];
@@ -246,6 +313,8 @@ int bam_read_records(const char *path, synth_records *out, int32_t *n_chrom_out,
 		if(chrom_len_out && k < cap) chrom_len_out[k] = l_ref;
 	}
 	if(n_chrom_out) *n_chrom_out = n_ref;
+	if(chrom_len_out && n_ref > cap) { fclose(rd.fp); return -4; }        // the caller's dictionary buffer is too small: no silent truncation
+	key_window keys;
 	size_t capn = 0, capc = 0;
 	int64_t n = 0, nc_tot = 0;
 	std::vector<uint8_t> rec;
@@ -285,7 +354,8 @@ int bam_read_records(const char *path, synth_records *out, int32_t *n_chrom_out,
 		nc_tot += ncig;
 		// aux fields: XS:A and ts:A (hit::set_tags, rnacore/hit.cc:106-123)
 		char xs = '.', ts = '.';
-		size_t a = o_a;
+		size_t a = o_a, cg_at = 0;
+		int32_t cg_n = 0;
 		while(a + 3 <= (size_t)bs)
 		{
 			char t0 = (char)rec[a], t1 = (char)rec[a + 1], ty = (char)rec[a + 2];
@@ -302,13 +372,36 @@ int bam_read_records(const char *path, synth_records *out, int32_t *n_chrom_out,
 				int32_t cnt;
 				memcpy(&cnt, &rec[a + 1], 4);
 				size_t es = (st == 'c' || st == 'C') ? 1 : ((st == 's' || st == 'S') ? 2 : 4);
+				if(cnt < 0 || (uint64_t)es * (uint64_t)cnt > (uint64_t)bs - a - 5) break;       // hostile count: would wrap / run past the record
 				len = 5 + es * (size_t)cnt;
+				if(t0 == 'C' && t1 == 'G' && st == 'I') { cg_at = a + 5; cg_n = cnt; }
 			}
 			else break;
 			if(a + len > (size_t)bs) break;
 			if(ty == 'A' && t0 == 'X' && t1 == 'S') xs = (char)rec[a];
 			if(ty == 'A' && t0 == 't' && t1 == 's') ts = (char)rec[a];
 			a += len;
+		}
+		// more than 65535 operations (long reads): the record holds the placeholder <read length>S <reference length>N and the real
+		// CIGAR in the CG:B,I tag (SAM specification, section 4.2.2; htslib swaps it in when reading)
+		if(cg_n > 0 && ncig == 2)
+		{
+			uint32_t c0, c1;
+			memcpy(&c0, &rec[o_c], 4); memcpy(&c1, &rec[o_c + 4], 4);
+			if((c0 & 0xf) == 4 && (int32_t)(c0 >> 4) == lseq && (c1 & 0xf) == 3)
+			{
+				nc_tot -= ncig;
+				if((size_t)nc_tot + (size_t)cg_n + 1 > capc) { capc = capc * 2 + (size_t)cg_n; out->cigar = grow(out->cigar, capc); }
+				rpos = pos;
+				for(int32_t k = 0; k < cg_n; k++)
+				{
+					uint32_t c;
+					memcpy(&c, &rec[cg_at + 4 * (size_t)k], 4);
+					out->cigar[nc_tot + k] = c;
+					if((0x3C1A7 >> ((c & 0xf) << 1)) & 2) rpos += (int32_t)(c >> 4);
+				}
+				nc_tot += cg_n;
+			}
 		}
 		if(xs == '.' && ts != '.')
 		{
@@ -319,7 +412,11 @@ int bam_read_records(const char *path, synth_records *out, int32_t *n_chrom_out,
 		}
 		out->tid[n] = tid; out->pos[n] = pos; out->rpos[n] = rpos; out->mpos[n] = mpos; out->isize[n] = isize;
 		out->flag[n] = flag; out->mapq[n] = mapq; out->xs[n] = (uint8_t)xs;
-		out->qid[n] = hash64((const char*)&rec[o_q], (size_t)lq - 1);
+		{
+			uint64_t key = hash64((const char*)&rec[o_q], (size_t)lq - 1);
+			if(g_key_bits < 64) key &= (1ULL << g_key_bits) - 1;
+			out->qid[n] = keys.resolve(tid, pos, key, hash64b((const char*)&rec[o_q], (size_t)lq - 1));
+		}
 		out->cigar_off[n + 1] = (uint32_t)nc_tot;
 		n++;
 		(void)mtid;
@@ -333,6 +430,13 @@ int bam_read_records(const char *path, synth_records *out, int32_t *n_chrom_out,
 	}
 	if(rd.bad) { synth_records_free(out); return -3; }
 	return 0;
+}
+
+int bam_set_key_bits(int bits)
+{
+	int old = g_key_bits;
+	g_key_bits = bits < 1 ? 1 : (bits > 64 ? 64 : bits);
+	return old;
 }
 
 }

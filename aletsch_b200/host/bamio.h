@@ -21,8 +21,18 @@ extern "C" {
 int bam_write_records(const char *path, int32_t n_chrom, const int32_t *chrom_len, const synth_records *r, int tag_mode);
 
 // read every record of a BAM file (free with synth_records_free).  n_chrom_out / chrom_len_out (optional, up to cap entries)
-// receive the reference dictionary.  Returns 0 on success, < 0 on a malformed file.
+// receive the reference dictionary.  Returns 0 on success, < 0 on a malformed file, -4 when the file has more reference
+// sequences than `cap`.
+// qid: a 64-bit hash of the query name made collision-free where it matters -- every record's key is checked (with a second,
+// independent hash) against the keys of all records within 1.2 Mb upstream, the only ones it can share a bundle with
+// (max_read_span is 500000), and a different name under an equal key is given another key.  So inside a bundle "equal key <=>
+// equal qname" holds, which is what the ABI promises the device (include/aletsch_gpu.h: agpu_batch_in::qid).
+// Records with more than 65535 CIGAR operations carry their CIGAR in the CG:B,I tag: it is swapped in, as htslib does.
 int bam_read_records(const char *path, synth_records *out, int32_t *n_chrom_out, int32_t *chrom_len_out, int32_t cap);
+
+// test hook: truncate the query-name hashes to `bits` bits (64 = off) so that colliding keys occur on ordinary data and the
+// re-keying above is exercised; returns the previous value
+int bam_set_key_bits(int bits);
 
 #ifdef __cplusplus
 }

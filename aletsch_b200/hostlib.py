@@ -111,6 +111,7 @@ def lib():
         L.synth_records_free.argtypes = [C.POINTER(SynthRecords)]
         L.bam_write_records.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.POINTER(SynthRecords), C.c_int]
         L.bam_read_records.argtypes = [C.c_char_p, C.POINTER(SynthRecords), C.POINTER(C.c_int32), C.c_void_p, C.c_int32]
+        L.bam_set_key_bits.argtypes = [C.c_int]
         L.packer_create.restype = C.c_void_p
         L.packer_destroy.argtypes = [C.c_void_p]
         L.packer_add_sample.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]

@@ -84,3 +84,61 @@ def test_bam_reader_rejects_garbage(tmp_path):
     open(path, "wb").write(b"not a bam file at all" * 10)
     with pytest.raises(RuntimeError):
         H.read_bam(path)
+
+
+def test_qname_keys_survive_hash_collisions(tmp_path):
+    """the ABI promises the device "equal qid <=> equal qname" inside a bundle (rnacore/bundle_base.cc:308 compares the names).
+    With the name hashes truncated to 16 bits a few hundred of the ~6000 names collide with a different name nearby; the reader must
+    still hand out keys with exactly the equality structure of the names (the synthetic names are "q<template id>")."""
+    cfg = H.default_config(H.SYNTH_PAIRED, chrom_len=800_000, seed=20260113)
+    rec = H.Synth(cfg).sample(0, 6000, threads=2)
+    path = str(tmp_path / "c.bam")
+    H.write_bam(path, rec, [cfg.chrom_len] * cfg.n_chrom)
+    old = H.lib().bam_set_key_bits(16)
+    try:
+        back, _ = H.read_bam(path)
+    finally:
+        H.lib().bam_set_key_bits(old)
+    # all records of this file lie within the 1.2 Mb window: the classes must agree over the whole file
+    assert np.array_equal(qid_classes(back["qid"]), qid_classes(rec["qid"]))
+    names = len(set(rec["qid"].tolist()))
+    assert len(set(back["qid"].tolist())) == names and int(back["qid"].max()) < 65536
+    # the birthday bound makes plain 16-bit truncation collide here (about names^2 / 2^17 pairs): without the re-keying the
+    # classes could not have matched
+    assert names * names // (1 << 17) > 50
+    full, _ = H.read_bam(path)
+    assert np.array_equal(qid_classes(full["qid"]), qid_classes(rec["qid"]))
+
+
+def test_long_cigar_in_cg_tag(tmp_path):
+    """a record with more than 65535 CIGAR operations keeps them in the CG:B,I tag behind a <read length>S<reference length>N
+    placeholder (SAM specification 4.2.2); the reader swaps them in like htslib, so rpos and the splices are the real ones"""
+    n_ops = 70001
+    ops = np.empty(n_ops, np.uint32)
+    ops[0::2] = (3 << 4) | 0          # 3M
+    ops[1::2] = (2 << 4) | 2          # 2D
+    ops[35001] = (500 << 4) | 3       # one intron in the middle
+    ref_len = int(sum((int(c) >> 4) for c in ops if (int(c) & 0xf) in (0, 2, 3)))
+    rec = {"n": 2, "tid": np.zeros(2, np.int32), "pos": np.array([1000, 1000 + ref_len + 50], np.int32),
+           "rpos": np.array([1000 + ref_len, 1000 + ref_len + 150], np.int32), "mpos": np.zeros(2, np.int32), "isize": np.zeros(2, np.int32),
+           "flag": np.zeros(2, np.uint16), "mapq": np.full(2, 60, np.uint8), "xs": np.array([ord("+"), ord(".")], np.uint8),
+           "qid": np.array([7, 8], np.uint64), "cigar_off": np.array([0, n_ops, n_ops + 1], np.uint32),
+           "cigar": np.concatenate([ops, np.array([(100 << 4) | 0], np.uint32)])}
+    path = str(tmp_path / "l.bam")
+    H.write_bam(path, rec, [2_000_000])
+    back, _ = H.read_bam(path)
+    assert back["n"] == 2
+    for k in ("pos", "rpos", "cigar_off", "cigar", "xs"):
+        assert np.array_equal(back[k], rec[k]), k
+
+
+def test_dictionary_larger_than_buffer_is_an_error(tmp_path):
+    cfg = H.default_config(H.SYNTH_PAIRED, chrom_len=300_000, n_chrom=3, seed=20260114)
+    rec = H.Synth(cfg).sample(0, 500, threads=1)
+    path = str(tmp_path / "d.bam")
+    H.write_bam(path, rec, [cfg.chrom_len] * 3)
+    import ctypes as C
+    r = H.SynthRecords()
+    n = C.c_int32(0)
+    cl = np.zeros(2, np.int32)
+    assert H.lib().bam_read_records(path.encode(), C.byref(r), C.byref(n), cl.ctypes.data, 2) == -4
