@@ -1285,4 +1285,38 @@ int ref_icl_apply(int n, const int32_t *l, const int32_t *r, const int32_t *v, i
 	return k;
 }
 
+// a script over two maps of the reference's types: op 0: A += (I, v); 1: A -= (I, v); 2: B += (I, v); 3: A += B (bundle::combine,
+// meta/bundle.cc:102); 4: A -= every segment of B.  join selects join_interval_map, else split_interval_map.  Dumps A.
+int ref_icl_script(int n, const int32_t *op, const int32_t *l, const int32_t *r, const int32_t *v, int join, int32_t *out, int cap)
+{
+	int k = 0;
+	if(join)
+	{
+		join_interval_map A, B;
+		for(int i = 0; i < n; i++)
+		{
+			if(op[i] == 0) A += make_pair(ROI(l[i], r[i]), v[i]);
+			if(op[i] == 1) A -= make_pair(ROI(l[i], r[i]), v[i]);
+			if(op[i] == 2) B += make_pair(ROI(l[i], r[i]), v[i]);
+			if(op[i] == 3) A += B;
+			if(op[i] == 4) for(JIMI it = B.begin(); it != B.end(); it++) A -= make_pair(it->first, it->second);
+		}
+		for(JIMI it = A.begin(); it != A.end() && k + 3 <= cap; it++) { out[k++] = lower(it->first); out[k++] = upper(it->first); out[k++] = it->second; }
+	}
+	else
+	{
+		split_interval_map A, B;
+		for(int i = 0; i < n; i++)
+		{
+			if(op[i] == 0) A += make_pair(ROI(l[i], r[i]), v[i]);
+			if(op[i] == 1) A -= make_pair(ROI(l[i], r[i]), v[i]);
+			if(op[i] == 2) B += make_pair(ROI(l[i], r[i]), v[i]);
+			if(op[i] == 3) A += B;
+			if(op[i] == 4) for(SIMI it = B.begin(); it != B.end(); it++) A -= make_pair(it->first, it->second);
+		}
+		for(SIMI it = A.begin(); it != A.end() && k + 3 <= cap; it++) { out[k++] = lower(it->first); out[k++] = upper(it->first); out[k++] = it->second; }
+	}
+	return k;
+}
+
 }
