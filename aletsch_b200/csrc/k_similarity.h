@@ -145,6 +145,179 @@ KERNEL k_sim_groups(sim_batch a)
 	}
 }
 
+// ---- all bundle groups of a call at once, any size, with the pairs filtered on the device ------------------------------------
+// bundle_group::build_splice_similarity only ever keeps a pair (i, j) when both have at most max_num_junctions_to_combine
+// junctions, c = |splices_i AND splices_j| > 0 and r = c / min(|i|, |j|) reaches the round's threshold (meta/bundle_group.cc:193-
+// 221).  The thresholds of the two rounds are known up front, so the device hands back, per bundle, only the partners j > i that
+// can pass the weaker one, with c, in ascending j: a CSR the host walks instead of a dense G x G matrix (1 GB of host memory and
+// most of the time at 1000 cells per region).
+//   dictionary : the group's splice positions as ranks in a per-group position bitmap (a region spans a few Mb: no sort)
+//   bitsets    : one row of ceil(distinct / 64) words per bundle
+//   tiles      : 32 x 32 pairs per CTA, AND + popcount over the rows staged in shared memory; pass 1 counts the qualifying pairs
+//                per (bundle, column tile), a look-back scan places them, pass 2 writes (j, c)
+struct sim_lists
+{
+	int32_t n_groups, n_lists;
+	const int32_t *group_off;      // [n_groups + 1]
+	const int32_t *list_group;     // [n_lists]
+	const int64_t *list_off;       // [n_lists + 1]
+	const int32_t *val;
+	int32_t *gmin, *gmax;          // [n_groups]
+	const int64_t *bm_off;         // [n_groups + 1] words of the position bitmaps
+	u32 *bitmap;
+	const u32 *wrank;              // global rank of every bitmap word
+	const int64_t *row_off;        // [n_lists + 1] words of the bitset rows
+	u64 *rows;
+};
+
+KERNEL k_simb_minmax(sim_lists a)
+{
+	int l = blockIdx.x * blockDim.x + threadIdx.x;
+	if(l >= a.n_lists) return;
+	const int64_t v0 = a.list_off[l], v1 = a.list_off[l + 1];
+	if(v1 <= v0) return;
+	const int g = a.list_group[l];
+	atomicMin(&a.gmin[g], a.val[v0]);
+	atomicMax(&a.gmax[g], a.val[v1 - 1]);
+}
+
+// list of every value (lists are short: a binary search over the offsets)
+DEV int simb_list_of(const sim_lists &a, int64_t i) { return find_segment(a.list_off, a.n_lists, i); }
+
+KERNEL k_simb_mark(sim_lists a, int64_t n_val)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_val) return;
+	const int g = a.list_group[simb_list_of(a, i)];
+	const int64_t bit = (int64_t)a.val[i] - a.gmin[g];
+	atomicOr(&a.bitmap[a.bm_off[g] + (bit >> 5)], 1u << (bit & 31));
+}
+
+KERNEL k_simb_rows(sim_lists a, int64_t n_val)
+{
+	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_val) return;
+	const int l = simb_list_of(a, i);
+	const int g = a.list_group[l];
+	const int64_t bit = (int64_t)a.val[i] - a.gmin[g];
+	const int64_t w = a.bm_off[g] + (bit >> 5);
+	const u32 k = a.wrank[w] - a.wrank[a.bm_off[g]] + (u32)__popc(a.bitmap[w] & ((1u << (bit & 31)) - 1u));
+	atomicOr(&a.rows[a.row_off[l] + (k >> 6)], (u64)1 << (k & 63));
+}
+
+struct sim_tiles
+{
+	int64_t n_jobs;
+	const int32_t *job_g, *job_ti, *job_tj;
+	const int64_t *cnt_off;        // [n_groups] start of the group's (bundle, column tile) counters
+	int max_junctions;
+	double thr;                    // the weaker of the two rounds' thresholds
+};
+
+// one 32 x 32 tile: c of every pair into sacc; returns (to all threads) nothing -- helper shared by the two passes
+DEV void simb_tile_counts(const sim_lists &a, int g, int ti, int tj, int G, int words, u64 (*sa)[SIM_CHUNK + 1], u64 (*sb)[SIM_CHUNK + 1], int *sacc)
+{
+	const int l0 = a.group_off[g];
+	const int nthr = blockDim.x;
+	for(int p = threadIdx.x; p < SIM_TILE * SIM_TILE; p += nthr) sacc[p] = 0;
+	for(int w0 = 0; w0 < words; w0 += SIM_CHUNK)
+	{
+		BLOCK_SYNC();
+		for(int x = threadIdx.x; x < SIM_TILE * SIM_CHUNK; x += nthr)
+		{
+			const int r = x / SIM_CHUNK, c = x % SIM_CHUNK;
+			const int gi = ti * SIM_TILE + r, gj = tj * SIM_TILE + r;
+			sa[r][c] = (gi < G && w0 + c < words) ? a.rows[a.row_off[l0 + gi] + w0 + c] : 0;
+			sb[r][c] = (gj < G && w0 + c < words) ? a.rows[a.row_off[l0 + gj] + w0 + c] : 0;
+		}
+		BLOCK_SYNC();
+		const int lim = words - w0 < SIM_CHUNK ? words - w0 : SIM_CHUNK;
+		for(int p = threadIdx.x; p < SIM_TILE * SIM_TILE; p += nthr)
+		{
+			const int x = p / SIM_TILE, y = p % SIM_TILE;
+			int s = 0;
+			for(int c = 0; c < lim; c++) s += __popcll(sa[x][c] & sb[y][c]);
+			sacc[p] += s;
+		}
+	}
+	BLOCK_SYNC();
+}
+
+// does the pair (local bundles i < j of group g) pass the weaker round?  (meta/bundle_group.cc:196-221)
+DEV bool simb_keep(const sim_lists &a, const sim_tiles &t, int l0, int i, int j, int G, int c)
+{
+	if(i >= G || j >= G || i >= j || c <= 0) return false;
+	const int64_t ni = a.list_off[l0 + i + 1] - a.list_off[l0 + i], nj = a.list_off[l0 + j + 1] - a.list_off[l0 + j];
+	if(ni / 2.0 > t.max_junctions || nj / 2.0 > t.max_junctions) return false;
+	const int64_t small = ni < nj ? ni : nj;
+	const double r = c * 1.0 / small;
+	return !(r < t.thr);
+}
+
+KERNEL k_simb_count(sim_lists a, sim_tiles t, int32_t *count)
+{
+	SHARED u64 sa[SIM_TILE][SIM_CHUNK + 1];
+	SHARED u64 sb[SIM_TILE][SIM_CHUNK + 1];
+	SHARED int sacc[SIM_TILE * SIM_TILE];
+	for(int64_t job = blockIdx.x; job < t.n_jobs; job += gridDim.x)
+	{
+		const int g = t.job_g[job], ti = t.job_ti[job], tj = t.job_tj[job];
+		const int l0 = a.group_off[g], G = a.group_off[g + 1] - l0;
+		const int T = (G + SIM_TILE - 1) / SIM_TILE;
+		const int words = (int)(a.row_off[l0 + 1] - a.row_off[l0]);
+		simb_tile_counts(a, g, ti, tj, G, words, sa, sb, sacc);
+		for(int x = threadIdx.x; x < SIM_TILE; x += blockDim.x)
+		{
+			const int i = ti * SIM_TILE + x;
+			if(i >= G) continue;
+			int n = 0;
+			for(int y = 0; y < SIM_TILE; y++) n += simb_keep(a, t, l0, i, tj * SIM_TILE + y, G, sacc[x * SIM_TILE + y]) ? 1 : 0;
+			count[t.cnt_off[g] + (int64_t)i * T + tj] = n;
+		}
+		BLOCK_SYNC();
+	}
+}
+
+KERNEL k_simb_fill(sim_lists a, sim_tiles t, const int64_t *place, int32_t *out_j, int32_t *out_c)
+{
+	SHARED u64 sa[SIM_TILE][SIM_CHUNK + 1];
+	SHARED u64 sb[SIM_TILE][SIM_CHUNK + 1];
+	SHARED int sacc[SIM_TILE * SIM_TILE];
+	for(int64_t job = blockIdx.x; job < t.n_jobs; job += gridDim.x)
+	{
+		const int g = t.job_g[job], ti = t.job_ti[job], tj = t.job_tj[job];
+		const int l0 = a.group_off[g], G = a.group_off[g + 1] - l0;
+		const int T = (G + SIM_TILE - 1) / SIM_TILE;
+		const int words = (int)(a.row_off[l0 + 1] - a.row_off[l0]);
+		simb_tile_counts(a, g, ti, tj, G, words, sa, sb, sacc);
+		for(int x = threadIdx.x; x < SIM_TILE; x += blockDim.x)
+		{
+			const int i = ti * SIM_TILE + x;
+			if(i >= G) continue;
+			int64_t w = place[t.cnt_off[g] + (int64_t)i * T + tj];
+			for(int y = 0; y < SIM_TILE; y++)
+			{
+				const int j = tj * SIM_TILE + y, c = sacc[x * SIM_TILE + y];
+				if(simb_keep(a, t, l0, i, j, G, c)) { out_j[w] = j; out_c[w] = c; w++; }
+			}
+		}
+		BLOCK_SYNC();
+	}
+}
+
+// row_ptr[l] = place of bundle l's first pair (its counters are contiguous); row_ptr[n_lists] = total
+KERNEL k_simb_rowptr(sim_lists a, const int64_t *cnt_off, const int64_t *place, int64_t n_count, int64_t *row_ptr)
+{
+	int l = blockIdx.x * blockDim.x + threadIdx.x;
+	if(l > a.n_lists) return;
+	if(l == a.n_lists) { row_ptr[l] = place[n_count]; return; }
+	const int g = a.list_group[l];
+	const int l0 = a.group_off[g], G = a.group_off[g + 1] - l0;
+	const int T = (G + SIM_TILE - 1) / SIM_TILE;
+	row_ptr[l] = place[cnt_off[g] + (int64_t)(l - l0) * T];
+}
+
 } // namespace agpu
+
 
 #endif

@@ -53,6 +53,7 @@ CONFIGS = {
 MAX_BATCH_SPAN = 3_000_000_000     # window positions per device batch: the ABI's coverage index is 32-bit (AGPU_ERR_CAPACITY above 2^32)
 MAX_BATCH_HITS = 60_000_000
 E2E_CHUNK_HITS = 8_000_000
+E2E_CHUNK_OPS = 32_000_000
 
 
 def log(*a):
@@ -374,7 +375,7 @@ def run_ours(args):
     # it has seen, so the sub-batch size bounds the device memory of the pipeline (2 x streams contexts)
     chunks = []
     for part in parts:
-        per_part = max(1, -(-args.chunks // len(parts)), -(-part.n_hits // E2E_CHUNK_HITS))
+        per_part = max(1, -(-args.chunks // len(parts)), -(-part.n_hits // E2E_CHUNK_HITS), -(-part.n_cigar // E2E_CHUNK_OPS))
         chunks.extend(part.split(per_part))
     views = []
     h2d_bytes = 0
@@ -443,6 +444,51 @@ def run_ours(args):
         for i, what, tid, a, b in pipe.trace[-4 * len(views) * args.steps:]:
             log("[trace] sub-batch %2d %-8s thread %x  %8.2f -> %8.2f ms (%7.2f)" % (i, what, tid & 0xffff, 1e3 * (a - t00), 1e3 * (b - t00), 1e3 * (b - a)))
     pipe.close()
+
+    # ---- the path's one exchange step (world > 1): samples ingested on different ranks share their per-bundle splice signatures
+    # with ONE all-gather over NCCL, after which every rank runs the identical bundle_group::resolve (aletsch_b200/shard.py).
+    # Here every rank contributes the signatures of its own chromosome(s); timed on the device, max over ranks.
+    collective = None
+    if world > 1:
+        from aletsch_b200 import shard
+        cctx = G.Context(local, stream=stream.cuda_stream)
+        sig_off, sig_val = [np.zeros(1, np.int64)], []
+        base = 0
+        for part in parts:
+            dev = {f: torch.from_numpy(_tview(part.a[f])).to("cuda") for f in FIELDS}
+            b = H.BatchIn()
+            b.n_bundles, b.n_hits, b.n_cigar = part.n_bundles, part.n_hits, part.n_cigar
+            for f in FIELDS:
+                setattr(b, f, dev[f].data_ptr())
+            x = cctx.adopt(b, keepalive=dev)
+            x.evidence(gp)
+            o, v = x.fetch_splices()
+            x.free()
+            sig_off.append(o[1:] + base)
+            sig_val.append(v)
+            base += int(o[-1]) if len(o) else 0
+            del dev
+        sig_off = np.concatenate(sig_off)
+        sig_val = np.concatenate(sig_val) if sig_val else np.zeros(0, np.int32)
+        keys = (np.int64(rank) << 40) | np.arange(batch.n_bundles, dtype=np.int64)
+        regs = shard.bundle_region_keys(batch) | (np.int64(rank) << 56)
+        for it in range(3):
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            t_host0 = time.perf_counter()
+            got = shard.gather_packed(sig_off, sig_val, keys, regs)
+            c1.record(stream)
+            barrier()
+            t_host = time.perf_counter() - t_host0
+            ms_coll = c0.elapsed_time(c1)
+        tc = torch.tensor([ms_coll, t_host * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        collective = {"name": "all_gather (NCCL, torch.distributed) of the per-bundle splice signatures: header + padded payload",
+                      "bundles_gathered": int(len(got[0]) - 1), "signature_values": int(len(got[1])), "bytes_received_per_rank": int(got[5]),
+                      "device_ms": float(tc[0]), "host_wall_ms": float(tc[1]), "timing": "CUDA events around the two collectives, max over ranks"}
+        cctx.close()
+        torch.cuda.empty_cache()
 
     # max over ranks, totals over ranks
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
@@ -537,6 +583,8 @@ def run_ours(args):
                        "prefetch": not args.no_prefetch, "stream_drains_per_step": syncs_e2e / steps, "sub_batches": len(views), "streams": args.streams,
                        "gpu_launches_per_step": int(launches_e2e // steps)},
                "roofline": roof, "clocks": clk}
+        if collective is not None:
+            out["collective"] = collective
         if stage5 is not None:
             out["stage5"] = stage5
         if group_leg is not None:
