@@ -58,8 +58,16 @@ def main(argv=None):
     if args.clusters and batch.n_bundles:
         off, val = bt.fetch_splices()
         a = batch.a
-        first = np.minimum(a["bundle_hit_off"][:-1], max(batch.n_hits - 1, 0))
-        key = (a["bundle_tid"].astype(np.int64) << 40) | ((a["pos"][first].astype(np.int64) // REGION) << 8) | a["strand"][first].astype(np.int64)
+        # bundle groups: (chromosome, 1 Mb region of the bundle's first hit, bundle strand).  The strand is the one
+        # bundle_base::compute_strand leaves (for unstranded libraries the majority of the XS tags: '+', '-' and '.' bundles are
+        # grouped separately, meta/incubator.cc:526-540).  The region is the NOMINAL one: the reference files a bundle under the
+        # region-table entry its generator::resolve ran for, which reaches past the 1 Mb multiple until a gap wider than
+        # min_bundle_gap (rnacore/sample_profile.cc:167-252), so a bundle starting just behind a boundary inside such a run joins
+        # the previous group there and the next one here; and bundle_group::remove_duplicates (meta/bundle_group.cc:58-91: '+'
+        # bundles that end at or before the previous region's end1 are emptied) is not applied.  This tool is a usage example of
+        # the ABI, not a reference-equivalent scheduler: the incubator stays on the host (BASELINE.json: north_star).
+        from .shard import bundle_region_keys
+        key = bundle_region_keys(batch)
         order = np.lexsort((np.arange(batch.n_bundles), a["bundle_sample"], key))
         cuts = np.nonzero(np.diff(key[order]))[0] + 1
         groups = [g for g in np.split(order, cuts) if len(g)]
