@@ -315,6 +315,7 @@ KERNEL k_group_leaders(int64_t n_frg, const int32_t *f_bundle, const int64_t *fr
 	{
 		int k = atomicAdd(n_big, 1);
 		if(k < big_cap) big_list[k] = (int32_t)f;
+		atomicAdd(n_big + 1, size);              // members the warp kernel handles (agpu_counts::big_group_members)
 	}
 	// one atomic per warp for the small groups
 	const bool small = lead && size <= BIG_GROUP;

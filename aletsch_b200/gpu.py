@@ -91,7 +91,7 @@ class PhaseView(C.Structure):
 class Counts(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("hits", "cigar_ops", "span", "segments", "chains", "splice_ints", "junctions", "vertices",
                                          "edges", "fragments", "clusters", "bridged", "piers", "borders", "cluster_members",
-                                         "bridge_chain_ints", "bridge_whole_ints")]
+                                         "bridge_chain_ints", "bridge_whole_ints", "big_group_members")]
 
 
 ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_error", "agpu_sync", "agpu_launch_count", "agpu_sync_count",

@@ -424,7 +424,7 @@ def run_ours(args):
     e3.record(stream)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
-    d2h_bytes = sum(r["d2h_bytes"] for r in res) / args.steps + 17 * 8 * len(views)     # result views + the counter struct of every sub-batch
+    d2h_bytes = sum(r["d2h_bytes"] for r in res) / args.steps + 18 * 8 * len(views)     # result views + the counter struct of every sub-batch
     launches_e2e = pipe.launches - launches_e2e0
     syncs_e2e = pipe.syncs - syncs_e2e0
     assert sum(r["hits"] for r in res) == n_hits * args.steps and sum(r["bridged"] for r in res) == counts["bridged"] * args.steps, "pipelined result differs"

@@ -322,6 +322,7 @@ typedef struct agpu_counts
 	int64_t hits, cigar_ops, span, segments, chains, splice_ints, junctions, vertices, edges;
 	int64_t fragments, clusters, bridged, piers;
 	int64_t borders, cluster_members, bridge_chain_ints, bridge_whole_ints;   /* ranked coverage borders, sum of frlist sizes, sizes of opt[].chain / opt[].whole */
+	int64_t big_group_members;   /* of cluster_members: those in fragment groups of more than 16 (partitioned by a warp each, not a thread) */
 } agpu_counts;
 int agpu_batch_counts(agpu_ctx *ctx, agpu_batch *b, agpu_counts *c);
 /* per bundle: out[4k..4k+3] = coverage segments (0 while the coverage map awaits its rebuild after agpu_batch_update), fragments,
