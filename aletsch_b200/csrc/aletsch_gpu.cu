@@ -853,8 +853,14 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(b->b_lpos.alloc(ctx, nb + 1)); TRY(b->b_rpos.alloc(ctx, nb + 1)); TRY(b->b_covhi.alloc(ctx, nb + 1));
 	TRY(b->b_strand.alloc(ctx, nb + 1)); TRY(b->b_span.alloc(ctx, nb + 1)); TRY(b->cov_base.alloc(ctx, nb + 2));
 	TRY(b->hit_bundle.alloc(ctx, nh + 1));
-	LAUNCH_B(ctx, k_bundle_bounds, nb, 128, b->h, p->library_type, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, b->b_strand.p, b->b_span.p,
-			b->hit_bundle.p, b->err.p);
+	{
+		dbuf<int32_t> npq;
+		TRY(npq.alloc(ctx, 2 * (size_t)nb + 2));
+		LAUNCH_T(ctx, k_bundle_init, nb, nb, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, npq.p);
+		LAUNCH_T(ctx, k_hit_bounds, nh, b->h, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, npq.p, b->hit_bundle.p, b->err.p);
+		LAUNCH_T(ctx, k_bundle_finish, nb, b->h, p->library_type, b->b_lpos.p, b->b_covhi.p, npq.p, b->b_strand.p, b->b_span.p);
+		npq.release(ctx);
+	}
 	TRY(lb_scan64(ctx, b->b_span.p, nb, b->cov_base.p));
 	b->ltot = 0;
 	TRY(d2h(ctx, &b->ltot, b->cov_base.p + nb, sizeof(int64_t)));

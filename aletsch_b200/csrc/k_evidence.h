@@ -41,58 +41,82 @@ struct hits_dev
 // error / statistics words shared by all kernels of a batch
 enum { ERR_ORDER = 0, ERR_DUP, ERR_STRAND, ERR_RPOS, ERR_LINK, ERR_QID, ERR_CAP, ERR_PACKED, ERR_WORDS = 16 };
 
-// ---- E0: bundle bounds (bundle_base::add_hit) + packing-contract check; one CTA per bundle
-KERNEL k_bundle_bounds(hits_dev h, int library_type, int32_t *b_lpos, int32_t *b_rpos, int32_t *b_covhi,
-		uint8_t *b_strand, int64_t *b_span, int32_t *hit_bundle, int *err)
+// ---- E0: bundle bounds (bundle_base::add_hit) + packing-contract check.  One thread per HIT (bundles range from one hit to
+// several hundred thousand: a CTA per bundle leaves the step waiting for the deepest one): every hit finds its bundle by
+// bisection of the offsets (neighbours share the search path, so it stays in L1), a warp whose hits all lie in one bundle
+// reduces first and issues one set of atomics.  k_bundle_init before, k_bundle_finish after (both one thread per bundle).
+KERNEL k_bundle_init(int32_t n_bundles, int32_t *b_lpos, int32_t *b_rpos, int32_t *b_covhi, int32_t *b_npq)
 {
-	SHARED int s_min, s_max, s_cov, s_np, s_nq;
-	for(int b = blockIdx.x; b < h.n_bundles; b += gridDim.x)
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if(b >= n_bundles) return;
+	b_lpos[b] = 1 << 30; b_rpos[b] = 0; b_covhi[b] = 0;        // rnacore/bundle_base.cc:21-22
+	b_npq[2 * b] = 0; b_npq[2 * b + 1] = 0;
+}
+
+KERNEL k_hit_bounds(hits_dev h, int32_t *b_lpos, int32_t *b_rpos, int32_t *b_covhi, int32_t *b_npq, int32_t *hit_bundle, int *err)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const bool in = i < h.n_hits;
+	int b = 0, p = 1 << 30, q = 0, r = 0, np = 0, nq = 0;
+	if(in)
 	{
-		int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
-		if(threadIdx.x == 0) { s_min = 1 << 30; s_max = 0; s_cov = 0; s_np = 0; s_nq = 0; }   // rnacore/bundle_base.cc:21-22
-		BLOCK_SYNC();
-		int lmin = 1 << 30, lmax = 0, lcov = 0, np = 0, nq = 0;
-		for(int64_t i = h0 + threadIdx.x; i < h1; i += blockDim.x)
+		// the last bundle whose first hit is not after i (empty bundles in front of it are skipped: their offset equals its own)
+		int lo = 0, hi = h.n_bundles;
+		while(hi - lo > 1)
 		{
-			int p = h.pos[i], r = h.rpos[i], m = h.mpos[i];
-			hit_bundle[i] = b;
-			if(p < lmin) lmin = p;
-			int q = r;
-			if(m > r && m <= r + 500000) q = m;            // rnacore/bundle_base.cc:92
-			if(q > lmax) lmax = q;
-			if(r > lcov) lcov = r;
-			if(h.xs[i] == '+') np++;
-			if(h.xs[i] == '-') nq++;
-			if(i > h0)
-			{
-				if(h.pos[i - 1] > p) atomicAdd(&err[ERR_ORDER], 1);
-				if(h.pos[i - 1] == p && h.rpos[i - 1] == r) atomicAdd(&err[ERR_DUP], 1);
-				if(h.strand && h.strand[i] != h.strand[h0]) atomicAdd(&err[ERR_STRAND], 1);
-			}
+			int mid = (lo + hi) >> 1;
+			if(h.bundle_hit_off[mid] <= i) lo = mid; else hi = mid;
 		}
-		atomicMin(&s_min, lmin); atomicMax(&s_max, lmax); atomicMax(&s_cov, lcov);
-		atomicAdd(&s_np, np); atomicAdd(&s_nq, nq);
-		BLOCK_SYNC();
-		if(threadIdx.x == 0)
+		b = lo;
+		const int64_t h0 = h.bundle_hit_off[b];
+		p = h.pos[i]; r = h.rpos[i];
+		const int m = h.mpos[i];
+		hit_bundle[i] = b;
+		q = r;
+		if(m > r && m <= r + 500000) q = m;                    // rnacore/bundle_base.cc:92
+		const uint8_t x = h.xs[i];
+		np = x == '+'; nq = x == '-';
+		if(i > h0)
 		{
-			b_lpos[b] = s_min;
-			b_rpos[b] = s_max;
-			b_covhi[b] = s_cov;
-			uint8_t st = '.';
-			if(h1 > h0) st = h.strand ? h.strand[h0] : h.bundle_strand[b];      // rnacore/bundle_base.cc:100
-			if(library_type == 0)                          // bundle_base::compute_strand, rnacore/bundle_base.cc:205-225
-			{
-				if(s_np > s_nq) st = '+';
-				else if(s_np < s_nq) st = '-';
-				else st = '.';
-			}
-			b_strand[b] = st;
-			// positions [lpos, covhi] inclusive (the -1 of a block ending at covhi lands there), tile-aligned
-			int64_t span = (h1 > h0) ? ((int64_t)s_cov - (int64_t)s_min + 1) : 0;
-			b_span[b] = (span + COV_ALIGN - 1) / COV_ALIGN * COV_ALIGN;
+			if(h.pos[i - 1] > p) atomicAdd(&err[ERR_ORDER], 1);
+			if(h.pos[i - 1] == p && h.rpos[i - 1] == r) atomicAdd(&err[ERR_DUP], 1);
+			if(h.strand && h.strand[i] != h.strand[h0]) atomicAdd(&err[ERR_STRAND], 1);
 		}
-		BLOCK_SYNC();
 	}
+#ifndef AGPU_EMU
+	const unsigned FULL = 0xffffffffu;
+	const int b0 = __shfl_sync(FULL, b, 0);
+	if(__all_sync(FULL, in && b == b0))
+	{
+		p = __reduce_min_sync(FULL, p); q = __reduce_max_sync(FULL, q); r = __reduce_max_sync(FULL, r);
+		np = __reduce_add_sync(FULL, np); nq = __reduce_add_sync(FULL, nq);
+		if((threadIdx.x & 31) != 0) return;
+	}
+#endif
+	if(!in) return;
+	atomicMin(&b_lpos[b], p); atomicMax(&b_rpos[b], q); atomicMax(&b_covhi[b], r);
+	if(np) atomicAdd(&b_npq[2 * b], np);
+	if(nq) atomicAdd(&b_npq[2 * b + 1], nq);
+}
+
+KERNEL k_bundle_finish(hits_dev h, int library_type, const int32_t *b_lpos, const int32_t *b_covhi, const int32_t *b_npq, uint8_t *b_strand, int64_t *b_span)
+{
+	int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if(b >= h.n_bundles) return;
+	const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
+	uint8_t st = '.';
+	if(h1 > h0) st = h.strand ? h.strand[h0] : h.bundle_strand[b];      // rnacore/bundle_base.cc:100
+	if(library_type == 0)                          // bundle_base::compute_strand, rnacore/bundle_base.cc:205-225
+	{
+		const int np = b_npq[2 * b], nq = b_npq[2 * b + 1];
+		if(np > nq) st = '+';
+		else if(np < nq) st = '-';
+		else st = '.';
+	}
+	b_strand[b] = st;
+	// positions [lpos, covhi] inclusive (the -1 of a block ending at covhi lands there), tile-aligned
+	int64_t span = (h1 > h0) ? ((int64_t)b_covhi[b] - (int64_t)b_lpos[b] + 1) : 0;
+	b_span[b] = (span + COV_ALIGN - 1) / COV_ALIGN * COV_ALIGN;
 }
 
 // ---- generic single-CTA exclusive scan of int64 (NB-sized arrays); out[n] = total

@@ -564,10 +564,7 @@ def run_ours(args):
                              "frac_survey": sb["survey"] / step_s / 1e9 / peak, "frac_layout": sb["layout"] / step_s / 1e9 / peak,
                              "note": "survey = SURVEY 8(d) formula with a per-base difference array (8.25 B/base); layout = the same with the "
                                      "border-compacted coverage map this implementation stores (3 bits/base + 16 B/border)"}}
-        config = reference_config(cfg, args)
-        config.update({"records_per_gpu": n_records, "admitted_hits_per_gpu": n_hits, "bundles_per_gpu": batch.n_bundles,
-                       "device_batches": len(parts),
-                       "l2": "inputs (%.2f GB) and scratch far larger than the 126 MB L2, no flush needed" % (h2d_bytes / 1e9)})
+        config = reference_config(cfg, args, batch, n_records, len(parts))
         out = {"metric": "hits_per_sec", "value": value, "unit": "hits/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
                "ms_per_step": ms_dev / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
                "data": "synthetic", "impl": "ours", "config": config,
@@ -606,10 +603,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def reference_config(cfg, args):
-    """the `config` keys both arms print (same workload string, generator and seed: the driver compares them)"""
-    return {"workload": workload_string(cfg, args.config), "generator": "synth-v1 seed %d" % cfg["seed"], "scale": cfg["scale_used"],
-            "samples": cfg["samples"], "templates_per_sample_per_gpu": cfg["per_sample"], "chromosomes_per_gpu": cfg["n_chrom"]}
+def reference_config(cfg, args, batch=None, n_records=None, n_parts=None):
+    """the `config` both arms print, key for key and value for value (the driver compares them): workload string, generator and
+    seed, and what the generator + packer made of it on rank 0"""
+    c = {"workload": workload_string(cfg, args.config), "generator": "synth-v1 seed %d" % cfg["seed"], "scale": cfg["scale_used"],
+         "samples": cfg["samples"], "templates_per_sample_per_gpu": cfg["per_sample"], "chromosomes_per_gpu": cfg["n_chrom"]}
+    if batch is not None:
+        plain = sum(batch.a[f].nbytes for f in FIELDS)
+        c.update({"records_per_gpu": int(n_records), "admitted_hits_per_gpu": int(batch.n_hits), "bundles_per_gpu": int(batch.n_bundles),
+                  "device_batches": int(n_parts if n_parts is not None else len(device_batches(batch))),
+                  "l2": "no flush: a step reads %.2f GB of plain input arrays and several GB of derived state, far more than the 126 MB L2" % (plain / 1e9)})
+    return c
 
 
 REGION = 1_000_000      # region_partition_length (util/parameters.cc:42)
@@ -1114,7 +1118,7 @@ def run_reference(args):
         bps = br / float(np.mean(secs))
         rt.close()
     value = float(np.mean(vals))
-    config = reference_config(cfg, args)
+    config = reference_config(cfg, args, batch, n_records)
     out = {"metric": "hits_per_sec", "value": value, "unit": "hits/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
            "data": "synthetic", "impl": "reference", "config": config,
