@@ -353,13 +353,18 @@ def group_resolve_arrays(ctx, group_off, list_off, list_val, params):
 
 
 def reorder_lists(off, val, order):
-    """packed lists (off, val) re-packed in the order `order` (vectorised gather)"""
-    order = np.asarray(order, np.int64)
-    lens = off[order + 1] - off[order]
+    """packed lists (off, val) re-packed in the order `order` (host library: one memcpy per list)"""
+    from . import hostlib
+    off = np.ascontiguousarray(off, np.int64)
+    val = np.ascontiguousarray(val, np.int32)
+    order = np.ascontiguousarray(order, np.int64)
     noff = np.zeros(len(order) + 1, np.int64)
-    np.cumsum(lens, out=noff[1:])
-    idx = np.repeat(off[order] - noff[:-1], lens) + np.arange(int(noff[-1]), dtype=np.int64)
-    return noff, val[idx] if len(val) else val
+    total = int((off[order + 1] - off[order]).sum()) if len(order) else 0
+    nval = np.empty(max(total, 1), np.int32)
+    got = hostlib.lib().packer_reorder_lists(len(off) - 1, off.ctypes.data, val.ctypes.data, len(order), order.ctypes.data, noff.ctypes.data, nval.ctypes.data)
+    if got != total:
+        raise ValueError("reorder_lists: index outside the lists")
+    return noff, nval[:total]
 
 
 class Batch:

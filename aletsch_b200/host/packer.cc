@@ -601,4 +601,21 @@ void *packer_compact_create(const agpu_batch_in *in)
 const agpu_batch_packed *packer_compact_view(void *c) { return c ? &((compact*)c)->v : NULL; }
 void packer_compact_destroy(void *c) { delete (compact*)c; }
 
+int64_t packer_reorder_lists(int64_t n_lists, const int64_t *off, const int32_t *val, int64_t n_out, const int64_t *order, int64_t *out_off,
+		int32_t *out_val)
+{
+	int64_t w = 0;
+	out_off[0] = 0;
+	for(int64_t k = 0; k < n_out; k++)
+	{
+		const int64_t l = order[k];
+		if(l < 0 || l >= n_lists) return -1;
+		const int64_t len = off[l + 1] - off[l];
+		if(len > 0) memcpy(out_val + w, val + off[l], sizeof(int32_t) * (size_t)len);
+		w += len;
+		out_off[k + 1] = w;
+	}
+	return w;
+}
+
 }

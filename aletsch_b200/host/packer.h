@@ -81,6 +81,11 @@ int packer_insertsize_profile(int64_t n_bundles, const int64_t *d_off, const int
 void *packer_compact_create(const agpu_batch_in *in);
 const agpu_batch_packed *packer_compact_view(void *c);
 void packer_compact_destroy(void *c);
+// packed int32 lists (off[n_lists + 1], val) re-packed in the order `order[n_out]` (e.g. the bundles' splice lists, fetched in
+// bundle order, laid out bundle group by bundle group for agpu_group_resolve_batch).  out_off[n_out + 1]; out_val holds the sum of
+// the chosen lists' lengths; returns that sum, or -1 when an index lies outside [0, n_lists)
+int64_t packer_reorder_lists(int64_t n_lists, const int64_t *off, const int32_t *val, int64_t n_out, const int64_t *order, int64_t *out_off,
+		int32_t *out_val);
 // view of everything appended so far (pointers stay valid until the next add / destroy)
 int packer_view(void *pk, agpu_batch_in *out);
 int64_t packer_records_seen(void *pk);

@@ -132,6 +132,8 @@ def lib():
         L.packer_preview_add.argtypes = [C.c_void_p, C.POINTER(PackerRecords), C.POINTER(PackerParams), C.c_int32]
         L.packer_preview_view.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 2 + [C.POINTER(C.c_int64)] + [C.POINTER(C.c_void_p)] * 4
         L.packer_insertsize_profile.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.packer_reorder_lists.restype = C.c_int64
+        L.packer_reorder_lists.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.packer_records_seen.restype = C.c_int64
         L.packer_records_seen.argtypes = [C.c_void_p]
         L.packer_bundle_side.restype = C.POINTER(C.c_uint8)
