@@ -489,7 +489,7 @@ static int check_hit_offsets(agpu_ctx *ctx, agpu_batch *b)
 }
 
 // average CIGAR operations per hit from which the evidence pass switches to the per-operation tile kernels (k_cigar_tile,
-// k_cov_add_tile).  Measured on B200 (profiles/r02_evidence_tiles.md) the thread-per-hit walk is faster at 2 operations per hit
+// k_cov_add_tile).  Measured on B200 (profiles/r02_notes.md) the thread-per-hit walk is faster at 2 operations per hit
 // (0.67 + 0.40 ms vs 1.16 + 0.75 ms at configs[1]) and still at 35 (6.3 + 3.7 ms vs 8.1 + 4.7 ms at configs[4]): the tile kernels
 // pay ~20 us of barrier-separated phases per tile.  They stay selectable (AGPU_TILE_MIN_OPS=<n>) and are parity-tested.
 static double tile_min_ops()
