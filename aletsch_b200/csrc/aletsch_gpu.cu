@@ -855,12 +855,14 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(b->b_strand.alloc(ctx, nb + 1)); TRY(b->b_span.alloc(ctx, nb + 1)); TRY(b->cov_base.alloc(ctx, nb + 2));
 	TRY(b->hit_bundle.alloc(ctx, nh + 1));
 	{
-		dbuf<int32_t> npq;
-		TRY(npq.alloc(ctx, 2 * (size_t)nb + 2));
+		dbuf<int32_t> npq, tile_bundle;
+		const int64_t n_tiles = (nh + HB_TILE - 1) / HB_TILE;
+		TRY(npq.alloc(ctx, 2 * (size_t)nb + 2)); TRY(tile_bundle.alloc(ctx, (size_t)n_tiles + 2));
 		LAUNCH_T(ctx, k_bundle_init, nb, nb, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, npq.p);
-		LAUNCH_T(ctx, k_hit_bounds, nh, b->h, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, npq.p, b->hit_bundle.p, b->err.p);
+		LAUNCH_T(ctx, k_tile_bundle, n_tiles + 1, b->h, n_tiles, tile_bundle.p);
+		LAUNCH_T(ctx, k_hit_bounds, nh, b->h, tile_bundle.p, b->b_lpos.p, b->b_rpos.p, b->b_covhi.p, npq.p, b->hit_bundle.p, b->err.p);
 		LAUNCH_T(ctx, k_bundle_finish, nb, b->h, p->library_type, b->b_lpos.p, b->b_covhi.p, npq.p, b->b_strand.p, b->b_span.p);
-		npq.release(ctx);
+		npq.release(ctx); tile_bundle.release(ctx);
 	}
 	TRY(lb_scan64(ctx, b->b_span.p, nb, b->cov_base.p));
 	b->ltot = 0;

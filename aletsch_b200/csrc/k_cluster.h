@@ -520,6 +520,8 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 	// the element array of a group of up to WARP_EL_CAP members lives in shared memory while its four levels are sorted:
 	// the per-lane std::sort replays are chains of dependent element reads and moves
 	__shared__ u64 s_el[4][WARP_EL_CAP];
+	__shared__ int s_tmp[4][4 * WARP_EL_CAP];        // range list, two position lists of the partition steps, leaf of every element
+	__shared__ unsigned char s_flag[4][WARP_EL_CAP];
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	int nb_ = *n_big;
@@ -572,9 +574,73 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 		}
 	}
 	__syncwarp();
+	key_less less;
+	if(n <= WARP_EL_CAP)
+	{
+		// everything of the group in shared memory.  A level: re-key, list the ranges, run the introsort loop of std::sort on the
+		// ranges above 16 elements (whole warp, one range after the other), then ONE pass in which every element ranks itself
+		// inside its leaf -- the stable order that the insertion sorts of std::sort leave (ncu: the per-lane insertion sorts were
+		// 40 % of this kernel's stall samples) -- then the gap flags.
+		const int wq = (threadIdx.x >> 5) & 3;
+		int *srl = s_tmp[wq], *sscr = srl + WARP_EL_CAP, *sseg = srl + 3 * WARP_EL_CAP;
+		unsigned char *sf = s_flag[wq];
+		for(int i = lane; i < n; i += 32) sf[i] = (i == 0) ? 1 : 0;
+		__syncwarp();
+		for(int r = 0; r < 4; r++)
+		{
+			for(int i = lane; i < n; i += 32) { int32_t fr = (int32_t)(u32)(el[i] & 0xffffffffULL); el[i] = pack_key(pc.key(r, fr), fr); }
+			int nr = 0;
+			for(int base = 0; base < n; base += 32)
+			{
+				int i = base + lane;
+				bool st = i < n && sf[i];
+				unsigned m = __ballot_sync(FULL, st);
+				if(st) srl[nr + __popc(m & ((1u << lane) - 1u))] = i;
+				nr += __popc(m);
+			}
+			__syncwarp();
+			for(int k = 0; k < nr; k++)
+			{
+				int lo = srl[k], hi = (k + 1 < nr) ? srl[k + 1] : n;
+				if(hi - lo > LANE_RANGE) warp_std_sort_loop(el + lo, hi - lo, less, sscr, sseg + lo, lo);
+				else if(lane < hi - lo) sseg[lo + lane] = (lo << 8) | (hi - lo);
+			}
+			__syncwarp();
+			u64 v[WARP_EL_CAP / 32];
+			int dst[WARP_EL_CAP / 32];
+#pragma unroll
+			for(int q = 0; q < WARP_EL_CAP / 32; q++)
+			{
+				const int i = lane + 32 * q;
+				dst[q] = -1;
+				if(i < n)
+				{
+					v[q] = el[i];
+					const int s = sseg[i], f = s >> 8, len = s & 0xff;
+					const u32 kv = (u32)(v[q] >> 32);
+					int rk = 0;
+					for(int j = f; j < f + len; j++)
+					{
+						const u32 kw = (u32)(el[j] >> 32);
+						rk += (kw < kv || (kw == kv && j < i)) ? 1 : 0;
+					}
+					dst[q] = f + rk;
+				}
+			}
+			__syncwarp();
+#pragma unroll
+			for(int q = 0; q < WARP_EL_CAP / 32; q++) if(dst[q] >= 0) el[dst[q]] = v[q];
+			__syncwarp();
+			for(int i = lane; i < n; i += 32)
+				if(i > 0 && !sf[i] && unpack_key(el[i]) - unpack_key(el[i - 1]) > gap) sf[i] = 1;
+			__syncwarp();
+		}
+		for(int i = lane; i < n; i += 32) { members[mo + i] = (int32_t)(u32)(el[i] & 0xffffffffULL); flag[i] = sf[i]; }
+		__syncwarp();
+		continue;
+	}
 	for(int i = lane; i < n; i += 32) flag[i] = (i == 0) ? 1 : 0;
 	__syncwarp();
-	key_less less;
 	for(int r = 0; r < 4; r++)
 	{
 		for(int i = lane; i < n; i += 32) { int32_t fr = (int32_t)(u32)(el[i] & 0xffffffffULL); el[i] = pack_key(pc.key(r, fr), fr); }

@@ -288,6 +288,78 @@ __device__ void warp_std_sort(T *a, int n, Less less, int *scratch)
 	}
 	__syncwarp();
 }
+
+// The introsort loop of warp_std_sort alone, for arrays in shared memory: what it leaves is a sequence of leaves of at most 16
+// elements whose final insertion sorts are independent STABLE sorts, so the caller can finish all leaves of all its ranges in
+// one pass in which every element ranks itself inside its leaf.  seg[i] = (first element of i's leaf, relative to `base`) << 8 |
+// leaf length; elements of heap-sorted stretches get a leaf of their own.  scratch holds 2 * n ints.
+template<typename T, typename Less>
+__device__ void warp_std_sort_loop(T *a, int n, Less less, int *scratch, int *seg, int base)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	if(n <= 16) { for(int i = lane; i < n; i += 32) seg[i] = (base << 8) | n; __syncwarp(); return; }
+	std_sort_emul<T, Less> seq(a, less);
+	int *Lp = scratch, *Rp = scratch + n;
+	int lg = 0;
+	while((n >> (lg + 1)) != 0) lg++;
+	int st_first[64], st_last[64], st_depth[64];
+	int sp = 1;
+	st_first[0] = 0; st_last[0] = n; st_depth[0] = lg * 2;
+	while(sp > 0)
+	{
+		--sp;
+		int f = st_first[sp], l = st_last[sp], d = st_depth[sp];
+		while(l - f > 16)
+		{
+			if(d == 0)
+			{
+				if(lane == 0) seq.partial_sort_all(f, l);
+				for(int i = f + lane; i < l; i += 32) seg[i] = ((base + i) << 8) | 1;
+				__syncwarp();
+				f = l;
+				break;
+			}
+			--d;
+			if(lane == 0) seq.move_median_to_first(f, f + 1, f + (l - f) / 2, l - 1);
+			__syncwarp();
+			const T pv = a[f];
+			int nL = 0, nR = 0;
+			for(int b0 = f + 1; b0 < l; b0 += 32)
+			{
+				int i = b0 + lane;
+				bool valid = i < l;
+				T x = valid ? a[i] : pv;
+				bool ge = valid && !less(x, pv);
+				bool le = valid && !less(pv, x);
+				unsigned mg = __ballot_sync(FULL, ge), ml = __ballot_sync(FULL, le);
+				unsigned below = (1u << lane) - 1u;
+				if(ge) Lp[nL + __popc(mg & below)] = i;
+				if(le) Rp[nR + __popc(ml & below)] = i;
+				nL += __popc(mg); nR += __popc(ml);
+			}
+			__syncwarp();
+			int m = nL < nR ? nL : nR;
+			int cnt = 0;
+			for(int k = lane; k < m; k += 32) if(Lp[k] < Rp[nR - 1 - k]) cnt++;
+			for(int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(FULL, cnt, o);
+			const int K = cnt;
+			for(int k = lane; k < K; k += 32)
+			{
+				int x = Lp[k], y = Rp[nR - 1 - k];
+				T t = a[x]; a[x] = a[y]; a[y] = t;
+			}
+			int cut = l;
+			if(K > 0) cut = Rp[nR - K];
+			if(K < nL && Lp[K] < cut) cut = Lp[K];
+			__syncwarp();
+			st_first[sp] = cut; st_last[sp] = l; st_depth[sp] = d; sp++;
+			l = cut;
+		}
+		if(l - f > 0 && lane < l - f) seg[f + lane] = ((base + f) << 8) | (l - f);
+	}
+	__syncwarp();
+}
 #endif
 
 } // namespace agpu
