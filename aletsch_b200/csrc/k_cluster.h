@@ -508,6 +508,165 @@ KERNEL k_group_partition(int64_t n_frg, const int32_t *f_bundle, const int64_t *
 }
 
 #ifndef AGPU_EMU
+// The introsort loop of std::sort (libstdc++: __introsort_loop, see stdsort.h) for 17 .. 32 elements held ONE PER LANE, lanes
+// [f0, l0): the median-of-three, the partition step (the k-th element from the left that is not less than the pivot swaps with
+// the k-th from the right that the pivot is not less than, while the former lies left of the latter) and the cut are bit
+// arithmetic on two ballots (__fns finds the k-th set bit), the swaps one shuffle.  On return every lane of the range knows the
+// leaf (first lane, length <= 16) whose stable insertion sort finishes std::sort; the caller ranks the elements inside the leaves.
+// The depth-limit fallback (heap sort) goes through shared memory `sh`, sequentially, like the reference's.
+__device__ __forceinline__ u32 ws32_key(u64 e) { return (u32)(e >> 32); }
+__device__ void warp_sort32_loop(u64 &x, int f0, int l0, int lane, int &leaf_f, int &leaf_len, u64 *sh)
+{
+	const unsigned FULL = 0xffffffffu;
+	const unsigned below = (1u << lane) - 1u, above = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+	const int n = l0 - f0;
+	int lg = 0;
+	while((n >> (lg + 1)) != 0) lg++;
+	int st_f[24], st_l[24], st_d[24];
+	int sp = 1;
+	st_f[0] = f0; st_l[0] = l0; st_d[0] = lg * 2;
+	while(sp > 0)
+	{
+		--sp;
+		int f = st_f[sp], l = st_l[sp], d = st_d[sp];
+		while(l - f > 16)
+		{
+			if(d == 0)
+			{
+				sh[lane] = x;
+				__syncwarp();
+				if(lane == 0) { key_less less; std_sort_emul<u64, key_less> seq(sh, less); seq.partial_sort_all(f, l); }
+				__syncwarp();
+				x = sh[lane];
+				__syncwarp();
+				if(lane >= f && lane < l) { leaf_f = lane; leaf_len = 1; }
+				f = l;
+				break;
+			}
+			--d;
+			const int mid = f + (l - f) / 2;
+			const u32 kx = ws32_key(__shfl_sync(FULL, x, f + 1)), ky = ws32_key(__shfl_sync(FULL, x, mid)), kz = ws32_key(__shfl_sync(FULL, x, l - 1));
+			int p;                                                        // __move_median_to_first(f, f + 1, mid, l - 1)
+			if(kx < ky) { if(ky < kz) p = mid; else if(kx < kz) p = l - 1; else p = f + 1; }
+			else if(kx < kz) p = f + 1;
+			else if(ky < kz) p = l - 1;
+			else p = mid;
+			{
+				const u64 vf = __shfl_sync(FULL, x, f), vp = __shfl_sync(FULL, x, p);
+				if(lane == f) x = vp; else if(lane == p) x = vf;
+			}
+			const u32 kp = ws32_key(__shfl_sync(FULL, x, f)), kme = ws32_key(x);
+			const bool valid = lane > f && lane < l;
+			const bool ge = valid && !(kme < kp), le = valid && !(kp < kme);
+			const unsigned mg = __ballot_sync(FULL, ge), ml = __ballot_sync(FULL, le);
+			const int nL = __popc(mg), nR = __popc(ml);
+			int src = lane;
+			bool left = false;
+			if(ge)
+			{
+				const int k = __popc(mg & below);
+				if(k < nR) { const unsigned y = __fns(ml, 31, -(k + 1)); if((unsigned)lane < y) { src = (int)y; left = true; } }
+			}
+			const int K = __popc(__ballot_sync(FULL, left));
+			if(le && !left)
+			{
+				const int k2 = __popc(ml & above);
+				if(k2 < nL) { const unsigned z = __fns(mg, 0, k2 + 1); if(z < (unsigned)lane) src = (int)z; }
+			}
+			x = __shfl_sync(FULL, x, src);
+			int cut = l;
+			if(K > 0) cut = (int)__fns(ml, 31, -K);
+			if(K < nL) { const int lk = (int)__fns(mg, 0, K + 1); if(lk < cut) cut = lk; }
+			st_f[sp] = cut; st_l[sp] = l; st_d[sp] = d; sp++;
+			l = cut;
+		}
+		if(l - f > 0 && lane >= f && lane < l) { leaf_f = f; leaf_len = l - f; }
+	}
+}
+
+// One level of graph_cluster::partition for a group of <= 32 elements, one per lane: std::sort of every current range (range
+// starts = lanes with sf set) by the key in the high word.
+__device__ void warp_sort_level32(u64 &x, bool have, bool sf, int n, int lane, u64 *sh)
+{
+	const unsigned FULL = 0xffffffffu;
+	const unsigned ms = __ballot_sync(FULL, have && sf);     // range starts; bit 0 is always set
+	const int lo = 31 - __clz(ms & (0xffffffffu >> (31 - lane)));
+	const unsigned up = lane == 31 ? 0u : (ms & (0xffffffffu << (lane + 1)));
+	const int hi = up ? __ffs((int)up) - 1 : n;
+	int leaf_f = have ? lo : lane, leaf_len = have ? hi - lo : 0;
+	// at most one range of a group of <= 32 exceeds 16 elements: the introsort loop runs on that one
+	const unsigned big = __ballot_sync(FULL, have && sf && hi - lo > 16);
+	if(big)
+	{
+		const int s0 = __ffs((int)big) - 1, e0 = __shfl_sync(FULL, hi, s0);
+		warp_sort32_loop(x, s0, e0, lane, leaf_f, leaf_len, sh);
+	}
+	// every element ranks itself inside its leaf: the stable order the insertion sorts of std::sort leave
+	int rk = 0;
+	const u32 kv = (u32)(x >> 32);
+	for(int j = 0; j < 16; j++)
+	{
+		const int idx = leaf_f + j;
+		const u64 o = __shfl_sync(FULL, x, idx & 31);
+		if(j < leaf_len) { const u32 ko = (u32)(o >> 32); rk += (ko < kv || (ko == kv && idx < lane)) ? 1 : 0; }
+	}
+	if(have) sh[leaf_f + rk] = x;
+	__syncwarp();
+	if(have) x = sh[lane];
+	__syncwarp();
+}
+
+// The same for a group of up to WARP_EL_CAP elements in shared memory (range starts = sf[i] set): the introsort loop on the
+// ranges above 16 elements (whole warp, one range after the other), then ONE pass in which every element ranks itself inside
+// its leaf.  srl: WARP_EL_CAP ints (range list), sscr: 2 * WARP_EL_CAP ints, sseg: WARP_EL_CAP ints.
+__device__ void warp_sort_level128(u64 *el, int n, const unsigned char *sf, int *srl, int *sscr, int *sseg, int lane)
+{
+	const unsigned FULL = 0xffffffffu;
+	key_less less;
+	int nr = 0;
+	for(int base = 0; base < n; base += 32)
+	{
+		int i = base + lane;
+		bool st = i < n && sf[i];
+		unsigned m = __ballot_sync(FULL, st);
+		if(st) srl[nr + __popc(m & ((1u << lane) - 1u))] = i;
+		nr += __popc(m);
+	}
+	__syncwarp();
+	for(int k = 0; k < nr; k++)
+	{
+		int lo = srl[k], hi = (k + 1 < nr) ? srl[k + 1] : n;
+		if(hi - lo > LANE_RANGE) warp_std_sort_loop(el + lo, hi - lo, less, sscr, sseg + lo, lo);
+		else if(lane < hi - lo) sseg[lo + lane] = (lo << 8) | (hi - lo);
+	}
+	__syncwarp();
+	u64 v[WARP_EL_CAP / 32];
+	int dst[WARP_EL_CAP / 32];
+#pragma unroll
+	for(int q = 0; q < WARP_EL_CAP / 32; q++)
+	{
+		const int i = lane + 32 * q;
+		dst[q] = -1;
+		if(i < n)
+		{
+			v[q] = el[i];
+			const int s = sseg[i], f = s >> 8, len = s & 0xff;
+			const u32 kv = (u32)(v[q] >> 32);
+			int rk = 0;
+			for(int j = f; j < f + len; j++)
+			{
+				const u32 kw = (u32)(el[j] >> 32);
+				rk += (kw < kv || (kw == kv && j < i)) ? 1 : 0;
+			}
+			dst[q] = f + rk;
+		}
+	}
+	__syncwarp();
+#pragma unroll
+	for(int q = 0; q < WARP_EL_CAP / 32; q++) if(dst[q] >= 0) el[dst[q]] = v[q];
+	__syncwarp();
+}
+
 // One warp per big group: members gathered in fragment order by scanning the bundle's fragments, then the four
 // partition levels breadth first.  A level = (re)key every element, sort every current range with the std::sort
 // permutation (big ranges by the whole warp, small ones one lane each), then open a new range wherever the gap
@@ -545,6 +704,32 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 	pc.f_h1 = f_h1 + f0; pc.f_h2 = f_h2 + f0;
 	pc.pos = h.pos + h.bundle_hit_off[b]; pc.rpos = h.rpos + h.bundle_hit_off[b];
 	pc.gap = gap;
+	if(n <= 32)
+	{
+		// ---- 17 .. 32 members (nine in ten of the big groups at configs[1]): one element per lane, the four levels in registers
+		u64 *sh = s_el[(threadIdx.x >> 5) & 3];
+		const bool have = lane < n;
+		u64 x = have ? (u64)(u32)members[mo + lane] : ~0ULL;          // the group's window, unordered
+		{
+			int rk = 0;                                              // ascending fragment index: rank by counting (distinct values)
+			for(int j = 0; j < n; j++) { const u64 o = __shfl_sync(FULL, x, j); rk += o < x ? 1 : 0; }
+			if(have) sh[rk] = x;
+			__syncwarp();
+			if(have) x = sh[lane];
+			__syncwarp();
+		}
+		bool sf = lane == 0;
+		for(int r = 0; r < 4; r++)
+		{
+			if(have) { const int32_t fr = (int32_t)(u32)(x & 0xffffffffULL); x = pack_key(pc.key(r, fr), fr); }
+			warp_sort_level32(x, have, sf, n, lane, sh);
+			const u64 prev = __shfl_up_sync(FULL, x, 1);
+			if(have && lane > 0 && !sf && unpack_key(x) - unpack_key(prev) > gap) sf = true;
+		}
+		if(have) { members[mo + lane] = (int32_t)(u32)(x & 0xffffffffULL); flag[lane] = sf ? 1 : 0; }
+		__syncwarp();
+		continue;
+	}
 	// members in ascending fragment index
 	if(n <= 1024 && (int64_t)n * n < (int64_t)nfb * 4)
 	{
@@ -589,48 +774,7 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 		for(int r = 0; r < 4; r++)
 		{
 			for(int i = lane; i < n; i += 32) { int32_t fr = (int32_t)(u32)(el[i] & 0xffffffffULL); el[i] = pack_key(pc.key(r, fr), fr); }
-			int nr = 0;
-			for(int base = 0; base < n; base += 32)
-			{
-				int i = base + lane;
-				bool st = i < n && sf[i];
-				unsigned m = __ballot_sync(FULL, st);
-				if(st) srl[nr + __popc(m & ((1u << lane) - 1u))] = i;
-				nr += __popc(m);
-			}
-			__syncwarp();
-			for(int k = 0; k < nr; k++)
-			{
-				int lo = srl[k], hi = (k + 1 < nr) ? srl[k + 1] : n;
-				if(hi - lo > LANE_RANGE) warp_std_sort_loop(el + lo, hi - lo, less, sscr, sseg + lo, lo);
-				else if(lane < hi - lo) sseg[lo + lane] = (lo << 8) | (hi - lo);
-			}
-			__syncwarp();
-			u64 v[WARP_EL_CAP / 32];
-			int dst[WARP_EL_CAP / 32];
-#pragma unroll
-			for(int q = 0; q < WARP_EL_CAP / 32; q++)
-			{
-				const int i = lane + 32 * q;
-				dst[q] = -1;
-				if(i < n)
-				{
-					v[q] = el[i];
-					const int s = sseg[i], f = s >> 8, len = s & 0xff;
-					const u32 kv = (u32)(v[q] >> 32);
-					int rk = 0;
-					for(int j = f; j < f + len; j++)
-					{
-						const u32 kw = (u32)(el[j] >> 32);
-						rk += (kw < kv || (kw == kv && j < i)) ? 1 : 0;
-					}
-					dst[q] = f + rk;
-				}
-			}
-			__syncwarp();
-#pragma unroll
-			for(int q = 0; q < WARP_EL_CAP / 32; q++) if(dst[q] >= 0) el[dst[q]] = v[q];
-			__syncwarp();
+			warp_sort_level128(el, n, sf, srl, sscr, sseg, lane);
 			for(int i = lane; i < n; i += 32)
 				if(i > 0 && !sf[i] && unpack_key(el[i]) - unpack_key(el[i - 1]) > gap) sf[i] = 1;
 			__syncwarp();
@@ -684,10 +828,30 @@ KERNEL k_debug_sort(const int32_t *keys, int n, u64 *el, int32_t *scratch, int32
 	key_less less;
 #ifndef AGPU_EMU
 	const int lane = threadIdx.x & 31;
+	// the same dispatch as k_group_partition_warp: <= 16 one lane, <= 32 in registers, <= WARP_EL_CAP in shared memory
+	__shared__ u64 d_el[WARP_EL_CAP];
+	__shared__ int d_tmp[4 * WARP_EL_CAP];
+	__shared__ unsigned char d_flag[WARP_EL_CAP];
 	for(int i = lane; i < n; i += 32) el[i] = pack_key(keys[i], i);
 	__syncwarp();
-	if(n > LANE_RANGE) warp_std_sort(el, n, less, scratch);
-	else { if(lane == 0) std_sort_handles(el, n, less); __syncwarp(); }
+	if(n <= LANE_RANGE) { if(lane == 0) std_sort_handles(el, n, less); __syncwarp(); }
+	else if(n <= 32)
+	{
+		const bool have = lane < n;
+		u64 x = have ? el[lane] : ~0ULL;
+		warp_sort_level32(x, have, lane == 0, n, lane, d_el);
+		if(have) el[lane] = x;
+		__syncwarp();
+	}
+	else if(n <= WARP_EL_CAP)
+	{
+		for(int i = lane; i < n; i += 32) { d_el[i] = el[i]; d_flag[i] = i == 0; }
+		__syncwarp();
+		warp_sort_level128(d_el, n, d_flag, d_tmp, d_tmp + WARP_EL_CAP, d_tmp + 3 * WARP_EL_CAP, lane);
+		for(int i = lane; i < n; i += 32) el[i] = d_el[i];
+		__syncwarp();
+	}
+	else warp_std_sort(el, n, less, scratch);
 	for(int i = lane; i < n; i += 32) perm[i] = (int32_t)(u32)(el[i] & 0xffffffffULL);
 #else
 	for(int i = 0; i < n; i++) el[i] = pack_key(keys[i], i);

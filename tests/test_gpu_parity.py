@@ -331,10 +331,13 @@ def test_std_sort_permutation(ctx):
     L = C.CDLL(orclib.ORC_SO)
     L.orc_std_sort_perm.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     rng = np.random.default_rng(5)
-    sizes = [1, 2, 15, 16, 17, 31, 33, 48, 49, 64, 100, 257, 1000, 4096, 20000]
+    # 17 .. 32: one element per lane in registers; 33 .. 128: in shared memory; above: the warp-cooperative replay in global memory
+    sizes = [1, 2, 15, 16] + list(range(17, 34)) + [47, 48, 49, 64, 65, 100, 127, 128, 129, 257, 1000, 4096, 20000]
     for n in sizes:
-        for kind in range(6):
-            if kind == 0:
+        for kind in range(10):
+            if kind >= 6:
+                keys = rng.integers(0, (2, 3, 8, 1 << 20)[kind - 6], n)
+            elif kind == 0:
                 keys = rng.integers(0, 4, n)
             elif kind == 1:
                 keys = rng.integers(0, max(2, n // 3), n)
