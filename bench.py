@@ -354,6 +354,11 @@ def run_ours(args):
         c.profile(False)
     counts = sum_counts()
     per_bundle = np.concatenate([x.bundle_counts() for x in bts]) if bts else np.zeros((0, 4), np.int64)   # [NB, 4]: segments, fragments, clusters, bridged
+    # digests of the result arrays of every bundle (for the full-size cross-check against the reference run, cpu_baseline)
+    digests = None
+    if not args.no_cpu_baseline and rank == 0:
+        digests = np.concatenate([view_digests(x.results(G.RESULT_EVIDENCE | G.RESULT_FRAGMENTS), x_part.n_bundles)
+                                  for x, x_part in zip(bts, parts)]) if bts else np.zeros((0, 3), np.uint64)
     stage5 = stage5_gpu(ctx, bts, batch, parts, cfg, args) if not args.no_stage5 else None
     single = len(parts) == 1
     group_leg = group_bridge_gpu(ctx, bt, gp, stage5_gpu.clusters, args) if (stage5 is not None and single and cfg["mode"] == "paired") else None
@@ -591,7 +596,7 @@ def run_ours(args):
         if phase_leg is not None:
             out["phase_set"] = phase_leg
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(batch, cfg, min(10, ncpu), args.cpu_seconds, gpu_bridged=per_bundle[:, 3])
+            out["cpu_baseline"] = cpu_baseline(batch, cfg, min(10, ncpu), args.cpu_seconds, gpu_bridged=per_bundle[:, 3], gpu_digests=digests)
             if stage5 is not None:
                 out["stage5"]["cpu_baseline"] = stage5_cpu(batch, cfg, min(10, ncpu), max(2.0, args.cpu_seconds / 4))
             if group_leg is not None:
@@ -1014,6 +1019,13 @@ class RefTimer:
         self.lib.ref_timing_run(self.h, self.threads, C.byref(sec), C.byref(br), self.per.ctypes.data)
         return sec.value, int(br.value)
 
+    def digests(self):
+        """[n_sample, 3] uint64: ref_timing_digest (untimed) -- mmap segments, frgs, splices of every sampled bundle after bundle::bridge()"""
+        self.lib.ref_timing_digest.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        d = np.zeros((max(len(self.sample), 1), 3), np.uint64)
+        self.lib.ref_timing_digest(self.h, self.threads, d.ctypes.data)
+        return d[:len(self.sample)]
+
     def describe(self, sec):
         return "every %d-th bundle of the same batch: %d bundles, %d hits, %.2f s per pass" % (self.step, len(self.sample), self.hits, sec)
 
@@ -1023,7 +1035,51 @@ class RefTimer:
             self.h = None
 
 
-def cpu_baseline(batch, cfg, threads, budget_s, gpu_bridged=None):
+def _mix_rows(a, b, c, j):
+    """row_digest of oracle/ref_driver.cc on arrays (uint64 arithmetic wraps)"""
+    u = lambda v: np.asarray(v).astype(np.uint32).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        x = (u(a) * np.uint64(0x9E3779B97F4A7C15)) ^ (u(b) * np.uint64(0xC2B2AE3D27D4EB4F)) ^ (u(c) * np.uint64(0x165667B19E3779F9)) \
+            ^ (j.astype(np.uint64) * np.uint64(0xD6E8FEB86659FD93))
+        x ^= x >> np.uint64(30)
+        x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27)
+        x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    return x
+
+
+def _segmented_sum(x, off):
+    """wrapping uint64 sums of x[off[k]:off[k+1]]"""
+    n = len(off) - 1
+    out = np.zeros(n, np.uint64)
+    if len(x) == 0 or n == 0:
+        return out
+    with np.errstate(over="ignore"):
+        cs = np.concatenate([np.zeros(1, np.uint64), np.cumsum(x, dtype=np.uint64)])
+        out[:] = cs[off[1:]] - cs[off[:-1]]
+    return out
+
+
+def view_digests(res, n_bundles):
+    """[NB, 3] uint64 from the views of agpu_batch_results(EVIDENCE | FRAGMENTS): the digests ref_timing_digest forms from the
+    reference's own bundle objects (mmap segments, frgs, splices), per bundle"""
+    ev, fr = res.evidence, res.fragments
+    out = np.zeros((n_bundles, 3), np.uint64)
+    for col, (off_p, val_p, width) in enumerate(((ev.seg_off, ev.seg, 3), (fr.frg_off, fr.frgs, 3), (ev.splice_off, ev.splices, 1))):
+        off = np.ctypeslib.as_array(off_p, shape=(n_bundles + 1,)).astype(np.int64)
+        tot = int(off[-1])
+        if tot == 0:
+            continue
+        v = np.ctypeslib.as_array(val_p, shape=(tot * width,)).reshape(tot, width)
+        j = np.arange(tot, dtype=np.int64) - np.repeat(off[:-1], np.diff(off))
+        z = np.zeros(tot, np.int32)
+        x = _mix_rows(v[:, 0], v[:, 1] if width > 1 else z, v[:, 2] if width > 2 else z, j)
+        out[:, col] = _segmented_sum(x, off)
+    return out
+
+
+def cpu_baseline(batch, cfg, threads, budget_s, gpu_bridged=None, gpu_digests=None):
     """the reference's own C++ (oracle/_ref) over a bounded sample of the same bundles (RefTimer), one untimed warm-up pass and
     then passes until the budget is used; the restatement (oracle/liboracle.so, kind "port") only if the reference build is absent"""
     if _checker_kind() != "reference":
@@ -1044,6 +1100,14 @@ def cpu_baseline(batch, cfg, threads, budget_s, gpu_bridged=None):
         # full-size cross-check: the bridged-pair count of every sampled bundle, CUDA path vs this CPU run
         bad = [int(k) for k, c in zip(rt.sample, rt.per) if int(gpu_bridged[k]) != int(c)]
         out["bridged_count_check"] = {"bundles": len(rt.sample), "mismatches": len(bad), "first": bad[:5]}
+    if gpu_digests is not None:
+        # full-size cross-check of the arrays themselves: order-sensitive digests of every sampled bundle's mmap segments, frgs and
+        # splices as the reference's own objects hold them after bundle::bridge() (untimed pass) vs the views the CUDA path returned
+        want = rt.digests()
+        got = gpu_digests[np.asarray(rt.sample, np.int64)] if len(rt.sample) else want
+        bad = np.nonzero((want != got).any(axis=1))[0]
+        out["array_digest_check"] = {"bundles": len(rt.sample), "arrays": ["mmap segments (l, r, cov)", "frgs (h1, h2, type)", "splices"],
+                                     "mismatches": int(len(bad)), "first": [int(rt.sample[k]) for k in bad[:5]]}
     rt.close()
     return out
 

@@ -441,6 +441,56 @@ int ref_timing_run(void *tp, int threads, double *seconds, int64_t *bridged, int
 	return 0;
 }
 
+// Full-size cross-check (untimed): the same per-bundle work as ref_timing_run, then three order-sensitive 64-bit digests of what
+// bundle::bridge leaves behind -- digest[3k] over the mmap segments (lower, upper, coverage), [3k + 1] over frgs (h1, h2, type),
+// [3k + 2] over bundle::splices -- each the wrapping sum over the rows j of row_digest(a, b, c, j).  bench.py forms the same
+// digests from the views of agpu_batch_results (bench.py: view_digests).
+static inline uint64_t row_digest(int32_t a, int32_t b, int32_t c, uint64_t j)
+{
+	uint64_t x = (uint64_t)(uint32_t)a * 0x9E3779B97F4A7C15ULL ^ (uint64_t)(uint32_t)b * 0xC2B2AE3D27D4EB4FULL
+		^ (uint64_t)(uint32_t)c * 0x165667B19E3779F9ULL ^ j * 0xD6E8FEB86659FD93ULL;
+	x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 27; x *= 0x94D049BB133111EBULL; x ^= x >> 31;
+	return x;
+}
+int ref_timing_digest(void *tp, int threads, uint64_t *digest)
+{
+	ref_timing *t = (ref_timing*)tp;
+	const int n = (int)t->bundles.size();
+	if(threads < 1) threads = 1;
+	std::atomic<int> next(0);
+	auto work = [&]()
+	{
+		while(true)
+		{
+			int k = next.fetch_add(1);
+			if(k >= n) return;
+			ref_timing_bundle &tb = t->bundles[k];
+			bundle bd(t->cfg, t->sp);
+			bam1_t b1t;
+			for(size_t i = 0; i < tb.hits.size(); i++)
+			{
+				hts_shim_view(tb.recs[i], &b1t);
+				bd.add_hit_intervals(tb.hits[i], &b1t);
+			}
+			bd.add_buf_intervals();
+			bd.splices = bd.hcst.get_splices();
+			bd.chrm = "chr";
+			bd.compute_strand(t->sp.library_type);
+			bd.build_fragments();
+			bd.bridge();
+			uint64_t d0 = 0, d1 = 0, d2 = 0, j = 0;
+			for(SIMI it = bd.mmap.begin(); it != bd.mmap.end(); ++it, ++j) d0 += row_digest(lower(it->first), upper(it->first), it->second, j);
+			for(size_t f = 0; f < bd.frgs.size(); f++) d1 += row_digest(bd.frgs[f][0], bd.frgs[f][1], bd.frgs[f][2], (uint64_t)f);
+			for(size_t s = 0; s < bd.splices.size(); s++) d2 += row_digest(bd.splices[s], 0, 0, (uint64_t)s);
+			digest[3 * (size_t)k] = d0; digest[3 * (size_t)k + 1] = d1; digest[3 * (size_t)k + 2] = d2;
+		}
+	};
+	std::vector<std::thread> pool;
+	for(int i = 0; i < threads; i++) pool.push_back(std::thread(work));
+	for(size_t i = 0; i < pool.size(); i++) pool[i].join();
+	return 0;
+}
+
 int ref_bundle_evidence(void *b, void *bag)
 {
 	dump_evidence(*(ref_handle*)b, *(orc_bag*)bag);
