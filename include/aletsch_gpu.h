@@ -90,7 +90,17 @@ void agpu_default_params(agpu_params *p);
  *   - strand[] / xs[] hold '+', '-' or '.'; all hits of a bundle share strand[]
  *     (rnacore/bundle_base.cc:100-101).
  * agpu_batch_evidence verifies these on the device and returns AGPU_ERR_INPUT if violated.
- * All arrays are caller-owned host memory (pinned memory makes the upload asynchronous). */
+ * All arrays are caller-owned host memory (pinned memory makes the upload asynchronous).
+ * BATCHING RULE.  One batch holds n_cigar < 2^32 CIGAR operations (cigar_off is 32 bits) and fewer than 2^32 - 64 coverage-window
+ * positions: the sum over its bundles of (largest rpos - smallest pos + 1) rounded up to 128 (the border bitmap is indexed with
+ * 32 bits).  agpu_batch_evidence returns AGPU_ERR_CAPACITY for a larger one and nothing partial is kept: cut the bundles of a
+ * region batch into contiguous runs of whole bundles below both bounds -- bundles are independent (meta/bundle.cc:55-88), so the
+ * cut changes no result.  bench.py: device_batches() is that cut (window estimated from the hits with 512 positions of slack per
+ * bundle); the whole human genome at the depth of BASELINE configs[2] needs 4 such batches per 3 chromosomes.
+ * QNAME KEYS.  qid[] stands for the query name: two hits of a bundle pair only if their keys are equal, so equal keys must mean
+ * equal names INSIDE A BUNDLE.  host/bamio.cc (bam_read_records) hashes the name to 64 bits and verifies every key against a
+ * 128-bit identity of the name inside the pairing window, re-keying a colliding name; a host that packs its own keys owes the
+ * same guarantee (0xffffffffffffffff is reserved: AGPU_ERR_INPUT). */
 typedef struct agpu_batch_in
 {
 	int32_t n_bundles;
