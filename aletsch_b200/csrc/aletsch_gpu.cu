@@ -278,6 +278,21 @@ static int lb_scan64(agpu_ctx *ctx, const int64_t *v, int64_t n, int64_t *out)
 	return AGPU_OK;
 }
 
+// k (<= 8) int64 arrays of the same length: one launch while they fit a CTA each
+static int lb_scan64_multi(agpu_ctx *ctx, int k, const int64_t *const *v, int64_t n, int64_t *const *out)
+{
+	if(n <= SMALL_SCAN_MAX && k <= 8)
+	{
+		small_scan_set s;
+		memset(&s, 0, sizeof(s));
+		for(int i = 0; i < k; i++) { s.in[i] = v[i]; s.out[i] = out[i]; }
+		LAUNCH_B(ctx, k_small_scan_i64_multi, k, SMALL_SCAN_THREADS, s, n);
+		return AGPU_OK;
+	}
+	for(int i = 0; i < k; i++) TRY(lb_scan64(ctx, v[i], n, out[i]));
+	return AGPU_OK;
+}
+
 template<typename T> static int pull(agpu_ctx *ctx, agpu_batch *b, const std::string &name, const T *dev, size_t n, T **out)
 {
 	T *h = b->host<T>(name, n);
@@ -923,10 +938,11 @@ int agpu_batch_graph(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	in.seg_nhead = b->seg_nhead.p; in.seg_psum = b->seg_psum.p;
 	for(int k = 0; k < 5; k++) { TRY(gs.ub[k].alloc(ctx, nb + 1)); TRY(gs.off[k].alloc(ctx, nb + 2)); }
 	LAUNCH_B(ctx, k_graph_bounds, nb, 128, in, gs.ub[0].p, gs.ub[1].p, gs.ub[2].p, gs.ub[3].p, gs.ub[4].p);
-	for(int k = 0; k < 5; k++)
 	{
-		TRY(lb_scan64(ctx, gs.ub[k].p, nb, gs.off[k].p));
-		TRY(d2h(ctx, &gs.tot[k], gs.off[k].p + nb, sizeof(int64_t)));
+		const int64_t *in5[5]; int64_t *out5[5];
+		for(int k = 0; k < 5; k++) { in5[k] = gs.ub[k].p; out5[k] = gs.off[k].p; }
+		TRY(lb_scan64_multi(ctx, 5, in5, nb, out5));
+		for(int k = 0; k < 5; k++) TRY(d2h(ctx, &gs.tot[k], gs.off[k].p + nb, sizeof(int64_t)));
 	}
 	TRY(stream_sync(ctx));
 	int64_t J = gs.tot[0], P = gs.tot[1], E = gs.tot[2];

@@ -102,6 +102,29 @@ DEV int block_excl_scan(int *a, int n)
 {
 	__shared__ int wsum[AGPU_MAX_BLOCK / 32];
 	const int nt = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5, nw = (nt + 31) >> 5;
+	if(n == nt * 8 && (nt & 31) == 0 && ((size_t)a & 15) == 0)
+	{
+		// a full tile of eight values per thread (the look-back kernels): every thread scans eight CONSECUTIVE values in registers
+		// (two 128-bit shared-memory accesses each way), then one scan of the thread sums -- three barriers instead of seventeen
+		__syncthreads();
+		int4 *p = (int4*)(a + t * 8);
+		int4 u = p[0], v = p[1];
+		const int x0 = u.x, x1 = u.y, x2 = u.z, x3 = u.w, x4 = v.x, x5 = v.y, x6 = v.z, x7 = v.w;
+		const int tsum = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+		int inc = tsum;
+#pragma unroll
+		for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+		if(lane == 31) wsum[w] = inc;
+		__syncthreads();
+		int pre = 0, tot = 0;
+		for(int k = 0; k < nw; k++) { int s = wsum[k]; if(k < w) pre += s; tot += s; }
+		int run = pre + inc - tsum;
+		u.x = run; run += x0; u.y = run; run += x1; u.z = run; run += x2; u.w = run; run += x3;
+		v.x = run; run += x4; v.y = run; run += x5; v.z = run; run += x6; v.w = run;
+		p[0] = u; p[1] = v;
+		__syncthreads();
+		return tot;
+	}
 	int carry = 0;
 	for(int base = 0; base < n; base += nt)
 	{

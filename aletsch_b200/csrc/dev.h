@@ -26,6 +26,7 @@
 #define DEV __device__ __forceinline__
 #define KERNEL __global__ void
 #define SHARED __shared__
+#define SHARED16 __shared__ __align__(16)        // tiles block_excl_scan reads with 128-bit accesses
 #define BLOCK_SYNC() __syncthreads()
 #else
 // ---------------------------------------------------------------- host emulation (tests only)
@@ -33,6 +34,7 @@
 #define DEV inline
 #define KERNEL static void
 #define SHARED static thread_local
+#define SHARED16 static thread_local
 #define BLOCK_SYNC() do {} while(0)
 struct agpu_emu_dim { unsigned x, y, z; };
 extern thread_local agpu_emu_dim threadIdx, blockIdx, blockDim, gridDim;

@@ -786,7 +786,7 @@ KERNEL k_seg_nhead(int64_t n, const int64_t *hrank, const int64_t *heads, int64_
 // wrank[w] = number of borders before bitmap word w (wrank[n_words] = total); *total gets the number of borders
 KERNEL k_lb_bord_rank(lb_ctl c, const u32 *border, int64_t n_words, u32 *wrank, int64_t *total)
 {
-	SHARED int f[LB_TILE];
+	SHARED16 int f[LB_TILE];
 	const int64_t n_tiles = (n_words + 1 + LB_TILE - 1) / LB_TILE;
 	for(int64_t t = lb_next_tile(c, n_tiles); t >= 0; t = lb_next_tile(c, n_tiles))
 	{
@@ -817,9 +817,9 @@ KERNEL k_lb_bord_rank(lb_ctl c, const u32 *border, int64_t n_words, u32 *wrank, 
 KERNEL k_lb_cov_segments(lb_ctl c, const int32_t *diffc, const int32_t *posc, int64_t n, int32_t n_bundles, const int64_t *bord_off,
 		int32_t *cov, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c, int64_t *seg_off, int32_t *seg_head, int64_t *seg_psum, int64_t *n_seg)
 {
-	SHARED int f[LB_TILE + 1];       // local prefix of the differences, then of the segment flags
+	SHARED16 int f[LB_TILE + 1];     // local prefix of the differences, then of the segment flags
 	SHARED int cv[LB_TILE + 1];      // coverage of the tile's borders; cv[LB_TILE]: coverage of the border before the tile
-	SHARED int pr[LB_TILE];          // products, then their local prefix
+	SHARED16 int pr[LB_TILE];         // products, then their local prefix
 	const int64_t n_tiles = (n + 1 + LB_TILE - 1) / LB_TILE;
 	for(int64_t t = lb_next_tile(c, n_tiles); t >= 0; t = lb_next_tile(c, n_tiles))
 	{
