@@ -718,15 +718,29 @@ __global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_
 			if(have) x = sh[lane];
 			__syncwarp();
 		}
+		// the four keys of every fragment are loaded ONCE (two rounds of dependent loads instead of eight) and stay in the lane
+		// that loaded them; the element that travels through the sorts carries that lane's number in its low word (the
+		// comparisons only read the key in the high word), and a level fetches its key with one shuffle
+		const int32_t fr0 = (int32_t)(u32)(x & 0xffffffffULL);
+		int32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+		if(have)
+		{
+			const int32_t h1 = pc.f_h1[fr0], h2 = pc.f_h2[fr0];
+			k0 = pc.pos[h1]; k1 = pc.rpos[h1]; k2 = pc.pos[h2]; k3 = pc.rpos[h2];
+		}
+		x = (u64)(u32)lane;
 		bool sf = lane == 0;
 		for(int r = 0; r < 4; r++)
 		{
-			if(have) { const int32_t fr = (int32_t)(u32)(x & 0xffffffffULL); x = pack_key(pc.key(r, fr), fr); }
+			const int slot = (int)(x & 31u);
+			const int32_t kr = __shfl_sync(FULL, r == 0 ? k0 : (r == 1 ? k1 : (r == 2 ? k2 : k3)), slot);
+			if(have) x = pack_key(kr, slot);
 			warp_sort_level32(x, have, sf, n, lane, sh);
 			const u64 prev = __shfl_up_sync(FULL, x, 1);
 			if(have && lane > 0 && !sf && unpack_key(x) - unpack_key(prev) > gap) sf = true;
 		}
-		if(have) { members[mo + lane] = (int32_t)(u32)(x & 0xffffffffULL); flag[lane] = sf ? 1 : 0; }
+		const int32_t fr_out = __shfl_sync(FULL, fr0, (int)(x & 31u));
+		if(have) { members[mo + lane] = fr_out; flag[lane] = sf ? 1 : 0; }
 		__syncwarp();
 		continue;
 	}
