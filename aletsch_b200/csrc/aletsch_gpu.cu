@@ -161,8 +161,6 @@ struct agpu_batch
 	dbuf<int32_t> tile_owner;              // hit owning the first operation of every tile of CG_TILE CIGAR operations
 	int32_t n_large = 0;
 	// regions of the per-bundle qname tables (mate pairing): a power of two >= 1.5 x the bundle's hits
-	dbuf<int64_t> qreg_off;
-	int64_t q_slots = 0;
 
 	dbuf<int> err;
 
@@ -546,7 +544,7 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 	b->n_large = 0;
 	while(b->n_large < b->nb && ho[ord[b->n_large] + 1] - ho[ord[b->n_large]] >= LARGE_BUNDLE_HITS) b->n_large++;
 	// staged through the context's pinned area: asynchronous copies, no stream drain here
-	const size_t need = sizeof(int64_t) * ((size_t)b->nb + 2) + sizeof(int32_t) * ((size_t)b->nb + 2);
+	const size_t need = sizeof(int32_t) * ((size_t)b->nb + 2);
 #ifndef AGPU_EMU
 	// the area may still feed the asynchronous copies of the previous batch of this context (agpu_upload_async, or a group
 	// pass queued behind an upload): wait for those copies -- not for the stream -- before overwriting it
@@ -559,20 +557,10 @@ static int batch_common(agpu_ctx *ctx, agpu_batch *b)
 		ctx->stage_pin = (char*)pinned_alloc(ctx->stage_cap);
 		if(!ctx->stage_pin) { ctx->stage_cap = 0; return AGPU_ERR_OOM; }
 	}
-	int64_t *qreg = (int64_t*)ctx->stage_pin;
-	int32_t *ord_pin = (int32_t*)(ctx->stage_pin + sizeof(int64_t) * ((size_t)b->nb + 2));
+	int32_t *ord_pin = (int32_t*)ctx->stage_pin;
 	memcpy(ord_pin, ord.data(), sizeof(int32_t) * b->nb);
 	TRY(b->order.alloc(ctx, b->nb + 1));
 	TRY(h2d(ctx, b->order.p, ord_pin, sizeof(int32_t) * b->nb));
-	qreg[0] = 0;
-	for(int k = 0; k < b->nb; k++)
-	{
-		int64_t ne = ho[k + 1] - ho[k];
-		qreg[k + 1] = qreg[k] + (int64_t)pow2_ceil((u32)std::max<int64_t>(ne + ne / 2, 2));
-	}
-	b->q_slots = qreg[b->nb];
-	TRY(b->qreg_off.alloc(ctx, b->nb + 2));
-	TRY(h2d(ctx, b->qreg_off.p, qreg, sizeof(int64_t) * (b->nb + 1)));
 #ifndef AGPU_EMU
 	if(ctx->ev_stage && cudaEventRecord((cudaEvent_t)ctx->ev_stage, ctx->stream) == cudaSuccess) ctx->stage_busy = true;
 	else TRY(stream_sync(ctx));
@@ -716,7 +704,7 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 	b->in_hit_off.release(ctx); b->in_pos.release(ctx); b->in_rpos.release(ctx); b->in_mpos.release(ctx); b->in_isize.release(ctx);
 	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_bstrand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
 	b->in_cigar_off.release(ctx); b->in_cigar.release(ctx);
-	b->err.release(ctx); b->order.release(ctx); b->qreg_off.release(ctx); b->tile_owner.release(ctx);
+	b->err.release(ctx); b->order.release(ctx); b->tile_owner.release(ctx);
 	b->cov_skip.release(ctx); b->cov_ex_bundle.release(ctx); b->cov_ex_l.release(ctx); b->cov_ex_r.release(ctx); b->cov_ex_cnt.release(ctx);
 	stream_sync(ctx);
 	if(ctx->arena_owner == b) { ctx->arena.rewind(); ctx->arena_owner = NULL; }

@@ -2,10 +2,27 @@
 //
 // Reference semantics: for i ascending, an unpaired hit i takes the first unpaired u != i (in index
 // order) with hits[u].pos == hits[i].mpos, isize sum 0 and the same qname; frgs is ordered by i.
-// The bucket hash of the reference only accelerates the search, so the result is a function of
-// the groups of equal qname alone: the greedy is run independently inside every qname group.
-// Groups are found with a per-bundle open-addressing table keyed by the 64-bit qname key; members
-// are chained through an atomicExch linked list and sorted by index by the group's first hit.
+// The bucket hash of the reference only accelerates the search, so the result is a function of the
+// candidate relation C(i) = { u != i : pos[u] == mpos[i], isize[u] == -isize[i], qname[u] == qname[i] } alone.
+//
+// The hits of a bundle arrive sorted by pos (packing contract, verified by k_hit_bounds), so C(i) is a
+// run of the bundle's own pos array: a JOIN ON THE SORTED POSITIONS finds it by bisection, and no table of
+// query names is built at all (the batch-wide open-addressing table this replaces was 32 bytes per hit
+// -- 750 MB at configs[1] -- and crossed the DRAM bus three times).
+//   k_pair_probe  : tile of PW_TILE consecutive hits, the pos values of the tile and of PW_HALO neighbours on
+//                   either side staged in shared memory; a hit bisects for mpos inside the staged window (global
+//                   bisection of its bundle when the run may leave the window), walks the run and records
+//                   cand[i] (-1 none, >= 0 the only candidate, -2 several) and want[u]++ for every candidate u
+//   k_pair_decide : the component of the candidate relation a hit lies in is CLOSED and of size two when
+//                   C(i) = {u}, nobody but i wants u, C(u) is empty or {i} and nobody but (possibly) u wants i:
+//                   the reference's greedy pairs such a component whatever else the bundle holds, discovered by i
+//                   (u's candidate list empty) or by the smaller index (mutual).  Every other hit that has or is a
+//                   candidate is marked (bit 31 of want[]) together with all its candidates; the marked hits are
+//                   exactly the members of the components that are not such pairs.
+//   k_pairx_*     : the marked hits (multi-mapped query names inside one bundle; none in most batches) go through
+//                   the exact greedy per (bundle, qname) group: compact list, open-addressing table sized for the
+//                   list, member lists sorted by hit index, pair_group.  Unmarked hits never appear in a marked
+//                   hit's candidate list, so running the greedy on the marked members of a group alone is exact.
 #ifndef ALETSCH_B200_CSRC_K_FRAGMENTS_H
 #define ALETSCH_B200_CSRC_K_FRAGMENTS_H
 
@@ -17,36 +34,96 @@ namespace agpu {
 #define QID_EMPTY 0xffffffffffffffffULL
 #define SCAN_TILE 2048
 
-// qname table slot: two 64-bit words, [0] = qname key (QID_EMPTY when free), [1] low half = head of the member list
-// (bundle-local hit index, -1 when empty).  A memset with 0xff initialises both.
-// Both kernels work on one WAVE of bundles at a time: the hits [hit_lo, hit_hi) of a run of consecutive bundles, whose table
-// regions start at slot_base in the batch's region offsets.  Default: ONE wave, one table for the whole batch.  With
-// AGPU_PAIR_WAVE_SLOTS=<n> (e.g. 4194304 = 64 MB of slots) the same table is cleared, filled and read wave after wave and stays
-// in the 126 MB L2, so the 16-byte slots never travel to DRAM (one table for the whole batch, 750 MB at configs[1], crosses the
-// DRAM bus three times).  Measured on B200 at configs[1]: 13 waves 0.78 + 0.61 ms, one wave 0.62 + 0.43 ms -- the launch tails of
-// 26 short kernels cost more than the DRAM traffic they save, so the waves are off by default (profiles/r02_notes.md).
-KERNEL k_qid_insert(hits_dev h, int64_t hit_lo, int64_t hit_hi, int64_t slot_base, const int32_t *hit_bundle, const int64_t *reg_off, u64 *slots,
-		int64_t *hit_qslot, int32_t *next, int *err)
+#define PW_TILE 1024                       // hits per tile (four per thread)
+#define PW_HALO 3584                       // neighbours staged on either side
+#define PW_WIN (PW_TILE + 2 * PW_HALO)     // 8192 positions = 32 KB of shared memory
+#define PC_NONE (-1)
+#define PC_MULTI (-2)
+#define WANT_MARK 0x80000000u
+
+// pair control words of a batch: [0] hits marked for the exact path, [1] cursor of the compact list, [2] cursor of the member scratch
+enum { PCTL_MARKED = 0, PCTL_LIST, PCTL_MEMBERS, PCTL_WORDS = 4 };
+
+// walks the run of pos == mpos[i] that starts at hit `lo` of i's bundle (which ends at h1) and calls f(u) for every candidate
+template<typename F> DEV void pair_candidates(const hits_dev &h, int64_t i, int64_t lo, int64_t h1, F f)
 {
-	int64_t i = hit_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= hit_hi) return;
-	int b = hit_bundle[i];
-	int64_t r0 = reg_off[b] - slot_base;
-	u32 mask = (u32)(reg_off[b + 1] - reg_off[b]) - 1;
-	u64 key = h.qid[i];
-	if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); hit_qslot[i] = -1; return; }
-	u32 pos = (u32)(mix64(key) >> 11) & mask;
-	int64_t sl = -1;
-	for(u32 probe = 0; probe <= mask; probe++)
+	const int32_t m = h.mpos[i];
+	const u32 is = (u32)h.isize[i];
+	const u64 key = h.qid[i];
+	for(int64_t u = lo; u < h1 && h.pos[u] == m; u++)
 	{
-		u64 cur = atomicCAS(&slots[2 * (r0 + pos)], (u64)QID_EMPTY, key);
-		if(cur == QID_EMPTY || cur == key) { sl = r0 + pos; break; }
-		pos = (pos + 1) & mask;
+		if(u == i) continue;
+		if((u32)h.isize[u] + is != 0u) continue;
+		if(h.qid[u] != key) continue;
+		f(u);
 	}
-	hit_qslot[i] = sl;
-	if(sl < 0) { atomicAdd(&err[ERR_CAP], 1); return; }
-	int32_t li = (int32_t)(i - h.bundle_hit_off[b]);
-	next[i] = atomicExch((int32_t*)&slots[2 * sl + 1], li);
+}
+
+KERNEL k_pair_probe(hits_dev h, int64_t n_tiles, const int32_t *hit_bundle, int32_t *cand, u32 *want, int *err)
+{
+	SHARED int32_t spos[PW_WIN];
+	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	{
+		const int64_t i0 = t * PW_TILE;
+		const int64_t s0 = i0 > PW_HALO ? i0 - PW_HALO : 0;
+		const int64_t s1 = i0 + PW_TILE + PW_HALO < h.n_hits ? i0 + PW_TILE + PW_HALO : h.n_hits;
+		for(int k = threadIdx.x; k < (int)(s1 - s0); k += blockDim.x) spos[k] = h.pos[s0 + k];
+		BLOCK_SYNC();
+		for(int k = threadIdx.x; k < PW_TILE; k += blockDim.x)
+		{
+			const int64_t i = i0 + k;
+			if(i >= h.n_hits) break;
+			const u64 key = h.qid[i];
+			if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); cand[i] = PC_NONE; continue; }
+			const int b = hit_bundle[i];
+			const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
+			const int32_t m = h.mpos[i];
+			// the part of the bundle that is staged; the run of pos == m lies inside it when the bundle does not continue to the
+			// left with a value that could still be m, nor to the right
+			const int64_t w0 = h0 > s0 ? h0 : s0, w1 = h1 < s1 ? h1 : s1;
+			const bool inside = (w0 == h0 || spos[w0 - s0] < m) && (w1 == h1 || spos[w1 - 1 - s0] > m);
+			int64_t lo;
+			if(inside) lo = w0 + lower_bound_idx(spos + (w0 - s0), (int)(w1 - w0), m);
+			else lo = h0 + lower_bound_idx(h.pos + h0, (int)(h1 - h0), m);
+			int n = 0;
+			int64_t first = -1;
+			pair_candidates(h, i, lo, h1, [&](int64_t u) { if(n == 0) first = u; n++; atomicAdd(&want[u], 1u); });
+			cand[i] = n == 0 ? PC_NONE : n == 1 ? (int32_t)(first - h0) : PC_MULTI;
+		}
+		BLOCK_SYNC();
+	}
+}
+
+DEV void pair_mark(u32 *want, int64_t x, int32_t *ctl)
+{
+	const u32 old = atomicOr(&want[x], WANT_MARK);
+	if(!(old & WANT_MARK)) atomicAdd(&ctl[PCTL_MARKED], 1);
+}
+
+// all: every hit that has a candidate goes to the exact path (test hook, AGPU_PAIR_EXACT=1)
+KERNEL k_pair_decide(hits_dev h, const int32_t *hit_bundle, const int32_t *cand, u32 *want, int32_t *mate, int32_t *ctl, int all)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	const int32_t c = cand[i];
+	if(c == PC_NONE) return;
+	const int b = hit_bundle[i];
+	const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
+	const int32_t li = (int32_t)(i - h0);
+	if(c >= 0 && !all)
+	{
+		const int64_t u = h0 + c;
+		const u32 wu = want[u] & ~WANT_MARK, wi = want[i] & ~WANT_MARK;
+		const int32_t cu = cand[u];
+		if(wu == 1 && ((cu == PC_NONE && wi == 0) || (cu == li && wi == 1)))
+		{
+			if(cu == PC_NONE || li < c) { mate[i] = c; mate[u] = -2 - li; }      // i discovered the pair
+			return;
+		}
+	}
+	pair_mark(want, i, ctl);
+	const int64_t lo = h0 + lower_bound_idx(h.pos + h0, (int)(h1 - h0), h.mpos[i]);
+	pair_candidates(h, i, lo, h1, [&](int64_t u) { pair_mark(want, u, ctl); });
 }
 
 // the reference's greedy over one qname group whose members m[0..n) are in ascending hit index
@@ -62,7 +139,7 @@ DEV void pair_group(const hits_dev &h, int64_t h0, const int32_t *m, int n, int3
 			int64_t ic = h0 + m[c];
 			if(mate[ic] != -1) continue;
 			if(h.pos[ic] != h.mpos[ia]) continue;
-			if(h.isize[ic] + h.isize[ia] != 0) continue;
+			if((u32)h.isize[ic] + (u32)h.isize[ia] != 0u) continue;
 			mate[ia] = m[c];                 // i discovered the pair
 			mate[ic] = -2 - m[a];            // partner
 			break;
@@ -70,48 +147,56 @@ DEV void pair_group(const hits_dev &h, int64_t h0, const int32_t *m, int n, int3
 	}
 }
 
-// one thread per qname group (the hit at the head of the group's member list) runs the greedy; frgs order is by
-// discoverer index, so which member runs it does not matter
-#define PAIR_LOCAL 8
-KERNEL k_pair(hits_dev h, int64_t hit_lo, int64_t hit_hi, const int32_t *hit_bundle, const int64_t *hit_qslot, const u64 *slots, const int32_t *next,
-		int32_t *cursor, int32_t *members, int32_t *mate)
+// ---- exact path over the marked hits
+KERNEL k_pairx_list(int64_t n_hits, const u32 *want, int32_t *ctl, int64_t *clist)
 {
-	int64_t i = hit_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= hit_hi) return;
-	int64_t sl = hit_qslot[i];
-	if(sl < 0) return;
-	int b = hit_bundle[i];
-	int64_t h0 = h.bundle_hit_off[b];
-	const int32_t li = (int32_t)(i - h0);
-	if((int32_t)(u32)(slots[2 * sl + 1] & 0xffffffffULL) != li) return;
-	int32_t x1 = next[i];
-	if(x1 < 0) return;                       // group of one
-	int32_t x2 = next[h0 + x1];
-	if(x2 < 0)
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_hits) return;
+	if(want[i] & WANT_MARK) clist[atomicAdd(&ctl[PCTL_LIST], 1)] = i;
+}
+
+// rep[p] = the marked hit that claimed slot p (QID_EMPTY when free); equality is checked on (bundle, key) of the claimant, so
+// hash collisions only cost a probe.  head[p] / nextx[t] chain the list positions t of a group.  The table has at least twice
+// as many slots as there are marked hits.
+KERNEL k_pairx_insert(hits_dev h, int64_t n_c, const int64_t *clist, const int32_t *hit_bundle, u64 mask, u64 *rep, u64 *head, u64 *nextx, u64 *slot_of)
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= n_c) return;
+	const int64_t i = clist[t];
+	const int b = hit_bundle[i];
+	const u64 key = h.qid[i];
+	u64 p = mix64(key ^ mix64((u64)(u32)b)) & mask;
+	for(;;)
 	{
-		// the common case, a group of two: members (lo, hi) in index order
-		int32_t lo = li < x1 ? li : x1, hi = li < x1 ? x1 : li;
-		int64_t ia = h0 + lo, ic = h0 + hi;
-		int32_t sum = h.isize[ia] + h.isize[ic];
-		if(sum != 0) return;
-		if(h.pos[ic] == h.mpos[ia]) { mate[ia] = hi; mate[ic] = -2 - lo; }
-		else if(h.pos[ia] == h.mpos[ic]) { mate[ic] = lo; mate[ia] = -2 - hi; }
-		return;
+		const u64 cur = atomicCAS(&rep[p], (u64)QID_EMPTY, (u64)i);
+		if(cur == QID_EMPTY) break;
+		if(hit_bundle[cur] == b && h.qid[cur] == key) break;
+		p = (p + 1) & mask;
 	}
-	int32_t loc[PAIR_LOCAL];
+	slot_of[t] = p;
+	nextx[t] = atomicExch(&head[p], (u64)t);
+}
+
+// one thread per group (the list position at the head of the group's chain): members in ascending hit index, then the greedy
+#define PAIR_LOCAL 8
+KERNEL k_pairx_resolve(hits_dev h, int64_t n_c, const int64_t *clist, const int32_t *hit_bundle, const u64 *head, const u64 *nextx, const u64 *slot_of,
+		int32_t *ctl, int32_t *members, int32_t *mate)
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(t >= n_c) return;
+	if(head[slot_of[t]] != (u64)t) return;
+	const int64_t h0 = h.bundle_hit_off[hit_bundle[clist[t]]];
 	int n = 0;
-	for(int32_t x = li; x >= 0; x = next[h0 + x]) { if(n < PAIR_LOCAL) loc[n] = x; n++; }
+	for(u64 x = (u64)t; x != QID_EMPTY; x = nextx[x]) n++;
+	if(n < 2) return;
+	int32_t loc[PAIR_LOCAL];
 	int32_t *m = loc;
-	if(n > PAIR_LOCAL)
+	if(n > PAIR_LOCAL) m = members + atomicAdd(&ctl[PCTL_MEMBERS], n);
+	int k = 0;
+	for(u64 x = (u64)t; x != QID_EMPTY; x = nextx[x]) m[k++] = (int32_t)(clist[x] - h0);
+	for(int a = 1; a < n; a++)               // ascending hit index (insertion sort; groups are tiny)
 	{
-		m = members + h0 + atomicAdd(&cursor[b], n);
-		int k = 0;
-		for(int32_t x = li; x >= 0 && k < n; x = next[h0 + x]) m[k++] = x;
-	}
-	// ascending hit index (insertion sort; groups are tiny)
-	for(int a = 1; a < n; a++)
-	{
-		int32_t v = m[a];
+		const int32_t v = m[a];
 		int c = a - 1;
 		while(c >= 0 && m[c] > v) { m[c + 1] = m[c]; c--; }
 		m[c + 1] = v;
@@ -187,18 +272,16 @@ KERNEL k_gather_i64(int64_t n, const int64_t *idx, const int64_t *src, int64_t *
 struct fragments_state
 {
 	bool built = false;
-	agpu::dbuf<agpu::u64> slots;
-	agpu::dbuf<int32_t> next, cursor, members, mate, tile_cnt;
-	agpu::dbuf<int64_t> hit_qslot, tile_off, rank, frg_off;
+	agpu::dbuf<int32_t> mate, tile_cnt;
+	agpu::dbuf<int64_t> tile_off, rank, frg_off;
 	agpu::dbuf<int32_t> f_h1, f_h2, f_type, f_bundle, bridged;
 	int64_t n_frg = 0;
 	std::vector<int64_t> frg_off_host;
 
 	void release(agpu_ctx *ctx)
 	{
-		slots.release(ctx); next.release(ctx);
-		cursor.release(ctx); members.release(ctx); mate.release(ctx); tile_cnt.release(ctx);
-		hit_qslot.release(ctx); tile_off.release(ctx); rank.release(ctx); frg_off.release(ctx);
+		mate.release(ctx); tile_cnt.release(ctx);
+		tile_off.release(ctx); rank.release(ctx); frg_off.release(ctx);
 		f_h1.release(ctx); f_h2.release(ctx); f_type.release(ctx); f_bundle.release(ctx); bridged.release(ctx);
 		built = false; n_frg = 0;
 	}

@@ -206,13 +206,12 @@ def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
         return Hh * 12 + 4 * n_cigar + 2 * n_mblocks * (4 + 4 + 8)
     if kernel == "k_covc_emit":
         return NBD * 8 + 12 * S
-    if kernel == "k_qid_insert":
-        return Hh * (8 + 4 + 8 + 4) + Hh * 16       # qid, bundle id in; slot index, next out; one 16-byte slot touch
-    if kernel == "k_pair":
-        return Hh * (8 + 4 + 16 + 4) + F * (2 * 12 + 8)   # slot index, bundle id, slot, next per hit; pos/mpos/isize of both mates, mate out
-    if kernel == "k_pair_bundle":
-        # per hit: qid (8) + pos, mpos, isize (12) in, mate (4) out
-        return Hh * (8 + 12 + 4)
+    if kernel == "k_pair_probe":
+        # per hit: qid (8) + pos, mpos, isize (12) + bundle id (4) in, candidate word (4) out; one want[] counter RMW (8) per mate found
+        return Hh * (8 + 12 + 4 + 4) + 2 * F * 8
+    if kernel == "k_pair_decide":
+        # per hit the candidate word (4); per paired hit its own and its mate's want / candidate words (16) in, mate (4) out
+        return Hh * 4 + 2 * F * (16 + 4)
     if kernel == "k_hcst_insert":
         return Hh * (4 + 8 + 4 + 1 + 8) + 8 * n_splice_pairs
     if kernel == "k_frag_align":

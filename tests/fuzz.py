@@ -30,10 +30,10 @@ def random_cigar(rng, spliced):
     return ops
 
 
-def random_bundle(rng, n_hits, strand, exon_grid):
+def random_bundle(rng, n_hits, strand, exon_grid, pair_heavy=False):
     """hits sorted by pos with no neighbour equal in (pos, rpos); splice positions are drawn from a small grid so that chains,
     junctions and coverage borders collide a lot"""
-    pos = np.sort(rng.integers(1000, 1000 + 40 * max(n_hits, 1) + 200, n_hits)).astype(np.int32)
+    pos = np.sort(rng.integers(1000, 1000 + (3 if pair_heavy else 40) * max(n_hits, 1) + 200, n_hits)).astype(np.int32)
     cig, cig_off, rpos = [], [0], []
     for i in range(n_hits):
         spliced = rng.random() < 0.45
@@ -100,6 +100,20 @@ def random_bundle(rng, n_hits, strand, exon_grid):
                 isize[int(m)] = sz if rng.random() < 0.5 else int(rng.integers(1, 500))
         q += 1
         k += g
+    if pair_heavy and n:
+        # candidate relations that are anything but isolated pairs: query names shared by up to 8 hits, mpos pointing at the
+        # position of a random member of the same group (possibly the hit's own), isize from a handful of values incl. 0
+        perm = rng.permutation(n)
+        k = 0
+        while k < n:
+            g = int(min(n - k, rng.choice([1, 2, 2, 3, 4, 5, 8])))
+            members = perm[k:k + g]
+            name = np.uint64(int(rng.integers(1, 1 << 50)))
+            for x in members:
+                qid[int(x)] = name
+                mpos[int(x)] = out["pos"][int(rng.choice(members))]
+                isize[int(x)] = int(rng.choice([-60, -50, 0, 50, 60, 50, -50]))
+            k += g
     out["qid"] = qid
     out["mpos"] = mpos
     out["isize"] = isize
@@ -114,7 +128,7 @@ def random_bundle(rng, n_hits, strand, exon_grid):
     return out
 
 
-def random_batch(seed, n_bundles=12, max_hits=60, empty_every=0, exon_grid=True):
+def random_batch(seed, n_bundles=12, max_hits=60, empty_every=0, exon_grid=True, pair_heavy=False):
     rng = np.random.default_rng(seed)
     parts = []
     for k in range(n_bundles):
@@ -122,7 +136,7 @@ def random_batch(seed, n_bundles=12, max_hits=60, empty_every=0, exon_grid=True)
             n = 0
         else:
             n = int(rng.integers(1, max_hits + 1))
-        parts.append(random_bundle(rng, n, str(rng.choice(["+", "-"])), exon_grid))
+        parts.append(random_bundle(rng, n, str(rng.choice(["+", "-"])), exon_grid, pair_heavy))
     arr = {f: (np.concatenate([p[f] for p in parts]).astype(dt) if parts else np.zeros(0, dt)) for f, dt in H.HIT_FIELDS}
     hit_off = np.zeros(len(parts) + 1, np.int64)
     cig_off = [np.zeros(1, np.uint32)]

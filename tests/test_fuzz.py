@@ -29,6 +29,18 @@ def run_seeds(ctx, checkers, seeds, big=False):
                 assert not bad, "seed %d vs %s (revision): %d mismatches, first: %s" % (seed, name, len(bad), bad[:3])
 
 
+def run_pair_seeds(ctx, checkers, seeds):
+    """mate pairing under candidate relations that are not isolated pairs (bundle_base::build_fragments, rnacore/bundle_base.cc:
+    267-323): shared query names, several hits per position, self-pointing and one-sided mates -- the join on the sorted
+    positions must hand exactly these to the greedy of the reference and pair the rest as it would"""
+    for seed in seeds:
+        batch = fuzz.random_batch(500 + seed, n_bundles=6, max_hits=(3000 if seed % 4 == 0 else 300), exon_grid=False, pair_heavy=True)
+        gp, op = parity.params_pair(H.FR_FIRST)
+        for name, chk in checkers.items():
+            bad = parity.compare_full(ctx, batch, chk, gp, op, {})
+            assert not bad, "seed %d vs %s: %d mismatches, first: %s" % (seed, name, len(bad), bad[:3])
+
+
 def run_group_seeds(ctx, checkers, seeds):
     """assembler::bridge on random clusters of random bundles, with and without a per-bundle bridging round before"""
     for seed in seeds:
@@ -67,6 +79,10 @@ def ctx(emu_lib):
 
 def test_fuzz_bundles(ctx, checkers):
     run_seeds(ctx, checkers, range(14))
+
+
+def test_fuzz_pairing(ctx, checkers):
+    run_pair_seeds(ctx, checkers, range(8))
 
 
 def test_fuzz_group_bridge(ctx, checkers):

@@ -225,6 +225,35 @@ def test_fuzz_bundles(ctx, checkers):
     test_fuzz.run_seeds(ctx, checkers, range(100, 104), big=True)
     test_fuzz.run_degenerate(ctx, checkers)
     test_fuzz.run_group_seeds(ctx, checkers, range(16))
+    test_fuzz.run_pair_seeds(ctx, checkers, range(12))
+
+
+def test_pairing_exact_path_at_scale():
+    """AGPU_PAIR_EXACT=1 sends EVERY hit that has a mate candidate through the exact per-(bundle, qname) greedy (the path only
+    multi-mapped query names take otherwise): same fragments as the reference on a batch of 60,000 templates.  The switch is
+    read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, 'tests'); import parity, orclib\n"
+            "from aletsch_b200 import gpu as G, hostlib as H\n"
+            "ctx = G.Context(0); batch, lt = parity.make_batch(H.SYNTH_PAIRED, 60000, seed=20260111)\n"
+            "gp, op = parity.params_pair(lt)\n"
+            "chk = None\n"
+            "for p in ('ref', 'orc'):\n"
+            "    try:\n"
+            "        chk = orclib.Checker(p); break\n"
+            "    except (OSError, FileNotFoundError):\n"
+            "        pass\n"
+            "stats = {}; bad = parity.compare_full(ctx, batch, chk, gp, op, stats)\n"
+            "assert not bad, bad[:3]\n"
+            "assert stats['fragments'] > 10000\n"
+            "print('exact path ok', stats['fragments'])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AGPU_PAIR_EXACT="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "exact path ok" in r.stdout
 
 
 def test_long_read_scale_parity(ctx, checkers):

@@ -11,7 +11,7 @@ timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/$
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${tag}_launches.csv \
 	python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-stage5 > gpurun_out/${tag}_ncu1.log 2>&1; echo "ncu launch list rc $?"
 ncu --set full --import-source on --clock-control none \
-	-k regex:"^(k_graph_build|k_group_partition|k_group_partition_warp|k_hit_cigar|k_qid_insert|k_bridge_dp_warp|k_lb_cov_segments|k_cov_add|k_vote_type2|k_pair|k_update|k_hit_bounds|k_hcst_insert|k_frag_group|k_frag_align|k_cluster_emit)$" \
+	-k regex:"^(k_graph_build|k_group_partition|k_group_partition_warp|k_hit_cigar|k_pair_probe|k_bridge_dp_warp|k_lb_cov_segments|k_cov_add|k_vote_type2|k_pair_decide|k_update|k_hit_bounds|k_hcst_insert|k_frag_group|k_frag_align|k_cluster_emit)$" \
 	--launch-skip 19 --launch-count 19 -o gpurun_out/${tag}_prof python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-stage5 > gpurun_out/${tag}_ncu2.log 2>&1; echo "ncu full rc $?"
 ncu -i gpurun_out/${tag}_prof.ncu-rep --page raw --csv > gpurun_out/${tag}_prof_raw.csv 2>/dev/null; echo "raw csv rc $?"
 # gpurun_out/ comes back only if it stays under 64 MiB: the report itself stays on the box when it is large (the raw page has every counter)
