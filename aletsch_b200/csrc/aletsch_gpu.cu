@@ -816,7 +816,7 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		LAUNCH_T(ctx, k_bord_off, nb + 1, nb, b->cov_base.p, b->wrank.p, b->bord_off.p);
 		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
 		if(b->op_tiles) LAUNCH_B(ctx, k_cov_add_tile, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->nc, b->h.cigar, b->ev_s.p, b->border.p, b->wrank.p, b->diffc.p);
-		else LAUNCH_T(ctx, k_cov_add, b->nh, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p, b->cov_skip.p);
+		else LAUNCH_T(ctx, k_cov_add, HQ_THREADS(b->nh), b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p, b->cov_skip.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);
 		// coverage = prefix sum of the differences; segments = borders with positive coverage; prefix sums of len * cov:
@@ -885,7 +885,7 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 		LAUNCH_B(ctx, k_cigar_tile, std::min<int64_t>((nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 6), 256, b->h, nc, b->tile_owner.p, b->hit_bundle.p, b->b_lpos.p,
 				b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, n_spliced.p, b->ev_s.p, b->err.p);
 	}
-	else LAUNCH_T(ctx, k_hit_cigar, nh, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_bundle.p, n_spliced.p, b->err.p, b->cov_skip.p);
+	else LAUNCH_T(ctx, k_hit_cigar, HQ_THREADS(nh), b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_bundle.p, n_spliced.p, b->err.p, b->cov_skip.p);
 	if(b->n_cov_extra > 0)
 	{
 		// foreign intervals of the insert-size preview (agpu_batch_coverage_edit): border bits now, weights with the ranked borders

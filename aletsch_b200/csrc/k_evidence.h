@@ -235,50 +235,83 @@ HD u64 chain_hash(const int32_t *v, int n)
 //   splices : (p - len, p) for every inner BAM_CREF_SKIP, written at spl[cigar_off[i] ...]
 //   skip    : optional per-hit mask (insert-size preview, agpu_batch_coverage_edit): bit z set = the hit's z-th BAM_CMATCH
 //             operation adds no coverage
+// Every per-hit walk below is a chain of dependent loads (hit -> bundle -> window base, hit -> CIGAR offset -> operation ->
+// bitmap word): one hit per thread leaves a thread with one 4-byte load in flight (ncu: 71-77 % of the stall samples on the long
+// scoreboard at full occupancy).  A thread therefore takes HQ hits, blockDim.x apart, and issues the loads of each level for all
+// of them before it uses any; the first CIGAR operation of a hit (the only one of an unspliced read) is fetched with that level.
+// Launch with HQ_THREADS(n_hits) threads.
+#define HQ 4
+#define HQ_THREADS(n) ((((int64_t)(n) + 256 * HQ - 1) / (256 * HQ)) * 256)
 KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
 		int32_t *spl, int32_t *hit_nspl, const int32_t *hit_bundle, int32_t *n_spliced, int *err, const uint16_t *skip)
 {
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= h.n_hits) return;
-	int b = hit_bundle[i];
-	int64_t base = cov_base[b] - (int64_t)b_lpos[b];
-	u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
-	int32_t p = h.pos[i];
-	int ns = 0, z = 0;
-	const u32 sk = skip ? skip[i] : 0u;
-	int32_t *out = spl + c0;
-	for(u32 k = c0; k < c1; k++)
+	const int64_t i0 = (int64_t)blockIdx.x * blockDim.x * HQ + threadIdx.x;
+	int bq[HQ];
+	u32 c0q[HQ], c1q[HQ], skq[HQ], firstq[HQ];
+	int32_t pq[HQ], rq[HQ];
+	int64_t baseq[HQ];
+#pragma unroll
+	for(int q = 0; q < HQ; q++)
 	{
-		u32 c = h.cigar[k];
-		u32 op = c & 0xf, len = c >> 4;
-		if((0x3C1A7 >> (op << 1)) & 2) p += (int32_t)len;      // bam_cigar_type: consumes reference
-		if(op == 0)                                            // BAM_CMATCH
+		const int64_t i = i0 + (int64_t)q * blockDim.x;
+		const bool in = i < h.n_hits;
+		bq[q] = in ? hit_bundle[i] : -1;
+		c0q[q] = in ? h.cigar_off[i] : 0u;
+		c1q[q] = in ? h.cigar_off[i + 1] : 0u;
+		pq[q] = in ? h.pos[i] : 0;
+		rq[q] = in ? h.rpos[i] : 0;
+		skq[q] = (in && skip) ? skip[i] : 0u;
+	}
+#pragma unroll
+	for(int q = 0; q < HQ; q++)
+	{
+		baseq[q] = bq[q] >= 0 ? cov_base[bq[q]] - (int64_t)b_lpos[bq[q]] : 0;
+		firstq[q] = c1q[q] > c0q[q] ? h.cigar[c0q[q]] : 0u;
+	}
+#pragma unroll
+	for(int q = 0; q < HQ; q++)
+	{
+		const int b = bq[q];
+		if(b < 0) continue;
+		const int64_t i = i0 + (int64_t)q * blockDim.x;
+		const int64_t base = baseq[q];
+		const u32 c0 = c0q[q], c1 = c1q[q], sk = skq[q];
+		int32_t p = pq[q];
+		int ns = 0, z = 0;
+		int32_t *out = spl + c0;
+		for(u32 k = c0; k < c1; k++)
 		{
-			int64_t s = base + p - (int32_t)len, e = base + p;
-			const bool skipped = z < 16 && ((sk >> z) & 1u);
-			z++;
-			if(len > 0 && !skipped)
+			const u32 c = k == c0 ? firstq[q] : h.cigar[k];
+			const u32 op = c & 0xf, len = c >> 4;
+			if((0x3C1A7 >> (op << 1)) & 2) p += (int32_t)len;      // bam_cigar_type: consumes reference
+			if(op == 0)                                            // BAM_CMATCH
 			{
-				atomicOr(&border[s >> 5], 1u << (s & 31));
-				atomicOr(&border[e >> 5], 1u << (e & 31));
+				const int64_t s = base + p - (int32_t)len, e = base + p;
+				const bool skipped = z < 16 && ((sk >> z) & 1u);
+				z++;
+				if(len > 0 && !skipped)
+				{
+					atomicOr(&border[s >> 5], 1u << (s & 31));
+					atomicOr(&border[e >> 5], 1u << (e & 31));
+				}
+			}
+			if(op == 3 && k != c0 && k != c1 - 1)                  // BAM_CREF_SKIP, not first / last op
+			{
+				out[ns++] = p - (int32_t)len;
+				out[ns++] = p;
 			}
 		}
-		if(op == 3 && k != c0 && k != c1 - 1)                  // BAM_CREF_SKIP, not first / last op
-		{
-			out[ns++] = p - (int32_t)len;
-			out[ns++] = p;
-		}
-	}
-	if(p != h.rpos[i]) atomicAdd(&err[ERR_RPOS], 1);
-	hit_nspl[i] = ns;
+		if(p != rq[q]) atomicAdd(&err[ERR_RPOS], 1);
+		hit_nspl[i] = ns;
 #ifndef AGPU_EMU
-	// hits of a bundle are neighbours: one atomic per (warp, bundle) instead of one per spliced hit
-	const unsigned act = __activemask();
-	const unsigned peers = __match_any_sync(act, ns > 0 ? b : -1);
-	if(ns > 0 && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&n_spliced[b], __popc(peers));
+		// hits of a bundle are neighbours: one atomic per (warp, bundle) instead of one per spliced hit
+		const unsigned act = __activemask();
+		const unsigned peers = __match_any_sync(act, ns > 0 ? b : -1);
+		if(ns > 0 && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&n_spliced[b], __popc(peers));
 #else
-	if(ns > 0) atomicAdd(&n_spliced[b], 1);
+		if(ns > 0) atomicAdd(&n_spliced[b], 1);
 #endif
+	}
 }
 
 // hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64) when the host did not send it
@@ -634,25 +667,51 @@ KERNEL k_bord_off(int32_t nb, const int64_t *cov_base, const u32 *wrank, int64_t
 KERNEL k_cov_add(hits_dev h, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, const u32 *border,
 		const u32 *wrank, int32_t *diffc, const uint16_t *skip)
 {
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= h.n_hits) return;
-	int b = hit_bundle[i];
-	int64_t base = cov_base[b] - (int64_t)b_lpos[b];
-	u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
-	int32_t p = h.pos[i];
-	int z = 0;
-	const u32 sk = skip ? skip[i] : 0u;
-	for(u32 k = c0; k < c1; k++)
+	const int64_t i0 = (int64_t)blockIdx.x * blockDim.x * HQ + threadIdx.x;       // HQ hits per thread, see k_hit_cigar
+	int bq[HQ];
+	u32 c0q[HQ], c1q[HQ], skq[HQ], firstq[HQ];
+	int32_t pq[HQ];
+	int64_t baseq[HQ];
+#pragma unroll
+	for(int q = 0; q < HQ; q++)
 	{
-		u32 c = h.cigar[k];
-		u32 op = c & 0xf, len = c >> 4;
-		if((0x3C1A7 >> (op << 1)) & 2) p += (int32_t)len;
-		const bool skipped = op == 0 && z < 16 && ((sk >> z) & 1u);
-		if(op == 0) z++;
-		if(op == 0 && len > 0 && !skipped)
+		const int64_t i = i0 + (int64_t)q * blockDim.x;
+		const bool in = i < h.n_hits;
+		bq[q] = in ? hit_bundle[i] : -1;
+		c0q[q] = in ? h.cigar_off[i] : 0u;
+		c1q[q] = in ? h.cigar_off[i + 1] : 0u;
+		pq[q] = in ? h.pos[i] : 0;
+		skq[q] = (in && skip) ? skip[i] : 0u;
+	}
+#pragma unroll
+	for(int q = 0; q < HQ; q++)
+	{
+		baseq[q] = bq[q] >= 0 ? cov_base[bq[q]] - (int64_t)b_lpos[bq[q]] : 0;
+		firstq[q] = c1q[q] > c0q[q] ? h.cigar[c0q[q]] : 0u;
+	}
+#pragma unroll
+	for(int q = 0; q < HQ; q++)
+	{
+		if(bq[q] < 0) continue;
+		const int64_t base = baseq[q];
+		const u32 c0 = c0q[q], c1 = c1q[q], sk = skq[q];
+		int32_t p = pq[q];
+		int z = 0;
+		for(u32 k = c0; k < c1; k++)
 		{
-			atomicAdd(&diffc[border_rank(border, wrank, base + p - (int32_t)len)], 1);
-			atomicAdd(&diffc[border_rank(border, wrank, base + p)], -1);
+			const u32 c = k == c0 ? firstq[q] : h.cigar[k];
+			const u32 op = c & 0xf, len = c >> 4;
+			if((0x3C1A7 >> (op << 1)) & 2) p += (int32_t)len;
+			const bool skipped = op == 0 && z < 16 && ((sk >> z) & 1u);
+			if(op == 0) z++;
+			if(op == 0 && len > 0 && !skipped)
+			{
+				const int64_t gs = base + p - (int32_t)len, ge = base + p;
+				const u32 ws = border[gs >> 5], we = border[ge >> 5];
+				const u32 rs = wrank[gs >> 5], re = wrank[ge >> 5];
+				atomicAdd(&diffc[(int64_t)rs + __popc(ws & ((1u << (gs & 31)) - 1u))], 1);
+				atomicAdd(&diffc[(int64_t)re + __popc(we & ((1u << (ge & 31)) - 1u))], -1);
+			}
 		}
 	}
 }

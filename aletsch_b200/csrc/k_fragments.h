@@ -59,7 +59,13 @@ template<typename F> DEV void pair_candidates(const hits_dev &h, int64_t i, int6
 	}
 }
 
-KERNEL k_pair_probe(hits_dev h, int64_t n_tiles, const int32_t *hit_bundle, int32_t *cand, u32 *want, int *err)
+#ifndef AGPU_EMU
+#define PAIR_PROBE_KERNEL __global__ void __launch_bounds__(PW_TILE, 2)
+#else
+#define PAIR_PROBE_KERNEL KERNEL
+#endif
+// PW_TILE threads, one hit each: two CTAs (2 x 32 KB of staged positions) fill an SM's 2048 thread slots
+PAIR_PROBE_KERNEL k_pair_probe(hits_dev h, int64_t n_tiles, const int32_t *hit_bundle, int32_t *cand, u32 *want, int *err)
 {
 	SHARED int32_t spos[PW_WIN];
 	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
@@ -74,24 +80,86 @@ KERNEL k_pair_probe(hits_dev h, int64_t n_tiles, const int32_t *hit_bundle, int3
 			const int64_t i = i0 + k;
 			if(i >= h.n_hits) break;
 			const u64 key = h.qid[i];
-			if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); cand[i] = PC_NONE; continue; }
-			const int b = hit_bundle[i];
-			const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
 			const int32_t m = h.mpos[i];
+			const u32 is = (u32)h.isize[i];
+			const int b = hit_bundle[i];
+			if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); cand[i] = PC_NONE; continue; }
+			const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
 			// the part of the bundle that is staged; the run of pos == m lies inside it when the bundle does not continue to the
 			// left with a value that could still be m, nor to the right
 			const int64_t w0 = h0 > s0 ? h0 : s0, w1 = h1 < s1 ? h1 : s1;
 			const bool inside = (w0 == h0 || spos[w0 - s0] < m) && (w1 == h1 || spos[w1 - 1 - s0] > m);
-			int64_t lo;
-			if(inside) lo = w0 + lower_bound_idx(spos + (w0 - s0), (int)(w1 - w0), m);
-			else lo = h0 + lower_bound_idx(h.pos + h0, (int)(h1 - h0), m);
 			int n = 0;
 			int64_t first = -1;
-			pair_candidates(h, i, lo, h1, [&](int64_t u) { if(n == 0) first = u; n++; atomicAdd(&want[u], 1u); });
+			if(inside)
+			{
+				const int e = (int)(w1 - s0);
+				for(int x = (int)(w0 - s0) + lower_bound_idx(spos + (w0 - s0), (int)(w1 - w0), m); x < e && spos[x] == m; x++)
+				{
+					const int64_t u = s0 + x;
+					if(u == i || (u32)h.isize[u] + is != 0u || h.qid[u] != key) continue;
+					if(n == 0) first = u;
+					n++;
+					atomicAdd(&want[u], 1u);
+				}
+			}
+			else
+			{
+				const int64_t lo = h0 + lower_bound_idx(h.pos + h0, (int)(h1 - h0), m);
+				pair_candidates(h, i, lo, h1, [&](int64_t u) { if(n == 0) first = u; n++; atomicAdd(&want[u], 1u); });
+			}
 			cand[i] = n == 0 ? PC_NONE : n == 1 ? (int32_t)(first - h0) : PC_MULTI;
 		}
 		BLOCK_SYNC();
 	}
+}
+
+// ---- the same probe without staging: pos64[j] = pos[64 j] over the whole batch (1/64 of the positions: the slice of a deep
+// bundle stays in L1), a hit bisects the samples that lie inside its bundle, then the 64 positions between two samples
+#define PS_STEP 64
+KERNEL k_pos_sample(hits_dev h, int64_t n_samples, int32_t *pos64)
+{
+	const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(j >= n_samples) return;
+	pos64[j] = h.pos[j * PS_STEP];
+}
+
+// first hit of the bundle [h0, h1) whose pos is >= m
+DEV int64_t sampled_lower_bound(const int32_t *pos, const int32_t *pos64, int64_t h0, int64_t h1, int32_t m)
+{
+	int64_t lo = h0, hi = h1;                                  // the answer lies in [lo, hi]
+	const int64_t j0 = (h0 + PS_STEP - 1) / PS_STEP, j1 = (h1 - 1) / PS_STEP;      // samples inside the bundle: j0 .. j1
+	if(h1 > h0 && j0 <= j1)
+	{
+		const int64_t js = j0 + lower_bound_idx(pos64 + j0, (int)(j1 - j0 + 1), m);   // first sample >= m (j1 + 1: none)
+		if(js > j0) lo = (js - 1) * PS_STEP + 1;
+		if(js <= j1) hi = js * PS_STEP;
+	}
+	return lo + lower_bound_idx(pos + lo, (int)(hi - lo), m);
+}
+
+KERNEL k_pair_probe_sampled(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle, int32_t *cand, u32 *want, int *err)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= h.n_hits) return;
+	const u64 key = h.qid[i];
+	const int32_t m = h.mpos[i];
+	const u32 is = (u32)h.isize[i];
+	const int b = hit_bundle[i];
+	if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); cand[i] = PC_NONE; return; }
+	const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
+	int n = 0;
+	int64_t first = -1;
+	for(int64_t u = sampled_lower_bound(h.pos, pos64, h0, h1, m); u < h1 && h.pos[u] == m; u++)
+	{
+		const u32 iu = (u32)h.isize[u];
+		const u64 ku = h.qid[u];                               // loaded next to isize, not after it
+		if(u == i || iu + is != 0u || ku != key) continue;
+		if(n == 0) first = u;
+		n++;
+		atomicAdd(&want[u], 1u);
+	}
+	cand[i] = n == 0 ? PC_NONE : n == 1 ? (int32_t)(first - h0) : PC_MULTI;
 }
 
 DEV void pair_mark(u32 *want, int64_t x, int32_t *ctl)
