@@ -9,10 +9,12 @@
 // run of the bundle's own pos array: a JOIN ON THE SORTED POSITIONS finds it by bisection, and no table of
 // query names is built at all (the batch-wide open-addressing table this replaces was 32 bytes per hit
 // -- 750 MB at configs[1] -- and crossed the DRAM bus three times).
-//   k_pair_probe  : tile of PW_TILE consecutive hits, the pos values of the tile and of PW_HALO neighbours on
-//                   either side staged in shared memory; a hit bisects for mpos inside the staged window (global
-//                   bisection of its bundle when the run may leave the window), walks the run and records
-//                   cand[i] (-1 none, >= 0 the only candidate, -2 several) and want[u]++ for every candidate u
+//   k_pair_probe  : one thread per hit: bisection of the bundle's pos array for mpos -- first over every 64th position
+//                   (k_pos_sample: 1/64 of the array, L1-resident for a bundle's slice), then inside the 64 positions
+//                   between two samples -- then the walk of the run, recording cand[i] (-1 none, >= 0 the only candidate,
+//                   -2 several) and want[u]++ for every candidate u.  (A variant that staged the positions of a tile of
+//                   1024 hits and 3584 neighbours on either side in shared memory measured 0.53 ms against 0.46 ms at
+//                   configs[1]: the deep bundles, whose mates lie thousands of hits away, fell back to global bisection.)
 //   k_pair_decide : the component of the candidate relation a hit lies in is CLOSED and of size two when
 //                   C(i) = {u}, nobody but i wants u, C(u) is empty or {i} and nobody but (possibly) u wants i:
 //                   the reference's greedy pairs such a component whatever else the bundle holds, discovered by i
@@ -34,9 +36,6 @@ namespace agpu {
 #define QID_EMPTY 0xffffffffffffffffULL
 #define SCAN_TILE 2048
 
-#define PW_TILE 1024                       // hits per tile (four per thread)
-#define PW_HALO 3584                       // neighbours staged on either side
-#define PW_WIN (PW_TILE + 2 * PW_HALO)     // 8192 positions = 32 KB of shared memory
 #define PC_NONE (-1)
 #define PC_MULTI (-2)
 #define WANT_MARK 0x80000000u
@@ -59,63 +58,8 @@ template<typename F> DEV void pair_candidates(const hits_dev &h, int64_t i, int6
 	}
 }
 
-#ifndef AGPU_EMU
-#define PAIR_PROBE_KERNEL __global__ void __launch_bounds__(PW_TILE, 2)
-#else
-#define PAIR_PROBE_KERNEL KERNEL
-#endif
-// PW_TILE threads, one hit each: two CTAs (2 x 32 KB of staged positions) fill an SM's 2048 thread slots
-PAIR_PROBE_KERNEL k_pair_probe(hits_dev h, int64_t n_tiles, const int32_t *hit_bundle, int32_t *cand, u32 *want, int *err)
-{
-	SHARED int32_t spos[PW_WIN];
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		const int64_t i0 = t * PW_TILE;
-		const int64_t s0 = i0 > PW_HALO ? i0 - PW_HALO : 0;
-		const int64_t s1 = i0 + PW_TILE + PW_HALO < h.n_hits ? i0 + PW_TILE + PW_HALO : h.n_hits;
-		for(int k = threadIdx.x; k < (int)(s1 - s0); k += blockDim.x) spos[k] = h.pos[s0 + k];
-		BLOCK_SYNC();
-		for(int k = threadIdx.x; k < PW_TILE; k += blockDim.x)
-		{
-			const int64_t i = i0 + k;
-			if(i >= h.n_hits) break;
-			const u64 key = h.qid[i];
-			const int32_t m = h.mpos[i];
-			const u32 is = (u32)h.isize[i];
-			const int b = hit_bundle[i];
-			if(key == QID_EMPTY) { atomicAdd(&err[ERR_QID], 1); cand[i] = PC_NONE; continue; }
-			const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
-			// the part of the bundle that is staged; the run of pos == m lies inside it when the bundle does not continue to the
-			// left with a value that could still be m, nor to the right
-			const int64_t w0 = h0 > s0 ? h0 : s0, w1 = h1 < s1 ? h1 : s1;
-			const bool inside = (w0 == h0 || spos[w0 - s0] < m) && (w1 == h1 || spos[w1 - 1 - s0] > m);
-			int n = 0;
-			int64_t first = -1;
-			if(inside)
-			{
-				const int e = (int)(w1 - s0);
-				for(int x = (int)(w0 - s0) + lower_bound_idx(spos + (w0 - s0), (int)(w1 - w0), m); x < e && spos[x] == m; x++)
-				{
-					const int64_t u = s0 + x;
-					if(u == i || (u32)h.isize[u] + is != 0u || h.qid[u] != key) continue;
-					if(n == 0) first = u;
-					n++;
-					atomicAdd(&want[u], 1u);
-				}
-			}
-			else
-			{
-				const int64_t lo = h0 + lower_bound_idx(h.pos + h0, (int)(h1 - h0), m);
-				pair_candidates(h, i, lo, h1, [&](int64_t u) { if(n == 0) first = u; n++; atomicAdd(&want[u], 1u); });
-			}
-			cand[i] = n == 0 ? PC_NONE : n == 1 ? (int32_t)(first - h0) : PC_MULTI;
-		}
-		BLOCK_SYNC();
-	}
-}
-
-// ---- the same probe without staging: pos64[j] = pos[64 j] over the whole batch (1/64 of the positions: the slice of a deep
-// bundle stays in L1), a hit bisects the samples that lie inside its bundle, then the 64 positions between two samples
+// pos64[j] = pos[64 j] over the whole batch (1/64 of the positions: the slice of a deep bundle stays in L1); a hit bisects the
+// samples that lie inside its bundle, then the 64 positions between two samples
 #define PS_STEP 64
 KERNEL k_pos_sample(hits_dev h, int64_t n_samples, int32_t *pos64)
 {
@@ -138,7 +82,7 @@ DEV int64_t sampled_lower_bound(const int32_t *pos, const int32_t *pos64, int64_
 	return lo + lower_bound_idx(pos + lo, (int)(hi - lo), m);
 }
 
-KERNEL k_pair_probe_sampled(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle, int32_t *cand, u32 *want, int *err)
+KERNEL k_pair_probe(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle, int32_t *cand, u32 *want, int *err)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
@@ -169,7 +113,7 @@ DEV void pair_mark(u32 *want, int64_t x, int32_t *ctl)
 }
 
 // all: every hit that has a candidate goes to the exact path (test hook, AGPU_PAIR_EXACT=1)
-KERNEL k_pair_decide(hits_dev h, const int32_t *hit_bundle, const int32_t *cand, u32 *want, int32_t *mate, int32_t *ctl, int all)
+KERNEL k_pair_decide(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle, const int32_t *cand, u32 *want, int32_t *mate, int32_t *ctl, int all)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
@@ -190,7 +134,7 @@ KERNEL k_pair_decide(hits_dev h, const int32_t *hit_bundle, const int32_t *cand,
 		}
 	}
 	pair_mark(want, i, ctl);
-	const int64_t lo = h0 + lower_bound_idx(h.pos + h0, (int)(h1 - h0), h.mpos[i]);
+	const int64_t lo = sampled_lower_bound(h.pos, pos64, h0, h1, h.mpos[i]);
 	pair_candidates(h, i, lo, h1, [&](int64_t u) { pair_mark(want, u, ctl); });
 }
 

@@ -27,7 +27,10 @@ class Pipeline:
             # spinning waits are the fastest as long as every waiting thread has a core of its own; with one stream pool per
             # rank and several ranks per box they do not
             ranks = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
-            blocking_sync = ranks * (self.n_threads + 1) > (os.cpu_count() or 1) // 2
+            cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            # (a rank bound to its GPU's NUMA node -- affinity.bind_to_device -- sees only that node's CPUs, shared with the
+            # other ranks of the node; os.cpu_count() would still report the whole box)
+            blocking_sync = ranks * (self.n_threads + 1) > (os.cpu_count() or 1) // 2 or (self.n_threads + 1) > cpus // 2
         for c in self.ctxs:
             c.blocking_sync(blocking_sync)
 

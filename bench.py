@@ -269,9 +269,16 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    # several ranks on one box: keep this rank's threads and pinned buffers on the NUMA node its GPU hangs off (before anything
+    # is pinned); a single rank keeps every core, its cpu_baseline leg uses them
+    numa_bind = {"bound": False, "why": "single rank"}
+    if world > 1:
+        from aletsch_b200 import affinity
+        numa_bind = affinity.bind_to_device(local)
+        print("[bench] rank %d: NUMA binding %s" % (rank, numa_bind), file=sys.stderr)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ncpu = os.cpu_count() or 8
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
     cfg = config_of(args)
     batch, n_records = build_workload(cfg, rank, max(2, ncpu // max(1, world)))
     parts = device_batches(batch)
@@ -583,7 +590,7 @@ def run_ours(args):
                                         "counts": "counters only"}[args.results],
                        "prefetch": not args.no_prefetch, "stream_drains_per_step": syncs_e2e / steps, "sub_batches": len(views), "streams": args.streams,
                        "gpu_launches_per_step": int(launches_e2e // steps)},
-               "roofline": roof, "clocks": clk}
+               "roofline": roof, "clocks": clk, "numa_bind": numa_bind}
         if collective is not None:
             out["collective"] = collective
         if stage5 is not None:
