@@ -25,6 +25,10 @@
 #define HD __host__ __device__ __forceinline__
 #define DEV __device__ __forceinline__
 #define KERNEL __global__ void
+// thread-per-item kernel of 256 threads whose register count is capped so that n CTAs fit an SM: these kernels wait on chains of
+// dependent loads, the resident warps are their memory-level parallelism
+#define KERNEL_OCC(n) __global__ void __launch_bounds__(256, n)
+#define KERNEL_OCC128(n) __global__ void __launch_bounds__(128, n)      // the same for the warp-per-item kernels of 4 warps
 #define SHARED __shared__
 #define SHARED16 __shared__ __align__(16)        // tiles block_excl_scan reads with 128-bit accesses
 #define BLOCK_SYNC() __syncthreads()
@@ -33,6 +37,8 @@
 #define HD inline
 #define DEV inline
 #define KERNEL static void
+#define KERNEL_OCC(n) static void
+#define KERNEL_OCC128(n) static void
 #define SHARED static thread_local
 #define SHARED16 static thread_local
 #define BLOCK_SYNC() do {} while(0)

@@ -566,7 +566,7 @@ DEV int dpw_cmp(const int32_t *a, const int32_t *b, int D)
 	return 0;
 }
 
-KERNEL k_bridge_dp_warp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bundle, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand,
+KERNEL_OCC128(8) k_bridge_dp_warp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bundle, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand,
 		bridge_dev br)
 {
 	SHARED int32_t s_cand[DPW_WARPS][DPW_CMAX * DPW_W];
@@ -938,7 +938,7 @@ struct vote_out
 	int32_t *chain, *whole;
 };
 
-KERNEL k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
+KERNEL_OCC(6) k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
 		const int32_t *c_chain2, chains_view cv, graph_dev g, const uint8_t *b_strand, bridge_dev br, vote_out o, vote_lists vl)
 {
 	int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1025,7 +1025,7 @@ KERNEL k_vote_type1(int64_t n_clu, const int32_t *c_bundle, const int64_t *clu_o
 	o.type[c] = 1; o.strand[c] = s; o.choices[c] = 1; o.score[c] = 10; o.clen[c] = 0; o.wlen[c] = wn; o.pick[c] = 0;
 }
 
-KERNEL k_vote_type2(int64_t n_clu, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
+KERNEL_OCC(6) k_vote_type2(int64_t n_clu, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
 		const int32_t *c_chain2, chains_view cv, graph_dev g, const uint8_t *b_strand, bridge_dev br, vote_out o, vote_lists vl)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1066,7 +1066,7 @@ struct update_dev
 	int64_t ex_base;
 };
 
-KERNEL k_update(int64_t n_mem, int apply, const int32_t *c_bundle, const int64_t *frg_off, const int32_t *members,
+KERNEL_OCC(8) k_update(int64_t n_mem, int apply, const int32_t *c_bundle, const int64_t *frg_off, const int32_t *members,
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, int32_t *f_type, const int32_t *o_type, const int32_t *o_strand,
 		const int64_t *o_coff, const int32_t *o_chain, const int32_t *b_lpos, const int32_t *b_covhi, const int64_t *cov_base,
 		u32 *border, update_dev u, int *err)

@@ -184,7 +184,7 @@ DEV u64 path_hash(const mate_path &x, u64 h)
 }
 
 // ---- C1: align both mates of every to-be-bridged fragment; frgs[i][2] := -1, then 0 if both align
-KERNEL k_frag_align(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+KERNEL_OCC(8) k_frag_align(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
 		int32_t *f_type, chains_view cv, chain_paths cp, const int32_t *handle_chain, graph_dev g, cluster_dev c)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -235,7 +235,7 @@ KERNEL k_frag_align(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_o
 }
 
 // ---- C2: group by (path1, path2): per-bundle table, exact comparison against the slot's first claimer
-KERNEL k_frag_group(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+KERNEL_OCC(6) k_frag_group(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
 		chains_view cv, chain_paths cp, const int32_t *handle_chain, cluster_dev c, int *err)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -672,7 +672,7 @@ __device__ void warp_sort_level128(u64 *el, int n, const unsigned char *sf, int 
 // permutation (big ranges by the whole warp, small ones one lane each), then open a new range wherever the gap
 // between neighbours exceeds max_reads_partition_gap.  Range starts are flags by position, so the clusters come
 // out in the same left-to-right order as the reference's recursion.
-__global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_list, int32_t big_cap, const int32_t *f_bundle, const int64_t *frg_off,
+__global__ void __launch_bounds__(128, 8) k_group_partition_warp(const int32_t *n_big, const int32_t *big_list, int32_t big_cap, const int32_t *f_bundle, const int64_t *frg_off,
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, cluster_dev c, const int64_t *member_off, int32_t *members, u64 *elems,
 		int32_t *cflag, int32_t *scratch, int gap)
 {
@@ -882,7 +882,7 @@ struct clusters_out
 };
 
 // ---- C4: one thread per member position that starts a cluster (rnacore/graph_cluster.cc:106-165)
-KERNEL k_cluster_emit(int64_t n_mem, const int32_t *cflag_i /* >= 0 at cluster starts, -1 elsewhere */, const int64_t *crank,
+KERNEL_OCC(6) k_cluster_emit(int64_t n_mem, const int32_t *cflag_i /* >= 0 at cluster starts, -1 elsewhere */, const int64_t *crank,
 		const int32_t *members, const int32_t *mem_bundle_hint, int32_t n_bundles, const int64_t *frg_off, const int64_t *member_boff,
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, const int32_t *handle_chain, graph_dev g, cluster_dev c, clusters_out o)
 {
