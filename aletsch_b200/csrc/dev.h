@@ -26,9 +26,10 @@
 #define DEV __device__ __forceinline__
 #define KERNEL __global__ void
 // thread-per-item kernel of 256 threads whose register count is capped so that n CTAs fit an SM: these kernels wait on chains of
-// dependent loads, the resident warps are their memory-level parallelism
+// dependent loads, the resident warps are their memory-level parallelism (measured at configs[1]: k_frag_group 0.40 -> 0.31 ms,
+// k_frag_align 0.36 -> 0.29, k_update 0.37 -> 0.30, k_cluster_emit 0.34 -> 0.32, k_vote_type2 0.44 -> 0.41; the warp-per-item
+// kernels k_graph_build, k_group_partition_warp and k_bridge_dp_warp got slower or stayed put under a cap and keep their registers)
 #define KERNEL_OCC(n) __global__ void __launch_bounds__(256, n)
-#define KERNEL_OCC128(n) __global__ void __launch_bounds__(128, n)      // the same for the warp-per-item kernels of 4 warps
 #define SHARED __shared__
 #define SHARED16 __shared__ __align__(16)        // tiles block_excl_scan reads with 128-bit accesses
 #define BLOCK_SYNC() __syncthreads()
@@ -38,7 +39,6 @@
 #define DEV inline
 #define KERNEL static void
 #define KERNEL_OCC(n) static void
-#define KERNEL_OCC128(n) static void
 #define SHARED static thread_local
 #define SHARED16 static thread_local
 #define BLOCK_SYNC() do {} while(0)

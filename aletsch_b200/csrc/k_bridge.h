@@ -566,7 +566,7 @@ DEV int dpw_cmp(const int32_t *a, const int32_t *b, int D)
 	return 0;
 }
 
-KERNEL_OCC128(8) k_bridge_dp_warp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bundle, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand,
+KERNEL k_bridge_dp_warp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bundle, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand,
 		bridge_dev br)
 {
 	SHARED int32_t s_cand[DPW_WARPS][DPW_CMAX * DPW_W];

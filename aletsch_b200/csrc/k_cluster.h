@@ -672,7 +672,7 @@ __device__ void warp_sort_level128(u64 *el, int n, const unsigned char *sf, int 
 // permutation (big ranges by the whole warp, small ones one lane each), then open a new range wherever the gap
 // between neighbours exceeds max_reads_partition_gap.  Range starts are flags by position, so the clusters come
 // out in the same left-to-right order as the reference's recursion.
-__global__ void __launch_bounds__(128, 8) k_group_partition_warp(const int32_t *n_big, const int32_t *big_list, int32_t big_cap, const int32_t *f_bundle, const int64_t *frg_off,
+__global__ void k_group_partition_warp(const int32_t *n_big, const int32_t *big_list, int32_t big_cap, const int32_t *f_bundle, const int64_t *frg_off,
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, cluster_dev c, const int64_t *member_off, int32_t *members, u64 *elems,
 		int32_t *cflag, int32_t *scratch, int gap)
 {

@@ -324,8 +324,7 @@ struct graph_params
 	double min_subregion_overlap, min_guaranteed_edge_weight;
 };
 
-// (64 registers: the one-warp CTAs of the bulk launch then fill the SM's 32 CTA slots instead of 25)
-KERNEL_OCC(4) k_graph_build(const int32_t *order, int n_order, graph_in in, graph_dev g, graph_params prm)
+KERNEL k_graph_build(const int32_t *order, int n_order, graph_in in, graph_dev g, graph_params prm)
 {
 	SHARED int s_a, s_b, s_c;
 	for(int bi = blockIdx.x; bi < n_order; bi += gridDim.x)

@@ -106,7 +106,8 @@ ABI_SYMBOLS = ["agpu_default_params", "agpu_create", "agpu_destroy", "agpu_last_
 
 
 def load(lib_path=None):
-    path = lib_path or GPU_SO
+    # ALETSCH_GPU_LIB: another build of the same sources (e.g. a tuning variant under test); never a different implementation
+    path = lib_path or os.environ.get("ALETSCH_GPU_LIB") or GPU_SO
     if not os.path.exists(path):
         raise RuntimeError("CUDA library %s is missing: run __graft_entry__.build() (there is no CPU fallback)" % path)
     L = C.CDLL(path)
