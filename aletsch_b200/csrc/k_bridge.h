@@ -791,7 +791,7 @@ struct stack_greater           // compare_bridge_path_stack (bridge/bridge_path.
 };
 
 // ---- B4: trace back, build the candidate bridges of every pier and order them (nominate :224-257, refine_pier :259-274)
-KERNEL k_pier_bridges(int64_t n_jobs, const int64_t *pier_job, const int32_t *pier_bundle, const int64_t *clu_off, graph_dev g,
+KERNEL_OCC(6) k_pier_bridges(int64_t n_jobs, const int64_t *pier_job, const int32_t *pier_bundle, const int64_t *clu_off, graph_dev g,
 		const uint8_t *b_strand, bridge_dev br)
 {
 	int64_t ji = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -938,7 +938,7 @@ struct vote_out
 	int32_t *chain, *whole;
 };
 
-KERNEL_OCC(6) k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
+KERNEL_OCC(8) k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
 		const int32_t *c_chain2, chains_view cv, graph_dev g, const uint8_t *b_strand, bridge_dev br, vote_out o, vote_lists vl)
 {
 	int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1001,7 +1001,7 @@ KERNEL_OCC(6) k_vote(int64_t n_clu, int emit, const int32_t *c_bundle, const int
 #endif
 }
 
-KERNEL k_vote_type1(int64_t n_clu, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
+KERNEL_OCC(8) k_vote_type1(int64_t n_clu, const int32_t *c_bundle, const int64_t *clu_off, const int32_t *c_bounds, const int32_t *c_chain1,
 		const int32_t *c_chain2, chains_view cv, graph_dev g, const uint8_t *b_strand, bridge_dev br, vote_out o, vote_lists vl)
 {
 	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

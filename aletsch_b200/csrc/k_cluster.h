@@ -235,7 +235,7 @@ KERNEL_OCC(8) k_frag_align(int64_t n_frg, const int32_t *f_bundle, const int64_t
 }
 
 // ---- C2: group by (path1, path2): per-bundle table, exact comparison against the slot's first claimer
-KERNEL_OCC(6) k_frag_group(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
+KERNEL_OCC(8) k_frag_group(int64_t n_frg, const int32_t *f_bundle, const int64_t *frg_off, hits_dev h, const int32_t *f_h1, const int32_t *f_h2,
 		chains_view cv, chain_paths cp, const int32_t *handle_chain, cluster_dev c, int *err)
 {
 	int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -882,7 +882,7 @@ struct clusters_out
 };
 
 // ---- C4: one thread per member position that starts a cluster (rnacore/graph_cluster.cc:106-165)
-KERNEL_OCC(6) k_cluster_emit(int64_t n_mem, const int32_t *cflag_i /* >= 0 at cluster starts, -1 elsewhere */, const int64_t *crank,
+KERNEL_OCC(8) k_cluster_emit(int64_t n_mem, const int32_t *cflag_i /* >= 0 at cluster starts, -1 elsewhere */, const int64_t *crank,
 		const int32_t *members, const int32_t *mem_bundle_hint, int32_t n_bundles, const int64_t *frg_off, const int64_t *member_boff,
 		hits_dev h, const int32_t *f_h1, const int32_t *f_h2, const int32_t *handle_chain, graph_dev g, cluster_dev c, clusters_out o)
 {
