@@ -12,17 +12,11 @@ from . import gpu as G
 
 
 class Pipeline:
-    def __init__(self, device=0, n_streams=3, lib_path=None, blocking_sync=None, prefetch=True, lockstep=None):
+    def __init__(self, device=0, n_streams=3, lib_path=None, blocking_sync=None, prefetch=True):
         """n_streams host threads.  prefetch: every thread owns a second context and queues the upload of its next batch there
-        (agpu_upload_async) before it runs the stages of the current one, so its copy hides behind its own kernels too.
-        lockstep: the threads take the batches in rounds (thread k takes batches k, k + n, ...) and wait for each other after the
-        stages and after the result fetch of a round.  The stages of one context slow down badly while another context's result
-        columns occupy the device-to-host copy engine (their size read-backs queue behind them, profiles/r02_notes.md section 3),
-        so a pool that drifts out of phase is slower than one that keeps the two phases apart; the free-running pool does so most
-        of the time, the rounds make it the rule.  Default: AGPU_PIPE_LOCKSTEP=1."""
+        (agpu_upload_async) before it runs the stages of the current one, so its copy hides behind its own kernels too."""
         self.n_threads = max(1, n_streams)
         self.prefetch = prefetch
-        self.lockstep = bool(int(os.environ.get("AGPU_PIPE_LOCKSTEP", "0"))) if lockstep is None else bool(lockstep)
         # AGPU_PIPE_TRACE=1: wall times of every phase of every sub-batch (upload, stages, results, free) in self.trace
         self.trace = [] if os.environ.get("AGPU_PIPE_TRACE") else None
         self.ctxs = [G.Context(device, lib_path=lib_path) for _ in range(self.n_threads * (2 if prefetch else 1))]
@@ -69,29 +63,11 @@ class Pipeline:
         lock = threading.Lock()
         errs = []
 
-        n_thr = max(1, min(self.n_threads, len(views)))
-        lockstep = self.lockstep and n_thr > 1
-        own = threading.local()
-        # one pair of barriers per round of n_thr batches (the last round may be short)
-        bars = []
-        if lockstep:
-            for r in range((len(views) + n_thr - 1) // n_thr):
-                n = min(n_thr, len(views) - r * n_thr)
-                bars.append((threading.Barrier(n), threading.Barrier(n)))
-
         def claim():
-            if lockstep:
-                i = own.next
-                own.next += n_thr
-                return i if i < len(views) and not errs else None
             with lock:
                 i = nxt[0]
                 nxt[0] += 1
             return i if i < len(views) and not errs else None
-
-        def gate(i, phase):
-            if lockstep:
-                bars[i // n_thr][phase].wait()
 
         tr = self.trace
 
@@ -103,9 +79,8 @@ class Pipeline:
                 tr.append((i, "upload", threading.get_ident(), t0, time.perf_counter()))
             return bt
 
-        def work(mine, k):
+        def work(mine):
             pending = cur = None
-            own.next = k
             try:
                 i = claim()
                 if i is None:
@@ -121,11 +96,9 @@ class Pipeline:
                     try:
                         t0 = time.perf_counter()
                         bt.bridge_all(params)
-                        gate(i, 0)
                         t1 = time.perf_counter()
                         cnt = None if consume else bt.counts()
                         res = bt.results(results) if results else None
-                        gate(i, 1)
                         if tr is not None:
                             tr.append((i, "stages", threading.get_ident(), t0, t1))
                             tr.append((i, "results", threading.get_ident(), t1, time.perf_counter()))
@@ -146,11 +119,7 @@ class Pipeline:
                         j = claim()
                         cur = (j, begin(mine[0], j)) if j is not None else None
             except Exception as e:      # noqa: BLE001 -- re-raised on the caller's thread
-                if not isinstance(e, threading.BrokenBarrierError):
-                    errs.append(e)
-                for pair in bars:        # nobody waits for a thread that has left
-                    pair[0].abort()
-                    pair[1].abort()
+                errs.append(e)
             finally:
                 # nothing stays resident on an error path: the prefetched batch and a current one whose stages never ran
                 for x in (pending, cur):
@@ -162,7 +131,7 @@ class Pipeline:
 
         per = 2 if self.prefetch and not resident else 1
         groups = [self.ctxs[k * per:(k + 1) * per] for k in range(self.n_threads)] if per == 2 else [[c] for c in self.ctxs[:self.n_threads]]
-        ths = [threading.Thread(target=work, args=(g, k)) for k, g in enumerate(groups[:n_thr])]
+        ths = [threading.Thread(target=work, args=(g,)) for g in groups[:max(1, min(len(groups), len(views)))]]
         for t in ths:
             t.start()
         for t in ths:

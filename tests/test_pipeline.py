@@ -37,8 +37,8 @@ def run_variants(lib_path, n_threads, device=0):
     keys = ("hits", "segments", "chains", "junctions", "vertices", "edges", "fragments", "clusters", "bridged", "piers")
     for compact in (False, True):
         views = sub_views(batch, 5, compact)
-        for prefetch, lockstep in ((False, False), (True, False), (True, True)):
-            pipe = Pipeline(device, n_streams=n_threads, lib_path=lib_path, prefetch=prefetch, lockstep=lockstep)
+        for prefetch in (False, True):
+            pipe = Pipeline(device, n_streams=n_threads, lib_path=lib_path, prefetch=prefetch)
             for rep in range(2):
                 res = pipe.run(views * 2, gp, results=G.RESULT_ALL if rep else 0)
                 for k in keys:
