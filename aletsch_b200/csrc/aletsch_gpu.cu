@@ -158,7 +158,6 @@ struct agpu_batch
 	std::vector<int32_t> tid_host, sample_host;
 	// bundles by descending hit count: [0, n_large) get wide CTAs, the rest one warp each
 	dbuf<int32_t> order;
-	dbuf<int32_t> tile_owner;              // hit owning the first operation of every tile of CG_TILE CIGAR operations
 	int32_t n_large = 0;
 	// regions of the per-bundle qname tables (mate pairing): a power of two >= 1.5 x the bundle's hits
 
@@ -188,8 +187,7 @@ struct agpu_batch
 	// insert-size preview result: fragment length per cluster (INT32_MIN: not counted)
 	dbuf<int32_t> pv_isize;
 	bool preview_built = false;
-	bool op_tiles = false;                 // this batch's evidence pass runs on the per-operation tile kernels
-	dbuf<u32> ev_s;                        // window position of the start of every BAM_CMATCH block (k_cigar_tile -> k_cov_add_ops)
+	bool op_warp = false;                  // this batch's evidence pass runs on the warp-per-hit CIGAR walks (long CIGARs)
 	chainset_state hcst, fcst;
 	// segments
 	bool cov_dirty = true;
@@ -501,35 +499,22 @@ static int check_hit_offsets(agpu_ctx *ctx, agpu_batch *b)
 	return AGPU_OK;
 }
 
-// average CIGAR operations per hit from which the evidence pass switches to the per-operation tile kernels (k_cigar_tile,
-// k_cov_add_tile).  Measured on B200 (profiles/r02_notes.md) the thread-per-hit walk is faster at 2 operations per hit
-// (0.67 + 0.40 ms vs 1.16 + 0.75 ms at configs[1]) and still at 35 (6.3 + 3.7 ms vs 8.1 + 4.7 ms at configs[4]): the tile kernels
-// pay ~20 us of barrier-separated phases per tile.  They stay selectable (AGPU_TILE_MIN_OPS=<n>) and are parity-tested.
-static double tile_min_ops()
+// average CIGAR operations per hit from which the CIGAR walks run one WARP per hit (k_hit_cigar_warp, k_cov_add_warp,
+// k_hit_rpos_warp) instead of four hits per thread: at 2 operations per hit (paired-end reads) 30 of a warp's 32 lanes would idle,
+// at 35 (long reads, configs[4]) the thread-per-hit walk serialises 35 dependent iterations.  AGPU_WARP_MIN_OPS=<x> overrides.
+static double warp_min_ops()
 {
 	static double v = -1;
-	if(v < 0) { const char *e = getenv("AGPU_TILE_MIN_OPS"); v = e ? atof(e) : 1e30; }
+	if(v < 0) { const char *e = getenv("AGPU_WARP_MIN_OPS"); v = e ? atof(e) : 8.0; }
 	return v;
 }
-
-// owner hit of every tile of CG_TILE CIGAR operations (k_tile_owner): once per batch, below the arena mark
-static int batch_tile_owner(agpu_ctx *ctx, agpu_batch *b)
-{
-	const int64_t n_tiles = (b->nc + CG_TILE - 1) / CG_TILE;
-	if(!(b->nh > 0 && (double)b->nc / (double)b->nh >= tile_min_ops())) return AGPU_OK;       // thread-per-hit walks: no tiles
-	if(b->tile_owner.p == NULL) TRY(b->tile_owner.alloc(ctx, n_tiles + 2, true));      // (the compact upload allocates it below its arena mark)
-	LAUNCH_T(ctx, k_tile_owner, b->nh, b->nh, b->h.cigar_off, n_tiles, b->tile_owner.p);
-	return AGPU_OK;
-}
+static bool long_cigars(const agpu_batch *b) { return b->nh > 0 && (double)b->nc / (double)b->nh >= warp_min_ops(); }
+#define CW_GRID(ctx, n_hits) std::min<int64_t>(((n_hits) + CW_WARPS - 1) / CW_WARPS, (int64_t)(ctx)->sm_count * 32)
 
 // hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64) on the device, when the host did not send it
 static int derive_rpos(agpu_ctx *ctx, agpu_batch *b)
 {
-	if(b->nh > 0 && (double)b->nc / (double)b->nh >= tile_min_ops())
-	{
-		TRY(d2d(ctx, b->in_rpos.p, b->h.pos, sizeof(int32_t) * (size_t)b->nh));
-		LAUNCH_B(ctx, k_cigar_rpos, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->h, b->nc, b->tile_owner.p, b->in_rpos.p);
-	}
+	if(long_cigars(b)) LAUNCH_B(ctx, k_hit_rpos_warp, CW_GRID(ctx, b->nh), CW_WARPS * CW_WS, b->h, b->in_rpos.p);
 	else LAUNCH_T(ctx, k_hit_rpos, b->nh, b->h, b->in_rpos.p);
 	return AGPU_OK;
 }
@@ -616,7 +601,6 @@ int agpu_batch_upload(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.pos = b->in_pos.p; b->h.rpos = b->in_rpos.p; b->h.mpos = b->in_mpos.p; b->h.isize = b->in_isize.p;
 	b->h.flag = NULL; b->h.strand = b->in_strand.p; b->h.bundle_strand = b->in_bstrand.p; b->h.xs = b->in_xs.p; b->h.qid = (const u64*)b->in_qid.p;
 	b->h.cigar_off = b->in_cigar_off.p; b->h.cigar = b->in_cigar.p;
-	if(batch_tile_owner(ctx, b) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 	if(!in->rpos)
 	{
 		// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), derived on the device
@@ -659,7 +643,6 @@ int agpu_batch_adopt(agpu_ctx *ctx, const agpu_batch_in *in, agpu_batch **out)
 	b->h.flag = in->flag; b->h.strand = in->strand; b->h.bundle_strand = in->bundle_strand; b->h.xs = in->xs; b->h.qid = (const u64*)in->qid;
 	b->h.cigar_off = in->cigar_off; b->h.cigar = in->cigar;
 	if(!in->strand && !in->bundle_strand) { agpu_batch_free(ctx, b); return AGPU_ERR_ARG; }
-	if(batch_tile_owner(ctx, b) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
 	if(!in->rpos)
 	{
 		if(b->in_rpos.alloc(ctx, (size_t)b->nh + 1) != AGPU_OK) { agpu_batch_free(ctx, b); return AGPU_ERR_OOM; }
@@ -688,7 +671,7 @@ static void release_derived(agpu_ctx *ctx, agpu_batch *b)
 	if(b->cb) { agpu_batch_free(ctx, b->cb); b->cb = NULL; }
 	b->g_remap.release(ctx); b->g_members.release(ctx); b->g_first.release(ctx); b->g_member_off.release(ctx); b->g_order_host.clear();
 	b->group_pass = false;
-	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx); b->ev_s.release(ctx);
+	b->spl.release(ctx); b->hit_nspl.release(ctx); b->hit_bundle.release(ctx);
 	b->hcst.release(ctx); b->fcst.release(ctx);
 	b->seg_off.release(ctx);
 	b->seg_l.release(ctx); b->seg_r.release(ctx); b->seg_c.release(ctx); b->seg_nhead.release(ctx); b->seg_psum.release(ctx);
@@ -704,7 +687,7 @@ void agpu_batch_free(agpu_ctx *ctx, agpu_batch *b)
 	b->in_hit_off.release(ctx); b->in_pos.release(ctx); b->in_rpos.release(ctx); b->in_mpos.release(ctx); b->in_isize.release(ctx);
 	b->in_flag.release(ctx); b->in_strand.release(ctx); b->in_bstrand.release(ctx); b->in_xs.release(ctx); b->in_qid.release(ctx);
 	b->in_cigar_off.release(ctx); b->in_cigar.release(ctx);
-	b->err.release(ctx); b->order.release(ctx); b->tile_owner.release(ctx);
+	b->err.release(ctx); b->order.release(ctx);
 	b->cov_skip.release(ctx); b->cov_ex_bundle.release(ctx); b->cov_ex_l.release(ctx); b->cov_ex_r.release(ctx); b->cov_ex_cnt.release(ctx);
 	stream_sync(ctx);
 	if(ctx->arena_owner == b) { ctx->arena.rewind(); ctx->arena_owner = NULL; }
@@ -815,7 +798,7 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		TRY(b->bord_off.alloc(ctx, nb + 2));
 		LAUNCH_T(ctx, k_bord_off, nb + 1, nb, b->cov_base.p, b->wrank.p, b->bord_off.p);
 		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
-		if(b->op_tiles) LAUNCH_B(ctx, k_cov_add_tile, std::min<int64_t>((b->nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 8), 256, b->nc, b->h.cigar, b->ev_s.p, b->border.p, b->wrank.p, b->diffc.p);
+		if(b->op_warp) LAUNCH_B(ctx, k_cov_add_warp, CW_GRID(ctx, b->nh), CW_WARPS * CW_WS, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p, b->cov_skip.p);
 		else LAUNCH_T(ctx, k_cov_add, HQ_THREADS(b->nh), b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p, b->cov_skip.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);
@@ -876,15 +859,10 @@ int agpu_batch_evidence(agpu_ctx *ctx, agpu_batch *b, const agpu_params *p)
 	TRY(b->spl.alloc(ctx, nc + 1)); TRY(b->hit_nspl.alloc(ctx, nh + 1, true));
 	dbuf<int32_t> n_spliced;
 	TRY(n_spliced.alloc(ctx, nb + 1, true));
-	// CIGAR walk.  Default: one thread per hit (k_hit_cigar here, k_cov_add after the borders are ranked).  For batches of long
-	// CIGARs (AGPU_TILE_MIN_OPS operations per hit on average, default off) the per-operation tile kernels: see k_evidence.h
-	b->op_tiles = nh > 0 && (double)nc / (double)nh >= tile_min_ops() && b->cov_skip.p == NULL;
-	if(b->op_tiles)
-	{
-		TRY(b->ev_s.alloc(ctx, nc + 1));
-		LAUNCH_B(ctx, k_cigar_tile, std::min<int64_t>((nc + CG_TILE - 1) / CG_TILE, (int64_t)ctx->sm_count * 6), 256, b->h, nc, b->tile_owner.p, b->hit_bundle.p, b->b_lpos.p,
-				b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, n_spliced.p, b->ev_s.p, b->err.p);
-	}
+	// CIGAR walk: four hits per thread (k_hit_cigar here, k_cov_add after the borders are ranked), or one warp per hit for batches
+	// of long CIGARs (warp_min_ops)
+	b->op_warp = long_cigars(b);
+	if(b->op_warp) LAUNCH_B(ctx, k_hit_cigar_warp, CW_GRID(ctx, nh), CW_WARPS * CW_WS, b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_bundle.p, n_spliced.p, b->err.p, b->cov_skip.p);
 	else LAUNCH_T(ctx, k_hit_cigar, HQ_THREADS(nh), b->h, b->b_lpos.p, b->cov_base.p, b->border.p, b->spl.p, b->hit_nspl.p, b->hit_bundle.p, n_spliced.p, b->err.p, b->cov_skip.p);
 	if(b->n_cov_extra > 0)
 	{

@@ -942,265 +942,169 @@ KERNEL k_lb_cov_segments(lb_ctl c, const int32_t *diffc, const int32_t *posc, in
 	}
 }
 
-// ---- CIGAR walk, one thread per OPERATION (replaces the thread-per-hit walks k_hit_cigar / k_cov_add / k_hit_rpos) ----------
-// A CTA takes a tile of CG_TILE consecutive entries of cigar[] -- whatever hits they belong to -- with 128-bit loads into shared
-// memory.  The reference position of every operation is pos[hit] + (exclusive prefix of the reference-consuming lengths inside
-// the hit): one plain block scan over the tile, minus its value at the hit's first operation; the rank of an inner N operation
-// among the hit's splices is the same with a second scan; the hit of every operation is a running maximum over the marks the
-// tile's hits leave at their first operation.  A hit that starts before the tile gets its carry (consumed length, inner N count)
-// from a cooperative loop over its earlier operations.  So long-read CIGARs (tens of operations per hit) and short-read ones
-// (two per hit) cost the same per operation, every global access is coalesced, and the border bits of the tile -- which lie
-// within a few kilobases because hits are position-sorted -- are collected in a shared-memory bitmap window and leave the CTA as
-// one atomicOr per non-empty word.
-#define CG_TILE 1024
-#define CG_WIN_WORDS 4096        // shared bitmap window: 131072 window positions from the first hit of the tile
-
-struct cg_tile
-{
-	int64_t g0;        // first operation of the tile
-	int m;             // operations in the tile
-	int64_t h0;        // hit owning operation g0
-	int carry_len;     // reference length the operations of h0 before the tile consume
-	int carry_n;       // inner N operations of h0 before the tile
-};
-
-// hit owning operation k: the h with cigar_off[h] <= k < cigar_off[h + 1]
-DEV int64_t cg_owner(const u32 *cigar_off, int64_t n_hits, int64_t k)
-{
-	int64_t lo = 0, hi = n_hits - 1;
-	while(lo < hi)
-	{
-		int64_t mid = (lo + hi) >> 1;
-		if((int64_t)cigar_off[mid + 1] <= k) lo = mid + 1; else hi = mid;
-	}
-	return lo;
-}
-
-// tile_owner[t] = hit owning operation t * CG_TILE (one thread per hit: a hit writes every tile boundary its operations cover);
-// tile_owner[n_tiles] = n_hits - 1 closes the last tile.  cigar_off never changes, so a batch computes this once.
-KERNEL k_tile_owner(int64_t n_hits, const u32 *cigar_off, int64_t n_tiles, int32_t *tile_owner)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= n_hits) return;
-	const int64_t c0 = cigar_off[i], c1 = cigar_off[i + 1];
-	if(i == n_hits - 1) tile_owner[n_tiles] = (int32_t)i;
-	if(c1 <= c0) return;
-	for(int64_t t = (c0 + CG_TILE - 1) / CG_TILE; t * CG_TILE < c1; t++) tile_owner[t] = (int32_t)i;
-}
-
-// loads the tile, fills hid[i] = hit of operation i, P[i] = exclusive prefix of the reference-consuming lengths, and (if R)
-// R[i] = exclusive prefix of the inner-N flags; returns the tile descriptor to every thread
-DEV cg_tile cg_tile_load(const hits_dev &h, int64_t n_ops, const int32_t *tile_owner, int64_t t, u32 *ops, int *hid, int *P, int *R)
-{
-	SHARED long long s_h0, s_h1;
-	SHARED int s_cl, s_cn;
-	cg_tile T;
-	T.g0 = t * CG_TILE;
-	T.m = (int)((n_ops - T.g0) < CG_TILE ? (n_ops - T.g0) : CG_TILE);
-	BLOCK_SYNC();
-	if(threadIdx.x == 0)
-	{
-		s_h0 = tile_owner[t];
-		s_h1 = tile_owner[t + 1];       // owner of the next tile's first operation: no hit of this tile lies beyond it
-		s_cl = 0; s_cn = 0;
-	}
-	// operations: 128-bit loads (tiles start at multiples of 1024 entries, the array base is 256-byte aligned)
+// ---- CIGAR walk, one WARP per hit: the walks for batches of long CIGARs (long reads: tens of operations per hit) -----------------
+// The thread-per-hit walks above read a hit's operations one after the other (35 dependent iterations per hit at configs[4],
+// every load a different cache line from its neighbour lanes' loads).  Here the lanes of a warp take 32 consecutive operations of
+// ONE hit with a single coalesced load; the reference position after every operation is pos + a warp scan of the reference-
+// consuming lengths, the index of an inner N operation among the hit's splices and of an M operation among the hit's match
+// blocks (the skip mask of the insert-size preview) are ballot counts.  CW_WARPS hits per CTA; the per-bundle count of spliced
+// hits leaves the CTA as one atomic per run of hits of the same bundle.  Selected per batch by the mean number of operations
+// per hit (warp_min_ops() in aletsch_gpu.cu).
 #ifndef AGPU_EMU
-	if((((size_t)(h.cigar + T.g0)) & 15) == 0)
-	{
-		const uint4 *src = (const uint4*)(h.cigar + T.g0);
-		for(int i = threadIdx.x; 4 * i < T.m; i += blockDim.x)
-		{
-			if(4 * i + 3 < T.m) { uint4 v = src[i]; ops[4 * i] = v.x; ops[4 * i + 1] = v.y; ops[4 * i + 2] = v.z; ops[4 * i + 3] = v.w; }
-			else for(int j = 4 * i; j < T.m; j++) ops[j] = h.cigar[T.g0 + j];
-		}
-	}
-	else
+#define CW_WS 32
+#else
+#define CW_WS 1                  // kernel-logic build: a "warp" of one lane runs the same code
 #endif
-		for(int i = threadIdx.x; i < T.m; i += blockDim.x) ops[i] = h.cigar[T.g0 + i];
-	for(int i = threadIdx.x; i < T.m; i += blockDim.x) hid[i] = -1;
-	BLOCK_SYNC();
-	T.h0 = (int64_t)s_h0;
-	const int64_t h1 = (int64_t)s_h1;
-	// marks: every hit of the tile at its first operation (hits without operations share an offset with their successor: the
-	// maximum wins, and that is the hit that owns the operation); hit indices relative to h0 keep the marks in 31 bits
-	if(threadIdx.x == 0) hid[0] = 0;
-	BLOCK_SYNC();
-	for(int64_t hh = T.h0 + 1 + threadIdx.x; hh <= h1; hh += blockDim.x)
-	{
-		const int64_t o = (int64_t)h.cigar_off[hh] - T.g0;
-		if(o >= 0 && o < T.m) atomicMax(&hid[o], (int)(hh - T.h0));
-	}
-	BLOCK_SYNC();
-	block_incl_maxscan(hid, T.m);
-	for(int i = threadIdx.x; i < T.m; i += blockDim.x)
-	{
-		const u32 c = ops[i];
-		const u32 op = c & 0xf;
-		P[i] = ((0x3C1A7 >> (op << 1)) & 2) ? (int)(c >> 4) : 0;
-		if(R)
-		{
-			const int64_t hh = T.h0 + hid[i], k = T.g0 + i;
-			R[i] = (op == 3 && k != (int64_t)h.cigar_off[hh] && k != (int64_t)h.cigar_off[hh + 1] - 1) ? 1 : 0;
-		}
-	}
-	// carry of the hit that started before the tile
-	const int64_t c00 = (int64_t)h.cigar_off[T.h0];
-	for(int64_t k = c00 + threadIdx.x; k < T.g0; k += blockDim.x)
-	{
-		const u32 c = h.cigar[k];
-		const u32 op = c & 0xf;
-		if((0x3C1A7 >> (op << 1)) & 2) atomicAdd(&s_cl, (int)(c >> 4));
-		if(op == 3 && k != c00) atomicAdd(&s_cn, 1);
-	}
-	BLOCK_SYNC();
-	block_excl_scan(P, T.m);
-	if(R) block_excl_scan(R, T.m);
-	T.carry_len = s_cl; T.carry_n = s_cn;
-	return T;
+#define CW_WARPS 8
+
+DEV int cw_excl_scan(int v, int lane, int *total)
+{
+#ifndef AGPU_EMU
+	int inc = v;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, inc, o); if(lane >= o) inc += y; }
+	*total = __shfl_sync(0xffffffffu, inc, 31);
+	return inc - v;
+#else
+	(void)lane;
+	*total = v;
+	return 0;
+#endif
+}
+DEV u32 cw_ballot(bool p)
+{
+#ifndef AGPU_EMU
+	return __ballot_sync(0xffffffffu, p);
+#else
+	return p ? 1u : 0u;
+#endif
 }
 
-// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64) when the host did not send it; rpos[] must be pre-filled with pos[]
-// (hits without operations keep it)
-KERNEL k_cigar_rpos(hits_dev h, int64_t n_ops, const int32_t *tile_owner, int32_t *rpos)
+KERNEL k_hit_cigar_warp(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
+		int32_t *spl, int32_t *hit_nspl, const int32_t *hit_bundle, int32_t *n_spliced, int *err, const uint16_t *skip)
 {
-	SHARED u32 ops[CG_TILE];
-	SHARED int hid[CG_TILE], P[CG_TILE];
-	const int64_t n_tiles = (n_ops + CG_TILE - 1) / CG_TILE;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
+	SHARED int s_b[CW_WARPS], s_n[CW_WARPS];
+	const int lane = threadIdx.x % CW_WS, warp = threadIdx.x / CW_WS;
+	const int wpb = blockDim.x / CW_WS;
+	const u32 lt = (1u << lane) - 1u;
+	for(int64_t base = (int64_t)blockIdx.x * wpb; base < h.n_hits; base += (int64_t)gridDim.x * wpb)
 	{
-		const cg_tile T = cg_tile_load(h, n_ops, tile_owner, t, ops, hid, P, (int*)NULL);
-		for(int i = threadIdx.x; i < T.m; i += blockDim.x)
+		const int64_t i = base + warp;
+		int b = -1, ns = 0;
+		if(i < h.n_hits)
 		{
-			const int64_t hh = T.h0 + hid[i], k = T.g0 + i;
-			if(k != (int64_t)h.cigar_off[hh + 1] - 1) continue;          // the hit's last operation writes
-			const int64_t c0 = (int64_t)h.cigar_off[hh];
-			const bool carried = c0 < T.g0;
-			const int ib = carried ? 0 : (int)(c0 - T.g0);
-			const u32 c = ops[i];
-			const int own = ((0x3C1A7 >> ((c & 0xf) << 1)) & 2) ? (int)(c >> 4) : 0;
-			rpos[hh] = h.pos[hh] + (carried ? T.carry_len : 0) + (P[i] - P[ib]) + own;
-		}
-		BLOCK_SYNC();
-	}
-}
-
-// evidence pass over the operations: border bits of every BAM_CMATCH block (bundle_base::add_intervals: only op M adds
-// coverage), splice coordinates (hit::extract_splices: every N that is neither the first nor the last operation), per-hit splice
-// count, per-bundle number of spliced hits, the rpos contract check, and ev_s[k] = window position of the start of block k for
-// the second pass (k_cov_add_ops).  hit_nspl must be zeroed by the caller (hits without operations).
-KERNEL k_cigar_tile(hits_dev h, int64_t n_ops, const int32_t *tile_owner, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
-		int32_t *spl, int32_t *hit_nspl, int32_t *n_spliced, u32 *ev_s, int *err)
-{
-	SHARED u32 ops[CG_TILE];
-	SHARED int hid[CG_TILE], P[CG_TILE], R[CG_TILE];
-	SHARED u32 win[CG_WIN_WORDS];
-	SHARED int s_hi;
-	const int64_t n_tiles = (n_ops + CG_TILE - 1) / CG_TILE;
-	for(int i = threadIdx.x; i < CG_WIN_WORDS; i += blockDim.x) win[i] = 0;
-	if(threadIdx.x == 0) s_hi = -1;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		const cg_tile T = cg_tile_load(h, n_ops, tile_owner, t, ops, hid, P, R);
-		// window of the shared bitmap: from the word of the first hit's start (hits are position-sorted inside a bundle and the
-		// bundles' windows follow one another, so nothing of the tile lies before it)
-		const int b00 = hit_bundle[T.h0];
-		const int64_t wword = (cov_base[b00] - (int64_t)b_lpos[b00] + (int64_t)h.pos[T.h0]) >> 5;
-		for(int i = threadIdx.x; i < T.m; i += blockDim.x)
-		{
-			const int64_t hh = T.h0 + hid[i], k = T.g0 + i;
-			const int64_t c0 = (int64_t)h.cigar_off[hh], c1 = (int64_t)h.cigar_off[hh + 1];
-			const bool carried = c0 < T.g0;
-			const int ib = carried ? 0 : (int)(c0 - T.g0);
-			const u32 c = ops[i];
-			const u32 op = c & 0xf, len = c >> 4;
-			const int own = ((0x3C1A7 >> (op << 1)) & 2) ? (int)len : 0;
-			const int32_t p0 = h.pos[hh] + (carried ? T.carry_len : 0) + (P[i] - P[ib]);      // reference position before the operation
-			const int32_t p1 = p0 + own;
-			const int rank = (carried ? T.carry_n : 0) + (R[i] - R[ib]);
-			const int b = hit_bundle[hh];
-			if(op == 0 && len > 0)
+			b = hit_bundle[i];
+			const int64_t wb = cov_base[b] - (int64_t)b_lpos[b];
+			const u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
+			const u32 sk = skip ? skip[i] : 0u;
+			int32_t p = h.pos[i];
+			int z = 0;
+			int32_t *out = spl + c0;
+			for(u32 k0 = c0; k0 < c1; k0 += CW_WS)
 			{
-				const int64_t base = cov_base[b] - (int64_t)b_lpos[b];
-				const int64_t s = base + p0, e = base + p1;
-				ev_s[k] = (u32)s;
-				const int64_t ws = (s >> 5) - wword, we = (e >> 5) - wword;
-				if(ws >= 0 && ws < CG_WIN_WORDS) { atomicOr(&win[ws], 1u << (s & 31)); atomicMax(&s_hi, (int)ws); }
-				else atomicOr(&border[s >> 5], 1u << (s & 31));
-				if(we >= 0 && we < CG_WIN_WORDS) { atomicOr(&win[we], 1u << (e & 31)); atomicMax(&s_hi, (int)we); }
-				else atomicOr(&border[e >> 5], 1u << (e & 31));
-			}
-			const bool inner_n = op == 3 && k != c0 && k != c1 - 1;
-			if(inner_n)
-			{
-				// a hit's splices live in its own stretch of spl[] (as many ints as it has operations)
-				if(2 * rank + 2 <= (int)(c1 - c0)) { spl[c0 + 2 * rank] = p1 - (int32_t)len; spl[c0 + 2 * rank + 1] = p1; }
-				else atomicAdd(&err[ERR_CAP], 1);
-			}
-			if(k == c1 - 1)
-			{
-				const int ns = 2 * rank;           // the last operation is never an inner N
-				hit_nspl[hh] = ns;
-				if(p1 != h.rpos[hh]) atomicAdd(&err[ERR_RPOS], 1);
-				if(ns > 0) atomicAdd(&n_spliced[b], 1);
-			}
-		}
-		BLOCK_SYNC();
-		const int hi = s_hi;
-		for(int w = threadIdx.x; w <= hi; w += blockDim.x)
-		{
-			const u32 bits = win[w];
-			if(bits) { atomicOr(&border[wword + w], bits); win[w] = 0; }
-		}
-		BLOCK_SYNC();
-		if(threadIdx.x == 0) s_hi = -1;
-	}
-}
-
-// second pass over the operations: +1 at the start and -1 at the end of every BAM_CMATCH block, at the borders' ranks.  The
-// hits of a tile start within a few kilobases of one another and share exon ends, so a tile's events are first summed per
-// position in a shared-memory hash table; every distinct position then costs one border_rank lookup and ONE global atomic.
-#define CA_SLOTS 4096            // >= 2 x the events of a tile (two per operation)
-KERNEL k_cov_add_tile(int64_t n_ops, const u32 *cigar, const u32 *ev_s, const u32 *border, const u32 *wrank, int32_t *diffc)
-{
-	SHARED u32 s_key[CA_SLOTS];
-	SHARED int s_cnt[CA_SLOTS];
-	const int64_t n_tiles = (n_ops + CG_TILE - 1) / CG_TILE;
-	for(int i = threadIdx.x; i < CA_SLOTS; i += blockDim.x) { s_key[i] = 0xffffffffu; s_cnt[i] = 0; }
-	BLOCK_SYNC();
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		const int64_t g0 = t * CG_TILE;
-		for(int i = threadIdx.x; i < CG_TILE; i += blockDim.x)
-		{
-			const int64_t k = g0 + i;
-			if(k >= n_ops) break;
-			const u32 c = cigar[k];
-			if((c & 0xf) != 0 || (c >> 4) == 0) continue;
-			const u32 s0 = ev_s[k];
-			for(int side = 0; side < 2; side++)
-			{
-				const u32 key = side ? s0 + (c >> 4) : s0;          // window positions stay below 2^32 - 64 (agpu_batch_evidence)
-				u32 p = (key * 2654435761u) >> 20;                    // 12 bits
-				while(true)
+				const u32 k = k0 + lane;
+				const bool act = k < c1;
+				const u32 c = act ? h.cigar[k] : 0u;
+				const u32 op = c & 0xf, len = c >> 4;
+				const int adv = (act && ((0x3C1A7 >> (op << 1)) & 2)) ? (int)len : 0;      // bam_cigar_type: consumes reference
+				int tot;
+				const int32_t pe = p + cw_excl_scan(adv, lane, &tot) + adv;                  // position after this operation
+				const bool isM = act && op == 0;                                           // BAM_CMATCH
+				const u32 mM = cw_ballot(isM);
+				const int zi = z + __popc(mM & lt);
+				if(isM && len > 0 && !(zi < 16 && ((sk >> zi) & 1u)))
 				{
-					const u32 cur = atomicCAS(&s_key[p], 0xffffffffu, key);
-					if(cur == 0xffffffffu || cur == key) break;
-					p = (p + 1) & (CA_SLOTS - 1);
+					const int64_t s = wb + pe - (int32_t)len, e = wb + pe;
+					atomicOr(&border[s >> 5], 1u << (s & 31));
+					atomicOr(&border[e >> 5], 1u << (e & 31));
 				}
-				atomicAdd(&s_cnt[p], side ? -1 : 1);
+				const bool isN = act && op == 3 && k != c0 && k != c1 - 1;                 // BAM_CREF_SKIP, not first / last op
+				const u32 mN = cw_ballot(isN);
+				if(isN)
+				{
+					const int o = ns + 2 * __popc(mN & lt);
+					out[o] = pe - (int32_t)len;
+					out[o + 1] = pe;
+				}
+				p += tot; z += __popc(mM); ns += 2 * __popc(mN);
+			}
+			if(lane == 0)
+			{
+				if(p != h.rpos[i]) atomicAdd(&err[ERR_RPOS], 1);
+				hit_nspl[i] = ns;
+			}
+		}
+		if(lane == 0) { s_b[warp] = b; s_n[warp] = ns > 0 ? 1 : 0; }
+		BLOCK_SYNC();
+		if(threadIdx.x == 0)
+		{
+			for(int w = 0; w < wpb; )
+			{
+				int e = w, cnt = 0;
+				while(e < wpb && s_b[e] == s_b[w]) { cnt += s_n[e]; e++; }
+				if(s_b[w] >= 0 && cnt > 0) atomicAdd(&n_spliced[s_b[w]], cnt);
+				w = e;
 			}
 		}
 		BLOCK_SYNC();
-		for(int i = threadIdx.x; i < CA_SLOTS; i += blockDim.x)
+	}
+}
+
+KERNEL k_cov_add_warp(hits_dev h, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, const u32 *border,
+		const u32 *wrank, int32_t *diffc, const uint16_t *skip)
+{
+	const int lane = threadIdx.x % CW_WS, warp = threadIdx.x / CW_WS;
+	const int wpb = blockDim.x / CW_WS;
+	const u32 lt = (1u << lane) - 1u;
+	for(int64_t i = (int64_t)blockIdx.x * wpb + warp; i < h.n_hits; i += (int64_t)gridDim.x * wpb)
+	{
+		const int b = hit_bundle[i];
+		const int64_t wb = cov_base[b] - (int64_t)b_lpos[b];
+		const u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
+		const u32 sk = skip ? skip[i] : 0u;
+		int32_t p = h.pos[i];
+		int z = 0;
+		for(u32 k0 = c0; k0 < c1; k0 += CW_WS)
 		{
-			const u32 key = s_key[i];
-			if(key == 0xffffffffu) continue;
-			const int d = s_cnt[i];
-			if(d != 0) atomicAdd(&diffc[border_rank(border, wrank, (int64_t)key)], d);
-			s_key[i] = 0xffffffffu; s_cnt[i] = 0;
+			const u32 k = k0 + lane;
+			const bool act = k < c1;
+			const u32 c = act ? h.cigar[k] : 0u;
+			const u32 op = c & 0xf, len = c >> 4;
+			const int adv = (act && ((0x3C1A7 >> (op << 1)) & 2)) ? (int)len : 0;
+			int tot;
+			const int32_t pe = p + cw_excl_scan(adv, lane, &tot) + adv;
+			const bool isM = act && op == 0;
+			const u32 mM = cw_ballot(isM);
+			const int zi = z + __popc(mM & lt);
+			if(isM && len > 0 && !(zi < 16 && ((sk >> zi) & 1u)))
+			{
+				atomicAdd(&diffc[border_rank(border, wrank, wb + pe - (int32_t)len)], 1);
+				atomicAdd(&diffc[border_rank(border, wrank, wb + pe)], -1);
+			}
+			p += tot; z += __popc(mM);
 		}
-		BLOCK_SYNC();
+	}
+}
+
+// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), one warp per hit
+KERNEL k_hit_rpos_warp(hits_dev h, int32_t *rpos)
+{
+	const int lane = threadIdx.x % CW_WS, warp = threadIdx.x / CW_WS;
+	const int wpb = blockDim.x / CW_WS;
+	for(int64_t i = (int64_t)blockIdx.x * wpb + warp; i < h.n_hits; i += (int64_t)gridDim.x * wpb)
+	{
+		const u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
+		int32_t p = h.pos[i];
+		for(u32 k0 = c0; k0 < c1; k0 += CW_WS)
+		{
+			const u32 k = k0 + lane;
+			const u32 c = k < c1 ? h.cigar[k] : 0u;
+			const int adv = (k < c1 && ((0x3C1A7 >> ((c & 0xf) << 1)) & 2)) ? (int)(c >> 4) : 0;
+			int tot;
+			(void)cw_excl_scan(adv, lane, &tot);
+			p += tot;
+		}
+		if(lane == 0) rpos[i] = p;
 	}
 }
 

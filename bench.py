@@ -197,6 +197,7 @@ def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
     J, V, E, NBD, M = cnt["junctions"], cnt["vertices"], cnt["edges"], cnt["borders"], cnt["cluster_members"]
     Mbig = cnt.get("big_group_members", 0)
     kernel = kernel.replace("(side)", "")
+    kernel = {"k_hit_cigar_warp": "k_hit_cigar", "k_cov_add_warp": "k_cov_add"}.get(kernel, kernel)      # the warp-per-hit walks of long CIGARs move the same bytes
     if kernel == "k_hit_cigar":
         # in: pos, rpos, cigar_off (12 B/hit) + CIGAR ops; out: nspl, hash, bundle id (16 B/hit) + splice coordinates
         # + one read-modify-write of a 4-byte bitmap word per block end

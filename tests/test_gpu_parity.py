@@ -228,32 +228,58 @@ def test_fuzz_bundles(ctx, checkers):
     test_fuzz.run_pair_seeds(ctx, checkers, range(12))
 
 
-def test_pairing_exact_path_at_scale():
-    """AGPU_PAIR_EXACT=1 sends EVERY hit that has a mate candidate through the exact per-(bundle, qname) greedy (the path only
-    multi-mapped query names take otherwise): same fragments as the reference on a batch of 60,000 templates.  The switch is
-    read once per process, hence the child process."""
+CHILD_PRELUDE = ("import sys; sys.path.insert(0, 'tests'); import parity, orclib, test_fuzz\n"
+                 "from aletsch_b200 import gpu as G, hostlib as H\n"
+                 "checkers = {}\n"
+                 "for p in ('ref', 'orc'):\n"
+                 "    try:\n"
+                 "        checkers[p] = orclib.Checker(p)\n"
+                 "    except (OSError, FileNotFoundError):\n"
+                 "        pass\n"
+                 "assert checkers\n"
+                 "chk = checkers.get('ref') or next(iter(checkers.values()))\n"
+                 "ctx = G.Context(0)\n")
+
+
+def run_child(env, body, marker):
+    """a parity run in a child process: the library reads its path switches from the environment once per process"""
     import os
     import subprocess
     import sys
-    code = ("import sys; sys.path.insert(0, 'tests'); import parity, orclib\n"
-            "from aletsch_b200 import gpu as G, hostlib as H\n"
-            "ctx = G.Context(0); batch, lt = parity.make_batch(H.SYNTH_PAIRED, 60000, seed=20260111)\n"
-            "gp, op = parity.params_pair(lt)\n"
-            "chk = None\n"
-            "for p in ('ref', 'orc'):\n"
-            "    try:\n"
-            "        chk = orclib.Checker(p); break\n"
-            "    except (OSError, FileNotFoundError):\n"
-            "        pass\n"
-            "stats = {}; bad = parity.compare_full(ctx, batch, chk, gp, op, stats)\n"
-            "assert not bad, bad[:3]\n"
-            "assert stats['fragments'] > 10000\n"
-            "print('exact path ok', stats['fragments'])\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, AGPU_PAIR_EXACT="1")
-    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-c", CHILD_PRELUDE + body], cwd=root, env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "exact path ok" in r.stdout
+    assert marker in r.stdout
+
+
+def test_pairing_exact_path_at_scale():
+    """AGPU_PAIR_EXACT=1 sends EVERY hit that has a mate candidate through the exact per-(bundle, qname) greedy (the path only
+    multi-mapped query names take otherwise): same fragments as the reference on a batch of 60,000 templates."""
+    run_child({"AGPU_PAIR_EXACT": "1"},
+              "batch, lt = parity.make_batch(H.SYNTH_PAIRED, 60000, seed=20260111)\n"
+              "gp, op = parity.params_pair(lt)\n"
+              "stats = {}; bad = parity.compare_full(ctx, batch, chk, gp, op, stats)\n"
+              "assert not bad, bad[:3]\n"
+              "assert stats['fragments'] > 10000\n"
+              "print('exact path ok', stats['fragments'])\n", "exact path ok")
+
+
+def test_warp_cigar_walk_on_short_reads():
+    """AGPU_WARP_MIN_OPS=0 runs the warp-per-hit CIGAR walks (the long-read path: k_hit_cigar_warp, k_cov_add_warp,
+    k_hit_rpos_warp) on every batch: adversarial CIGARs of 1-9 operations, the synthetic paired-end batch through the compact
+    upload (rpos derived on the device), and the insert-size preview (the skip mask of the match blocks)."""
+    run_child({"AGPU_WARP_MIN_OPS": "0"},
+              "test_fuzz.run_seeds(ctx, checkers, range(10))\n"
+              "test_fuzz.run_seeds(ctx, checkers, range(100, 102), big=True)\n"
+              "batch, lt = parity.make_batch(H.SYNTH_PAIRED, 30000, seed=20260112)\n"
+              "gp, op = parity.params_pair(lt)\n"
+              "stats = {}; bad = parity.compare_full(ctx, batch, chk, gp, op, stats)\n"
+              "assert not bad, bad[:3]\n"
+              "import test_gpu_parity as T\n"
+              "T.test_compact_upload_matches_full(ctx, H.SYNTH_PAIRED, 20000)\n"
+              "import test_preview_insertsize as P\n"
+              "P.run_cases(ctx, chk)\n"
+              "print('warp walk ok', stats['segments'])\n", "warp walk ok")
 
 
 def test_long_read_scale_parity(ctx, checkers):
