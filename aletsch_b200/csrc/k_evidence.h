@@ -241,6 +241,13 @@ HD u64 chain_hash(const int32_t *v, int n)
 // of them before it uses any; the first CIGAR operation of a hit (the only one of an unspliced read) is fetched with that level.
 // Launch with HQ_THREADS(n_hits) threads.
 #define HQ 4
+// A border bit is set once and asked for many times (every read that starts or ends a block there: twice per border at
+// configs[1], 28 times at configs[4]): look first -- a stale cached word only costs the atomic it would have cost anyway.
+DEV void border_set(u32 *border, int64_t g)
+{
+	const u32 bit = 1u << (g & 31);
+	if(!(border[g >> 5] & bit)) atomicOr(&border[g >> 5], bit);
+}
 #define HQ_THREADS(n) ((((int64_t)(n) + 256 * HQ - 1) / (256 * HQ)) * 256)
 KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
 		int32_t *spl, int32_t *hit_nspl, const int32_t *hit_bundle, int32_t *n_spliced, int *err, const uint16_t *skip)
@@ -289,11 +296,7 @@ KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u
 				const int64_t s = base + p - (int32_t)len, e = base + p;
 				const bool skipped = z < 16 && ((sk >> z) & 1u);
 				z++;
-				if(len > 0 && !skipped)
-				{
-					atomicOr(&border[s >> 5], 1u << (s & 31));
-					atomicOr(&border[e >> 5], 1u << (e & 31));
-				}
+				if(len > 0 && !skipped) { border_set(border, s); border_set(border, e); }
 			}
 			if(op == 3 && k != c0 && k != c1 - 1)                  // BAM_CREF_SKIP, not first / last op
 			{
@@ -1014,9 +1017,8 @@ KERNEL k_hit_cigar_warp(hits_dev h, const int32_t *b_lpos, const int64_t *cov_ba
 				const int zi = z + __popc(mM & lt);
 				if(isM && len > 0 && !(zi < 16 && ((sk >> zi) & 1u)))
 				{
-					const int64_t s = wb + pe - (int32_t)len, e = wb + pe;
-					atomicOr(&border[s >> 5], 1u << (s & 31));
-					atomicOr(&border[e >> 5], 1u << (e & 31));
+					border_set(border, wb + pe - (int32_t)len);
+					border_set(border, wb + pe);
 				}
 				const bool isN = act && op == 3 && k != c0 && k != c1 - 1;                 // BAM_CREF_SKIP, not first / last op
 				const u32 mN = cw_ballot(isN);
@@ -1050,39 +1052,77 @@ KERNEL k_hit_cigar_warp(hits_dev h, const int32_t *b_lpos, const int64_t *cov_ba
 	}
 }
 
+// The +1 / -1 of the match blocks, aggregated per CTA: a CTA takes CA_CHUNK consecutive hits -- reads of one locus, whose blocks
+// start and end at the same few exon boundaries -- counts their borders in a shared-memory table keyed by border rank and adds
+// every distinct border to diffc[] once (an entry that finds no slot within CA_PROBES goes to diffc[] directly).
+#define CA_LOG_SLOTS 12
+#define CA_SLOTS (1 << CA_LOG_SLOTS)
+#define CA_PROBES 16
+#define CA_CHUNK 256
+#define CA_EMPTY 0xffffffffu
+DEV void ca_add(u32 *s_key, int *s_cnt, int32_t *diffc, int64_t rank, int d)
+{
+	const u32 key = (u32)rank;
+	u32 x = (key * 2654435761u) >> (32 - CA_LOG_SLOTS);
+	for(int probe = 0; probe < CA_PROBES; probe++)
+	{
+		const u32 cur = atomicCAS(&s_key[x], CA_EMPTY, key);
+		if(cur == CA_EMPTY || cur == key) { atomicAdd(&s_cnt[x], d); return; }
+		x = (x + 1) & (CA_SLOTS - 1);
+	}
+	atomicAdd(&diffc[rank], d);
+}
 KERNEL k_cov_add_warp(hits_dev h, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, const u32 *border,
 		const u32 *wrank, int32_t *diffc, const uint16_t *skip)
 {
+	SHARED u32 s_key[CA_SLOTS];
+	SHARED int s_cnt[CA_SLOTS];
 	const int lane = threadIdx.x % CW_WS, warp = threadIdx.x / CW_WS;
 	const int wpb = blockDim.x / CW_WS;
 	const u32 lt = (1u << lane) - 1u;
-	for(int64_t i = (int64_t)blockIdx.x * wpb + warp; i < h.n_hits; i += (int64_t)gridDim.x * wpb)
+	for(int x = threadIdx.x; x < CA_SLOTS; x += blockDim.x) { s_key[x] = CA_EMPTY; s_cnt[x] = 0; }
+	BLOCK_SYNC();
+	for(int64_t base = (int64_t)blockIdx.x * CA_CHUNK; base < h.n_hits; base += (int64_t)gridDim.x * CA_CHUNK)
 	{
-		const int b = hit_bundle[i];
-		const int64_t wb = cov_base[b] - (int64_t)b_lpos[b];
-		const u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
-		const u32 sk = skip ? skip[i] : 0u;
-		int32_t p = h.pos[i];
-		int z = 0;
-		for(u32 k0 = c0; k0 < c1; k0 += CW_WS)
+		const int64_t end = base + CA_CHUNK < h.n_hits ? base + CA_CHUNK : h.n_hits;
+		for(int64_t i = base + warp; i < end; i += wpb)
 		{
-			const u32 k = k0 + lane;
-			const bool act = k < c1;
-			const u32 c = act ? h.cigar[k] : 0u;
-			const u32 op = c & 0xf, len = c >> 4;
-			const int adv = (act && ((0x3C1A7 >> (op << 1)) & 2)) ? (int)len : 0;
-			int tot;
-			const int32_t pe = p + cw_excl_scan(adv, lane, &tot) + adv;
-			const bool isM = act && op == 0;
-			const u32 mM = cw_ballot(isM);
-			const int zi = z + __popc(mM & lt);
-			if(isM && len > 0 && !(zi < 16 && ((sk >> zi) & 1u)))
+			const int b = hit_bundle[i];
+			const int64_t wb = cov_base[b] - (int64_t)b_lpos[b];
+			const u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
+			const u32 sk = skip ? skip[i] : 0u;
+			int32_t p = h.pos[i];
+			int z = 0;
+			for(u32 k0 = c0; k0 < c1; k0 += CW_WS)
 			{
-				atomicAdd(&diffc[border_rank(border, wrank, wb + pe - (int32_t)len)], 1);
-				atomicAdd(&diffc[border_rank(border, wrank, wb + pe)], -1);
+				const u32 k = k0 + lane;
+				const bool act = k < c1;
+				const u32 c = act ? h.cigar[k] : 0u;
+				const u32 op = c & 0xf, len = c >> 4;
+				const int adv = (act && ((0x3C1A7 >> (op << 1)) & 2)) ? (int)len : 0;
+				int tot;
+				const int32_t pe = p + cw_excl_scan(adv, lane, &tot) + adv;
+				const bool isM = act && op == 0;
+				const u32 mM = cw_ballot(isM);
+				const int zi = z + __popc(mM & lt);
+				if(isM && len > 0 && !(zi < 16 && ((sk >> zi) & 1u)))
+				{
+					ca_add(s_key, s_cnt, diffc, border_rank(border, wrank, wb + pe - (int32_t)len), 1);
+					ca_add(s_key, s_cnt, diffc, border_rank(border, wrank, wb + pe), -1);
+				}
+				p += tot; z += __popc(mM);
 			}
-			p += tot; z += __popc(mM);
 		}
+		BLOCK_SYNC();
+		for(int x = threadIdx.x; x < CA_SLOTS; x += blockDim.x)
+		{
+			const u32 key = s_key[x];
+			if(key == CA_EMPTY) continue;
+			const int d = s_cnt[x];
+			if(d != 0) atomicAdd(&diffc[key], d);
+			s_key[x] = CA_EMPTY; s_cnt[x] = 0;
+		}
+		BLOCK_SYNC();
 	}
 }
 
