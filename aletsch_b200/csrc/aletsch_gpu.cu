@@ -509,7 +509,8 @@ static double warp_min_ops()
 	return v;
 }
 static bool long_cigars(const agpu_batch *b) { return b->nh > 0 && (double)b->nc / (double)b->nh >= warp_min_ops(); }
-#define CW_GRID(ctx, n_hits) std::min<int64_t>(((n_hits) + CW_WARPS - 1) / CW_WARPS, (int64_t)(ctx)->sm_count * 32)
+// one warp per group of CW_WS hits, CW_WARPS warps per CTA
+#define CW_GRID(ctx, n_hits) std::min<int64_t>(((n_hits) + CW_WARPS * CW_WS - 1) / (CW_WARPS * CW_WS), (int64_t)(ctx)->sm_count * 32)
 
 // hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64) on the device, when the host did not send it
 static int derive_rpos(agpu_ctx *ctx, agpu_batch *b)
@@ -798,7 +799,7 @@ static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 		TRY(b->bord_off.alloc(ctx, nb + 2));
 		LAUNCH_T(ctx, k_bord_off, nb + 1, nb, b->cov_base.p, b->wrank.p, b->bord_off.p);
 		LAUNCH_T(ctx, k_bord_positions, nw, nw, b->border.p, b->wrank.p, nb, b->cov_base.p, b->b_lpos.p, b->posc.p);
-		if(b->op_warp) LAUNCH_B(ctx, k_cov_add_warp, std::min<int64_t>((b->nh + CA_CHUNK - 1) / CA_CHUNK, (int64_t)ctx->sm_count * 8), CW_WARPS * CW_WS, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p, b->cov_skip.p);
+		if(b->op_warp) LAUNCH_B(ctx, k_cov_add_warp, CW_GRID(ctx, b->nh), CW_WARPS * CW_WS, b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p, b->cov_skip.p);
 		else LAUNCH_T(ctx, k_cov_add, HQ_THREADS(b->nh), b->h, b->hit_bundle.p, b->b_lpos.p, b->cov_base.p, b->border.p, b->wrank.p, b->diffc.p, b->cov_skip.p);
 		LAUNCH_T(ctx, k_cov_add_extra, b->n_extra, b->n_extra, b->ex_s.p, b->ex_e.p, b->border.p, b->wrank.p, b->diffc.p);
 		LAUNCH_T(ctx, k_cov_add_points, b->n_pts, b->n_pts, b->pt_g.p, b->pt_d.p, b->border.p, b->wrank.p, b->diffc.p);

@@ -241,14 +241,10 @@ HD u64 chain_hash(const int32_t *v, int n)
 // of them before it uses any; the first CIGAR operation of a hit (the only one of an unspliced read) is fetched with that level.
 // Launch with HQ_THREADS(n_hits) threads.
 #define HQ 4
-// A border bit is set once and asked for many times (every read that starts or ends a block there: twice per border at
-// configs[1], 28 times at configs[4]): look first -- a stale cached word only costs the atomic it would have cost anyway.
-DEV void border_set(u32 *border, int64_t g)
-{
-	const u32 bit = 1u << (g & 31);
-	if(!(border[g >> 5] & bit)) atomicOr(&border[g >> 5], bit);
-}
 #define HQ_THREADS(n) ((((int64_t)(n) + 256 * HQ - 1) / (256 * HQ)) * 256)
+DEV void border_set(u32 *border, int64_t g) { atomicOr(&border[g >> 5], 1u << (g & 31)); }
+// (looking at the word first -- a border is asked for 2 times at configs[1], 28 times at configs[4] -- measured slower: the
+// load it adds sits in front of the atomic, which otherwise leaves the thread without waiting)
 KERNEL k_hit_cigar(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
 		int32_t *spl, int32_t *hit_nspl, const int32_t *hit_bundle, int32_t *n_spliced, int *err, const uint16_t *skip)
 {
@@ -945,18 +941,21 @@ KERNEL k_lb_cov_segments(lb_ctl c, const int32_t *diffc, const int32_t *posc, in
 	}
 }
 
-// ---- CIGAR walk, one WARP per hit: the walks for batches of long CIGARs (long reads: tens of operations per hit) -----------------
+// ---- CIGAR walk by warps: the walks for batches of long CIGARs (long reads: tens of operations per hit) ----------------------
 // The thread-per-hit walks above read a hit's operations one after the other (35 dependent iterations per hit at configs[4],
-// every load a different cache line from its neighbour lanes' loads).  Here the lanes of a warp take 32 consecutive operations of
-// ONE hit with a single coalesced load; the reference position after every operation is pos + a warp scan of the reference-
-// consuming lengths, the index of an inner N operation among the hit's splices and of an M operation among the hit's match
-// blocks (the skip mask of the insert-size preview) are ballot counts.  CW_WARPS hits per CTA; the per-bundle count of spliced
-// hits leaves the CTA as one atomic per run of hits of the same bundle.  Selected per batch by the mean number of operations
-// per hit (warp_min_ops() in aletsch_gpu.cu).
+// every load a different cache line from its neighbour lanes' loads).  Here a warp takes a GROUP of 32 consecutive hits: lane j
+// loads the fields of hit j (one coalesced load per field, one pass over the dependent bundle lookups for all 32), then the
+// warp walks the hits one after the other, the fields of the current one broadcast by shuffles, its operations loaded 32 at a
+// time by the lanes -- and the first 32 operations of the NEXT hit requested before the current one is processed, so a hit
+// costs no load latency of its own (a first version with one hit per warp and its loads in front of the walk ran 4.9 + 4.2 ms
+// at configs[4] against 6.0 + 3.7 ms for the thread-per-hit walks: ~3.5 us of dependent loads per hit and warp).  The reference
+// position after every operation is pos + a warp scan of the reference-consuming lengths; the index of an inner N operation
+// among the hit's splices and of an M operation among its match blocks (the skip mask of the insert-size preview) are ballot
+// counts.  Selected per batch by the mean number of operations per hit (warp_min_ops() in aletsch_gpu.cu).
 #ifndef AGPU_EMU
 #define CW_WS 32
 #else
-#define CW_WS 1                  // kernel-logic build: a "warp" of one lane runs the same code
+#define CW_WS 1                  // kernel-logic build: a "warp" of one lane runs the same code on groups of one hit
 #endif
 #define CW_WARPS 8
 
@@ -982,169 +981,159 @@ DEV u32 cw_ballot(bool p)
 	return p ? 1u : 0u;
 #endif
 }
+template<typename T> DEV T cw_shfl(T v, int j)
+{
+#ifndef AGPU_EMU
+	return __shfl_sync(0xffffffffu, v, j);
+#else
+	(void)j;
+	return v;
+#endif
+}
+
+// the walk of one group: begin(j) before hit j, chunk(j, first, k, c0, c1, act, op, len, pe) for every 32 operations (pe = the
+// reference position after the lane's operation), end(j, p) with the position after the last one.  All hooks run warp-uniformly.
+template<typename B, typename C, typename E> DEV void cw_walk(const hits_dev &h, int64_t g, int lane, B begin, C chunk, E end)
+{
+	const int64_t i = g * CW_WS + lane;
+	const bool valid = i < h.n_hits;
+	const u32 c0 = valid ? h.cigar_off[i] : 0u, c1 = valid ? h.cigar_off[i + 1] : 0u;
+	const int32_t p0 = valid ? h.pos[i] : 0;
+	const u32 f0 = cw_shfl(c0, 0), f1 = cw_shfl(c1, 0);
+	u32 nxt = f0 + lane < f1 ? h.cigar[f0 + lane] : 0u;
+	for(int j = 0; j < CW_WS; j++)
+	{
+		const u32 jc0 = cw_shfl(c0, j), jc1 = cw_shfl(c1, j);
+		int32_t p = cw_shfl(p0, j);
+		u32 c = nxt;
+		if(j + 1 < CW_WS)
+		{
+			const u32 n0 = cw_shfl(c0, j + 1), n1 = cw_shfl(c1, j + 1);
+			nxt = n0 + lane < n1 ? h.cigar[n0 + lane] : 0u;
+		}
+		begin(j);
+		for(u32 k0 = jc0; k0 < jc1; k0 += CW_WS)
+		{
+			const u32 k = k0 + lane;
+			const bool act = k < jc1;
+			if(k0 != jc0) c = act ? h.cigar[k] : 0u;
+			const u32 op = c & 0xf, len = c >> 4;
+			const int adv = (act && ((0x3C1A7 >> (op << 1)) & 2)) ? (int)len : 0;      // bam_cigar_type: consumes reference
+			int tot;
+			const int32_t pe = p + cw_excl_scan(adv, lane, &tot) + adv;
+			chunk(j, k0 == jc0, k, jc0, jc1, act, op, len, pe);
+			p += tot;
+		}
+		end(j, p);
+	}
+}
 
 KERNEL k_hit_cigar_warp(hits_dev h, const int32_t *b_lpos, const int64_t *cov_base, u32 *border,
 		int32_t *spl, int32_t *hit_nspl, const int32_t *hit_bundle, int32_t *n_spliced, int *err, const uint16_t *skip)
 {
-	SHARED int s_b[CW_WARPS], s_n[CW_WARPS];
 	const int lane = threadIdx.x % CW_WS, warp = threadIdx.x / CW_WS;
 	const int wpb = blockDim.x / CW_WS;
 	const u32 lt = (1u << lane) - 1u;
-	for(int64_t base = (int64_t)blockIdx.x * wpb; base < h.n_hits; base += (int64_t)gridDim.x * wpb)
+	const int64_t n_groups = (h.n_hits + CW_WS - 1) / CW_WS;
+	for(int64_t g = (int64_t)blockIdx.x * wpb + warp; g < n_groups; g += (int64_t)gridDim.x * wpb)
 	{
-		const int64_t i = base + warp;
-		int b = -1, ns = 0;
-		if(i < h.n_hits)
-		{
-			b = hit_bundle[i];
-			const int64_t wb = cov_base[b] - (int64_t)b_lpos[b];
-			const u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
-			const u32 sk = skip ? skip[i] : 0u;
-			int32_t p = h.pos[i];
-			int z = 0;
-			int32_t *out = spl + c0;
-			for(u32 k0 = c0; k0 < c1; k0 += CW_WS)
+		const int64_t i = g * CW_WS + lane;
+		const bool valid = i < h.n_hits;
+		const int b = valid ? hit_bundle[i] : -1;
+		const int64_t wb = valid ? cov_base[b] - (int64_t)b_lpos[b] : 0;
+		const u32 sk = (valid && skip) ? skip[i] : 0u;
+		const int32_t rp = valid ? h.rpos[i] : 0;
+		int my_ns = 0;
+		int32_t my_p = 0;
+		int64_t jwb = 0;
+		u32 jsk = 0;
+		int z = 0, ns = 0;
+		cw_walk(h, g, lane,
+			[&](int j) { jwb = cw_shfl(wb, j); jsk = cw_shfl(sk, j); z = 0; ns = 0; },
+			[&](int, bool, u32 k, u32 jc0, u32 jc1, bool act, u32 op, u32 len, int32_t pe)
 			{
-				const u32 k = k0 + lane;
-				const bool act = k < c1;
-				const u32 c = act ? h.cigar[k] : 0u;
-				const u32 op = c & 0xf, len = c >> 4;
-				const int adv = (act && ((0x3C1A7 >> (op << 1)) & 2)) ? (int)len : 0;      // bam_cigar_type: consumes reference
-				int tot;
-				const int32_t pe = p + cw_excl_scan(adv, lane, &tot) + adv;                  // position after this operation
 				const bool isM = act && op == 0;                                           // BAM_CMATCH
 				const u32 mM = cw_ballot(isM);
 				const int zi = z + __popc(mM & lt);
-				if(isM && len > 0 && !(zi < 16 && ((sk >> zi) & 1u)))
+				if(isM && len > 0 && !(zi < 16 && ((jsk >> zi) & 1u)))
 				{
-					border_set(border, wb + pe - (int32_t)len);
-					border_set(border, wb + pe);
+					border_set(border, jwb + pe - (int32_t)len);
+					border_set(border, jwb + pe);
 				}
-				const bool isN = act && op == 3 && k != c0 && k != c1 - 1;                 // BAM_CREF_SKIP, not first / last op
+				const bool isN = act && op == 3 && k != jc0 && k != jc1 - 1;               // BAM_CREF_SKIP, not first / last op
 				const u32 mN = cw_ballot(isN);
 				if(isN)
 				{
-					const int o = ns + 2 * __popc(mN & lt);
-					out[o] = pe - (int32_t)len;
-					out[o + 1] = pe;
+					int32_t *out = spl + jc0 + ns + 2 * __popc(mN & lt);
+					out[0] = pe - (int32_t)len;
+					out[1] = pe;
 				}
-				p += tot; z += __popc(mM); ns += 2 * __popc(mN);
-			}
-			if(lane == 0)
-			{
-				if(p != h.rpos[i]) atomicAdd(&err[ERR_RPOS], 1);
-				hit_nspl[i] = ns;
-			}
-		}
-		if(lane == 0) { s_b[warp] = b; s_n[warp] = ns > 0 ? 1 : 0; }
-		BLOCK_SYNC();
-		if(threadIdx.x == 0)
+				z += __popc(mM); ns += 2 * __popc(mN);
+			},
+			[&](int j, int32_t p) { if(lane == j) { my_ns = ns; my_p = p; } });
+		if(valid)
 		{
-			for(int w = 0; w < wpb; )
-			{
-				int e = w, cnt = 0;
-				while(e < wpb && s_b[e] == s_b[w]) { cnt += s_n[e]; e++; }
-				if(s_b[w] >= 0 && cnt > 0) atomicAdd(&n_spliced[s_b[w]], cnt);
-				w = e;
-			}
+			if(my_p != rp) atomicAdd(&err[ERR_RPOS], 1);
+			hit_nspl[i] = my_ns;
 		}
-		BLOCK_SYNC();
+#ifndef AGPU_EMU
+		// the lanes hold consecutive hits: one atomic per (warp, bundle) instead of one per spliced hit
+		const unsigned peers = __match_any_sync(0xffffffffu, (valid && my_ns > 0) ? b : -1);
+		if(valid && my_ns > 0 && lane == __ffs((int)peers) - 1) atomicAdd(&n_spliced[b], __popc(peers));
+#else
+		if(valid && my_ns > 0) atomicAdd(&n_spliced[b], 1);
+#endif
 	}
 }
 
-// The +1 / -1 of the match blocks, aggregated per CTA: a CTA takes CA_CHUNK consecutive hits -- reads of one locus, whose blocks
-// start and end at the same few exon boundaries -- counts their borders in a shared-memory table keyed by border rank and adds
-// every distinct border to diffc[] once (an entry that finds no slot within CA_PROBES goes to diffc[] directly).
-#define CA_LOG_SLOTS 12
-#define CA_SLOTS (1 << CA_LOG_SLOTS)
-#define CA_PROBES 16
-#define CA_CHUNK 256
-#define CA_EMPTY 0xffffffffu
-DEV void ca_add(u32 *s_key, int *s_cnt, int32_t *diffc, int64_t rank, int d)
-{
-	const u32 key = (u32)rank;
-	u32 x = (key * 2654435761u) >> (32 - CA_LOG_SLOTS);
-	for(int probe = 0; probe < CA_PROBES; probe++)
-	{
-		const u32 cur = atomicCAS(&s_key[x], CA_EMPTY, key);
-		if(cur == CA_EMPTY || cur == key) { atomicAdd(&s_cnt[x], d); return; }
-		x = (x + 1) & (CA_SLOTS - 1);
-	}
-	atomicAdd(&diffc[rank], d);
-}
 KERNEL k_cov_add_warp(hits_dev h, const int32_t *hit_bundle, const int32_t *b_lpos, const int64_t *cov_base, const u32 *border,
 		const u32 *wrank, int32_t *diffc, const uint16_t *skip)
 {
-	SHARED u32 s_key[CA_SLOTS];
-	SHARED int s_cnt[CA_SLOTS];
 	const int lane = threadIdx.x % CW_WS, warp = threadIdx.x / CW_WS;
 	const int wpb = blockDim.x / CW_WS;
 	const u32 lt = (1u << lane) - 1u;
-	for(int x = threadIdx.x; x < CA_SLOTS; x += blockDim.x) { s_key[x] = CA_EMPTY; s_cnt[x] = 0; }
-	BLOCK_SYNC();
-	for(int64_t base = (int64_t)blockIdx.x * CA_CHUNK; base < h.n_hits; base += (int64_t)gridDim.x * CA_CHUNK)
+	const int64_t n_groups = (h.n_hits + CW_WS - 1) / CW_WS;
+	for(int64_t g = (int64_t)blockIdx.x * wpb + warp; g < n_groups; g += (int64_t)gridDim.x * wpb)
 	{
-		const int64_t end = base + CA_CHUNK < h.n_hits ? base + CA_CHUNK : h.n_hits;
-		for(int64_t i = base + warp; i < end; i += wpb)
-		{
-			const int b = hit_bundle[i];
-			const int64_t wb = cov_base[b] - (int64_t)b_lpos[b];
-			const u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
-			const u32 sk = skip ? skip[i] : 0u;
-			int32_t p = h.pos[i];
-			int z = 0;
-			for(u32 k0 = c0; k0 < c1; k0 += CW_WS)
+		const int64_t i = g * CW_WS + lane;
+		const bool valid = i < h.n_hits;
+		const int b = valid ? hit_bundle[i] : -1;
+		const int64_t wb = valid ? cov_base[b] - (int64_t)b_lpos[b] : 0;
+		const u32 sk = (valid && skip) ? skip[i] : 0u;
+		int64_t jwb = 0;
+		u32 jsk = 0;
+		int z = 0;
+		cw_walk(h, g, lane,
+			[&](int j) { jwb = cw_shfl(wb, j); jsk = cw_shfl(sk, j); z = 0; },
+			[&](int, bool, u32, u32, u32, bool act, u32 op, u32 len, int32_t pe)
 			{
-				const u32 k = k0 + lane;
-				const bool act = k < c1;
-				const u32 c = act ? h.cigar[k] : 0u;
-				const u32 op = c & 0xf, len = c >> 4;
-				const int adv = (act && ((0x3C1A7 >> (op << 1)) & 2)) ? (int)len : 0;
-				int tot;
-				const int32_t pe = p + cw_excl_scan(adv, lane, &tot) + adv;
 				const bool isM = act && op == 0;
 				const u32 mM = cw_ballot(isM);
 				const int zi = z + __popc(mM & lt);
-				if(isM && len > 0 && !(zi < 16 && ((sk >> zi) & 1u)))
+				if(isM && len > 0 && !(zi < 16 && ((jsk >> zi) & 1u)))
 				{
-					ca_add(s_key, s_cnt, diffc, border_rank(border, wrank, wb + pe - (int32_t)len), 1);
-					ca_add(s_key, s_cnt, diffc, border_rank(border, wrank, wb + pe), -1);
+					atomicAdd(&diffc[border_rank(border, wrank, jwb + pe - (int32_t)len)], 1);
+					atomicAdd(&diffc[border_rank(border, wrank, jwb + pe)], -1);
 				}
-				p += tot; z += __popc(mM);
-			}
-		}
-		BLOCK_SYNC();
-		for(int x = threadIdx.x; x < CA_SLOTS; x += blockDim.x)
-		{
-			const u32 key = s_key[x];
-			if(key == CA_EMPTY) continue;
-			const int d = s_cnt[x];
-			if(d != 0) atomicAdd(&diffc[key], d);
-			s_key[x] = CA_EMPTY; s_cnt[x] = 0;
-		}
-		BLOCK_SYNC();
+				z += __popc(mM);
+			},
+			[&](int, int32_t) {});
 	}
 }
 
-// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64), one warp per hit
+// hit.rpos = pos + bam_cigar2rlen (rnacore/hit.cc:64)
 KERNEL k_hit_rpos_warp(hits_dev h, int32_t *rpos)
 {
 	const int lane = threadIdx.x % CW_WS, warp = threadIdx.x / CW_WS;
 	const int wpb = blockDim.x / CW_WS;
-	for(int64_t i = (int64_t)blockIdx.x * wpb + warp; i < h.n_hits; i += (int64_t)gridDim.x * wpb)
+	const int64_t n_groups = (h.n_hits + CW_WS - 1) / CW_WS;
+	for(int64_t g = (int64_t)blockIdx.x * wpb + warp; g < n_groups; g += (int64_t)gridDim.x * wpb)
 	{
-		const u32 c0 = h.cigar_off[i], c1 = h.cigar_off[i + 1];
-		int32_t p = h.pos[i];
-		for(u32 k0 = c0; k0 < c1; k0 += CW_WS)
-		{
-			const u32 k = k0 + lane;
-			const u32 c = k < c1 ? h.cigar[k] : 0u;
-			const int adv = (k < c1 && ((0x3C1A7 >> ((c & 0xf) << 1)) & 2)) ? (int)(c >> 4) : 0;
-			int tot;
-			(void)cw_excl_scan(adv, lane, &tot);
-			p += tot;
-		}
-		if(lane == 0) rpos[i] = p;
+		const int64_t i = g * CW_WS + lane;
+		int32_t my_p = 0;
+		cw_walk(h, g, lane, [&](int) {}, [&](int, bool, u32, u32, u32, bool, u32, u32, int32_t) {},
+			[&](int j, int32_t p) { if(lane == j) my_p = p; });
+		if(i < h.n_hits) rpos[i] = my_p;
 	}
 }
 
