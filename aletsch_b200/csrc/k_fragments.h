@@ -21,6 +21,9 @@
 //                   (u's candidate list empty) or by the smaller index (mutual).  Every other hit that has or is a
 //                   candidate is marked (bit 31 of want[]) together with all its candidates; the marked hits are
 //                   exactly the members of the components that are not such pairs.
+//                   A bundle in which some mate position holds more than run_max (1024, AGPU_PAIR_RUN_MAX) hits is marked as a
+//                   whole, so a hit never walks a longer run: R reads at one start position cost R table operations there,
+//                   not R^2 comparisons.
 //   k_pairx_*     : the marked hits (multi-mapped query names inside one bundle; none in most batches) go through
 //                   the exact greedy per (bundle, qname) group: compact list, open-addressing table sized for the
 //                   list, member lists sorted by hit index, pair_group.  Unmarked hits never appear in a marked
@@ -82,7 +85,10 @@ DEV int64_t sampled_lower_bound(const int32_t *pos, const int32_t *pos64, int64_
 	return lo + lower_bound_idx(pos + lo, (int)(hi - lo), m);
 }
 
-KERNEL k_pair_probe(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle, int32_t *cand, u32 *want, int *err)
+// run_max: a run of more than run_max hits at the mate position is not walked (a walk per hit that points there would make a
+// bundle with R reads at one start position cost R^2, which the reference's bucketed search does not); the hit's whole BUNDLE
+// then goes through the exact path, whose table finds a name in O(1) -- components never leave a bundle, so that is closed.
+KERNEL k_pair_probe(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle, int32_t *cand, u32 *want, int32_t *bundle_exact, int run_max, int *err)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
@@ -94,8 +100,11 @@ KERNEL k_pair_probe(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle,
 	const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
 	int n = 0;
 	int64_t first = -1;
-	for(int64_t u = sampled_lower_bound(h.pos, pos64, h0, h1, m); u < h1 && h.pos[u] == m; u++)
+	const int64_t lo = sampled_lower_bound(h.pos, pos64, h0, h1, m);
+	for(int64_t u = lo; u < h1 && h.pos[u] == m; u++)
 	{
+		// (the want[] counts left behind do not matter: no hit of the bundle takes the direct path)
+		if(u - lo >= run_max) { bundle_exact[b] = 1; cand[i] = PC_MULTI; return; }
 		const u32 iu = (u32)h.isize[u];
 		const u64 ku = h.qid[u];                               // loaded next to isize, not after it
 		if(u == i || iu + is != 0u || ku != key) continue;
@@ -113,13 +122,15 @@ DEV void pair_mark(u32 *want, int64_t x, int32_t *ctl)
 }
 
 // all: every hit that has a candidate goes to the exact path (test hook, AGPU_PAIR_EXACT=1)
-KERNEL k_pair_decide(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle, const int32_t *cand, u32 *want, int32_t *mate, int32_t *ctl, int all)
+KERNEL k_pair_decide(hits_dev h, const int32_t *pos64, const int32_t *hit_bundle, const int32_t *cand, u32 *want, const int32_t *bundle_exact,
+		int32_t *mate, int32_t *ctl, int all)
 {
 	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= h.n_hits) return;
 	const int32_t c = cand[i];
-	if(c == PC_NONE) return;
 	const int b = hit_bundle[i];
+	if(bundle_exact[b]) { pair_mark(want, i, ctl); return; }      // every hit of such a bundle, candidates or not
+	if(c == PC_NONE) return;
 	const int64_t h0 = h.bundle_hit_off[b], h1 = h.bundle_hit_off[b + 1];
 	const int32_t li = (int32_t)(i - h0);
 	if(c >= 0 && !all)

@@ -84,7 +84,8 @@ void agpu_default_params(agpu_params *p);
 
 /* Packed input: NB bundles, hits concatenated bundle by bundle in BAM order.
  * Packing contract (what meta/generator.cc:77-179 + bundle_base::add_hit guarantee):
- *   - within a bundle pos[] is non-decreasing;
+ *   - within a bundle pos[] is non-decreasing (mate pairing relies on it: a hit's mate candidates are found by bisecting the
+ *     bundle's pos[] for mpos; agpu_batch_fragments only runs after agpu_batch_evidence has verified the order);
  *   - no hit equals its predecessor in (pos, rpos)        (rnacore/bundle_base.cc:75-82);
  *   - rpos[i] == pos[i] + bam_cigar2rlen(cigar of i)      (rnacore/hit.cc:64);
  *   - strand[] / xs[] hold '+', '-' or '.'; all hits of a bundle share strand[]

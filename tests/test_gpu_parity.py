@@ -264,6 +264,19 @@ def test_pairing_exact_path_at_scale():
               "print('exact path ok', stats['fragments'])\n", "exact path ok")
 
 
+def test_pairing_long_runs_take_exact_path():
+    """AGPU_PAIR_RUN_MAX=2: a bundle in which some mate position holds more than two hits goes through the exact greedy as a
+    whole (the bound that keeps R reads at one start position from costing R^2 candidate walks; 1024 by default)."""
+    run_child({"AGPU_PAIR_RUN_MAX": "2"},
+              "test_fuzz.run_pair_seeds(ctx, checkers, range(6))\n"
+              "test_fuzz.run_seeds(ctx, checkers, range(6))\n"
+              "batch, lt = parity.make_batch(H.SYNTH_PAIRED, 60000, seed=20260113)\n"
+              "gp, op = parity.params_pair(lt)\n"
+              "stats = {}; bad = parity.compare_full(ctx, batch, chk, gp, op, stats)\n"
+              "assert not bad, bad[:3]\n"
+              "print('long runs ok', stats['fragments'])\n", "long runs ok")
+
+
 def test_warp_cigar_walk_on_short_reads():
     """AGPU_WARP_MIN_OPS=0 runs the warp-per-hit CIGAR walks (the long-read path: k_hit_cigar_warp, k_cov_add_warp,
     k_hit_rpos_warp) on every batch: adversarial CIGARs of 1-9 operations, the synthetic paired-end batch through the compact
