@@ -766,14 +766,6 @@ static int chainset_finish(agpu_ctx *ctx, agpu_batch *b, chainset_state &cs, int
 static int flag_rank(agpu_ctx *ctx, const int32_t *v, int64_t n, dbuf<int32_t> &tile_cnt, dbuf<int64_t> &tile_off, dbuf<int64_t> &rank, int64_t *total);
 static int value_scan(agpu_ctx *ctx, const int32_t *v, int64_t n, dbuf<int32_t> &tile_sum, dbuf<int64_t> &tile_off, dbuf<int64_t> &out, int64_t *total);
 
-// device-wide exclusive scan of per-tile int32 sums (at most a few 10^4 tiles): one CTA
-static int tile_scan(agpu_ctx *ctx, dbuf<int32_t> &tile_sum, dbuf<int64_t> &tile_off, int64_t nt)
-{
-	TRY(tile_off.alloc(ctx, nt + 2));
-	TRY(lb_scan32(ctx, tile_sum.p, nt, 0, tile_off.p));
-	return AGPU_OK;
-}
-
 // border bitmap + hits (+ the stretches of update_bridges) -> ranked borders, differences, coverage, segments
 static int coverage_scan(agpu_ctx *ctx, agpu_batch *b)
 {

@@ -426,87 +426,8 @@ KERNEL k_bridge_job_fill(int64_t nb, const int64_t *clu_off, const uint8_t *b_st
 	for(int pi = 0; pi < br.n_piers[b]; pi++) { pier_job[o] = clu_off[b] + pi; pier_bundle[o] = (int32_t)b; o++; }
 }
 
-// ---- B3: bottleneck top-K DP, one thread per (pier group, strand pass) (dynamic_programming :484-530)
-KERNEL k_bridge_dp(int64_t n_jobs, const int64_t *dp_job, const int32_t *dp_bundle, const int64_t *clu_off, graph_dev g, const uint8_t *b_strand,
-		bridge_dev br)
-{
-	int64_t ji = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if(ji >= n_jobs) return;
-	int64_t job = dp_job[ji];
-	int64_t slot = job >> 1;
-	int pass = (int)(job & 1);
-	int b = dp_bundle[ji];
-	sgraph sg = sgraph_of(g, b_strand, b);
-	int strand = pass_strand(sg.strand, pass);
-	const int K = br.K, D = br.D, W = D + 3;
-	int k1 = br.g_k1[slot], k2 = br.g_k2[slot];
-	int nrow = k2 - k1 + 1;
-	int64_t row0 = br.g_row_off[slot] + (int64_t)pass * nrow;
-	const int64_t poff = (int64_t)pass * br.maxin[b] * K;
-	int32_t *cand = br.cand + (br.g_cand_off[slot] + poff) * W;
-	int32_t *cidx = br.cand_idx + br.g_cand_off[slot] + poff;
-	// table[k1]: one entry, stack of D times 999999, length of the vertex, no trace
-	br.t_cnt[row0] = 1;
-	for(int d = 0; d < D; d++) br.t_stack[row0 * K * D + d] = 999999;
-	br.t_len[row0 * K] = sg.gv.v_r[k1] - sg.gv.v_l[k1];
-	br.t_tr1[row0 * K] = -1; br.t_tr2[row0 * K] = -1;
-	for(int k = k1 + 1; k <= k2; k++)
-	{
-		int64_t row = row0 + (k - k1);
-		int32_t len = sg.gv.v_r[k] - sg.gv.v_l[k];
-		int nc = 0;
-		// in-edges in (source, target) order; the pseudo edge from k - 1, if any, has the largest source
-		int lo = sg.in_off[k], hi = sg.in_off[k + 1];
-		bool pseudo = pseudo_edge(sg, k - 1);
-		for(int x = lo; x < hi + (pseudo ? 1 : 0); x++)
-		{
-			int j, w, s;
-			if(x < hi) { int e = sg.in_eid[x]; j = sg.in_src[x]; s = sg.e_strand[e]; w = (int)sg.e_w[e]; }
-			else { j = k - 1; s = 0; w = 0; }            // (int)0.5
-			if(s != 0 && s != strand) continue;
-			if(j < k1) continue;
-			int64_t jr = row0 + (j - k1);
-			int nj = br.t_cnt[jr];
-			for(int i = 0; i < nj; i++)
-			{
-				int32_t *ce = cand + (int64_t)nc * W;
-				const int32_t *v = br.t_stack + (jr * K + i) * D;
-				// update_stack (:532-546)
-				for(int q = 0; q < D; q++) ce[q] = 0;
-				for(int a = 0, q = 0; a < D && q < D; a++, q++)
-				{
-					if(a == q && v[a] > w)
-					{
-						ce[q] = w;
-						q++;
-						if(q >= D) break;
-					}
-					ce[q] = v[a];
-				}
-				ce[D] = br.t_len[jr * K + i] + len;
-				ce[D + 1] = j;
-				ce[D + 2] = i;
-				cidx[nc] = nc;
-				nc++;
-			}
-		}
-		entry_less less;
-		less.cand = cand; less.D = D; less.W = W;
-		std_sort_handles(cidx, nc, less);
-		int keep = nc > K ? K : nc;
-		br.t_cnt[row] = keep;
-		for(int i = 0; i < keep; i++)
-		{
-			const int32_t *ce = cand + (int64_t)cidx[i] * W;
-			for(int d = 0; d < D; d++) br.t_stack[(row * K + i) * D + d] = ce[d];
-			br.t_len[row * K + i] = ce[D];
-			br.t_tr1[row * K + i] = ce[D + 1];
-			br.t_tr2[row * K + i] = ce[D + 2];
-		}
-	}
-}
-
-// ---- B3 (device build): the same DP with one WARP per (pier group, strand pass).  Per vertex the warp's lanes take the
+// ---- B3: bottleneck top-K DP (dynamic_programming, bridge/bridge_solver.cc:484-530 with update_stack :532-546), one WARP per
+// (pier group, strand pass).  Per vertex the warp's lanes take the
 // in-edges (coalesced reads of the CSR row), a warp scan places every edge's candidates, the lanes then build the candidates
 // -- update_stack of one predecessor entry each -- into the warp's shared-memory slice, and rank them by counting under
 // entry_compare (rank = number of smaller candidates + number of equal ones generated earlier: the stable order).  std::sort of

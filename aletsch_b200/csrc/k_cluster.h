@@ -334,48 +334,6 @@ KERNEL k_group_leaders(int64_t n_frg, const int32_t *f_bundle, const int64_t *fr
 #endif
 }
 
-// generic device-wide exclusive scan of int32 values into int64 (tile sums + single-CTA scan + apply)
-KERNEL k_val_tile_sum(const int32_t *v, int64_t n, int64_t n_tiles, int32_t *tile_sum)
-{
-	SHARED int s;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		if(threadIdx.x == 0) s = 0;
-		BLOCK_SYNC();
-		int acc = 0;
-		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
-		{
-			int64_t gi = t * SCAN_TILE + i;
-			if(gi < n) acc += v[gi];
-		}
-		atomicAdd(&s, acc);
-		BLOCK_SYNC();
-		if(threadIdx.x == 0) tile_sum[t] = s;
-		BLOCK_SYNC();
-	}
-}
-
-KERNEL k_val_tile_scan(const int32_t *v, int64_t n, int64_t n_tiles, const int64_t *tile_off, int64_t *out)
-{
-	SHARED int f[SCAN_TILE];
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
-		{
-			int64_t gi = t * SCAN_TILE + i;
-			f[i] = gi < n ? v[gi] : 0;
-		}
-		BLOCK_SYNC();
-		block_excl_scan(f, SCAN_TILE);
-		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
-		{
-			int64_t gi = t * SCAN_TILE + i;
-			if(gi <= n) out[gi] = tile_off[t] + f[i];
-		}
-		BLOCK_SYNC();
-	}
-}
-
 struct part_ctx
 {
 	u64 *el;                     // elements of the group: key of the current level in the high word, fragment in the low word

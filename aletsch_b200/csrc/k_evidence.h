@@ -135,92 +135,8 @@ KERNEL k_bundle_finish(hits_dev h, int library_type, const int32_t *b_lpos, cons
 	b_span[b] = (span + COV_ALIGN - 1) / COV_ALIGN * COV_ALIGN;
 }
 
-// ---- generic single-CTA exclusive scan of int64 (NB-sized arrays); out[n] = total
-KERNEL k_scan_i64(const int64_t *in, int64_t *out, int n)
-{
-	SHARED int64_t part[SCAN1_MAX];
-	int nt = blockDim.x, t = threadIdx.x;
-	int chunk = (n + nt - 1) / nt;
-	int lo = t * chunk, hi = lo + chunk;
-	if(lo > n) lo = n;
-	if(hi > n) hi = n;
-	int64_t s = 0;
-	for(int i = lo; i < hi; i++) s += in[i];
-	part[t] = s;
-	BLOCK_SYNC();
-	if(t == 0)
-	{
-		int64_t run = 0;
-		for(int k = 0; k < nt; k++) { int64_t v = part[k]; part[k] = run; run += v; }
-		out[n] = run;
-	}
-	BLOCK_SYNC();
-	int64_t run = part[t];
-	for(int i = lo; i < hi; i++) { int64_t v = in[i]; out[i] = run; run += v; }
-}
-
 // ---- device-wide exclusive scan of int64: tile sums, single-CTA scan of the sums, per-tile apply
 #define SCAN64_TILE 2048
-KERNEL k_i64_tile_sum(const int64_t *in, int64_t n, int64_t n_tiles, int64_t *tile_sum)
-{
-	SHARED unsigned long long s;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		if(threadIdx.x == 0) s = 0;
-		BLOCK_SYNC();
-		unsigned long long acc = 0;
-		for(int i = threadIdx.x; i < SCAN64_TILE; i += blockDim.x)
-		{
-			int64_t g = t * SCAN64_TILE + i;
-			if(g < n) acc += (unsigned long long)in[g];
-		}
-		atomicAdd(&s, acc);
-		BLOCK_SYNC();
-		if(threadIdx.x == 0) tile_sum[t] = (int64_t)s;
-		BLOCK_SYNC();
-	}
-}
-
-KERNEL k_i64_tile_apply(const int64_t *in, int64_t n, int64_t n_tiles, const int64_t *tile_off, int64_t *out)
-{
-	SHARED int64_t f[SCAN64_TILE];
-	SHARED int64_t part[SCAN1_MAX];
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		for(int i = threadIdx.x; i < SCAN64_TILE; i += blockDim.x)
-		{
-			int64_t g = t * SCAN64_TILE + i;
-			f[i] = g < n ? in[g] : 0;
-		}
-		BLOCK_SYNC();
-		int nt = blockDim.x, th = threadIdx.x;
-		int chunk = (SCAN64_TILE + nt - 1) / nt;
-		int lo = th * chunk, hi = lo + chunk;
-		if(lo > SCAN64_TILE) lo = SCAN64_TILE;
-		if(hi > SCAN64_TILE) hi = SCAN64_TILE;
-		int64_t sm = 0;
-		for(int i = lo; i < hi; i++) sm += f[i];
-		part[th] = sm;
-		BLOCK_SYNC();
-		if(th == 0)
-		{
-			int64_t run = tile_off[t];
-			for(int k = 0; k < nt; k++) { int64_t v = part[k]; part[k] = run; run += v; }
-		}
-		BLOCK_SYNC();
-		int64_t run = part[th];
-		for(int i = lo; i < hi; i++) { int64_t v = f[i]; f[i] = run; run += v; }
-		BLOCK_SYNC();
-		for(int i = threadIdx.x; i < SCAN64_TILE; i += blockDim.x)
-		{
-			int64_t g = t * SCAN64_TILE + i;
-			if(g < n) out[g] = f[i];
-		}
-		if(t == n_tiles - 1 && threadIdx.x == 0) out[n] = tile_off[n_tiles];
-		BLOCK_SYNC();
-	}
-}
-
 // hash of one intron chain (length + coordinates)
 HD u64 chain_hash(const int32_t *v, int n)
 {
@@ -548,30 +464,6 @@ KERNEL k_gather_off(int64_t n, const int64_t *idx, const u32 *src, int64_t *out)
 	out[i] = (int64_t)src[idx[i]];
 }
 
-// single CTA: exclusive scan of int32 array of length n into int64 out (out[n] = total)
-KERNEL k_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n)
-{
-	SHARED int64_t part[SCAN1_MAX];
-	int nt = blockDim.x, t = threadIdx.x;
-	int64_t chunk = (n + nt - 1) / nt;
-	int64_t lo = t * chunk, hi = lo + chunk;
-	if(lo > n) lo = n;
-	if(hi > n) hi = n;
-	int64_t s = 0;
-	for(int64_t i = lo; i < hi; i++) s += in[i];
-	part[t] = s;
-	BLOCK_SYNC();
-	if(t == 0)
-	{
-		int64_t run = 0;
-		for(int k = 0; k < nt; k++) { int64_t v = part[k]; part[k] = run; run += v; }
-		out[n] = run;
-	}
-	BLOCK_SYNC();
-	int64_t run = part[t];
-	for(int64_t i = lo; i < hi; i++) { int64_t v = in[i]; out[i] = run; run += v; }
-}
-
 // ---- coverage map (bundle_base::mmap, a Boost.ICL split_interval_map) on BORDER-COMPACTED coordinates
 //
 // split_interval_map semantics (rnacore/interval_map.h:31): every inserted interval end stays a segment border for
@@ -582,49 +474,6 @@ KERNEL k_scan_i32_to_i64(const int32_t *in, int64_t *out, int64_t n)
 //   diffc[NB]      difference array indexed by border rank;   posc[NB] genomic coordinate of every border
 // A bundle's differences sum to 0, so ONE device-wide prefix sum over diffc yields every bundle's coverage, and one
 // device-wide rank of (coverage > 0) compacts the segments: seg i = (posc[i], posc[i + 1], cov[i]).
-
-// tile sums of the border popcounts
-KERNEL k_bord_tile_sum(const u32 *border, int64_t n_words, int64_t n_tiles, int32_t *tile_sum)
-{
-	SHARED int s;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		if(threadIdx.x == 0) s = 0;
-		BLOCK_SYNC();
-		int acc = 0;
-		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
-		{
-			int64_t w = t * CTILE + i;
-			if(w < n_words) acc += __popc(border[w]);
-		}
-		if(acc) atomicAdd(&s, acc);
-		BLOCK_SYNC();
-		if(threadIdx.x == 0) tile_sum[t] = s;
-		BLOCK_SYNC();
-	}
-}
-
-// wrank[w] = number of borders before word w (wrank[n_words] = total)
-KERNEL k_bord_tile_rank(const u32 *border, int64_t n_words, int64_t n_tiles, const int64_t *tile_off, u32 *wrank)
-{
-	SHARED int f[CTILE];
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
-		{
-			int64_t w = t * CTILE + i;
-			f[i] = w < n_words ? __popc(border[w]) : 0;
-		}
-		BLOCK_SYNC();
-		block_excl_scan(f, CTILE);
-		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
-		{
-			int64_t w = t * CTILE + i;
-			if(w <= n_words) wrank[w] = (u32)(tile_off[t] + f[i]);
-		}
-		BLOCK_SYNC();
-	}
-}
 
 // rank of global window position g among the borders (g itself must be a border)
 DEV int64_t border_rank(const u32 *border, const u32 *wrank, int64_t g)
@@ -722,104 +571,6 @@ KERNEL k_cov_add_extra(int64_t n, const int64_t *ex_s, const int64_t *ex_e, cons
 	if(i >= n) return;
 	atomicAdd(&diffc[border_rank(border, wrank, ex_s[i])], 1);
 	atomicAdd(&diffc[border_rank(border, wrank, ex_e[i])], -1);
-}
-
-// tile sums of the differences
-KERNEL k_covc_tile_sum(const int32_t *diffc, int64_t n, int64_t n_tiles, int32_t *tile_sum)
-{
-	SHARED int s;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		if(threadIdx.x == 0) s = 0;
-		BLOCK_SYNC();
-		int acc = 0;
-		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
-		{
-			int64_t g = t * CTILE + i;
-			if(g < n) acc += diffc[g];
-		}
-		if(acc) atomicAdd(&s, acc);
-		BLOCK_SYNC();
-		if(threadIdx.x == 0) tile_sum[t] = s;
-		BLOCK_SYNC();
-	}
-}
-
-// cov[i] = coverage right of border i (inclusive prefix sum, written in place of the differences is NOT done: the
-// differences stay, update_bridges adds to them); tile_cnt[t] = borders of the tile that open a segment (cov > 0)
-KERNEL k_covc_tile_cover(const int32_t *diffc, int64_t n, int64_t n_tiles, const int64_t *tile_pre, int32_t *cov, int32_t *tile_cnt)
-{
-	SHARED int f[CTILE];
-	SHARED int s;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		if(threadIdx.x == 0) s = 0;
-		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
-		{
-			int64_t g = t * CTILE + i;
-			f[i] = g < n ? diffc[g] : 0;
-		}
-		BLOCK_SYNC();
-		block_excl_scan(f, CTILE);
-		int acc = 0;
-		int pre = (int)tile_pre[t];
-		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
-		{
-			int64_t g = t * CTILE + i;
-			if(g >= n) continue;
-			int c = pre + f[i] + diffc[g];
-			cov[g] = c;
-			if(c > 0) acc++;
-		}
-		if(acc) atomicAdd(&s, acc);
-		BLOCK_SYNC();
-		if(threadIdx.x == 0) tile_cnt[t] = s;
-		BLOCK_SYNC();
-	}
-}
-
-// segments in order: border i with cov[i] > 0 opens [posc[i], posc[i + 1]) with value cov[i]; also seg_off[b] = number of
-// segments before the first border of bundle b
-// seg_head[o] = 0 if segment o does not touch its predecessor (it opens a run of region::build_join_interval_map), else -1;
-// seg_prod[o] = (r - l) * c in int32 arithmetic (the summand of compute_sum_overlap)
-KERNEL k_covc_emit(const int32_t *cov, const int32_t *posc, int64_t n, int64_t n_tiles, const int64_t *tile_off, int32_t n_bundles,
-		const int64_t *bord_off, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c, int64_t *seg_off, int32_t *seg_head, int32_t *seg_prod)
-{
-	SHARED int f[CTILE + 1];
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		const int64_t g0 = t * CTILE;
-		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
-		{
-			int64_t g = g0 + i;
-			f[i] = (g < n && cov[g] > 0) ? 1 : 0;
-		}
-		BLOCK_SYNC();
-		int tot = block_excl_scan(f, CTILE);
-		if(threadIdx.x == 0) f[CTILE] = tot;
-		BLOCK_SYNC();
-		const int64_t o0 = tile_off[t];
-		for(int i = threadIdx.x; i < CTILE; i += blockDim.x)
-		{
-			int64_t g = g0 + i;
-			if(g >= n || cov[g] <= 0) continue;
-			int64_t o = o0 + f[i];
-			int32_t pl = posc[g], pr = g + 1 < n ? posc[g + 1] : posc[g], c = cov[g];
-			seg_l[o] = pl;
-			seg_r[o] = pr;
-			seg_c[o] = c;
-			// the previous segment ends at this border iff the previous border opened a segment (a bundle's coverage returns
-			// to 0 at its last border, so this never links two bundles)
-			seg_head[o] = (g > 0 && cov[g - 1] > 0) ? -1 : 0;
-			seg_prod[o] = (int32_t)((u32)(pr - pl) * (u32)c);
-		}
-		// bundles whose first border falls into this tile (the last tile also owns rank n)
-		int64_t hi = (t == n_tiles - 1) ? n + 1 : g0 + CTILE;
-		int b0 = lower_bound_idx(bord_off, n_bundles + 1, g0);
-		for(int b = b0 + (int)threadIdx.x; b <= n_bundles && bord_off[b] < hi; b += blockDim.x)
-			seg_off[b] = o0 + f[bord_off[b] - g0];
-		BLOCK_SYNC();
-	}
 }
 
 // heads[k] = index of the k-th run-opening segment (heads[total] = n)

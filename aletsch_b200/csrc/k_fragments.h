@@ -227,49 +227,6 @@ KERNEL k_pairx_resolve(hits_dev h, int64_t n_c, const int64_t *clist, const int3
 	pair_group(h, h0, m, n, mate);
 }
 
-// ---- generic device-wide exclusive scan of 0/1 flags derived from an int array (flag = v[i] >= 0)
-KERNEL k_flag_tile_count(const int32_t *v, int64_t n, int64_t n_tiles, int32_t *tile_cnt)
-{
-	SHARED int s;
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		if(threadIdx.x == 0) s = 0;
-		BLOCK_SYNC();
-		int acc = 0;
-		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
-		{
-			int64_t g = t * SCAN_TILE + i;
-			if(g < n && v[g] >= 0) acc++;
-		}
-		atomicAdd(&s, acc);
-		BLOCK_SYNC();
-		if(threadIdx.x == 0) tile_cnt[t] = s;
-		BLOCK_SYNC();
-	}
-}
-
-// rank[i] = number of flagged elements before i (written for every i, plus rank[n] = total)
-KERNEL k_flag_tile_rank(const int32_t *v, int64_t n, int64_t n_tiles, const int64_t *tile_off, int64_t *rank)
-{
-	SHARED int f[SCAN_TILE];
-	for(int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x)
-	{
-		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
-		{
-			int64_t g = t * SCAN_TILE + i;
-			f[i] = (g < n && v[g] >= 0) ? 1 : 0;
-		}
-		BLOCK_SYNC();
-		block_excl_scan(f, SCAN_TILE);
-		for(int i = threadIdx.x; i < SCAN_TILE; i += blockDim.x)
-		{
-			int64_t g = t * SCAN_TILE + i;
-			if(g <= n) rank[g] = tile_off[t] + f[i];
-		}
-		BLOCK_SYNC();
-	}
-}
-
 KERNEL k_frag_emit(hits_dev h, const int32_t *hit_bundle, const int32_t *mate, const int64_t *rank, int32_t *f_h1, int32_t *f_h2, int32_t *f_type,
 		int32_t *f_bundle)
 {
