@@ -621,8 +621,10 @@ KERNEL k_lb_bord_rank(lb_ctl c, const u32 *border, int64_t n_words, u32 *wrank, 
 //   chain 0: sum of the differences        -> cov[i] = coverage right of border i
 //   chain 1: number of borders with cov > 0 -> position of every segment in the compact list
 //   chain 2: sum of the products (r - l) * c of the tile's segments, int32 wrap-around arithmetic -> seg_psum
-// Outputs as k_covc_emit: seg_l / seg_r / seg_c, seg_head (0 = opens a run, -1 = touches its predecessor), seg_psum[o] = sum of
-// the products of the segments before o (seg_psum[n_seg] = total), seg_off[b] per bundle, *n_seg.
+// Outputs: the segments in order -- border i with cov[i] > 0 opens [posc[i], posc[i + 1]) with value cov[i] -- as seg_l / seg_r /
+// seg_c; seg_head[o] = 0 if segment o does not touch its predecessor (it opens a run of region::build_join_interval_map), else -1;
+// seg_psum[o] = sum of the products (r - l) * c, int32 arithmetic (the summands of compute_sum_overlap), of the segments before o
+// (seg_psum[n_seg] = total); seg_off[b] = number of segments before the first border of bundle b; *n_seg.
 KERNEL k_lb_cov_segments(lb_ctl c, const int32_t *diffc, const int32_t *posc, int64_t n, int32_t n_bundles, const int64_t *bord_off,
 		int32_t *cov, int32_t *seg_l, int32_t *seg_r, int32_t *seg_c, int64_t *seg_off, int32_t *seg_head, int64_t *seg_psum, int64_t *n_seg)
 {

@@ -205,8 +205,6 @@ def algorithmic_bytes(kernel, cnt, n_cigar, n_mblocks, n_splice_pairs):
     if kernel == "k_cov_add":
         # in: pos, cigar_off, bundle id (12 B/hit) + CIGAR ops; per block end a bitmap word, a rank word and a 4-byte RMW
         return Hh * 12 + 4 * n_cigar + 2 * n_mblocks * (4 + 4 + 8)
-    if kernel == "k_covc_emit":
-        return NBD * 8 + 12 * S
     if kernel == "k_pair_probe":
         # per hit: qid (8) + pos, mpos, isize (12) + bundle id (4) in, candidate word (4) out; one want[] counter RMW (8) per mate found
         return Hh * (8 + 12 + 4 + 4) + 2 * F * 8
@@ -522,7 +520,7 @@ def run_ours(args):
             log("[bench] kernel %-26s %9.3f ms/step  (%d launches/step, %.1f%% of kernel time)" %
                 (name, ms / steps, cnt // steps, 100 * ms / max(total_k, 1e-9)))
         # bridged pairs / time of stage 4 + update = the bridging kernels' accumulated time (rank 0's batch)
-        stage4 = ("k_bridge_vertices", "k_piers", "k_cluster_pier", "k_group_cand", "k_bridge_job_counts", "k_bridge_job_fill", "k_bridge_dp",
+        stage4 = ("k_bridge_vertices", "k_piers", "k_cluster_pier", "k_group_cand", "k_bridge_job_counts", "k_bridge_job_fill",
                   "k_bridge_dp_warp", "k_pier_bridges", "k_vote", "k_vote_type1", "k_vote_type2", "k_update", "k_fcst_insert", "k_merge_entries", "k_scatter_handle")
         stage4_ms = sum(ms for name, (ms, cnt) in prof.items() if name.replace("(side)", "") in stage4) / steps
         dom = None
